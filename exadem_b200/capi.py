@@ -1,0 +1,424 @@
+"""ctypes binding of the C ABI declared in include/exadem_b200.h.
+
+This is the Python view of the drop-in boundary (tests, bench.py and examples drive the library through it).
+It holds NO compute: every method forwards to `libexadem_b200.so` (CUDA, sm_100a).  If the shared library is
+missing the import of :class:`Library` raises — there is no CPU fallback on the product path.
+
+The same struct definitions and the same :class:`Engine` wrapper are reused by the test-only oracle binding
+(tests/oracle_binding.py) with the ``orc_`` symbol prefix, so parity tests run identical scripts on both sides.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+NTYPES = 14
+MODE_SPHERE, MODE_POLYHEDRON = 0, 1
+LAW_NONE, LAW_COHESIVE, LAW_DMT = 0, 1, 2
+DRIVER_CYLINDER, DRIVER_SURFACE, DRIVER_BALL, DRIVER_RSHAPE, DRIVER_UNDEFINED = 0, 1, 2, 3, 4
+
+_D = C.POINTER(C.c_double)
+_U64 = C.POINTER(C.c_uint64)
+_U32 = C.POINTER(C.c_uint32)
+
+
+class Config(C.Structure):
+    _fields_ = [("lo", C.c_double * 3), ("hi", C.c_double * 3), ("glo", C.c_double * 3), ("ghi", C.c_double * 3),
+                ("cell_size", C.c_double), ("periodic", C.c_int32 * 3), ("mode", C.c_int32), ("device", C.c_int32),
+                ("rank", C.c_int32), ("nranks", C.c_int32), ("pgrid", C.c_int32 * 3),
+                ("emit_contact_state", C.c_int32), ("reserved", C.c_int32)]
+
+
+F64_FIELDS = ["rx", "ry", "rz", "vx", "vy", "vz", "fx", "fy", "fz", "mass", "homothety", "radius",
+              "qw", "qx", "qy", "qz", "momx", "momy", "momz", "vrotx", "vroty", "vrotz",
+              "arotx", "aroty", "arotz", "inertiax", "inertiay", "inertiaz"]
+
+
+class Particles(C.Structure):
+    _fields_ = ([("n", C.c_uint64)] + [(f, _D) for f in F64_FIELDS] + [("id", _U64), ("type", _U32), ("group", _U32)])
+
+
+class ContactParams(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("kn", "kt", "kr", "mu", "damp_rate", "fc", "dncut", "gamma")]
+
+
+class Driver(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("need_forces", C.c_int32), ("radius", C.c_double), ("axis", C.c_double * 3),
+                ("center", C.c_double * 3), ("offset", C.c_double), ("normal", C.c_double * 3),
+                ("vel", C.c_double * 3), ("vrot", C.c_double * 3), ("shape", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Shape(C.Structure):
+    _fields_ = [("nv", C.c_int32), ("ne", C.c_int32), ("nf", C.c_int32), ("faces_len", C.c_int32),
+                ("vertices", _D), ("edges", C.POINTER(C.c_int32)), ("faces", C.POINTER(C.c_int32)),
+                ("obb", C.c_double * 15), ("radius", C.c_double)]
+
+
+class Interaction(C.Structure):
+    _fields_ = [("id_i", C.c_uint64), ("cell_i", C.c_uint32), ("p_i", C.c_uint16), ("pad_i", C.c_uint16),
+                ("sub_i", C.c_uint32), ("pad_i2", C.c_uint32),
+                ("id_j", C.c_uint64), ("cell_j", C.c_uint32), ("p_j", C.c_uint16), ("pad_j", C.c_uint16),
+                ("sub_j", C.c_uint32), ("pad_j2", C.c_uint32),
+                ("type", C.c_uint16), ("swap", C.c_uint8), ("ghost", C.c_uint8), ("pad_t", C.c_uint32),
+                ("friction", C.c_double * 3), ("moment", C.c_double * 3)]
+
+
+INTERACTION_DTYPE = np.dtype([("id_i", "<u8"), ("cell_i", "<u4"), ("p_i", "<u2"), ("pad_i", "<u2"), ("sub_i", "<u4"),
+                              ("pad_i2", "<u4"), ("id_j", "<u8"), ("cell_j", "<u4"), ("p_j", "<u2"), ("pad_j", "<u2"),
+                              ("sub_j", "<u4"), ("pad_j2", "<u4"), ("type", "<u2"), ("swap", "u1"), ("ghost", "u1"),
+                              ("pad_t", "<u4"), ("friction", "<f8", 3), ("moment", "<f8", 3)])
+assert INTERACTION_DTYPE.itemsize == C.sizeof(Interaction) == 104
+
+
+class Counters(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("interaction_updates", C.c_uint64), ("particle_steps", C.c_uint64),
+                ("rebuilds", C.c_uint64), ("contact_ms", C.c_double), ("gather_ms", C.c_double),
+                ("prolog_ms", C.c_double), ("epilog_ms", C.c_double), ("rebuild_ms", C.c_double),
+                ("ghost_ms", C.c_double), ("contact_launches", C.c_uint64), ("bytes_contact_algorithmic", C.c_uint64)]
+
+
+class EdbError(RuntimeError):
+    pass
+
+
+def repo_root() -> Path:
+    return Path(__file__).resolve().parent.parent
+
+
+def product_library_path() -> Path:
+    return Path(__file__).resolve().parent / "libexadem_b200.so"
+
+
+class Library:
+    """Loads libexadem_b200.so (the CUDA product).  Raises if it is not built — no fallback."""
+
+    prefix = "edb_"
+
+    def __init__(self, path: os.PathLike | None = None):
+        p = Path(path) if path else product_library_path()
+        if not p.exists():
+            raise EdbError(f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a). There is no CPU fallback for the product path.")
+        self.path = p
+        self.dll = C.CDLL(str(p), mode=C.RTLD_GLOBAL)
+
+    def fn(self, name):
+        f = getattr(self.dll, self.prefix + name)
+        f.restype = C.c_int
+        return f
+
+
+def _as(a, ct):
+    return a.ctypes.data_as(ct)
+
+
+class ParticleArrays:
+    """Host SoA mirror of DEMFieldSet (include/exaDEM/fields.h:34-54): one contiguous numpy array per field."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+        for f in F64_FIELDS:
+            setattr(self, f, np.zeros(n, dtype=np.float64))
+        self.mass[:] = 1.0
+        self.homothety[:] = 1.0
+        self.radius[:] = 0.5
+        self.qw[:] = 1.0
+        self.inertiax[:] = 1.0
+        self.inertiay[:] = 1.0
+        self.inertiaz[:] = 1.0
+        self.id = np.arange(n, dtype=np.uint64)
+        self.type = np.zeros(n, dtype=np.uint32)
+        self.group = np.zeros(n, dtype=np.uint32)
+
+    def view(self, fields=None) -> Particles:
+        P = Particles()
+        P.n = self.n
+        for f in F64_FIELDS:
+            if fields is None or f in fields:
+                a = getattr(self, f)
+                assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == (self.n,)
+                setattr(P, f, _as(a, _D))
+        if fields is None or "id" in fields:
+            P.id = _as(self.id, _U64)
+        if fields is None or "type" in fields:
+            P.type = _as(self.type, _U32)
+        if fields is None or "group" in fields:
+            P.group = _as(self.group, _U32)
+        return P
+
+    def copy(self) -> "ParticleArrays":
+        o = ParticleArrays(self.n)
+        for f in F64_FIELDS + ["id", "type", "group"]:
+            setattr(o, f, getattr(self, f).copy())
+        return o
+
+    def vec(self, name) -> np.ndarray:
+        comps = {"r": ("rx", "ry", "rz"), "v": ("vx", "vy", "vz"), "f": ("fx", "fy", "fz"),
+                 "mom": ("momx", "momy", "momz"), "vrot": ("vrotx", "vroty", "vrotz"),
+                 "arot": ("arotx", "aroty", "arotz"), "q": ("qw", "qx", "qy", "qz")}[name]
+        return np.stack([getattr(self, c) for c in comps], axis=1)
+
+
+def make_shape(vertices, edges, faces, obb, radius):
+    """Build a :class:`Shape` (keeps the numpy buffers alive on the returned object)."""
+    v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+    e = np.ascontiguousarray(edges, dtype=np.int32).reshape(-1, 2)
+    stream = []
+    for f in faces:
+        stream.append(len(f))
+        stream.extend(int(x) for x in f)
+    fs = np.asarray(stream, dtype=np.int32)
+    s = Shape()
+    s.nv, s.ne, s.nf, s.faces_len = len(v), len(e), len(faces), len(fs)
+    s.vertices = _as(v, _D)
+    s.edges = _as(e, C.POINTER(C.c_int32))
+    s.faces = _as(fs, C.POINTER(C.c_int32))
+    for k in range(15):
+        s.obb[k] = float(obb[k])
+    s.radius = float(radius)
+    s._keep = (v, e, fs)
+    return s
+
+
+class Engine:
+    """Thin object wrapper over one context of the C ABI.  Method names = C function names without the prefix;
+    they mirror the reference operator names (nbh/contact/prolog/epilog ...)."""
+
+    def __init__(self, lib, config: Config):
+        self.lib = lib
+        self.cfg = config
+        self.h = C.c_void_p()
+        rc = lib.fn("create")(C.byref(config), C.byref(self.h))
+        if rc != 0:
+            raise EdbError(f"create failed rc={rc}: {self._err(None)}")
+
+    # -- plumbing
+    def _err(self, h):
+        try:
+            f = getattr(self.lib.dll, self.lib.prefix + "last_error")
+        except AttributeError:
+            return ""
+        f.restype = C.c_char_p
+        s = f(h)
+        return s.decode() if s else ""
+
+    def _call(self, name, *args):
+        rc = self.lib.fn(name)(self.h, *args)
+        if rc != 0:
+            raise EdbError(f"{self.lib.prefix}{name} failed rc={rc}: {self._err(self.h)}")
+
+    def close(self):
+        if self.h:
+            self.lib.fn("destroy")(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parameters
+    def set_contact_params(self, particle: dict, driver: dict | None = None):
+        a = ContactParams(**particle)
+        b = ContactParams(**(driver if driver is not None else particle))
+        self._call("set_contact_params", C.byref(a), C.byref(b))
+
+    def set_contact_params_multimat(self, n_groups, pp, n_drivers, pd):
+        A = (ContactParams * (n_groups * n_groups))(*[ContactParams(**d) for d in pp])
+        B = (ContactParams * max(1, n_groups * n_drivers))(*[ContactParams(**d) for d in pd])
+        self._call("set_contact_params_multimat", C.c_int32(n_groups), A, C.c_int32(n_drivers), B)
+
+    def set_law(self, law):
+        self._call("set_law", C.c_int32(law))
+
+    def set_drivers(self, drivers):
+        arr = (Driver * max(1, len(drivers)))()
+        for k, d in enumerate(drivers):
+            D = Driver()
+            D.kind = d["kind"]
+            D.need_forces = d.get("need_forces", 0)
+            D.radius = d.get("radius", 0.0)
+            for name, dflt in (("axis", (1, 0, 1)), ("center", (0, 0, 0)), ("normal", (0, 0, 1)), ("vel", (0, 0, 0)),
+                               ("vrot", (0, 0, 0))):
+                val = d.get(name, dflt)
+                for c in range(3):
+                    getattr(D, name)[c] = float(val[c])
+            D.offset = d.get("offset", 0.0)
+            D.shape = d.get("shape", -1)
+            arr[k] = D
+        self._call("set_drivers", C.c_int32(len(drivers)), arr)
+
+    def set_shapes(self, shapes):
+        arr = (Shape * len(shapes))(*shapes)
+        self._keep_shapes = shapes
+        self._call("set_shapes", C.c_int32(len(shapes)), arr)
+
+    # -- grid
+    def upload_particles(self, pa: ParticleArrays):
+        v = pa.view()
+        self._call("upload_particles", C.byref(v))
+
+    def download_particles(self, pa: ParticleArrays | None = None) -> ParticleArrays:
+        nr, _ = self.num_particles()
+        if pa is None:
+            pa = ParticleArrays(nr)
+        assert pa.n == nr
+        v = pa.view()
+        self._call("download_particles", C.byref(v))
+        return pa
+
+    def upload_dynamic(self, pa: ParticleArrays):
+        v = pa.view()
+        self._call("upload_dynamic", C.byref(v))
+
+    def download_dynamic(self, pa: ParticleArrays):
+        v = pa.view()
+        self._call("download_dynamic", C.byref(v))
+
+    def num_particles(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._call("num_particles", C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    # -- operators
+    def update_particle_neighbors(self, rcut_inc, symetric=True):
+        self._call("update_particle_neighbors", C.c_double(rcut_inc), C.c_int32(1 if symetric else 0))
+
+    def ghost_update_rq(self):
+        self._call("ghost_update_rq")
+
+    def compute_vertices(self):
+        self._call("compute_vertices")
+
+    def reset_force_moment(self):
+        self._call("reset_force_moment")
+
+    def gravity_force(self, g=(0.0, 0.0, -9.807)):
+        self._call("gravity_force", (C.c_double * 3)(*g))
+
+    def contact_sphere(self, dt):
+        self._call("contact_sphere", C.c_double(dt))
+
+    def contact_polyhedron(self, dt):
+        self._call("contact_polyhedron", C.c_double(dt))
+
+    def contact(self, dt):
+        (self.contact_polyhedron if self.cfg.mode == MODE_POLYHEDRON else self.contact_sphere)(dt)
+
+    def force_to_accel(self):
+        self._call("force_to_accel")
+
+    def combined_compute_prolog(self, dt):
+        self._call("combined_compute_prolog", C.c_double(dt))
+
+    def combined_compute_epilog(self, dt):
+        self._call("combined_compute_epilog", C.c_double(dt))
+
+    def push_to_quaternion(self, dt):
+        self._call("push_to_quaternion", C.c_double(dt))
+
+    def push_to_angular_velocity(self, dt):
+        self._call("push_to_angular_velocity", C.c_double(dt))
+
+    def push_to_angular_acceleration(self):
+        self._call("push_to_angular_acceleration")
+
+    def freeze_particles(self):
+        self._call("freeze_particles")
+
+    def displ_over(self, threshold) -> int:
+        n = C.c_uint64()
+        self._call("displ_over", C.c_double(threshold), C.byref(n))
+        return n.value
+
+    def compute_driver_force_moment(self, n_drivers):
+        f = np.zeros((n_drivers, 3))
+        m = np.zeros((n_drivers, 3))
+        self._call("compute_driver_force_moment", _as(f, _D), _as(m, _D))
+        return f, m
+
+    def run_verlet(self, dt, g, rcut_inc, symetric, nsteps, rebuild_every=0) -> int:
+        nb = C.c_uint64()
+        self._call("run_verlet", C.c_double(dt), (C.c_double * 3)(*g), C.c_double(rcut_inc),
+                   C.c_int32(1 if symetric else 0), C.c_int32(nsteps), C.c_int32(rebuild_every), C.byref(nb))
+        return nb.value
+
+    # -- views
+    def interaction_counts(self):
+        c = (C.c_uint64 * NTYPES)()
+        a = (C.c_uint64 * NTYPES)()
+        self._call("interaction_counts", c, a)
+        return np.array(c[:], dtype=np.uint64), np.array(a[:], dtype=np.uint64)
+
+    def export_interactions(self) -> np.ndarray:
+        counts, _ = self.interaction_counts()
+        n = int(counts.sum())
+        out = np.zeros(max(n, 1), dtype=INTERACTION_DTYPE)
+        got = C.c_uint64()
+        self._call("export_interactions", out.ctypes.data_as(C.POINTER(Interaction)), C.c_uint64(n), C.byref(got))
+        assert got.value == n, (got.value, n)
+        return out[:n]
+
+    def import_interactions(self, rec: np.ndarray):
+        rec = np.ascontiguousarray(rec, dtype=INTERACTION_DTYPE)
+        self._call("import_interactions", rec.ctypes.data_as(C.POINTER(Interaction)), C.c_uint64(len(rec)))
+
+    def get_contact_state(self, t):
+        counts, _ = self.interaction_counts()
+        n = int(counts[t])
+        dn = np.zeros(max(n, 1))
+        cp, fn, ft = (np.zeros((max(n, 1), 3)) for _ in range(3))
+        self._call("get_contact_state", C.c_int32(t), _as(dn, _D), _as(cp, _D), _as(fn, _D), _as(ft, _D))
+        return dn[:n], cp[:n], fn[:n], ft[:n]
+
+    def counters(self) -> Counters:
+        c = Counters()
+        self._call("get_counters", C.byref(c))
+        return c
+
+    def reset_counters(self):
+        self._call("reset_counters")
+
+    def set_timing(self, on):
+        self._call("set_timing", C.c_int32(1 if on else 0))
+
+    def sync(self):
+        self._call("sync")
+
+    def flush_l2(self):
+        self._call("flush_l2")
+
+    def comm_init(self, uid: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._call("comm_init", buf)
+
+
+def comm_unique_id(lib) -> bytes:
+    buf = (C.c_uint8 * 128)()
+    f = getattr(lib.dll, lib.prefix + "comm_unique_id")
+    f.restype = C.c_int
+    rc = f(buf)
+    if rc != 0:
+        raise EdbError(f"comm_unique_id rc={rc}")
+    return bytes(buf)
+
+
+def make_config(lo, hi, cell_size, periodic=(0, 0, 0), mode=MODE_SPHERE, device=0, glo=None, ghi=None, rank=0,
+                nranks=1, pgrid=(1, 1, 1), emit_contact_state=1) -> Config:
+    c = Config()
+    glo = lo if glo is None else glo
+    ghi = hi if ghi is None else ghi
+    for k in range(3):
+        c.lo[k], c.hi[k], c.glo[k], c.ghi[k] = float(lo[k]), float(hi[k]), float(glo[k]), float(ghi[k])
+        c.periodic[k] = int(periodic[k])
+        c.pgrid[k] = int(pgrid[k])
+    c.cell_size = float(cell_size)
+    c.mode = mode
+    c.device = device
+    c.rank, c.nranks = rank, nranks
+    c.emit_contact_state = emit_contact_state
+    return c

@@ -1,0 +1,203 @@
+/* exadem_b200.h — C ABI of libexadem_b200.so: the B200-native (sm_100a) DEM contact hot path.
+ *
+ * Drop-in boundary for the hot-path operators of exaDEM v1.2.2.  The reference has NO C ABI:
+ * its operators are Onika `OperatorNode` plugins (C++), so each entry point below names the reference
+ * operator (YAML name, file:line under /root/reference) whose `execute()` it replaces.  The C++ host operators
+ * in exadem_b200/host/ keep the reference's operator names, slots and parameters and call these functions;
+ * INTEGRATION.md shows the Onika-side binding.
+ *
+ * Conventions
+ *  - plain pointers + sizes only; every function returns 0 on success, <0 on error (edb_last_error()).
+ *  - all particle pointers are BORROWED host pointers (pageable or pinned) unless a function says "device".
+ *  - one context per GPU / rank; a context is not re-entrant (reference: operators run sequentially from one
+ *    host thread, SURVEY.md 8b "Threading").  Launches are asynchronous on the context stream; edb_sync() waits.
+ *  - no CPU fallback: every compute entry point fails with EDB_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef EXADEM_B200_H
+#define EXADEM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDB_OK 0
+#define EDB_ERR_INVALID (-1)
+#define EDB_ERR_NO_DEVICE (-2)
+#define EDB_ERR_CUDA (-3)
+#define EDB_ERR_NCCL (-4)
+#define EDB_ERR_STATE (-5)
+#define EDB_ERR_CAPACITY (-6)
+
+/* interaction type ids: src/interaction/include/exaDEM/interaction/interaction_enum.hpp:24-57 */
+#define EDB_NTYPES 14
+enum { EDB_MODE_SPHERE = 0, EDB_MODE_POLYHEDRON = 1 };
+/* cohesive-law variants of the contact operators: src/forcefield/include/exaDEM/forcefield/contact_force.hpp:32-52 */
+enum { EDB_LAW_HOOKE_NONE = 0, EDB_LAW_HOOKE_COHESIVE = 1, EDB_LAW_HOOKE_DMT = 2 };
+/* DRIVER_TYPE: src/driver/include/exaDEM/driver_base.hpp */
+enum { EDB_DRIVER_CYLINDER = 0, EDB_DRIVER_SURFACE = 1, EDB_DRIVER_BALL = 2, EDB_DRIVER_RSHAPE = 3, EDB_DRIVER_UNDEFINED = 4 };
+
+typedef struct edb_context edb_context;
+
+/* `domain` + `grid` slots (exaNBody Domain / Grid; contract in SURVEY.md 2f).  The brick [lo,hi) is THIS rank's
+ * sub-domain; glo/ghi the global periodic box.  cell_size >= 2*r_max + rcut_inc (check_rcut.cpp:72,88-116). */
+typedef struct edb_config {
+  double lo[3], hi[3];   /* local brick bounds */
+  double glo[3], ghi[3]; /* global domain bounds (== lo/hi on one GPU) */
+  double cell_size;
+  int32_t periodic[3];
+  int32_t mode;          /* EDB_MODE_* */
+  int32_t device;        /* CUDA ordinal */
+  int32_t rank, nranks;  /* position in the process grid */
+  int32_t pgrid[3];      /* process grid (bricks per axis), product == nranks */
+  int32_t emit_contact_state; /* 1: keep dn/cp/fn/ft per interaction like classifier.hpp:238-249 (default 1) */
+  int32_t reserved;
+} edb_config;
+
+/* DEMFieldSet (include/exaDEM/fields.h:34-54) as borrowed SoA pointers; NULL = field not transferred. */
+typedef struct edb_particles {
+  uint64_t n;
+  double *rx, *ry, *rz, *vx, *vy, *vz, *fx, *fy, *fz;
+  double *mass, *homothety, *radius;
+  double *qw, *qx, *qy, *qz;          /* orient (Quaternion w,x,y,z) */
+  double *momx, *momy, *momz;
+  double *vrotx, *vroty, *vrotz;
+  double *arotx, *aroty, *arotz;
+  double *inertiax, *inertiay, *inertiaz;
+  uint64_t* id;
+  uint32_t* type;
+  uint32_t* group;
+} edb_particles;
+
+/* ContactParams (src/forcefield/include/exaDEM/forcefield/contact_parameters.hpp:32-41) */
+typedef struct edb_contact_params {
+  double kn, kt, kr, mu, damp_rate, fc, dncut, gamma;
+} edb_contact_params;
+
+/* One driver (src/driver/include/exaDEM/{cylinder,surface,ball}.hpp fields).  Cylinder `center` is given as in
+ * the YAML deck; the library applies the reference's component-wise `center*axis` pre-multiplication
+ * (cylinder.hpp:104, quirk Q11). */
+typedef struct edb_driver {
+  int32_t kind;        /* EDB_DRIVER_* */
+  int32_t need_forces; /* motion_type.hpp:133-141: accumulate -f on the driver */
+  double radius;       /* cylinder, ball */
+  double axis[3];      /* cylinder */
+  double center[3];    /* cylinder, ball, surface reference centre */
+  double offset;       /* surface */
+  double normal[3];    /* surface */
+  double vel[3], vrot[3];
+  int32_t shape;       /* RSHAPE: mesh shape index (edb_set_shapes table) */
+  int32_t reserved;
+} edb_driver;
+
+/* `shape` (src/shape/include/exaDEM/shape.hpp:50-69) flattened: faces as the [n0, v.., n1, v..] stream. */
+typedef struct edb_shape {
+  int32_t nv, ne, nf, faces_len;
+  const double* vertices; /* nv*3 */
+  const int32_t* edges;   /* ne*2 */
+  const int32_t* faces;   /* faces_len ints: per face {n, v0..v(n-1)} */
+  double obb[15];         /* center, e1, e2, e3, extent (extent includes the Minkowski radius, shape_prepro.hpp:95) */
+  double radius;          /* Minkowski radius */
+} edb_shape;
+
+/* One exported interaction = `Interaction` (interaction.hpp:44-48 + interaction_pair.hpp:30-70), 104 B, same
+ * member order/offsets as the reference record so dumps/restarts interoperate. */
+typedef struct edb_interaction {
+  uint64_t id_i; uint32_t cell_i; uint16_t p_i; uint16_t pad_i; uint32_t sub_i; uint32_t pad_i2;
+  uint64_t id_j; uint32_t cell_j; uint16_t p_j; uint16_t pad_j; uint32_t sub_j; uint32_t pad_j2;
+  uint16_t type; uint8_t swap; uint8_t ghost; uint32_t pad_t;
+  double friction[3];
+  double moment[3];
+} edb_interaction;
+
+/* ---- lifetime --------------------------------------------------------------------------------------- */
+int edb_create(const edb_config* cfg, edb_context** out);
+int edb_destroy(edb_context* ctx);
+const char* edb_last_error(const edb_context* ctx); /* ctx may be NULL: last error of a failed edb_create */
+int edb_sync(edb_context* ctx);                     /* ONIKA_CU_DEVICE_SYNCHRONIZE equivalent */
+int edb_version(void);
+
+/* ---- slots: parameters -------------------------------------------------------------------------------- */
+/* `config` / `config_driver` slots of contact_sphere / contact_polyhedron (contact_force_sphere.cu.in:52-73) */
+int edb_set_contact_params(edb_context*, const edb_contact_params* particle, const edb_contact_params* driver);
+/* `multimat_cp` / drivers_contact_params tables (multimat_parameters.hpp:149-200): pp[gA*n_groups+gB], pd[g*n_drivers+d] */
+int edb_set_contact_params_multimat(edb_context*, int32_t n_groups, const edb_contact_params* pp, int32_t n_drivers,
+                                    const edb_contact_params* pd);
+int edb_set_law(edb_context*, int32_t law); /* operator variant: ..._hooke_none | _cohesive | _dmt */
+int edb_set_drivers(edb_context*, int32_t n, const edb_driver* drivers);      /* `drivers` slot */
+int edb_set_shapes(edb_context*, int32_t n, const edb_shape* shapes);         /* `shapes_collection` slot */
+
+/* ---- slots: grid ------------------------------------------------------------------------------------- */
+int edb_upload_particles(edb_context*, const edb_particles* host);   /* full DEMFieldSet, any order */
+int edb_download_particles(edb_context*, edb_particles* host);       /* same order as uploaded/last rebuilt; see edb_get_order */
+int edb_num_particles(edb_context*, uint64_t* n_real, uint64_t* n_ghost);
+/* dynamic fields only (r, v, vrot, orient in; + f, mom, arot out) — the per-step host<->device traffic of a host-owned grid */
+int edb_upload_dynamic(edb_context*, const edb_particles* host);
+int edb_download_dynamic(edb_context*, edb_particles* host);
+
+/* ---- operators (reference YAML name in brackets) ----------------------------------------------------- */
+/* [chunk_neighbors_contact + nbh_sphere | nbh_polyhedron + update_interaction_ghost + classify_interactions]
+ * = chunk_neighbors_impl, data/config/config_spheres.msp:7-12, config_polyhedra.msp:11-18.  Re-bins particles,
+ * rebuilds ghosts, enumerates candidates (src/sphere/nbh_sphere.cu:64-309, src/polyhedron/nbh_polyhedron.cpp:75-384),
+ * carries friction/moment history over (interaction_manager.hpp:205-217) and classifies into waves. */
+int edb_update_particle_neighbors(edb_context*, double rcut_inc, int32_t symetric);
+int edb_ghost_update_rq(edb_context*);                       /* [ghost_update_rq] src/grid/update_ghosts.cu:46-63 */
+int edb_compute_vertices(edb_context*);                      /* [compute_vertices] src/polyhedron/compute_vertices.cu:68-108 */
+int edb_reset_force_moment(edb_context*);                    /* [reset_force_moment] src/numericalscheme/reset_force_moment.cu:55-72 */
+int edb_gravity_force(edb_context*, const double g[3]);      /* [gravity_force] src/forcefield/gravity_force.cu:67-86 */
+int edb_contact_sphere(edb_context*, double dt);             /* [contact_sphere*] src/sphere/contact_force_sphere.cu.in:132-188 */
+int edb_contact_polyhedron(edb_context*, double dt);         /* [contact_polyhedron*] src/polyhedron/contact_force_polyhedron.cu.in:148-245 */
+int edb_force_to_accel(edb_context*);                        /* [force_to_accel] src/numericalscheme/force_to_accel.cu:48-52 */
+int edb_combined_compute_prolog(edb_context*, double dt);    /* [combined_compute_prolog] src/numericalscheme/combined_compute_prolog.cu:94-116 */
+int edb_combined_compute_epilog(edb_context*, double dt);    /* [combined_compute_epilog] src/numericalscheme/combined_compute_epilog.cu:94-113 */
+int edb_push_to_quaternion(edb_context*, double dt);         /* [push_to_quaternion] src/numericalscheme/push_to_quaternion.cu */
+int edb_push_to_angular_velocity(edb_context*, double dt);   /* [push_to_angular_velocity] */
+int edb_push_to_angular_acceleration(edb_context*);          /* [push_to_angular_acceleration] */
+int edb_freeze_particles(edb_context*);                      /* [freeze_particles] src/numericalscheme/freeze_particles.cu:33-88 (no region) */
+/* [particle_displ_over | vertex_displ_over] rebuild trigger: *over = #particles (vertices) moved >= threshold since
+ * the last edb_update_particle_neighbors (which takes the backup, backup_dem.cpp:40-80); all-reduced over ranks. */
+int edb_displ_over(edb_context*, double threshold, uint64_t* over);
+/* [compute_driver_force_moment] src/interaction/compute_driver_force_moment.cu:79-146: forces[n_drivers*3], moments[n_drivers*3] */
+int edb_compute_driver_force_moment(edb_context*, double* forces, double* moments);
+/* [stress_tensor] src/interaction/stress_tensor.cu:142-178: per-particle 3x3 (row-major, upload order), scaled by 1/volume outside */
+int edb_stress_tensor(edb_context*, double* stress9);
+
+/* Fused fast path = numerical_scheme_verlet (data/config/config_numerical_schemes.msp:6-30), `nsteps` iterations:
+ * prolog -> (rebuild if displacement >= rcut_inc/2 | ghost_update_rq) -> [compute_vertices] -> reset+gravity+contact
+ * +force_to_accel -> epilog.  rebuild_every > 0 forces a fixed rebuild schedule instead of the displacement trigger
+ * (parity runs make the schedule an explicit input); 0 = trigger; <0 = never rebuild. */
+int edb_run_verlet(edb_context*, double dt, const double g[3], double rcut_inc, int32_t symetric, int32_t nsteps,
+                   int32_t rebuild_every, uint64_t* n_rebuilds);
+
+/* ---- classifier / ges views --------------------------------------------------------------------------- */
+int edb_interaction_counts(edb_context*, uint64_t counts[EDB_NTYPES], uint64_t active[EDB_NTYPES]);
+/* [unclassify_interactions + compress_interaction] view: all records (type-major, owner-sorted); cap = capacity of out */
+int edb_export_interactions(edb_context*, edb_interaction* out, uint64_t cap, uint64_t* n);
+int edb_import_interactions(edb_context*, const edb_interaction* in, uint64_t n); /* restart: history source for the next rebuild */
+/* ContactState buffers (classifier/contact_state.hpp:22-51) of one wave; each array has counts[type] entries (x3 for vectors) */
+int edb_get_contact_state(edb_context*, int32_t type, double* dn, double* cp, double* fn, double* ft);
+
+/* ---- multi-GPU (replaces MPI in ghost_update_rq / migrate_cell_particles_interaction) ------------------- */
+int edb_comm_unique_id(uint8_t id_out[128]);                       /* rank 0: ncclGetUniqueId */
+int edb_comm_init(edb_context*, const uint8_t id[128]);            /* all ranks: ncclCommInitRank(nranks, rank) */
+
+/* ---- measurement hooks -------------------------------------------------------------------------------- */
+typedef struct edb_counters {
+  uint64_t kernel_launches;     /* kernels of this library launched since creation */
+  uint64_t interaction_updates; /* sum over waves of records processed by the contact kernels */
+  uint64_t particle_steps;      /* real particles x steps */
+  uint64_t rebuilds;
+  double   contact_ms;          /* CUDA-event time of the contact wave kernels (accumulated, when timing enabled) */
+  double   gather_ms, prolog_ms, epilog_ms, rebuild_ms, ghost_ms;
+  uint64_t contact_launches;
+  uint64_t bytes_contact_algorithmic; /* accumulated algorithmic bytes of the contact kernels */
+} edb_counters;
+int edb_set_timing(edb_context*, int32_t enabled);
+int edb_get_counters(edb_context*, edb_counters* out);
+int edb_reset_counters(edb_context*);
+int edb_flush_l2(edb_context*); /* writes a >L2-sized scratch buffer (bench hygiene) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXADEM_B200_H */

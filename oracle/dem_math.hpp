@@ -1,0 +1,390 @@
+// oracle/dem_math.hpp — CPU restatement of the exaDEM contact arithmetic.  TEST INFRASTRUCTURE ONLY.
+//
+// This header is part of the ORACLE (the checker).  Only tests/, __graft_entry__.smoke() and the
+// cpu_baseline / --impl reference legs of bench.py may use it; the product path (exadem_b200/) must never
+// include, link or call it.
+//
+// Every function cites the reference file:line whose arithmetic (including operation ORDER, which matters
+// for bit-exact threshold filters and 1e-10 force parity) it restates.  Paths are relative to /root/reference.
+// The vector algebra of the un-vendored Onika library (onika/math/*) is restated from its call-site contract
+//  — "parity unpinned" for that layer (risk R1); everything above it is pinned bit-for-bit
+// against the reference's own headers through oracle/_ref (tests/test_oracle_vs_ref.py).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <vector>
+
+namespace orc {
+
+struct v3 {
+  double x, y, z;
+};
+struct q4 {
+  double w, x, y, z;
+};  // exanb::Quaternion {w,x,y,z}
+
+// --- onika/math/basic_types_operators.h (absent; working definition, evaluation order left-to-right) ---
+static inline v3 operator+(v3 a, v3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+static inline v3 operator-(v3 a, v3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline v3 operator-(v3 a) { return {-a.x, -a.y, -a.z}; }
+static inline v3 operator*(v3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+static inline v3 operator*(double s, v3 a) { return {s * a.x, s * a.y, s * a.z}; }
+static inline v3 operator/(v3 a, double s) { return {a.x / s, a.y / s, a.z / s}; }
+static inline v3 cmul(v3 a, v3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }  // Vec3d*Vec3d (cylinder.hpp:226)
+static inline double dot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline double norm(v3 a) { return std::sqrt(dot(a, a)); }
+static inline v3 cross(v3 u, v3 v) { return {u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x}; }
+static inline bool is_zero(v3 a) { return a.x == 0.0 && a.y == 0.0 && a.z == 0.0; }
+
+// quaternion rotation: src/shape/include/exaDEM/type/quat.hpp:79-90 (v + 2s(q x v) + 2 q x (q x v))
+static inline v3 qrot(q4 q, v3 v) {
+  const v3 u{q.x, q.y, q.z};
+  v3 uv = cross(u, v);
+  v3 uuv = cross(u, uv);
+  uv = uv * (2.0 * q.w);
+  uuv = uuv * 2.0;
+  return v + uv + uuv;
+}
+static inline q4 qconj(q4 q) { return {q.w, -q.x, -q.y, -q.z}; }
+// dQ/dt = 1/2 omega (x) Q : quat.hpp:92-96
+static inline q4 qdot(q4 q, v3 o) {
+  return {-0.5 * (o.x * q.x + o.y * q.y + o.z * q.z), 0.5 * (o.y * q.z - o.z * q.y + o.x * q.w),
+          0.5 * (o.z * q.x - o.x * q.z + o.y * q.w), 0.5 * (o.x * q.y - o.y * q.x + o.z * q.w)};
+}
+
+struct Contact {
+  bool hit = false;
+  double dn = 0;
+  v3 n{0, 0, 0};
+  v3 cp{0, 0, 0};
+};
+
+// ---- filters / detection cores: src/shape/include/exaDEM/shape_detection_core.hpp ----
+// :43-53
+static inline bool filter_vv(double rV, v3 vi, double ri, v3 vj, double rj) {
+  const double R = ri + rj + rV;
+  const v3 d = vi - vj;
+  return dot(d, d) <= R * R;
+}
+// :57-81
+static inline Contact detect_vv(v3 pi, double ri, v3 pj, double rj) {
+  const double R = ri + rj;
+  const v3 d = pi - pj;
+  const double len = norm(d);
+  const double inv = 1.0 / len;
+  Contact c;
+  c.dn = len - R;
+  c.n = d * inv;
+  c.cp = pi - c.n * (ri + 0.5 * c.dn);
+  c.hit = c.dn < 0;
+  return c;
+}
+// :83-101
+static inline bool filter_ve(double rV, v3 vi, double ri, v3 vf, v3 vs, double rj) {
+  const v3 fs = vs - vf, fi = vi - vf;
+  const double r = dot(fs, fi) / dot(fs, fs);
+  if (r < -rV || r > 1.0 + rV) return false;
+  const v3 d = fi - fs * r;
+  const double Rmax = ri + rj + rV;
+  return dot(d, d) < Rmax * Rmax;
+}
+// :122-148
+static inline Contact detect_ve(v3 vi, double ri, v3 vf, v3 vs, double rj) {
+  const v3 fs = vs - vf, fi = vi - vf;
+  const double r = dot(fs, fi) / dot(fs, fs);
+  if (r <= 0 || r >= 1.0) return Contact();
+  v3 n = fi - fs * r;
+  const double dn = norm(n) - (ri + rj);
+  if (dn > 0) return Contact();
+  n = n / norm(n);  // _normalize, include/exaDEM/normalize.hpp
+  Contact c;
+  c.hit = true;
+  c.dn = dn;
+  c.n = n;
+  c.cp = vi - n * (ri + 0.5 * dn);
+  return c;
+}
+
+// point-in-polygon shared by filter (:245-309) and detection (:398-466); `va` = world vertices of the
+// face owner, `idx[0..nf)` = the face's vertex indices.  Returns (inside?, dist, n).
+template <class VA>
+static inline bool face_test(v3 vi, const VA& va, const int* idx, int nf, double cut, double& dist_out, v3& n_out) {
+  const v3 a = va[idx[0]], b = va[idx[1]], c = va[idx[nf - 1]];
+  const v3 v = vi - a;
+  v3 v1 = b - a;
+  v3 v2 = c - a;
+  v1 = v1 / norm(v1);
+  v3 n = cross(v1, v2);
+  n = n / norm(n);
+  double dist = dot(n, v);
+  if (dist < 0) {
+    n = n * (-1);
+    dist = -dist;
+  }
+  dist_out = dist;
+  n_out = n;
+  if (dist > cut) return false;  // caller distinguishes "too far" via dist_out > cut
+  const v3 P = vi - n * dist;
+  int odd = 0;
+  v2 = cross(n, v1);
+  const double o1 = dot(P, v1), o2 = dot(P, v2);
+  for (int ia = 0; ia < nf; ++ia) {
+    int ib = ia + 1;
+    if (ib == nf) ib = 0;
+    const v3 pa = va[idx[ia]], pb = va[idx[ib]];
+    const double pa1 = dot(pa, v1), pb1 = dot(pb, v1), pa2 = dot(pa, v2), pb2 = dot(pb, v2);
+    if ((pa2 < o2 && pb2 >= o2) || (pb2 < o2 && pa2 >= o2)) {
+      if (pa1 + (o2 - pa2) / (pb2 - pa2) * (pb1 - pa1) < o1) odd = 1 - odd;
+    }
+  }
+  return odd == 1;
+}
+template <class VA>
+static inline bool filter_vf(double rV, v3 vi, double ri, const VA& va, double rj, const int* idx, int nf) {
+  double dist;
+  v3 n;
+  return face_test(vi, va, idx, nf, ri + rj + rV, dist, n);
+}
+template <class VA>
+static inline Contact detect_vf(v3 vi, double ri, const VA& va, double rj, const int* idx, int nf) {
+  double dist;
+  v3 n;
+  const bool inside = face_test(vi, va, idx, nf, ri + rj, dist, n);
+  if (dist > ri + rj) return Contact();
+  Contact c;
+  c.dn = dist - (ri + rj);
+  c.n = n;
+  c.cp = vi - n * (ri + 0.5 * c.dn);
+  c.hit = inside;
+  return c;
+}
+// :468-504 / :521-566
+static inline bool ee_closest(v3 fi, v3 si, v3 fj, v3 sj, v3& pi, v3& pj) {
+  const v3 Ei = si - fi, Ej = sj - fj, v = fi - fj;
+  const double c = dot(Ei, Ei), d = dot(Ej, Ej), e = dot(Ei, Ej);
+  double f = (c * d) - (e * e);
+  if (!(std::fabs(f) > 1.0e-12)) return false;
+  f = 1.0 / f;
+  const double a = dot(Ei, v), b = dot(Ej, v);
+  const double s = (e * b - a * d) * f;
+  const double t = (c * b - e * a) * f;
+  if (s <= 0.0 || s >= 1.0 || t <= 0.0 || t >= 1.0) return false;
+  pi = fi + Ei * s;
+  pj = fj + Ej * t;
+  return true;
+}
+static inline bool filter_ee(double rV, v3 fi, v3 si, double ri, v3 fj, v3 sj, double rj) {
+  const double R = ri + rj + rV;
+  v3 pi, pj;
+  if (!ee_closest(fi, si, fj, sj, pi, pj)) return false;
+  const v3 n = pi - pj;
+  return dot(n, n) <= R * R;
+}
+static inline Contact detect_ee(v3 fi, v3 si, double ri, v3 fj, v3 sj, double rj) {
+  const double R = ri + rj;
+  v3 pi, pj;
+  if (!ee_closest(fi, si, fj, sj, pi, pj)) return Contact();
+  v3 n = pi - pj;
+  const double dn = norm(n) - R;
+  if (dn > 0) return Contact();
+  n = n / norm(n);
+  Contact c;
+  c.hit = dn <= 0;
+  c.dn = dn;
+  c.n = n;
+  c.cp = pi - n * (ri + 0.5 * dn);
+  return c;
+}
+
+// ---- OBB: src/shape/include/exaDEM/type/OBB.hpp ----
+struct Obb {
+  v3 c, e1, e2, e3, ext;
+};
+// basic_types.hpp:37-49 (+ OBB::rotate :83-88, enlarge :63-67)
+static inline Obb obb_world(const Obb& in, v3 pos, q4 q, double h) {
+  Obb o = in;
+  o.e1 = qrot(q, o.e1);
+  o.e2 = qrot(q, o.e2);
+  o.e3 = qrot(q, o.e3);
+  o.c = qrot(q, o.c);
+  if (h != 1.0) {
+    o.ext = o.ext * h;
+    o.c = o.c * h;
+  }
+  o.c = o.c + pos;
+  return o;
+}
+static inline void obb_enlarge(Obb& o, double m) {
+  o.ext.x += m;
+  o.ext.y += m;
+  o.ext.z += m;
+}
+// OBB.hpp:90-222 — 15-axis SAT, tol = FLT_EPSILON added to every |R| term
+static inline bool obb_intersect(const Obb& A, const Obb& B) {
+  const double tol = 1.1920928955078125e-07;  // FLT_EPSILON
+  double R[3][3], Q[3][3];
+  const v3 ea[3] = {A.e1, A.e2, A.e3}, eb[3] = {B.e1, B.e2, B.e3};
+  const double xa[3] = {A.ext.x, A.ext.y, A.ext.z}, xb[3] = {B.ext.x, B.ext.y, B.ext.z};
+  const v3 tt = A.c - B.c;
+  const double t[3] = {dot(tt, A.e1), dot(tt, A.e2), dot(tt, A.e3)};
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) {
+      R[i][j] = dot(ea[i], eb[j]);
+      Q[i][j] = std::fabs(R[i][j]) + tol;
+    }
+    const double ra = xa[i];
+    const double rb = xb[0] * Q[i][0] + xb[1] * Q[i][1] + xb[2] * Q[i][2];
+    if (std::fabs(t[i]) > ra + rb) return false;
+  }
+  for (int j = 0; j < 3; j++) {
+    const double ra = xa[0] * Q[0][j] + xa[1] * Q[1][j] + xa[2] * Q[2][j];
+    const double rb = xb[j];
+    if (std::fabs(t[0] * R[0][j] + t[1] * R[1][j] + t[2] * R[2][j]) > ra + rb) return false;
+  }
+  double ra, rb;
+  // A0 x B0..B2
+  ra = xa[1] * Q[2][0] + xa[2] * Q[1][0]; rb = xb[1] * Q[0][2] + xb[2] * Q[0][1];
+  if (std::fabs(t[2] * R[1][0] - t[1] * R[2][0]) > ra + rb) return false;
+  ra = xa[1] * Q[2][1] + xa[2] * Q[1][1]; rb = xb[0] * Q[0][2] + xb[2] * Q[0][0];
+  if (std::fabs(t[2] * R[1][1] - t[1] * R[2][1]) > ra + rb) return false;
+  ra = xa[1] * Q[2][2] + xa[2] * Q[1][2]; rb = xb[0] * Q[0][1] + xb[1] * Q[0][0];
+  if (std::fabs(t[2] * R[1][2] - t[1] * R[2][2]) > ra + rb) return false;
+  // A1 x B0..B2
+  ra = xa[0] * Q[2][0] + xa[2] * Q[0][0]; rb = xb[1] * Q[1][2] + xb[2] * Q[1][1];
+  if (std::fabs(t[0] * R[2][0] - t[2] * R[0][0]) > ra + rb) return false;
+  ra = xa[0] * Q[2][1] + xa[2] * Q[0][1]; rb = xb[0] * Q[1][2] + xb[2] * Q[1][0];
+  if (std::fabs(t[0] * R[2][1] - t[2] * R[0][1]) > ra + rb) return false;
+  ra = xa[0] * Q[2][2] + xa[2] * Q[0][2]; rb = xb[0] * Q[1][1] + xb[1] * Q[1][0];
+  if (std::fabs(t[0] * R[2][2] - t[2] * R[0][2]) > ra + rb) return false;
+  // A2 x B0..B2
+  ra = xa[0] * Q[1][0] + xa[1] * Q[0][0]; rb = xb[1] * Q[2][2] + xb[2] * Q[2][1];
+  if (std::fabs(t[1] * R[0][0] - t[0] * R[1][0]) > ra + rb) return false;
+  ra = xa[0] * Q[1][1] + xa[1] * Q[0][1]; rb = xb[0] * Q[2][2] + xb[2] * Q[2][0];
+  if (std::fabs(t[1] * R[0][1] - t[0] * R[1][1]) > ra + rb) return false;
+  ra = xa[0] * Q[1][2] + xa[1] * Q[0][2]; rb = xb[0] * Q[2][1] + xb[1] * Q[2][0];
+  if (std::fabs(t[1] * R[0][2] - t[0] * R[1][2]) > ra + rb) return false;
+  return true;
+}
+// nbh_polyhedron.cpp:305-310 — axis-aligned cube of half-width `m` around a vertex
+static inline Obb obb_point(v3 c, double m) { return Obb{c, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {m, m, m}}; }
+
+// ---- contact law: src/forcefield/include/exaDEM/forcefield/{common_kernels,contact_force}.hpp ----
+struct Params {
+  double kn = 0, kt = 0, kr = 0, mu = 0, damp = 0, fc = 0, dncut = 0, gamma = 0;  // contact_parameters.hpp:32-41
+};
+enum Law { LAW_NONE = 0, LAW_COHESIVE = 1, LAW_DMT = 2 };
+
+// contact_force.hpp:146-235.  ft, mom: per-interaction history (in/out); f: force on i (out).
+static inline void contact_force(int law, double dn, v3 n, double dt, const Params& p, double meff, double reff, v3& ft,
+                                 v3 cp, v3 pos_i, v3 vel_i, v3& f, v3& mom, v3 w_i, v3 pos_j, v3 vel_j, v3 w_j) {
+  if (law == LAW_COHESIVE && dn >= 0) {  // :165-173
+    const double fnv = (p.fc / p.dncut) * dn - p.fc;
+    f = f + fnv * n;
+    ft = {0, 0, 0};
+    return;
+  }
+  const double damp = p.damp * 2.0 * std::sqrt(p.kn * meff);  // common_kernels.hpp:28-31
+  const v3 ci = vel_i - cross(cp - pos_i, w_i);                 // :34-41
+  const v3 cj = vel_j - cross(cp - pos_j, w_j);
+  const v3 vel = cj - ci;
+  const double vn = dot(vel, n);
+  const double fne = -p.kn * dn, fnv = damp * vn;               // :48-53
+  double fs = (fnv + fne > 0) ? fnv + fne : 0;
+  v3 fn;
+  if (law == LAW_COHESIVE) {                                    // :69-76
+    const double a = fs - p.fc;
+    const double b = a < (-p.fc) ? -p.fc : a;
+    fn = b * n;
+  } else {
+    fn = fs * n;
+  }
+  const v3 vt = vel - vn * n;                                   // :80-90
+  ft = ft + p.kt * (dt * vt);
+  double thr;
+  if (law != LAW_COHESIVE) thr = std::fabs(p.mu * (p.kn * dn));  // :108-114
+  else thr = std::fabs(p.mu * (dot(fn, n) + p.fc));              // :116-120
+  const double ft2 = dot(ft, ft);                               // :122-128
+  if (ft2 > 0.0 && ft2 > thr * thr) ft = ft * (thr / std::sqrt(ft2));
+  f = fn + ft;
+  if (law == LAW_DMT && p.gamma > 0.0 && dn < 0.0) {            // contact_force.hpp:115-127
+    const double Fd = 2.0 * M_PI * reff * p.gamma;
+    f = f - Fd * n;
+  }
+  mom = mom + p.kr * (w_j - w_i) * dt;                          // :223
+  v3 branch = cp - pos_i;
+  const double r = dot(branch, w_i) / dot(w_i, w_i);            // NaN when w_i == 0 (quirk Q1)
+  branch = branch - r * w_i;
+  const double mur = 0;
+  const double thm = std::fabs(mur * norm(branch) * norm(fn));
+  const double m2 = dot(mom, mom);
+  if (m2 > 0.0 && m2 > thm * thm) mom = mom * (thm / std::sqrt(m2));
+}
+// common_kernels.hpp:137-145
+static inline v3 moments(v3 cp, v3 p, v3 f, v3 m) { return cross(cp - p, f) + m; }
+
+// ---- drivers: src/driver/include/exaDEM/{cylinder,surface,ball}.hpp ----
+enum DriverKind { DRV_CYLINDER = 0, DRV_SURFACE = 1, DRV_BALL = 2, DRV_RSHAPE = 3, DRV_UNDEFINED = 4 };
+struct Driver {
+  int kind = DRV_UNDEFINED;
+  double radius = 0;      // cylinder, ball
+  v3 axis{1, 0, 1};       // cylinder (component mask, quirk Q11)
+  v3 center{0, 0, 0};     // cylinder: already multiplied by axis (cylinder.hpp:104); ball center; surface ref. center
+  double offset = 0;      // surface
+  v3 normal{0, 0, 1};     // surface
+  v3 vel{0, 0, 0}, vrot{0, 0, 0};
+  v3 forces{0, 0, 0};     // accumulated -f when need_forces
+  int need_forces = 0;    // motion_type.hpp:133-141
+  int shape = -1;         // RSHAPE: index into the mesh-shape table
+  v3 center_proj() const { return offset * normal; }  // surface.hpp:149
+};
+// cylinder.hpp:225-235, surface.hpp:320-324, ball.hpp:292-296
+static inline bool driver_filter(const Driver& d, double rcut, v3 p) {
+  if (d.kind == DRV_CYLINDER) {
+    const v3 dir = cmul(p, d.axis) - d.center;
+    const double dn = d.radius - (norm(dir) + rcut);
+    return dn <= 0;
+  } else if (d.kind == DRV_SURFACE) {
+    const v3 proj = dot(p, d.normal) * d.normal;
+    return norm(proj - d.center_proj()) <= rcut;
+  } else {
+    const v3 dist = d.center - p;
+    const double dd = d.radius - norm(dist);
+    return std::fabs(dd) <= rcut;
+  }
+}
+// cylinder.hpp:255-279, surface.hpp:338-350, ball.hpp:309-327
+static inline Contact driver_detect(const Driver& d, double rcut, v3 p) {
+  Contact c;
+  if (d.kind == DRV_CYLINDER) {
+    const v3 dir = d.center - cmul(p, d.axis);
+    const double len = norm(dir);
+    c.dn = d.radius - (rcut + len);
+    if (c.dn > 0) return c;
+    c.n = dir / len;
+  } else if (d.kind == DRV_SURFACE) {
+    const v3 proj = dot(p, d.normal) * d.normal;
+    const v3 s2p = -(d.center_proj() - proj);
+    const double len = norm(s2p);
+    c.dn = len - rcut;
+    if (c.dn > 0) return c;
+    c.n = s2p / len;
+  } else {
+    const v3 p2c = d.center - p;
+    const double len = norm(p2c);
+    v3 n = p2c / len;
+    if (len > d.radius) {
+      c.dn = len - d.radius - rcut;
+      n = (-1) * n;
+    } else {
+      c.dn = d.radius - len - rcut;
+    }
+    if (c.dn > 0) return c;
+    c.n = n;
+  }
+  c.cp = p - c.n * (rcut + 0.5 * c.dn);
+  c.hit = true;
+  return c;
+}
+
+}  // namespace orc

@@ -1,0 +1,863 @@
+// oracle/dem_oracle.cpp -> oracle/liboracle_dem.so — CPU restatement of the exaDEM contact hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  This is the ORACLE (the checker): only tests/, __graft_entry__.smoke() and the
+// cpu_baseline / `--impl reference` legs of bench.py may load it.  The product (exadem_b200/) never does.
+//
+// Parity status: the arithmetic layer (dem_math.hpp) is pinned bit-for-bit against the reference's own headers
+// compiled in place (oracle/_ref, tests/test_oracle_vs_ref.py).  The operator loops below depend on exaNBody /
+// Onika code that is NOT in /root/reference (cell grid, neighbour visit, PushVec3 functors, quaternion algebra):
+// they are restated from the call-site contract and the reference ships no golden vectors for
+// them  =>  "parity unpinned" for that layer (risks R1-R3).
+//
+// Reference loops restated here (paths relative to /root/reference):
+//   neighbour filter              src/grid/chunk_neighbors_contact.cpp:46-57
+//   nbh_sphere                    src/sphere/nbh_sphere.cu:64-309
+//   nbh_polyhedron                src/polyhedron/nbh_polyhedron.cpp:75-384, include/exaDEM/polyhedron/nbh_polyhedron_driver.hpp:205-238
+//   history carry-over            src/interaction/include/exaDEM/interaction/interaction_manager.hpp:88-112,205-217,
+//                                 placeholder_interaction.hpp:398-408, interaction_pair.hpp:204-249, interaction.hpp:129-136
+//   classify (wave order)         src/interaction/classify_interactions.cpp:52-136
+//   wave loop                     src/interaction/include/exaDEM/classifier/classifier_for_all.hpp:116-156
+//   sphere kernels                src/sphere/include/exaDEM/sphere/contact_sphere.hpp:121-297
+//   polyhedron kernels            src/polyhedron/include/exaDEM/polyhedron/contact.hpp:124-304
+//   compute_vertices              src/polyhedron/include/exaDEM/polyhedron/compute_vertices.hpp:26-67, shape.hpp:259-262
+//   integrators                   src/numericalscheme/combined_compute_{prolog,epilog}.cu, include/exaDEM/{push_to_quaternion,
+//                                 angular_acceleration,angular_velocity,force_to_accel}.hpp, forcefield/gravity_force.hpp:38-46
+//   ghost refresh field list      src/grid/update_ghosts.cu:46-58
+#include "dem_math.hpp"
+#include "../include/exadem_b200.h"
+
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+using namespace orc;
+
+namespace {
+
+struct Shape {
+  std::vector<v3> v;
+  std::vector<int> edges;               // 2*ne
+  std::vector<int> fidx;                // concatenated face vertex indices
+  std::vector<int> foff, fn;            // per face offset into fidx, vertex count
+  Obb obb;
+  double radius = 0;
+  int nv() const { return (int)v.size(); }
+  int ne() const { return (int)edges.size() / 2; }
+  int nf() const { return (int)fn.size(); }
+};
+
+struct Inter {
+  uint32_t i = 0, j = 0;      // particle indices (j unused for drivers)
+  uint64_t id_i = 0, id_j = 0;
+  uint32_t sub_i = 0, sub_j = 0;
+  uint16_t type = 0;
+  uint8_t swap = 0, ghost = 0;
+  v3 ft{0, 0, 0}, mom{0, 0, 0};
+  // contact state (classifier/contact_state.hpp)
+  double dn = 0;
+  v3 cp{0, 0, 0}, fn{0, 0, 0};
+  uint32_t owner() const { return swap ? j : i; }
+};
+
+// ordering key of InteractionPair::operator< (interaction_pair.hpp:222-249): owner.id, partner.id, type, swap, owner.sub, partner.sub
+using Key = std::tuple<uint64_t, uint64_t, uint16_t, uint8_t, uint32_t, uint32_t>;
+static Key key_of(const Inter& I) {
+  if (!I.swap) return Key{I.id_i, I.id_j, I.type, I.swap, I.sub_i, I.sub_j};
+  return Key{I.id_j, I.id_i, I.type, I.swap, I.sub_j, I.sub_i};
+}
+
+struct Sim {
+  edb_config cfg{};
+  int law = 0;
+  bool multimat = false;
+  int n_groups = 1;
+  std::vector<Params> pp{Params()}, pd{Params()};
+  std::vector<Driver> drivers;
+  std::vector<Shape> shapes;
+  int nvmax = 0;
+
+  // particles: [0,nreal) real, [nreal,ntot) ghosts
+  size_t nreal = 0, ntot = 0;
+  std::vector<v3> r, v, f, mom, w, arot, inertia;
+  std::vector<q4> q;
+  std::vector<double> mass, h, radius;
+  std::vector<uint64_t> id;
+  std::vector<uint32_t> type, group;
+  std::vector<uint32_t> gsrc;
+  std::vector<v3> gshift;
+  std::vector<v3> r_backup;
+  std::vector<q4> q_backup;
+  std::vector<v3> verts;  // ntot*nvmax world vertices
+
+  // grid (with 1 ghost layer)
+  int nc[3]{1, 1, 1}, g[3]{3, 3, 3};
+  std::vector<uint32_t> cstart, citems;
+
+  std::vector<Inter> inter;                 // "ges": owner-major, enumeration order
+  std::vector<uint32_t> wave[EDB_NTYPES];   // "ic": indices into inter per type, classify order
+  double rcut_inc = 0;
+  int symetric = 1;
+  std::string err;
+  int omp_threads = 1;  // 1 = canonical serial accumulation order
+  uint64_t interaction_updates = 0, particle_steps = 0, rebuilds = 0;
+
+  void resize_particles(size_t n) {
+    r.resize(n); v.resize(n); f.resize(n); mom.resize(n); w.resize(n); arot.resize(n); inertia.resize(n);
+    q.resize(n); mass.resize(n); h.resize(n); radius.resize(n); id.resize(n); type.resize(n); group.resize(n);
+    ntot = n;
+  }
+  const Params& cp_pp(uint32_t ga, uint32_t gb) const { return multimat ? pp[ga * n_groups + gb] : pp[0]; }
+  const Params& cp_pd(uint32_t ga, uint32_t d) const { return multimat ? pd[ga * drivers.size() + d] : pd[0]; }
+  size_t cell_of(int i, int j, int k) const { return (size_t)i + (size_t)g[0] * ((size_t)j + (size_t)g[1] * (size_t)k); }
+  bool is_ghost_cell(int i, int j, int k) const {
+    return i == 0 || j == 0 || k == 0 || i == g[0] - 1 || j == g[1] - 1 || k == g[2] - 1;
+  }
+  const v3* pv(uint32_t p) const { return &verts[(size_t)p * nvmax]; }
+};
+
+static inline double L(const Sim& s, int d) { return s.cfg.ghi[d] - s.cfg.glo[d]; }
+
+// --- grid + ghosts -----------------------------------------------------------------------------------------
+static void wrap_positions(Sim& s) {
+  for (size_t p = 0; p < s.nreal; p++) {
+    double* c = &s.r[p].x;
+    for (int d = 0; d < 3; d++) {
+      if (!s.cfg.periodic[d]) continue;
+      if (c[d] >= s.cfg.ghi[d]) c[d] -= L(s, d);
+      else if (c[d] < s.cfg.glo[d]) c[d] += L(s, d);
+    }
+  }
+}
+static inline int cell_coord(const Sim& s, double x, int d) {
+  int c = (int)std::floor((x - s.cfg.lo[d]) / s.cfg.cell_size);
+  if (c < 0) c = 0;
+  if (c > s.nc[d] - 1) c = s.nc[d] - 1;
+  return c;
+}
+static void build_grid(Sim& s) {
+  for (int d = 0; d < 3; d++) {
+    s.nc[d] = std::max(1, (int)std::floor((s.cfg.hi[d] - s.cfg.lo[d]) / s.cfg.cell_size + 1e-9));
+    s.g[d] = s.nc[d] + 2;
+  }
+  s.resize_particles(s.nreal);
+  wrap_positions(s);
+  const size_t ncell = (size_t)s.g[0] * s.g[1] * s.g[2];
+  std::vector<std::vector<uint32_t>> cells(ncell);
+  for (size_t p = 0; p < s.nreal; p++) {
+    const int ci = cell_coord(s, s.r[p].x, 0) + 1, cj = cell_coord(s, s.r[p].y, 1) + 1, ck = cell_coord(s, s.r[p].z, 2) + 1;
+    cells[s.cell_of(ci, cj, ck)].push_back((uint32_t)p);
+  }
+  // deterministic order inside a cell: by particle id
+  for (auto& c : cells) std::sort(c.begin(), c.end(), [&](uint32_t a, uint32_t b) { return s.id[a] < s.id[b]; });
+  // ghosts: every ghost-shell cell mirrors the periodic source cell (whole cell is copied, exaNBody ghost layer)
+  s.gsrc.clear();
+  s.gshift.clear();
+  std::vector<std::pair<size_t, uint32_t>> gcell;  // (ghost cell, ghost particle index)
+  for (int k = 0; k < s.g[2]; k++)
+    for (int j = 0; j < s.g[1]; j++)
+      for (int i = 0; i < s.g[0]; i++) {
+        if (!s.is_ghost_cell(i, j, k)) continue;
+        int src[3] = {i, j, k};
+        double sh[3] = {0, 0, 0};
+        bool ok = true;
+        for (int d = 0; d < 3; d++) {
+          if (src[d] == 0) {
+            if (!s.cfg.periodic[d]) { ok = false; break; }
+            src[d] = s.nc[d];
+            sh[d] = -L(s, d);
+          } else if (src[d] == s.g[d] - 1) {
+            if (!s.cfg.periodic[d]) { ok = false; break; }
+            src[d] = 1;
+            sh[d] = L(s, d);
+          }
+        }
+        if (!ok) continue;
+        const size_t cs = s.cell_of(src[0], src[1], src[2]), cg = s.cell_of(i, j, k);
+        for (uint32_t p : cells[cs]) {
+          if (p >= s.nreal) continue;
+          gcell.push_back({cg, (uint32_t)(s.nreal + s.gsrc.size())});
+          s.gsrc.push_back(p);
+          s.gshift.push_back({sh[0], sh[1], sh[2]});
+        }
+      }
+  s.resize_particles(s.nreal + s.gsrc.size());
+  for (auto& gc : gcell) cells[gc.first].push_back(gc.second);
+  s.cstart.assign(ncell + 1, 0);
+  s.citems.clear();
+  for (size_t c = 0; c < ncell; c++) {
+    s.cstart[c] = (uint32_t)s.citems.size();
+    s.citems.insert(s.citems.end(), cells[c].begin(), cells[c].end());
+  }
+  s.cstart[ncell] = (uint32_t)s.citems.size();
+}
+// ghost_update_rq field list (update_ghosts.cu:46-51) + static fields on (re)build
+static void ghost_refresh(Sim& s, bool all_fields) {
+  for (size_t gI = 0; gI < s.gsrc.size(); gI++) {
+    const size_t p = s.nreal + gI, src = s.gsrc[gI];
+    s.r[p] = s.r[src] + s.gshift[gI];
+    s.v[p] = s.v[src]; s.w[p] = s.w[src]; s.q[p] = s.q[src];
+    s.type[p] = s.type[src]; s.radius[p] = s.radius[src]; s.mass[p] = s.mass[src];
+    if (all_fields) {
+      s.h[p] = s.h[src]; s.id[p] = s.id[src]; s.group[p] = s.group[src]; s.inertia[p] = s.inertia[src];
+      s.arot[p] = s.arot[src]; s.f[p] = {0, 0, 0}; s.mom[p] = {0, 0, 0};
+    }
+  }
+}
+
+static void compute_vertices(Sim& s) {
+  if (s.cfg.mode != EDB_MODE_POLYHEDRON) return;
+  s.verts.resize(s.ntot * (size_t)s.nvmax);
+  for (size_t p = 0; p < s.ntot; p++) {
+    const Shape& sh = s.shapes[s.type[p]];
+    for (int k = 0; k < sh.nv(); k++) s.verts[p * s.nvmax + k] = s.r[p] + qrot(s.q[p], s.h[p] * sh.v[k]);  // shape.hpp:259-262
+  }
+}
+
+// --- candidate enumeration -----------------------------------------------------------------------------------
+template <class F>
+static void for_each_neighbor(const Sim& s, int ci, int cj, int ck, uint32_t a, F&& fn) {
+  const double rcut = 0;  // nbh_dist: implied by the radius filter under check_rcut.cpp constraints
+  (void)rcut;
+  for (int dk = -1; dk <= 1; dk++)
+    for (int dj = -1; dj <= 1; dj++)
+      for (int di = -1; di <= 1; di++) {
+        const int i = ci + di, j = cj + dj, k = ck + dk;
+        if (i < 0 || j < 0 || k < 0 || i >= s.g[0] || j >= s.g[1] || k >= s.g[2]) continue;
+        const size_t cb = s.cell_of(i, j, k);
+        const bool ghostc = s.is_ghost_cell(i, j, k);
+        for (uint32_t it = s.cstart[cb]; it < s.cstart[cb + 1]; it++) {
+          const uint32_t b = s.citems[it];
+          if (b == a) continue;
+          // ContactNeighborFilterFunc (chunk_neighbors_contact.cpp:46-57)
+          const v3 d = s.r[b] - s.r[a];
+          const double d2 = dot(d, d);
+          const double rmax = s.radius[a] + s.radius[b] + s.rcut_inc;
+          if (d2 > 0.0 && d2 < rmax * rmax) fn(b, ghostc);
+        }
+      }
+}
+
+static void enumerate_sphere(Sim& s, uint32_t a, int ci, int cj, int ck, std::vector<Inter>& out) {
+  Inter it;
+  it.i = a; it.id_i = s.id[a]; it.sub_i = 0; it.sub_j = 0; it.swap = 0; it.ghost = 0;
+  // drivers first (nbh_sphere.cu:182-231)
+  for (size_t d = 0; d < s.drivers.size(); d++) {
+    const Driver& D = s.drivers[d];
+    if (D.kind == DRV_UNDEFINED || D.kind == DRV_RSHAPE) continue;
+    it.type = (uint16_t)(4 + D.kind);
+    it.id_j = d; it.j = 0xffffffffu;
+    if (driver_filter(D, s.radius[a] + s.rcut_inc, s.r[a])) out.push_back(it);
+  }
+  it.type = 0;
+  for_each_neighbor(s, ci, cj, ck, a, [&](uint32_t b, bool ghostc) {
+    Inter n = it;
+    n.ghost = 0;
+    if (s.symetric) {  // nbh_sphere.cu:239-263
+      if (s.id[a] >= s.id[b] && !ghostc) return;
+    } else {           // :266-294
+      if (s.id[a] >= s.id[b]) return;
+      if (ghostc) n.ghost = 1;
+    }
+    n.j = b; n.id_j = s.id[b];
+    out.push_back(n);
+  });
+}
+
+static void enumerate_polyhedron(Sim& s, uint32_t a, int ci, int cj, int ck, std::vector<Inter>& out) {
+  const Shape& sa = s.shapes[s.type[a]];
+  const double ha = s.h[a], rV = s.rcut_inc;
+  const v3* va = s.pv(a);
+  Inter it;
+  it.i = a; it.id_i = s.id[a]; it.swap = 0; it.ghost = 0;
+  // drivers (nbh_polyhedron_driver.hpp:205-238): one candidate per vertex passing driver.filter(rVerlet + minkowski, vertex)
+  for (size_t d = 0; d < s.drivers.size(); d++) {
+    const Driver& D = s.drivers[d];
+    if (D.kind == DRV_UNDEFINED || D.kind == DRV_RSHAPE) continue;
+    it.type = (uint16_t)(4 + D.kind);
+    it.id_j = d; it.j = 0xffffffffu; it.sub_j = (uint32_t)-1;
+    for (int k = 0; k < sa.nv(); k++)
+      if (driver_filter(D, rV + ha * sa.radius, va[k])) { it.sub_i = k; out.push_back(it); }
+  }
+  for_each_neighbor(s, ci, cj, ck, a, [&](uint32_t b, bool ghostc) {
+    if (s.id[a] >= s.id[b]) return;  // nbh_polyhedron.cpp:234-236
+    Inter n;
+    n.ghost = ghostc ? 1 : 0;        // :237-239 OwnerGhost
+    const Shape& sb = s.shapes[s.type[b]];
+    const double hb = s.h[b];
+    const v3* vb = s.pv(b);
+    Obb oi = obb_world(sa.obb, s.r[a], s.q[a], ha), oj = obb_world(sb.obb, s.r[b], s.q[b], hb);
+    obb_enlarge(oi, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);   // :268-269
+    if (!obb_intersect(oi, oj)) return;
+    obb_enlarge(oi, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);   // :275-276
+    const double ra = ha * sa.radius, rb = hb * sb.radius;
+    // A -> B, swap = false
+    n.swap = 0; n.i = a; n.id_i = s.id[a]; n.j = b; n.id_j = s.id[b];
+    for (int i = 0; i < sa.nv(); i++) {
+      if (!obb_intersect(oj, obb_point(va[i], ra))) continue;   // :305-310
+      n.sub_i = i;
+      n.type = 0;
+      for (int j = 0; j < sb.nv(); j++) if (filter_vv(rV, va[i], ra, vb[j], rb)) { n.sub_j = j; out.push_back(n); }
+      n.type = 1;
+      for (int j = 0; j < sb.ne(); j++) if (filter_ve(rV, va[i], ra, vb[sb.edges[2 * j]], vb[sb.edges[2 * j + 1]], rb)) { n.sub_j = j; out.push_back(n); }
+      n.type = 2;
+      for (int j = 0; j < sb.nf(); j++) if (filter_vf(rV, va[i], ra, vb, rb, &sb.fidx[sb.foff[j]], sb.fn[j])) { n.sub_j = j; out.push_back(n); }
+    }
+    n.type = 3;
+    for (int i = 0; i < sa.ne(); i++)
+      for (int j = 0; j < sb.ne(); j++)
+        if (filter_ee(rV, va[sa.edges[2 * i]], va[sa.edges[2 * i + 1]], ra, vb[sb.edges[2 * j]], vb[sb.edges[2 * j + 1]], rb)) {
+          n.sub_i = i; n.sub_j = j; out.push_back(n);
+        }
+    // B -> A, swap = true: pi = b, pj = a (owner() stays a, interaction_pair.hpp:75-90)
+    n.swap = 1; n.i = b; n.id_i = s.id[b]; n.j = a; n.id_j = s.id[a];
+    for (int j = 0; j < sb.nv(); j++) {
+      if (!obb_intersect(oi, obb_point(vb[j], rb))) continue;
+      n.sub_i = j;
+      n.type = 1;
+      for (int i = 0; i < sa.ne(); i++) if (filter_ve(rV, vb[j], rb, va[sa.edges[2 * i]], va[sa.edges[2 * i + 1]], ra)) { n.sub_j = i; out.push_back(n); }
+      n.type = 2;
+      for (int i = 0; i < sa.nf(); i++) if (filter_vf(rV, vb[j], rb, va, ra, &sa.fidx[sa.foff[i]], sa.fn[i])) { n.sub_j = i; out.push_back(n); }
+    }
+  });
+}
+
+static void classify(Sim& s) {
+  for (auto& w : s.wave) w.clear();
+  for (size_t k = 0; k < s.inter.size(); k++) s.wave[s.inter[k].type].push_back((uint32_t)k);
+}
+
+static void rebuild(Sim& s, double rcut_inc, int symetric) {
+  s.rcut_inc = rcut_inc;
+  s.symetric = symetric;
+  // history = active records (interaction.hpp:129-136), PartnerGhost excluded; first record wins on duplicate keys
+  std::map<Key, std::pair<v3, v3>> hist;
+  for (const Inter& I : s.inter) {
+    if (I.ghost == 2) continue;
+    if (is_zero(I.ft) && is_zero(I.mom)) continue;
+    hist.emplace(key_of(I), std::make_pair(I.ft, I.mom));
+  }
+  build_grid(s);
+  ghost_refresh(s, true);
+  compute_vertices(s);
+  s.r_backup.assign(s.r.begin(), s.r.begin() + s.nreal);
+  s.q_backup.assign(s.q.begin(), s.q.begin() + s.nreal);
+  s.inter.clear();
+  for (int k = 1; k < s.g[2] - 1; k++)
+    for (int j = 1; j < s.g[1] - 1; j++)
+      for (int i = 1; i < s.g[0] - 1; i++) {
+        const size_t c = s.cell_of(i, j, k);
+        for (uint32_t itp = s.cstart[c]; itp < s.cstart[c + 1]; itp++) {
+          const uint32_t a = s.citems[itp];
+          if (s.cfg.mode == EDB_MODE_SPHERE) enumerate_sphere(s, a, i, j, k, s.inter);
+          else enumerate_polyhedron(s, a, i, j, k, s.inter);
+        }
+      }
+  for (Inter& I : s.inter) {
+    auto h = hist.find(key_of(I));
+    if (h != hist.end()) { I.ft = h->second.first; I.mom = h->second.second; }
+  }
+  classify(s);
+  s.rebuilds++;
+}
+
+// --- contact waves ---------------------------------------------------------------------------------------
+struct Acc {  // force / torque accumulation target
+  Sim& s;
+  bool atomic;
+  void add(v3& dst, v3 a) {
+    if (!atomic) { dst.x += a.x; dst.y += a.y; dst.z += a.z; return; }
+#pragma omp atomic
+    dst.x += a.x;
+#pragma omp atomic
+    dst.y += a.y;
+#pragma omp atomic
+    dst.z += a.z;
+  }
+};
+
+static inline void contact_one(Sim& s, Inter& I, double dt, Acc& acc) {
+  const int t = I.type;
+  const bool poly = s.cfg.mode == EDB_MODE_POLYHEDRON;
+  const uint32_t i = I.i;
+  Contact c;
+  const Params* cp;
+  double meff, reff;
+  v3 pj, vj, wj;
+  const v3 ri = s.r[i];
+  if (t <= 3) {
+    const uint32_t j = I.j;
+    cp = &s.cp_pp(s.group[i], s.group[j]);
+    if (!poly) {
+      c = detect_vv(ri, s.radius[i], s.r[j], s.radius[j]);  // contact_sphere.hpp:143
+    } else {
+      const Shape &si = s.shapes[s.type[i]], &sj = s.shapes[s.type[j]];
+      const v3 *vi = s.pv(i), *vj_ = s.pv(j);
+      const double rmi = s.h[i] * si.radius, rmj = s.h[j] * sj.radius;
+      if (t == 0) c = detect_vv(vi[I.sub_i], rmi, vj_[I.sub_j], rmj);
+      else if (t == 1) c = detect_ve(vi[I.sub_i], rmi, vj_[sj.edges[2 * I.sub_j]], vj_[sj.edges[2 * I.sub_j + 1]], rmj);
+      else if (t == 2) c = detect_vf(vi[I.sub_i], rmi, vj_, rmj, &sj.fidx[sj.foff[I.sub_j]], sj.fn[I.sub_j]);
+      else c = detect_ee(vi[si.edges[2 * I.sub_i]], vi[si.edges[2 * I.sub_i + 1]], rmi, vj_[sj.edges[2 * I.sub_j]], vj_[sj.edges[2 * I.sub_j + 1]], rmj);
+    }
+    pj = s.r[j]; vj = s.v[j]; wj = s.w[j];
+    if (!poly) { meff = (s.mass[i] * s.mass[j]) / (s.mass[i] + s.mass[j]); reff = (s.radius[i] * s.radius[j]) / (s.radius[i] + s.radius[j]); }
+    else {
+      const double rmi = s.h[i] * s.shapes[s.type[i]].radius, rmj = s.h[j] * s.shapes[s.type[j]].radius;
+      meff = (s.mass[i] * s.mass[j]) / (s.mass[i] + s.mass[j]); reff = (rmi * rmj) / (rmi + rmj);  // contact.hpp:183
+    }
+  } else {
+    const Driver& D = s.drivers[I.id_j];
+    cp = &s.cp_pd(s.group[i], (uint32_t)I.id_j);
+    if (!poly) { c = driver_detect(D, s.radius[i], ri); reff = s.radius[i]; }              // contact_sphere.hpp:248,270
+    else { const Shape& si = s.shapes[s.type[i]]; const double rm = s.h[i] * si.radius; c = driver_detect(D, rm, s.pv(i)[I.sub_i]); reff = rm; }  // contact.hpp:262,285
+    meff = s.mass[i];
+    pj = D.center; vj = D.vel; wj = D.vrot;
+  }
+  bool contact = c.hit;
+  if (s.law == LAW_COHESIVE) contact = (contact || c.dn <= cp->dncut);
+  v3 fn{0, 0, 0};
+  double dn = c.dn;
+  if (contact) {
+    v3 f{0, 0, 0};
+    contact_force(s.law, c.dn, c.n, dt, *cp, meff, reff, I.ft, c.cp, ri, s.v[i], f, I.mom, s.w[i], pj, vj, wj);
+    fn = f - I.ft;
+    acc.add(s.mom[i], moments(c.cp, ri, f, I.mom));
+    acc.add(s.f[i], f);
+    if (t <= 3) {
+      if (poly || s.symetric) {
+        const uint32_t j = I.j;
+        acc.add(s.mom[j], moments(c.cp, pj, -f, -I.mom));
+        acc.add(s.f[j], -f);
+      }
+    } else if (s.drivers[I.id_j].need_forces) {
+      acc.add(s.drivers[I.id_j].forces, -f);
+    }
+  } else {
+    I.ft = {0, 0, 0}; I.mom = {0, 0, 0};
+    dn = 0;
+  }
+  I.dn = dn; I.cp = c.cp; I.fn = fn;
+}
+
+static void contact_all(Sim& s, double dt) {
+  const bool par = s.omp_threads > 1;
+  Acc acc{s, par};
+  for (int t = 0; t < EDB_NTYPES; t++) {
+    auto& w = s.wave[t];
+    const long n = (long)w.size();
+    if (!par) {
+      for (long k = 0; k < n; k++) contact_one(s, s.inter[w[k]], dt, acc);
+    } else {
+#pragma omp parallel for schedule(static) num_threads(s.omp_threads)
+      for (long k = 0; k < n; k++) contact_one(s, s.inter[w[k]], dt, acc);
+    }
+    s.interaction_updates += (uint64_t)n;
+  }
+}
+
+// --- per-particle operators --------------------------------------------------------------------------------
+#define PFOR(n) _Pragma("omp parallel for schedule(static) num_threads(s.omp_threads) if (s.omp_threads > 1)") for (long p = 0; p < (long)(n); p++)
+
+static void prolog(Sim& s, double dt) {
+  const double dt2 = dt * dt * 0.5, hdt = dt * 0.5;
+  PFOR(s.nreal) {
+    // PushVec3SecondOrderFunctor{dt, dt^2/2}: r += v*dt + a*dt2 ; PushVec3FirstOrderFunctor{dt/2}: v += a*dt/2  (exaNBody, unpinned R2)
+    v3 &r = s.r[p], &v = s.v[p];
+    const v3 a = s.f[p];
+    r.x += v.x * dt + a.x * dt2; r.y += v.y * dt + a.y * dt2; r.z += v.z * dt + a.z * dt2;
+    v.x += a.x * hdt; v.y += a.y * hdt; v.z += a.z * hdt;
+    // push_to_quaternion.hpp:26-38
+    q4& Q = s.q[p];
+    const q4 dq = qdot(Q, s.w[p]);
+    Q = {Q.w + dq.w * dt, Q.x + dq.x * dt, Q.y + dq.y * dt, Q.z + dq.z * dt};
+    const double nn = std::sqrt(Q.w * Q.w + Q.x * Q.x + Q.y * Q.y + Q.z * Q.z);
+    Q = {Q.w / nn, Q.x / nn, Q.y / nn, Q.z / nn};
+    s.w[p] = s.w[p] + hdt * s.arot[p];
+  }
+}
+static void push_to_quaternion(Sim& s, double dt) {
+  const double hdt = dt * 0.5;
+  PFOR(s.nreal) {
+    q4& Q = s.q[p];
+    const q4 dq = qdot(Q, s.w[p]);
+    Q = {Q.w + dq.w * dt, Q.x + dq.x * dt, Q.y + dq.y * dt, Q.z + dq.z * dt};
+    const double nn = std::sqrt(Q.w * Q.w + Q.x * Q.x + Q.y * Q.y + Q.z * Q.z);
+    Q = {Q.w / nn, Q.x / nn, Q.y / nn, Q.z / nn};
+    s.w[p] = s.w[p] + hdt * s.arot[p];
+  }
+}
+static void angular_accel(Sim& s) {  // angular_acceleration.hpp:27-43
+  PFOR(s.nreal) {
+    const q4 Qi = qconj(s.q[p]);
+    const v3 o = qrot(Qi, s.w[p]), M = qrot(Qi, s.mom[p]), I = s.inertia[p];
+    const v3 dw{(M.x - (I.z - I.y) * o.y * o.z) / I.x, (M.y - (I.x - I.z) * o.z * o.x) / I.y, (M.z - (I.y - I.x) * o.x * o.y) / I.z};
+    s.arot[p] = qrot(s.q[p], dw);
+  }
+}
+static void angular_vel(Sim& s, double dt) {  // angular_velocity.hpp:27-33
+  const double hdt = dt * 0.5;
+  PFOR(s.nreal) s.w[p] = s.w[p] + s.arot[p] * hdt;
+}
+static void epilog(Sim& s, double dt) {
+  const double hdt = dt * 0.5;
+  PFOR(s.nreal) {
+    const q4 Qi = qconj(s.q[p]);
+    const v3 o = qrot(Qi, s.w[p]), M = qrot(Qi, s.mom[p]), I = s.inertia[p];
+    const v3 dw{(M.x - (I.z - I.y) * o.y * o.z) / I.x, (M.y - (I.x - I.z) * o.z * o.x) / I.y, (M.z - (I.y - I.x) * o.x * o.y) / I.z};
+    s.arot[p] = qrot(s.q[p], dw);
+    s.w[p] = s.w[p] + s.arot[p] * hdt;
+    v3& v = s.v[p];
+    const v3 a = s.f[p];
+    v.x += a.x * hdt; v.y += a.y * hdt; v.z += a.z * hdt;
+  }
+}
+static void reset_fm(Sim& s) {
+  PFOR(s.ntot) { s.f[p] = {0, 0, 0}; s.mom[p] = {0, 0, 0}; }
+  for (auto& d : s.drivers) d.forces = {0, 0, 0};
+}
+static void gravity(Sim& s, const double* g) {
+  PFOR(s.nreal) { s.f[p].x += g[0] * s.mass[p]; s.f[p].y += g[1] * s.mass[p]; s.f[p].z += g[2] * s.mass[p]; }
+}
+static void force_to_accel(Sim& s) {
+  PFOR(s.nreal) { s.f[p].x /= s.mass[p]; s.f[p].y /= s.mass[p]; s.f[p].z /= s.mass[p]; }
+}
+// particle_displ_over (exaNBody, unpinned R3) / vertex_displ_over (backup_dem.hpp:66-100): count of particles
+// (vertices) whose displacement since the last rebuild is >= threshold
+static uint64_t displ_over(Sim& s, double thr) {
+  uint64_t n = 0;
+  const double t2 = thr * thr;
+  for (size_t p = 0; p < s.nreal && p < s.r_backup.size(); p++) {
+    if (s.cfg.mode == EDB_MODE_SPHERE) {
+      const v3 d = s.r[p] - s.r_backup[p];
+      if (dot(d, d) >= t2) n++;
+    } else {
+      const Shape& sh = s.shapes[s.type[p]];
+      for (int k = 0; k < sh.nv(); k++) {
+        const v3 vo = s.r_backup[p] + qrot(s.q_backup[p], s.h[p] * sh.v[k]);
+        const v3 vn = s.r[p] + qrot(s.q[p], s.h[p] * sh.v[k]);
+        const v3 d = vn - vo;
+        if (dot(d, d) >= t2) n++;
+      }
+    }
+  }
+  return n;
+}
+
+}  // namespace
+
+// =============================================================================================================
+extern "C" {
+
+struct orc_sim;  // opaque == Sim
+
+int orc_create(const edb_config* cfg, orc_sim** out) {
+  Sim* s = new Sim();
+  s->cfg = *cfg;
+  *out = (orc_sim*)s;
+  return 0;
+}
+int orc_destroy(orc_sim* h) { delete (Sim*)h; return 0; }
+int orc_set_threads(orc_sim* h, int n) { ((Sim*)h)->omp_threads = n < 1 ? 1 : n; return 0; }
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+static Params to_params(const edb_contact_params& c) {
+  Params p; p.kn = c.kn; p.kt = c.kt; p.kr = c.kr; p.mu = c.mu; p.damp = c.damp_rate; p.fc = c.fc; p.dncut = c.dncut; p.gamma = c.gamma;
+  return p;
+}
+int orc_set_contact_params(orc_sim* h, const edb_contact_params* a, const edb_contact_params* b) {
+  Sim& s = *(Sim*)h;
+  s.multimat = false;
+  s.pp.assign(1, to_params(*a));
+  s.pd.assign(1, b ? to_params(*b) : Params());
+  return 0;
+}
+int orc_set_contact_params_multimat(orc_sim* h, int32_t n_groups, const edb_contact_params* pp, int32_t n_drivers, const edb_contact_params* pd) {
+  Sim& s = *(Sim*)h;
+  s.multimat = true;
+  s.n_groups = n_groups;
+  s.pp.clear(); s.pd.clear();
+  for (int i = 0; i < n_groups * n_groups; i++) s.pp.push_back(to_params(pp[i]));
+  for (int i = 0; i < n_groups * n_drivers; i++) s.pd.push_back(to_params(pd[i]));
+  return 0;
+}
+int orc_set_law(orc_sim* h, int32_t law) { ((Sim*)h)->law = law; return 0; }
+int orc_set_drivers(orc_sim* h, int32_t n, const edb_driver* d) {
+  Sim& s = *(Sim*)h;
+  s.drivers.clear();
+  for (int i = 0; i < n; i++) {
+    Driver D;
+    D.kind = d[i].kind; D.need_forces = d[i].need_forces; D.radius = d[i].radius;
+    D.axis = {d[i].axis[0], d[i].axis[1], d[i].axis[2]};
+    D.center = {d[i].center[0], d[i].center[1], d[i].center[2]};
+    if (D.kind == DRV_CYLINDER) D.center = cmul(D.axis, D.center);  // cylinder.hpp:104
+    D.offset = d[i].offset; D.normal = {d[i].normal[0], d[i].normal[1], d[i].normal[2]};
+    D.vel = {d[i].vel[0], d[i].vel[1], d[i].vel[2]}; D.vrot = {d[i].vrot[0], d[i].vrot[1], d[i].vrot[2]};
+    D.shape = d[i].shape;
+    s.drivers.push_back(D);
+  }
+  return 0;
+}
+int orc_set_shapes(orc_sim* h, int32_t n, const edb_shape* sh) {
+  Sim& s = *(Sim*)h;
+  s.shapes.clear();
+  s.nvmax = 0;
+  for (int i = 0; i < n; i++) {
+    Shape S;
+    for (int k = 0; k < sh[i].nv; k++) S.v.push_back({sh[i].vertices[3 * k], sh[i].vertices[3 * k + 1], sh[i].vertices[3 * k + 2]});
+    S.edges.assign(sh[i].edges, sh[i].edges + 2 * sh[i].ne);
+    int pos = 0;
+    for (int f = 0; f < sh[i].nf; f++) {
+      const int nfv = sh[i].faces[pos++];
+      S.foff.push_back((int)S.fidx.size()); S.fn.push_back(nfv);
+      for (int k = 0; k < nfv; k++) S.fidx.push_back(sh[i].faces[pos++]);
+    }
+    const double* o = sh[i].obb;
+    S.obb = Obb{{o[0], o[1], o[2]}, {o[3], o[4], o[5]}, {o[6], o[7], o[8]}, {o[9], o[10], o[11]}, {o[12], o[13], o[14]}};
+    S.radius = sh[i].radius;
+    s.nvmax = std::max(s.nvmax, S.nv());
+    s.shapes.push_back(S);
+  }
+  return 0;
+}
+
+#define LD3(dst, a, b, c) if (P->a && P->b && P->c) for (size_t p = 0; p < n; p++) s.dst[p] = {P->a[p], P->b[p], P->c[p]}
+#define ST3(src, a, b, c) if (P->a && P->b && P->c) for (size_t p = 0; p < n; p++) { P->a[p] = s.src[p].x; P->b[p] = s.src[p].y; P->c[p] = s.src[p].z; }
+int orc_upload_particles(orc_sim* h, const edb_particles* P) {
+  Sim& s = *(Sim*)h;
+  const size_t n = P->n;
+  s.nreal = n;
+  s.gsrc.clear(); s.gshift.clear();
+  s.resize_particles(n);
+  for (size_t p = 0; p < n; p++) {
+    s.f[p] = {0, 0, 0}; s.mom[p] = {0, 0, 0}; s.w[p] = {0, 0, 0}; s.arot[p] = {0, 0, 0}; s.v[p] = {0, 0, 0};
+    s.inertia[p] = {1, 1, 1}; s.q[p] = {1, 0, 0, 0}; s.h[p] = 1.0; s.mass[p] = 1.0; s.radius[p] = 0.5;
+    s.id[p] = p; s.type[p] = 0; s.group[p] = 0;
+  }
+  LD3(r, rx, ry, rz); LD3(v, vx, vy, vz); LD3(f, fx, fy, fz); LD3(mom, momx, momy, momz); LD3(w, vrotx, vroty, vrotz);
+  LD3(arot, arotx, aroty, arotz); LD3(inertia, inertiax, inertiay, inertiaz);
+  if (P->qw) for (size_t p = 0; p < n; p++) s.q[p] = {P->qw[p], P->qx[p], P->qy[p], P->qz[p]};
+  if (P->mass) std::copy(P->mass, P->mass + n, s.mass.begin());
+  if (P->homothety) std::copy(P->homothety, P->homothety + n, s.h.begin());
+  if (P->radius) std::copy(P->radius, P->radius + n, s.radius.begin());
+  if (P->id) std::copy(P->id, P->id + n, s.id.begin());
+  if (P->type) std::copy(P->type, P->type + n, s.type.begin());
+  if (P->group) std::copy(P->group, P->group + n, s.group.begin());
+  s.inter.clear();
+  for (auto& w : s.wave) w.clear();
+  return 0;
+}
+int orc_download_particles(orc_sim* h, edb_particles* P) {
+  Sim& s = *(Sim*)h;
+  const size_t n = s.nreal;
+  P->n = n;
+  ST3(r, rx, ry, rz) ST3(v, vx, vy, vz) ST3(f, fx, fy, fz) ST3(mom, momx, momy, momz) ST3(w, vrotx, vroty, vrotz)
+  ST3(arot, arotx, aroty, arotz) ST3(inertia, inertiax, inertiay, inertiaz)
+  if (P->qw) for (size_t p = 0; p < n; p++) { P->qw[p] = s.q[p].w; P->qx[p] = s.q[p].x; P->qy[p] = s.q[p].y; P->qz[p] = s.q[p].z; }
+  if (P->mass) std::copy(s.mass.begin(), s.mass.begin() + n, P->mass);
+  if (P->homothety) std::copy(s.h.begin(), s.h.begin() + n, P->homothety);
+  if (P->radius) std::copy(s.radius.begin(), s.radius.begin() + n, P->radius);
+  if (P->id) std::copy(s.id.begin(), s.id.begin() + n, P->id);
+  if (P->type) std::copy(s.type.begin(), s.type.begin() + n, P->type);
+  if (P->group) std::copy(s.group.begin(), s.group.begin() + n, P->group);
+  return 0;
+}
+int orc_num_particles(orc_sim* h, uint64_t* nr, uint64_t* ng) {
+  Sim& s = *(Sim*)h;
+  if (nr) *nr = s.nreal;
+  if (ng) *ng = s.ntot - s.nreal;
+  return 0;
+}
+
+int orc_update_particle_neighbors(orc_sim* h, double rcut_inc, int32_t symetric) { rebuild(*(Sim*)h, rcut_inc, symetric); return 0; }
+int orc_ghost_update_rq(orc_sim* h) { ghost_refresh(*(Sim*)h, false); return 0; }
+int orc_compute_vertices(orc_sim* h) { compute_vertices(*(Sim*)h); return 0; }
+int orc_reset_force_moment(orc_sim* h) { reset_fm(*(Sim*)h); return 0; }
+int orc_gravity_force(orc_sim* h, const double* g) { gravity(*(Sim*)h, g); return 0; }
+int orc_contact_sphere(orc_sim* h, double dt) { contact_all(*(Sim*)h, dt); return 0; }
+int orc_contact_polyhedron(orc_sim* h, double dt) { contact_all(*(Sim*)h, dt); return 0; }
+int orc_force_to_accel(orc_sim* h) { force_to_accel(*(Sim*)h); return 0; }
+int orc_combined_compute_prolog(orc_sim* h, double dt) { prolog(*(Sim*)h, dt); return 0; }
+int orc_combined_compute_epilog(orc_sim* h, double dt) { epilog(*(Sim*)h, dt); return 0; }
+int orc_push_to_quaternion(orc_sim* h, double dt) { push_to_quaternion(*(Sim*)h, dt); return 0; }
+int orc_push_to_angular_velocity(orc_sim* h, double dt) { angular_vel(*(Sim*)h, dt); return 0; }
+int orc_push_to_angular_acceleration(orc_sim* h) { angular_accel(*(Sim*)h); return 0; }
+int orc_freeze_particles(orc_sim* h) {
+  Sim& s = *(Sim*)h;
+  for (size_t p = 0; p < s.nreal; p++) { s.f[p] = {0, 0, 0}; s.mom[p] = {0, 0, 0}; s.v[p] = {0, 0, 0}; s.w[p] = {0, 0, 0}; }
+  return 0;
+}
+int orc_displ_over(orc_sim* h, double thr, uint64_t* over) { *over = displ_over(*(Sim*)h, thr); return 0; }
+int orc_compute_driver_force_moment(orc_sim* h, double* forces, double* moments) {
+  // compute_driver_force_moment.cu:34-54: per driver, sum of -(fn+ft) and of cross(cp - center, -(fn+ft)) over driver waves
+  Sim& s = *(Sim*)h;
+  for (size_t d = 0; d < s.drivers.size(); d++) for (int k = 0; k < 3; k++) { forces[3 * d + k] = 0; moments[3 * d + k] = 0; }
+  for (int t = 4; t <= 12; t++)
+    for (uint32_t k : s.wave[t]) {
+      const Inter& I = s.inter[k];
+      const size_t d = I.id_j;
+      const v3 f = -(I.fn + I.ft);
+      const v3 m = cross(I.cp - s.drivers[d].center, f);
+      forces[3 * d] += f.x; forces[3 * d + 1] += f.y; forces[3 * d + 2] += f.z;
+      moments[3 * d] += m.x; moments[3 * d + 1] += m.y; moments[3 * d + 2] += m.z;
+    }
+  return 0;
+}
+
+int orc_run_verlet(orc_sim* h, double dt, const double* g, double rcut_inc, int32_t symetric, int32_t nsteps, int32_t rebuild_every, uint64_t* n_rebuilds) {
+  Sim& s = *(Sim*)h;
+  uint64_t nb = 0;
+  for (int it = 0; it < nsteps; it++) {
+    prolog(s, dt);
+    bool rb;
+    if (rebuild_every > 0) rb = ((it + 1) % rebuild_every) == 0;
+    else if (rebuild_every < 0) rb = false;
+    else rb = displ_over(s, 0.5 * rcut_inc) > 0;
+    if (rb) { rebuild(s, rcut_inc, symetric); nb++; }
+    else { ghost_refresh(s, false); compute_vertices(s); }
+    reset_fm(s);
+    gravity(s, g);
+    contact_all(s, dt);
+    force_to_accel(s);
+    epilog(s, dt);
+    s.particle_steps += s.nreal;
+  }
+  if (n_rebuilds) *n_rebuilds = nb;
+  return 0;
+}
+
+int orc_interaction_counts(orc_sim* h, uint64_t* counts, uint64_t* active) {
+  Sim& s = *(Sim*)h;
+  for (int t = 0; t < EDB_NTYPES; t++) {
+    counts[t] = s.wave[t].size();
+    uint64_t a = 0;
+    for (uint32_t k : s.wave[t]) if (!(is_zero(s.inter[k].ft) && is_zero(s.inter[k].mom))) a++;
+    if (active) active[t] = a;
+  }
+  return 0;
+}
+int orc_export_interactions(orc_sim* h, edb_interaction* out, uint64_t cap, uint64_t* n) {
+  Sim& s = *(Sim*)h;
+  uint64_t k = 0;
+  for (int t = 0; t < EDB_NTYPES; t++)
+    for (uint32_t idx : s.wave[t]) {
+      if (k < cap) {
+        const Inter& I = s.inter[idx];
+        edb_interaction e;
+        memset(&e, 0, sizeof(e));
+        e.id_i = I.id_i; e.id_j = I.id_j; e.sub_i = I.sub_i; e.sub_j = I.sub_j; e.type = I.type; e.swap = I.swap; e.ghost = I.ghost;
+        e.friction[0] = I.ft.x; e.friction[1] = I.ft.y; e.friction[2] = I.ft.z;
+        e.moment[0] = I.mom.x; e.moment[1] = I.mom.y; e.moment[2] = I.mom.z;
+        out[k] = e;
+      }
+      k++;
+    }
+  *n = k;
+  return 0;
+}
+int orc_import_interactions(orc_sim* h, const edb_interaction* in, uint64_t n) {
+  Sim& s = *(Sim*)h;
+  s.inter.clear();
+  for (uint64_t k = 0; k < n; k++) {
+    Inter I;
+    I.id_i = in[k].id_i; I.id_j = in[k].id_j; I.sub_i = in[k].sub_i; I.sub_j = in[k].sub_j; I.type = in[k].type; I.swap = in[k].swap; I.ghost = in[k].ghost;
+    I.ft = {in[k].friction[0], in[k].friction[1], in[k].friction[2]};
+    I.mom = {in[k].moment[0], in[k].moment[1], in[k].moment[2]};
+    s.inter.push_back(I);
+  }
+  for (auto& w : s.wave) w.clear();
+  return 0;
+}
+int orc_get_contact_state(orc_sim* h, int32_t type, double* dn, double* cp, double* fn, double* ft) {
+  Sim& s = *(Sim*)h;
+  size_t k = 0;
+  for (uint32_t idx : s.wave[type]) {
+    const Inter& I = s.inter[idx];
+    if (dn) dn[k] = I.dn;
+    if (cp) { cp[3 * k] = I.cp.x; cp[3 * k + 1] = I.cp.y; cp[3 * k + 2] = I.cp.z; }
+    if (fn) { fn[3 * k] = I.fn.x; fn[3 * k + 1] = I.fn.y; fn[3 * k + 2] = I.fn.z; }
+    if (ft) { ft[3 * k] = I.ft.x; ft[3 * k + 1] = I.ft.y; ft[3 * k + 2] = I.ft.z; }
+    k++;
+  }
+  return 0;
+}
+int orc_get_counters(orc_sim* h, edb_counters* c) {
+  Sim& s = *(Sim*)h;
+  memset(c, 0, sizeof(*c));
+  c->interaction_updates = s.interaction_updates; c->particle_steps = s.particle_steps; c->rebuilds = s.rebuilds;
+  return 0;
+}
+int orc_reset_counters(orc_sim* h) { Sim& s = *(Sim*)h; s.interaction_updates = s.particle_steps = s.rebuilds = 0; return 0; }
+// world vertices of particle p (testing compute_vertices)
+int orc_get_vertices(orc_sim* h, double* out, uint64_t cap_doubles) {
+  Sim& s = *(Sim*)h;
+  const size_t n = s.nreal * (size_t)s.nvmax;
+  for (size_t k = 0; k < n && 3 * k + 2 < cap_doubles; k++) { out[3 * k] = s.verts[k].x; out[3 * k + 1] = s.verts[k].y; out[3 * k + 2] = s.verts[k].z; }
+  return s.nvmax;
+}
+
+// ---- function-level entry points (pinned against oracle/_ref in tests/test_oracle_vs_ref.py) ----------------
+static v3 V(const double* p) { return {p[0], p[1], p[2]}; }
+static int packc(const Contact& c, double* o) { o[0] = c.dn; o[1] = c.n.x; o[2] = c.n.y; o[3] = c.n.z; o[4] = c.cp.x; o[5] = c.cp.y; o[6] = c.cp.z; return c.hit; }
+int orc_filter_vertex_vertex(double rV, const double* vi, double ri, const double* vj, double rj) { return filter_vv(rV, V(vi), ri, V(vj), rj); }
+int orc_detection_vertex_vertex_core(const double* pi, double ri, const double* pj, double rj, double* o) { return packc(detect_vv(V(pi), ri, V(pj), rj), o); }
+int orc_filter_vertex_edge_core(double rV, const double* vi, double ri, const double* vf, const double* vs, double rj) { return filter_ve(rV, V(vi), ri, V(vf), V(vs), rj); }
+int orc_detection_vertex_edge_core(const double* vi, double ri, const double* vf, const double* vs, double rj, double* o) { return packc(detect_ve(V(vi), ri, V(vf), V(vs), rj), o); }
+int orc_filter_edge_edge_core(double rV, const double* a, const double* b, double ri, const double* c, const double* d, double rj) { return filter_ee(rV, V(a), V(b), ri, V(c), V(d), rj); }
+int orc_detection_edge_edge_core(const double* a, const double* b, double ri, const double* c, const double* d, double rj, double* o) { return packc(detect_ee(V(a), V(b), ri, V(c), V(d), rj), o); }
+int orc_filter_vertex_face(double rV, const double* vi, double ri, int nvj, const double* vaj, double rj, const int* idx, int nf) {
+  std::vector<v3> va(nvj);
+  for (int k = 0; k < nvj; k++) va[k] = V(vaj + 3 * k);
+  return filter_vf(rV, V(vi), ri, va, rj, idx, nf);
+}
+int orc_detection_vertex_face_core(const double* vi, double ri, int nvj, const double* vaj, double rj, const int* idx, int nf, double* o) {
+  std::vector<v3> va(nvj);
+  for (int k = 0; k < nvj; k++) va[k] = V(vaj + 3 * k);
+  return packc(detect_vf(V(vi), ri, va, rj, idx, nf), o);
+}
+void orc_get_vertex(const double* lv, const double* p, double hh, const double* q, double* o) {
+  const v3 r = V(p) + qrot(q4{q[0], q[1], q[2], q[3]}, hh * V(lv));
+  o[0] = r.x; o[1] = r.y; o[2] = r.z;
+}
+static Obb obbf(const double* a) { return Obb{{a[0], a[1], a[2]}, {a[3], a[4], a[5]}, {a[6], a[7], a[8]}, {a[9], a[10], a[11]}, {a[12], a[13], a[14]}}; }
+int orc_obb_intersect(const double* a, const double* b) { return obb_intersect(obbf(a), obbf(b)); }
+void orc_compute_obb(const double* in, const double* pos, const double* q, double hh, double enl, double* o) {
+  Obb r = obb_world(obbf(in), V(pos), q4{q[0], q[1], q[2], q[3]}, hh);
+  obb_enlarge(r, enl);
+  const v3* f = &r.c;
+  for (int k = 0; k < 5; k++) { o[3 * k] = f[k].x; o[3 * k + 1] = f[k].y; o[3 * k + 2] = f[k].z; }
+}
+void orc_contact_force_core(int law, double dn, const double* n, double dt, const double* prm, double meff, double reff, double* ft, const double* cp,
+                            const double* pi, const double* vi, double* f, double* mom, const double* wi, const double* pj, const double* vj, const double* wj) {
+  Params p; p.kn = prm[0]; p.kt = prm[1]; p.kr = prm[2]; p.mu = prm[3]; p.damp = prm[4]; p.fc = prm[5]; p.dncut = prm[6]; p.gamma = prm[7];
+  v3 FT = V(ft), F = V(f), M = V(mom);
+  contact_force(law, dn, V(n), dt, p, meff, reff, FT, V(cp), V(pi), V(vi), F, M, V(wi), V(pj), V(vj), V(wj));
+  ft[0] = FT.x; ft[1] = FT.y; ft[2] = FT.z; f[0] = F.x; f[1] = F.y; f[2] = F.z; mom[0] = M.x; mom[1] = M.y; mom[2] = M.z;
+}
+void orc_compute_moments(const double* cp, const double* p, const double* f, const double* m, double* o) {
+  const v3 r = moments(V(cp), V(p), V(f), V(m));
+  o[0] = r.x; o[1] = r.y; o[2] = r.z;
+}
+static Driver mkdrv(int kind, const double* prm) {
+  Driver d; d.kind = kind;
+  if (kind == 0) { d.radius = prm[0]; d.axis = V(prm + 1); d.center = V(prm + 4); }
+  else if (kind == 1) { d.offset = prm[0]; d.normal = V(prm + 1); }
+  else { d.radius = prm[0]; d.center = V(prm + 1); }
+  return d;
+}
+int orc_driver_filter(int kind, const double* prm, double rcut, const double* p) { return driver_filter(mkdrv(kind, prm), rcut, V(p)); }
+int orc_driver_detector(int kind, const double* prm, double rcut, const double* p, double* o) { return packc(driver_detect(mkdrv(kind, prm), rcut, V(p)), o); }
+
+}  // extern "C"

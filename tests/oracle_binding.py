@@ -1,0 +1,57 @@
+"""Test-only loader of the CPU oracle (oracle/liboracle_dem.so) and of the compiled reference math
+(oracle/_ref/libexadem_refmath.so).  Importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs ONLY — never from the exadem_b200 package."""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+from exadem_b200 import capi
+
+ORACLE_DIR = Path(__file__).resolve().parent.parent / "oracle"
+
+
+def build_oracle(force=False):
+    so = ORACLE_DIR / "liboracle_dem.so"
+    if force or not so.exists() or so.stat().st_mtime < max((ORACLE_DIR / f).stat().st_mtime
+                                                              for f in ("dem_oracle.cpp", "dem_math.hpp")):
+        subprocess.run(["make", "-C", str(ORACLE_DIR), "liboracle_dem.so"], check=True, capture_output=True)
+    return so
+
+
+class OracleLibrary:
+    prefix = "orc_"
+
+    def __init__(self):
+        self.path = build_oracle()
+        self.dll = C.CDLL(str(self.path))
+
+    def fn(self, name):
+        f = getattr(self.dll, self.prefix + name)
+        f.restype = C.c_int
+        return f
+
+
+class OracleEngine(capi.Engine):
+    """Same scripting surface as the product Engine, running the CPU restatement."""
+
+    def set_threads(self, n):
+        self._call("set_threads", C.c_int(n))
+
+    def sync(self):
+        pass
+
+    def set_timing(self, on):
+        pass
+
+    def flush_l2(self):
+        pass
+
+
+def ref_math():
+    """ctypes handle on the reference's own header-only math (None when oracle/_ref was not built)."""
+    so = ORACLE_DIR / "_ref" / "libexadem_refmath.so"
+    if not so.exists():
+        return None
+    return C.CDLL(str(so))
