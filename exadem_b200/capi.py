@@ -4,8 +4,8 @@ This is the Python view of the drop-in boundary (tests, bench.py and examples dr
 It holds NO compute: every method forwards to `libexadem_b200.so` (CUDA, sm_100a).  If the shared library is
 missing the import of :class:`Library` raises — there is no CPU fallback on the product path.
 
-The same struct definitions and the same :class:`Engine` wrapper are reused by the test-only oracle binding
-(tests/oracle_binding.py) with the ``orc_`` symbol prefix, so parity tests run identical scripts on both sides.
+The struct definitions and the :class:`Engine` wrapper are prefix-agnostic, so the test suite can drive its CPU
+checker through the same scripting surface (the checker itself lives outside this package).
 """
 from __future__ import annotations
 

@@ -1,0 +1,1076 @@
+// edb_lib.cu — libexadem_b200.so: context management + the C ABI of include/exadem_b200.h.
+// All compute is in the CUDA kernels of kernels_rebuild.cuh / kernels_step.cuh (sm_100a).  No CPU fallback.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_rebuild.cuh"
+#include "kernels_step.cuh"
+#include "comm.cuh"
+
+using namespace edb;
+
+static thread_local std::string g_create_error;
+static_assert(sizeof(edb_config) == 152 && sizeof(edb_interaction) == 104 && sizeof(edb_contact_params) == 64 &&
+                  sizeof(edb_particles) == 8 + 31 * 8,
+              "C ABI struct layout changed: update include/exadem_b200.h users and exadem_b200/capi.py");
+
+enum Bucket { B_CONTACT = 0, B_GATHER, B_PROLOG, B_EPILOG, B_REBUILD, B_GHOST, B_N };
+
+struct edb_context {
+  edb_config cfg{};
+  cudaStream_t st = nullptr;
+  std::string err;
+  int law = 0;
+  bool timing = false;
+
+  GridDev G{};
+  // particles
+  PArr pa, pb;            // current / scratch (double-buffered for the cell sort)
+  uint32_t nreal = 0, nghost = 0;
+  uint32_t n_old_real = 0;  // #real slots the `prev` waves refer to
+  DevBuf<uint32_t> cidx, cidx2, ccount, cstart, cfill, tmp, new2old, old2new, cbeg, cend;
+  DevBuf<uint32_t> scan_bsum, scan_total;
+  DevBuf<double4> pr_backup, q_backup, vert;
+  bool have_backup = false;
+  // ghost table (host-built, static for a given grid)
+  uint32_t n_gent = 0;
+  DevBuf<uint32_t> g_cell, g_src_cell, g_count, g_off, g_src, g_ent;
+  DevBuf<double> g_shift;
+  // interactions
+  Wave wave[NT], prev[NT];
+  bool have_prev = false;
+  DevBuf<uint32_t> inc_cnt, inc_off, inc;
+  bool have_inc = false;
+  double rcut_inc = 0;
+  int symetric = 1;
+  // parameters
+  ParamsDev prm{};
+  DevBuf<Params> tpp, tpd;
+  std::vector<Driver> h_drv;
+  DevBuf<Driver> drv;
+  // shapes
+  std::vector<ShapeDev> h_sh;
+  DevBuf<ShapeDev> d_sh;
+  DevBuf<v3> d_sv;
+  DevBuf<int> d_se, d_sfoff, d_sfn, d_sfidx;
+  ShapesView S{};
+  // staging for host transfers
+  DevBuf<double> stage;
+  DevBuf<uint64_t> stage_u64;
+  DevBuf<uint32_t> stage_u32;
+  // pinned scalars
+  unsigned long long* h_flag = nullptr;
+  unsigned long long* d_flag = nullptr;
+  uint32_t* h_tot = nullptr;  // pinned, NT+4 entries
+  // counters / timing
+  edb_counters ctr{};
+  std::vector<EventPair> ev_pending, ev_free;
+  // L2 flush scratch
+  DevBuf<double4> l2buf;
+  // multi-GPU
+  Comm comm;
+
+  bool poly() const { return cfg.mode == EDB_MODE_POLYHEDRON; }
+};
+
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                 \
+  do {                                                            \
+    if ((grid) > 0) {                                             \
+      kern<<<(grid), (block), (smem), (ctx)->st>>>(__VA_ARGS__);  \
+      (ctx)->ctr.kernel_launches++;                               \
+    }                                                             \
+  } while (0)
+
+static inline uint32_t nblk(uint64_t n, int b = BLK) { return (uint32_t)((n + b - 1) / b); }
+
+struct ScopedTimer {
+  edb_context* c;
+  EventPair ep;
+  bool on;
+  ScopedTimer(edb_context* c_, int bucket) : c(c_), on(c_->timing) {
+    if (!on) return;
+    if (!c->ev_free.empty()) { ep = c->ev_free.back(); c->ev_free.pop_back(); }
+    else { CK(cudaEventCreate(&ep.a)); CK(cudaEventCreate(&ep.b)); }
+    ep.bucket = bucket;
+    CK(cudaEventRecord(ep.a, c->st));
+  }
+  ~ScopedTimer() {
+    if (!on) return;
+    cudaEventRecord(ep.b, c->st);
+    c->ev_pending.push_back(ep);
+  }
+};
+
+static void resolve_timers(edb_context* c) {
+  if (c->ev_pending.empty()) return;
+  CK(cudaStreamSynchronize(c->st));
+  for (auto& ep : c->ev_pending) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ep.a, ep.b));
+    double* b[B_N] = {&c->ctr.contact_ms, &c->ctr.gather_ms, &c->ctr.prolog_ms, &c->ctr.epilog_ms, &c->ctr.rebuild_ms, &c->ctr.ghost_ms};
+    *b[ep.bucket] += ms;
+    c->ev_free.push_back(ep);
+  }
+  c->ev_pending.clear();
+}
+
+// exclusive scan of n uint32 (out has n+1 entries); returns nothing, total stays on device in out[n]
+static void scan_u32(edb_context* c, const uint32_t* in, uint32_t* out, uint32_t n) {
+  const uint32_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  c->scan_bsum.ensure(nb + 1);
+  c->scan_total.ensure(1);
+  if (n == 0) {
+    CK(cudaMemsetAsync(out, 0, sizeof(uint32_t), c->st));
+    return;
+  }
+  LAUNCH(c, k_scan_reduce, nb, SCAN_T, 0, in, c->scan_bsum.p, n);
+  LAUNCH(c, k_scan_bsum, 1, SCAN_T, 0, c->scan_bsum.p, nb, c->scan_total.p);
+  LAUNCH(c, k_scan_apply, nb, SCAN_T, 0, in, out, c->scan_bsum.p, c->scan_total.p, n);
+}
+
+static int fail(edb_context* c, int code, const std::string& m) {
+  if (c) c->err = m;
+  else g_create_error = m;
+  return code;
+}
+
+#define API_BEGIN(ctx)                                                \
+  if (!(ctx)) return EDB_ERR_INVALID;                                 \
+  try {                                                               \
+    CK(cudaSetDevice((ctx)->cfg.device));
+#define API_END(ctx)                                                                                            \
+  }                                                                                                             \
+  catch (const CudaError& e) {                                                                                  \
+    char b[512];                                                                                                \
+    snprintf(b, sizeof b, "CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e.e), cudaGetErrorString(e.e), \
+             e.file, e.line, e.what);                                                                           \
+    return fail((ctx), EDB_ERR_CUDA, b);                                                                        \
+  }                                                                                                             \
+  catch (const StateError& e) { return fail((ctx), e.code, e.msg); }                                            \
+  catch (const std::exception& e) { return fail((ctx), EDB_ERR_INVALID, e.what()); }                            \
+  return EDB_OK;
+
+// ---------------------------------------------------------------------------------------------------------------
+static void setup_grid(edb_context* c) {
+  GridDev& G = c->G;
+  for (int d = 0; d < 3; d++) {
+    const double len = c->cfg.hi[d] - c->cfg.lo[d];
+    if (!(len > 0) || !(c->cfg.cell_size > 0)) throw StateError{EDB_ERR_INVALID, "empty domain or cell_size <= 0"};
+    G.nc[d] = std::max(1, (int)std::floor(len / c->cfg.cell_size + 1e-9));
+    G.cs[d] = len / G.nc[d];
+    G.g[d] = G.nc[d] + 2;
+    G.lo[d] = c->cfg.lo[d];
+    G.glo[d] = c->cfg.glo[d];
+    G.ghi[d] = c->cfg.ghi[d];
+    G.periodic[d] = c->cfg.periodic[d];
+  }
+  G.ncell = (uint32_t)G.g[0] * G.g[1] * G.g[2];
+  // ghost table: every shell cell mirrors a source cell of some brick (possibly our own, shifted by the period)
+  std::vector<uint32_t> gc, gs;
+  std::vector<double> sh;
+  c->comm.plan_reset(c->cfg, G);
+  for (int k = 0; k < G.g[2]; k++)
+    for (int j = 0; j < G.g[1]; j++)
+      for (int i = 0; i < G.g[0]; i++) {
+        const int idx[3] = {i, j, k};
+        if (!(i == 0 || j == 0 || k == 0 || i == G.g[0] - 1 || j == G.g[1] - 1 || k == G.g[2] - 1)) continue;
+        int src[3];
+        double shift[3];
+        int peer;
+        if (!c->comm.ghost_source(c->cfg, G, idx, src, shift, &peer)) continue;
+        const uint32_t cg = (uint32_t)i + G.g[0] * ((uint32_t)j + G.g[1] * (uint32_t)k);
+        const uint32_t csrc = (uint32_t)src[0] + G.g[0] * ((uint32_t)src[1] + G.g[1] * (uint32_t)src[2]);
+        if (peer == c->cfg.rank) {
+          gc.push_back(cg); gs.push_back(csrc);
+          sh.push_back(shift[0]); sh.push_back(shift[1]); sh.push_back(shift[2]);
+        } else {
+          c->comm.plan_add_remote(peer, cg, csrc, shift);
+        }
+      }
+  c->n_gent = (uint32_t)gc.size();
+  c->g_cell.ensure(gc.size() + 1); c->g_src_cell.ensure(gc.size() + 1); c->g_shift.ensure(sh.size() + 3);
+  c->g_count.ensure(gc.size() + 2); c->g_off.ensure(gc.size() + 2);
+  if (!gc.empty()) {
+    CK(cudaMemcpy(c->g_cell.p, gc.data(), gc.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->g_src_cell.p, gs.data(), gs.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->g_shift.p, sh.data(), sh.size() * 8, cudaMemcpyHostToDevice));
+  }
+  c->comm.plan_finalize();
+  c->ccount.ensure(G.ncell + 1); c->cstart.ensure(G.ncell + 2); c->cfill.ensure(G.ncell + 1);
+  c->cbeg.ensure(G.ncell + 1); c->cend.ensure(G.ncell + 1);
+}
+
+extern "C" int edb_version(void) { return 100; }
+
+extern "C" const char* edb_last_error(const edb_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
+  if (!cfg || !out) return EDB_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, EDB_ERR_NO_DEVICE, "no CUDA device: libexadem_b200 has no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, EDB_ERR_NO_DEVICE, "invalid device ordinal");
+  edb_context* c = new edb_context();
+  c->cfg = *cfg;
+  if (c->cfg.nranks < 1) c->cfg.nranks = 1;
+  try {
+    CK(cudaSetDevice(cfg->device));
+    CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CK(cudaMallocHost(&c->h_flag, sizeof(unsigned long long) * 4));
+    CK(cudaMalloc(&c->d_flag, sizeof(unsigned long long) * 4));
+    CK(cudaMallocHost(&c->h_tot, sizeof(uint32_t) * (NT + 8)));
+    for (int d = 0; d < 3; d++)
+      if (c->cfg.periodic[d] && c->cfg.pgrid[d] <= 1) {
+        const int nc = std::max(1, (int)std::floor((c->cfg.hi[d] - c->cfg.lo[d]) / c->cfg.cell_size + 1e-9));
+        if (nc < 3) throw StateError{EDB_ERR_INVALID, "a periodic axis needs at least 3 cells"};
+      }
+    setup_grid(c);
+    Params z{};
+    c->prm.pp = z; c->prm.pd = z; c->prm.tpp = nullptr; c->prm.tpd = nullptr; c->prm.n_groups = 1; c->prm.n_drivers = 0;
+    c->drv.ensure(1);
+  } catch (const CudaError& e) {
+    char b[512];
+    snprintf(b, sizeof b, "CUDA error %s at %s:%d in %s", cudaGetErrorString(e.e), e.file, e.line, e.what);
+    g_create_error = b;
+    delete c;
+    return EDB_ERR_CUDA;
+  } catch (const StateError& e) {
+    g_create_error = e.msg;
+    delete c;
+    return e.code;
+  }
+  *out = c;
+  return EDB_OK;
+}
+
+extern "C" int edb_destroy(edb_context* c) {
+  if (!c) return EDB_ERR_INVALID;
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->st);
+  c->comm.destroy();
+  c->pa.release(); c->pb.release();
+  for (int t = 0; t < NT; t++) { c->wave[t].release(); c->prev[t].release(); }
+  DevBuf<uint32_t>* u32s[] = {&c->cidx, &c->cidx2, &c->ccount, &c->cstart, &c->cfill, &c->tmp, &c->new2old, &c->old2new, &c->cbeg, &c->cend,
+                              &c->scan_bsum, &c->scan_total, &c->g_cell, &c->g_src_cell, &c->g_count, &c->g_off, &c->g_src, &c->g_ent,
+                              &c->inc_cnt, &c->inc_off, &c->inc, &c->stage_u32};
+  for (auto* b : u32s) b->release();
+  c->pr_backup.release(); c->q_backup.release(); c->vert.release(); c->g_shift.release(); c->tpp.release(); c->tpd.release();
+  c->drv.release(); c->d_sh.release(); c->d_sv.release(); c->d_se.release(); c->d_sfoff.release(); c->d_sfn.release(); c->d_sfidx.release();
+  c->stage.release(); c->stage_u64.release(); c->l2buf.release();
+  for (auto& e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (auto& e : c->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  if (c->h_flag) cudaFreeHost(c->h_flag);
+  if (c->d_flag) cudaFree(c->d_flag);
+  if (c->h_tot) cudaFreeHost(c->h_tot);
+  cudaStreamDestroy(c->st);
+  delete c;
+  return EDB_OK;
+}
+
+extern "C" int edb_sync(edb_context* c) {
+  API_BEGIN(c)
+  CK(cudaStreamSynchronize(c->st));
+  API_END(c)
+}
+
+// ---- parameters -------------------------------------------------------------------------------------------------
+static Params to_params(const edb_contact_params& p) { return Params{p.kn, p.kt, p.kr, p.mu, p.damp_rate, p.fc, p.dncut, p.gamma}; }
+
+extern "C" int edb_set_contact_params(edb_context* c, const edb_contact_params* a, const edb_contact_params* b) {
+  API_BEGIN(c)
+  if (!a) throw StateError{EDB_ERR_INVALID, "config is required"};
+  c->prm.pp = to_params(*a);
+  c->prm.pd = b ? to_params(*b) : Params{};
+  c->prm.tpp = nullptr; c->prm.tpd = nullptr; c->prm.n_groups = 1;
+  API_END(c)
+}
+extern "C" int edb_set_contact_params_multimat(edb_context* c, int32_t ng, const edb_contact_params* pp, int32_t nd, const edb_contact_params* pd) {
+  API_BEGIN(c)
+  if (ng < 1 || !pp) throw StateError{EDB_ERR_INVALID, "multimat table is empty"};
+  std::vector<Params> A, B;
+  for (int i = 0; i < ng * ng; i++) A.push_back(to_params(pp[i]));
+  for (int i = 0; i < ng * nd; i++) B.push_back(to_params(pd[i]));
+  c->tpp.ensure(A.size()); c->tpd.ensure(B.size() + 1);
+  CK(cudaMemcpy(c->tpp.p, A.data(), A.size() * sizeof(Params), cudaMemcpyHostToDevice));
+  if (!B.empty()) CK(cudaMemcpy(c->tpd.p, B.data(), B.size() * sizeof(Params), cudaMemcpyHostToDevice));
+  c->prm.tpp = c->tpp.p; c->prm.tpd = c->tpd.p; c->prm.n_groups = ng; c->prm.n_drivers = nd;
+  API_END(c)
+}
+extern "C" int edb_set_law(edb_context* c, int32_t law) {
+  API_BEGIN(c)
+  if (law < 0 || law > 2) throw StateError{EDB_ERR_INVALID, "unknown law"};
+  c->law = law;
+  API_END(c)
+}
+extern "C" int edb_set_drivers(edb_context* c, int32_t n, const edb_driver* d) {
+  API_BEGIN(c)
+  c->h_drv.clear();
+  for (int i = 0; i < n; i++) {
+    Driver D{};
+    D.kind = d[i].kind; D.need_forces = d[i].need_forces; D.radius = d[i].radius;
+    D.axis = mk3(d[i].axis[0], d[i].axis[1], d[i].axis[2]);
+    D.center = mk3(d[i].center[0], d[i].center[1], d[i].center[2]);
+    if (D.kind == EDB_DRIVER_CYLINDER) D.center = cmul(D.axis, D.center);  // cylinder.hpp:104 (quirk Q11)
+    D.offset = d[i].offset;
+    D.normal = mk3(d[i].normal[0], d[i].normal[1], d[i].normal[2]);
+    D.center_proj = D.offset * D.normal;                                   // surface.hpp:149
+    D.vel = mk3(d[i].vel[0], d[i].vel[1], d[i].vel[2]);
+    D.vrot = mk3(d[i].vrot[0], d[i].vrot[1], d[i].vrot[2]);
+    D.shape = d[i].shape;
+    c->h_drv.push_back(D);
+  }
+  c->drv.ensure(n + 1);
+  if (n) CK(cudaMemcpy(c->drv.p, c->h_drv.data(), n * sizeof(Driver), cudaMemcpyHostToDevice));
+  if (!c->prm.tpd) c->prm.n_drivers = n;
+  API_END(c)
+}
+extern "C" int edb_set_shapes(edb_context* c, int32_t n, const edb_shape* sh) {
+  API_BEGIN(c)
+  std::vector<v3> sv;
+  std::vector<int> se, sfoff, sfn, sfidx;
+  c->h_sh.clear();
+  int nvmax = 0;
+  for (int i = 0; i < n; i++) {
+    ShapeDev S{};
+    S.nv = sh[i].nv; S.ne = sh[i].ne; S.nf = sh[i].nf;
+    S.v0 = (int)sv.size(); S.e0 = (int)se.size() / 2; S.f0 = (int)sfn.size(); S.fi0 = (int)sfidx.size();
+    for (int k = 0; k < S.nv; k++) sv.push_back(mk3(sh[i].vertices[3 * k], sh[i].vertices[3 * k + 1], sh[i].vertices[3 * k + 2]));
+    for (int k = 0; k < 2 * S.ne; k++) se.push_back(sh[i].edges[k]);
+    int pos = 0;
+    for (int f = 0; f < S.nf; f++) {
+      const int nfv = sh[i].faces[pos++];
+      if (nfv < 3 || pos + nfv > sh[i].faces_len) throw StateError{EDB_ERR_INVALID, "malformed face stream"};
+      sfoff.push_back((int)sfidx.size() - S.fi0);
+      sfn.push_back(nfv);
+      for (int k = 0; k < nfv; k++) sfidx.push_back(sh[i].faces[pos++]);
+    }
+    const double* o = sh[i].obb;
+    S.obb = Obb{mk3(o[0], o[1], o[2]), mk3(o[3], o[4], o[5]), mk3(o[6], o[7], o[8]), mk3(o[9], o[10], o[11]), mk3(o[12], o[13], o[14])};
+    S.radius = sh[i].radius;
+    nvmax = std::max(nvmax, S.nv);
+    c->h_sh.push_back(S);
+  }
+  c->d_sh.ensure(n + 1); c->d_sv.ensure(sv.size() + 1); c->d_se.ensure(se.size() + 1); c->d_sfoff.ensure(sfoff.size() + 1);
+  c->d_sfn.ensure(sfn.size() + 1); c->d_sfidx.ensure(sfidx.size() + 1);
+  CK(cudaMemcpy(c->d_sh.p, c->h_sh.data(), n * sizeof(ShapeDev), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_sv.p, sv.data(), sv.size() * sizeof(v3), cudaMemcpyHostToDevice));
+  if (!se.empty()) CK(cudaMemcpy(c->d_se.p, se.data(), se.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (!sfn.empty()) {
+    CK(cudaMemcpy(c->d_sfoff.p, sfoff.data(), sfoff.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_sfn.p, sfn.data(), sfn.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_sfidx.p, sfidx.data(), sfidx.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  c->S = ShapesView{c->d_sh.p, c->d_sv.p, c->d_se.p, c->d_sfoff.p, c->d_sfn.p, c->d_sfidx.p, nvmax};
+  API_END(c)
+}
+
+// ---- host <-> device particle transfer ------------------------------------------------------------------------------
+// staging layout: field-major blocks of n doubles
+__global__ void k_pack_upload(PView P, const double* __restrict__ s, const uint64_t* __restrict__ id, const uint32_t* __restrict__ type,
+                              const uint32_t* __restrict__ group, uint32_t n, unsigned long long have) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  auto F = [&](int f, double dflt) { return (have >> f) & 1ull ? s[(size_t)f * n + p] : dflt; };
+  // field order = edb_particles: rx ry rz vx vy vz fx fy fz mass homothety radius qw qx qy qz mom(3) vrot(3) arot(3) inertia(3)
+  P.pr[p] = make_double4(F(0, 0), F(1, 0), F(2, 0), F(11, 0.5));
+  P.vm[p] = make_double4(F(3, 0), F(4, 0), F(5, 0), F(9, 1.0));
+  const unsigned long long tg = (unsigned long long)(type ? type[p] : 0u) | ((unsigned long long)(group ? group[p] : 0u) << 32);
+  P.wg[p] = make_double4(F(19, 0), F(20, 0), F(21, 0), __longlong_as_double((long long)tg));
+  P.q[p] = make_double4(F(12, 1.0), F(13, 0), F(14, 0), F(15, 0));
+  P.fx[p] = F(6, 0); P.fy[p] = F(7, 0); P.fz[p] = F(8, 0);
+  P.mx[p] = F(16, 0); P.my[p] = F(17, 0); P.mz[p] = F(18, 0);
+  P.ax[p] = F(22, 0); P.ay[p] = F(23, 0); P.az[p] = F(24, 0);
+  P.ix[p] = F(25, 1.0); P.iy[p] = F(26, 1.0); P.iz[p] = F(27, 1.0);
+  P.h[p] = F(10, 1.0);
+  P.id[p] = id ? id[p] : (uint64_t)p;
+  P.orig[p] = p;
+}
+__global__ void k_unpack_download(PView P, double* __restrict__ s, uint64_t* __restrict__ id, uint32_t* __restrict__ type,
+                                  uint32_t* __restrict__ group, uint32_t n) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t o = P.orig[p];
+  const double4 r = P.pr[p], v = P.vm[p], w = P.wg[p], q = P.q[p];
+  auto W = [&](int f, double val) { s[(size_t)f * n + o] = val; };
+  W(0, r.x); W(1, r.y); W(2, r.z); W(3, v.x); W(4, v.y); W(5, v.z); W(6, P.fx[p]); W(7, P.fy[p]); W(8, P.fz[p]);
+  W(9, v.w); W(10, P.h[p]); W(11, r.w); W(12, q.x); W(13, q.y); W(14, q.z); W(15, q.w);
+  W(16, P.mx[p]); W(17, P.my[p]); W(18, P.mz[p]); W(19, w.x); W(20, w.y); W(21, w.z);
+  W(22, P.ax[p]); W(23, P.ay[p]); W(24, P.az[p]); W(25, P.ix[p]); W(26, P.iy[p]); W(27, P.iz[p]);
+  id[o] = P.id[p];
+  const unsigned long long tg = (unsigned long long)__double_as_longlong(w.w);
+  type[o] = (uint32_t)(tg & 0xffffffffu);
+  group[o] = (uint32_t)(tg >> 32);
+}
+// dynamic subset in upload order: 13 inputs (r, v, vrot, q)
+__global__ void k_scatter_dynamic(PView P, const double* __restrict__ s, uint32_t n) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const size_t o = P.orig[p];
+  double4 r = P.pr[p], v = P.vm[p], w = P.wg[p];
+  r.x = s[0 * (size_t)n + o]; r.y = s[1 * (size_t)n + o]; r.z = s[2 * (size_t)n + o];
+  v.x = s[3 * (size_t)n + o]; v.y = s[4 * (size_t)n + o]; v.z = s[5 * (size_t)n + o];
+  w.x = s[6 * (size_t)n + o]; w.y = s[7 * (size_t)n + o]; w.z = s[8 * (size_t)n + o];
+  P.pr[p] = r; P.vm[p] = v; P.wg[p] = w;
+  P.q[p] = make_double4(s[9 * (size_t)n + o], s[10 * (size_t)n + o], s[11 * (size_t)n + o], s[12 * (size_t)n + o]);
+}
+// 22 outputs: r v vrot q f mom arot
+__global__ void k_gather_dynamic(PView P, double* __restrict__ s, uint32_t n) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const size_t o = P.orig[p];
+  const double4 r = P.pr[p], v = P.vm[p], w = P.wg[p], q = P.q[p];
+  const double vals[22] = {r.x, r.y, r.z, v.x, v.y, v.z, w.x, w.y, w.z, q.x, q.y, q.z, q.w, P.fx[p], P.fy[p], P.fz[p],
+                           P.mx[p], P.my[p], P.mz[p], P.ax[p], P.ay[p], P.az[p]};
+#pragma unroll
+  for (int f = 0; f < 22; f++) s[(size_t)f * n + o] = vals[f];
+}
+
+static double* const* field_ptrs(const edb_particles* P, double* out[28]) {
+  double* f[28] = {P->rx, P->ry, P->rz, P->vx, P->vy, P->vz, P->fx, P->fy, P->fz, P->mass, P->homothety, P->radius, P->qw, P->qx,
+                   P->qy, P->qz, P->momx, P->momy, P->momz, P->vrotx, P->vroty, P->vrotz, P->arotx, P->aroty, P->arotz,
+                   P->inertiax, P->inertiay, P->inertiaz};
+  for (int i = 0; i < 28; i++) out[i] = f[i];
+  return out;
+}
+
+static void clear_interactions(edb_context* c) {
+  for (int t = 0; t < NT; t++) { c->wave[t].n = 0; c->prev[t].n = 0; }
+  c->have_prev = false;
+  c->have_inc = false;
+  c->have_backup = false;
+}
+
+extern "C" int edb_upload_particles(edb_context* c, const edb_particles* P) {
+  API_BEGIN(c)
+  if (!P || !P->rx || !P->ry || !P->rz) throw StateError{EDB_ERR_INVALID, "positions are required"};
+  const uint64_t n = P->n;
+  if (n >= (1ull << 31)) throw StateError{EDB_ERR_CAPACITY, "too many particles for one GPU context"};
+  c->pa.ensure(n + 1, false, c->st);
+  c->stage.ensure(28 * n + 1); c->stage_u64.ensure(n + 1); c->stage_u32.ensure(2 * n + 1);
+  double* f[28];
+  field_ptrs(P, f);
+  unsigned long long have = 0;
+  for (int i = 0; i < 28; i++)
+    if (f[i]) {
+      have |= 1ull << i;
+      CK(cudaMemcpyAsync(c->stage.p + (size_t)i * n, f[i], n * 8, cudaMemcpyHostToDevice, c->st));
+    }
+  if (P->id) CK(cudaMemcpyAsync(c->stage_u64.p, P->id, n * 8, cudaMemcpyHostToDevice, c->st));
+  if (P->type) CK(cudaMemcpyAsync(c->stage_u32.p, P->type, n * 4, cudaMemcpyHostToDevice, c->st));
+  if (P->group) CK(cudaMemcpyAsync(c->stage_u32.p + n, P->group, n * 4, cudaMemcpyHostToDevice, c->st));
+  LAUNCH(c, k_pack_upload, nblk(n), BLK, 0, view(c->pa), c->stage.p, P->id ? c->stage_u64.p : nullptr,
+         P->type ? c->stage_u32.p : nullptr, P->group ? c->stage_u32.p + n : nullptr, (uint32_t)n, have);
+  CK(cudaStreamSynchronize(c->st));
+  c->nreal = (uint32_t)n;
+  c->nghost = 0;
+  clear_interactions(c);
+  API_END(c)
+}
+
+extern "C" int edb_download_particles(edb_context* c, edb_particles* P) {
+  API_BEGIN(c)
+  const uint64_t n = c->nreal;
+  if (!P) throw StateError{EDB_ERR_INVALID, "null particle view"};
+  P->n = n;
+  c->stage.ensure(28 * n + 1); c->stage_u64.ensure(n + 1); c->stage_u32.ensure(2 * n + 1);
+  LAUNCH(c, k_unpack_download, nblk(n), BLK, 0, view(c->pa), c->stage.p, c->stage_u64.p, c->stage_u32.p, c->stage_u32.p + n, (uint32_t)n);
+  double* f[28];
+  field_ptrs(P, f);
+  for (int i = 0; i < 28; i++)
+    if (f[i]) CK(cudaMemcpyAsync(f[i], c->stage.p + (size_t)i * n, n * 8, cudaMemcpyDeviceToHost, c->st));
+  if (P->id) CK(cudaMemcpyAsync(P->id, c->stage_u64.p, n * 8, cudaMemcpyDeviceToHost, c->st));
+  if (P->type) CK(cudaMemcpyAsync(P->type, c->stage_u32.p, n * 4, cudaMemcpyDeviceToHost, c->st));
+  if (P->group) CK(cudaMemcpyAsync(P->group, c->stage_u32.p + n, n * 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  API_END(c)
+}
+
+extern "C" int edb_upload_dynamic(edb_context* c, const edb_particles* P) {
+  API_BEGIN(c)
+  const uint64_t n = c->nreal;
+  if (!P || P->n != n) throw StateError{EDB_ERR_INVALID, "particle count mismatch"};
+  c->stage.ensure(28 * n + 1);
+  double* f[13] = {P->rx, P->ry, P->rz, P->vx, P->vy, P->vz, P->vrotx, P->vroty, P->vrotz, P->qw, P->qx, P->qy, P->qz};
+  for (int i = 0; i < 13; i++) {
+    if (!f[i]) throw StateError{EDB_ERR_INVALID, "upload_dynamic needs r, v, vrot and orient"};
+    CK(cudaMemcpyAsync(c->stage.p + (size_t)i * n, f[i], n * 8, cudaMemcpyHostToDevice, c->st));
+  }
+  LAUNCH(c, k_scatter_dynamic, nblk(n), BLK, 0, view(c->pa), c->stage.p, (uint32_t)n);
+  API_END(c)
+}
+extern "C" int edb_download_dynamic(edb_context* c, edb_particles* P) {
+  API_BEGIN(c)
+  const uint64_t n = c->nreal;
+  if (!P || P->n != n) throw StateError{EDB_ERR_INVALID, "particle count mismatch"};
+  c->stage.ensure(28 * n + 1);
+  LAUNCH(c, k_gather_dynamic, nblk(n), BLK, 0, view(c->pa), c->stage.p, (uint32_t)n);
+  double* f[22] = {P->rx, P->ry, P->rz, P->vx, P->vy, P->vz, P->vrotx, P->vroty, P->vrotz, P->qw, P->qx, P->qy, P->qz,
+                   P->fx, P->fy, P->fz, P->momx, P->momy, P->momz, P->arotx, P->aroty, P->arotz};
+  for (int i = 0; i < 22; i++)
+    if (f[i]) CK(cudaMemcpyAsync(f[i], c->stage.p + (size_t)i * n, n * 8, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  API_END(c)
+}
+
+extern "C" int edb_num_particles(edb_context* c, uint64_t* nr, uint64_t* ng) {
+  if (!c) return EDB_ERR_INVALID;
+  if (nr) *nr = c->nreal;
+  if (ng) *ng = c->nghost;
+  return EDB_OK;
+}
+
+// ---- rebuild -----------------------------------------------------------------------------------------------------
+static void ghost_refresh(edb_context* c, bool all) {
+  if (c->nghost == 0 && c->cfg.nranks == 1) return;
+  ScopedTimer tm(c, B_GHOST);
+  const uint32_t nloc = c->comm.n_local_ghost;
+  if (nloc) {
+    if (all) LAUNCH(c, k_ghost_refresh<true>, nblk(nloc), BLK, 0, view(c->pa), c->g_src.p, c->g_ent.p, c->g_shift.p, c->nreal, nloc, c->cidx.p, c->g_cell.p);
+    else LAUNCH(c, k_ghost_refresh<false>, nblk(nloc), BLK, 0, view(c->pa), c->g_src.p, c->g_ent.p, c->g_shift.p, c->nreal, nloc, c->cidx.p, c->g_cell.p);
+  }
+  if (c->cfg.nranks > 1) c->comm.exchange_ghosts(view(c->pa), c->nreal, all, c->st, &c->ctr.kernel_launches);
+}
+
+static void compute_vertices(edb_context* c) {
+  if (!c->poly()) return;
+  const uint32_t ntot = c->nreal + c->nghost;
+  if (c->S.nvmax <= 0) throw StateError{EDB_ERR_STATE, "polyhedron mode needs edb_set_shapes"};
+  c->vert.ensure((size_t)ntot * c->S.nvmax + 1);
+  LAUNCH(c, k_compute_vertices, nblk(ntot), BLK, 0, view(c->pa), ntot, c->S, c->vert.p);
+}
+
+static void rebuild(edb_context* c, double rcut_inc, int symetric) {
+  ScopedTimer tm(c, B_REBUILD);
+  const GridDev& G = c->G;
+  c->rcut_inc = rcut_inc;
+  c->symetric = symetric;
+  const bool poly = c->poly();
+  if (poly && c->h_sh.empty()) throw StateError{EDB_ERR_STATE, "polyhedron mode needs edb_set_shapes"};
+
+  // multi-GPU: particles that left the brick migrate (with their interaction history) before re-binning
+  if (c->cfg.nranks > 1) throw StateError{EDB_ERR_STATE, "multi-GPU rebuild goes through comm (not wired in this build step)"};
+
+  uint32_t n = c->nreal;
+  // 1. bin reals into cells, id-ordered inside each cell
+  c->cidx.ensure(n + 1); c->tmp.ensure(n + 1); c->new2old.ensure(n + 1); c->old2new.ensure(n + 1);
+  CK(cudaMemsetAsync(c->ccount.p, 0, (G.ncell + 1) * 4, c->st));
+  CK(cudaMemsetAsync(c->cfill.p, 0, (G.ncell + 1) * 4, c->st));
+  LAUNCH(c, k_cell_assign, nblk(n), BLK, 0, c->pa.pr.p, n, G, c->cidx.p, c->ccount.p);
+  scan_u32(c, c->ccount.p, c->cstart.p, G.ncell);
+  LAUNCH(c, k_cell_scatter, nblk(n), BLK, 0, c->cidx.p, n, c->cstart.p, c->cfill.p, c->tmp.p);
+  LAUNCH(c, k_cell_rank, nblk(n), BLK, 0, c->cidx.p, c->pa.id.p, n, c->cstart.p, c->tmp.p, c->new2old.p, c->old2new.p);
+  // 2. ghosts: count, size, permute into the (possibly grown) scratch set, fill
+  LAUNCH(c, k_ghost_count, nblk(c->n_gent), BLK, 0, c->g_src_cell.p, c->n_gent, c->cstart.p, c->g_count.p);
+  scan_u32(c, c->g_count.p, c->g_off.p, c->n_gent);
+  CK(cudaMemcpyAsync(c->h_tot, c->g_off.p + c->n_gent, 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  const uint32_t nloc_ghost = c->n_gent ? c->h_tot[0] : 0;
+  c->comm.n_local_ghost = nloc_ghost;
+  c->nghost = nloc_ghost;
+  const uint32_t ntot = n + c->nghost;
+  c->pb.ensure(ntot + 1, false, c->st);
+  c->cidx2.ensure(ntot + 1);
+  LAUNCH(c, k_permute, nblk(n), BLK, 0, view(c->pb), view(c->pa), c->new2old.p, c->cidx.p, c->cidx2.p, n);
+  std::swap(c->pa, c->pb);
+  std::swap(c->cidx, c->cidx2);
+  LAUNCH(c, k_cell_ranges, nblk(G.ncell), BLK, 0, c->cstart.p, G.ncell, c->cbeg.p, c->cend.p);
+  c->g_src.ensure(c->nghost + 1); c->g_ent.ensure(c->nghost + 1);
+  LAUNCH(c, k_ghost_fill, nblk(c->n_gent), BLK, 0, c->g_cell.p, c->g_src_cell.p, c->n_gent, c->cstart.p, c->g_off.p, n, c->g_src.p,
+         c->g_ent.p, c->cbeg.p, c->cend.p);
+  ghost_refresh(c, true);
+  compute_vertices(c);
+  // 3. backup for the displacement trigger (backup_r / backup_dem)
+  c->pr_backup.ensure(n + 1);
+  if (poly) c->q_backup.ensure(n + 1);
+  LAUNCH(c, k_backup, nblk(n), BLK, 0, c->pa.pr.p, c->pa.q.p, c->pr_backup.p, poly ? c->q_backup.p : nullptr, n);
+  c->have_backup = true;
+
+  // 4. enumerate candidates: count -> scan -> fill (per type, owner-sorted)
+  for (int t = 0; t < NT; t++) std::swap(c->wave[t], c->prev[t]);
+  const bool had = c->have_prev;  // prev now holds the waves of the previous build (valid if had)
+  bool active[NT] = {};
+  bool has_drv[3] = {false, false, false};
+  for (auto& D : c->h_drv)
+    if (D.kind >= 0 && D.kind <= 2) has_drv[D.kind] = true;
+  active[0] = true;
+  if (poly) active[1] = active[2] = active[3] = true;
+  for (int k = 0; k < 3; k++) active[4 + k] = has_drv[k];
+  CntTab C{};
+  for (int t = 0; t < NT; t++) {
+    C.c[t] = nullptr;
+    c->wave[t].n = 0;
+    if (active[t]) {
+      c->wave[t].off.ensure(n + 2);
+      C.c[t] = c->wave[t].off.p;
+    }
+  }
+  NbhArgs A{view(c->pa), c->cidx.p, c->cbeg.p, c->cend.p, G, c->drv.p, (int)c->h_drv.size(), rcut_inc, symetric, n, c->vert.p, c->S};
+  WTab W{};
+  if (!poly) LAUNCH(c, k_nbh_sphere<false>, nblk(n, 128), 128, 0, A, C, W);
+  else LAUNCH(c, k_nbh_poly<false>, nblk(n, 64), 64, 0, A, C, W);
+  for (int t = 0; t < NT; t++)
+    if (active[t]) {
+      scan_u32(c, C.c[t], C.c[t], n);
+      CK(cudaMemcpyAsync(c->h_tot + t, C.c[t] + n, 4, cudaMemcpyDeviceToHost, c->st));
+    }
+  CK(cudaStreamSynchronize(c->st));
+  for (int t = 0; t < NT; t++) {
+    if (!active[t]) continue;
+    c->wave[t].n = c->h_tot[t];
+    if (c->wave[t].n >= (1ull << INC_SHIFT)) throw StateError{EDB_ERR_CAPACITY, "wave larger than 2^28 records"};
+    c->wave[t].ensure(c->wave[t].n + 1, poly);
+    W.w[t] = view(c->wave[t]);
+  }
+  if (!poly) LAUNCH(c, k_nbh_sphere<true>, nblk(n, 128), 128, 0, A, C, W);
+  else LAUNCH(c, k_nbh_poly<true>, nblk(n, 64), 64, 0, A, C, W);
+  // 5. history carry-over
+  if (had) {
+    for (int t = 0; t < NT; t++)
+      if (active[t] && c->wave[t].n && c->prev[t].n)
+        LAUNCH(c, k_history, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), view(c->prev[t]), c->new2old.p, c->n_old_real, poly);
+  }
+  c->have_prev = true;
+  c->n_old_real = n;
+  // 6. partner incidence lists
+  const bool partner = poly || symetric;
+  c->have_inc = false;
+  if (partner) {
+    c->inc_cnt.ensure(n + 2); c->inc_off.ensure(n + 2);
+    CK(cudaMemsetAsync(c->inc_cnt.p, 0, (n + 1) * 4, c->st));
+    const int tmax = poly ? 3 : 0;
+    uint64_t tot = 0;
+    for (int t = 0; t <= tmax; t++) {
+      tot += c->wave[t].n;
+      if (c->wave[t].n) LAUNCH(c, k_incidence<false>, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), t, n, c->inc_cnt.p, nullptr, nullptr);
+    }
+    scan_u32(c, c->inc_cnt.p, c->inc_off.p, n);
+    c->inc.ensure(tot + 1);
+    CK(cudaMemsetAsync(c->inc_cnt.p, 0, (n + 1) * 4, c->st));
+    for (int t = 0; t <= tmax; t++)
+      if (c->wave[t].n) LAUNCH(c, k_incidence<true>, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), t, n, c->inc_cnt.p, c->inc_off.p, c->inc.p);
+    LAUNCH(c, k_incidence_sort, nblk(n), BLK, 0, c->inc_off.p, c->inc.p, n);
+    c->have_inc = true;
+  }
+  c->ctr.rebuilds++;
+}
+
+extern "C" int edb_update_particle_neighbors(edb_context* c, double rcut_inc, int32_t symetric) {
+  API_BEGIN(c)
+  rebuild(c, rcut_inc, symetric);
+  API_END(c)
+}
+extern "C" int edb_ghost_update_rq(edb_context* c) {
+  API_BEGIN(c)
+  ghost_refresh(c, false);
+  API_END(c)
+}
+extern "C" int edb_compute_vertices(edb_context* c) {
+  API_BEGIN(c)
+  compute_vertices(c);
+  API_END(c)
+}
+
+// ---- per-step operators -----------------------------------------------------------------------------------------
+extern "C" int edb_reset_force_moment(edb_context* c) {
+  API_BEGIN(c)
+  LAUNCH(c, k_reset_fm, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal);
+  API_END(c)
+}
+extern "C" int edb_gravity_force(edb_context* c, const double g[3]) {
+  API_BEGIN(c)
+  LAUNCH(c, k_gravity, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, g[0], g[1], g[2]);
+  API_END(c)
+}
+extern "C" int edb_force_to_accel(edb_context* c) {
+  API_BEGIN(c)
+  LAUNCH(c, k_force_to_accel, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal);
+  API_END(c)
+}
+static void prolog(edb_context* c, double dt) {
+  ScopedTimer tm(c, B_PROLOG);
+  LAUNCH(c, k_prolog, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, dt, dt * dt * 0.5, dt * 0.5);
+}
+extern "C" int edb_combined_compute_prolog(edb_context* c, double dt) {
+  API_BEGIN(c)
+  prolog(c, dt);
+  API_END(c)
+}
+extern "C" int edb_combined_compute_epilog(edb_context* c, double dt) {
+  API_BEGIN(c)
+  ScopedTimer tm(c, B_EPILOG);
+  LAUNCH(c, k_epilog<2>, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, dt * 0.5);
+  API_END(c)
+}
+extern "C" int edb_push_to_quaternion(edb_context* c, double dt) {
+  API_BEGIN(c)
+  LAUNCH(c, k_push_to_quaternion, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, dt, dt * 0.5);
+  API_END(c)
+}
+extern "C" int edb_push_to_angular_velocity(edb_context* c, double dt) {
+  API_BEGIN(c)
+  LAUNCH(c, k_epilog<1>, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, dt * 0.5);
+  API_END(c)
+}
+extern "C" int edb_push_to_angular_acceleration(edb_context* c) {
+  API_BEGIN(c)
+  LAUNCH(c, k_epilog<0>, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, 0.0);
+  API_END(c)
+}
+extern "C" int edb_freeze_particles(edb_context* c) {
+  API_BEGIN(c)
+  LAUNCH(c, k_freeze, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal);
+  API_END(c)
+}
+
+static const int ORDER_SPHERE[] = {0, 4, 5, 6, 7, 8, 9};
+static const int ORDER_POLY[] = {0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 4, 5, 6};
+
+template <int LAW>
+static void launch_contact_waves(edb_context* c, double dt) {
+  const bool poly = c->poly();
+  ContactArgs A{view(c->pa), WView{}, c->prm, c->drv.p, c->vert.p, c->S, dt, 0, c->symetric};
+  const int* order = poly ? ORDER_POLY : ORDER_SPHERE;
+  const int norder = poly ? 13 : 7;
+  for (int o = 0; o < norder; o++) {
+    const int t = order[o];
+    Wave& w = c->wave[t];
+    if (!w.n) continue;
+    A.w = view(w);
+    A.type = t;
+    if (t <= 3) {
+      if (poly) LAUNCH(c, k_contact_poly_pp<LAW>, nblk(w.n), BLK, 0, A);
+      else LAUNCH(c, k_contact_sphere_pp<LAW>, nblk(w.n), BLK, 0, A);
+    } else if (t <= 6) {
+      if (poly) LAUNCH(c, (k_contact_driver<LAW, true>), nblk(w.n), BLK, 0, A);
+      else LAUNCH(c, (k_contact_driver<LAW, false>), nblk(w.n), BLK, 0, A);
+    }
+    c->ctr.interaction_updates += w.n;
+    c->ctr.contact_launches++;
+    // algorithmic bytes of this launch: per record 8 (ij) + 48 r + 48 w history + 80 contact state;
+    // per distinct particle touched 92 B of gathers (r, radius, vrot, group, v, mass) counted once per wave
+    c->ctr.bytes_contact_algorithmic += w.n * 184ull + (uint64_t)c->nreal * 92ull;
+  }
+}
+
+static void contact_waves(edb_context* c, double dt) {
+  ScopedTimer tm(c, B_CONTACT);
+  if (!c->have_prev) throw StateError{EDB_ERR_STATE, "contact operator before update_particle_neighbors"};
+  if (c->law == 0) launch_contact_waves<0>(c, dt);
+  else if (c->law == 1) launch_contact_waves<1>(c, dt);
+  else launch_contact_waves<2>(c, dt);
+}
+
+template <int FUSE>
+static void gather(edb_context* c, const double* g, double dt) {
+  ScopedTimer tm(c, B_GATHER);
+  const bool poly = c->poly();
+  GatherArgs A{};
+  A.P = view(c->pa);
+  for (int t = 0; t < NT; t++) A.W.w[t] = view(c->wave[t]);
+  const int* order = poly ? ORDER_POLY : ORDER_SPHERE;
+  A.norder = poly ? 13 : 7;
+  for (int o = 0; o < A.norder; o++) A.order[o] = order[o];
+  A.pp_partner = (poly || c->symetric) && c->have_inc ? 1 : 0;
+  A.inc_off = A.pp_partner ? c->inc_off.p : nullptr;
+  A.inc = A.pp_partner ? c->inc.p : nullptr;
+  A.nreal = c->nreal;
+  A.has_swap = poly ? 1 : 0;
+  if (g) { A.g[0] = g[0]; A.g[1] = g[1]; A.g[2] = g[2]; }
+  A.hdt = dt * 0.5;
+  LAUNCH(c, k_gather<FUSE>, nblk(c->nreal), BLK, 0, A);
+}
+
+extern "C" int edb_contact_sphere(edb_context* c, double dt) {
+  API_BEGIN(c)
+  if (c->poly()) throw StateError{EDB_ERR_STATE, "contact_sphere on a polyhedron context"};
+  contact_waves(c, dt);
+  gather<0>(c, nullptr, dt);
+  API_END(c)
+}
+extern "C" int edb_contact_polyhedron(edb_context* c, double dt) {
+  API_BEGIN(c)
+  if (!c->poly()) throw StateError{EDB_ERR_STATE, "contact_polyhedron on a sphere context"};
+  contact_waves(c, dt);
+  gather<0>(c, nullptr, dt);
+  API_END(c)
+}
+
+static uint64_t displ_over(edb_context* c, double thr) {
+  if (!c->have_backup) throw StateError{EDB_ERR_STATE, "displ_over before update_particle_neighbors"};
+  CK(cudaMemsetAsync(c->d_flag, 0, 8, c->st));
+  if (c->poly()) LAUNCH(c, k_displ_over<true>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, c->q_backup.p, c->nreal, c->S, thr * thr, c->d_flag);
+  else LAUNCH(c, k_displ_over<false>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, nullptr, c->nreal, c->S, thr * thr, c->d_flag);
+  CK(cudaMemcpyAsync(c->h_flag, c->d_flag, 8, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  uint64_t v = c->h_flag[0];
+  if (c->cfg.nranks > 1) v = c->comm.allreduce_sum_u64(v, c->st);
+  return v;
+}
+extern "C" int edb_displ_over(edb_context* c, double thr, uint64_t* over) {
+  API_BEGIN(c)
+  *over = displ_over(c, thr);
+  API_END(c)
+}
+
+extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], double rcut_inc, int32_t symetric, int32_t nsteps,
+                              int32_t rebuild_every, uint64_t* n_rebuilds) {
+  API_BEGIN(c)
+  uint64_t nb = 0;
+  if (!c->have_prev) { rebuild(c, rcut_inc, symetric); }
+  for (int it = 0; it < nsteps; it++) {
+    prolog(c, dt);
+    bool rb;
+    if (rebuild_every > 0) rb = ((it + 1) % rebuild_every) == 0;
+    else if (rebuild_every < 0) rb = false;
+    else rb = displ_over(c, 0.5 * rcut_inc) > 0;
+    if (rb) { rebuild(c, rcut_inc, symetric); nb++; }
+    else { ghost_refresh(c, false); compute_vertices(c); }
+    contact_waves(c, dt);
+    gather<1>(c, g, dt);
+    c->ctr.particle_steps += c->nreal;
+  }
+  if (n_rebuilds) *n_rebuilds = nb;
+  API_END(c)
+}
+
+// ---- views ---------------------------------------------------------------------------------------------------------
+__global__ void k_count_active(WView w, unsigned long long* __restrict__ out) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int a = 0;
+  if (k < w.n) {
+    const double4 f = w.ft[k], m = w.mo[k];
+    a = (f.x != 0.0 || f.y != 0.0 || f.z != 0.0 || m.x != 0.0 || m.y != 0.0 || m.z != 0.0) ? 1 : 0;
+  }
+  a = __reduce_add_sync(0xffffffffu, a);
+  if ((threadIdx.x & 31) == 0 && a) atomicAdd(out, (unsigned long long)a);
+}
+extern "C" int edb_interaction_counts(edb_context* c, uint64_t counts[EDB_NTYPES], uint64_t active[EDB_NTYPES]) {
+  API_BEGIN(c)
+  for (int t = 0; t < NT; t++) {
+    counts[t] = c->wave[t].n;
+    if (active) {
+      active[t] = 0;
+      if (c->wave[t].n) {
+        CK(cudaMemsetAsync(c->d_flag, 0, 8, c->st));
+        LAUNCH(c, k_count_active, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), c->d_flag);
+        CK(cudaMemcpyAsync(c->h_flag, c->d_flag, 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        active[t] = c->h_flag[0];
+      }
+    }
+  }
+  API_END(c)
+}
+
+__global__ void k_export(WView w, const uint64_t* __restrict__ id, int type, bool has_sub, bool driver, edb_interaction* __restrict__ out) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= w.n) return;
+  const uint2 ij = w.ij[k];
+  const uint8_t fl = w.flg[k];
+  const double4 ft = w.ft[k], mo = w.mo[k];
+  edb_interaction e;
+  memset(&e, 0, sizeof(e));
+  e.id_i = id[ij.x];
+  e.id_j = driver ? (uint64_t)ij.y : id[ij.y];
+  if (has_sub) { const uint2 s = w.sub[k]; e.sub_i = s.x; e.sub_j = s.y; }
+  e.type = (uint16_t)type; e.swap = fl & 1; e.ghost = (fl >> 1) & 3;
+  e.friction[0] = ft.x; e.friction[1] = ft.y; e.friction[2] = ft.z;
+  e.moment[0] = mo.x; e.moment[1] = mo.y; e.moment[2] = mo.z;
+  out[k] = e;
+}
+extern "C" int edb_export_interactions(edb_context* c, edb_interaction* out, uint64_t cap, uint64_t* n) {
+  API_BEGIN(c)
+  uint64_t tot = 0;
+  for (int t = 0; t < NT; t++) tot += c->wave[t].n;
+  *n = tot;
+  if (tot > cap) throw StateError{EDB_ERR_CAPACITY, "export buffer too small"};
+  edb_interaction* d = nullptr;
+  if (tot) {
+    CK(cudaMalloc(&d, tot * sizeof(edb_interaction)));
+    uint64_t o = 0;
+    for (int t = 0; t < NT; t++) {
+      if (!c->wave[t].n) continue;
+      LAUNCH(c, k_export, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), c->pa.id.p, t, c->poly(), t >= 4, d + o);
+      o += c->wave[t].n;
+    }
+    CK(cudaMemcpyAsync(out, d, tot * sizeof(edb_interaction), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    CK(cudaFree(d));
+  }
+  API_END(c)
+}
+
+__global__ void k_state(WView w, double* __restrict__ dn, double* __restrict__ cp, double* __restrict__ fn, double* __restrict__ ft) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= w.n) return;
+  const double4 fd = w.fd[k], c4 = w.cp[k], f4 = w.ft[k];
+  dn[k] = fd.w;
+  cp[3 * k] = c4.x; cp[3 * k + 1] = c4.y; cp[3 * k + 2] = c4.z;
+  // fn = f - friction (contact_sphere.hpp:180); zero for records without contact
+  fn[3 * k] = fd.x - f4.x; fn[3 * k + 1] = fd.y - f4.y; fn[3 * k + 2] = fd.z - f4.z;
+  ft[3 * k] = f4.x; ft[3 * k + 1] = f4.y; ft[3 * k + 2] = f4.z;
+}
+extern "C" int edb_get_contact_state(edb_context* c, int32_t type, double* dn, double* cp, double* fn, double* ft) {
+  API_BEGIN(c)
+  if (type < 0 || type >= NT) throw StateError{EDB_ERR_INVALID, "bad type"};
+  const uint64_t n = c->wave[type].n;
+  if (n) {
+    c->stage.ensure(10 * n + 1);
+    double* s = c->stage.p;
+    LAUNCH(c, k_state, nblk(n), BLK, 0, view(c->wave[type]), s, s + n, s + 4 * n, s + 7 * n);
+    if (dn) CK(cudaMemcpyAsync(dn, s, n * 8, cudaMemcpyDeviceToHost, c->st));
+    if (cp) CK(cudaMemcpyAsync(cp, s + n, 3 * n * 8, cudaMemcpyDeviceToHost, c->st));
+    if (fn) CK(cudaMemcpyAsync(fn, s + 4 * n, 3 * n * 8, cudaMemcpyDeviceToHost, c->st));
+    if (ft) CK(cudaMemcpyAsync(ft, s + 7 * n, 3 * n * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+  }
+  API_END(c)
+}
+
+extern "C" int edb_import_interactions(edb_context* c, const edb_interaction* in, uint64_t n) {
+  API_BEGIN(c)
+  // Restart path: the records become the history source of the NEXT rebuild.  Owner slots are resolved on the host
+  // through the id -> slot map of the current device order (rebuild-frequency operation, not on the per-step path).
+  const uint32_t np = c->nreal;
+  std::vector<uint64_t> ids(np);
+  CK(cudaMemcpy(ids.data(), c->pa.id.p, (size_t)np * 8, cudaMemcpyDeviceToHost));
+  std::unordered_map<uint64_t, uint32_t> slot;
+  slot.reserve(np * 2);
+  for (uint32_t p = 0; p < np; p++) slot[ids[p]] = p;
+  const bool poly = c->poly();
+  std::vector<std::vector<uint32_t>> per_type(NT);
+  for (uint64_t k = 0; k < n; k++)
+    if (in[k].type < NT) per_type[in[k].type].push_back((uint32_t)k);
+  for (int t = 0; t < NT; t++) {
+    Wave& w = c->wave[t];
+    auto& idx = per_type[t];
+    // owner slot per record; records whose owner is unknown are dropped
+    std::vector<std::pair<uint32_t, uint32_t>> key;  // (owner slot, record)
+    for (uint32_t r : idx) {
+      const auto& e = in[r];
+      const uint64_t oid = e.swap ? e.id_j : e.id_i;
+      auto it = slot.find(oid);
+      if (it != slot.end()) key.push_back({it->second, r});
+    }
+    std::stable_sort(key.begin(), key.end(), [](auto& a, auto& b) { return a.first < b.first; });
+    const size_t m = key.size();
+    w.n = m;
+    w.off.ensure(np + 2);
+    w.ensure(m + 1, poly);
+    std::vector<uint32_t> off(np + 1, 0);
+    std::vector<uint2> ij(m), sub(m);
+    std::vector<uint8_t> flg(m);
+    std::vector<double4> ft(m), mo(m);
+    for (size_t s = 0; s < m; s++) {
+      const auto& e = in[key[s].second];
+      off[key[s].first + 1]++;
+      const uint64_t pid = (t >= 4) ? e.id_j : (e.swap ? e.id_i : e.id_j);
+      uint32_t si = 0, sj = 0;
+      auto a = slot.find(e.id_i), b = slot.find(e.id_j);
+      if (a != slot.end()) si = a->second;
+      if (t >= 4) sj = (uint32_t)e.id_j; else if (b != slot.end()) sj = b->second;
+      ij[s] = make_uint2(si, sj);
+      sub[s] = make_uint2(e.sub_i, e.sub_j);
+      flg[s] = (uint8_t)((e.swap & 1) | ((e.ghost & 3) << 1));
+      long long pb = (long long)pid;
+      double pidd;
+      memcpy(&pidd, &pb, 8);
+      ft[s] = make_double4(e.friction[0], e.friction[1], e.friction[2], pidd);
+      mo[s] = make_double4(e.moment[0], e.moment[1], e.moment[2], 0.0);
+    }
+    for (uint32_t p = 0; p < np; p++) off[p + 1] += off[p];
+    CK(cudaMemcpy(w.off.p, off.data(), (np + 1) * 4, cudaMemcpyHostToDevice));
+    if (m) {
+      CK(cudaMemcpy(w.ij.p, ij.data(), m * sizeof(uint2), cudaMemcpyHostToDevice));
+      if (poly) CK(cudaMemcpy(w.sub.p, sub.data(), m * sizeof(uint2), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(w.flg.p, flg.data(), m, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(w.ft.p, ft.data(), m * sizeof(double4), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(w.mo.p, mo.data(), m * sizeof(double4), cudaMemcpyHostToDevice));
+      CK(cudaMemset(w.fd.p, 0, m * sizeof(double4)));
+      CK(cudaMemset(w.cp.p, 0, m * sizeof(double4)));
+    }
+  }
+  c->have_prev = true;   // valid history source; contact operators still require a rebuild (have_inc = false)
+  c->n_old_real = np;
+  c->have_inc = false;
+  // identity permutation until the next rebuild re-bins
+  API_END(c)
+}
+
+extern "C" int edb_compute_driver_force_moment(edb_context* c, double* forces, double* moments) {
+  API_BEGIN(c)
+  const int nd = (int)c->h_drv.size();
+  std::vector<double> acc((size_t)nd * 6, 0.0);
+  for (int t = 4; t <= 12; t++) {
+    Wave& w = c->wave[t];
+    if (!w.n || !nd) continue;
+    const uint32_t nb = nblk(w.n);
+    c->stage.ensure((size_t)nb * nd * 6 + 1);
+    const size_t smem = (size_t)(BLK / 32) * nd * 6 * sizeof(double);
+    LAUNCH(c, k_driver_force, nb, BLK, smem, view(w), c->drv.p, nd, c->stage.p);
+    std::vector<double> part((size_t)nb * nd * 6);
+    CK(cudaMemcpyAsync(part.data(), c->stage.p, part.size() * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for (uint32_t b = 0; b < nb; b++)
+      for (int i = 0; i < nd * 6; i++) acc[i] += part[(size_t)b * nd * 6 + i];
+  }
+  for (int d = 0; d < nd; d++)
+    for (int k = 0; k < 3; k++) {
+      forces[3 * d + k] = acc[d * 6 + k];
+      moments[3 * d + k] = acc[d * 6 + 3 + k];
+    }
+  API_END(c)
+}
+
+extern "C" int edb_stress_tensor(edb_context* c, double* stress9) {
+  API_BEGIN(c)
+  (void)stress9;
+  throw StateError{EDB_ERR_STATE, "stress_tensor: not built yet (SURVEY 8f rank 2)"};
+  API_END(c)
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------------------------------------
+extern "C" int edb_comm_unique_id(uint8_t id_out[128]) { return Comm::unique_id(id_out); }
+extern "C" int edb_comm_init(edb_context* c, const uint8_t id[128]) {
+  API_BEGIN(c)
+  c->comm.init(c->cfg, id);
+  API_END(c)
+}
+
+// ---- measurement ---------------------------------------------------------------------------------------------------
+extern "C" int edb_set_timing(edb_context* c, int32_t on) {
+  API_BEGIN(c)
+  resolve_timers(c);
+  c->timing = on != 0;
+  API_END(c)
+}
+extern "C" int edb_get_counters(edb_context* c, edb_counters* out) {
+  API_BEGIN(c)
+  resolve_timers(c);
+  *out = c->ctr;
+  API_END(c)
+}
+extern "C" int edb_reset_counters(edb_context* c) {
+  API_BEGIN(c)
+  resolve_timers(c);
+  c->ctr = edb_counters{};
+  API_END(c)
+}
+__global__ void k_flush(double4* p, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = make_double4(0, 0, 0, 0);
+}
+extern "C" int edb_flush_l2(edb_context* c) {
+  API_BEGIN(c)
+  const size_t n = (size_t)256 << 20 >> 5;  // 256 MiB > 126 MB L2
+  c->l2buf.ensure(n);
+  k_flush<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(c->l2buf.p, n);
+  API_END(c)
+}

@@ -1,0 +1,496 @@
+// kernels_rebuild.cuh — neighbour / interaction rebuild on the device (runs every 10-100 steps).
+//   cell binning (counting sort by cell, id-ordered inside a cell) -> ghost layer -> candidate enumeration
+//   (count + scan + fill, owner-sorted per interaction type) -> friction/moment history carry-over -> partner
+//   incidence lists for the deterministic force gather.
+// Reference behaviour reproduced: src/grid/chunk_neighbors_contact.cpp:46-57, src/sphere/nbh_sphere.cu:64-309,
+// src/polyhedron/nbh_polyhedron.cpp:75-384, polyhedron/nbh_polyhedron_driver.hpp:205-238,
+// src/interaction/include/exaDEM/interaction/interaction_manager.hpp:88-112 + placeholder_interaction.hpp:398-408.
+#pragma once
+#include "common.cuh"
+
+namespace edb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// exclusive scan (uint32) : reduce tiles -> scan tile sums (one block) -> apply
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SCAN_T = 256;
+constexpr int SCAN_I = 8;
+constexpr int SCAN_TILE = SCAN_T * SCAN_I;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v += t;
+  }
+  return v;
+}
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t ws[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t inc = warp_incl_scan(v);
+  if (lane == 31) ws[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t s = (lane < (blockDim.x >> 5)) ? ws[lane] : 0;
+    s = warp_incl_scan(s);
+    ws[lane] = s;
+  }
+  __syncthreads();
+  const uint32_t base = wid ? ws[wid - 1] : 0;
+  *total = ws[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return base + inc - v;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_reduce(const uint32_t* __restrict__ in, uint32_t* __restrict__ bsum, uint32_t n) {
+  const uint32_t base = blockIdx.x * SCAN_TILE;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_I; k++) {
+    const uint32_t i = base + k * SCAN_T + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  uint32_t tot;
+  block_excl_scan(s, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_bsum(uint32_t* __restrict__ bsum, uint32_t nb, uint32_t* __restrict__ total) {
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nb; base += SCAN_T) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < nb ? bsum[i] : 0;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan(v, &tot);
+    if (i < nb) bsum[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+// out has n+1 entries (out[n] = total); in-place allowed
+__global__ void __launch_bounds__(SCAN_T) k_scan_apply(const uint32_t* in, uint32_t* out, const uint32_t* __restrict__ bsum,
+                                                       const uint32_t* __restrict__ total, uint32_t n) {
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_I;
+  uint32_t v[SCAN_I], s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_I; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  uint32_t tot;
+  uint32_t ex = block_excl_scan(s, &tot) + bsum[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_I; k++) {
+    if (base + k < n) out[base + k] = ex;
+    ex += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = *total;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// cell binning
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cell_coord(const GridDev& G, double x, int d) {
+  int c = (int)floor((x - G.lo[d]) / G.cs[d]);
+  c = c < 0 ? 0 : c;
+  c = c > G.nc[d] - 1 ? G.nc[d] - 1 : c;
+  return c;
+}
+__device__ __forceinline__ uint32_t cell_lin(const GridDev& G, int i, int j, int k) {
+  return (uint32_t)i + (uint32_t)G.g[0] * ((uint32_t)j + (uint32_t)G.g[1] * (uint32_t)k);
+}
+// wrap periodic coordinates into the global box, assign the (ghost-shelled) cell index, histogram
+__global__ void k_cell_assign(double4* __restrict__ pr, uint32_t n, GridDev G, uint32_t* __restrict__ cidx,
+                              uint32_t* __restrict__ ccount) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double4 r = pr[p];
+  double c[3] = {r.x, r.y, r.z};
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    if (G.periodic[d]) {
+      const double L = G.ghi[d] - G.glo[d];
+      if (c[d] >= G.ghi[d]) c[d] -= L;
+      else if (c[d] < G.glo[d]) c[d] += L;
+    }
+  }
+  r.x = c[0]; r.y = c[1]; r.z = c[2];
+  pr[p] = r;
+  const uint32_t lin = cell_lin(G, cell_coord(G, c[0], 0) + 1, cell_coord(G, c[1], 1) + 1, cell_coord(G, c[2], 2) + 1);
+  cidx[p] = lin;
+  atomicAdd(&ccount[lin], 1u);
+}
+__global__ void k_cell_scatter(const uint32_t* __restrict__ cidx, uint32_t n, const uint32_t* __restrict__ cstart,
+                               uint32_t* __restrict__ cfill, uint32_t* __restrict__ tmp) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t c = cidx[p];
+  tmp[cstart[c] + atomicAdd(&cfill[c], 1u)] = p;
+}
+// deterministic order inside a cell: rank by particle id (ids are unique)
+__global__ void k_cell_rank(const uint32_t* __restrict__ cidx, const uint64_t* __restrict__ id, uint32_t n,
+                            const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ tmp,
+                            uint32_t* __restrict__ new2old, uint32_t* __restrict__ old2new) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t c = cidx[p];
+  const uint64_t me = id[p];
+  uint32_t rank = 0;
+  for (uint32_t s = cstart[c]; s < cstart[c + 1]; s++) rank += (id[tmp[s]] < me) ? 1u : 0u;
+  const uint32_t np = cstart[c] + rank;
+  new2old[np] = p;
+  old2new[p] = np;
+}
+__global__ void k_permute(PView dst, PView src, const uint32_t* __restrict__ new2old, const uint32_t* __restrict__ cidx_old,
+                          uint32_t* __restrict__ cidx_new, uint32_t n) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const uint32_t o = new2old[s];
+  dst.pr[s] = src.pr[o]; dst.vm[s] = src.vm[o]; dst.wg[s] = src.wg[o]; dst.q[s] = src.q[o];
+  dst.fx[s] = src.fx[o]; dst.fy[s] = src.fy[o]; dst.fz[s] = src.fz[o];
+  dst.mx[s] = src.mx[o]; dst.my[s] = src.my[o]; dst.mz[s] = src.mz[o];
+  dst.ax[s] = src.ax[o]; dst.ay[s] = src.ay[o]; dst.az[s] = src.az[o];
+  dst.ix[s] = src.ix[o]; dst.iy[s] = src.iy[o]; dst.iz[s] = src.iz[o];
+  dst.h[s] = src.h[o]; dst.id[s] = src.id[o]; dst.orig[s] = src.orig[o];
+  cidx_new[s] = cidx_old[o];
+}
+__global__ void k_cell_ranges(const uint32_t* __restrict__ cstart, uint32_t ncell, uint32_t* __restrict__ cbeg,
+                              uint32_t* __restrict__ cend) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  cbeg[c] = cstart[c];
+  cend[c] = cstart[c + 1];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ghost layer (periodic images of the local brick; remote bricks are handled by the exchange in comm.cuh)
+// ghost table entry k: ghost cell gcell[k] mirrors local real cell gsrc_cell[k] shifted by gshift[k]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_ghost_count(const uint32_t* __restrict__ gsrc_cell, uint32_t nent, const uint32_t* __restrict__ cstart,
+                              uint32_t* __restrict__ gcount) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nent) return;
+  const uint32_t c = gsrc_cell[k];
+  gcount[k] = cstart[c + 1] - cstart[c];
+}
+__global__ void k_ghost_fill(const uint32_t* __restrict__ gcell, const uint32_t* __restrict__ gsrc_cell, uint32_t nent,
+                             const uint32_t* __restrict__ cstart, const uint32_t* __restrict__ goff, uint32_t base,
+                             uint32_t* __restrict__ gsrc, uint32_t* __restrict__ gent, uint32_t* __restrict__ cbeg,
+                             uint32_t* __restrict__ cend) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nent) return;
+  const uint32_t c = gsrc_cell[k];
+  const uint32_t s0 = cstart[c], cnt = cstart[c + 1] - s0, o = goff[k];
+  for (uint32_t t = 0; t < cnt; t++) {
+    gsrc[o + t] = s0 + t;
+    gent[o + t] = k;
+  }
+  cbeg[gcell[k]] = base + o;
+  cend[gcell[k]] = base + o + cnt;
+}
+// ghost refresh.  ALL=false: the per-step field list of ghost_update_rq (src/grid/update_ghosts.cu:46-51):
+// r (+shift), v, vrot, orient (+ type/radius/mass which ride in the same 32-byte sectors).
+template <bool ALL>
+__global__ void k_ghost_refresh(PView P, const uint32_t* __restrict__ gsrc, const uint32_t* __restrict__ gent,
+                                const double* __restrict__ gshift, uint32_t nreal, uint32_t nghost, uint32_t* __restrict__ cidx,
+                                const uint32_t* __restrict__ gcell) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nghost) return;
+  const uint32_t s = gsrc[g], k = gent[g], d = nreal + g;
+  double4 r = P.pr[s];
+  r.x = r.x + gshift[3 * k]; r.y = r.y + gshift[3 * k + 1]; r.z = r.z + gshift[3 * k + 2];
+  P.pr[d] = r;
+  P.vm[d] = P.vm[s];
+  P.wg[d] = P.wg[s];
+  P.q[d] = P.q[s];
+  if (ALL) {
+    P.h[d] = P.h[s];
+    P.id[d] = P.id[s];
+    cidx[d] = gcell[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// candidate enumeration
+// ---------------------------------------------------------------------------------------------------------------
+struct CntTab {
+  uint32_t* c[NT];  // per type: count (count pass) / CSR offsets (fill pass) per owner slot, nullptr = type inactive
+};
+struct NbhArgs {
+  PView P;
+  const uint32_t* cidx;
+  const uint32_t* cbeg;
+  const uint32_t* cend;
+  GridDev G;
+  const Driver* drv;
+  int ndrv;
+  double rcut_inc;
+  int symetric;
+  uint32_t nreal;
+  const double4* vert;  // polyhedra: world vertices
+  ShapesView S;
+};
+
+__device__ __forceinline__ void cell_ijk(const GridDev& G, uint32_t lin, int& i, int& j, int& k) {
+  i = lin % G.g[0];
+  const uint32_t t = lin / G.g[0];
+  j = t % G.g[1];
+  k = t / G.g[1];
+}
+__device__ __forceinline__ bool is_ghost_cell(const GridDev& G, int i, int j, int k) {
+  return i == 0 || j == 0 || k == 0 || i == G.g[0] - 1 || j == G.g[1] - 1 || k == G.g[2] - 1;
+}
+
+// Visit the 3x3x3 stencil of particle a in the order (dk, dj, di) x cell order, applying ContactNeighborFilterFunc
+// (chunk_neighbors_contact.cpp:46-57).  f(b, ghost_cell)
+template <class F>
+__device__ __forceinline__ void for_each_neighbor(const NbhArgs& A, uint32_t a, const double4 ra, F&& f) {
+  int ci, cj, ck;
+  cell_ijk(A.G, A.cidx[a], ci, cj, ck);
+  for (int dk = -1; dk <= 1; dk++)
+    for (int dj = -1; dj <= 1; dj++)
+      for (int di = -1; di <= 1; di++) {
+        const int i = ci + di, j = cj + dj, k = ck + dk;
+        if (i < 0 || j < 0 || k < 0 || i >= A.G.g[0] || j >= A.G.g[1] || k >= A.G.g[2]) continue;
+        const uint32_t cb = cell_lin(A.G, i, j, k);
+        const bool gc = is_ghost_cell(A.G, i, j, k);
+        const uint32_t e = A.cend[cb];
+        for (uint32_t b = A.cbeg[cb]; b < e; b++) {
+          if (b == a) continue;
+          const double4 rb = A.P.pr[b];
+          const v3 d = mk3(rb.x, rb.y, rb.z) - mk3(ra.x, ra.y, ra.z);
+          const double d2 = dot(d, d);
+          const double rmax = ra.w + rb.w + A.rcut_inc;
+          if (d2 > 0.0 && d2 < rmax * rmax) f(b, gc);
+        }
+      }
+}
+
+// FILL=false: count candidates per type;  FILL=true: write records at the owner's CSR offset
+struct WTab {
+  WView w[NT];
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_nbh_sphere(NbhArgs A, CntTab C, WTab W) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A.nreal) return;
+  const double4 ra = A.P.pr[a];
+  const uint64_t ida = A.P.id[a];
+  const v3 pa = mk3(ra.x, ra.y, ra.z);
+  // drivers first (nbh_sphere.cu:182-231)
+  uint32_t nd[3] = {0, 0, 0};
+  for (int d = 0; d < A.ndrv; d++) {
+    const Driver D = A.drv[d];
+    if (D.kind > 2) continue;
+    if (driver_filter(D, ra.w + A.rcut_inc, pa)) {
+      const int t = 4 + D.kind;
+      if (FILL) {
+        const uint32_t k = C.c[t][a] + nd[D.kind];
+        W.w[t].ij[k] = make_uint2(a, (uint32_t)d);
+        W.w[t].flg[k] = 0;
+        W.w[t].ft[k] = make_double4(0, 0, 0, __longlong_as_double((long long)d));
+        W.w[t].mo[k] = make_double4(0, 0, 0, 0);
+      }
+      nd[D.kind]++;
+    }
+  }
+  uint32_t n0 = 0;
+  const uint32_t base0 = FILL ? C.c[0][a] : 0;
+  for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
+    const uint64_t idb = A.P.id[b];
+    uint8_t ghost = 0;
+    if (A.symetric) {  // nbh_sphere.cu:245-249
+      if (ida >= idb && !gc) return;
+    } else {           // :272-279
+      if (ida >= idb) return;
+      if (gc) ghost = 1;
+    }
+    if (FILL) {
+      const uint32_t k = base0 + n0;
+      W.w[0].ij[k] = make_uint2(a, b);
+      W.w[0].flg[k] = (uint8_t)(ghost << 1);
+      W.w[0].ft[k] = make_double4(0, 0, 0, __longlong_as_double((long long)idb));
+      W.w[0].mo[k] = make_double4(0, 0, 0, 0);
+    }
+    n0++;
+  });
+  if (!FILL) {
+    C.c[0][a] = n0;
+    if (C.c[4]) C.c[4][a] = nd[0];
+    if (C.c[5]) C.c[5][a] = nd[1];
+    if (C.c[6]) C.c[6][a] = nd[2];
+  }
+}
+
+struct VA {  // world-vertex accessor of one particle
+  const double4* p;
+  __device__ __forceinline__ v3 operator[](int i) const {
+    const double4 t = p[i];
+    return mk3(t.x, t.y, t.z);
+  }
+};
+
+template <bool FILL>
+__device__ __forceinline__ void emit(const CntTab& C, const WTab& W, uint32_t owner, uint32_t* cnt, int t, uint32_t i, uint32_t j,
+                                     uint32_t si, uint32_t sj, uint8_t flg, uint64_t partner_id) {
+  if (FILL) {
+    const uint32_t k = C.c[t][owner] + cnt[t];
+    W.w[t].ij[k] = make_uint2(i, j);
+    W.w[t].sub[k] = make_uint2(si, sj);
+    W.w[t].flg[k] = flg;
+    W.w[t].ft[k] = make_double4(0, 0, 0, __longlong_as_double((long long)partner_id));
+    W.w[t].mo[k] = make_double4(0, 0, 0, 0);
+  }
+  cnt[t]++;
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(64) k_nbh_poly(NbhArgs A, CntTab C, WTab W) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A.nreal) return;
+  const double4 ra = A.P.pr[a];
+  const uint64_t ida = A.P.id[a];
+  const double4 wga = A.P.wg[a];
+  const uint32_t ta = (uint32_t)((unsigned long long)__double_as_longlong(wga.w) & 0xffffffffu);
+  const ShapeDev sa = A.S.sh[ta];
+  const double ha = A.P.h[a], rV = A.rcut_inc;
+  const VA va{A.vert + (size_t)a * A.S.nvmax};
+  const double rma = ha * sa.radius;
+  uint32_t cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+  // drivers (nbh_polyhedron_driver.hpp:205-238): one record per vertex with sub_j = -1
+  for (int d = 0; d < A.ndrv; d++) {
+    const Driver D = A.drv[d];
+    if (D.kind > 2) continue;
+    const int t = 4 + D.kind;
+    for (int k = 0; k < sa.nv; k++)
+      if (driver_filter(D, rV + rma, va[k])) emit<FILL>(C, W, a, cnt, t, a, (uint32_t)d, (uint32_t)k, 0xffffffffu, 0, (uint64_t)d);
+  }
+  const double4 qa4 = A.P.q[a];
+  const q4 qa{qa4.x, qa4.y, qa4.z, qa4.w};
+  const int* ea = A.S.edges + 2 * sa.e0;
+  for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
+    const uint64_t idb = A.P.id[b];
+    if (ida >= idb) return;  // nbh_polyhedron.cpp:234-236
+    const uint8_t ghost = gc ? 1 : 0;
+    const double4 rb = A.P.pr[b];
+    const double4 wgb = A.P.wg[b];
+    const uint32_t tb = (uint32_t)((unsigned long long)__double_as_longlong(wgb.w) & 0xffffffffu);
+    const ShapeDev sb = A.S.sh[tb];
+    const double hb = A.P.h[b];
+    const double4 qb4 = A.P.q[b];
+    const q4 qb{qb4.x, qb4.y, qb4.z, qb4.w};
+    Obb oi = obb_world(sa.obb, mk3(ra.x, ra.y, ra.z), qa, ha), oj = obb_world(sb.obb, mk3(rb.x, rb.y, rb.z), qb, hb);
+    obb_enlarge(oi, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
+    if (!obb_intersect(oi, oj)) return;
+    obb_enlarge(oi, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
+    const VA vb{A.vert + (size_t)b * A.S.nvmax};
+    const double rmb = hb * sb.radius;
+    const int* eb = A.S.edges + 2 * sb.e0;
+    // A -> B (swap = 0)
+    const uint8_t f0 = (uint8_t)(ghost << 1);
+    for (int i = 0; i < sa.nv; i++) {
+      const v3 vi = va[i];
+      if (!obb_intersect(oj, obb_point(vi, rma))) continue;
+      for (int j = 0; j < sb.nv; j++)
+        if (filter_vv(rV, vi, rma, vb[j], rmb)) emit<FILL>(C, W, a, cnt, 0, a, b, i, j, f0, idb);
+      for (int j = 0; j < sb.ne; j++)
+        if (filter_ve(rV, vi, rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb)) emit<FILL>(C, W, a, cnt, 1, a, b, i, j, f0, idb);
+      for (int j = 0; j < sb.nf; j++)
+        if (filter_vf(rV, vi, rma, vb, rmb, A.S.fidx + sb.fi0 + A.S.foff[sb.f0 + j], A.S.fn[sb.f0 + j])) emit<FILL>(C, W, a, cnt, 2, a, b, i, j, f0, idb);
+    }
+    for (int i = 0; i < sa.ne; i++)
+      for (int j = 0; j < sb.ne; j++)
+        if (filter_ee(rV, va[ea[2 * i]], va[ea[2 * i + 1]], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb)) emit<FILL>(C, W, a, cnt, 3, a, b, i, j, f0, idb);
+    // B -> A (swap = 1): pi = b, pj = a; the owner stays a (interaction_pair.hpp:75-90)
+    const uint8_t f1 = (uint8_t)(1 | (ghost << 1));
+    for (int j = 0; j < sb.nv; j++) {
+      const v3 vj = vb[j];
+      if (!obb_intersect(oi, obb_point(vj, rmb))) continue;
+      for (int i = 0; i < sa.ne; i++)
+        if (filter_ve(rV, vj, rmb, va[ea[2 * i]], va[ea[2 * i + 1]], rma)) emit<FILL>(C, W, a, cnt, 1, b, a, j, i, f1, idb);
+      for (int i = 0; i < sa.nf; i++)
+        if (filter_vf(rV, vj, rmb, va, rma, A.S.fidx + sa.fi0 + A.S.foff[sa.f0 + i], A.S.fn[sa.f0 + i])) emit<FILL>(C, W, a, cnt, 2, b, a, j, i, f1, idb);
+    }
+  });
+  if (!FILL) {
+    for (int t = 0; t < 7; t++)
+      if (C.c[t]) C.c[t][a] = cnt[t];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// history carry-over: new record -> same key in the previous owner segment (key = partner id, subs, swap; the
+// type is implied by the wave, the owner by the segment).  interaction_pair.hpp:204-216, placeholder_interaction.hpp:398-408
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_history(WView nw, WView ow, const uint32_t* __restrict__ new2old, uint32_t n_old_real, bool has_sub) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nw.n) return;
+  const uint8_t fl = nw.flg[k];
+  const uint2 ij = nw.ij[k];
+  const uint32_t owner = (fl & 1) ? ij.y : ij.x;
+  const uint32_t oo = new2old[owner];
+  if (oo >= n_old_real) return;
+  const double4 ft = nw.ft[k];
+  const long long pid = __double_as_longlong(ft.w);
+  uint2 sb = make_uint2(0, 0);
+  if (has_sub) sb = nw.sub[k];
+  const uint32_t e = ow.off[oo + 1];
+  for (uint32_t s = ow.off[oo]; s < e; s++) {
+    const double4 oft = ow.ft[s];
+    if (__double_as_longlong(oft.w) != pid) continue;
+    const uint8_t ofl = ow.flg[s];
+    if ((ofl & 1) != (fl & 1)) continue;
+    if (((ofl >> 1) & 3) == 2) continue;  // PartnerGhost records are not history sources (interaction_pair.hpp:108-109)
+    if (has_sub) {
+      const uint2 osb = ow.sub[s];
+      if (osb.x != sb.x || osb.y != sb.y) continue;
+    }
+    nw.ft[k] = make_double4(oft.x, oft.y, oft.z, ft.w);
+    nw.mo[k] = ow.mo[s];
+    return;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// partner incidence lists (particle-particle waves): for every real particle, the records in which it is the
+// PARTNER, as codes (type << 28 | k), sorted ascending so that the gather reproduces the wave-by-wave serial order.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t INC_SHIFT = 28;
+constexpr uint32_t INC_MASK = (1u << INC_SHIFT) - 1;
+
+template <bool FILL>
+__global__ void k_incidence(WView w, int type, uint32_t nreal, uint32_t* __restrict__ cnt_or_fill,
+                            const uint32_t* __restrict__ inc_off, uint32_t* __restrict__ inc) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= w.n) return;
+  const uint2 ij = w.ij[k];
+  const uint32_t partner = (w.flg[k] & 1) ? ij.x : ij.y;
+  if (partner >= nreal) return;  // forces on ghost copies are discarded (quirk Q6)
+  const uint32_t s = atomicAdd(&cnt_or_fill[partner], 1u);
+  if (FILL) inc[inc_off[partner] + s] = ((uint32_t)type << INC_SHIFT) | k;
+}
+__global__ void k_incidence_sort(const uint32_t* __restrict__ inc_off, uint32_t* __restrict__ inc, uint32_t nreal) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nreal) return;
+  const uint32_t b = inc_off[p], e = inc_off[p + 1];
+  for (uint32_t i = b + 1; i < e; i++) {
+    const uint32_t v = inc[i];
+    uint32_t j = i;
+    while (j > b && inc[j - 1] > v) {
+      inc[j] = inc[j - 1];
+      j--;
+    }
+    inc[j] = v;
+  }
+}
+
+__global__ void k_backup(const double4* __restrict__ pr, const double4* __restrict__ q, double4* __restrict__ pr_b,
+                         double4* __restrict__ q_b, uint32_t n) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  pr_b[p] = pr[p];
+  if (q_b) q_b[p] = q[p];
+}
+
+}  // namespace edb

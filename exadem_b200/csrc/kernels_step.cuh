@@ -1,0 +1,432 @@
+// kernels_step.cuh — per-time-step kernels (sm_100a, fp64, HBM-bound gather/scatter; no tensor cores by design).
+//
+//   k_prolog / k_epilog ...   streaming per-particle operators (src/numericalscheme/*)
+//   k_contact_*               one thread per interaction record of a wave (classifier_for_all.hpp:116-156):
+//                             gather the two particles (3 aligned 32-byte sectors each), detect, Hooke law,
+//                             update the friction/moment history in place, emit (f, dn, cp)
+//   k_gather                  one thread per particle: deterministic, fixed-order sum of the wrenches of all records
+//                             incident to the particle (owner segment = contiguous; partner side = incidence list)
+//                             — replaces the reference's 12 atomic adds per contact (contact_sphere.hpp:183-196)
+#pragma once
+#include "common.cuh"
+#include "kernels_rebuild.cuh"
+
+namespace edb {
+
+__device__ __forceinline__ uint32_t group_of(const double4& wg) {
+  return (uint32_t)(((unsigned long long)__double_as_longlong(wg.w)) >> 32);
+}
+__device__ __forceinline__ uint32_t type_of(const double4& wg) {
+  return (uint32_t)(((unsigned long long)__double_as_longlong(wg.w)) & 0xffffffffu);
+}
+__device__ __forceinline__ const Params& cp_pp(const ParamsDev& P, uint32_t ga, uint32_t gb) {
+  return P.tpp ? P.tpp[ga * P.n_groups + gb] : P.pp;
+}
+__device__ __forceinline__ const Params& cp_pd(const ParamsDev& P, uint32_t ga, uint32_t d) {
+  return P.tpd ? P.tpd[ga * P.n_drivers + d] : P.pd;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// streaming operators
+// ---------------------------------------------------------------------------------------------------------------
+// combined_compute_prolog.cu:35-47: r += v dt + a dt^2/2 ; v += a dt/2 ; Q = normalize(Q + dot(Q,w) dt) ; w += arot dt/2
+// (fx,fy,fz hold the ACCELERATION here: force_to_accel ran at the end of the previous step.)
+__global__ void k_prolog(PView P, uint32_t n, double dt, double dt2, double hdt) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double4 r = P.pr[p], v = P.vm[p], w = P.wg[p], Q = P.q[p];
+  const double ax = P.fx[p], ay = P.fy[p], az = P.fz[p];
+  r.x += v.x * dt + ax * dt2; r.y += v.y * dt + ay * dt2; r.z += v.z * dt + az * dt2;
+  v.x += ax * hdt; v.y += ay * hdt; v.z += az * hdt;
+  const q4 q{Q.x, Q.y, Q.z, Q.w};
+  const q4 dq = qdot(q, mk3(w.x, w.y, w.z));
+  q4 nq{q.w + dq.w * dt, q.x + dq.x * dt, q.y + dq.y * dt, q.z + dq.z * dt};
+  const double nn = sqrt(nq.w * nq.w + nq.x * nq.x + nq.y * nq.y + nq.z * nq.z);
+  Q = make_double4(nq.w / nn, nq.x / nn, nq.y / nn, nq.z / nn);
+  const v3 wn = mk3(w.x, w.y, w.z) + hdt * mk3(P.ax[p], P.ay[p], P.az[p]);
+  w.x = wn.x; w.y = wn.y; w.z = wn.z;
+  P.pr[p] = r; P.vm[p] = v; P.wg[p] = w; P.q[p] = Q;
+}
+// push_to_quaternion.hpp:26-38
+__global__ void k_push_to_quaternion(PView P, uint32_t n, double dt, double hdt) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double4 w = P.wg[p], Q = P.q[p];
+  const q4 q{Q.x, Q.y, Q.z, Q.w};
+  const q4 dq = qdot(q, mk3(w.x, w.y, w.z));
+  q4 nq{q.w + dq.w * dt, q.x + dq.x * dt, q.y + dq.y * dt, q.z + dq.z * dt};
+  const double nn = sqrt(nq.w * nq.w + nq.x * nq.x + nq.y * nq.y + nq.z * nq.z);
+  P.q[p] = make_double4(nq.w / nn, nq.x / nn, nq.y / nn, nq.z / nn);
+  const v3 wn = mk3(w.x, w.y, w.z) + hdt * mk3(P.ax[p], P.ay[p], P.az[p]);
+  w.x = wn.x; w.y = wn.y; w.z = wn.z;
+  P.wg[p] = w;
+}
+// angular_acceleration.hpp:27-43
+__device__ __forceinline__ v3 ang_accel(const double4& Q, v3 mom, v3 w, v3 I) {
+  const q4 q{Q.x, Q.y, Q.z, Q.w};
+  const q4 qi = qconj(q);
+  const v3 o = qrot(qi, w), M = qrot(qi, mom);
+  const v3 dw = mk3((M.x - (I.z - I.y) * o.y * o.z) / I.x, (M.y - (I.x - I.z) * o.z * o.x) / I.y,
+                    (M.z - (I.y - I.x) * o.x * o.y) / I.z);
+  return qrot(q, dw);
+}
+// MODE 0: push_to_angular_acceleration; 1: push_to_angular_velocity; 2: combined_compute_epilog (.cu:35-46)
+template <int MODE>
+__global__ void k_epilog(PView P, uint32_t n, double hdt) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  double4 w = P.wg[p];
+  v3 ar;
+  if (MODE == 0 || MODE == 2) {
+    ar = ang_accel(P.q[p], mk3(P.mx[p], P.my[p], P.mz[p]), mk3(w.x, w.y, w.z), mk3(P.ix[p], P.iy[p], P.iz[p]));
+    P.ax[p] = ar.x; P.ay[p] = ar.y; P.az[p] = ar.z;
+  } else {
+    ar = mk3(P.ax[p], P.ay[p], P.az[p]);
+  }
+  if (MODE == 1 || MODE == 2) {
+    const v3 wn = mk3(w.x, w.y, w.z) + ar * hdt;  // angular_velocity.hpp:27-33
+    w.x = wn.x; w.y = wn.y; w.z = wn.z;
+    P.wg[p] = w;
+  }
+  if (MODE == 2) {
+    double4 v = P.vm[p];
+    v.x += P.fx[p] * hdt; v.y += P.fy[p] * hdt; v.z += P.fz[p] * hdt;
+    P.vm[p] = v;
+  }
+}
+__global__ void k_reset_fm(PView P, uint32_t n) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  P.fx[p] = 0; P.fy[p] = 0; P.fz[p] = 0; P.mx[p] = 0; P.my[p] = 0; P.mz[p] = 0;
+}
+__global__ void k_gravity(PView P, uint32_t n, double gx, double gy, double gz) {  // gravity_force.hpp:38-46
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double m = P.vm[p].w;
+  P.fx[p] += gx * m; P.fy[p] += gy * m; P.fz[p] += gz * m;
+}
+__global__ void k_force_to_accel(PView P, uint32_t n) {  // force_to_accel.hpp:26-33
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double m = P.vm[p].w;
+  P.fx[p] /= m; P.fy[p] /= m; P.fz[p] /= m;
+}
+__global__ void k_freeze(PView P, uint32_t n) {  // freeze_particles.cu:33-88 (whole grid)
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  P.fx[p] = 0; P.fy[p] = 0; P.fz[p] = 0; P.mx[p] = 0; P.my[p] = 0; P.mz[p] = 0;
+  double4 v = P.vm[p], w = P.wg[p];
+  v.x = v.y = v.z = 0; w.x = w.y = w.z = 0;
+  P.vm[p] = v; P.wg[p] = w;
+}
+// compute_vertices.hpp:26-67: world vertex k of particle p = r + Q*(h*v_k)  (shape.hpp:259-262)
+__global__ void k_compute_vertices(PView P, uint32_t n, ShapesView S, double4* __restrict__ vert) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double4 r = P.pr[p], Q = P.q[p];
+  const ShapeDev sh = S.sh[type_of(P.wg[p])];
+  const double h = P.h[p];
+  const q4 q{Q.x, Q.y, Q.z, Q.w};
+  for (int k = 0; k < sh.nv; k++) {
+    const v3 w = mk3(r.x, r.y, r.z) + qrot(q, h * S.verts[sh.v0 + k]);
+    vert[(size_t)p * S.nvmax + k] = make_double4(w.x, w.y, w.z, 0.0);
+  }
+}
+// particle_displ_over / vertex_displ_over (backup_dem.hpp:66-100): count of particles (vertices) with |d|^2 >= thr^2
+template <bool POLY>
+__global__ void k_displ_over(PView P, const double4* __restrict__ pr_b, const double4* __restrict__ q_b, uint32_t n,
+                             ShapesView S, double thr2, unsigned long long* __restrict__ count) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int c = 0;
+  if (p < n) {
+    const double4 r = P.pr[p], rb = pr_b[p];
+    if (!POLY) {
+      const v3 d = mk3(r.x, r.y, r.z) - mk3(rb.x, rb.y, rb.z);
+      c = dot(d, d) >= thr2 ? 1 : 0;
+    } else {
+      const ShapeDev sh = S.sh[type_of(P.wg[p])];
+      const double h = P.h[p];
+      const double4 Q = P.q[p], Qb = q_b[p];
+      const q4 q{Q.x, Q.y, Q.z, Q.w}, qb{Qb.x, Qb.y, Qb.z, Qb.w};
+      for (int k = 0; k < sh.nv; k++) {
+        const v3 lv = h * S.verts[sh.v0 + k];
+        const v3 vo = mk3(rb.x, rb.y, rb.z) + qrot(qb, lv);
+        const v3 vn = mk3(r.x, r.y, r.z) + qrot(q, lv);
+        const v3 d = vn - vo;
+        c += dot(d, d) >= thr2 ? 1 : 0;
+      }
+    }
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, (unsigned long long)c);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// contact waves
+// ---------------------------------------------------------------------------------------------------------------
+struct ContactArgs {
+  PView P;
+  WView w;
+  ParamsDev prm;
+  const Driver* drv;
+  const double4* vert;
+  ShapesView S;
+  double dt;
+  int type;
+  int symetric;
+};
+
+// finish one record: history update + ContactState emission.  `contact` already includes the cohesive extension.
+template <int LAW>
+__device__ __forceinline__ void finish_record(const ContactArgs& A, uint32_t k, bool contact, const Contact& c, const Params& cp,
+                                              double meff, double reff, v3 ri, v3 vi, v3 wi, v3 pj, v3 vj, v3 wj) {
+  if (contact) {
+    const double4 ft4 = A.w.ft[k], mo4 = A.w.mo[k];
+    v3 ft = mk3(ft4.x, ft4.y, ft4.z), mom = mk3(mo4.x, mo4.y, mo4.z), f = mk3(0, 0, 0);
+    contact_force<LAW>(c.dn, c.n, A.dt, cp, meff, reff, ft, c.cp, ri, vi, f, mom, wi, pj, vj, wj);
+    A.w.ft[k] = make_double4(ft.x, ft.y, ft.z, ft4.w);
+    A.w.mo[k] = make_double4(mom.x, mom.y, mom.z, 1.0);   // .w = 1 marks "contact this step" for the gather
+    A.w.fd[k] = make_double4(f.x, f.y, f.z, c.dn);
+  } else {
+    // item.reset(); dn = 0 (contact_sphere.hpp:197-200) — friction & moment history are dropped
+    const double4 ft4 = A.w.ft[k];
+    A.w.ft[k] = make_double4(0, 0, 0, ft4.w);
+    A.w.mo[k] = make_double4(0, 0, 0, 0);
+    A.w.fd[k] = make_double4(0, 0, 0, 0);
+  }
+  A.w.cp[k] = make_double4(c.cp.x, c.cp.y, c.cp.z, 0);
+}
+
+// wave 0 of the sphere operator: sphere::ContactLawFunc (contact_sphere.hpp:121-203)
+template <int LAW>
+__global__ void __launch_bounds__(BLK) k_contact_sphere_pp(ContactArgs A) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= A.w.n) return;
+  const uint2 ij = A.w.ij[k];
+  const double4 pi = A.P.pr[ij.x], pj = A.P.pr[ij.y];
+  const v3 ri = mk3(pi.x, pi.y, pi.z), rj = mk3(pj.x, pj.y, pj.z);
+  const Contact c = detect_vv(ri, pi.w, rj, pj.w);
+  const double4 wi = A.P.wg[ij.x], wj = A.P.wg[ij.y];
+  const Params& cp = cp_pp(A.prm, group_of(wi), group_of(wj));
+  bool contact = c.hit;
+  if (LAW == LAW_COHESIVE) contact = contact || c.dn <= cp.dncut;
+  double meff = 0, reff = 0;
+  double4 vi = make_double4(0, 0, 0, 0), vj = vi;
+  if (contact) {
+    vi = A.P.vm[ij.x]; vj = A.P.vm[ij.y];
+    meff = (vi.w * vj.w) / (vi.w + vj.w);   // common_kernels.hpp:93-96
+    reff = (pi.w * pj.w) / (pi.w + pj.w);   // :99-102
+  }
+  finish_record<LAW>(A, k, contact, c, cp, meff, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), rj,
+                     mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z));
+}
+
+// waves 4,5,6 (cylinder / surface / ball): sphere::ContactLawDriverFunc (contact_sphere.hpp:232-296),
+// polyhedron::ContactLawDriverFunc (polyhedron/contact.hpp:237-303)
+template <int LAW, bool POLY>
+__global__ void __launch_bounds__(BLK) k_contact_driver(ContactArgs A) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= A.w.n) return;
+  const uint2 ij = A.w.ij[k];
+  const Driver D = A.drv[ij.y];
+  const double4 pi = A.P.pr[ij.x], wi = A.P.wg[ij.x];
+  const v3 ri = mk3(pi.x, pi.y, pi.z);
+  Contact c;
+  double reff;
+  if (!POLY) {
+    c = driver_detect(D, pi.w, ri);
+    reff = pi.w;
+  } else {
+    const ShapeDev sh = A.S.sh[type_of(wi)];
+    const double rm = A.P.h[ij.x] * sh.radius;
+    const double4 vx = A.vert[(size_t)ij.x * A.S.nvmax + A.w.sub[k].x];
+    c = driver_detect(D, rm, mk3(vx.x, vx.y, vx.z));
+    reff = rm;
+  }
+  const Params& cp = cp_pd(A.prm, group_of(wi), ij.y);
+  bool contact = c.hit;
+  if (LAW == LAW_COHESIVE) contact = contact || c.dn <= cp.dncut;
+  double4 vi = make_double4(0, 0, 0, 0);
+  if (contact) vi = A.P.vm[ij.x];
+  finish_record<LAW>(A, k, contact, c, cp, vi.w, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), D.center, D.vel, D.vrot);
+}
+
+// waves 0..3 of the polyhedron operator: polyhedron::ContactLawFunc<type> (polyhedron/contact.hpp:124-211)
+template <int LAW>
+__global__ void __launch_bounds__(BLK) k_contact_poly_pp(ContactArgs A) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= A.w.n) return;
+  const uint2 ij = A.w.ij[k], sb = A.w.sub[k];
+  const double4 pi = A.P.pr[ij.x], pj = A.P.pr[ij.y];
+  const double4 wi = A.P.wg[ij.x], wj = A.P.wg[ij.y];
+  const ShapeDev si = A.S.sh[type_of(wi)], sj = A.S.sh[type_of(wj)];
+  const double rmi = A.P.h[ij.x] * si.radius, rmj = A.P.h[ij.y] * sj.radius;
+  const VA vi_{A.vert + (size_t)ij.x * A.S.nvmax}, vj_{A.vert + (size_t)ij.y * A.S.nvmax};
+  Contact c;
+  if (A.type == 0) {
+    c = detect_vv(vi_[sb.x], rmi, vj_[sb.y], rmj);
+  } else if (A.type == 1) {
+    const int* e = A.S.edges + 2 * (sj.e0 + sb.y);
+    c = detect_ve(vi_[sb.x], rmi, vj_[e[0]], vj_[e[1]], rmj);
+  } else if (A.type == 2) {
+    c = detect_vf(vi_[sb.x], rmi, vj_, rmj, A.S.fidx + sj.fi0 + A.S.foff[sj.f0 + sb.y], A.S.fn[sj.f0 + sb.y]);
+  } else {
+    const int* ei = A.S.edges + 2 * (si.e0 + sb.x);
+    const int* ej = A.S.edges + 2 * (sj.e0 + sb.y);
+    c = detect_ee(vi_[ei[0]], vi_[ei[1]], rmi, vj_[ej[0]], vj_[ej[1]], rmj);
+  }
+  const Params& cp = cp_pp(A.prm, group_of(wi), group_of(wj));
+  bool contact = c.hit;
+  if (LAW == LAW_COHESIVE) contact = contact || c.dn <= cp.dncut;
+  double meff = 0, reff = 0;
+  double4 vi = make_double4(0, 0, 0, 0), vj = vi;
+  if (contact) {
+    vi = A.P.vm[ij.x]; vj = A.P.vm[ij.y];
+    meff = (vi.w * vj.w) / (vi.w + vj.w);
+    reff = (rmi * rmj) / (rmi + rmj);  // contact.hpp:183 (effective-mass formula on the Minkowski radii)
+  }
+  finish_record<LAW>(A, k, contact, c, cp, meff, reff, mk3(pi.x, pi.y, pi.z), mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z),
+                     mk3(pj.x, pj.y, pj.z), mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// deterministic force / torque gather
+// ---------------------------------------------------------------------------------------------------------------
+struct GatherArgs {
+  PView P;
+  WTab W;
+  int order[NT];     // wave order of the operator (sphere: 0,4,5,6,7,8,9 ; polyhedron: 0..3,7..12,4,5,6)
+  int norder;
+  const uint32_t* inc_off;
+  const uint32_t* inc;
+  uint32_t nreal;
+  int pp_partner;    // 1: add the reaction on the partner (symetric spheres, all polyhedra)
+  int has_swap;      // polyhedra: role of the owner depends on the swap bit
+  double g[3];
+  double hdt;
+};
+
+// role_i: particle acts as "i" of the record: F += f, M += (cp - r) x f + mom;  as "j": F += -f, M += (cp - r) x (-f) + (-mom)
+__device__ __forceinline__ void add_wrench(const WView& w, uint32_t k, bool role_i, v3 r, v3& F, v3& M) {
+  const double4 mo = w.mo[k];
+  if (mo.w == 0.0) return;  // no contact this step: the record contributes nothing (f = 0, mom = 0)
+  const double4 fd = w.fd[k], cp = w.cp[k];
+  v3 f = mk3(fd.x, fd.y, fd.z), m = mk3(mo.x, mo.y, mo.z);
+  if (!role_i) {
+    f = -f;
+    m = -m;
+  }
+  const v3 t = moments(mk3(cp.x, cp.y, cp.z), r, f, m);
+  M.x += t.x; M.y += t.y; M.z += t.z;   // lockAndAdd(mom, ...) first, then f (contact_sphere.hpp:183-189)
+  F.x += f.x; F.y += f.y; F.z += f.z;
+}
+
+// FUSE 0: [contact_*] only: f, mom += sum        (drop-in operator semantics: accumulate on top of gravity etc.)
+// FUSE 1: reset_force_moment + gravity_force + contact + force_to_accel + combined_compute_epilog in one pass
+template <int FUSE>
+__global__ void __launch_bounds__(BLK) k_gather(GatherArgs A) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= A.nreal) return;
+  const double4 pr = A.P.pr[p];
+  const v3 r = mk3(pr.x, pr.y, pr.z);
+  v3 F, M;
+  double4 vm;
+  if (FUSE) {
+    vm = A.P.vm[p];
+    F = mk3(0.0 + A.g[0] * vm.w, 0.0 + A.g[1] * vm.w, 0.0 + A.g[2] * vm.w);
+    M = mk3(0, 0, 0);
+  } else {
+    F = mk3(A.P.fx[p], A.P.fy[p], A.P.fz[p]);
+    M = mk3(A.P.mx[p], A.P.my[p], A.P.mz[p]);
+  }
+  uint32_t e = A.inc_off ? A.inc_off[p] : 0;
+  const uint32_t eend = A.inc_off ? A.inc_off[p + 1] : 0;
+  uint32_t code = e < eend ? A.inc[e] : 0xffffffffu;
+  for (int o = 0; o < A.norder; o++) {
+    const int t = A.order[o];
+    const WView& w = A.W.w[t];
+    if (w.n == 0) continue;
+    const uint32_t a = w.off[p], b = w.off[p + 1];
+    if (t <= 3 && A.pp_partner) {  // partner records that precede the owner segment in wave order
+      while ((code >> INC_SHIFT) == (uint32_t)t && (code & INC_MASK) < a) {
+        const uint32_t k = code & INC_MASK;
+        const bool owner_is_i = A.has_swap ? !(w.flg[k] & 1) : true;
+        add_wrench(w, k, !owner_is_i, r, F, M);
+        e++;
+        code = e < eend ? A.inc[e] : 0xffffffffu;
+      }
+    }
+    for (uint32_t k = a; k < b; k++) {
+      const bool owner_is_i = (t <= 3 && A.has_swap) ? !(w.flg[k] & 1) : true;
+      add_wrench(w, k, owner_is_i, r, F, M);
+    }
+    if (t <= 3 && A.pp_partner) {
+      while ((code >> INC_SHIFT) == (uint32_t)t) {
+        const uint32_t k = code & INC_MASK;
+        const bool owner_is_i = A.has_swap ? !(w.flg[k] & 1) : true;
+        add_wrench(w, k, !owner_is_i, r, F, M);
+        e++;
+        code = e < eend ? A.inc[e] : 0xffffffffu;
+      }
+    }
+  }
+  if (!FUSE) {
+    A.P.fx[p] = F.x; A.P.fy[p] = F.y; A.P.fz[p] = F.z;
+    A.P.mx[p] = M.x; A.P.my[p] = M.y; A.P.mz[p] = M.z;
+  } else {
+    // force_to_accel, then combined_compute_epilog
+    const v3 acc = mk3(F.x / vm.w, F.y / vm.w, F.z / vm.w);
+    double4 w = A.P.wg[p];
+    const v3 ar = ang_accel(A.P.q[p], M, mk3(w.x, w.y, w.z), mk3(A.P.ix[p], A.P.iy[p], A.P.iz[p]));
+    const v3 wn = mk3(w.x, w.y, w.z) + ar * A.hdt;
+    w.x = wn.x; w.y = wn.y; w.z = wn.z;
+    vm.x += acc.x * A.hdt; vm.y += acc.y * A.hdt; vm.z += acc.z * A.hdt;
+    A.P.fx[p] = acc.x; A.P.fy[p] = acc.y; A.P.fz[p] = acc.z;
+    A.P.mx[p] = M.x; A.P.my[p] = M.y; A.P.mz[p] = M.z;
+    A.P.ax[p] = ar.x; A.P.ay[p] = ar.y; A.P.az[p] = ar.z;
+    A.P.wg[p] = w; A.P.vm[p] = vm;
+  }
+}
+
+// compute_driver_force_moment.cu:34-54 — per-driver sum of -(fn+ft) and of (cp - center) x (-(fn+ft)) - moment over the driver waves.
+// Deterministic: one block per driver wave chunk writes a partial; partials are summed in order on the host side buffer.
+__global__ void __launch_bounds__(BLK) k_driver_force(WView w, const Driver* __restrict__ drv, int ndrv, double* __restrict__ partial) {
+  // partial layout: [block][driver][6]
+  extern __shared__ double sm[];
+  double* acc = sm;  // ndrv*6 per warp
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < nw * ndrv * 6; i += blockDim.x) acc[i] = 0.0;
+  __syncthreads();
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  v3 f = mk3(0, 0, 0), m = mk3(0, 0, 0);
+  int d = -1;
+  if (k < w.n) {
+    const double4 mo = w.mo[k];
+    if (mo.w != 0.0) {
+      const double4 fd = w.fd[k], cp = w.cp[k], ft4 = w.ft[k];
+      d = (int)w.ij[k].y;
+      const v3 ft = mk3(ft4.x, ft4.y, ft4.z);
+      const v3 fn = mk3(fd.x, fd.y, fd.z) - ft;   // ContactState fn (contact_sphere.hpp:180)
+      f = -(fn + ft);                              // compute_driver_force_moment.cu:46-47
+      m = cross(mk3(cp.x, cp.y, cp.z) - drv[d].center, f) + -mk3(mo.x, mo.y, mo.z);  // :48-49
+    }
+  }
+  // serial, lane-ordered accumulation inside each warp keeps the sum order fixed
+  for (int l = 0; l < 32; l++) {
+    const int dl = __shfl_sync(0xffffffffu, d, l);
+    const double fx = __shfl_sync(0xffffffffu, f.x, l), fy = __shfl_sync(0xffffffffu, f.y, l), fz = __shfl_sync(0xffffffffu, f.z, l);
+    const double mx = __shfl_sync(0xffffffffu, m.x, l), my = __shfl_sync(0xffffffffu, m.y, l), mz = __shfl_sync(0xffffffffu, m.z, l);
+    if (lane == 0 && dl >= 0) {
+      double* a = acc + (wid * ndrv + dl) * 6;
+      a[0] += fx; a[1] += fy; a[2] += fz; a[3] += mx; a[4] += my; a[5] += mz;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ndrv * 6; i += blockDim.x) {
+    double s = 0;
+    for (int ww = 0; ww < nw; ww++) s += acc[ww * ndrv * 6 + i];
+    partial[(size_t)blockIdx.x * ndrv * 6 + i] = s;
+  }
+}
+
+}  // namespace edb

@@ -99,6 +99,7 @@ struct Sim {
 
   // grid (with 1 ghost layer)
   int nc[3]{1, 1, 1}, g[3]{3, 3, 3};
+  double cs[3]{1, 1, 1};  // effective cell size per axis: (hi-lo)/nc >= cfg.cell_size
   std::vector<uint32_t> cstart, citems;
 
   std::vector<Inter> inter;                 // "ges": owner-major, enumeration order
@@ -137,14 +138,16 @@ static void wrap_positions(Sim& s) {
   }
 }
 static inline int cell_coord(const Sim& s, double x, int d) {
-  int c = (int)std::floor((x - s.cfg.lo[d]) / s.cfg.cell_size);
+  int c = (int)std::floor((x - s.cfg.lo[d]) / s.cs[d]);
   if (c < 0) c = 0;
   if (c > s.nc[d] - 1) c = s.nc[d] - 1;
   return c;
 }
 static void build_grid(Sim& s) {
   for (int d = 0; d < 3; d++) {
+    // the grid covers the brick exactly: nc cells of size (hi-lo)/nc >= cell_size (exaNBody: grid_dims*cell_size = bounds)
     s.nc[d] = std::max(1, (int)std::floor((s.cfg.hi[d] - s.cfg.lo[d]) / s.cfg.cell_size + 1e-9));
+    s.cs[d] = (s.cfg.hi[d] - s.cfg.lo[d]) / s.nc[d];
     s.g[d] = s.nc[d] + 2;
   }
   s.resize_particles(s.nreal);
@@ -449,7 +452,12 @@ static inline void contact_one(Sim& s, Inter& I, double dt, Acc& acc) {
 static void contact_all(Sim& s, double dt) {
   const bool par = s.omp_threads > 1;
   Acc acc{s, par};
-  for (int t = 0; t < EDB_NTYPES; t++) {
+  // wave order of the operators: contact_force_sphere.cu.in:159-170 (0,4,5,6,7..9), contact_force_polyhedron.cu.in:186-216 (0..3,7..12,4,5,6)
+  static const int order_s[] = {0, 4, 5, 6, 7, 8, 9, 1, 2, 3, 10, 11, 12, 13};
+  static const int order_p[] = {0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 4, 5, 6, 13};
+  const int* order = s.cfg.mode == EDB_MODE_POLYHEDRON ? order_p : order_s;
+  for (int o = 0; o < EDB_NTYPES; o++) {
+    const int t = order[o];
     auto& w = s.wave[t];
     const long n = (long)w.size();
     if (!par) {
@@ -709,7 +717,7 @@ int orc_compute_driver_force_moment(orc_sim* h, double* forces, double* moments)
       const Inter& I = s.inter[k];
       const size_t d = I.id_j;
       const v3 f = -(I.fn + I.ft);
-      const v3 m = cross(I.cp - s.drivers[d].center, f);
+      const v3 m = cross(I.cp - s.drivers[d].center, f) + -I.mom;
       forces[3 * d] += f.x; forces[3 * d + 1] += f.y; forces[3 * d + 2] += f.z;
       moments[3 * d] += m.x; moments[3 * d + 1] += m.y; moments[3 * d + 2] += m.z;
     }

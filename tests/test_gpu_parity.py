@@ -1,0 +1,219 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars: interaction/candidate set bit-exact as a sorted set; forces, torques, positions, velocities, quaternions within
+1e-10 (relative to the field scale) in fp64 — north_star.  Sizes are chosen so that the oracle finishes in seconds."""
+import numpy as np
+import pytest
+
+from exadem_b200 import Engine, capi, workloads
+from oracle_binding import OracleEngine
+from parity import bit_identical, compare_interaction_sets, compare_particles, field_close
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def pair(wl, product_lib, oracle_lib):
+    gpu = wl.setup(Engine(product_lib, wl.config()))
+    cpu = wl.setup(OracleEngine(oracle_lib, wl.config()))
+    return gpu, cpu
+
+
+def both(engines, fn):
+    for e in engines:
+        fn(e)
+
+
+def check(gpu, cpu, rtol=RTOL, payload=True):
+    n = compare_interaction_sets(gpu.export_interactions(), cpu.export_interactions(), payload_rtol=rtol if payload else None)
+    errs = compare_particles(gpu.download_particles(), cpu.download_particles(), rtol=rtol)
+    return n, errs
+
+
+def test_sphere_operators_one_by_one(product_lib, oracle_lib):
+    """The reference's operator sequence of one Verlet step (config_numerical_schemes.msp:6-30), operator by operator."""
+    wl = workloads.spheres_box((9, 8, 10), jitter=0.03, omega_sigma=0.5, polydisperse=0.2)
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    es = (gpu, cpu)
+    both(es, lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    cg, _ = gpu.interaction_counts()
+    cc, _ = cpu.interaction_counts()
+    assert np.array_equal(cg, cc) and cg[0] > 1000
+    for step in range(3):
+        for op in (lambda e: e.combined_compute_prolog(wl.dt), lambda e: e.ghost_update_rq(), lambda e: e.reset_force_moment(),
+                   lambda e: e.gravity_force(wl.gravity), lambda e: e.contact_sphere(wl.dt), lambda e: e.force_to_accel(),
+                   lambda e: e.combined_compute_epilog(wl.dt)):
+            both(es, op)
+            check(gpu, cpu)
+    _, active = gpu.interaction_counts()
+    assert active[0] > 100  # friction history is being exercised
+
+
+def test_unfused_push_operators(product_lib, oracle_lib):
+    wl = workloads.spheres_box((6, 6, 6), jitter=0.03, omega_sigma=1.0)
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    es = (gpu, cpu)
+    both(es, lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    for op in (lambda e: e.reset_force_moment(), lambda e: e.gravity_force((0.3, -0.2, -9.807)), lambda e: e.contact_sphere(wl.dt),
+               lambda e: e.push_to_angular_acceleration(), lambda e: e.push_to_angular_velocity(wl.dt),
+               lambda e: e.push_to_quaternion(wl.dt), lambda e: e.force_to_accel(), lambda e: e.freeze_particles()):
+        both(es, op)
+        check(gpu, cpu)
+
+
+@pytest.mark.parametrize("rebuild_every", [-1, 4, 0])
+def test_drum_fused_run(product_lib, oracle_lib, rebuild_every):
+    """S2-like drum (cylinder driver, periodic y) through the fused numerical_scheme_verlet path."""
+    wl = workloads.rotating_drum(6000, jitter=0.02)
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 24, rebuild_every) for e in (gpu, cpu)]
+    assert nb[0] == nb[1]
+    n, errs = check(gpu, cpu)
+    cg, ag = gpu.interaction_counts()
+    assert cg[4] > 0 and ag[0] > 0
+    # the fused path equals the operator-by-operator path bit for bit
+    gpu2 = wl.setup(Engine(product_lib, wl.config()))
+    gpu2.update_particle_neighbors(wl.rcut_inc, True)
+    for it in range(24):
+        gpu2.combined_compute_prolog(wl.dt)
+        if rebuild_every > 0 and (it + 1) % rebuild_every == 0 or rebuild_every == 0 and gpu2.displ_over(0.5 * wl.rcut_inc) > 0:
+            gpu2.update_particle_neighbors(wl.rcut_inc, True)
+        else:
+            gpu2.ghost_update_rq()
+        gpu2.reset_force_moment(); gpu2.gravity_force(wl.gravity); gpu2.contact_sphere(wl.dt); gpu2.force_to_accel()
+        gpu2.combined_compute_epilog(wl.dt)
+    assert all(bit_identical(gpu.download_particles(), gpu2.download_particles()).values())
+
+
+def test_history_survives_rebuild(product_lib, oracle_lib):
+    wl = workloads.spheres_box((8, 8, 8), jitter=0.03, omega_sigma=0.3)
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    both((gpu, cpu), lambda e: e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 6, -1))
+    before = gpu.export_interactions()
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    after = gpu.export_interactions()
+    compare_interaction_sets(after, cpu.export_interactions(), payload_rtol=RTOL)
+    nz_b = int((np.abs(before["friction"]).sum(axis=1) > 0).sum())
+    nz_a = int((np.abs(after["friction"]).sum(axis=1) > 0).sum())
+    assert nz_b > 50 and nz_a == nz_b  # no particle moved out of range in 6 steps: every active record is carried over
+
+
+@pytest.mark.parametrize("law", [capi.LAW_COHESIVE, capi.LAW_DMT])
+def test_cohesive_and_dmt_laws(product_lib, oracle_lib, law):
+    wl = workloads.deposit((8, 8, 6))
+    wl.law = law
+    wl.params = dict(wl.params, fc=10.0, dncut=0.1, gamma=10.0)      # rotating-drum-periodic-cohesion.msp:30-34, add_xyz.msp:59
+    wl.params_driver = dict(wl.params)
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    both((gpu, cpu), lambda e: e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 12, 5))
+    check(gpu, cpu)
+    dn_g, cp_g, fn_g, ft_g = gpu.get_contact_state(0)
+    dn_c, cp_c, fn_c, ft_c = cpu.get_contact_state(0)
+    assert len(dn_g) == len(dn_c) > 0
+
+
+def test_surface_ball_drivers_and_contact_state(product_lib, oracle_lib):
+    wl = workloads.deposit((9, 9, 5))
+    wl.drivers.append(dict(kind=capi.DRIVER_BALL, radius=7.0, center=(4.5, 4.5, 3.0), vel=(0.1, 0, 0), vrot=(0, 0, 0.2)))
+    wl.drivers.append(dict(kind=capi.DRIVER_CYLINDER, radius=6.2, center=(4.5, 4.5, 4.5), axis=(1, 1, 0), vrot=(0, 0, 0.5)))
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    both((gpu, cpu), lambda e: e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 10, 0))
+    check(gpu, cpu)
+    cg, _ = gpu.interaction_counts()
+    assert cg[5] > 0 and cg[6] > 0 and cg[4] > 0
+    # ContactState buffers (dn, cp, fn, ft) per wave, in wave order on both sides (owner-sorted enumeration order)
+    for t in (0, 4, 5, 6):
+        sg, sc = gpu.get_contact_state(t), cpu.get_contact_state(t)
+        for a, b, name in zip(sg, sc, ("dn", "cp", "fn", "ft")):
+            field_close(a, b, RTOL, f"contact state {name} wave {t}")
+    fg, mg = gpu.compute_driver_force_moment(3)
+    fc, mc = cpu.compute_driver_force_moment(3)
+    field_close(fg, fc, 1e-9, "driver forces")
+    field_close(mg, mc, 1e-9, "driver moments")
+
+
+def test_multimat_and_asymmetric(product_lib, oracle_lib):
+    wl = workloads.spheres_box((7, 7, 7), jitter=0.03, omega_sigma=0.2, periodic=(1, 0, 1))
+    wl.particles.group[:] = (np.arange(wl.particles.n) % 3).astype(np.uint32)
+    wl.drivers = [dict(kind=capi.DRIVER_SURFACE, offset=-0.1, normal=(0, 1, 0))]
+    base = wl.params
+    pp = [dict(base, kn=base["kn"] * (1 + 0.1 * (a + b)), mu=0.1 * (1 + a * b)) for a in range(3) for b in range(3)]
+    pd = [dict(base, kt=5e4 * (1 + a)) for a in range(3)]
+    es = []
+    for mk in (lambda: Engine(product_lib, wl.config()), lambda: OracleEngine(oracle_lib, wl.config())):
+        e = mk()
+        e.set_law(wl.law)
+        e.set_drivers(wl.drivers)
+        e.set_contact_params_multimat(3, pp, 1, pd)
+        e.upload_particles(wl.particles)
+        es.append(e)
+    gpu, cpu = es
+    for sym in (True, False):
+        both(es, lambda e: e.update_particle_neighbors(wl.rcut_inc, sym))
+        both(es, lambda e: e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, sym, 5, -1))
+        check(gpu, cpu)
+
+
+def test_edge_cases(product_lib, oracle_lib):
+    # a single particle, no interactions; then two far-apart particles
+    for n_side in ((1, 1, 1), (2, 1, 1)):
+        wl = workloads.spheres_box(n_side, periodic=(0, 0, 0), cell_size=1.0)
+        wl.lo, wl.hi = (-5.0, -5.0, -5.0), (5.0, 5.0, 5.0)
+        wl.particles.rx[:] *= 3.0
+        gpu, cpu = pair(wl, product_lib, oracle_lib)
+        both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+        both((gpu, cpu), lambda e: e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 3, 0))
+        n, _ = check(gpu, cpu)
+        assert n == 0
+
+
+@pytest.mark.parametrize("shapes", [("octahedron",), ("octahedron", "cube")])
+def test_polyhedra(product_lib, oracle_lib, shapes):
+    wl = workloads.polyhedra_box((6, 6, 6), shapes=shapes, pitch=0.78)
+    wl.drivers = [dict(kind=capi.DRIVER_SURFACE, offset=0.15, normal=(0, 0, 1)),
+                  dict(kind=capi.DRIVER_BALL, radius=4.0, center=(2.3, 2.3, 2.3))]
+    wl.periodic = (1, 1, 0)
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    cg, _ = gpu.interaction_counts()
+    cc, _ = cpu.interaction_counts()
+    assert np.array_equal(cg, cc)
+    assert all(cg[t] > 0 for t in (0, 1, 2, 3, 5, 6)), cg
+    check(gpu, cpu)
+    # operator sequence once, then the fused path with rebuilds
+    for op in (lambda e: e.combined_compute_prolog(wl.dt), lambda e: e.ghost_update_rq(), lambda e: e.compute_vertices(),
+               lambda e: e.reset_force_moment(), lambda e: e.gravity_force(wl.gravity), lambda e: e.contact_polyhedron(wl.dt),
+               lambda e: e.force_to_accel(), lambda e: e.combined_compute_epilog(wl.dt)):
+        both((gpu, cpu), op)
+        check(gpu, cpu)
+    nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 12, 4) for e in (gpu, cpu)]
+    assert nb[0] == nb[1] == 3
+    check(gpu, cpu)
+    _, ag = gpu.interaction_counts()
+    assert ag[:4].sum() > 20
+    for t in (0, 1, 2, 3):
+        sg, sc = gpu.get_contact_state(t), cpu.get_contact_state(t)
+        for a, b, name in zip(sg, sc, ("dn", "cp", "fn", "ft")):
+            field_close(a, b, RTOL, f"contact state {name} wave {t}")
+    assert gpu.displ_over(1e-7) == cpu.displ_over(1e-7)
+
+
+def test_bounded_drift_1000_steps(product_lib, oracle_lib):
+    """north_star: bounded drift over 1,000 steps (trajectories are chaotic, so the bar is on conserved-ish aggregates
+    and on the divergence staying small, not on bit equality)."""
+    wl = workloads.spheres_box((6, 6, 6), jitter=2e-5, sigma_v=0.05)
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    g0 = (0.0, 0.0, 0.0)
+    both((gpu, cpu), lambda e: e.run_verlet(wl.dt, g0, wl.rcut_inc, True, 1000, 0))
+    pg, pc = gpu.download_particles(), cpu.download_particles()
+    assert np.isfinite(pg.vec("r")).all()
+    drift = np.max(np.abs(pg.vec("r") - pc.vec("r")))
+    assert drift < 1e-6, drift
+    ek_g = 0.5 * np.sum(pg.mass[:, None] * pg.vec("v") ** 2)
+    ek_c = 0.5 * np.sum(pc.mass[:, None] * pc.vec("v") ** 2)
+    assert abs(ek_g - ek_c) <= 1e-6 * max(ek_c, 1e-30)
