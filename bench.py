@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — measures the DEM contact hot path on N B200s of one node (driver contract in the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload drum|box|box8m|poly]
+
+A "step" is one full Verlet time step of the hot path (prolog -> rebuild-or-ghost-refresh -> contact waves ->
+deterministic gather fused with gravity/force_to_accel/epilog) over the synthetic workload:
+  N = 1 : BASELINE.json configs[1] — 1 M monodisperse spheres in a rotating drum (cylinder driver), fp64.
+  N > 1 : weak scaling, one 1 M-sphere brick per GPU of a periodic box (S5 topology), NCCL ghost exchange.
+metric = interaction-updates/s (sum over waves of records processed by the contact kernels per wall second, whole job);
+particle-steps/s is reported beside it.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "interaction-updates/s"
+UNIT = "interaction-updates/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, help="drum (N=1 default) | box (N>1 default) | box8m | poly")
+    ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampling
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.p = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def make_workload(name, n, rank=0, nranks=1):
+    from exadem_b200 import workloads
+    if name == "drum":
+        return workloads.rotating_drum(n)
+    if name in ("box", "box8m"):
+        side = int(round((8_000_000 if name == "box8m" else n) ** (1.0 / 3.0)))
+        side = max(8, int(round(side / 5.0)) * 5)  # multiple of 2 cells of 2.5
+        from exadem_b200 import parallel
+        return parallel.brick_workload(side, rank, nranks)
+    if name == "poly":
+        side = int(round(n ** (1.0 / 3.0)))
+        return workloads.polyhedra_box((side, side, side), pitch=0.78)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def pinned_like(pa):
+    """Copy of a ParticleArrays whose dynamic fields live in pinned host memory (torch allocator)."""
+    import torch
+    out = pa.copy()
+    keep = []
+    for f in ("rx", "ry", "rz", "vx", "vy", "vz", "vrotx", "vroty", "vrotz", "qw", "qx", "qy", "qz", "fx", "fy", "fz",
+              "momx", "momy", "momz", "arotx", "aroty", "arotz"):
+        t = torch.empty(pa.n, dtype=torch.float64, pin_memory=torch.cuda.is_available())
+        a = t.numpy()
+        a[:] = getattr(pa, f)
+        setattr(out, f, a)
+        keep.append(t)
+    out._pinned = keep
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_run(wl, seconds, threads=None, max_steps=10_000):
+    """Times the oracle (the CPU restatement of the reference path, OpenMP over all host cores) on `wl`.
+    Returns (interaction-updates/s, particle-steps/s, steps, wall seconds, threads)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle_binding import OracleEngine, OracleLibrary
+    lib = OracleLibrary()
+    nthr = threads or (os.cpu_count() or 1)
+    e = wl.setup(OracleEngine(lib, wl.config()))
+    e.set_threads(nthr)
+    e.update_particle_neighbors(wl.rcut_inc, wl.symetric)
+    e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, 2, 0)
+    e.reset_counters()
+    t0 = time.perf_counter()
+    steps = 0
+    chunk = 5
+    while steps < max_steps:
+        e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, chunk, 0)
+        steps += chunk
+        if time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    c = e.counters()
+    return c.interaction_updates / dt, c.particle_steps / dt, steps, dt, nthr
+
+
+def reference_arm(args):
+    """`--impl reference`: the reference's CPU implementation of the path.  The real exaDEM cannot be built here
+    (needs exaNBody + Onika + MPI + yaml-cpp, none present) so this is the oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload or ("drum" if args.gpus == 1 else "box")
+    n_sample = min(args.particles, 200_000)
+    wl = make_workload(name if name != "box8m" else "box", n_sample)
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle_binding import OracleEngine, OracleLibrary
+    lib = OracleLibrary()
+    nthr = os.cpu_count() or 1
+    e = wl.setup(OracleEngine(lib, wl.config()))
+    e.set_threads(nthr)
+    e.update_particle_neighbors(wl.rcut_inc, wl.symetric)
+    e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, max(args.warmup, 1), 0)
+    e.reset_counters()
+    t0 = time.perf_counter()
+    e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, args.steps, 0)
+    dt = time.perf_counter() - t0
+    c = e.counters()
+    val = c.interaction_updates / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "particle_steps_per_s": c.particle_steps / dt,
+            "config": {"workload": f"{name}: bounded sample of {wl.particles.n} spheres of the {args.particles}-particle-per-GPU workload",
+                       "particles": int(wl.particles.n), "rebuild": "displacement trigger rcut_inc/2"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port",
+                             "sample": f"{wl.particles.n} particles x {args.steps} steps, oracle OpenMP"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    import torch
+    from exadem_b200 import Engine, Library, capi, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    name = args.workload or ("drum" if world == 1 else "box")
+    wl = make_workload(name, args.particles, rank, world)
+    lib = Library()
+    cfg = wl.config(device=local) if world == 1 else parallel.brick_config(wl, rank, world, device=local)
+    eng = Engine(lib, cfg)
+    if world > 1:
+        parallel.init_comm(eng, lib, rank)
+    wl.setup(eng)
+    g = wl.gravity
+
+    def barrier():
+        eng.sync()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        eng.sync()
+
+    eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)
+    eng.run_verlet(wl.dt, g, wl.rcut_inc, wl.symetric, max(args.warmup, 3), 0)
+    barrier()
+    eng.reset_counters()
+    eng.set_timing(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    eng.event_record(0)
+    t0 = time.perf_counter()
+    nreb = eng.run_verlet(wl.dt, g, wl.rcut_inc, wl.symetric, args.steps, 0)
+    eng.event_record(1)
+    ms = eng.event_elapsed_ms(0, 1)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    c = eng.counters()
+    eng.set_timing(False)
+    counts, active = eng.interaction_counts()
+    stats = np.array([ms, float(c.interaction_updates), float(c.particle_steps), float(c.kernel_launches), float(nreb)], dtype=np.float64)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor(stats, device="cuda")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0])
+        iu, ps, launches = float(t[1]), float(t[2]), float(t[3])
+    else:
+        iu, ps, launches = stats[1], stats[2], stats[3]
+    value = iu / (ms * 1e-3)
+
+    # ---- e2e: the host owns the grid; every step ships the dynamic fields in and the results out (pinned memory)
+    e2e = None
+    if not args.no_e2e:
+        host = pinned_like(eng.download_particles())
+        h2d = 13 * 8 * host.n
+        d2h = 22 * 8 * host.n
+        ke = max(5, min(args.steps, 40))
+        eng.reset_counters()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            eng.upload_dynamic(host)
+            eng.run_verlet(wl.dt, g, wl.rcut_inc, wl.symetric, 1, 0)
+            eng.download_dynamic(host)
+        barrier()
+        dt = time.perf_counter() - t0
+        ce = eng.counters()
+        iu_e = float(ce.interaction_updates)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([iu_e, dt], device="cuda", dtype=torch.float64)
+            tm = t.clone()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            iu_e, dt = float(t[0]), float(tm[1])
+        e2e = {"value": iu_e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ke,
+               "ms_per_step": 1e3 * dt / ke}
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    # roofline of the dominant kernel (wave 0 contact kernel): algorithmic bytes per launch / mean launch duration
+    rec_per_launch = c.contact_pp_records / max(c.contact_pp_launches, 1)
+    alg_bytes = rec_per_launch * 184.0 + wl.particles.n * 92.0
+    t_launch = (c.contact_pp_ms / max(c.contact_pp_launches, 1)) * 1e-3
+    achieved = alg_bytes / t_launch / 1e9 if t_launch > 0 else 0.0
+    roof = {"kernel": "k_contact_sphere_pp" if wl.mode == 0 else "k_contact_poly_pp", "bound": "hbm", "achieved": achieved,
+            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": t_launch * 1e3,
+            "share_of_step": c.contact_pp_ms / ms if ms > 0 else None,
+            "per_step_ms": {"contact_all": c.contact_ms / args.steps, "gather_fused": c.gather_ms / args.steps,
+                            "prolog": c.prolog_ms / args.steps, "ghost": c.ghost_ms / args.steps,
+                            "rebuild_amortised": c.rebuild_ms / args.steps}}
+    prof = ROOT / "profiles" / "ncu_traffic.json"
+    if prof.exists():
+        try:
+            roof["traffic"] = json.loads(prof.read_text()).get(roof["kernel"])
+        except Exception:
+            pass
+    cpu = None
+    if not args.no_cpu_baseline:
+        n_sample = min(args.particles, 200_000)
+        wls = make_workload(name if name != "box8m" else "box", n_sample)
+        v, pss, st, dt, nthr = cpu_run(wls, args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": nthr, "kind": "port", "particle_steps_per_s": pss,
+               "sample": f"{wls.particles.n}-particle sample of the workload, {st} steps in {dt:.1f} s, oracle OpenMP ({nthr} threads)"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "particle_steps_per_s": ps / (ms * 1e-3),
+            "config": {"workload": f"{name}: {wl.particles.n * world} spheres ({wl.particles.n}/GPU), {wl.name}", "particles_per_gpu": int(wl.particles.n),
+                       "interactions_per_gpu": int(counts.sum()), "active_interactions_per_gpu": int(active.sum()),
+                       "rebuilds_in_timed_region": int(nreb), "rebuild": "displacement trigger rcut_inc/2",
+                       "l2": "working set (particles + interaction waves) > 126 MB L2, no flush",
+                       "timing": "CUDA events on the library stream, max over ranks", "wall_s": wall},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

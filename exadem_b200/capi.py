@@ -77,7 +77,9 @@ class Counters(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("interaction_updates", C.c_uint64), ("particle_steps", C.c_uint64),
                 ("rebuilds", C.c_uint64), ("contact_ms", C.c_double), ("gather_ms", C.c_double),
                 ("prolog_ms", C.c_double), ("epilog_ms", C.c_double), ("rebuild_ms", C.c_double),
-                ("ghost_ms", C.c_double), ("contact_launches", C.c_uint64), ("bytes_contact_algorithmic", C.c_uint64)]
+                ("ghost_ms", C.c_double), ("contact_launches", C.c_uint64), ("bytes_contact_algorithmic", C.c_uint64),
+                ("contact_pp_ms", C.c_double), ("contact_pp_launches", C.c_uint64), ("contact_pp_records", C.c_uint64),
+                ("gather_launches", C.c_uint64)]
 
 
 class EdbError(RuntimeError):
@@ -391,6 +393,14 @@ class Engine:
 
     def flush_l2(self):
         self._call("flush_l2")
+
+    def event_record(self, slot):
+        self._call("event_record", C.c_int32(slot))
+
+    def event_elapsed_ms(self, a, b) -> float:
+        ms = C.c_double()
+        self._call("event_elapsed_ms", C.c_int32(a), C.c_int32(b), C.byref(ms))
+        return ms.value
 
     def comm_init(self, uid: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)

@@ -18,7 +18,7 @@ static_assert(sizeof(edb_config) == 152 && sizeof(edb_interaction) == 104 && siz
                   sizeof(edb_particles) == 8 + 31 * 8,
               "C ABI struct layout changed: update include/exadem_b200.h users and exadem_b200/capi.py");
 
-enum Bucket { B_CONTACT = 0, B_GATHER, B_PROLOG, B_EPILOG, B_REBUILD, B_GHOST, B_N };
+enum Bucket { B_CONTACT = 0, B_GATHER, B_PROLOG, B_EPILOG, B_REBUILD, B_GHOST, B_CONTACT_PP, B_N };
 
 struct edb_context {
   edb_config cfg{};
@@ -71,6 +71,7 @@ struct edb_context {
   std::vector<EventPair> ev_pending, ev_free;
   // L2 flush scratch
   DevBuf<double4> l2buf;
+  cudaEvent_t user_ev[8] = {};
   // multi-GPU
   Comm comm;
 
@@ -111,7 +112,7 @@ static void resolve_timers(edb_context* c) {
   for (auto& ep : c->ev_pending) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ep.a, ep.b));
-    double* b[B_N] = {&c->ctr.contact_ms, &c->ctr.gather_ms, &c->ctr.prolog_ms, &c->ctr.epilog_ms, &c->ctr.rebuild_ms, &c->ctr.ghost_ms};
+    double* b[B_N] = {&c->ctr.contact_ms, &c->ctr.gather_ms, &c->ctr.prolog_ms, &c->ctr.epilog_ms, &c->ctr.rebuild_ms, &c->ctr.ghost_ms, &c->ctr.contact_pp_ms};
     *b[ep.bucket] += ms;
     c->ev_free.push_back(ep);
   }
@@ -266,6 +267,7 @@ extern "C" int edb_destroy(edb_context* c) {
   c->stage.release(); c->stage_u64.release(); c->l2buf.release();
   for (auto& e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (auto& e : c->user_ev) if (e) cudaEventDestroy(e);
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->h_tot) cudaFreeHost(c->h_tot);
@@ -745,8 +747,11 @@ static void launch_contact_waves(edb_context* c, double dt) {
     A.w = view(w);
     A.type = t;
     if (t <= 3) {
+      ScopedTimer tpp(c, B_CONTACT_PP);
       if (poly) LAUNCH(c, k_contact_poly_pp<LAW>, nblk(w.n), BLK, 0, A);
       else LAUNCH(c, k_contact_sphere_pp<LAW>, nblk(w.n), BLK, 0, A);
+      c->ctr.contact_pp_launches++;
+      c->ctr.contact_pp_records += w.n;
     } else if (t <= 6) {
       if (poly) LAUNCH(c, (k_contact_driver<LAW, true>), nblk(w.n), BLK, 0, A);
       else LAUNCH(c, (k_contact_driver<LAW, false>), nblk(w.n), BLK, 0, A);
@@ -785,6 +790,7 @@ static void gather(edb_context* c, const double* g, double dt) {
   if (g) { A.g[0] = g[0]; A.g[1] = g[1]; A.g[2] = g[2]; }
   A.hdt = dt * 0.5;
   LAUNCH(c, k_gather<FUSE>, nblk(c->nreal), BLK, 0, A);
+  c->ctr.gather_launches++;
 }
 
 extern "C" int edb_contact_sphere(edb_context* c, double dt) {
@@ -1066,6 +1072,22 @@ extern "C" int edb_reset_counters(edb_context* c) {
 __global__ void k_flush(double4* p, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = make_double4(0, 0, 0, 0);
+}
+extern "C" int edb_event_record(edb_context* c, int32_t slot) {
+  API_BEGIN(c)
+  if (slot < 0 || slot >= 8) throw StateError{EDB_ERR_INVALID, "event slot out of range"};
+  if (!c->user_ev[slot]) CK(cudaEventCreate(&c->user_ev[slot]));
+  CK(cudaEventRecord(c->user_ev[slot], c->st));
+  API_END(c)
+}
+extern "C" int edb_event_elapsed_ms(edb_context* c, int32_t a, int32_t b, double* ms) {
+  API_BEGIN(c)
+  if (a < 0 || a >= 8 || b < 0 || b >= 8 || !c->user_ev[a] || !c->user_ev[b]) throw StateError{EDB_ERR_INVALID, "event slot not recorded"};
+  CK(cudaEventSynchronize(c->user_ev[b]));
+  float f = 0;
+  CK(cudaEventElapsedTime(&f, c->user_ev[a], c->user_ev[b]));
+  *ms = f;
+  API_END(c)
 }
 extern "C" int edb_flush_l2(edb_context* c) {
   API_BEGIN(c)

@@ -35,8 +35,20 @@ class Workload:
     gravity: tuple = (0.0, 0.0, -9.807)
     symetric: bool = True
 
+    def effective_cell_size(self):
+        """cell_size, shrunk so that every periodic axis has >= 3 cells (a 1-cell ghost layer must not alias the
+        images), but never below the grid constraint 2*r_max + rcut_inc (src/field/check_rcut.cpp:72,88-116)."""
+        cs = self.cell_size
+        for d in range(3):
+            if self.periodic[d]:
+                cs = min(cs, (self.hi[d] - self.lo[d]) / 3.0)
+        need = 2.0 * float(self.particles.radius.max()) + self.rcut_inc
+        if cs < need:
+            raise ValueError(f"periodic box too small: cell {cs} < 2*rmax+rcut_inc = {need}")
+        return cs
+
     def config(self, device=0, emit_contact_state=1, **kw):
-        return capi.make_config(self.lo, self.hi, self.cell_size, self.periodic, self.mode, device,
+        return capi.make_config(self.lo, self.hi, self.effective_cell_size(), self.periodic, self.mode, device,
                                 emit_contact_state=emit_contact_state, **kw)
 
     def shapes(self):
@@ -137,7 +149,7 @@ def deposit(n_side=(22, 22, 22), seed=0xD3A1, name="deposit") -> Workload:
     sphere_mass_inertia(pa, 0.02)
     pa.id[:] = rng.permutation(n).astype(np.uint64)
     prm = dict(kn=1e4, kt=1e4, kr=0.1, mu=0.2, damp_rate=0.9, fc=0.0, dncut=0.0, gamma=0.0)
-    drv = dict(kind=capi.DRIVER_SURFACE, offset=-0.3, normal=(0, 0, 1), center=(0, 0, -0.3))
+    drv = dict(kind=capi.DRIVER_SURFACE, offset=0.05, normal=(0, 0, 1), center=(0, 0, 0.05))
     return Workload(name, (0.0, 0.0, -2.0), (hi[0], hi[1], hi[2] + 2.0), 2.0, (1, 1, 0), pa, prm, prm, [drv],
                     dt=1e-4, rcut_inc=0.2)
 

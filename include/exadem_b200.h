@@ -187,15 +187,22 @@ typedef struct edb_counters {
   uint64_t interaction_updates; /* sum over waves of records processed by the contact kernels */
   uint64_t particle_steps;      /* real particles x steps */
   uint64_t rebuilds;
-  double   contact_ms;          /* CUDA-event time of the contact wave kernels (accumulated, when timing enabled) */
+  double   contact_ms;          /* CUDA-event time of all contact wave kernels (accumulated, when timing enabled) */
   double   gather_ms, prolog_ms, epilog_ms, rebuild_ms, ghost_ms;
   uint64_t contact_launches;
   uint64_t bytes_contact_algorithmic; /* accumulated algorithmic bytes of the contact kernels */
+  double   contact_pp_ms;       /* wave 0 (particle-particle) kernel alone: the dominant kernel of the step */
+  uint64_t contact_pp_launches;
+  uint64_t contact_pp_records;  /* records processed by those launches */
+  uint64_t gather_launches;
 } edb_counters;
 int edb_set_timing(edb_context*, int32_t enabled);
 int edb_get_counters(edb_context*, edb_counters* out);
 int edb_reset_counters(edb_context*);
 int edb_flush_l2(edb_context*); /* writes a >L2-sized scratch buffer (bench hygiene) */
+/* CUDA events on the context stream (the stream every kernel of this library is launched on): slot in [0,8) */
+int edb_event_record(edb_context*, int32_t slot);
+int edb_event_elapsed_ms(edb_context*, int32_t slot_begin, int32_t slot_end, double* ms); /* synchronises slot_end */
 
 #ifdef __cplusplus
 }

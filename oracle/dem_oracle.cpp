@@ -807,6 +807,7 @@ int orc_get_counters(orc_sim* h, edb_counters* c) {
   c->interaction_updates = s.interaction_updates; c->particle_steps = s.particle_steps; c->rebuilds = s.rebuilds;
   return 0;
 }
+int orc_event_record(orc_sim*, int32_t) { return 0; }
 int orc_reset_counters(orc_sim* h) { Sim& s = *(Sim*)h; s.interaction_updates = s.particle_steps = s.rebuilds = 0; return 0; }
 // world vertices of particle p (testing compute_vertices)
 int orc_get_vertices(orc_sim* h, double* out, uint64_t cap_doubles) {

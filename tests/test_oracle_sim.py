@@ -15,7 +15,7 @@ def mk(wl, lib, threads=1):
 
 
 def test_serial_vs_openmp_order(oracle_lib):
-    for wl in (workloads.rotating_drum(3000, jitter=0.02), workloads.polyhedra_box((5, 5, 5), shapes=("octahedron", "cube"), pitch=0.78)):
+    for wl in (workloads.rotating_drum(3000, jitter=0.02), workloads.polyhedra_box((6, 6, 6), shapes=("octahedron", "cube"), pitch=0.78)):
         a, b = mk(wl, oracle_lib, 1), mk(wl, oracle_lib, 4)
         for e in (a, b):
             e.update_particle_neighbors(wl.rcut_inc, True)
@@ -84,7 +84,7 @@ def test_history_reset_and_carry_over(oracle_lib):
 
 def test_rolling_moment_quirk_q1(oracle_lib):
     """contact_force.hpp:223-234: with vrot_i == 0 the NaN threshold keeps mom = kr*(w_j - w_i)*dt; otherwise mur = 0 zeroes it."""
-    wl = workloads.spheres_box((2, 1, 1), periodic=(0, 0, 0), cell_size=1.0, jitter=0.0, sigma_v=0.0)
+    wl = workloads.spheres_box((2, 1, 1), periodic=(0, 0, 0), cell_size=2.0, jitter=0.0, sigma_v=0.0)
     wl.lo, wl.hi = (-3.0, -3.0, -3.0), (5.0, 3.0, 3.0)
     pa = wl.particles
     pa.rx[:] = [0.0, 0.95]
