@@ -32,6 +32,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool load() {
     if (h) return true;
@@ -48,9 +49,9 @@ struct NcclApi {
     if (!h) return false;
 #define EDB_SYM(f) f = (decltype(f))dlsym(h, "nccl" #f)
     EDB_SYM(GetUniqueId); EDB_SYM(CommInitRank); EDB_SYM(CommDestroy); EDB_SYM(GroupStart); EDB_SYM(GroupEnd);
-    EDB_SYM(Send); EDB_SYM(Recv); EDB_SYM(AllReduce); EDB_SYM(GetErrorString);
+    EDB_SYM(Send); EDB_SYM(Recv); EDB_SYM(AllReduce); EDB_SYM(AllGather); EDB_SYM(GetErrorString);
 #undef EDB_SYM
-    return GetUniqueId && CommInitRank && Send && Recv && GroupStart && GroupEnd && AllReduce;
+    return GetUniqueId && CommInitRank && Send && Recv && GroupStart && GroupEnd && AllReduce && AllGather;
   }
 };
 static NcclApi g_nccl;
@@ -115,6 +116,7 @@ struct Comm {
   uint32_t n_local_ghost = 0;
   std::map<int, Peer> peers;
   DevBuf<unsigned long long> d_red;
+  DevBuf<uint32_t> d_gather;
 
   static int unique_id(uint8_t out[128]) {
     if (!g_nccl.load()) return EDB_ERR_NCCL;
@@ -140,6 +142,7 @@ struct Comm {
       p.s_h.release(); p.s_id.release();
     }
     d_red.release();
+    d_gather.release();
   }
   static void coords(const int pg[3], int r, int out[3]) {
     out[0] = r % pg[0];
@@ -223,6 +226,38 @@ struct Comm {
         CK(cudaMemcpy(p.d_sshift.p, sh.data(), sh.size() * 8, cudaMemcpyHostToDevice));
       }
     }
+  }
+  // every rank contributes n uint32; out (host) receives nranks*n in rank order
+  void allgather_u32(const uint32_t* h_in, uint32_t n, uint32_t* h_out, cudaStream_t st) {
+    if (!comm) throw StateError{EDB_ERR_STATE, "multi-GPU context without edb_comm_init"};
+    d_gather.ensure((size_t)n * (nranks + 1));
+    CK(cudaMemcpyAsync(d_gather.p, h_in, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    NCK(g_nccl.AllGather(d_gather.p, d_gather.p + n, n, ncclUint32, comm, st));
+    CK(cudaMemcpyAsync(h_out, d_gather.p + n, (size_t)n * nranks * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  // variable-size all-to-all of raw bytes: (s/r)off, (s/r)cnt in ELEMENTS of `elem` bytes per rank
+  void alltoallv_bytes(const void* sbuf, const uint32_t* soff, const uint32_t* scnt, void* rbuf, const uint32_t* roff,
+                       const uint32_t* rcnt, size_t elem, cudaStream_t st) {
+    if (!comm) throw StateError{EDB_ERR_STATE, "multi-GPU context without edb_comm_init"};
+    NCK(g_nccl.GroupStart());
+    for (int r = 0; r < nranks; r++) {
+      if (r == rank) continue;
+      if (scnt[r]) NCK(g_nccl.Send((const char*)sbuf + (size_t)soff[r] * elem, (size_t)scnt[r] * elem, ncclUint8, r, comm, st));
+      if (rcnt[r]) NCK(g_nccl.Recv((char*)rbuf + (size_t)roff[r] * elem, (size_t)rcnt[r] * elem, ncclUint8, r, comm, st));
+    }
+    NCK(g_nccl.GroupEnd());
+  }
+  // rebuild: per-entry particle counts of the ghost cells travel from the source rank to the ghost owner
+  void exchange_ghost_counts(cudaStream_t st) {
+    if (!comm) throw StateError{EDB_ERR_STATE, "multi-GPU context without edb_comm_init"};
+    NCK(g_nccl.GroupStart());
+    for (auto& kv : peers) {
+      Peer& p = kv.second;
+      if (!p.send.empty()) NCK(g_nccl.Send(p.d_scnt.p, p.send.size(), ncclUint32, p.rank, comm, st));
+      if (!p.recv.empty()) NCK(g_nccl.Recv(p.d_rcnt.p, p.recv.size(), ncclUint32, p.rank, comm, st));
+    }
+    NCK(g_nccl.GroupEnd());
   }
   uint64_t allreduce_sum_u64(uint64_t v, cudaStream_t st) {
     if (!comm) return v;

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "kernels_rebuild.cuh"
 #include "kernels_step.cuh"
+#include "kernels_migrate.cuh"
 #include "comm.cuh"
 
 using namespace edb;
@@ -74,6 +75,12 @@ struct edb_context {
   cudaEvent_t user_ev[8] = {};
   // multi-GPU
   Comm comm;
+  DevBuf<int> mig_dest;
+  DevBuf<uint32_t> mig_midx, mig_cnt, mig_off, imm_cnt, imm_off;
+  DevBuf<MigPart> mig_sp, mig_rp;
+  DevBuf<MigRec> mig_sh, mig_rh, imm_tab;
+  uint32_t n_imm = 0;
+  uint64_t migrated_out = 0, migrated_in = 0;
 
   bool poly() const { return cfg.mode == EDB_MODE_POLYHEDRON; }
 };
@@ -200,6 +207,7 @@ static void setup_grid(edb_context* c) {
     CK(cudaMemcpy(c->g_src_cell.p, gs.data(), gs.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->g_shift.p, sh.data(), sh.size() * 8, cudaMemcpyHostToDevice));
   }
+  if (c->cfg.nranks > 1) c->comm.plan_send_lists(c->cfg, G);
   c->comm.plan_finalize();
   c->ccount.ensure(G.ncell + 1); c->cstart.ensure(G.ncell + 2); c->cfill.ensure(G.ncell + 1);
   c->cbeg.ensure(G.ncell + 1); c->cend.ensure(G.ncell + 1);
@@ -265,6 +273,8 @@ extern "C" int edb_destroy(edb_context* c) {
   c->pr_backup.release(); c->q_backup.release(); c->vert.release(); c->g_shift.release(); c->tpp.release(); c->tpd.release();
   c->drv.release(); c->d_sh.release(); c->d_sv.release(); c->d_se.release(); c->d_sfoff.release(); c->d_sfn.release(); c->d_sfidx.release();
   c->stage.release(); c->stage_u64.release(); c->l2buf.release();
+  c->mig_dest.release(); c->mig_midx.release(); c->mig_cnt.release(); c->mig_off.release(); c->imm_cnt.release(); c->imm_off.release();
+  c->mig_sp.release(); c->mig_rp.release(); c->mig_sh.release(); c->mig_rh.release(); c->imm_tab.release();
   for (auto& e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto& e : c->user_ev) if (e) cudaEventDestroy(e);
@@ -548,6 +558,79 @@ static void compute_vertices(edb_context* c) {
   LAUNCH(c, k_compute_vertices, nblk(ntot), BLK, 0, view(c->pa), ntot, c->S, c->vert.p);
 }
 
+// Multi-GPU: particles that left the brick move to their new owner together with their active interaction records.
+// Returns the number of occupied slots (stayers + leavers' dead slots + immigrants); *n_live = particles now owned.
+static uint32_t migrate(edb_context* c, uint32_t* n_live) {
+  const int R = c->cfg.nranks, me = c->cfg.rank;
+  const uint32_t n = c->nreal;
+  const bool poly = c->poly();
+  BrickMap B{};
+  for (int d = 0; d < 3; d++) {
+    B.glo[d] = c->cfg.glo[d]; B.ghi[d] = c->cfg.ghi[d]; B.pg[d] = c->comm.pg[d]; B.periodic[d] = c->cfg.periodic[d];
+    B.len[d] = (c->cfg.ghi[d] - c->cfg.glo[d]) / c->comm.pg[d];
+  }
+  B.me = me;
+  c->mig_dest.ensure(n + 1); c->mig_midx.ensure(n + 1);
+  c->mig_cnt.ensure(2 * R + 2); c->mig_off.ensure(2 * R + 2);
+  uint32_t* d_cp = c->mig_cnt.p;      // particles per destination
+  uint32_t* d_ch = c->mig_cnt.p + R;  // history records per destination
+  CK(cudaMemsetAsync(c->mig_cnt.p, 0, 2 * R * 4, c->st));
+  LAUNCH(c, k_mig_classify, nblk(n), BLK, 0, c->pa.pr.p, n, B, c->mig_dest.p, c->mig_midx.p, d_cp);
+  WTabC W{};
+  const bool had = c->have_prev;
+  for (int t = 0; t < NT; t++) {
+    W.w[t] = view(c->wave[t]);
+    if (!had) W.w[t].n = 0;
+  }
+  LAUNCH(c, k_mig_pack<false>, nblk(n), BLK, 0, view(c->pa), n, c->mig_dest.p, c->mig_midx.p, W, poly, d_ch, nullptr, nullptr, nullptr, nullptr);
+  std::vector<uint32_t> mine(2 * R), all((size_t)2 * R * R);
+  CK(cudaMemcpyAsync(mine.data(), c->mig_cnt.p, 2 * R * 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  c->comm.allgather_u32(mine.data(), 2 * R, all.data(), c->st);
+  // send side: offsets per destination; receive side: what every source has for me
+  std::vector<uint32_t> sp_off(R + 1, 0), sh_off(R + 1, 0), rp_cnt(R), rh_cnt(R), rp_off(R + 1, 0), rh_off(R + 1, 0);
+  for (int r = 0; r < R; r++) {
+    sp_off[r + 1] = sp_off[r] + mine[r];
+    sh_off[r + 1] = sh_off[r] + mine[R + r];
+    rp_cnt[r] = all[(size_t)r * 2 * R + me];
+    rh_cnt[r] = all[(size_t)r * 2 * R + R + me];
+    rp_off[r + 1] = rp_off[r] + rp_cnt[r];
+    rh_off[r + 1] = rh_off[r] + rh_cnt[r];
+  }
+  const uint32_t n_out = sp_off[R], h_out = sh_off[R], n_in = rp_off[R], h_in = rh_off[R];
+  c->n_imm = n_in;
+  c->migrated_out += n_out; c->migrated_in += n_in;
+  *n_live = n - n_out + n_in;
+  // any rank migrating => all ranks take part in the exchange (counts are globally known, so everyone agrees)
+  uint64_t any = 0;
+  for (size_t i = 0; i < all.size(); i++) any += all[i];
+  if (any == 0) return n;
+  c->mig_sp.ensure(n_out + 1); c->mig_sh.ensure(h_out + 1); c->mig_rp.ensure(n_in + 1); c->mig_rh.ensure(h_in + 1);
+  CK(cudaMemcpyAsync(c->mig_off.p, sp_off.data(), R * 4, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->mig_off.p + R, sh_off.data(), R * 4, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemsetAsync(d_ch, 0, R * 4, c->st));
+  if (n_out)
+    LAUNCH(c, k_mig_pack<true>, nblk(n), BLK, 0, view(c->pa), n, c->mig_dest.p, c->mig_midx.p, W, poly, d_ch, c->mig_off.p, c->mig_off.p + R,
+           c->mig_sp.p, c->mig_sh.p);
+  c->comm.alltoallv_bytes(c->mig_sp.p, sp_off.data(), mine.data(), c->mig_rp.p, rp_off.data(), rp_cnt.data(), sizeof(MigPart), c->st);
+  c->comm.alltoallv_bytes(c->mig_sh.p, sh_off.data(), mine.data() + R, c->mig_rh.p, rh_off.data(), rh_cnt.data(), sizeof(MigRec), c->st);
+  // immigrants are appended behind the old real range (the ghost range is rebuilt anyway)
+  const uint32_t n_all = n + n_in;
+  c->pa.ensure(n_all + 1, true, c->st);
+  c->mig_dest.ensure(n_all + 1, true, c->st);
+  if (n_in) LAUNCH(c, k_mig_unpack, nblk(n_in), BLK, 0, view(c->pa), n, n_in, c->mig_rp.p, c->mig_dest.p);
+  // immigrant history table: CSR by immigrant index
+  c->imm_cnt.ensure(n_in + 2); c->imm_off.ensure(n_in + 2); c->imm_tab.ensure(h_in + 1);
+  CK(cudaMemsetAsync(c->imm_cnt.p, 0, (n_in + 1) * 4, c->st));
+  for (int r = 0; r < R; r++)
+    if (rh_cnt[r]) LAUNCH(c, k_imm_hist<false>, nblk(rh_cnt[r]), BLK, 0, c->mig_rh.p, rh_off[r], rh_cnt[r], rp_off[r], c->imm_cnt.p, nullptr, nullptr);
+  scan_u32(c, c->imm_cnt.p, c->imm_off.p, n_in);
+  CK(cudaMemsetAsync(c->imm_cnt.p, 0, (n_in + 1) * 4, c->st));
+  for (int r = 0; r < R; r++)
+    if (rh_cnt[r]) LAUNCH(c, k_imm_hist<true>, nblk(rh_cnt[r]), BLK, 0, c->mig_rh.p, rh_off[r], rh_cnt[r], rp_off[r], c->imm_cnt.p, c->imm_off.p, c->imm_tab.p);
+  return n_all;
+}
+
 static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   ScopedTimer tm(c, B_REBUILD);
   const GridDev& G = c->G;
@@ -556,36 +639,83 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   const bool poly = c->poly();
   if (poly && c->h_sh.empty()) throw StateError{EDB_ERR_STATE, "polyhedron mode needs edb_set_shapes"};
 
-  // multi-GPU: particles that left the brick migrate (with their interaction history) before re-binning
-  if (c->cfg.nranks > 1) throw StateError{EDB_ERR_STATE, "multi-GPU rebuild goes through comm (not wired in this build step)"};
-
-  uint32_t n = c->nreal;
+  // 0. multi-GPU: particles that left the brick migrate (with their interaction history) before re-binning
+  const bool multi = c->cfg.nranks > 1;
+  const uint32_t n_before = c->nreal;   // slots the previous waves refer to
+  uint32_t n_all = c->nreal, n = c->nreal;
+  c->n_imm = 0;
+  if (multi) n_all = migrate(c, &n);
+  const int* dead = multi ? c->mig_dest.p : nullptr;
   // 1. bin reals into cells, id-ordered inside each cell
-  c->cidx.ensure(n + 1); c->tmp.ensure(n + 1); c->new2old.ensure(n + 1); c->old2new.ensure(n + 1);
+  c->cidx.ensure(n_all + 1); c->tmp.ensure(n_all + 1); c->new2old.ensure(n_all + 1); c->old2new.ensure(n_all + 1);
   CK(cudaMemsetAsync(c->ccount.p, 0, (G.ncell + 1) * 4, c->st));
   CK(cudaMemsetAsync(c->cfill.p, 0, (G.ncell + 1) * 4, c->st));
-  LAUNCH(c, k_cell_assign, nblk(n), BLK, 0, c->pa.pr.p, n, G, c->cidx.p, c->ccount.p);
+  LAUNCH(c, k_cell_assign, nblk(n_all), BLK, 0, c->pa.pr.p, n_all, G, c->cidx.p, c->ccount.p, dead);
   scan_u32(c, c->ccount.p, c->cstart.p, G.ncell);
-  LAUNCH(c, k_cell_scatter, nblk(n), BLK, 0, c->cidx.p, n, c->cstart.p, c->cfill.p, c->tmp.p);
-  LAUNCH(c, k_cell_rank, nblk(n), BLK, 0, c->cidx.p, c->pa.id.p, n, c->cstart.p, c->tmp.p, c->new2old.p, c->old2new.p);
+  LAUNCH(c, k_cell_scatter, nblk(n_all), BLK, 0, c->cidx.p, n_all, c->cstart.p, c->cfill.p, c->tmp.p);
+  LAUNCH(c, k_cell_rank, nblk(n_all), BLK, 0, c->cidx.p, c->pa.id.p, n_all, c->cstart.p, c->tmp.p, c->new2old.p, c->old2new.p);
   // 2. ghosts: count, size, permute into the (possibly grown) scratch set, fill
   LAUNCH(c, k_ghost_count, nblk(c->n_gent), BLK, 0, c->g_src_cell.p, c->n_gent, c->cstart.p, c->g_count.p);
   scan_u32(c, c->g_count.p, c->g_off.p, c->n_gent);
   CK(cudaMemcpyAsync(c->h_tot, c->g_off.p + c->n_gent, 4, cudaMemcpyDeviceToHost, c->st));
+  std::vector<uint32_t> h_peer;
+  if (multi) {
+    // remote ghosts: the source rank counts the particles of each cell it feeds and tells the ghost owner
+    for (auto& kv : c->comm.peers) {
+      Peer& p = kv.second;
+      if (!p.send.empty()) LAUNCH(c, k_ghost_count, nblk(p.send.size()), BLK, 0, p.d_scell.p, (uint32_t)p.send.size(), c->cstart.p, p.d_scnt.p);
+    }
+    c->comm.exchange_ghost_counts(c->st);
+    h_peer.assign(2 * c->comm.peers.size() + 2, 0);
+    size_t i = 0;
+    c->stage_u32.ensure(2 * c->comm.peers.size() + 2);
+    for (auto& kv : c->comm.peers) {
+      Peer& p = kv.second;
+      scan_u32(c, p.d_scnt.p, p.d_soff.p, (uint32_t)p.send.size());
+      CK(cudaMemcpyAsync(c->stage_u32.p + i, p.d_soff.p + p.send.size(), 4, cudaMemcpyDeviceToDevice, c->st));
+      scan_u32(c, p.d_rcnt.p, p.d_roff.p, (uint32_t)p.recv.size());
+      CK(cudaMemcpyAsync(c->stage_u32.p + i + 1, p.d_roff.p + p.recv.size(), 4, cudaMemcpyDeviceToDevice, c->st));
+      i += 2;
+    }
+    CK(cudaMemcpyAsync(h_peer.data(), c->stage_u32.p, i * 4, cudaMemcpyDeviceToHost, c->st));
+  }
   CK(cudaStreamSynchronize(c->st));
   const uint32_t nloc_ghost = c->n_gent ? c->h_tot[0] : 0;
   c->comm.n_local_ghost = nloc_ghost;
   c->nghost = nloc_ghost;
+  if (multi) {
+    size_t i = 0;
+    uint32_t base = 0;
+    for (auto& kv : c->comm.peers) {
+      Peer& p = kv.second;
+      p.n_send = h_peer[i]; p.n_recv = h_peer[i + 1]; p.recv_base = base;
+      base += p.n_recv;
+      i += 2;
+      p.d_smap.ensure(p.n_send + 1); p.d_sent.ensure(p.n_send + 1);
+      p.s_pr.ensure(p.n_send + 1); p.s_vm.ensure(p.n_send + 1); p.s_wg.ensure(p.n_send + 1); p.s_q.ensure(p.n_send + 1);
+      p.s_h.ensure(p.n_send + 1); p.s_id.ensure(p.n_send + 1);
+    }
+    c->nghost += base;
+  }
   const uint32_t ntot = n + c->nghost;
   c->pb.ensure(ntot + 1, false, c->st);
   c->cidx2.ensure(ntot + 1);
   LAUNCH(c, k_permute, nblk(n), BLK, 0, view(c->pb), view(c->pa), c->new2old.p, c->cidx.p, c->cidx2.p, n);
   std::swap(c->pa, c->pb);
   std::swap(c->cidx, c->cidx2);
+  c->nreal = n;
+  if (multi) LAUNCH(c, k_iota, nblk(n), BLK, 0, c->pa.orig.p, n);  // download order = device order once particles migrate
   LAUNCH(c, k_cell_ranges, nblk(G.ncell), BLK, 0, c->cstart.p, G.ncell, c->cbeg.p, c->cend.p);
-  c->g_src.ensure(c->nghost + 1); c->g_ent.ensure(c->nghost + 1);
+  c->g_src.ensure(nloc_ghost + 1); c->g_ent.ensure(nloc_ghost + 1);
   LAUNCH(c, k_ghost_fill, nblk(c->n_gent), BLK, 0, c->g_cell.p, c->g_src_cell.p, c->n_gent, c->cstart.p, c->g_off.p, n, c->g_src.p,
          c->g_ent.p, c->cbeg.p, c->cend.p);
+  if (multi)
+    for (auto& kv : c->comm.peers) {
+      Peer& p = kv.second;
+      if (!p.send.empty()) LAUNCH(c, k_send_map, nblk(p.send.size()), BLK, 0, p.d_scell.p, (uint32_t)p.send.size(), c->cstart.p, p.d_soff.p, p.d_smap.p, p.d_sent.p);
+      if (!p.recv.empty()) LAUNCH(c, k_recv_cells, nblk(p.recv.size()), BLK, 0, p.d_rgcell.p, (uint32_t)p.recv.size(), p.d_roff.p, p.d_rcnt.p,
+                                  n + nloc_ghost + p.recv_base, c->cbeg.p, c->cend.p, c->cidx.p);
+    }
   ghost_refresh(c, true);
   compute_vertices(c);
   // 3. backup for the displacement trigger (backup_r / backup_dem)
@@ -633,10 +763,14 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   if (!poly) LAUNCH(c, k_nbh_sphere<true>, nblk(n, 128), 128, 0, A, C, W);
   else LAUNCH(c, k_nbh_poly<true>, nblk(n, 64), 64, 0, A, C, W);
   // 5. history carry-over
-  if (had) {
+  if (had || c->n_imm) {
+    const ImmHist H{c->imm_off.p, (const ImmRec*)c->imm_tab.p, c->n_imm};
     for (int t = 0; t < NT; t++)
-      if (active[t] && c->wave[t].n && c->prev[t].n)
-        LAUNCH(c, k_history, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), view(c->prev[t]), c->new2old.p, c->n_old_real, poly);
+      if (active[t] && c->wave[t].n && ((had && c->prev[t].n) || c->n_imm)) {
+        WView ow = view(c->prev[t]);
+        if (!had) ow.n = 0;
+        LAUNCH(c, k_history, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), ow, c->new2old.p, had ? c->n_old_real : n_before, poly, t, H);
+      }
   }
   c->have_prev = true;
   c->n_old_real = n;

@@ -100,10 +100,16 @@ __device__ __forceinline__ uint32_t cell_lin(const GridDev& G, int i, int j, int
   return (uint32_t)i + (uint32_t)G.g[0] * ((uint32_t)j + (uint32_t)G.g[1] * (uint32_t)k);
 }
 // wrap periodic coordinates into the global box, assign the (ghost-shelled) cell index, histogram
+// dest (multi-GPU only): >= 0 marks a particle that migrated away — its slot is dead and is dropped by the sort
+constexpr uint32_t DEAD_CELL = 0xffffffffu;
 __global__ void k_cell_assign(double4* __restrict__ pr, uint32_t n, GridDev G, uint32_t* __restrict__ cidx,
-                              uint32_t* __restrict__ ccount) {
+                              uint32_t* __restrict__ ccount, const int* __restrict__ dest) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
+  if (dest && dest[p] >= 0) {
+    cidx[p] = DEAD_CELL;
+    return;
+  }
   double4 r = pr[p];
   double c[3] = {r.x, r.y, r.z};
 #pragma unroll
@@ -125,6 +131,7 @@ __global__ void k_cell_scatter(const uint32_t* __restrict__ cidx, uint32_t n, co
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const uint32_t c = cidx[p];
+  if (c == DEAD_CELL) return;
   tmp[cstart[c] + atomicAdd(&cfill[c], 1u)] = p;
 }
 // deterministic order inside a cell: rank by particle id (ids are unique)
@@ -134,6 +141,10 @@ __global__ void k_cell_rank(const uint32_t* __restrict__ cidx, const uint64_t* _
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const uint32_t c = cidx[p];
+  if (c == DEAD_CELL) {
+    old2new[p] = DEAD_CELL;
+    return;
+  }
   const uint64_t me = id[p];
   uint32_t rank = 0;
   for (uint32_t s = cstart[c]; s < cstart[c + 1]; s++) rank += (id[tmp[s]] < me) ? 1u : 0u;
@@ -423,18 +434,47 @@ __global__ void __launch_bounds__(64) k_nbh_poly(NbhArgs A, CntTab C, WTab W) {
 // history carry-over: new record -> same key in the previous owner segment (key = partner id, subs, swap; the
 // type is implied by the wave, the owner by the segment).  interaction_pair.hpp:204-216, placeholder_interaction.hpp:398-408
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_history(WView nw, WView ow, const uint32_t* __restrict__ new2old, uint32_t n_old_real, bool has_sub) {
+// Immigrants (multi-GPU migration) have no old owner segment: their history arrives as a CSR table by immigrant index.
+struct ImmRec {  // = MigRec of kernels_migrate.cuh
+  uint32_t m;
+  uint8_t type, flg;
+  uint16_t pad;
+  uint32_t sub_i, sub_j;
+  long long pid;
+  double ft[3], mo[3];
+};
+struct ImmHist {
+  const uint32_t* off;  // n_imm + 1
+  const ImmRec* rec;
+  uint32_t n_imm;
+};
+__global__ void k_history(WView nw, WView ow, const uint32_t* __restrict__ new2old, uint32_t n_old_real, bool has_sub, int type,
+                          ImmHist H) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nw.n) return;
   const uint8_t fl = nw.flg[k];
   const uint2 ij = nw.ij[k];
   const uint32_t owner = (fl & 1) ? ij.y : ij.x;
   const uint32_t oo = new2old[owner];
-  if (oo >= n_old_real) return;
   const double4 ft = nw.ft[k];
   const long long pid = __double_as_longlong(ft.w);
   uint2 sb = make_uint2(0, 0);
   if (has_sub) sb = nw.sub[k];
+  if (oo >= n_old_real) {
+    const uint32_t m = oo - n_old_real;
+    if (m >= H.n_imm) return;
+    const uint32_t e = H.off[m + 1];
+    for (uint32_t s = H.off[m]; s < e; s++) {
+      const ImmRec& r = H.rec[s];
+      if (r.type != type || r.pid != pid || (r.flg & 1) != (fl & 1)) continue;
+      if (has_sub && (r.sub_i != sb.x || r.sub_j != sb.y)) continue;
+      nw.ft[k] = make_double4(r.ft[0], r.ft[1], r.ft[2], ft.w);
+      nw.mo[k] = make_double4(r.mo[0], r.mo[1], r.mo[2], 0.0);
+      return;
+    }
+    return;
+  }
+  if (ow.n == 0) return;
   const uint32_t e = ow.off[oo + 1];
   for (uint32_t s = ow.off[oo]; s < e; s++) {
     const double4 oft = ow.ft[s];

@@ -60,6 +60,7 @@ struct Inter {
   uint32_t sub_i = 0, sub_j = 0;
   uint16_t type = 0;
   uint8_t swap = 0, ghost = 0;
+  uint8_t foreign = 0;        // virtual bricks: the partner is a REAL slot that another rank would own (force on it discarded)
   v3 ft{0, 0, 0}, mom{0, 0, 0};
   // contact state (classifier/contact_state.hpp)
   double dn = 0;
@@ -108,6 +109,21 @@ struct Sim {
   int symetric = 1;
   std::string err;
   int omp_threads = 1;  // 1 = canonical serial accumulation order
+  // Virtual bricks (multi-rank emulation, used only by the multi-GPU parity worker): the single domain is cut into
+  // vb[0] x vb[1] x vb[2] bricks of whole cells and a neighbour cell of ANOTHER brick is treated exactly like the ghost
+  // cell it would be on the owning MPI rank of the reference (pair enumerated from both sides, partner force discarded).
+  int vb[3]{1, 1, 1};
+  int brick_of_cell(int i, int j, int k) const {
+    const int c[3] = {i, j, k};
+    int r = 0, mult = 1;
+    for (int d = 0; d < 3; d++) {
+      int b = (c[d] - 1) / (nc[d] / vb[d]);
+      b = b < 0 ? 0 : (b > vb[d] - 1 ? vb[d] - 1 : b);
+      r += mult * b;
+      mult *= vb[d];
+    }
+    return r;
+  }
   uint64_t interaction_updates = 0, particle_steps = 0, rebuilds = 0;
 
   void resize_particles(size_t n) {
@@ -150,6 +166,8 @@ static void build_grid(Sim& s) {
     s.cs[d] = (s.cfg.hi[d] - s.cfg.lo[d]) / s.nc[d];
     s.g[d] = s.nc[d] + 2;
   }
+  for (int d = 0; d < 3; d++)
+    if (s.nc[d] % s.vb[d]) { s.err = "virtual bricks must hold a whole number of cells"; s.vb[d] = 1; }
   s.resize_particles(s.nreal);
   wrap_positions(s);
   const size_t ncell = (size_t)s.g[0] * s.g[1] * s.g[2];
@@ -235,7 +253,7 @@ static void for_each_neighbor(const Sim& s, int ci, int cj, int ck, uint32_t a, 
         const int i = ci + di, j = cj + dj, k = ck + dk;
         if (i < 0 || j < 0 || k < 0 || i >= s.g[0] || j >= s.g[1] || k >= s.g[2]) continue;
         const size_t cb = s.cell_of(i, j, k);
-        const bool ghostc = s.is_ghost_cell(i, j, k);
+        const bool ghostc = s.is_ghost_cell(i, j, k) || s.brick_of_cell(i, j, k) != s.brick_of_cell(ci, cj, ck);
         for (uint32_t it = s.cstart[cb]; it < s.cstart[cb + 1]; it++) {
           const uint32_t b = s.citems[it];
           if (b == a) continue;
@@ -270,6 +288,7 @@ static void enumerate_sphere(Sim& s, uint32_t a, int ci, int cj, int ck, std::ve
       if (ghostc) n.ghost = 1;
     }
     n.j = b; n.id_j = s.id[b];
+    n.foreign = (ghostc && b < s.nreal) ? 1 : 0;
     out.push_back(n);
   });
 }
@@ -293,6 +312,7 @@ static void enumerate_polyhedron(Sim& s, uint32_t a, int ci, int cj, int ck, std
     if (s.id[a] >= s.id[b]) return;  // nbh_polyhedron.cpp:234-236
     Inter n;
     n.ghost = ghostc ? 1 : 0;        // :237-239 OwnerGhost
+    n.foreign = (ghostc && b < s.nreal) ? 1 : 0;
     const Shape& sb = s.shapes[s.type[b]];
     const double hb = s.h[b];
     const v3* vb = s.pv(b);
@@ -431,10 +451,13 @@ static inline void contact_one(Sim& s, Inter& I, double dt, Acc& acc) {
     v3 f{0, 0, 0};
     contact_force(s.law, c.dn, c.n, dt, *cp, meff, reff, I.ft, c.cp, ri, s.v[i], f, I.mom, s.w[i], pj, vj, wj);
     fn = f - I.ft;
-    acc.add(s.mom[i], moments(c.cp, ri, f, I.mom));
-    acc.add(s.f[i], f);
+    // virtual bricks: the PARTNER (j, or i for swapped polyhedron records) is another rank's particle: its share is dropped
+    if (!(I.foreign && I.swap)) {
+      acc.add(s.mom[i], moments(c.cp, ri, f, I.mom));
+      acc.add(s.f[i], f);
+    }
     if (t <= 3) {
-      if (poly || s.symetric) {
+      if ((poly || s.symetric) && !(I.foreign && !I.swap)) {
         const uint32_t j = I.j;
         acc.add(s.mom[j], moments(c.cp, pj, -f, -I.mom));
         acc.add(s.f[j], -f);
@@ -572,6 +595,11 @@ int orc_create(const edb_config* cfg, orc_sim** out) {
   return 0;
 }
 int orc_destroy(orc_sim* h) { delete (Sim*)h; return 0; }
+int orc_set_virtual_bricks(orc_sim* h, const int32_t* pg) {
+  Sim& s = *(Sim*)h;
+  for (int d = 0; d < 3; d++) s.vb[d] = pg[d] < 1 ? 1 : pg[d];
+  return 0;
+}
 int orc_set_threads(orc_sim* h, int n) { ((Sim*)h)->omp_threads = n < 1 ? 1 : n; return 0; }
 int orc_max_threads(void) {
 #ifdef _OPENMP

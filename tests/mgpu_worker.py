@@ -1,0 +1,146 @@
+"""Multi-GPU parity worker — launched with one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tests/mgpu_worker.py [--mode sphere|poly] [--steps K] [--rebuild-every E]
+
+Every rank owns one brick of a global periodic box (exadem_b200.parallel), runs K Verlet steps with NCCL ghost exchange
+and rebuild-time migration inside libexadem_b200, then rank 0 gathers everything and checks it against the CPU oracle
+run on the SAME particles as ONE domain: particle state within 1e-10 (matched by id), the canonical interaction set
+bit-exact with its friction/moment history within 1e-10, same number of rebuilds.  Exit code 0 = parity."""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (str(ROOT), str(ROOT / "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def global_workload(mode, world):
+    from exadem_b200 import parallel, workloads
+    pg = parallel.process_grid(world)
+    if mode == "sphere":
+        side = [10 * pg[d] for d in range(3)]
+        wl = workloads.spheres_box(tuple(side), jitter=0.03, omega_sigma=0.3, sigma_v=0.1, seed=0xD3B0 + world)
+        # lattice planes 5e-4 below the brick faces: particles cross brick (and periodic) boundaries within ~50 steps
+        wl.particles.rx[:] = np.mod(wl.particles.rx + 0.4995, side[0])
+        wl.particles.ry[:] = np.mod(wl.particles.ry + 0.4995, side[1])
+    else:
+        n_side = [10 * pg[d] for d in range(3)]
+        wl = workloads.polyhedra_box(tuple(n_side), shapes=("octahedron", "cube"), pitch=0.8, seed=0xD3B8 + world, cell_size=2.0)
+        L = n_side[0] * 0.8
+        wl.particles.rx[:] = np.mod(wl.particles.rx + 0.3995, L)
+        wl.particles.vx[:] *= 30.0
+    return wl, pg
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="sphere")
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--rebuild-every", type=int, default=10)
+    ap.add_argument("--rtol", type=float, default=1e-10)
+    ap.add_argument("--verbose", action="store_true")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+    from exadem_b200 import Engine, Library, capi, parallel
+    from parity import compare_interaction_sets, field_close
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    wl, pg = global_workload(args.mode, world)
+    pos = wl.particles.vec("r")
+    mine = parallel.owner_rank(pos, wl.lo, wl.hi, pg) == rank
+    lo, hi = parallel.brick_bounds(wl.lo, wl.hi, pg, rank)
+    cfg = capi.make_config(lo, hi, wl.effective_cell_size(), wl.periodic, wl.mode, local, glo=wl.lo, ghi=wl.hi, rank=rank,
+                           nranks=world, pgrid=pg)
+    lib = Library()
+    eng = Engine(lib, cfg)
+    parallel.init_comm(eng, lib, rank)
+    eng.set_law(wl.law)
+    eng.set_contact_params(wl.params, wl.params_driver)
+    if wl.shapes_spec:
+        eng.set_shapes(wl.shapes())
+    eng.set_drivers(wl.drivers)
+    eng.upload_particles(parallel.select(wl.particles, mine))
+    sym = wl.symetric
+    eng.update_particle_neighbors(wl.rcut_inc, sym)
+    nreb = eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, sym, args.steps, args.rebuild_every)
+    pa = eng.download_particles()
+    rec = eng.export_interactions()
+    ctr = eng.counters()
+    payload = {"pa": {f: getattr(pa, f) for f in capi.F64_FIELDS + ["id", "type", "group"]}, "rec": rec, "nreb": nreb,
+               "n": pa.n, "launches": ctr.kernel_launches}
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(payload, gathered, dst=0)
+    ok = True
+    if rank == 0:
+        from oracle_binding import OracleEngine, OracleLibrary
+        ref = wl.setup(OracleEngine(OracleLibrary(), wl.config()))
+        ref.set_threads(os.cpu_count() or 1)
+        ref.set_virtual_bricks(pg)   # same both-sides enumeration of brick-straddling pairs as the N ranks (quirk Q6)
+        ref.update_particle_neighbors(wl.rcut_inc, sym)
+        nreb_ref = ref.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, sym, args.steps, args.rebuild_every)
+        pr = ref.download_particles()
+        rr = ref.export_interactions()
+        try:
+            counts = [g["n"] for g in gathered]
+            assert sum(counts) == pr.n, f"particle count {counts} != {pr.n}"
+            assert all(g["nreb"] == nreb_ref for g in gathered), f"rebuild counts {[g['nreb'] for g in gathered]} vs {nreb_ref}"
+            ids = np.concatenate([g["pa"]["id"] for g in gathered])
+            order = np.argsort(ids)
+            oref = np.argsort(pr.id)
+            assert np.array_equal(ids[order], pr.id[oref]), "particle id sets differ"
+            errs = {}
+            for f in capi.F64_FIELDS:
+                a = np.concatenate([g["pa"][f] for g in gathered])[order]
+                b = getattr(pr, f)[oref]
+                if f in ("rx", "ry", "rz"):   # positions: compare modulo the period (a particle may sit on either side of a wrap)
+                    d = "xyz".index(f[1])
+                    L = wl.hi[d] - wl.lo[d]
+                    a = a - L * np.round((a - b) / L)
+                try:
+                    errs[f] = field_close(a, b, args.rtol, f)
+                except AssertionError as e:
+                    if not args.verbose:
+                        raise
+                    bad = np.nonzero(np.abs(a - b) > args.rtol * max(np.max(np.abs(b)), 1e-300))[0]
+                    print(f"  {e}; {len(bad)} particles off; first: " + "; ".join(
+                        f"id={pr.id[oref][k]} r=({pr.rx[oref][k]:.4f},{pr.ry[oref][k]:.4f},{pr.rz[oref][k]:.4f}) got={a[k]:.6g} ref={b[k]:.6g}" for k in bad[:6]), flush=True)
+                    errs[f] = 1.0
+            all_rec = np.concatenate([g["rec"] for g in gathered])
+            sphere = wl.mode == capi.MODE_SPHERE
+            for r_ in (all_rec, rr):
+                r_["cell_i"] = r_["cell_j"] = 0
+                r_["p_i"] = r_["p_j"] = 0
+            n = compare_interaction_sets(all_rec, rr, payload_rtol=args.rtol)
+            cb = rr
+            active = int((np.abs(cb["friction"]).sum(axis=1) > 0).sum())
+            moved = sum(abs(c - counts[0]) for c in counts)
+            print(f"mgpu parity OK: {world} GPUs pgrid={pg} mode={args.mode} particles={pr.n} per-rank={counts} rebuilds={nreb_ref} "
+                  f"interactions={n} (active {active}) max field err={max(errs.values()):.2e}", flush=True)
+        except AssertionError as e:
+            print(f"mgpu parity FAILED: {e}", flush=True)
+            ok = False
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,10 @@ class OracleEngine(capi.Engine):
     def set_threads(self, n):
         self._call("set_threads", C.c_int(n))
 
+    def set_virtual_bricks(self, pgrid):
+        """Multi-rank emulation: treat cells of another brick like the ghost cells they would be on the owning rank."""
+        self._call("set_virtual_bricks", (C.c_int32 * 3)(*pgrid))
+
     def sync(self):
         pass
 

@@ -57,3 +57,29 @@ def compare_particles(pa, pb, rtol=1e-10, fields=("r", "v", "vrot", "q", "f", "m
 
 def bit_identical(pa, pb, fields=("r", "v", "vrot", "q", "f", "mom", "arot")) -> dict:
     return {f: bool(np.array_equal(pa.vec(f), pb.vec(f))) for f in fields}
+
+
+def canonical_interactions(rec: np.ndarray, sphere: bool) -> np.ndarray:
+    """Decomposition-independent view of an interaction set.
+
+    With `symetric: true` spheres, a pair that straddles a sub-domain or periodic boundary is enumerated from BOTH sides
+    (nbh_sphere.cu:245-249), each side holding a mirrored history record (friction, moment negated).  Which pairs straddle
+    a boundary depends on the decomposition, so sets from different decompositions are compared after (i) orienting every
+    sphere pair as id_i < id_j (negating the payload when flipped), (ii) clearing the ghost flag, (iii) dropping duplicates.
+    Polyhedron records are owned by the lower-id particle only, so (ii) alone makes them comparable."""
+    r = rec.copy()
+    if sphere:
+        flip = (r["type"] == 0) & (r["id_i"] > r["id_j"])
+        a, b = r["id_i"][flip].copy(), r["id_j"][flip].copy()
+        r["id_i"][flip], r["id_j"][flip] = b, a
+        r["friction"][flip] *= -1.0
+        r["moment"][flip] *= -1.0
+    r["ghost"] = 0
+    r["cell_i"] = r["cell_j"] = 0
+    r["p_i"] = r["p_j"] = 0
+    r = sort_interactions(r)
+    k = keys_of(r)
+    keep = np.ones(len(r), dtype=bool)
+    if len(r) > 1:
+        keep[1:] = (k[1:] != k[:-1]).any(axis=1)
+    return r[keep]

@@ -1,0 +1,44 @@
+"""Multi-GPU parity: N bricks over NCCL vs the single-domain oracle.  Needs >= 2 GPUs on the box; the
+worker (tests/mgpu_worker.py) is launched with torch.distributed.run exactly like bench.py is."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+def _run(n, *extra):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29500 + (os.getpid() % 400)), str(ROOT / "tests" / "mgpu_worker.py"), *extra]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "mgpu parity OK" in r.stdout
+    return r.stdout
+
+
+@pytest.mark.parametrize("rebuild_every", [10, 0])
+def test_two_gpu_spheres(rebuild_every):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, "--mode", "sphere", "--steps", "60", "--rebuild-every", str(rebuild_every))
+
+
+def test_two_gpu_polyhedra():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, "--mode", "poly", "--steps", "30", "--rebuild-every", "10")
+
+
+def test_eight_gpu_spheres():
+    if _ngpu() < 8:
+        pytest.skip("needs 8 GPUs")
+    _run(8, "--mode", "sphere", "--steps", "40", "--rebuild-every", "10")
