@@ -269,8 +269,11 @@ def main():
         t0 = time.perf_counter()
         for _ in range(ke):
             eng.upload_dynamic(host)
-            eng.run_verlet(wl.dt, g, wl.rcut_inc, wl.symetric, 1, 0)
-            eng.download_dynamic(host)
+            nr = eng.run_verlet(wl.dt, g, wl.rcut_inc, wl.symetric, 1, 0)
+            if nr and world > 1:   # a rebuild may have migrated particles between bricks: the host mirror follows
+                host = pinned_like(eng.download_particles())
+            else:
+                eng.download_dynamic(host)
         barrier()
         dt = time.perf_counter() - t0
         ce = eng.counters()
