@@ -76,9 +76,9 @@ __global__ void k_pack_ghosts(PView P, const uint32_t* __restrict__ smap, const 
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const uint32_t s = smap[k], e = sent[k];
-  double4 r = P.pr[s];
+  double4 r = ld4(P.pr + s);
   r.x = r.x + sshift[3 * e]; r.y = r.y + sshift[3 * e + 1]; r.z = r.z + sshift[3 * e + 2];
-  o_pr[k] = r; o_vm[k] = P.vm[s]; o_wg[k] = P.wg[s]; o_q[k] = P.q[s];
+  st4(o_pr + k, r); st4(o_vm + k, ld4(P.vm + s)); st4(o_wg + k, ld4(P.wg + s)); st4(o_q + k, ld4(P.q + s));
   if (all) { o_h[k] = P.h[s]; o_id[k] = P.id[s]; }
 }
 __global__ void k_send_map(const uint32_t* __restrict__ scell, uint32_t nent, const uint32_t* __restrict__ cstart,

@@ -19,6 +19,30 @@ struct q4 {
 
 #define EDB_HD __host__ __device__ __forceinline__
 
+// 256-bit global accesses (sm_100a: LDG.E.ENL2.256 / STG.E.ENL2.256).  CUDA 12.9's double4 is only 16-byte aligned, so a plain
+// double4 access compiles to two 128-bit instructions = twice the L1 wavefronts on scattered gathers, which is what bounds the
+// contact / gather kernels (profiles/).  All double4 arrays of the library are 32-byte aligned (cudaMalloc + 32-byte stride).
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ double4 ld4(const double4* p) {
+  double4 v;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// read-only for the lifetime of the kernel (non-coherent path)
+__device__ __forceinline__ double4 ldg4(const double4* p) {
+  double4 v;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st4(double4* p, const double4 v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+#else
+inline double4 ld4(const double4* p) { return *p; }
+inline double4 ldg4(const double4* p) { return *p; }
+inline void st4(double4* p, const double4 v) { *p = v; }
+#endif
+
 EDB_HD v3 mk3(double x, double y, double z) { return v3{x, y, z}; }
 EDB_HD v3 operator+(v3 a, v3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 EDB_HD v3 operator-(v3 a, v3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }

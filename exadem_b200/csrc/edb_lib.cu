@@ -985,8 +985,11 @@ __global__ void k_count_active(WView w, unsigned long long* __restrict__ out) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned int a = 0;
   if (k < w.n) {
-    const double4 f = w.ft[k], m = w.mo[k];
-    a = (f.x != 0.0 || f.y != 0.0 || f.z != 0.0 || m.x != 0.0 || m.y != 0.0 || m.z != 0.0) ? 1 : 0;
+    const uint8_t fl = w.flg[k];
+    if (fl & FLG_HOT) {
+      const double4 f = w.ft[k], m = (fl & FLG_MOM) ? w.mo[k] : make_double4(0, 0, 0, 0);
+      a = (f.x != 0.0 || f.y != 0.0 || f.z != 0.0 || m.x != 0.0 || m.y != 0.0 || m.z != 0.0) ? 1 : 0;
+    }
   }
   a = __reduce_add_sync(0xffffffffu, a);
   if ((threadIdx.x & 31) == 0 && a) atomicAdd(out, (unsigned long long)a);
@@ -1014,7 +1017,8 @@ __global__ void k_export(WView w, const uint64_t* __restrict__ id, int type, boo
   if (k >= w.n) return;
   const uint2 ij = w.ij[k];
   const uint8_t fl = w.flg[k];
-  const double4 ft = w.ft[k], mo = w.mo[k];
+  const double4 ft = (fl & FLG_HOT) ? w.ft[k] : make_double4(0, 0, 0, 0);
+  const double4 mo = (fl & FLG_MOM) ? w.mo[k] : make_double4(0, 0, 0, 0);
   edb_interaction e;
   memset(&e, 0, sizeof(e));
   e.id_i = id[ij.x];
@@ -1047,16 +1051,6 @@ extern "C" int edb_export_interactions(edb_context* c, edb_interaction* out, uin
   API_END(c)
 }
 
-__global__ void k_state(WView w, double* __restrict__ dn, double* __restrict__ cp, double* __restrict__ fn, double* __restrict__ ft) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= w.n) return;
-  const double4 fd = w.fd[k], c4 = w.cp[k], f4 = w.ft[k];
-  dn[k] = fd.w;
-  cp[3 * k] = c4.x; cp[3 * k + 1] = c4.y; cp[3 * k + 2] = c4.z;
-  // fn = f - friction (contact_sphere.hpp:180); zero for records without contact
-  fn[3 * k] = fd.x - f4.x; fn[3 * k + 1] = fd.y - f4.y; fn[3 * k + 2] = fd.z - f4.z;
-  ft[3 * k] = f4.x; ft[3 * k + 1] = f4.y; ft[3 * k + 2] = f4.z;
-}
 extern "C" int edb_get_contact_state(edb_context* c, int32_t type, double* dn, double* cp, double* fn, double* ft) {
   API_BEGIN(c)
   if (type < 0 || type >= NT) throw StateError{EDB_ERR_INVALID, "bad type"};
@@ -1064,7 +1058,9 @@ extern "C" int edb_get_contact_state(edb_context* c, int32_t type, double* dn, d
   if (n) {
     c->stage.ensure(10 * n + 1);
     double* s = c->stage.p;
-    LAUNCH(c, k_state, nblk(n), BLK, 0, view(c->wave[type]), s, s + n, s + 4 * n, s + 7 * n);
+    ContactArgs A{view(c->pa), view(c->wave[type]), c->prm, c->drv.p, c->vert.p, c->S, 0.0, type, c->symetric};
+    if (c->poly()) LAUNCH(c, k_state<true>, nblk(n), BLK, 0, A, s, s + n, s + 4 * n, s + 7 * n);
+    else LAUNCH(c, k_state<false>, nblk(n), BLK, 0, A, s, s + n, s + 4 * n, s + 7 * n);
     if (dn) CK(cudaMemcpyAsync(dn, s, n * 8, cudaMemcpyDeviceToHost, c->st));
     if (cp) CK(cudaMemcpyAsync(cp, s + n, 3 * n * 8, cudaMemcpyDeviceToHost, c->st));
     if (fn) CK(cudaMemcpyAsync(fn, s + 4 * n, 3 * n * 8, cudaMemcpyDeviceToHost, c->st));
@@ -1118,7 +1114,10 @@ extern "C" int edb_import_interactions(edb_context* c, const edb_interaction* in
       if (t >= 4) sj = (uint32_t)e.id_j; else if (b != slot.end()) sj = b->second;
       ij[s] = make_uint2(si, sj);
       sub[s] = make_uint2(e.sub_i, e.sub_j);
-      flg[s] = (uint8_t)((e.swap & 1) | ((e.ghost & 3) << 1));
+      const bool live = e.friction[0] != 0.0 || e.friction[1] != 0.0 || e.friction[2] != 0.0 || e.moment[0] != 0.0 || e.moment[1] != 0.0 ||
+                        e.moment[2] != 0.0;
+      const bool mlive = e.moment[0] != 0.0 || e.moment[1] != 0.0 || e.moment[2] != 0.0;
+      flg[s] = (uint8_t)((e.swap & 1) | ((e.ghost & 3) << 1) | (live ? FLG_HOT : 0) | (mlive ? FLG_MOM : 0));
       long long pb = (long long)pid;
       double pidd;
       memcpy(&pidd, &pb, 8);

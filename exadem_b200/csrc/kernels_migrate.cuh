@@ -101,8 +101,9 @@ __global__ void k_mig_pack(PView P, uint32_t n, const int* __restrict__ dest, co
     if (w.n == 0 || w.off == nullptr) continue;
     const uint32_t e = w.off[p + 1];
     for (uint32_t k = w.off[p]; k < e; k++) {
-      const double4 ft = w.ft[k], mo = w.mo[k];
       const uint8_t fl = w.flg[k];
+      if (!(fl & 8)) continue;  // not FLG_HOT: no history
+      const double4 ft = w.ft[k], mo = (fl & 16) ? w.mo[k] : make_double4(0, 0, 0, 0);
       if (!rec_active(ft, mo, fl)) continue;
       const uint32_t s = atomicAdd(&cnt_hist[d], 1u);
       if (PACK) {

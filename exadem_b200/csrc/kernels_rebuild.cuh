@@ -208,12 +208,12 @@ __global__ void k_ghost_refresh(PView P, const uint32_t* __restrict__ gsrc, cons
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nghost) return;
   const uint32_t s = gsrc[g], k = gent[g], d = nreal + g;
-  double4 r = P.pr[s];
+  double4 r = ld4(P.pr + s);
   r.x = r.x + gshift[3 * k]; r.y = r.y + gshift[3 * k + 1]; r.z = r.z + gshift[3 * k + 2];
-  P.pr[d] = r;
-  P.vm[d] = P.vm[s];
-  P.wg[d] = P.wg[s];
-  P.q[d] = P.q[s];
+  st4(P.pr + d, r);
+  st4(P.vm + d, ld4(P.vm + s));
+  st4(P.wg + d, ld4(P.wg + s));
+  st4(P.q + d, ld4(P.q + s));
   if (ALL) {
     P.h[d] = P.h[s];
     P.id[d] = P.id[s];
@@ -268,7 +268,7 @@ __device__ __forceinline__ void for_each_neighbor(const NbhArgs& A, uint32_t a, 
         const uint32_t e = A.cend[cb];
         for (uint32_t b = A.cbeg[cb]; b < e; b++) {
           if (b == a) continue;
-          const double4 rb = A.P.pr[b];
+          const double4 rb = ldg4(A.P.pr + b);
           const v3 d = mk3(rb.x, rb.y, rb.z) - mk3(ra.x, ra.y, ra.z);
           const double d2 = dot(d, d);
           const double rmax = ra.w + rb.w + A.rcut_inc;
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(128) k_nbh_sphere(NbhArgs A, CntTab C, WTab W)
 struct VA {  // world-vertex accessor of one particle
   const double4* p;
   __device__ __forceinline__ v3 operator[](int i) const {
-    const double4 t = p[i];
+    const double4 t = ldg4(p + i);
     return mk3(t.x, t.y, t.z);
   }
 };
@@ -470,6 +470,7 @@ __global__ void k_history(WView nw, WView ow, const uint32_t* __restrict__ new2o
       if (has_sub && (r.sub_i != sb.x || r.sub_j != sb.y)) continue;
       nw.ft[k] = make_double4(r.ft[0], r.ft[1], r.ft[2], ft.w);
       nw.mo[k] = make_double4(r.mo[0], r.mo[1], r.mo[2], 0.0);
+      nw.flg[k] = fl | 8 | ((r.mo[0] != 0.0 || r.mo[1] != 0.0 || r.mo[2] != 0.0) ? 16 : 0);  // FLG_HOT | FLG_MOM (kernels_step.cuh)
       return;
     }
     return;
@@ -486,8 +487,12 @@ __global__ void k_history(WView nw, WView ow, const uint32_t* __restrict__ new2o
       const uint2 osb = ow.sub[s];
       if (osb.x != sb.x || osb.y != sb.y) continue;
     }
+    if (!(ofl & 8)) return;  // the old record was not in contact: no history (its payload is zero)
     nw.ft[k] = make_double4(oft.x, oft.y, oft.z, ft.w);
-    nw.mo[k] = ow.mo[s];
+    if (ofl & 16) nw.mo[k] = ow.mo[s];
+    nw.fd[k] = make_double4(0, 0, 0, 0);  // the wrench of the old evaluation does not survive the rebuild
+    nw.cp[k] = make_double4(0, 0, 0, 0);
+    nw.flg[k] = fl | 8 | (ofl & 16);
     return;
   }
 }

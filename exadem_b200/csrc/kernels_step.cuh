@@ -34,7 +34,7 @@ __device__ __forceinline__ const Params& cp_pd(const ParamsDev& P, uint32_t ga, 
 __global__ void k_prolog(PView P, uint32_t n, double dt, double dt2, double hdt) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
-  double4 r = P.pr[p], v = P.vm[p], w = P.wg[p], Q = P.q[p];
+  double4 r = ld4(P.pr + p), v = ld4(P.vm + p), w = ld4(P.wg + p), Q = ld4(P.q + p);
   const double ax = P.fx[p], ay = P.fy[p], az = P.fz[p];
   r.x += v.x * dt + ax * dt2; r.y += v.y * dt + ay * dt2; r.z += v.z * dt + az * dt2;
   v.x += ax * hdt; v.y += ay * hdt; v.z += az * hdt;
@@ -45,7 +45,7 @@ __global__ void k_prolog(PView P, uint32_t n, double dt, double dt2, double hdt)
   Q = make_double4(nq.w / nn, nq.x / nn, nq.y / nn, nq.z / nn);
   const v3 wn = mk3(w.x, w.y, w.z) + hdt * mk3(P.ax[p], P.ay[p], P.az[p]);
   w.x = wn.x; w.y = wn.y; w.z = wn.z;
-  P.pr[p] = r; P.vm[p] = v; P.wg[p] = w; P.q[p] = Q;
+  st4(P.pr + p, r); st4(P.vm + p, v); st4(P.wg + p, w); st4(P.q + p, Q);
 }
 // push_to_quaternion.hpp:26-38
 __global__ void k_push_to_quaternion(PView P, uint32_t n, double dt, double hdt) {
@@ -176,117 +176,219 @@ struct ContactArgs {
   int symetric;
 };
 
-// finish one record: history update + ContactState emission.  `contact` already includes the cohesive extension.
+// Record state bit FLG_HOT (flg bit 3): the record was in contact at its last evaluation, i.e. its history (ft, mo) and its
+// wrench (fd, cp) are live.  Invariant: !HOT  =>  friction = moment = 0 (contact_sphere.hpp:197-200 resets them) and fd/cp are
+// never read (the gather tests the bit; the ContactState export recomputes cp).  A record that is not in contact and was not
+// hot therefore costs 9 bytes (ij + flg) and two position gathers — no history read, no write.
+// FLG_MOM (flg bit 4): the rolling-moment history `mo` is non-zero.  With the reference's degenerate clamp (quirk Q1,
+// contact_force.hpp:229-234: mur = 0) the moment is zero for every contact whose particle i rotates, so the mo sector is
+// neither read nor written by the contact kernel, nor read by the gather, unless the bit says it holds something.
+constexpr uint8_t FLG_SWAP = 1, FLG_HOT = 8, FLG_MOM = 16;
+
+struct Hist {
+  double4 ft, mo;
+};
+
+// finish one record.  `contact` already includes the cohesive extension.  H is valid when `have_h`.
 template <int LAW>
-__device__ __forceinline__ void finish_record(const ContactArgs& A, uint32_t k, bool contact, const Contact& c, const Params& cp,
-                                              double meff, double reff, v3 ri, v3 vi, v3 wi, v3 pj, v3 vj, v3 wj) {
+__device__ __forceinline__ void finish_record(const ContactArgs& A, uint32_t k, uint8_t fl, bool contact, const Contact& c,
+                                              const Params& cp, double meff, double reff, v3 ri, v3 vi, v3 wi, v3 pj, v3 vj, v3 wj,
+                                              const Hist& H) {
+  uint8_t nf = fl;
   if (contact) {
-    const double4 ft4 = A.w.ft[k], mo4 = A.w.mo[k];
-    v3 ft = mk3(ft4.x, ft4.y, ft4.z), mom = mk3(mo4.x, mo4.y, mo4.z), f = mk3(0, 0, 0);
+    v3 ft = mk3(H.ft.x, H.ft.y, H.ft.z), mom = mk3(H.mo.x, H.mo.y, H.mo.z), f = mk3(0, 0, 0);
     contact_force<LAW>(c.dn, c.n, A.dt, cp, meff, reff, ft, c.cp, ri, vi, f, mom, wi, pj, vj, wj);
-    A.w.ft[k] = make_double4(ft.x, ft.y, ft.z, ft4.w);
-    A.w.mo[k] = make_double4(mom.x, mom.y, mom.z, 1.0);   // .w = 1 marks "contact this step" for the gather
-    A.w.fd[k] = make_double4(f.x, f.y, f.z, c.dn);
-  } else {
+    st4(A.w.ft + k, make_double4(ft.x, ft.y, ft.z, H.ft.w));
+    st4(A.w.fd + k, make_double4(f.x, f.y, f.z, c.dn));
+    st4(A.w.cp + k, make_double4(c.cp.x, c.cp.y, c.cp.z, 0));
+    const bool live = !is_zero(mom);   // NaN components count as live (x == 0.0 is false for NaN)
+    if (live || (fl & FLG_MOM)) st4(A.w.mo + k, make_double4(mom.x, mom.y, mom.z, 0.0));
+    nf = (uint8_t)((fl | FLG_HOT) & ~FLG_MOM) | (live ? FLG_MOM : 0);
+  } else if (fl & FLG_HOT) {
     // item.reset(); dn = 0 (contact_sphere.hpp:197-200) — friction & moment history are dropped
-    const double4 ft4 = A.w.ft[k];
-    A.w.ft[k] = make_double4(0, 0, 0, ft4.w);
-    A.w.mo[k] = make_double4(0, 0, 0, 0);
-    A.w.fd[k] = make_double4(0, 0, 0, 0);
+    st4(A.w.ft + k, make_double4(0, 0, 0, H.ft.w));
+    if (fl & FLG_MOM) st4(A.w.mo + k, make_double4(0, 0, 0, 0));
+    nf = fl & (uint8_t)~(FLG_HOT | FLG_MOM);
   }
-  A.w.cp[k] = make_double4(c.cp.x, c.cp.y, c.cp.z, 0);
+  if (nf != fl) A.w.flg[k] = nf;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // wave 0 of the sphere operator: sphere::ContactLawFunc (contact_sphere.hpp:121-203)
+// Two phases per block of BLK records.  Phase A (all threads): detection only (ij, flg, two position gathers); records that
+// need the force law (contact) or a history reset (hot, no contact) are compacted, order-preserving, into shared memory and
+// their remaining operands are prefetched into L2.  Phase B (the first `tot` threads): dense evaluation of the Hooke law — no
+// divergence between contacting and non-contacting lanes, which was 58 % of the lanes of every warp in the drum.
 template <int LAW>
-__global__ void __launch_bounds__(BLK) k_contact_sphere_pp(ContactArgs A) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= A.w.n) return;
+__global__ void __launch_bounds__(BLK, 3) k_contact_sphere_pp(ContactArgs A) {
+  __shared__ uint32_t s_list[BLK];
+  const uint32_t k0 = blockIdx.x * BLK;
+  bool need = false;
+  {
+    const uint32_t k = k0 + threadIdx.x;
+    if (k < A.w.n) {
+      const uint2 ij = A.w.ij[k];
+      const uint8_t fl = A.w.flg[k];
+      const bool hot = fl & FLG_HOT;
+      if (hot) {
+        prefetch_l2(A.w.ft + k);
+        prefetch_l2(A.P.vm + ij.x); prefetch_l2(A.P.vm + ij.y); prefetch_l2(A.P.wg + ij.x); prefetch_l2(A.P.wg + ij.y);
+      }
+      const double4 pi = ldg4(A.P.pr + ij.x), pj = ldg4(A.P.pr + ij.y);
+      const Contact c = detect_vv(mk3(pi.x, pi.y, pi.z), pi.w, mk3(pj.x, pj.y, pj.z), pj.w);
+      bool contact = c.hit;
+      if (LAW == LAW_COHESIVE) {
+        const double dncut = A.prm.tpp ? cp_pp(A.prm, group_of(ldg4(A.P.wg + ij.x)), group_of(ldg4(A.P.wg + ij.y))).dncut : A.prm.pp.dncut;
+        contact = contact || c.dn <= dncut;
+      }
+      need = contact || hot;
+    }
+  }
+  uint32_t tot;
+  const uint32_t pos = block_excl_scan(need ? 1u : 0u, &tot);
+  if (need) s_list[pos] = threadIdx.x;
+  __syncthreads();
+  if (threadIdx.x >= tot) return;
+  const uint32_t k = k0 + s_list[threadIdx.x];
   const uint2 ij = A.w.ij[k];
-  const double4 pi = A.P.pr[ij.x], pj = A.P.pr[ij.y];
+  const uint8_t fl = A.w.flg[k];
+  const double4 pi = ldg4(A.P.pr + ij.x), pj = ldg4(A.P.pr + ij.y);
+  const double4 wi = ldg4(A.P.wg + ij.x), wj = ldg4(A.P.wg + ij.y);
+  const double4 vi = ldg4(A.P.vm + ij.x), vj = ldg4(A.P.vm + ij.y);
+  Hist H;
+  H.ft = ld4(A.w.ft + k);
+  H.mo = (fl & FLG_MOM) ? ld4(A.w.mo + k) : make_double4(0, 0, 0, 0);
   const v3 ri = mk3(pi.x, pi.y, pi.z), rj = mk3(pj.x, pj.y, pj.z);
   const Contact c = detect_vv(ri, pi.w, rj, pj.w);
-  const double4 wi = A.P.wg[ij.x], wj = A.P.wg[ij.y];
   const Params& cp = cp_pp(A.prm, group_of(wi), group_of(wj));
   bool contact = c.hit;
   if (LAW == LAW_COHESIVE) contact = contact || c.dn <= cp.dncut;
-  double meff = 0, reff = 0;
-  double4 vi = make_double4(0, 0, 0, 0), vj = vi;
-  if (contact) {
-    vi = A.P.vm[ij.x]; vj = A.P.vm[ij.y];
-    meff = (vi.w * vj.w) / (vi.w + vj.w);   // common_kernels.hpp:93-96
-    reff = (pi.w * pj.w) / (pi.w + pj.w);   // :99-102
-  }
-  finish_record<LAW>(A, k, contact, c, cp, meff, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), rj,
-                     mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z));
+  const double meff = (vi.w * vj.w) / (vi.w + vj.w);   // common_kernels.hpp:93-96
+  const double reff = (pi.w * pj.w) / (pi.w + pj.w);   // :99-102
+  finish_record<LAW>(A, k, fl, contact, c, cp, meff, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), rj,
+                     mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z), H);
 }
 
-// waves 4,5,6 (cylinder / surface / ball): sphere::ContactLawDriverFunc (contact_sphere.hpp:232-296),
+// detection of a driver record (waves 4,5,6): sphere::ContactLawDriverFunc (contact_sphere.hpp:232-296),
 // polyhedron::ContactLawDriverFunc (polyhedron/contact.hpp:237-303)
+template <bool POLY>
+__device__ __forceinline__ Contact detect_driver_record(const ContactArgs& A, uint32_t k, const uint2 ij, const Driver& D, const double4& pi,
+                                                        const double4& wi, double& reff) {
+  if (!POLY) {
+    reff = pi.w;
+    return driver_detect(D, pi.w, mk3(pi.x, pi.y, pi.z));
+  }
+  const ShapeDev sh = A.S.sh[type_of(wi)];
+  const double rm = A.P.h[ij.x] * sh.radius;
+  const double4 vx = A.vert[(size_t)ij.x * A.S.nvmax + A.w.sub[k].x];
+  reff = rm;
+  return driver_detect(D, rm, mk3(vx.x, vx.y, vx.z));
+}
 template <int LAW, bool POLY>
 __global__ void __launch_bounds__(BLK) k_contact_driver(ContactArgs A) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= A.w.n) return;
   const uint2 ij = A.w.ij[k];
+  const uint8_t fl = A.w.flg[k];
+  const bool hot = fl & FLG_HOT;
   const Driver D = A.drv[ij.y];
-  const double4 pi = A.P.pr[ij.x], wi = A.P.wg[ij.x];
-  const v3 ri = mk3(pi.x, pi.y, pi.z);
-  Contact c;
+  const double4 pi = ldg4(A.P.pr + ij.x), wi = ldg4(A.P.wg + ij.x);
+  Hist H;
+  double4 vi = make_double4(0, 0, 0, 0);
+  if (hot) { H.ft = ld4(A.w.ft + k); vi = ldg4(A.P.vm + ij.x); }
+  H.mo = (fl & FLG_MOM) ? ld4(A.w.mo + k) : make_double4(0, 0, 0, 0);
   double reff;
-  if (!POLY) {
-    c = driver_detect(D, pi.w, ri);
-    reff = pi.w;
-  } else {
-    const ShapeDev sh = A.S.sh[type_of(wi)];
-    const double rm = A.P.h[ij.x] * sh.radius;
-    const double4 vx = A.vert[(size_t)ij.x * A.S.nvmax + A.w.sub[k].x];
-    c = driver_detect(D, rm, mk3(vx.x, vx.y, vx.z));
-    reff = rm;
-  }
+  const Contact c = detect_driver_record<POLY>(A, k, ij, D, pi, wi, reff);
   const Params& cp = cp_pd(A.prm, group_of(wi), ij.y);
   bool contact = c.hit;
   if (LAW == LAW_COHESIVE) contact = contact || c.dn <= cp.dncut;
-  double4 vi = make_double4(0, 0, 0, 0);
-  if (contact) vi = A.P.vm[ij.x];
-  finish_record<LAW>(A, k, contact, c, cp, vi.w, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), D.center, D.vel, D.vrot);
+  if (!contact && !hot) return;
+  if (contact && !hot) { H.ft = ld4(A.w.ft + k); vi = ldg4(A.P.vm + ij.x); }
+  finish_record<LAW>(A, k, fl, contact, c, cp, vi.w, reff, mk3(pi.x, pi.y, pi.z), mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), D.center,
+                     D.vel, D.vrot, H);
 }
 
+// detection of a polyhedron particle-particle record of wave `type` (polyhedron/contact.hpp:124-211 -> detect<type>)
+__device__ __forceinline__ Contact detect_poly_record(const ContactArgs& A, int type, const uint2 ij, const uint2 sb, const ShapeDev& si,
+                                                      const ShapeDev& sj, double rmi, double rmj) {
+  const VA vi_{A.vert + (size_t)ij.x * A.S.nvmax}, vj_{A.vert + (size_t)ij.y * A.S.nvmax};
+  if (type == 0) return detect_vv(vi_[sb.x], rmi, vj_[sb.y], rmj);
+  if (type == 1) {
+    const int* e = A.S.edges + 2 * (sj.e0 + sb.y);
+    return detect_ve(vi_[sb.x], rmi, vj_[e[0]], vj_[e[1]], rmj);
+  }
+  if (type == 2) return detect_vf(vi_[sb.x], rmi, vj_, rmj, A.S.fidx + sj.fi0 + A.S.foff[sj.f0 + sb.y], A.S.fn[sj.f0 + sb.y]);
+  const int* ei = A.S.edges + 2 * (si.e0 + sb.x);
+  const int* ej = A.S.edges + 2 * (sj.e0 + sb.y);
+  return detect_ee(vi_[ei[0]], vi_[ei[1]], rmi, vj_[ej[0]], vj_[ej[1]], rmj);
+}
 // waves 0..3 of the polyhedron operator: polyhedron::ContactLawFunc<type> (polyhedron/contact.hpp:124-211)
 template <int LAW>
 __global__ void __launch_bounds__(BLK) k_contact_poly_pp(ContactArgs A) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= A.w.n) return;
   const uint2 ij = A.w.ij[k], sb = A.w.sub[k];
-  const double4 pi = A.P.pr[ij.x], pj = A.P.pr[ij.y];
-  const double4 wi = A.P.wg[ij.x], wj = A.P.wg[ij.y];
+  const uint8_t fl = A.w.flg[k];
+  const bool hot = fl & FLG_HOT;
+  const double4 wi = ldg4(A.P.wg + ij.x), wj = ldg4(A.P.wg + ij.y);
+  Hist H;
+  double4 vi = make_double4(0, 0, 0, 0), vj = vi;
+  if (hot) { H.ft = ld4(A.w.ft + k); vi = ldg4(A.P.vm + ij.x); vj = ldg4(A.P.vm + ij.y); }
+  H.mo = (fl & FLG_MOM) ? ld4(A.w.mo + k) : make_double4(0, 0, 0, 0);
   const ShapeDev si = A.S.sh[type_of(wi)], sj = A.S.sh[type_of(wj)];
   const double rmi = A.P.h[ij.x] * si.radius, rmj = A.P.h[ij.y] * sj.radius;
-  const VA vi_{A.vert + (size_t)ij.x * A.S.nvmax}, vj_{A.vert + (size_t)ij.y * A.S.nvmax};
-  Contact c;
-  if (A.type == 0) {
-    c = detect_vv(vi_[sb.x], rmi, vj_[sb.y], rmj);
-  } else if (A.type == 1) {
-    const int* e = A.S.edges + 2 * (sj.e0 + sb.y);
-    c = detect_ve(vi_[sb.x], rmi, vj_[e[0]], vj_[e[1]], rmj);
-  } else if (A.type == 2) {
-    c = detect_vf(vi_[sb.x], rmi, vj_, rmj, A.S.fidx + sj.fi0 + A.S.foff[sj.f0 + sb.y], A.S.fn[sj.f0 + sb.y]);
-  } else {
-    const int* ei = A.S.edges + 2 * (si.e0 + sb.x);
-    const int* ej = A.S.edges + 2 * (sj.e0 + sb.y);
-    c = detect_ee(vi_[ei[0]], vi_[ei[1]], rmi, vj_[ej[0]], vj_[ej[1]], rmj);
-  }
+  const Contact c = detect_poly_record(A, A.type, ij, sb, si, sj, rmi, rmj);
   const Params& cp = cp_pp(A.prm, group_of(wi), group_of(wj));
   bool contact = c.hit;
   if (LAW == LAW_COHESIVE) contact = contact || c.dn <= cp.dncut;
+  if (!contact && !hot) return;
+  if (contact && !hot) { H.ft = ld4(A.w.ft + k); vi = ldg4(A.P.vm + ij.x); vj = ldg4(A.P.vm + ij.y); }
+  const double4 pi = ldg4(A.P.pr + ij.x), pj = ldg4(A.P.pr + ij.y);
   double meff = 0, reff = 0;
-  double4 vi = make_double4(0, 0, 0, 0), vj = vi;
   if (contact) {
-    vi = A.P.vm[ij.x]; vj = A.P.vm[ij.y];
     meff = (vi.w * vj.w) / (vi.w + vj.w);
     reff = (rmi * rmj) / (rmi + rmj);  // contact.hpp:183 (effective-mass formula on the Minkowski radii)
   }
-  finish_record<LAW>(A, k, contact, c, cp, meff, reff, mk3(pi.x, pi.y, pi.z), mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z),
-                     mk3(pj.x, pj.y, pj.z), mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z));
+  finish_record<LAW>(A, k, fl, contact, c, cp, meff, reff, mk3(pi.x, pi.y, pi.z), mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z),
+                     mk3(pj.x, pj.y, pj.z), mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z), H);
+}
+
+// ContactState view of a wave (classifier/contact_state.hpp:22-51): dn, cp, fn = f - ft (contact_sphere.hpp:180), ft.
+// Records that are not hot hold no stored state: dn = fn = ft = 0 and cp is what the detection returns for the current
+// positions (what the reference stores too, since it runs the detection for every record).
+template <bool POLY>
+__global__ void k_state(ContactArgs A, double* __restrict__ dn, double* __restrict__ cp, double* __restrict__ fn, double* __restrict__ ft) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= A.w.n) return;
+  const uint8_t fl = A.w.flg[k];
+  if (fl & FLG_HOT) {
+    const double4 fd = ld4(A.w.fd + k), c4 = ld4(A.w.cp + k), f4 = ld4(A.w.ft + k);
+    dn[k] = fd.w;
+    cp[3 * k] = c4.x; cp[3 * k + 1] = c4.y; cp[3 * k + 2] = c4.z;
+    fn[3 * k] = fd.x - f4.x; fn[3 * k + 1] = fd.y - f4.y; fn[3 * k + 2] = fd.z - f4.z;
+    ft[3 * k] = f4.x; ft[3 * k + 1] = f4.y; ft[3 * k + 2] = f4.z;
+    return;
+  }
+  const uint2 ij = A.w.ij[k];
+  Contact c;
+  if (A.type <= 3) {
+    if (!POLY) {
+      const double4 pi = ldg4(A.P.pr + ij.x), pj = ldg4(A.P.pr + ij.y);
+      c = detect_vv(mk3(pi.x, pi.y, pi.z), pi.w, mk3(pj.x, pj.y, pj.z), pj.w);
+    } else {
+      const double4 wi = ldg4(A.P.wg + ij.x), wj = ldg4(A.P.wg + ij.y);
+      const ShapeDev si = A.S.sh[type_of(wi)], sj = A.S.sh[type_of(wj)];
+      c = detect_poly_record(A, A.type, ij, A.w.sub[k], si, sj, A.P.h[ij.x] * si.radius, A.P.h[ij.y] * sj.radius);
+    }
+  } else {
+    double reff;
+    c = detect_driver_record<POLY>(A, k, ij, A.drv[ij.y], ldg4(A.P.pr + ij.x), ldg4(A.P.wg + ij.x), reff);
+  }
+  dn[k] = 0.0;
+  cp[3 * k] = c.cp.x; cp[3 * k + 1] = c.cp.y; cp[3 * k + 2] = c.cp.z;
+  fn[3 * k] = 0.0; fn[3 * k + 1] = 0.0; fn[3 * k + 2] = 0.0;
+  ft[3 * k] = 0.0; ft[3 * k + 1] = 0.0; ft[3 * k + 2] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -307,10 +409,9 @@ struct GatherArgs {
 };
 
 // role_i: particle acts as "i" of the record: F += f, M += (cp - r) x f + mom;  as "j": F += -f, M += (cp - r) x (-f) + (-mom)
-__device__ __forceinline__ void add_wrench(const WView& w, uint32_t k, bool role_i, v3 r, v3& F, v3& M) {
-  const double4 mo = w.mo[k];
-  if (mo.w == 0.0) return;  // no contact this step: the record contributes nothing (f = 0, mom = 0)
-  const double4 fd = w.fd[k], cp = w.cp[k];
+__device__ __forceinline__ void add_wrench(const WView& w, uint32_t k, uint8_t fl, bool role_i, v3 r, v3& F, v3& M) {
+  const double4 fd = ld4(w.fd + k), cp = ld4(w.cp + k);
+  const double4 mo = (fl & FLG_MOM) ? ld4(w.mo + k) : make_double4(0, 0, 0, 0);
   v3 f = mk3(fd.x, fd.y, fd.z), m = mk3(mo.x, mo.y, mo.z);
   if (!role_i) {
     f = -f;
@@ -327,12 +428,12 @@ template <int FUSE>
 __global__ void __launch_bounds__(BLK) k_gather(GatherArgs A) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= A.nreal) return;
-  const double4 pr = A.P.pr[p];
+  const double4 pr = ldg4(A.P.pr + p);
   const v3 r = mk3(pr.x, pr.y, pr.z);
   v3 F, M;
   double4 vm;
   if (FUSE) {
-    vm = A.P.vm[p];
+    vm = ld4(A.P.vm + p);
     F = mk3(0.0 + A.g[0] * vm.w, 0.0 + A.g[1] * vm.w, 0.0 + A.g[2] * vm.w);
     M = mk3(0, 0, 0);
   } else {
@@ -350,21 +451,24 @@ __global__ void __launch_bounds__(BLK) k_gather(GatherArgs A) {
     if (t <= 3 && A.pp_partner) {  // partner records that precede the owner segment in wave order
       while ((code >> INC_SHIFT) == (uint32_t)t && (code & INC_MASK) < a) {
         const uint32_t k = code & INC_MASK;
-        const bool owner_is_i = A.has_swap ? !(w.flg[k] & 1) : true;
-        add_wrench(w, k, !owner_is_i, r, F, M);
+        const uint8_t fl = w.flg[k];
+        const bool owner_is_i = A.has_swap ? !(fl & FLG_SWAP) : true;
+        if (fl & FLG_HOT) add_wrench(w, k, fl, !owner_is_i, r, F, M);
         e++;
         code = e < eend ? A.inc[e] : 0xffffffffu;
       }
     }
     for (uint32_t k = a; k < b; k++) {
-      const bool owner_is_i = (t <= 3 && A.has_swap) ? !(w.flg[k] & 1) : true;
-      add_wrench(w, k, owner_is_i, r, F, M);
+      const uint8_t fl = w.flg[k];
+      const bool owner_is_i = (t <= 3 && A.has_swap) ? !(fl & FLG_SWAP) : true;
+      if (fl & FLG_HOT) add_wrench(w, k, fl, owner_is_i, r, F, M);
     }
     if (t <= 3 && A.pp_partner) {
       while ((code >> INC_SHIFT) == (uint32_t)t) {
         const uint32_t k = code & INC_MASK;
-        const bool owner_is_i = A.has_swap ? !(w.flg[k] & 1) : true;
-        add_wrench(w, k, !owner_is_i, r, F, M);
+        const uint8_t fl = w.flg[k];
+        const bool owner_is_i = A.has_swap ? !(fl & FLG_SWAP) : true;
+        if (fl & FLG_HOT) add_wrench(w, k, fl, !owner_is_i, r, F, M);
         e++;
         code = e < eend ? A.inc[e] : 0xffffffffu;
       }
@@ -376,15 +480,15 @@ __global__ void __launch_bounds__(BLK) k_gather(GatherArgs A) {
   } else {
     // force_to_accel, then combined_compute_epilog
     const v3 acc = mk3(F.x / vm.w, F.y / vm.w, F.z / vm.w);
-    double4 w = A.P.wg[p];
-    const v3 ar = ang_accel(A.P.q[p], M, mk3(w.x, w.y, w.z), mk3(A.P.ix[p], A.P.iy[p], A.P.iz[p]));
+    double4 w = ld4(A.P.wg + p);
+    const v3 ar = ang_accel(ldg4(A.P.q + p), M, mk3(w.x, w.y, w.z), mk3(A.P.ix[p], A.P.iy[p], A.P.iz[p]));
     const v3 wn = mk3(w.x, w.y, w.z) + ar * A.hdt;
     w.x = wn.x; w.y = wn.y; w.z = wn.z;
     vm.x += acc.x * A.hdt; vm.y += acc.y * A.hdt; vm.z += acc.z * A.hdt;
     A.P.fx[p] = acc.x; A.P.fy[p] = acc.y; A.P.fz[p] = acc.z;
     A.P.mx[p] = M.x; A.P.my[p] = M.y; A.P.mz[p] = M.z;
     A.P.ax[p] = ar.x; A.P.ay[p] = ar.y; A.P.az[p] = ar.z;
-    A.P.wg[p] = w; A.P.vm[p] = vm;
+    st4(A.P.wg + p, w); st4(A.P.vm + p, vm);
   }
 }
 
@@ -401,9 +505,8 @@ __global__ void __launch_bounds__(BLK) k_driver_force(WView w, const Driver* __r
   v3 f = mk3(0, 0, 0), m = mk3(0, 0, 0);
   int d = -1;
   if (k < w.n) {
-    const double4 mo = w.mo[k];
-    if (mo.w != 0.0) {
-      const double4 fd = w.fd[k], cp = w.cp[k], ft4 = w.ft[k];
+    if (w.flg[k] & FLG_HOT) {
+      const double4 mo = w.mo[k], fd = w.fd[k], cp = w.cp[k], ft4 = w.ft[k];
       d = (int)w.ij[k].y;
       const v3 ft = mk3(ft4.x, ft4.y, ft4.z);
       const v3 fn = mk3(fd.x, fd.y, fd.z) - ft;   // ContactState fn (contact_sphere.hpp:180)
