@@ -158,3 +158,27 @@ def ghost_plan(glo, ghi, periodic, pgrid, rank, nc):
                 if ok:
                     plan.append((idx, rb[0] + pgrid[0] * (rb[1] + pgrid[1] * rb[2]), tuple(src), tuple(shift)))
     return plan
+
+
+def send_plan(glo, ghi, periodic, pgrid, rank, nc):
+    """What `rank` must SEND: for every other rank, the entries of THAT rank's ghost plan whose source is `rank`, in that
+    rank's enumeration order (every brick has the same cell grid, so no handshake is needed) — mirrors
+    Comm::plan_send_lists in csrc/comm.cuh."""
+    nranks = pgrid[0] * pgrid[1] * pgrid[2]
+    out = {}
+    for other in range(nranks):
+        if other == rank:
+            continue
+        ent = [(g, s, sh) for (g, src_rank, s, sh) in ghost_plan(glo, ghi, periodic, pgrid, other, nc) if src_rank == rank]
+        if ent:
+            out[other] = ent
+    return out
+
+
+def recv_plan(glo, ghi, periodic, pgrid, rank, nc):
+    """What `rank` RECEIVES, per source rank, in its own enumeration order (local periodic images excluded)."""
+    out = {}
+    for (g, src_rank, s, sh) in ghost_plan(glo, ghi, periodic, pgrid, rank, nc):
+        if src_rank != rank:
+            out.setdefault(src_rank, []).append((g, s, sh))
+    return out
