@@ -48,7 +48,8 @@ class ContactParams(C.Structure):
 class Driver(C.Structure):
     _fields_ = [("kind", C.c_int32), ("need_forces", C.c_int32), ("radius", C.c_double), ("axis", C.c_double * 3),
                 ("center", C.c_double * 3), ("offset", C.c_double), ("normal", C.c_double * 3),
-                ("vel", C.c_double * 3), ("vrot", C.c_double * 3), ("shape", C.c_int32), ("reserved", C.c_int32)]
+                ("vel", C.c_double * 3), ("vrot", C.c_double * 3), ("shape", C.c_int32), ("reserved", C.c_int32),
+                ("quat", C.c_double * 4)]
 
 
 class Shape(C.Structure):
@@ -251,6 +252,8 @@ class Engine:
                     getattr(D, name)[c] = float(val[c])
             D.offset = d.get("offset", 0.0)
             D.shape = d.get("shape", -1)
+            for c, qv in enumerate(d.get("quat", (1.0, 0.0, 0.0, 0.0))):
+                D.quat[c] = float(qv)
             arr[k] = D
         self._call("set_drivers", C.c_int32(len(drivers)), arr)
 
@@ -258,6 +261,12 @@ class Engine:
         arr = (Shape * len(shapes))(*shapes)
         self._keep_shapes = shapes
         self._call("set_shapes", C.c_int32(len(shapes)), arr)
+
+    def set_driver_shapes(self, shapes):
+        """Mesh shapes of the RShape drivers (call before set_drivers)."""
+        arr = (Shape * max(1, len(shapes)))(*shapes)
+        self._keep_driver_shapes = shapes
+        self._call("set_driver_shapes", C.c_int32(len(shapes)), arr)
 
     # -- grid
     def upload_particles(self, pa: ParticleArrays):

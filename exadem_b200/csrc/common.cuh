@@ -134,6 +134,28 @@ struct ShapesView {
   int nvmax;
 };
 
+// RShape (STL mesh) drivers, device view.  One MeshDev per RSHAPE driver (Driver::shape = its slot): world vertices are
+// RShapeDriver::vertices_ = position + orientation * v (rshape.hpp:381-384), computed when the drivers are set.
+// cell_off/cell_data: per (mesh, grid cell, kind in {vertex, edge, face}) the primitives that can reach a particle of the cell —
+// the role of the reference's RShapeDriverGridCellIndexes (rshape_grid.hpp, grid_stl_mesh.cpp:150-251).
+struct MeshDev {
+  int nv, ne, nf, pad;
+  int v0, e0, f0, fi0;  // offsets into the pooled mesh arrays
+  double radius;        // Minkowski radius (homothety 1)
+};
+struct MeshView {
+  const MeshDev* md;
+  const double4* verts;   // world vertices
+  const int* edges;
+  const int* foff;
+  const int* fn;
+  const int* fidx;
+  const uint32_t* cell_off;  // [(m * ncell + cell) * 3 + kind], nmesh * ncell * 3 + 1 entries
+  const int* cell_data;
+  int nmesh;
+  uint32_t ncell;
+};
+
 struct GridDev {
   int nc[3], g[3];
   double lo[3], cs[3];

@@ -59,6 +59,20 @@ struct edb_context {
   DevBuf<v3> d_sv;
   DevBuf<int> d_se, d_sfoff, d_sfn, d_sfidx;
   ShapesView S{};
+  // RShape (mesh) drivers
+  std::vector<edb_shape> h_mesh_shape;            // as given (pointers re-homed into the pools below)
+  std::vector<std::vector<double>> h_mesh_v;      // local vertices per mesh shape
+  std::vector<std::vector<int>> h_mesh_e, h_mesh_foff, h_mesh_fn, h_mesh_fidx;
+  std::vector<double> h_mesh_radius;
+  std::vector<MeshDev> h_md;                      // one per RSHAPE driver
+  std::vector<double4> h_mverts;                  // pooled world vertices
+  std::vector<int> h_medges, h_mfoff, h_mfn, h_mfidx;
+  DevBuf<MeshDev> d_md;
+  DevBuf<double4> d_mverts;
+  DevBuf<int> d_medges, d_mfoff, d_mfn, d_mfidx, d_mcell_data;
+  DevBuf<uint32_t> d_mcell_off;
+  MeshView M{};
+  bool mesh_dirty = false;
   // staging for host transfers
   DevBuf<double> stage;
   DevBuf<uint64_t> stage_u64;
@@ -273,6 +287,8 @@ extern "C" int edb_destroy(edb_context* c) {
   c->pr_backup.release(); c->q_backup.release(); c->vert.release(); c->g_shift.release(); c->tpp.release(); c->tpd.release();
   c->drv.release(); c->d_sh.release(); c->d_sv.release(); c->d_se.release(); c->d_sfoff.release(); c->d_sfn.release(); c->d_sfidx.release();
   c->stage.release(); c->stage_u64.release(); c->l2buf.release();
+  c->d_md.release(); c->d_mverts.release(); c->d_medges.release(); c->d_mfoff.release(); c->d_mfn.release(); c->d_mfidx.release();
+  c->d_mcell_data.release(); c->d_mcell_off.release();
   c->mig_dest.release(); c->mig_midx.release(); c->mig_cnt.release(); c->mig_off.release(); c->imm_cnt.release(); c->imm_off.release();
   c->mig_sp.release(); c->mig_rp.release(); c->mig_sh.release(); c->mig_rh.release(); c->imm_tab.release();
   for (auto& e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -338,9 +354,54 @@ extern "C" int edb_set_drivers(edb_context* c, int32_t n, const edb_driver* d) {
     D.shape = d[i].shape;
     c->h_drv.push_back(D);
   }
+  // RShape drivers: world vertices = position + orientation * v (rshape.hpp:381-384), pooled per driver
+  c->h_md.clear(); c->h_mverts.clear(); c->h_medges.clear(); c->h_mfoff.clear(); c->h_mfn.clear(); c->h_mfidx.clear();
+  for (int i = 0; i < n; i++) {
+    Driver& D = c->h_drv[i];
+    if (D.kind != EDB_DRIVER_RSHAPE) continue;
+    const int sidx = d[i].shape;
+    if (sidx < 0 || sidx >= (int)c->h_mesh_v.size()) throw StateError{EDB_ERR_INVALID, "RSHAPE driver: shape index outside the edb_set_driver_shapes table"};
+    MeshDev md{};
+    const auto& lv = c->h_mesh_v[sidx];
+    md.nv = (int)lv.size() / 3; md.ne = (int)c->h_mesh_e[sidx].size() / 2; md.nf = (int)c->h_mesh_fn[sidx].size();
+    md.v0 = (int)c->h_mverts.size(); md.e0 = (int)c->h_medges.size() / 2; md.f0 = (int)c->h_mfn.size(); md.fi0 = (int)c->h_mfidx.size();
+    md.radius = c->h_mesh_radius[sidx];
+    const q4 q{d[i].quat[0], d[i].quat[1], d[i].quat[2], d[i].quat[3]};
+    for (int k = 0; k < md.nv; k++) {
+      const v3 w = D.center + qrot(q, 1.0 * mk3(lv[3 * k], lv[3 * k + 1], lv[3 * k + 2]));
+      c->h_mverts.push_back(make_double4(w.x, w.y, w.z, 0.0));
+    }
+    c->h_medges.insert(c->h_medges.end(), c->h_mesh_e[sidx].begin(), c->h_mesh_e[sidx].end());
+    c->h_mfoff.insert(c->h_mfoff.end(), c->h_mesh_foff[sidx].begin(), c->h_mesh_foff[sidx].end());
+    c->h_mfn.insert(c->h_mfn.end(), c->h_mesh_fn[sidx].begin(), c->h_mesh_fn[sidx].end());
+    c->h_mfidx.insert(c->h_mfidx.end(), c->h_mesh_fidx[sidx].begin(), c->h_mesh_fidx[sidx].end());
+    D.shape = (int)c->h_md.size();   // device: slot of this driver's mesh
+    c->h_md.push_back(md);
+  }
+  c->mesh_dirty = true;
   c->drv.ensure(n + 1);
   if (n) CK(cudaMemcpy(c->drv.p, c->h_drv.data(), n * sizeof(Driver), cudaMemcpyHostToDevice));
   if (!c->prm.tpd) c->prm.n_drivers = n;
+  API_END(c)
+}
+extern "C" int edb_set_driver_shapes(edb_context* c, int32_t n, const edb_shape* sh) {
+  API_BEGIN(c)
+  c->h_mesh_v.clear(); c->h_mesh_e.clear(); c->h_mesh_foff.clear(); c->h_mesh_fn.clear(); c->h_mesh_fidx.clear(); c->h_mesh_radius.clear();
+  for (int i = 0; i < n; i++) {
+    c->h_mesh_v.emplace_back(sh[i].vertices, sh[i].vertices + 3 * (size_t)sh[i].nv);
+    c->h_mesh_e.emplace_back(sh[i].edges, sh[i].edges + 2 * (size_t)sh[i].ne);
+    std::vector<int> foff, fn, fidx;
+    int pos = 0;
+    for (int f = 0; f < sh[i].nf; f++) {
+      const int nfv = sh[i].faces[pos++];
+      if (nfv < 3 || pos + nfv > sh[i].faces_len) throw StateError{EDB_ERR_INVALID, "malformed face stream"};
+      foff.push_back((int)fidx.size());
+      fn.push_back(nfv);
+      for (int k = 0; k < nfv; k++) fidx.push_back(sh[i].faces[pos++]);
+    }
+    c->h_mesh_foff.push_back(foff); c->h_mesh_fn.push_back(fn); c->h_mesh_fidx.push_back(fidx);
+    c->h_mesh_radius.push_back(sh[i].radius);
+  }
   API_END(c)
 }
 extern "C" int edb_set_shapes(edb_context* c, int32_t n, const edb_shape* sh) {
@@ -558,6 +619,70 @@ static void compute_vertices(edb_context* c) {
   LAUNCH(c, k_compute_vertices, nblk(ntot), BLK, 0, view(c->pa), ntot, c->S, c->vert.p);
 }
 
+// Per-cell primitive lists of the RShape meshes (host-built, rebuild-frequency; the reference builds them on the host too,
+// grid_stl_mesh.cpp:150-251).  A primitive is listed in every real cell its bounding box, enlarged by Minkowski radius + cell
+// size, overlaps: conservative for any particle of the cell because cell_size >= 2 r_max + rcut_inc (check_rcut.cpp:72).
+static void build_mesh_grid(edb_context* c) {
+  const GridDev& G = c->G;
+  const int nm = (int)c->h_md.size();
+  c->M = MeshView{};
+  c->mesh_dirty = false;
+  if (nm == 0) return;
+  const size_t ncell = G.ncell;
+  std::vector<std::vector<int>> lists((size_t)nm * ncell * 3);
+  const double Rmax = std::max(c->cfg.cell_size, std::max(G.cs[0], std::max(G.cs[1], G.cs[2])));
+  for (int m = 0; m < nm; m++) {
+    const MeshDev& md = c->h_md[m];
+    auto add = [&](int kind, int id, const int* vidx, int nvtx) {
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int k = 0; k < nvtx; k++) {
+        const double4 v = c->h_mverts[md.v0 + vidx[k]];
+        const double x[3] = {v.x, v.y, v.z};
+        for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], x[d]); hi[d] = std::max(hi[d], x[d]); }
+      }
+      int a[3], b[3];
+      for (int d = 0; d < 3; d++) {
+        const double e = md.radius + Rmax;
+        a[d] = (int)std::floor((lo[d] - e - G.lo[d]) / G.cs[d]) + 1;
+        b[d] = (int)std::floor((hi[d] + e - G.lo[d]) / G.cs[d]) + 1;
+        a[d] = std::max(a[d], 1); b[d] = std::min(b[d], G.nc[d]);
+        if (a[d] > b[d]) return;
+      }
+      for (int z = a[2]; z <= b[2]; z++)
+        for (int y = a[1]; y <= b[1]; y++)
+          for (int x = a[0]; x <= b[0]; x++) {
+            const size_t cell = (size_t)x + (size_t)G.g[0] * ((size_t)y + (size_t)G.g[1] * (size_t)z);
+            lists[((size_t)m * ncell + cell) * 3 + kind].push_back(id);
+          }
+    };
+    for (int v = 0; v < md.nv; v++) add(0, v, &v, 1);
+    for (int e = 0; e < md.ne; e++) add(1, e, &c->h_medges[2 * (md.e0 + e)], 2);
+    for (int f = 0; f < md.nf; f++) add(2, f, &c->h_mfidx[md.fi0 + c->h_mfoff[md.f0 + f]], c->h_mfn[md.f0 + f]);
+  }
+  std::vector<uint32_t> off(lists.size() + 1, 0);
+  std::vector<int> data;
+  for (size_t i = 0; i < lists.size(); i++) {
+    off[i] = (uint32_t)data.size();
+    data.insert(data.end(), lists[i].begin(), lists[i].end());
+  }
+  off[lists.size()] = (uint32_t)data.size();
+  c->d_md.ensure(nm); c->d_mverts.ensure(c->h_mverts.size() + 1); c->d_medges.ensure(c->h_medges.size() + 1);
+  c->d_mfoff.ensure(c->h_mfoff.size() + 1); c->d_mfn.ensure(c->h_mfn.size() + 1); c->d_mfidx.ensure(c->h_mfidx.size() + 1);
+  c->d_mcell_off.ensure(off.size()); c->d_mcell_data.ensure(data.size() + 1);
+  CK(cudaMemcpy(c->d_md.p, c->h_md.data(), nm * sizeof(MeshDev), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_mverts.p, c->h_mverts.data(), c->h_mverts.size() * sizeof(double4), cudaMemcpyHostToDevice));
+  if (!c->h_medges.empty()) CK(cudaMemcpy(c->d_medges.p, c->h_medges.data(), c->h_medges.size() * 4, cudaMemcpyHostToDevice));
+  if (!c->h_mfn.empty()) {
+    CK(cudaMemcpy(c->d_mfoff.p, c->h_mfoff.data(), c->h_mfoff.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_mfn.p, c->h_mfn.data(), c->h_mfn.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_mfidx.p, c->h_mfidx.data(), c->h_mfidx.size() * 4, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemcpy(c->d_mcell_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+  if (!data.empty()) CK(cudaMemcpy(c->d_mcell_data.p, data.data(), data.size() * 4, cudaMemcpyHostToDevice));
+  c->M = MeshView{c->d_md.p, c->d_mverts.p, c->d_medges.p, c->d_mfoff.p, c->d_mfn.p, c->d_mfidx.p, c->d_mcell_off.p, c->d_mcell_data.p, nm,
+                  (uint32_t)ncell};
+}
+
 // Multi-GPU: particles that left the brick move to their new owner together with their active interaction records.
 // Returns the number of occupied slots (stayers + leavers' dead slots + immigrants); *n_live = particles now owned.
 static uint32_t migrate(edb_context* c, uint32_t* n_live) {
@@ -734,6 +859,9 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   active[0] = true;
   if (poly) active[1] = active[2] = active[3] = true;
   for (int k = 0; k < 3; k++) active[4 + k] = has_drv[k];
+  if (c->mesh_dirty) build_mesh_grid(c);
+  if (c->M.nmesh)
+    for (int t = 7; t <= (poly ? 12 : 9); t++) active[t] = true;
   CntTab C{};
   for (int t = 0; t < NT; t++) {
     C.c[t] = nullptr;
@@ -743,7 +871,7 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
       C.c[t] = c->wave[t].off.p;
     }
   }
-  NbhArgs A{view(c->pa), c->cidx.p, c->cbeg.p, c->cend.p, G, c->drv.p, (int)c->h_drv.size(), rcut_inc, symetric, n, c->vert.p, c->S};
+  NbhArgs A{view(c->pa), c->cidx.p, c->cbeg.p, c->cend.p, G, c->drv.p, (int)c->h_drv.size(), rcut_inc, symetric, n, c->vert.p, c->S, c->M};
   WTab W{};
   if (!poly) LAUNCH(c, k_nbh_sphere<false>, nblk(n, 128), 128, 0, A, C, W);
   else LAUNCH(c, k_nbh_poly<false>, nblk(n, 64), 64, 0, A, C, W);
@@ -757,7 +885,7 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
     if (!active[t]) continue;
     c->wave[t].n = c->h_tot[t];
     if (c->wave[t].n >= (1ull << INC_SHIFT)) throw StateError{EDB_ERR_CAPACITY, "wave larger than 2^28 records"};
-    c->wave[t].ensure(c->wave[t].n + 1, poly);
+    c->wave[t].ensure(c->wave[t].n + 1, poly || t >= 7);
     W.w[t] = view(c->wave[t]);
   }
   if (!poly) LAUNCH(c, k_nbh_sphere<true>, nblk(n, 128), 128, 0, A, C, W);
@@ -769,7 +897,7 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
       if (active[t] && c->wave[t].n && ((had && c->prev[t].n) || c->n_imm)) {
         WView ow = view(c->prev[t]);
         if (!had) ow.n = 0;
-        LAUNCH(c, k_history, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), ow, c->new2old.p, had ? c->n_old_real : n_before, poly, t, H);
+        LAUNCH(c, k_history, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), ow, c->new2old.p, had ? c->n_old_real : n_before, poly || t >= 7, t, H);
       }
   }
   c->have_prev = true;
@@ -871,7 +999,7 @@ static const int ORDER_POLY[] = {0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 4, 5, 6};
 template <int LAW>
 static void launch_contact_waves(edb_context* c, double dt) {
   const bool poly = c->poly();
-  ContactArgs A{view(c->pa), WView{}, c->prm, c->drv.p, c->vert.p, c->S, dt, 0, c->symetric};
+  ContactArgs A{view(c->pa), WView{}, c->prm, c->drv.p, c->vert.p, c->S, dt, 0, c->symetric, c->M};
   const int* order = poly ? ORDER_POLY : ORDER_SPHERE;
   const int norder = poly ? 13 : 7;
   for (int o = 0; o < norder; o++) {
@@ -889,6 +1017,9 @@ static void launch_contact_waves(edb_context* c, double dt) {
     } else if (t <= 6) {
       if (poly) LAUNCH(c, (k_contact_driver<LAW, true>), nblk(w.n), BLK, 0, A);
       else LAUNCH(c, (k_contact_driver<LAW, false>), nblk(w.n), BLK, 0, A);
+    } else if (t <= 12) {
+      if (poly) LAUNCH(c, (k_contact_mesh<LAW, true>), nblk(w.n), BLK, 0, A);
+      else LAUNCH(c, (k_contact_mesh<LAW, false>), nblk(w.n), BLK, 0, A);
     }
     c->ctr.interaction_updates += w.n;
     c->ctr.contact_launches++;
@@ -1041,7 +1172,7 @@ extern "C" int edb_export_interactions(edb_context* c, edb_interaction* out, uin
     uint64_t o = 0;
     for (int t = 0; t < NT; t++) {
       if (!c->wave[t].n) continue;
-      LAUNCH(c, k_export, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), c->pa.id.p, t, c->poly(), t >= 4, d + o);
+      LAUNCH(c, k_export, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), c->pa.id.p, t, c->poly() || t >= 7, t >= 4, d + o);
       o += c->wave[t].n;
     }
     CK(cudaMemcpyAsync(out, d, tot * sizeof(edb_interaction), cudaMemcpyDeviceToHost, c->st));
@@ -1058,7 +1189,7 @@ extern "C" int edb_get_contact_state(edb_context* c, int32_t type, double* dn, d
   if (n) {
     c->stage.ensure(10 * n + 1);
     double* s = c->stage.p;
-    ContactArgs A{view(c->pa), view(c->wave[type]), c->prm, c->drv.p, c->vert.p, c->S, 0.0, type, c->symetric};
+    ContactArgs A{view(c->pa), view(c->wave[type]), c->prm, c->drv.p, c->vert.p, c->S, 0.0, type, c->symetric, c->M};
     if (c->poly()) LAUNCH(c, k_state<true>, nblk(n), BLK, 0, A, s, s + n, s + 4 * n, s + 7 * n);
     else LAUNCH(c, k_state<false>, nblk(n), BLK, 0, A, s, s + n, s + 4 * n, s + 7 * n);
     if (dn) CK(cudaMemcpyAsync(dn, s, n * 8, cudaMemcpyDeviceToHost, c->st));
@@ -1099,7 +1230,7 @@ extern "C" int edb_import_interactions(edb_context* c, const edb_interaction* in
     const size_t m = key.size();
     w.n = m;
     w.off.ensure(np + 2);
-    w.ensure(m + 1, poly);
+    w.ensure(m + 1, poly || t >= 7);
     std::vector<uint32_t> off(np + 1, 0);
     std::vector<uint2> ij(m), sub(m);
     std::vector<uint8_t> flg(m);
@@ -1128,7 +1259,7 @@ extern "C" int edb_import_interactions(edb_context* c, const edb_interaction* in
     CK(cudaMemcpy(w.off.p, off.data(), (np + 1) * 4, cudaMemcpyHostToDevice));
     if (m) {
       CK(cudaMemcpy(w.ij.p, ij.data(), m * sizeof(uint2), cudaMemcpyHostToDevice));
-      if (poly) CK(cudaMemcpy(w.sub.p, sub.data(), m * sizeof(uint2), cudaMemcpyHostToDevice));
+      if (poly || t >= 7) CK(cudaMemcpy(w.sub.p, sub.data(), m * sizeof(uint2), cudaMemcpyHostToDevice));
       CK(cudaMemcpy(w.flg.p, flg.data(), m, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(w.ft.p, ft.data(), m * sizeof(double4), cudaMemcpyHostToDevice));
       CK(cudaMemcpy(w.mo.p, mo.data(), m * sizeof(double4), cudaMemcpyHostToDevice));
@@ -1153,7 +1284,7 @@ extern "C" int edb_compute_driver_force_moment(edb_context* c, double* forces, d
     const uint32_t nb = nblk(w.n);
     c->stage.ensure((size_t)nb * nd * 6 + 1);
     const size_t smem = (size_t)(BLK / 32) * nd * 6 * sizeof(double);
-    LAUNCH(c, k_driver_force, nb, BLK, smem, view(w), c->drv.p, nd, c->stage.p);
+    LAUNCH(c, k_driver_force, nb, BLK, smem, view(w), t, c->drv.p, nd, c->stage.p);
     std::vector<double> part((size_t)nb * nd * 6);
     CK(cudaMemcpyAsync(part.data(), c->stage.p, part.size() * 8, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));

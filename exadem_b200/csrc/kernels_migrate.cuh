@@ -110,7 +110,7 @@ __global__ void k_mig_pack(PView P, uint32_t n, const int* __restrict__ dest, co
         MigRec r;
         r.m = midx[p]; r.type = (uint8_t)t; r.flg = fl; r.pad = 0;
         uint2 sb = make_uint2(0, 0);
-        if (has_sub && w.sub) sb = w.sub[k];
+        if (w.sub && (has_sub || t >= 7)) sb = w.sub[k];
         r.sub_i = sb.x; r.sub_j = sb.y;
         r.pid = __double_as_longlong(ft.w);
         r.ft[0] = ft.x; r.ft[1] = ft.y; r.ft[2] = ft.z;

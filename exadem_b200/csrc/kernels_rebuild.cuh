@@ -240,6 +240,7 @@ struct NbhArgs {
   uint32_t nreal;
   const double4* vert;  // polyhedra: world vertices
   ShapesView S;
+  MeshView M;
 };
 
 __device__ __forceinline__ void cell_ijk(const GridDev& G, uint32_t lin, int& i, int& j, int& k) {
@@ -277,6 +278,14 @@ __device__ __forceinline__ void for_each_neighbor(const NbhArgs& A, uint32_t a, 
       }
 }
 
+struct VA {  // world-vertex accessor of one particle
+  const double4* p;
+  __device__ __forceinline__ v3 operator[](int i) const {
+    const double4 t = ldg4(p + i);
+    return mk3(t.x, t.y, t.z);
+  }
+};
+
 // FILL=false: count candidates per type;  FILL=true: write records at the owner's CSR offset
 struct WTab {
   WView w[NT];
@@ -306,6 +315,38 @@ __global__ void __launch_bounds__(128) k_nbh_sphere(NbhArgs A, CntTab C, WTab W)
       nd[D.kind]++;
     }
   }
+  // RShape (mesh) drivers: detection_sphere_driver (sphere/nbh_sphere.hpp:25-80) over the per-cell primitive lists
+  uint32_t nm[3] = {0, 0, 0};
+  if (A.M.nmesh) {
+    const uint32_t cell = A.cidx[a];
+    for (int d = 0; d < A.ndrv; d++) {
+      const Driver D = A.drv[d];
+      if (D.kind != 3) continue;
+      const MeshDev md = A.M.md[D.shape];
+      const VA mv{A.M.verts + md.v0};
+      const uint32_t* off = A.M.cell_off + ((size_t)D.shape * A.M.ncell + cell) * 3;
+      for (int kind = 0; kind < 3; kind++) {
+        const int t = 7 + kind;
+        for (uint32_t s = off[kind]; s < off[kind + 1]; s++) {
+          const int j = A.M.cell_data[s];
+          bool ok;
+          if (kind == 0) ok = filter_vv(A.rcut_inc, pa, ra.w, mv[j], md.radius);
+          else if (kind == 1) ok = filter_ve(A.rcut_inc, pa, ra.w, mv[A.M.edges[2 * (md.e0 + j)]], mv[A.M.edges[2 * (md.e0 + j) + 1]], md.radius);
+          else ok = filter_vf(A.rcut_inc, pa, ra.w, mv, md.radius, A.M.fidx + md.fi0 + A.M.foff[md.f0 + j], A.M.fn[md.f0 + j]);
+          if (!ok) continue;
+          if (FILL) {
+            const uint32_t k = C.c[t][a] + nm[kind];
+            W.w[t].ij[k] = make_uint2(a, (uint32_t)d);
+            W.w[t].sub[k] = make_uint2(0u, (uint32_t)j);
+            W.w[t].flg[k] = 0;
+            W.w[t].ft[k] = make_double4(0, 0, 0, __longlong_as_double((long long)d));
+            W.w[t].mo[k] = make_double4(0, 0, 0, 0);
+          }
+          nm[kind]++;
+        }
+      }
+    }
+  }
   uint32_t n0 = 0;
   const uint32_t base0 = FILL ? C.c[0][a] : 0;
   for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
@@ -331,16 +372,11 @@ __global__ void __launch_bounds__(128) k_nbh_sphere(NbhArgs A, CntTab C, WTab W)
     if (C.c[4]) C.c[4][a] = nd[0];
     if (C.c[5]) C.c[5][a] = nd[1];
     if (C.c[6]) C.c[6][a] = nd[2];
+    if (C.c[7]) C.c[7][a] = nm[0];
+    if (C.c[8]) C.c[8][a] = nm[1];
+    if (C.c[9]) C.c[9][a] = nm[2];
   }
 }
-
-struct VA {  // world-vertex accessor of one particle
-  const double4* p;
-  __device__ __forceinline__ v3 operator[](int i) const {
-    const double4 t = ldg4(p + i);
-    return mk3(t.x, t.y, t.z);
-  }
-};
 
 template <bool FILL>
 __device__ __forceinline__ void emit(const CntTab& C, const WTab& W, uint32_t owner, uint32_t* cnt, int t, uint32_t i, uint32_t j,
@@ -368,7 +404,7 @@ __global__ void __launch_bounds__(64) k_nbh_poly(NbhArgs A, CntTab C, WTab W) {
   const double ha = A.P.h[a], rV = A.rcut_inc;
   const VA va{A.vert + (size_t)a * A.S.nvmax};
   const double rma = ha * sa.radius;
-  uint32_t cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+  uint32_t cnt[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   // drivers (nbh_polyhedron_driver.hpp:205-238): one record per vertex with sub_j = -1
   for (int d = 0; d < A.ndrv; d++) {
     const Driver D = A.drv[d];
@@ -377,9 +413,53 @@ __global__ void __launch_bounds__(64) k_nbh_poly(NbhArgs A, CntTab C, WTab W) {
     for (int k = 0; k < sa.nv; k++)
       if (driver_filter(D, rV + rma, va[k])) emit<FILL>(C, W, a, cnt, t, a, (uint32_t)d, (uint32_t)k, 0xffffffffu, 0, (uint64_t)d);
   }
+  const int* ea = A.S.edges + 2 * sa.e0;
+  // RShape (mesh) drivers: add_driver_interaction (nbh_polyhedron_driver.hpp:61-201), types 7..12
+  if (A.M.nmesh) {
+    const uint32_t cell = A.cidx[a];
+    for (int d = 0; d < A.ndrv; d++) {
+      const Driver D = A.drv[d];
+      if (D.kind != 3) continue;
+      const MeshDev md = A.M.md[D.shape];
+      const VA mv{A.M.verts + md.v0};
+      const uint32_t* off = A.M.cell_off + ((size_t)D.shape * A.M.ncell + cell) * 3;
+      const int* me = A.M.edges + 2 * md.e0;
+      const double rd = md.radius;
+      for (int i = 0; i < sa.nv; i++) {
+        const v3 vi = va[i];
+        for (uint32_t s = off[0]; s < off[1]; s++) {
+          const int j = A.M.cell_data[s];
+          if (filter_vv(rV, vi, rma, mv[j], rd)) emit<FILL>(C, W, a, cnt, 7, a, (uint32_t)d, (uint32_t)i, (uint32_t)j, 0, (uint64_t)d);
+        }
+        for (uint32_t s = off[1]; s < off[2]; s++) {
+          const int j = A.M.cell_data[s];
+          if (filter_ve(rV, vi, rma, mv[me[2 * j]], mv[me[2 * j + 1]], rd)) emit<FILL>(C, W, a, cnt, 8, a, (uint32_t)d, (uint32_t)i, (uint32_t)j, 0, (uint64_t)d);
+        }
+        for (uint32_t s = off[2]; s < off[3]; s++) {
+          const int j = A.M.cell_data[s];
+          if (filter_vf(rV, vi, rma, mv, rd, A.M.fidx + md.fi0 + A.M.foff[md.f0 + j], A.M.fn[md.f0 + j]))
+            emit<FILL>(C, W, a, cnt, 9, a, (uint32_t)d, (uint32_t)i, (uint32_t)j, 0, (uint64_t)d);
+        }
+      }
+      for (int i = 0; i < sa.ne; i++)
+        for (uint32_t s = off[1]; s < off[2]; s++) {
+          const int j = A.M.cell_data[s];
+          if (filter_ee(rV, va[ea[2 * i]], va[ea[2 * i + 1]], rma, mv[me[2 * j]], mv[me[2 * j + 1]], rd))
+            emit<FILL>(C, W, a, cnt, 10, a, (uint32_t)d, (uint32_t)i, (uint32_t)j, 0, (uint64_t)d);
+        }
+      for (uint32_t s = off[0]; s < off[1]; s++) {
+        const int j = A.M.cell_data[s];
+        const v3 vj = mv[j];
+        for (int i = 0; i < sa.ne; i++)
+          if (filter_ve(rV, vj, rd, va[ea[2 * i]], va[ea[2 * i + 1]], rma)) emit<FILL>(C, W, a, cnt, 11, a, (uint32_t)d, (uint32_t)i, (uint32_t)j, 0, (uint64_t)d);
+        for (int i = 0; i < sa.nf; i++)
+          if (filter_vf(rV, vj, rd, va, rma, A.S.fidx + sa.fi0 + A.S.foff[sa.f0 + i], A.S.fn[sa.f0 + i]))
+            emit<FILL>(C, W, a, cnt, 12, a, (uint32_t)d, (uint32_t)i, (uint32_t)j, 0, (uint64_t)d);
+      }
+    }
+  }
   const double4 qa4 = A.P.q[a];
   const q4 qa{qa4.x, qa4.y, qa4.z, qa4.w};
-  const int* ea = A.S.edges + 2 * sa.e0;
   for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
     const uint64_t idb = A.P.id[b];
     if (ida >= idb) return;  // nbh_polyhedron.cpp:234-236
@@ -425,7 +505,7 @@ __global__ void __launch_bounds__(64) k_nbh_poly(NbhArgs A, CntTab C, WTab W) {
     }
   });
   if (!FILL) {
-    for (int t = 0; t < 7; t++)
+    for (int t = 0; t < 13; t++)
       if (C.c[t]) C.c[t][a] = cnt[t];
   }
 }

@@ -174,6 +174,7 @@ struct ContactArgs {
   double dt;
   int type;
   int symetric;
+  MeshView M;
 };
 
 // Record state bit FLG_HOT (flg bit 3): the record was in contact at its last evaluation, i.e. its history (ft, mo) and its
@@ -354,6 +355,73 @@ __global__ void __launch_bounds__(BLK) k_contact_poly_pp(ContactArgs A) {
                      mk3(pj.x, pj.y, pj.z), mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z), H);
 }
 
+// detection of an RShape (mesh) driver record, waves 7..12: detect<7..12> (shape_detection_api.hpp:356-406) on the particle
+// (sphere centre / polyhedron world vertices) and the cached world vertices of the mesh (quirk Q13: both reference paths agree)
+template <bool POLY>
+__device__ __forceinline__ Contact detect_mesh_record(const ContactArgs& A, int t, uint32_t k, const uint2 ij, const Driver& D, const double4& pi,
+                                                      const double4& wi, double& reff) {
+  const MeshDev md = A.M.md[D.shape];
+  const VA mv{A.M.verts + md.v0};
+  const int* me = A.M.edges + 2 * md.e0;
+  const uint2 sb = A.w.sub[k];
+  const double rd = md.radius;
+  if (!POLY) {
+    const v3 ri = mk3(pi.x, pi.y, pi.z);
+    reff = pi.w;
+    if (t == 7) return detect_vv(ri, pi.w, mv[sb.y], rd);
+    if (t == 8) return detect_ve(ri, pi.w, mv[me[2 * sb.y]], mv[me[2 * sb.y + 1]], rd);
+    return detect_vf(ri, pi.w, mv, rd, A.M.fidx + md.fi0 + A.M.foff[md.f0 + sb.y], A.M.fn[md.f0 + sb.y]);
+  }
+  const ShapeDev sh = A.S.sh[type_of(wi)];
+  const double ra = A.P.h[ij.x] * sh.radius;
+  const VA vi{A.vert + (size_t)ij.x * A.S.nvmax};
+  const int* ei = A.S.edges + 2 * sh.e0;
+  reff = (ra * rd) / (ra + rd);  // contact.hpp:388
+  if (t == 7) return detect_vv(vi[sb.x], ra, mv[sb.y], rd);
+  if (t == 8) return detect_ve(vi[sb.x], ra, mv[me[2 * sb.y]], mv[me[2 * sb.y + 1]], rd);
+  if (t == 9) return detect_vf(vi[sb.x], ra, mv, rd, A.M.fidx + md.fi0 + A.M.foff[md.f0 + sb.y], A.M.fn[md.f0 + sb.y]);
+  if (t == 10) return detect_ee(vi[ei[2 * sb.x]], vi[ei[2 * sb.x + 1]], ra, mv[me[2 * sb.y]], mv[me[2 * sb.y + 1]], rd);
+  if (t == 11) return detect_ve(mv[sb.y], rd, vi[ei[2 * sb.x]], vi[ei[2 * sb.x + 1]], ra);
+  return detect_vf(mv[sb.y], rd, vi, ra, A.S.fidx + sh.fi0 + A.S.foff[sh.f0 + sb.x], A.S.fn[sh.f0 + sb.x]);
+}
+// waves 7..12: sphere::ContactLawRShapeDriverFunc (contact_sphere.hpp:306-396), polyhedron::ContactLawRShapeDriverFunc
+// (polyhedron/contact.hpp:309-432).  Types 11/12 are "j to i": the driver plays i in the law and the stored friction flips sign.
+template <int LAW, bool POLY>
+__global__ void __launch_bounds__(BLK) k_contact_mesh(ContactArgs A) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= A.w.n) return;
+  const uint2 ij = A.w.ij[k];
+  const uint8_t fl = A.w.flg[k];
+  const bool hot = fl & FLG_HOT;
+  const Driver D = A.drv[ij.y];
+  const double4 pi = ldg4(A.P.pr + ij.x), wi = ldg4(A.P.wg + ij.x);
+  double reff;
+  const Contact c = detect_mesh_record<POLY>(A, A.type, k, ij, D, pi, wi, reff);
+  const Params& cp = cp_pd(A.prm, group_of(wi), ij.y);
+  bool contact = c.hit;
+  if (LAW == LAW_COHESIVE) contact = contact || c.dn <= cp.dncut;
+  if (!contact && !hot) return;
+  Hist H;
+  H.ft = ld4(A.w.ft + k);
+  H.mo = (fl & FLG_MOM) ? ld4(A.w.mo + k) : make_double4(0, 0, 0, 0);
+  const double4 vi = ldg4(A.P.vm + ij.x);
+  const v3 ri = mk3(pi.x, pi.y, pi.z), v_i = mk3(vi.x, vi.y, vi.z), w_i = mk3(wi.x, wi.y, wi.z);
+  if (A.type <= 10 || !contact) {
+    finish_record<LAW>(A, k, fl, contact, c, cp, vi.w, reff, ri, v_i, w_i, D.center, D.vel, D.vrot, H);
+  } else {
+    v3 ft = mk3(H.ft.x, H.ft.y, H.ft.z), mom = mk3(H.mo.x, H.mo.y, H.mo.z), f = mk3(0, 0, 0);
+    contact_force<LAW>(c.dn, c.n, A.dt, cp, vi.w, reff, ft, c.cp, D.center, D.vel, f, mom, D.vrot, ri, v_i, w_i);
+    // stored: fd = f of the law (the particle receives -f, see the gather), friction negated (contact.hpp:417)
+    st4(A.w.ft + k, make_double4(-ft.x, -ft.y, -ft.z, H.ft.w));
+    st4(A.w.fd + k, make_double4(f.x, f.y, f.z, c.dn));
+    st4(A.w.cp + k, make_double4(c.cp.x, c.cp.y, c.cp.z, 0));
+    const bool live = !is_zero(mom);
+    if (live || (fl & FLG_MOM)) st4(A.w.mo + k, make_double4(mom.x, mom.y, mom.z, 0.0));
+    const uint8_t nf = (uint8_t)((fl | FLG_HOT) & ~FLG_MOM) | (live ? FLG_MOM : 0);
+    if (nf != fl) A.w.flg[k] = nf;
+  }
+}
+
 // ContactState view of a wave (classifier/contact_state.hpp:22-51): dn, cp, fn = f - ft (contact_sphere.hpp:180), ft.
 // Records that are not hot hold no stored state: dn = fn = ft = 0 and cp is what the detection returns for the current
 // positions (what the reference stores too, since it runs the detection for every record).
@@ -366,7 +434,11 @@ __global__ void k_state(ContactArgs A, double* __restrict__ dn, double* __restri
     const double4 fd = ld4(A.w.fd + k), c4 = ld4(A.w.cp + k), f4 = ld4(A.w.ft + k);
     dn[k] = fd.w;
     cp[3 * k] = c4.x; cp[3 * k + 1] = c4.y; cp[3 * k + 2] = c4.z;
-    fn[3 * k] = fd.x - f4.x; fn[3 * k + 1] = fd.y - f4.y; fn[3 * k + 2] = fd.z - f4.z;
+    if (A.type == 11 || A.type == 12) {  // fn = friction - f with the friction BEFORE its sign flip (contact.hpp:409,417)
+      fn[3 * k] = -f4.x - fd.x; fn[3 * k + 1] = -f4.y - fd.y; fn[3 * k + 2] = -f4.z - fd.z;
+    } else {
+      fn[3 * k] = fd.x - f4.x; fn[3 * k + 1] = fd.y - f4.y; fn[3 * k + 2] = fd.z - f4.z;
+    }
     ft[3 * k] = f4.x; ft[3 * k + 1] = f4.y; ft[3 * k + 2] = f4.z;
     return;
   }
@@ -381,9 +453,12 @@ __global__ void k_state(ContactArgs A, double* __restrict__ dn, double* __restri
       const ShapeDev si = A.S.sh[type_of(wi)], sj = A.S.sh[type_of(wj)];
       c = detect_poly_record(A, A.type, ij, A.w.sub[k], si, sj, A.P.h[ij.x] * si.radius, A.P.h[ij.y] * sj.radius);
     }
-  } else {
+  } else if (A.type <= 6) {
     double reff;
     c = detect_driver_record<POLY>(A, k, ij, A.drv[ij.y], ldg4(A.P.pr + ij.x), ldg4(A.P.wg + ij.x), reff);
+  } else {
+    double reff;
+    c = detect_mesh_record<POLY>(A, A.type, k, ij, A.drv[ij.y], ldg4(A.P.pr + ij.x), ldg4(A.P.wg + ij.x), reff);
   }
   dn[k] = 0.0;
   cp[3 * k] = c.cp.x; cp[3 * k + 1] = c.cp.y; cp[3 * k + 2] = c.cp.z;
@@ -460,7 +535,8 @@ __global__ void __launch_bounds__(BLK) k_gather(GatherArgs A) {
     }
     for (uint32_t k = a; k < b; k++) {
       const uint8_t fl = w.flg[k];
-      const bool owner_is_i = (t <= 3 && A.has_swap) ? !(fl & FLG_SWAP) : true;
+      // polyhedra: swapped records; mesh waves 11/12 ("j to i", contact.hpp:405-421): the particle receives -f, -mom
+      const bool owner_is_i = (t <= 3 && A.has_swap) ? !(fl & FLG_SWAP) : !(t == 11 || t == 12);
       if (fl & FLG_HOT) add_wrench(w, k, fl, owner_is_i, r, F, M);
     }
     if (t <= 3 && A.pp_partner) {
@@ -494,7 +570,7 @@ __global__ void __launch_bounds__(BLK) k_gather(GatherArgs A) {
 
 // compute_driver_force_moment.cu:34-54 — per-driver sum of -(fn+ft) and of (cp - center) x (-(fn+ft)) - moment over the driver waves.
 // Deterministic: one block per driver wave chunk writes a partial; partials are summed in order on the host side buffer.
-__global__ void __launch_bounds__(BLK) k_driver_force(WView w, const Driver* __restrict__ drv, int ndrv, double* __restrict__ partial) {
+__global__ void __launch_bounds__(BLK) k_driver_force(WView w, int type, const Driver* __restrict__ drv, int ndrv, double* __restrict__ partial) {
   // partial layout: [block][driver][6]
   extern __shared__ double sm[];
   double* acc = sm;  // ndrv*6 per warp
@@ -509,7 +585,8 @@ __global__ void __launch_bounds__(BLK) k_driver_force(WView w, const Driver* __r
       const double4 mo = w.mo[k], fd = w.fd[k], cp = w.cp[k], ft4 = w.ft[k];
       d = (int)w.ij[k].y;
       const v3 ft = mk3(ft4.x, ft4.y, ft4.z);
-      const v3 fn = mk3(fd.x, fd.y, fd.z) - ft;   // ContactState fn (contact_sphere.hpp:180)
+      // ContactState fn (contact_sphere.hpp:180; contact.hpp:409 for the "j to i" mesh waves whose stored friction is negated)
+      const v3 fn = (type == 11 || type == 12) ? (-ft) - mk3(fd.x, fd.y, fd.z) : mk3(fd.x, fd.y, fd.z) - ft;
       f = -(fn + ft);                              // compute_driver_force_moment.cu:46-47
       m = cross(mk3(cp.x, cp.y, cp.z) - drv[d].center, f) + -mk3(mo.x, mo.y, mo.z);  // :48-49
     }

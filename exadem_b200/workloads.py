@@ -28,6 +28,7 @@ class Workload:
     params_driver: dict | None = None
     drivers: list = field(default_factory=list)
     shapes_spec: list = field(default_factory=list)  # list of dicts(vertices, edges, faces, obb, radius)
+    mesh_spec: list = field(default_factory=list)    # shapes of the RShape (mesh) drivers, same dict layout
     mode: int = capi.MODE_SPHERE
     law: int = capi.LAW_NONE
     dt: float = 1e-4
@@ -60,6 +61,8 @@ class Workload:
         engine.set_contact_params(self.params, self.params_driver)
         if self.shapes_spec:
             engine.set_shapes(self.shapes())
+        if self.mesh_spec:
+            engine.set_driver_shapes([capi.make_shape(s["vertices"], s["edges"], s["faces"], s["obb"], s["radius"]) for s in self.mesh_spec])
         engine.set_drivers(self.drivers)
         engine.upload_particles(self.particles)
         return engine
@@ -214,3 +217,17 @@ def polyhedra_box(n_side=(8, 8, 8), seed=0xD3A3, shapes=("octahedron",), pitch=0
     prm = dict(kn=1e4, kt=1e4, kr=0.0, mu=0.1, damp_rate=0.999, fc=0.0, dncut=0.0, gamma=0.0)
     return Workload(name, (0.0, 0.0, 0.0), hi, cell_size, periodic, pa, prm, dict(prm, mu=0.3), drivers or [],
                     shapes_spec=spec, mode=capi.MODE_POLYHEDRON, dt=1e-4, rcut_inc=0.1)
+
+
+def box_mesh(lo, hi, mink=0.01):
+    """Closed axis-aligned box as an RShape mesh (8 v / 12 e / 6 quad faces), the topology of
+    example/polyhedra/stl_mesh/box.stl after stl_mesh_to_driver (vertex numbering is an input, quirk Q12).  Local
+    coordinates are centred on the box centre; use `center` of the driver to place it."""
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    c, hl = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    v = [[sx * hl[0], sy * hl[1], sz * hl[2]] for sz in (-1, 1) for sy in (-1, 1) for sx in (-1, 1)]
+    e = [[0, 1], [1, 3], [3, 2], [2, 0], [4, 5], [5, 7], [7, 6], [6, 4], [0, 4], [1, 5], [2, 6], [3, 7]]
+    f = [[0, 1, 3, 2], [4, 6, 7, 5], [0, 4, 5, 1], [2, 3, 7, 6], [0, 2, 6, 4], [1, 5, 7, 3]]
+    ext = hl + mink
+    spec = dict(vertices=v, edges=e, faces=f, obb=[0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, ext[0], ext[1], ext[2]], radius=mink)
+    return spec, tuple(c)

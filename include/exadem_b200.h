@@ -86,8 +86,9 @@ typedef struct edb_driver {
   double offset;       /* surface */
   double normal[3];    /* surface */
   double vel[3], vrot[3];
-  int32_t shape;       /* RSHAPE: mesh shape index (edb_set_shapes table) */
+  int32_t shape;       /* RSHAPE: mesh shape index (edb_set_driver_shapes table); center = position of the mesh */
   int32_t reserved;
+  double quat[4];      /* RSHAPE: orientation (w,x,y,z), rshape.hpp:370-384 */
 } edb_driver;
 
 /* `shape` (src/shape/include/exaDEM/shape.hpp:50-69) flattened: faces as the [n0, v.., n1, v..] stream. */
@@ -126,6 +127,9 @@ int edb_set_contact_params_multimat(edb_context*, int32_t n_groups, const edb_co
 int edb_set_law(edb_context*, int32_t law); /* operator variant: ..._hooke_none | _cohesive | _dmt */
 int edb_set_drivers(edb_context*, int32_t n, const edb_driver* drivers);      /* `drivers` slot */
 int edb_set_shapes(edb_context*, int32_t n, const edb_shape* shapes);         /* `shapes_collection` slot */
+/* shapes of the RShape (STL mesh) drivers: RShapeDriver::shp_, src/driver/include/exaDEM/rshape.hpp.  Call BEFORE edb_set_drivers.
+ * The mesh shape arrays are an input (quirk Q12: the reference's STL->shape numbering is thread-order dependent). */
+int edb_set_driver_shapes(edb_context*, int32_t n, const edb_shape* shapes);
 
 /* ---- slots: grid ------------------------------------------------------------------------------------- */
 int edb_upload_particles(edb_context*, const edb_particles* host);   /* full DEMFieldSet, any order */

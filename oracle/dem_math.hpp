@@ -336,6 +336,7 @@ struct Driver {
   v3 forces{0, 0, 0};     // accumulated -f when need_forces
   int need_forces = 0;    // motion_type.hpp:133-141
   int shape = -1;         // RSHAPE: index into the mesh-shape table
+  q4 quat{1, 0, 0, 0};    // RSHAPE: orientation
   v3 center_proj() const { return offset * normal; }  // surface.hpp:149
 };
 // cylinder.hpp:225-235, surface.hpp:320-324, ball.hpp:292-296

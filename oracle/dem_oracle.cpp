@@ -84,6 +84,8 @@ struct Sim {
   std::vector<Driver> drivers;
   std::vector<Shape> shapes;
   int nvmax = 0;
+  std::vector<Shape> mesh_shapes;               // RShapeDriver::shp_ (rshape.hpp)
+  std::vector<std::vector<v3>> mesh_verts;      // per driver: RShapeDriver::vertices_ = position + orientation * v (rshape.hpp:381-384)
 
   // particles: [0,nreal) real, [nreal,ntot) ghosts
   size_t nreal = 0, ntot = 0;
@@ -277,6 +279,23 @@ static void enumerate_sphere(Sim& s, uint32_t a, int ci, int cj, int ck, std::ve
     it.id_j = d; it.j = 0xffffffffu;
     if (driver_filter(D, s.radius[a] + s.rcut_inc, s.r[a])) out.push_back(it);
   }
+  // RShape (mesh) drivers: detection_sphere_driver (src/sphere/include/exaDEM/sphere/nbh_sphere.hpp:25-80).  The reference walks
+  // the per-cell index grid of the mesh (rshape_grid.hpp:125-149), a conservative accelerator: the set is defined by the filters.
+  for (size_t d = 0; d < s.drivers.size(); d++) {
+    const Driver& D = s.drivers[d];
+    if (D.kind != DRV_RSHAPE) continue;
+    const Shape& sd = s.mesh_shapes[D.shape];
+    const v3* mv = s.mesh_verts[d].data();
+    const double rd = sd.radius;  // minkowski(1.0)
+    it.id_j = d; it.j = 0xffffffffu; it.sub_i = 0;
+    it.type = 7;
+    for (int j = 0; j < sd.nv(); j++) if (filter_vv(s.rcut_inc, s.r[a], s.radius[a], mv[j], rd)) { it.sub_j = j; out.push_back(it); }
+    it.type = 8;
+    for (int j = 0; j < sd.ne(); j++) if (filter_ve(s.rcut_inc, s.r[a], s.radius[a], mv[sd.edges[2 * j]], mv[sd.edges[2 * j + 1]], rd)) { it.sub_j = j; out.push_back(it); }
+    it.type = 9;
+    for (int j = 0; j < sd.nf(); j++) if (filter_vf(s.rcut_inc, s.r[a], s.radius[a], mv, rd, &sd.fidx[sd.foff[j]], sd.fn[j])) { it.sub_j = j; out.push_back(it); }
+  }
+  it.sub_i = 0; it.sub_j = 0;
   it.type = 0;
   for_each_neighbor(s, ci, cj, ck, a, [&](uint32_t b, bool ghostc) {
     Inter n = it;
@@ -307,6 +326,36 @@ static void enumerate_polyhedron(Sim& s, uint32_t a, int ci, int cj, int ck, std
     it.id_j = d; it.j = 0xffffffffu; it.sub_j = (uint32_t)-1;
     for (int k = 0; k < sa.nv(); k++)
       if (driver_filter(D, rV + ha * sa.radius, va[k])) { it.sub_i = k; out.push_back(it); }
+  }
+  // RShape (mesh) drivers: add_driver_interaction (nbh_polyhedron_driver.hpp:61-201), types 7..12.  The OBB pre-culls of the
+  // reference (:103-110, :134-139, :163-169) are conservative accelerators; the set is defined by the filters.
+  for (size_t d = 0; d < s.drivers.size(); d++) {
+    const Driver& D = s.drivers[d];
+    if (D.kind != DRV_RSHAPE) continue;
+    const Shape& sd = s.mesh_shapes[D.shape];
+    const v3* mv = s.mesh_verts[d].data();
+    const double rd = sd.radius, ra = ha * sa.radius;
+    it.id_j = d; it.j = 0xffffffffu;
+    for (int i = 0; i < sa.nv(); i++) {
+      it.sub_i = i;
+      it.type = 7;
+      for (int j = 0; j < sd.nv(); j++) if (filter_vv(rV, va[i], ra, mv[j], rd)) { it.sub_j = j; out.push_back(it); }
+      it.type = 8;
+      for (int j = 0; j < sd.ne(); j++) if (filter_ve(rV, va[i], ra, mv[sd.edges[2 * j]], mv[sd.edges[2 * j + 1]], rd)) { it.sub_j = j; out.push_back(it); }
+      it.type = 9;
+      for (int j = 0; j < sd.nf(); j++) if (filter_vf(rV, va[i], ra, mv, rd, &sd.fidx[sd.foff[j]], sd.fn[j])) { it.sub_j = j; out.push_back(it); }
+    }
+    it.type = 10;
+    for (int i = 0; i < sa.ne(); i++)
+      for (int j = 0; j < sd.ne(); j++)
+        if (filter_ee(rV, va[sa.edges[2 * i]], va[sa.edges[2 * i + 1]], ra, mv[sd.edges[2 * j]], mv[sd.edges[2 * j + 1]], rd)) { it.sub_i = i; it.sub_j = j; out.push_back(it); }
+    for (int j = 0; j < sd.nv(); j++) {
+      it.sub_j = j;
+      it.type = 11;   // mesh vertex vs particle edge
+      for (int i = 0; i < sa.ne(); i++) if (filter_ve(rV, mv[j], rd, va[sa.edges[2 * i]], va[sa.edges[2 * i + 1]], ra)) { it.sub_i = i; out.push_back(it); }
+      it.type = 12;   // mesh vertex vs particle face
+      for (int i = 0; i < sa.nf(); i++) if (filter_vf(rV, mv[j], rd, va, ra, &sa.fidx[sa.foff[i]], sa.fn[i])) { it.sub_i = i; out.push_back(it); }
+    }
   }
   for_each_neighbor(s, ci, cj, ck, a, [&](uint32_t b, bool ghostc) {
     if (s.id[a] >= s.id[b]) return;  // nbh_polyhedron.cpp:234-236
@@ -435,6 +484,33 @@ static inline void contact_one(Sim& s, Inter& I, double dt, Acc& acc) {
       const double rmi = s.h[i] * s.shapes[s.type[i]].radius, rmj = s.h[j] * s.shapes[s.type[j]].radius;
       meff = (s.mass[i] * s.mass[j]) / (s.mass[i] + s.mass[j]); reff = (rmi * rmj) / (rmi + rmj);  // contact.hpp:183
     }
+  } else if (t >= 7) {
+    // RShape mesh waves: sphere::ContactLawRShapeDriverFunc (contact_sphere.hpp:306-396), polyhedron:: (contact.hpp:309-432)
+    const Driver& D = s.drivers[I.id_j];
+    const Shape& sd = s.mesh_shapes[D.shape];
+    const v3* mv = s.mesh_verts[I.id_j].data();
+    const double rd = sd.radius;
+    cp = &s.cp_pd(s.group[i], (uint32_t)I.id_j);
+    meff = s.mass[i];
+    pj = D.center; vj = D.vel; wj = D.vrot;
+    if (!poly) {
+      const double ra = s.radius[i];
+      if (t == 7) c = detect_vv(ri, ra, mv[I.sub_j], rd);
+      else if (t == 8) c = detect_ve(ri, ra, mv[sd.edges[2 * I.sub_j]], mv[sd.edges[2 * I.sub_j + 1]], rd);
+      else c = detect_vf(ri, ra, mv, rd, &sd.fidx[sd.foff[I.sub_j]], sd.fn[I.sub_j]);
+      reff = ra;
+    } else {
+      const Shape& si = s.shapes[s.type[i]];
+      const v3* vi = s.pv(i);
+      const double ra = s.h[i] * si.radius;
+      if (t == 7) c = detect_vv(vi[I.sub_i], ra, mv[I.sub_j], rd);
+      else if (t == 8) c = detect_ve(vi[I.sub_i], ra, mv[sd.edges[2 * I.sub_j]], mv[sd.edges[2 * I.sub_j + 1]], rd);
+      else if (t == 9) c = detect_vf(vi[I.sub_i], ra, mv, rd, &sd.fidx[sd.foff[I.sub_j]], sd.fn[I.sub_j]);
+      else if (t == 10) c = detect_ee(vi[si.edges[2 * I.sub_i]], vi[si.edges[2 * I.sub_i + 1]], ra, mv[sd.edges[2 * I.sub_j]], mv[sd.edges[2 * I.sub_j + 1]], rd);
+      else if (t == 11) c = detect_ve(mv[I.sub_j], rd, vi[si.edges[2 * I.sub_i]], vi[si.edges[2 * I.sub_i + 1]], ra);   // detect<11>: roles inverted
+      else c = detect_vf(mv[I.sub_j], rd, vi, ra, &si.fidx[si.foff[I.sub_i]], si.fn[I.sub_i]);                          // detect<12>
+      reff = (ra * rd) / (ra + rd);   // contact.hpp:388 compute_effective_radius
+    }
   } else {
     const Driver& D = s.drivers[I.id_j];
     cp = &s.cp_pd(s.group[i], (uint32_t)I.id_j);
@@ -447,7 +523,16 @@ static inline void contact_one(Sim& s, Inter& I, double dt, Acc& acc) {
   if (s.law == LAW_COHESIVE) contact = (contact || c.dn <= cp->dncut);
   v3 fn{0, 0, 0};
   double dn = c.dn;
-  if (contact) {
+  if (contact && (t == 11 || t == 12)) {
+    // "j to i" (contact.hpp:405-421): the driver plays i in the law, the particle receives -f; the stored friction flips sign
+    v3 f{0, 0, 0};
+    contact_force(s.law, c.dn, c.n, dt, *cp, meff, reff, I.ft, c.cp, pj, vj, f, I.mom, wj, ri, s.v[i], s.w[i]);
+    fn = I.ft - f;
+    acc.add(s.mom[i], moments(c.cp, ri, -f, -I.mom));
+    acc.add(s.f[i], -f);
+    I.ft = -I.ft;
+    if (s.drivers[I.id_j].need_forces) acc.add(s.drivers[I.id_j].forces, f);
+  } else if (contact) {
     v3 f{0, 0, 0};
     contact_force(s.law, c.dn, c.n, dt, *cp, meff, reff, I.ft, c.cp, ri, s.v[i], f, I.mom, s.w[i], pj, vj, wj);
     fn = f - I.ft;
@@ -642,8 +727,38 @@ int orc_set_drivers(orc_sim* h, int32_t n, const edb_driver* d) {
     D.offset = d[i].offset; D.normal = {d[i].normal[0], d[i].normal[1], d[i].normal[2]};
     D.vel = {d[i].vel[0], d[i].vel[1], d[i].vel[2]}; D.vrot = {d[i].vrot[0], d[i].vrot[1], d[i].vrot[2]};
     D.shape = d[i].shape;
+    D.quat = {d[i].quat[0], d[i].quat[1], d[i].quat[2], d[i].quat[3]};
     s.drivers.push_back(D);
   }
+  s.mesh_verts.assign(s.drivers.size(), {});
+  for (size_t k = 0; k < s.drivers.size(); k++) {
+    const Driver& D = s.drivers[k];
+    if (D.kind != DRV_RSHAPE) continue;
+    if (D.shape < 0 || D.shape >= (int)s.mesh_shapes.size()) { s.err = "RSHAPE driver without a mesh shape"; return EDB_ERR_INVALID; }
+    for (const v3& v : s.mesh_shapes[D.shape].v) s.mesh_verts[k].push_back(D.center + qrot(D.quat, 1.0 * v));  // shape.hpp:259-262, h = 1
+  }
+  return 0;
+}
+static void load_shapes(std::vector<Shape>& dst, int32_t n, const edb_shape* sh) {
+  dst.clear();
+  for (int i = 0; i < n; i++) {
+    Shape S;
+    for (int k = 0; k < sh[i].nv; k++) S.v.push_back({sh[i].vertices[3 * k], sh[i].vertices[3 * k + 1], sh[i].vertices[3 * k + 2]});
+    S.edges.assign(sh[i].edges, sh[i].edges + 2 * sh[i].ne);
+    int pos = 0;
+    for (int f = 0; f < sh[i].nf; f++) {
+      const int nfv = sh[i].faces[pos++];
+      S.foff.push_back((int)S.fidx.size()); S.fn.push_back(nfv);
+      for (int k = 0; k < nfv; k++) S.fidx.push_back(sh[i].faces[pos++]);
+    }
+    const double* o = sh[i].obb;
+    S.obb = Obb{{o[0], o[1], o[2]}, {o[3], o[4], o[5]}, {o[6], o[7], o[8]}, {o[9], o[10], o[11]}, {o[12], o[13], o[14]}};
+    S.radius = sh[i].radius;
+    dst.push_back(S);
+  }
+}
+int orc_set_driver_shapes(orc_sim* h, int32_t n, const edb_shape* sh) {
+  load_shapes(((Sim*)h)->mesh_shapes, n, sh);
   return 0;
 }
 int orc_set_shapes(orc_sim* h, int32_t n, const edb_shape* sh) {

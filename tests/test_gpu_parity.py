@@ -217,3 +217,68 @@ def test_bounded_drift_1000_steps(product_lib, oracle_lib):
     ek_g = 0.5 * np.sum(pg.mass[:, None] * pg.vec("v") ** 2)
     ek_c = 0.5 * np.sum(pc.mass[:, None] * pc.vec("v") ** 2)
     assert abs(ek_g - ek_c) <= 1e-6 * max(ek_c, 1e-30)
+
+
+def _boxed(wl, lo, hi, mink, **drv):
+    """Encloses a workload in a closed box RShape driver (mesh walls) and makes the domain non-periodic."""
+    spec, centre = workloads.box_mesh(lo, hi, mink)
+    wl.mesh_spec = [spec]
+    wl.drivers = list(wl.drivers) + [dict(kind=capi.DRIVER_RSHAPE, shape=0, center=centre, **drv)]
+    wl.periodic = (0, 0, 0)
+    return wl
+
+
+def test_rshape_mesh_spheres(product_lib, oracle_lib):
+    """Waves 7,8,9: spheres against an STL-like box mesh (vertex / edge / face of the mesh), config 4 of BASELINE.json."""
+    wl = workloads.spheres_box((8, 8, 6), jitter=0.03, omega_sigma=0.3, polydisperse=0.1, cell_size=2.0)
+    wl.lo, wl.hi = (-1.0, -1.0, -1.0), (9.0, 9.0, 7.0)
+    c45 = np.sqrt(0.5)
+    _boxed(wl, (0.03, 0.04, 0.05), (7.96, 7.97, 5.98), 0.02, vel=(0.05, 0.0, 0.0), vrot=(0.0, 0.0, 0.1))
+    # a second, rotated mesh: exercises the orientation path (rshape.hpp:381-384)
+    spec2, _ = workloads.box_mesh((-1.0, -1.0, -1.0), (1.0, 1.0, 1.0), 0.05)
+    wl.mesh_spec.append(spec2)
+    wl.drivers.append(dict(kind=capi.DRIVER_RSHAPE, shape=1, center=(4.0, 4.0, 3.0), quat=(c45, 0.0, c45 * 0.6, c45 * 0.8)))
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    cg, _ = gpu.interaction_counts()
+    cc, _ = cpu.interaction_counts()
+    assert np.array_equal(cg, cc) and all(cg[t] > 0 for t in (7, 8, 9)), cg
+    check(gpu, cpu)
+    nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 12, 5) for e in (gpu, cpu)]
+    assert nb[0] == nb[1]
+    check(gpu, cpu)
+    _, ag = gpu.interaction_counts()
+    assert ag[9] > 0
+    for t in (7, 8, 9):
+        sg, sc = gpu.get_contact_state(t), cpu.get_contact_state(t)
+        for a, b, name in zip(sg, sc, ("dn", "cp", "fn", "ft")):
+            field_close(a, b, RTOL, f"contact state {name} wave {t}")
+    fg, mg = gpu.compute_driver_force_moment(2)
+    fc, mc = cpu.compute_driver_force_moment(2)
+    field_close(fg, fc, 1e-9, "mesh driver forces")
+    field_close(mg, mc, 1e-9, "mesh driver moments")
+
+
+def test_rshape_mesh_polyhedra(product_lib, oracle_lib):
+    """Waves 7..12: polyhedra against a box mesh, including the 'j to i' waves 11/12 whose stored friction flips sign."""
+    wl = workloads.polyhedra_box((5, 5, 5), shapes=("octahedron", "cube"), pitch=0.8, cell_size=2.0)
+    wl.lo, wl.hi = (-2.0, -2.0, -2.0), (6.0, 6.0, 6.0)
+    _boxed(wl, (0.1, 0.12, 0.11), (3.9, 3.88, 3.91), 0.03, vrot=(0.0, 0.2, 0.0))
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    cg, _ = gpu.interaction_counts()
+    cc, _ = cpu.interaction_counts()
+    assert np.array_equal(cg, cc) and all(cg[t] > 0 for t in (7, 8, 9, 10, 11, 12)), cg
+    check(gpu, cpu)
+    nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 12, 5) for e in (gpu, cpu)]
+    assert nb[0] == nb[1]
+    check(gpu, cpu)
+    _, ag = gpu.interaction_counts()
+    assert ag[7:13].sum() > 0
+    for t in range(7, 13):
+        sg, sc = gpu.get_contact_state(t), cpu.get_contact_state(t)
+        for a, b, name in zip(sg, sc, ("dn", "cp", "fn", "ft")):
+            field_close(a, b, RTOL, f"contact state {name} wave {t}")
+    fg, mg = gpu.compute_driver_force_moment(1)
+    fc, mc = cpu.compute_driver_force_moment(1)
+    field_close(fg, fc, 1e-9, "mesh driver forces")
