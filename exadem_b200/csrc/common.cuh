@@ -106,6 +106,10 @@ struct Wave {
   void ensure(size_t nn, bool need_sub) {
     ij.ensure(nn); if (need_sub) sub.ensure(nn); flg.ensure(nn); ft.ensure(nn); mo.ensure(nn); fd.ensure(nn); cp.ensure(nn);
   }
+  void ensure_keep(size_t nn, bool need_sub, cudaStream_t s) {  // grows and preserves the records (twins are appended)
+    ij.ensure(nn, true, s); if (need_sub) sub.ensure(nn, true, s); flg.ensure(nn, true, s); ft.ensure(nn, true, s); mo.ensure(nn, true, s);
+    fd.ensure(nn, true, s); cp.ensure(nn, true, s);
+  }
   void release() { ij.release(); sub.release(); flg.release(); ft.release(); mo.release(); fd.release(); cp.release(); off.release(); n = 0; }
 };
 struct WView {

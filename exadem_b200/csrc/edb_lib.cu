@@ -10,6 +10,7 @@
 #include "kernels_rebuild.cuh"
 #include "kernels_step.cuh"
 #include "kernels_migrate.cuh"
+#include "kernels_twin.cuh"
 #include "comm.cuh"
 
 using namespace edb;
@@ -95,6 +96,10 @@ struct edb_context {
   DevBuf<MigRec> mig_sh, mig_rh, imm_tab;
   uint32_t n_imm = 0;
   uint64_t migrated_out = 0, migrated_in = 0;
+  // update_interaction_ghost (PartnerGhost twins)
+  DevBuf<uint32_t> tw_cnt, tw_flag, tw_pos, tw_own, tw_par, tw_tpos;
+  DevBuf<TwinMsg> tw_s, tw_r;
+  uint64_t twins = 0;
 
   bool poly() const { return cfg.mode == EDB_MODE_POLYHEDRON; }
 };
@@ -291,6 +296,8 @@ extern "C" int edb_destroy(edb_context* c) {
   c->d_mcell_data.release(); c->d_mcell_off.release();
   c->mig_dest.release(); c->mig_midx.release(); c->mig_cnt.release(); c->mig_off.release(); c->imm_cnt.release(); c->imm_off.release();
   c->mig_sp.release(); c->mig_rp.release(); c->mig_sh.release(); c->mig_rh.release(); c->imm_tab.release();
+  c->tw_cnt.release(); c->tw_flag.release(); c->tw_pos.release(); c->tw_own.release(); c->tw_par.release(); c->tw_tpos.release();
+  c->tw_s.release(); c->tw_r.release();
   for (auto& e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto& e : c->user_ev) if (e) cudaEventDestroy(e);
@@ -756,6 +763,117 @@ static uint32_t migrate(edb_context* c, uint32_t* n_live) {
   return n_all;
 }
 
+// update_interaction_ghost (src/interaction/update_interaction_ghost.cpp:58-285): ship every OwnerGhost record to the brick
+// where its partner is real and append it there as a PartnerGhost record (see kernels_twin.cuh).  Runs after the history
+// carry-over so the payload travels with the record.  No OwnerGhost records exist for spheres with symetric:true.
+static void update_interaction_ghost(edb_context* c) {
+  const bool poly = c->poly();
+  if (!poly && c->symetric) return;
+  const int tmax = poly ? 3 : 0;
+  const int R = c->cfg.nranks, me = c->cfg.rank;
+  const bool multi = R > 1;
+  const uint32_t n = c->nreal, nloc = c->comm.n_local_ghost;
+  // destinations: 0 = periodic images of the own brick, then the peers in rank order
+  TwinDest D{};
+  std::vector<Peer*> dpeer;
+  D.n = 1; D.lo[0] = n; D.hi[0] = n + nloc;
+  dpeer.push_back(nullptr);
+  if (multi)
+    for (auto& kv : c->comm.peers) {
+      Peer& p = kv.second;
+      if (!p.n_recv) continue;
+      if (D.n >= TWIN_MAXD) throw StateError{EDB_ERR_CAPACITY, "more than 27 neighbouring ranks"};
+      D.lo[D.n] = n + nloc + p.recv_base; D.hi[D.n] = D.lo[D.n] + p.n_recv;
+      dpeer.push_back(&p);
+      D.n++;
+    }
+  const int nd = D.n;
+  c->tw_cnt.ensure((size_t)(tmax + 1) * TWIN_MAXD);
+  CK(cudaMemsetAsync(c->tw_cnt.p, 0, (size_t)(tmax + 1) * TWIN_MAXD * 4, c->st));
+  uint64_t nmax = 0;
+  for (int t = 0; t <= tmax; t++) {
+    nmax = std::max<uint64_t>(nmax, c->wave[t].n);
+    if (c->wave[t].n) LAUNCH(c, k_twin_count, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), D, c->tw_cnt.p + (size_t)t * TWIN_MAXD);
+  }
+  std::vector<uint32_t> cnt((size_t)(tmax + 1) * TWIN_MAXD);
+  CK(cudaMemcpyAsync(cnt.data(), c->tw_cnt.p, cnt.size() * 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  // send layout: per destination, ordered by wave then record index
+  std::vector<uint32_t> doff(nd + 1, 0);
+  for (int d = 0; d < nd; d++) {
+    uint32_t s = 0;
+    for (int t = 0; t <= tmax; t++) s += cnt[(size_t)t * TWIN_MAXD + d];
+    doff[d + 1] = doff[d] + s;
+  }
+  const uint32_t n_out = doff[nd];
+  c->tw_s.ensure(n_out + 1);
+  c->tw_flag.ensure(nmax + 2); c->tw_pos.ensure(nmax + 2);
+  for (int d = 0; d < nd; d++) {
+    uint32_t base = doff[d];
+    for (int t = 0; t <= tmax; t++) {
+      const uint32_t m = cnt[(size_t)t * TWIN_MAXD + d];
+      if (!m) continue;
+      Wave& w = c->wave[t];
+      LAUNCH(c, k_twin_flag, nblk(w.n), BLK, 0, view(w), D.lo[d], D.hi[d], c->tw_flag.p);
+      scan_u32(c, c->tw_flag.p, c->tw_pos.p, (uint32_t)w.n);
+      LAUNCH(c, k_twin_pack, nblk(w.n), BLK, 0, view(w), t, poly, D.lo[d], D.hi[d], c->tw_pos.p, c->pa.id.p, d == 0 ? c->g_src.p : nullptr, n,
+             c->tw_s.p + base);
+      base += m;
+    }
+  }
+  // receive layout: own-brick messages first, then one range per source rank
+  std::vector<uint32_t> scnt(R, 0), soff(R, 0), rcnt(R, 0), roff(R + 1, 0);
+  uint32_t n_in = doff[1];
+  if (multi) {
+    for (int d = 1; d < nd; d++) { scnt[dpeer[d]->rank] = doff[d + 1] - doff[d]; soff[dpeer[d]->rank] = doff[d]; }
+    std::vector<uint32_t> all((size_t)R * R);
+    c->comm.allgather_u32(scnt.data(), R, all.data(), c->st);
+    for (int r = 0; r < R; r++) {
+      rcnt[r] = all[(size_t)r * R + me];
+      roff[r] = n_in;
+      n_in += rcnt[r];
+    }
+  }
+  c->tw_r.ensure(n_in + 1);
+  if (doff[1]) CK(cudaMemcpyAsync(c->tw_r.p, c->tw_s.p, (size_t)doff[1] * sizeof(TwinMsg), cudaMemcpyDeviceToDevice, c->st));
+  if (multi) c->comm.alltoallv_bytes(c->tw_s.p, soff.data(), scnt.data(), c->tw_r.p, roff.data(), rcnt.data(), sizeof(TwinMsg), c->st);
+  if (!n_in) return;
+  // resolve the slots on this side
+  c->tw_own.ensure(n_in + 1); c->tw_par.ensure(n_in + 1);
+  if (doff[1])
+    LAUNCH(c, k_twin_resolve, nblk(doff[1]), BLK, 0, c->tw_r.p, doff[1], nullptr, 0u, c->cidx.p, c->cbeg.p, c->cend.p, c->G, c->pa.id.p, n,
+           c->tw_own.p, c->tw_par.p);
+  if (multi)
+    for (auto& kv : c->comm.peers) {
+      Peer& p = kv.second;
+      const uint32_t m = rcnt[p.rank];
+      if (!m) continue;
+      LAUNCH(c, k_twin_resolve, nblk(m), BLK, 0, c->tw_r.p + roff[p.rank], m, p.d_smap.p, p.n_send, c->cidx.p, c->cbeg.p, c->cend.p, c->G,
+             c->pa.id.p, n, c->tw_own.p + roff[p.rank], c->tw_par.p + roff[p.rank]);
+    }
+  // per-type order-preserving append
+  c->tw_flag.ensure(n_in + 2);
+  c->tw_tpos.ensure((size_t)(tmax + 1) * (n_in + 2));
+  for (int t = 0; t <= tmax; t++) {
+    uint32_t* pos = c->tw_tpos.p + (size_t)t * (n_in + 2);
+    LAUNCH(c, k_twin_tflag, nblk(n_in), BLK, 0, c->tw_r.p, c->tw_own.p, n_in, t, c->tw_flag.p);
+    scan_u32(c, c->tw_flag.p, pos, n_in);
+    CK(cudaMemcpyAsync(c->h_tot + t, pos + n_in, 4, cudaMemcpyDeviceToHost, c->st));
+  }
+  CK(cudaStreamSynchronize(c->st));
+  for (int t = 0; t <= tmax; t++) {
+    const uint32_t m = c->h_tot[t];
+    if (!m) continue;
+    Wave& w = c->wave[t];
+    if (w.n + m >= (1ull << INC_SHIFT)) throw StateError{EDB_ERR_CAPACITY, "wave larger than 2^28 records"};
+    w.ensure_keep(w.n + m + 1, poly, c->st);
+    LAUNCH(c, k_twin_append, nblk(n_in), BLK, 0, c->tw_r.p, c->tw_own.p, c->tw_par.p, n_in, t, c->tw_tpos.p + (size_t)t * (n_in + 2), view(w),
+           (uint32_t)w.n, poly, c->pa.id.p);
+    w.n += m;
+    c->twins += m;
+  }
+}
+
 static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   ScopedTimer tm(c, B_REBUILD);
   const GridDev& G = c->G;
@@ -902,6 +1020,8 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   }
   c->have_prev = true;
   c->n_old_real = n;
+  // 5b. OwnerGhost records -> PartnerGhost twins where the partner is real
+  update_interaction_ghost(c);
   // 6. partner incidence lists
   const bool partner = poly || symetric;
   c->have_inc = false;

@@ -61,6 +61,7 @@ struct Inter {
   uint16_t type = 0;
   uint8_t swap = 0, ghost = 0;
   uint8_t foreign = 0;        // virtual bricks: the partner is a REAL slot that another rank would own (force on it discarded)
+  uint8_t drop_owner = 0;     // PartnerGhost twin (update_interaction_ghost.cpp): the owner is a ghost copy, only the partner's share counts
   v3 ft{0, 0, 0}, mom{0, 0, 0};
   // contact state (classifier/contact_state.hpp)
   double dn = 0;
@@ -436,6 +437,36 @@ static void rebuild(Sim& s, double rcut_inc, int symetric) {
     auto h = hist.find(key_of(I));
     if (h != hist.end()) { I.ft = h->second.first; I.mom = h->second.second; }
   }
+  // update_interaction_ghost (src/interaction/update_interaction_ghost.cpp:58-285): every OwnerGhost record is shipped to the
+  // sub-domain (MPI rank, or periodic image) where its partner is a real particle; there the owner is re-located in the ghost
+  // cell (:206-231), the partner by id among the neighbouring NON-ghost cells (:242-266), and the record is stored, payload
+  // included, as PartnerGhost.  It is then evaluated like any other record (classify_interactions walks traversal_all), so the
+  // partner receives its share of the wrench from its own rank's copy.
+  {
+    const size_t n0 = s.inter.size();
+    std::multimap<uint32_t, uint32_t> images;   // real slot -> its ghost copies
+    for (size_t q = 0; q < s.gsrc.size(); q++) images.emplace(s.gsrc[q], (uint32_t)q);
+    for (size_t k = 0; k < n0; k++) {
+      if (s.inter[k].ghost != 1) continue;
+      Inter T = s.inter[k];
+      const uint32_t a = T.swap ? T.j : T.i, b = T.swap ? T.i : T.j;   // owner, partner
+      uint32_t g = a, bp = b;
+      if (b >= s.nreal) {   // periodic image: the twin lives where the partner is real, its owner is the opposite image of a
+        bp = s.gsrc[b - s.nreal];
+        const v3 sh = s.gshift[b - s.nreal];
+        bool found = false;
+        auto rng = images.equal_range(a);
+        for (auto it = rng.first; it != rng.second && !found; ++it) {
+          const uint32_t q = it->second;
+          if (s.gshift[q].x == -sh.x && s.gshift[q].y == -sh.y && s.gshift[q].z == -sh.z) { g = (uint32_t)(s.nreal + q); found = true; }
+        }
+        if (!found) continue;   // "can append cause not all particles are copied in ghost cells" (:229-231)
+      }
+      if (T.swap) { T.j = g; T.i = bp; } else { T.i = g; T.j = bp; }
+      T.ghost = 2; T.drop_owner = 1; T.foreign = 0;
+      s.inter.push_back(T);
+    }
+  }
   classify(s);
   s.rebuilds++;
 }
@@ -537,12 +568,12 @@ static inline void contact_one(Sim& s, Inter& I, double dt, Acc& acc) {
     contact_force(s.law, c.dn, c.n, dt, *cp, meff, reff, I.ft, c.cp, ri, s.v[i], f, I.mom, s.w[i], pj, vj, wj);
     fn = f - I.ft;
     // virtual bricks: the PARTNER (j, or i for swapped polyhedron records) is another rank's particle: its share is dropped
-    if (!(I.foreign && I.swap)) {
+    if (!(I.foreign && I.swap) && !(I.drop_owner && !I.swap)) {
       acc.add(s.mom[i], moments(c.cp, ri, f, I.mom));
       acc.add(s.f[i], f);
     }
     if (t <= 3) {
-      if ((poly || s.symetric) && !(I.foreign && !I.swap)) {
+      if ((poly || s.symetric) && !(I.foreign && !I.swap) && !(I.drop_owner && I.swap)) {
         const uint32_t j = I.j;
         acc.add(s.mom[j], moments(c.cp, pj, -f, -I.mom));
         acc.add(s.f[j], -f);

@@ -117,3 +117,43 @@ def test_polyhedra_candidates_cover_all_contacts(oracle_lib):
     c1, a1 = e.interaction_counts()
     assert np.array_equal(c0, c1) and a1[:4].sum() > 0
     assert c0[1] > c0[0]  # octahedra: more vertex-edge than vertex-vertex candidates
+
+
+def test_update_interaction_ghost_twins(oracle_lib):
+    """update_interaction_ghost.cpp:58-285: every OwnerGhost record of a polyhedron pair that straddles the periodic boundary
+    has one PartnerGhost twin (same ids, subs, swap, payload) on the side where the partner is real, so that the pair force
+    is applied to both particles: total force and linear momentum are conserved in a periodic box."""
+    wl = workloads.polyhedra_box((6, 6, 6), shapes=("octahedron", "cube"), pitch=0.78)
+    wl.periodic = (1, 1, 1)
+    wl.drivers = []
+    e = mk(wl, oracle_lib)
+    e.update_particle_neighbors(wl.rcut_inc, True)
+    e.run_verlet(wl.dt, (0, 0, 0), wl.rcut_inc, True, 6, 3)
+    rec = e.export_interactions()
+    og, pg = rec[rec["ghost"] == 1], rec[rec["ghost"] == 2]
+    assert len(og) > 50 and len(og) == len(pg)
+    key = lambda r: sorted(zip(r["type"].tolist(), r["id_i"].tolist(), r["id_j"].tolist(), r["sub_i"].tolist(), r["sub_j"].tolist(), r["swap"].tolist()))
+    assert key(og) == key(pg)
+    e.ghost_update_rq()   # the epilog changed v and vrot since the last refresh
+    e.compute_vertices()
+    e.reset_force_moment()
+    e.contact_polyhedron(wl.dt)
+    pa = e.download_particles()
+    f = pa.vec("f")
+    assert np.abs(f).sum() > 0
+    assert np.max(np.abs(f.sum(axis=0))) < 1e-11 * np.abs(f).sum()
+    # the twin is not a history source, and a rebuild re-ships the payload with the record
+    e.update_particle_neighbors(wl.rcut_inc, True)
+    rec2 = e.export_interactions()
+    og2, pg2 = sort_interactions(rec2[rec2["ghost"] == 1]), sort_interactions(rec2[rec2["ghost"] == 2])
+    assert np.array_equal(og2["friction"], pg2["friction"]) and np.abs(og2["friction"]).sum() > 0
+
+
+def test_asymmetric_spheres_get_twins_without_force(oracle_lib):
+    """nbh_sphere.cu:266-294 (symetric:false): boundary pairs are OwnerGhost and get a PartnerGhost twin record, but the
+    non-symmetric kernel applies the force to particle i only (contact_sphere.hpp:190-196), i.e. to the ghost copy: dropped."""
+    wl = workloads.spheres_box((6, 6, 6), jitter=0.03)
+    e = mk(wl, oracle_lib)
+    e.update_particle_neighbors(wl.rcut_inc, False)
+    rec = e.export_interactions()
+    assert (rec["ghost"] == 1).sum() > 0 and (rec["ghost"] == 1).sum() == (rec["ghost"] == 2).sum()
