@@ -20,6 +20,11 @@ static_assert(sizeof(edb_config) == 152 && sizeof(edb_interaction) == 104 && siz
                   sizeof(edb_particles) == 8 + 31 * 8,
               "C ABI struct layout changed: update include/exadem_b200.h users and exadem_b200/capi.py");
 
+// wave order of the contact operators (classifier_for_all.hpp:116-156 as called by contact_force_sphere.cu.in:132-188 and
+// contact_force_polyhedron.cu.in:148-245)
+static const int ORDER_SPHERE[] = {0, 4, 5, 6, 7, 8, 9};
+static const int ORDER_POLY[] = {0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 4, 5, 6};
+
 enum Bucket { B_CONTACT = 0, B_GATHER, B_PROLOG, B_EPILOG, B_REBUILD, B_GHOST, B_CONTACT_PP, B_N };
 
 struct edb_context {
@@ -47,6 +52,9 @@ struct edb_context {
   bool have_prev = false;
   DevBuf<uint32_t> inc_cnt, inc_off, inc;
   bool have_inc = false;
+  DevBuf<uint4> need;               // work list of the two-pass contact kernels (kernels_step.cuh)
+  uint32_t* d_need_count = nullptr;
+  int n_sm = 148;
   double rcut_inc = 0;
   int symetric = 1;
   // parameters
@@ -253,6 +261,8 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CK(cudaMallocHost(&c->h_flag, sizeof(unsigned long long) * 4));
     CK(cudaMalloc(&c->d_flag, sizeof(unsigned long long) * 4));
+    CK(cudaMalloc(&c->d_need_count, 16));
+    { int dev = 0, v = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) c->n_sm = v; }
     CK(cudaMallocHost(&c->h_tot, sizeof(uint32_t) * (NT + 8)));
     for (int d = 0; d < 3; d++)
       if (c->cfg.periodic[d] && c->cfg.pgrid[d] <= 1) {
@@ -303,6 +313,7 @@ extern "C" int edb_destroy(edb_context* c) {
   for (auto& e : c->user_ev) if (e) cudaEventDestroy(e);
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->d_flag) cudaFree(c->d_flag);
+  if (c->d_need_count) cudaFree(c->d_need_count);
   if (c->h_tot) cudaFreeHost(c->h_tot);
   cudaStreamDestroy(c->st);
   delete c;
@@ -1022,24 +1033,29 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   c->n_old_real = n;
   // 5b. OwnerGhost records -> PartnerGhost twins where the partner is real
   update_interaction_ghost(c);
-  // 6. partner incidence lists
-  const bool partner = poly || symetric;
-  c->have_inc = false;
-  if (partner) {
+  // 6. incidence lists (owner + partner entries, canonical order) for the deterministic gather
+  {
+    const bool partner = poly || symetric;
+    c->have_inc = false;
     c->inc_cnt.ensure(n + 2); c->inc_off.ensure(n + 2);
-    CK(cudaMemsetAsync(c->inc_cnt.p, 0, (n + 1) * 4, c->st));
-    const int tmax = poly ? 3 : 0;
+    OrderTab O{};
+    const int* order = poly ? ORDER_POLY : ORDER_SPHERE;
+    O.norder = poly ? 13 : 7;
+    for (int o = 0; o < O.norder; o++) O.order[o] = order[o];
+    WTab WT{};
     uint64_t tot = 0;
-    for (int t = 0; t <= tmax; t++) {
-      tot += c->wave[t].n;
+    for (int t = 0; t < NT; t++) { WT.w[t] = view(c->wave[t]); tot += c->wave[t].n; }
+    const int tmax = partner ? (poly ? 3 : 0) : -1;
+    if (partner) for (int t = 0; t <= tmax; t++) tot += c->wave[t].n;
+    LAUNCH(c, k_inc_owner<false>, nblk(n), BLK, 0, WT, O, n, c->inc_cnt.p, nullptr, nullptr);
+    for (int t = 0; t <= tmax; t++)
       if (c->wave[t].n) LAUNCH(c, k_incidence<false>, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), t, n, c->inc_cnt.p, nullptr, nullptr);
-    }
     scan_u32(c, c->inc_cnt.p, c->inc_off.p, n);
     c->inc.ensure(tot + 1);
-    CK(cudaMemsetAsync(c->inc_cnt.p, 0, (n + 1) * 4, c->st));
+    LAUNCH(c, k_inc_owner<true>, nblk(n), BLK, 0, WT, O, n, c->inc_cnt.p, c->inc_off.p, c->inc.p);
     for (int t = 0; t <= tmax; t++)
       if (c->wave[t].n) LAUNCH(c, k_incidence<true>, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), t, n, c->inc_cnt.p, c->inc_off.p, c->inc.p);
-    LAUNCH(c, k_incidence_sort, nblk(n), BLK, 0, c->inc_off.p, c->inc.p, n);
+    if (partner) LAUNCH(c, k_incidence_sort, nblk(n), BLK, 0, c->inc_off.p, c->inc.p, n);
     c->have_inc = true;
   }
   c->ctr.rebuilds++;
@@ -1113,8 +1129,6 @@ extern "C" int edb_freeze_particles(edb_context* c) {
   API_END(c)
 }
 
-static const int ORDER_SPHERE[] = {0, 4, 5, 6, 7, 8, 9};
-static const int ORDER_POLY[] = {0, 1, 2, 3, 7, 8, 9, 10, 11, 12, 4, 5, 6};
 
 template <int LAW>
 static void launch_contact_waves(edb_context* c, double dt) {
@@ -1131,7 +1145,13 @@ static void launch_contact_waves(edb_context* c, double dt) {
     if (t <= 3) {
       ScopedTimer tpp(c, B_CONTACT_PP);
       if (poly) LAUNCH(c, k_contact_poly_pp<LAW>, nblk(w.n), BLK, 0, A);
-      else LAUNCH(c, k_contact_sphere_pp<LAW>, nblk(w.n), BLK, 0, A);
+      else {
+        c->need.ensure(w.n + 1);
+        const NeedList L{c->need.p, c->d_need_count};
+        CK(cudaMemsetAsync(c->d_need_count, 0, 4, c->st));
+        LAUNCH(c, k_detect_sphere_pp<LAW>, nblk(w.n, BLK * DPT), BLK, 0, A, L);
+        LAUNCH(c, k_law_sphere_pp<LAW>, (uint32_t)std::min<uint64_t>(nblk(w.n), (uint64_t)c->n_sm * 2), BLK, 0, A, L);
+      }
       c->ctr.contact_pp_launches++;
       c->ctr.contact_pp_records += w.n;
     } else if (t <= 6) {
@@ -1167,9 +1187,10 @@ static void gather(edb_context* c, const double* g, double dt) {
   const int* order = poly ? ORDER_POLY : ORDER_SPHERE;
   A.norder = poly ? 13 : 7;
   for (int o = 0; o < A.norder; o++) A.order[o] = order[o];
-  A.pp_partner = (poly || c->symetric) && c->have_inc ? 1 : 0;
-  A.inc_off = A.pp_partner ? c->inc_off.p : nullptr;
-  A.inc = A.pp_partner ? c->inc.p : nullptr;
+  if (!c->have_inc) throw StateError{EDB_ERR_STATE, "contact operator before update_particle_neighbors"};
+  A.inc_off = c->inc_off.p;
+  A.inc = c->inc.p;
+  A.npp = poly ? 4 : 1;
   A.nreal = c->nreal;
   A.has_swap = poly ? 1 : 0;
   if (g) { A.g[0] = g[0]; A.g[1] = g[1]; A.g[2] = g[2]; }

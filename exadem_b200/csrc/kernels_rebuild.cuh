@@ -578,14 +578,39 @@ __global__ void k_history(WView nw, WView ow, const uint32_t* __restrict__ new2o
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// partner incidence lists (particle-particle waves): for every real particle, the records in which it is the
-// PARTNER, as codes (type << 28 | k), sorted ascending so that the gather reproduces the wave-by-wave serial order.
+// incidence lists: for every real particle, ALL records it takes part in — as owner (any wave) or as partner (particle-
+// particle waves) — as codes (position of the wave in the operator's wave order << 28 | record index), sorted ascending, which
+// is the order in which the reference's serial wave-by-wave loop would add their wrenches to the particle.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr uint32_t INC_SHIFT = 28;
 constexpr uint32_t INC_MASK = (1u << INC_SHIFT) - 1;
+struct OrderTab {
+  int order[NT];
+  int norder;
+};
 
+// owner entries.  FILL=false: cnt[p] = number of owned records;  FILL=true: writes them at the head of the particle's list and
+// leaves cnt[p] = that number (the cursor at which k_incidence<true> appends the partner entries).
 template <bool FILL>
-__global__ void k_incidence(WView w, int type, uint32_t nreal, uint32_t* __restrict__ cnt_or_fill,
+__global__ void k_inc_owner(WTab W, OrderTab O, uint32_t nreal, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ inc_off,
+                            uint32_t* __restrict__ inc) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nreal) return;
+  uint32_t s = 0;
+  const uint32_t base = FILL ? inc_off[p] : 0;
+  for (int o = 0; o < O.norder; o++) {
+    const WView& w = W.w[O.order[o]];
+    if (w.n == 0) continue;
+    const uint32_t a = w.off[p], b = w.off[p + 1];
+    if (FILL)
+      for (uint32_t k = a; k < b; k++) inc[base + s + (k - a)] = ((uint32_t)o << INC_SHIFT) | k;
+    s += b - a;
+  }
+  cnt[p] = s;
+}
+// partner entries of the particle-particle wave at order position `o`
+template <bool FILL>
+__global__ void k_incidence(WView w, int o, uint32_t nreal, uint32_t* __restrict__ cnt_or_fill,
                             const uint32_t* __restrict__ inc_off, uint32_t* __restrict__ inc) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= w.n) return;
@@ -593,7 +618,7 @@ __global__ void k_incidence(WView w, int type, uint32_t nreal, uint32_t* __restr
   const uint32_t partner = (w.flg[k] & 1) ? ij.x : ij.y;
   if (partner >= nreal) return;  // forces on ghost copies are discarded (quirk Q6)
   const uint32_t s = atomicAdd(&cnt_or_fill[partner], 1u);
-  if (FILL) inc[inc_off[partner] + s] = ((uint32_t)type << INC_SHIFT) | k;
+  if (FILL) inc[inc_off[partner] + s] = ((uint32_t)o << INC_SHIFT) | k;
 }
 __global__ void k_incidence_sort(const uint32_t* __restrict__ inc_off, uint32_t* __restrict__ inc, uint32_t nreal) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -214,61 +214,117 @@ __device__ __forceinline__ void finish_record(const ContactArgs& A, uint32_t k, 
   if (nf != fl) A.w.flg[k] = nf;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// wave 0 of the sphere operator: sphere::ContactLawFunc (contact_sphere.hpp:121-203), as two launches.
+//
+// k_detect_sphere_pp (one thread per record, ~32 registers, full occupancy): reads ij + flg (9 B, coalesced).  A HOT record goes
+// straight to the work list; a cold one gathers the two position sectors and is listed only if the spheres touch (or are inside
+// the cohesive range).  A cold record that stays cold costs 9 B + two L1/L2-resident gathers and nothing else.  The list entry
+// carries (k, i, j, flg) so the second launch needs ONE dependent round trip (entry -> everything) instead of four.
+// Warp-aggregated append: one atomic per warp, a warp's entries are contiguous (512 B) and keep their record order.
+//
+// k_law_sphere_pp (persistent, one list entry per thread and iteration): all eight 32-byte operands of a record (r, v, w of both
+// particles, friction, moment) are issued back to back, then detection + Hooke law on dense warps, then the history / wrench
+// stores.  The order of the list does not influence any result: records are independent and the force sum is done by k_gather.
+struct NeedList {
+  uint4* ent;
+  uint32_t* count;
+};
 
-// wave 0 of the sphere operator: sphere::ContactLawFunc (contact_sphere.hpp:121-203)
-// Two phases per block of BLK records.  Phase A (all threads): detection only (ij, flg, two position gathers); records that
-// need the force law (contact) or a history reset (hot, no contact) are compacted, order-preserving, into shared memory and
-// their remaining operands are prefetched into L2.  Phase B (the first `tot` threads): dense evaluation of the Hooke law — no
-// divergence between contacting and non-contacting lanes, which was 58 % of the lanes of every warp in the drum.
+constexpr int DPT = 4;  // records per thread of the detection pass
 template <int LAW>
-__global__ void __launch_bounds__(BLK, 3) k_contact_sphere_pp(ContactArgs A) {
-  __shared__ uint32_t s_list[BLK];
-  const uint32_t k0 = blockIdx.x * BLK;
-  bool need = false;
-  {
-    const uint32_t k = k0 + threadIdx.x;
-    if (k < A.w.n) {
-      const uint2 ij = A.w.ij[k];
-      const uint8_t fl = A.w.flg[k];
-      const bool hot = fl & FLG_HOT;
-      if (hot) {
-        prefetch_l2(A.w.ft + k);
-        prefetch_l2(A.P.vm + ij.x); prefetch_l2(A.P.vm + ij.y); prefetch_l2(A.P.wg + ij.x); prefetch_l2(A.P.wg + ij.y);
+__device__ __forceinline__ bool detect_need(const ContactArgs& A, const uint2 ij, const uint8_t fl) {
+  if (fl & FLG_HOT) return true;
+  const double4 pi = ldg4(A.P.pr + ij.x), pj = ldg4(A.P.pr + ij.y);
+  const Contact c = detect_vv(mk3(pi.x, pi.y, pi.z), pi.w, mk3(pj.x, pj.y, pj.z), pj.w);
+  bool need = c.hit;
+  if (LAW == LAW_COHESIVE) {
+    const double dncut = A.prm.tpp ? cp_pp(A.prm, group_of(ldg4(A.P.wg + ij.x)), group_of(ldg4(A.P.wg + ij.y))).dncut : A.prm.pp.dncut;
+    need = need || c.dn <= dncut;
+  }
+  return need;
+}
+template <int LAW>
+__global__ void __launch_bounds__(BLK) k_detect_sphere_pp(ContactArgs A, NeedList L) {
+  // thread t of the block owns the DPT consecutive records [k0, k0 + DPT): one 32-byte ij load, one 4-byte flg load
+  const uint32_t k0 = (blockIdx.x * BLK + threadIdx.x) * DPT;
+  uint2 ij[DPT];
+  uint8_t fl[DPT];
+  bool need[DPT];
+  if (k0 + DPT <= A.w.n) {
+    const uint4 a = reinterpret_cast<const uint4*>(A.w.ij + k0)[0], b = reinterpret_cast<const uint4*>(A.w.ij + k0)[1];
+    const uint32_t f4 = *reinterpret_cast<const uint32_t*>(A.w.flg + k0);
+    ij[0] = make_uint2(a.x, a.y); ij[1] = make_uint2(a.z, a.w); ij[2] = make_uint2(b.x, b.y); ij[3] = make_uint2(b.z, b.w);
+#pragma unroll
+    for (int u = 0; u < DPT; u++) fl[u] = (uint8_t)(f4 >> (8 * u));
+#pragma unroll
+    for (int u = 0; u < DPT; u++) need[u] = detect_need<LAW>(A, ij[u], fl[u]);
+  } else {
+#pragma unroll
+    for (int u = 0; u < DPT; u++) {
+      need[u] = false;
+      if (k0 + u < A.w.n) {
+        ij[u] = A.w.ij[k0 + u];
+        fl[u] = A.w.flg[k0 + u];
+        need[u] = detect_need<LAW>(A, ij[u], fl[u]);
       }
-      const double4 pi = ldg4(A.P.pr + ij.x), pj = ldg4(A.P.pr + ij.y);
-      const Contact c = detect_vv(mk3(pi.x, pi.y, pi.z), pi.w, mk3(pj.x, pj.y, pj.z), pj.w);
-      bool contact = c.hit;
-      if (LAW == LAW_COHESIVE) {
-        const double dncut = A.prm.tpp ? cp_pp(A.prm, group_of(ldg4(A.P.wg + ij.x)), group_of(ldg4(A.P.wg + ij.y))).dncut : A.prm.pp.dncut;
-        contact = contact || c.dn <= dncut;
-      }
-      need = contact || hot;
     }
   }
+  uint32_t c = 0;
+#pragma unroll
+  for (int u = 0; u < DPT; u++) c += need[u] ? 1u : 0u;
+  // order-preserving compaction inside the block, one atomic per block (BLK * DPT records) for its range of the list
+  __shared__ uint32_t s_base;
   uint32_t tot;
-  const uint32_t pos = block_excl_scan(need ? 1u : 0u, &tot);
-  if (need) s_list[pos] = threadIdx.x;
+  uint32_t pos = block_excl_scan(c, &tot);
+  if (threadIdx.x == 0) s_base = tot ? atomicAdd(L.count, tot) : 0u;
   __syncthreads();
-  if (threadIdx.x >= tot) return;
-  const uint32_t k = k0 + s_list[threadIdx.x];
-  const uint2 ij = A.w.ij[k];
-  const uint8_t fl = A.w.flg[k];
-  const double4 pi = ldg4(A.P.pr + ij.x), pj = ldg4(A.P.pr + ij.y);
-  const double4 wi = ldg4(A.P.wg + ij.x), wj = ldg4(A.P.wg + ij.y);
-  const double4 vi = ldg4(A.P.vm + ij.x), vj = ldg4(A.P.vm + ij.y);
-  Hist H;
-  H.ft = ld4(A.w.ft + k);
-  H.mo = (fl & FLG_MOM) ? ld4(A.w.mo + k) : make_double4(0, 0, 0, 0);
-  const v3 ri = mk3(pi.x, pi.y, pi.z), rj = mk3(pj.x, pj.y, pj.z);
-  const Contact c = detect_vv(ri, pi.w, rj, pj.w);
-  const Params& cp = cp_pp(A.prm, group_of(wi), group_of(wj));
-  bool contact = c.hit;
-  if (LAW == LAW_COHESIVE) contact = contact || c.dn <= cp.dncut;
-  const double meff = (vi.w * vj.w) / (vi.w + vj.w);   // common_kernels.hpp:93-96
-  const double reff = (pi.w * pj.w) / (pi.w + pj.w);   // :99-102
-  finish_record<LAW>(A, k, fl, contact, c, cp, meff, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), rj,
-                     mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z), H);
+  pos += s_base;
+#pragma unroll
+  for (int u = 0; u < DPT; u++)
+    if (need[u]) L.ent[pos++] = make_uint4(k0 + u, ij[u].x, ij[u].y, fl[u]);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int LAW>
+__global__ void __launch_bounds__(BLK, 2) k_law_sphere_pp(ContactArgs A, NeedList L) {
+  const uint32_t cnt = *L.count;
+  const uint32_t stride = gridDim.x * BLK;
+  uint32_t t = blockIdx.x * BLK + threadIdx.x;
+  if (t >= cnt) return;
+  // software pipeline: the entry of the next iteration is already in registers, and its eight operand sectors are pulled into
+  // L2 while the current record is evaluated (prefetches hold no registers)
+  uint4 e = L.ent[t];
+  uint4 en = (t + stride < cnt) ? L.ent[t + stride] : make_uint4(0, 0, 0, 0);
+  for (; t < cnt; t += stride) {
+    const uint32_t k = e.x;
+    const uint8_t fl = (uint8_t)e.w;
+    const double4 pi = ldg4(A.P.pr + e.y), pj = ldg4(A.P.pr + e.z);
+    const double4 wi = ldg4(A.P.wg + e.y), wj = ldg4(A.P.wg + e.z);
+    const double4 vi = ldg4(A.P.vm + e.y), vj = ldg4(A.P.vm + e.z);
+    Hist H;
+    H.ft = ld4(A.w.ft + k);
+    H.mo = (fl & FLG_MOM) ? ld4(A.w.mo + k) : make_double4(0, 0, 0, 0);
+    const bool more = t + stride < cnt;
+    if (more) {
+      prefetch_l2(A.P.pr + en.y); prefetch_l2(A.P.pr + en.z);
+      prefetch_l2(A.P.wg + en.y); prefetch_l2(A.P.wg + en.z);
+      prefetch_l2(A.P.vm + en.y); prefetch_l2(A.P.vm + en.z);
+      prefetch_l2(A.w.ft + en.x);
+    }
+    const uint4 en2 = (t + 2 * stride < cnt) ? L.ent[t + 2 * stride] : make_uint4(0, 0, 0, 0);
+    const v3 ri = mk3(pi.x, pi.y, pi.z), rj = mk3(pj.x, pj.y, pj.z);
+    const Contact c = detect_vv(ri, pi.w, rj, pj.w);
+    const Params& cp = cp_pp(A.prm, group_of(wi), group_of(wj));
+    bool contact = c.hit;
+    if (LAW == LAW_COHESIVE) contact = contact || c.dn <= cp.dncut;
+    const double meff = (vi.w * vj.w) / (vi.w + vj.w);   // common_kernels.hpp:93-96
+    const double reff = (pi.w * pj.w) / (pi.w + pj.w);   // :99-102
+    finish_record<LAW>(A, k, fl, contact, c, cp, meff, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), rj,
+                       mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z), H);
+    e = en;
+    en = en2;
+  }
 }
 
 // detection of a driver record (waves 4,5,6): sphere::ContactLawDriverFunc (contact_sphere.hpp:232-296),
@@ -474,19 +530,17 @@ struct GatherArgs {
   WTab W;
   int order[NT];     // wave order of the operator (sphere: 0,4,5,6,7,8,9 ; polyhedron: 0..3,7..12,4,5,6)
   int norder;
-  const uint32_t* inc_off;
-  const uint32_t* inc;
+  const uint32_t* inc_off;   // per real particle: range of its incidence list (kernels_rebuild.cuh: k_inc_owner / k_incidence)
+  const uint32_t* inc;       // codes (position in `order` << 28 | record index), canonical (serial-reference) order
   uint32_t nreal;
-  int pp_partner;    // 1: add the reaction on the partner (symetric spheres, all polyhedra)
+  int npp;           // number of particle-particle waves (1 spheres, 4 polyhedra): their owner ranges decide owner / partner
   int has_swap;      // polyhedra: role of the owner depends on the swap bit
   double g[3];
   double hdt;
 };
 
 // role_i: particle acts as "i" of the record: F += f, M += (cp - r) x f + mom;  as "j": F += -f, M += (cp - r) x (-f) + (-mom)
-__device__ __forceinline__ void add_wrench(const WView& w, uint32_t k, uint8_t fl, bool role_i, v3 r, v3& F, v3& M) {
-  const double4 fd = ld4(w.fd + k), cp = ld4(w.cp + k);
-  const double4 mo = (fl & FLG_MOM) ? ld4(w.mo + k) : make_double4(0, 0, 0, 0);
+__device__ __forceinline__ void add_wrench(const double4& fd, const double4& cp, const double4& mo, bool role_i, v3 r, v3& F, v3& M) {
   v3 f = mk3(fd.x, fd.y, fd.z), m = mk3(mo.x, mo.y, mo.z);
   if (!role_i) {
     f = -f;
@@ -497,12 +551,22 @@ __device__ __forceinline__ void add_wrench(const WView& w, uint32_t k, uint8_t f
   F.x += f.x; F.y += f.y; F.z += f.z;
 }
 
+// One thread per real particle walks its incidence list — every record in which the particle is owner or partner, in the order
+// the serial reference loop would have applied them (wave by wave, record index ascending) — GU entries at a time: GU codes,
+// then GU flag bytes, then the wrenches of the hot ones are all in flight together (three dependent round trips per GU records
+// instead of three per record), and the sum is taken in list order, so the result is bit-reproducible.
 // FUSE 0: [contact_*] only: f, mom += sum        (drop-in operator semantics: accumulate on top of gravity etc.)
 // FUSE 1: reset_force_moment + gravity_force + contact + force_to_accel + combined_compute_epilog in one pass
+constexpr int GU = 4;
 template <int FUSE>
-__global__ void __launch_bounds__(BLK) k_gather(GatherArgs A) {
+__global__ void __launch_bounds__(BLK, 2) k_gather(const __grid_constant__ GatherArgs A) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= A.nreal) return;
+  const uint32_t e0 = A.inc_off[p], e1 = A.inc_off[p + 1];
+  uint32_t oa[4] = {0, 0, 0, 0}, ob[4] = {0, 0, 0, 0};   // owner ranges of the pp waves (order positions 0..npp-1 = waves 0..npp-1)
+#pragma unroll
+  for (int t = 0; t < 4; t++)
+    if (t < A.npp && A.W.w[t].n) { oa[t] = A.W.w[t].off[p]; ob[t] = A.W.w[t].off[p + 1]; }
   const double4 pr = ldg4(A.P.pr + p);
   const v3 r = mk3(pr.x, pr.y, pr.z);
   v3 F, M;
@@ -515,40 +579,48 @@ __global__ void __launch_bounds__(BLK) k_gather(GatherArgs A) {
     F = mk3(A.P.fx[p], A.P.fy[p], A.P.fz[p]);
     M = mk3(A.P.mx[p], A.P.my[p], A.P.mz[p]);
   }
-  uint32_t e = A.inc_off ? A.inc_off[p] : 0;
-  const uint32_t eend = A.inc_off ? A.inc_off[p + 1] : 0;
-  uint32_t code = e < eend ? A.inc[e] : 0xffffffffu;
-  for (int o = 0; o < A.norder; o++) {
-    const int t = A.order[o];
-    const WView& w = A.W.w[t];
-    if (w.n == 0) continue;
-    const uint32_t a = w.off[p], b = w.off[p + 1];
-    if (t <= 3 && A.pp_partner) {  // partner records that precede the owner segment in wave order
-      while ((code >> INC_SHIFT) == (uint32_t)t && (code & INC_MASK) < a) {
-        const uint32_t k = code & INC_MASK;
-        const uint8_t fl = w.flg[k];
-        const bool owner_is_i = A.has_swap ? !(fl & FLG_SWAP) : true;
-        if (fl & FLG_HOT) add_wrench(w, k, fl, !owner_is_i, r, F, M);
-        e++;
-        code = e < eend ? A.inc[e] : 0xffffffffu;
+  for (uint32_t e = e0; e < e1; e += GU) {
+    uint32_t code[GU];
+    const WView* w[GU];
+    uint8_t fl[GU];
+#pragma unroll
+    for (int u = 0; u < GU; u++) w[u] = &A.W.w[0];
+    double4 fd[GU], cp[GU];
+#pragma unroll
+    for (int u = 0; u < GU; u++) code[u] = (e + u < e1) ? A.inc[e + u] : 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < GU; u++) {
+      fl[u] = 0;
+      if (code[u] != 0xffffffffu) {
+        w[u] = &A.W.w[A.order[code[u] >> INC_SHIFT]];
+        fl[u] = w[u]->flg[code[u] & INC_MASK];
       }
     }
-    for (uint32_t k = a; k < b; k++) {
-      const uint8_t fl = w.flg[k];
-      // polyhedra: swapped records; mesh waves 11/12 ("j to i", contact.hpp:405-421): the particle receives -f, -mom
-      const bool owner_is_i = (t <= 3 && A.has_swap) ? !(fl & FLG_SWAP) : !(t == 11 || t == 12);
-      if (fl & FLG_HOT) add_wrench(w, k, fl, owner_is_i, r, F, M);
-    }
-    if (t <= 3 && A.pp_partner) {
-      while ((code >> INC_SHIFT) == (uint32_t)t) {
-        const uint32_t k = code & INC_MASK;
-        const uint8_t fl = w.flg[k];
-        const bool owner_is_i = A.has_swap ? !(fl & FLG_SWAP) : true;
-        if (fl & FLG_HOT) add_wrench(w, k, fl, !owner_is_i, r, F, M);
-        e++;
-        code = e < eend ? A.inc[e] : 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < GU; u++)
+      if (fl[u] & FLG_HOT) {
+        fd[u] = ld4(w[u]->fd + (code[u] & INC_MASK));
+        cp[u] = ld4(w[u]->cp + (code[u] & INC_MASK));
       }
-    }
+#pragma unroll
+    for (int u = 0; u < GU; u++)
+      if (fl[u] & FLG_HOT) {
+        const uint32_t o = code[u] >> INC_SHIFT, k = code[u] & INC_MASK;
+        const double4 mo = (fl[u] & FLG_MOM) ? ld4(w[u]->mo + k) : make_double4(0, 0, 0, 0);
+        bool role_i;
+        if ((int)o < A.npp) {
+          const uint32_t a = o == 0 ? oa[0] : o == 1 ? oa[1] : o == 2 ? oa[2] : oa[3];
+          const uint32_t b = o == 0 ? ob[0] : o == 1 ? ob[1] : o == 2 ? ob[2] : ob[3];
+          const bool owner = k >= a && k < b;
+          const bool owner_is_i = A.has_swap ? !(fl[u] & FLG_SWAP) : true;
+          role_i = owner ? owner_is_i : !owner_is_i;
+        } else {
+          // mesh waves 11/12 ("j to i", contact.hpp:405-421): the particle receives -f, -mom
+          const int t = A.order[o];
+          role_i = !(t == 11 || t == 12);
+        }
+        add_wrench(fd[u], cp[u], mo, role_i, r, F, M);
+      }
   }
   if (!FUSE) {
     A.P.fx[p] = F.x; A.P.fy[p] = F.y; A.P.fz[p] = F.z;
