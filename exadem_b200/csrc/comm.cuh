@@ -259,6 +259,11 @@ struct Comm {
     }
     NCK(g_nccl.GroupEnd());
   }
+  // in place, on the stream, no host round trip (rebuild trigger of the speculative step loop)
+  void allreduce_sum_u64_dev(unsigned long long* d, cudaStream_t st) {
+    if (!comm) return;
+    NCK(g_nccl.AllReduce(d, d, 1, ncclUint64, ncclSum, comm, st));
+  }
   uint64_t allreduce_sum_u64(uint64_t v, cudaStream_t st) {
     if (!comm) return v;
     d_red.ensure(2);

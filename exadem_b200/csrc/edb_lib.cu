@@ -54,6 +54,9 @@ struct edb_context {
   bool have_inc = false;
   DevBuf<uint4> need;               // work list of the two-pass contact kernels (kernels_step.cuh)
   uint32_t* d_need_count = nullptr;
+  unsigned long long* d_sflag = nullptr;   // rebuild trigger of the speculative step loop (2 slots, device)
+  unsigned long long* h_sflag = nullptr;   // ... pinned host copies
+  cudaEvent_t ev_sflag[2] = {};
   int n_sm = 148;
   double rcut_inc = 0;
   int symetric = 1;
@@ -262,6 +265,9 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
     CK(cudaMallocHost(&c->h_flag, sizeof(unsigned long long) * 4));
     CK(cudaMalloc(&c->d_flag, sizeof(unsigned long long) * 4));
     CK(cudaMalloc(&c->d_need_count, 16));
+    CK(cudaMalloc(&c->d_sflag, 16));
+    CK(cudaMallocHost(&c->h_sflag, 16));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&c->ev_sflag[i], cudaEventDisableTiming));
     { int dev = 0, v = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) c->n_sm = v; }
     CK(cudaMallocHost(&c->h_tot, sizeof(uint32_t) * (NT + 8)));
     for (int d = 0; d < 3; d++)
@@ -314,6 +320,9 @@ extern "C" int edb_destroy(edb_context* c) {
   if (c->h_flag) cudaFreeHost(c->h_flag);
   if (c->d_flag) cudaFree(c->d_flag);
   if (c->d_need_count) cudaFree(c->d_need_count);
+  if (c->d_sflag) cudaFree(c->d_sflag);
+  if (c->h_sflag) cudaFreeHost(c->h_sflag);
+  for (int i = 0; i < 2; i++) if (c->ev_sflag[i]) cudaEventDestroy(c->ev_sflag[i]);
   if (c->h_tot) cudaFreeHost(c->h_tot);
   cudaStreamDestroy(c->st);
   delete c;
@@ -1131,9 +1140,9 @@ extern "C" int edb_freeze_particles(edb_context* c) {
 
 
 template <int LAW>
-static void launch_contact_waves(edb_context* c, double dt) {
+static void launch_contact_waves(edb_context* c, double dt, const unsigned long long* gate) {
   const bool poly = c->poly();
-  ContactArgs A{view(c->pa), WView{}, c->prm, c->drv.p, c->vert.p, c->S, dt, 0, c->symetric, c->M};
+  ContactArgs A{view(c->pa), WView{}, c->prm, c->drv.p, c->vert.p, c->S, dt, 0, c->symetric, c->M, gate};
   const int* order = poly ? ORDER_POLY : ORDER_SPHERE;
   const int norder = poly ? 13 : 7;
   for (int o = 0; o < norder; o++) {
@@ -1169,16 +1178,18 @@ static void launch_contact_waves(edb_context* c, double dt) {
   }
 }
 
-static void contact_waves(edb_context* c, double dt) {
+static void contact_waves(edb_context* c, double dt, const unsigned long long* gate = nullptr) {
   ScopedTimer tm(c, B_CONTACT);
   if (!c->have_prev) throw StateError{EDB_ERR_STATE, "contact operator before update_particle_neighbors"};
-  if (c->law == 0) launch_contact_waves<0>(c, dt);
-  else if (c->law == 1) launch_contact_waves<1>(c, dt);
-  else launch_contact_waves<2>(c, dt);
+  if (c->law == 0) launch_contact_waves<0>(c, dt, gate);
+  else if (c->law == 1) launch_contact_waves<1>(c, dt, gate);
+  else launch_contact_waves<2>(c, dt, gate);
 }
 
+// next_flag (FUSE 2 only): where the rebuild trigger of the next step is accumulated (nullptr: not evaluated)
 template <int FUSE>
-static void gather(edb_context* c, const double* g, double dt) {
+static void gather(edb_context* c, const double* g, double dt, const unsigned long long* gate = nullptr,
+                   unsigned long long* next_flag = nullptr, double thr = 0.0) {
   ScopedTimer tm(c, B_GATHER);
   const bool poly = c->poly();
   GatherArgs A{};
@@ -1195,6 +1206,12 @@ static void gather(edb_context* c, const double* g, double dt) {
   A.has_swap = poly ? 1 : 0;
   if (g) { A.g[0] = g[0]; A.g[1] = g[1]; A.g[2] = g[2]; }
   A.hdt = dt * 0.5;
+  A.dt = dt;
+  A.dt2 = dt * dt * 0.5;
+  A.gate = gate;
+  A.next_flag = next_flag;
+  A.pr_backup = (next_flag && !poly) ? c->pr_backup.p : nullptr;
+  A.thr2 = thr * thr;
   LAUNCH(c, k_gather<FUSE>, nblk(c->nreal), BLK, 0, A);
   c->ctr.gather_launches++;
 }
@@ -1217,8 +1234,8 @@ extern "C" int edb_contact_polyhedron(edb_context* c, double dt) {
 static uint64_t displ_over(edb_context* c, double thr) {
   if (!c->have_backup) throw StateError{EDB_ERR_STATE, "displ_over before update_particle_neighbors"};
   CK(cudaMemsetAsync(c->d_flag, 0, 8, c->st));
-  if (c->poly()) LAUNCH(c, k_displ_over<true>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, c->q_backup.p, c->nreal, c->S, thr * thr, c->d_flag);
-  else LAUNCH(c, k_displ_over<false>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, nullptr, c->nreal, c->S, thr * thr, c->d_flag);
+  if (c->poly()) LAUNCH(c, k_displ_over<true>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, c->q_backup.p, c->nreal, c->S, thr * thr, c->d_flag, nullptr);
+  else LAUNCH(c, k_displ_over<false>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, nullptr, c->nreal, c->S, thr * thr, c->d_flag, nullptr);
   CK(cudaMemcpyAsync(c->h_flag, c->d_flag, 8, cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
   uint64_t v = c->h_flag[0];
@@ -1231,21 +1248,78 @@ extern "C" int edb_displ_over(edb_context* c, double thr, uint64_t* over) {
   API_END(c)
 }
 
+// Rebuild trigger of the step whose prolog has just been enqueued: the count lands in d_sflag[slot] (device, read by the gated
+// kernels of that step) and, reduced over the ranks, in h_sflag[slot] (pinned) once ev_sflag[slot] has completed.
+static void trigger_publish(edb_context* c, int slot) {
+  if (c->cfg.nranks > 1) c->comm.allreduce_sum_u64_dev(c->d_sflag + slot, c->st);
+  CK(cudaMemcpyAsync(c->h_sflag + slot, c->d_sflag + slot, 8, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaEventRecord(c->ev_sflag[slot], c->st));
+}
+static void trigger_standalone(edb_context* c, int slot, double thr) {
+  if (!c->have_backup) throw StateError{EDB_ERR_STATE, "displ_over before update_particle_neighbors"};
+  CK(cudaMemsetAsync(c->d_sflag + slot, 0, 8, c->st));
+  if (c->poly()) LAUNCH(c, k_displ_over<true>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, c->q_backup.p, c->nreal, c->S, thr * thr, c->d_sflag + slot, nullptr);
+  else LAUNCH(c, k_displ_over<false>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, nullptr, c->nreal, c->S, thr * thr, c->d_sflag + slot, nullptr);
+  trigger_publish(c, slot);
+}
+
+// The Verlet loop of numerical_scheme_verlet_macro (config_numerical_schemes.msp:6-30).  Per step the device runs
+//   [ghost refresh] -> contact waves -> gather fused with gravity, force_to_accel, the epilog AND the prolog + rebuild trigger of
+//   the next step (k_gather<2>).
+// With the displacement trigger (rebuild_every = 0) the host does not wait for the trigger before it enqueues the step: the
+// kernels that change state are launched gated on the device-side flag, and the host reads the flag (already copied to pinned
+// memory, one step behind the launch front) afterwards.  When the flag says "rebuild", the gated kernels have done nothing and
+// the step is enqueued again behind the rebuild.  The GPU never idles on the host in the common no-rebuild case.
 extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], double rcut_inc, int32_t symetric, int32_t nsteps,
                               int32_t rebuild_every, uint64_t* n_rebuilds) {
   API_BEGIN(c)
   uint64_t nb = 0;
   if (!c->have_prev) { rebuild(c, rcut_inc, symetric); }
-  for (int it = 0; it < nsteps; it++) {
+  const bool trig = rebuild_every == 0;
+  const double thr = 0.5 * rcut_inc;
+  const bool poly = c->poly();
+  if (nsteps > 0) {
     prolog(c, dt);
-    bool rb;
-    if (rebuild_every > 0) rb = ((it + 1) % rebuild_every) == 0;
-    else if (rebuild_every < 0) rb = false;
-    else rb = displ_over(c, 0.5 * rcut_inc) > 0;
-    if (rb) { rebuild(c, rcut_inc, symetric); nb++; }
-    else { ghost_refresh(c, false); compute_vertices(c); }
-    contact_waves(c, dt);
-    gather<1>(c, g, dt);
+    if (trig) trigger_standalone(c, 0, thr);
+  }
+  for (int it = 0; it < nsteps; it++) {
+    const bool last = it + 1 == nsteps;
+    const int slot = it & 1, nslot = slot ^ 1;
+    auto step_kernels = [&](const unsigned long long* gate) {
+      contact_waves(c, dt, gate);
+      if (last) {
+        gather<1>(c, g, dt, gate);
+        return;
+      }
+      if (!trig) {
+        gather<2>(c, g, dt, gate);
+        return;
+      }
+      CK(cudaMemsetAsync(c->d_sflag + nslot, 0, 8, c->st));
+      gather<2>(c, g, dt, gate, c->d_sflag + nslot, thr);
+      if (poly) LAUNCH(c, k_displ_over<true>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, c->q_backup.p, c->nreal, c->S, thr * thr, c->d_sflag + nslot, gate);
+      trigger_publish(c, nslot);
+    };
+    if (!trig) {
+      const bool rb = rebuild_every > 0 && ((it + 1) % rebuild_every) == 0;
+      if (rb) { rebuild(c, rcut_inc, symetric); nb++; }
+      else { ghost_refresh(c, false); compute_vertices(c); }
+      step_kernels(nullptr);
+    } else {
+      const edb_counters snap = c->ctr;
+      ghost_refresh(c, false);
+      compute_vertices(c);
+      step_kernels(c->d_sflag + slot);
+      CK(cudaEventSynchronize(c->ev_sflag[slot]));
+      if (c->h_sflag[slot] > 0) {
+        const uint64_t launches = c->ctr.kernel_launches;
+        c->ctr = snap;   // the gated launches did nothing
+        c->ctr.kernel_launches = launches;
+        rebuild(c, rcut_inc, symetric);
+        nb++;
+        step_kernels(nullptr);
+      }
+    }
     c->ctr.particle_steps += c->nreal;
   }
   if (n_rebuilds) *n_rebuilds = nb;

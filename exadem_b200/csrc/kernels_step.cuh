@@ -135,8 +135,9 @@ __global__ void k_compute_vertices(PView P, uint32_t n, ShapesView S, double4* _
 // particle_displ_over / vertex_displ_over (backup_dem.hpp:66-100): count of particles (vertices) with |d|^2 >= thr^2
 template <bool POLY>
 __global__ void k_displ_over(PView P, const double4* __restrict__ pr_b, const double4* __restrict__ q_b, uint32_t n,
-                             ShapesView S, double thr2, unsigned long long* __restrict__ count) {
+                             ShapesView S, double thr2, unsigned long long* __restrict__ count, const unsigned long long* gate) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gate && *gate) return;
   unsigned int c = 0;
   if (p < n) {
     const double4 r = P.pr[p], rb = pr_b[p];
@@ -175,7 +176,10 @@ struct ContactArgs {
   int type;
   int symetric;
   MeshView M;
+  // speculative step (edb_run_verlet): non-zero *gate = "this step needs a neighbour rebuild first" -> the kernel does nothing
+  const unsigned long long* gate;
 };
+__device__ __forceinline__ bool gated(const unsigned long long* gate) { return gate && *gate; }
 
 // Record state bit FLG_HOT (flg bit 3): the record was in contact at its last evaluation, i.e. its history (ft, mo) and its
 // wrench (fd, cp) are live.  Invariant: !HOT  =>  friction = moment = 0 (contact_sphere.hpp:197-200 resets them) and fd/cp are
@@ -288,6 +292,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 template <int LAW>
 __global__ void __launch_bounds__(BLK, 2) k_law_sphere_pp(ContactArgs A, NeedList L) {
+  if (gated(A.gate)) return;
   const uint32_t cnt = *L.count;
   const uint32_t stride = gridDim.x * BLK;
   uint32_t t = blockIdx.x * BLK + threadIdx.x;
@@ -345,7 +350,7 @@ __device__ __forceinline__ Contact detect_driver_record(const ContactArgs& A, ui
 template <int LAW, bool POLY>
 __global__ void __launch_bounds__(BLK) k_contact_driver(ContactArgs A) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= A.w.n) return;
+  if (k >= A.w.n || gated(A.gate)) return;
   const uint2 ij = A.w.ij[k];
   const uint8_t fl = A.w.flg[k];
   const bool hot = fl & FLG_HOT;
@@ -384,7 +389,7 @@ __device__ __forceinline__ Contact detect_poly_record(const ContactArgs& A, int 
 template <int LAW>
 __global__ void __launch_bounds__(BLK) k_contact_poly_pp(ContactArgs A) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= A.w.n) return;
+  if (k >= A.w.n || gated(A.gate)) return;
   const uint2 ij = A.w.ij[k], sb = A.w.sub[k];
   const uint8_t fl = A.w.flg[k];
   const bool hot = fl & FLG_HOT;
@@ -445,7 +450,7 @@ __device__ __forceinline__ Contact detect_mesh_record(const ContactArgs& A, int 
 template <int LAW, bool POLY>
 __global__ void __launch_bounds__(BLK) k_contact_mesh(ContactArgs A) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= A.w.n) return;
+  if (k >= A.w.n || gated(A.gate)) return;
   const uint2 ij = A.w.ij[k];
   const uint8_t fl = A.w.flg[k];
   const bool hot = fl & FLG_HOT;
@@ -537,6 +542,12 @@ struct GatherArgs {
   int has_swap;      // polyhedra: role of the owner depends on the swap bit
   double g[3];
   double hdt;
+  // FUSE 2 only: the prolog of the NEXT step and its rebuild trigger
+  double dt, dt2;
+  const double4* pr_backup;            // positions at the last neighbour build (nullptr: no trigger evaluation)
+  double thr2;
+  unsigned long long* next_flag;       // += number of particles with |r - r_backup|^2 >= thr2 after the next prolog
+  const unsigned long long* gate;      // see ContactArgs::gate
 };
 
 // role_i: particle acts as "i" of the record: F += f, M += (cp - r) x f + mom;  as "j": F += -f, M += (cp - r) x (-f) + (-mom)
@@ -557,11 +568,16 @@ __device__ __forceinline__ void add_wrench(const double4& fd, const double4& cp,
 // instead of three per record), and the sum is taken in list order, so the result is bit-reproducible.
 // FUSE 0: [contact_*] only: f, mom += sum        (drop-in operator semantics: accumulate on top of gravity etc.)
 // FUSE 1: reset_force_moment + gravity_force + contact + force_to_accel + combined_compute_epilog in one pass
+// FUSE 2: FUSE 1 + combined_compute_prolog of the NEXT step + particle_displ_over of the next step, all on the registers that
+//         already hold the particle: one pass over the particle arrays per time step instead of three.  The intermediate
+//         acceleration / moment / angular acceleration are not stored (nothing reads them before the next gather overwrites
+//         them; the last step of edb_run_verlet runs FUSE 1, so the state a caller can observe is complete).
 constexpr int GU = 4;
 template <int FUSE>
 __global__ void __launch_bounds__(BLK, 2) k_gather(const __grid_constant__ GatherArgs A) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= A.nreal) return;
+  if (gated(A.gate)) return;
+  if (p >= A.nreal) return;   // (exited lanes are not waited for by the full-mask reduction of the FUSE 2 trigger)
   const uint32_t e0 = A.inc_off[p], e1 = A.inc_off[p + 1];
   uint32_t oa[4] = {0, 0, 0, 0}, ob[4] = {0, 0, 0, 0};   // owner ranges of the pp waves (order positions 0..npp-1 = waves 0..npp-1)
 #pragma unroll
@@ -625,18 +641,44 @@ __global__ void __launch_bounds__(BLK, 2) k_gather(const __grid_constant__ Gathe
   if (!FUSE) {
     A.P.fx[p] = F.x; A.P.fy[p] = F.y; A.P.fz[p] = F.z;
     A.P.mx[p] = M.x; A.P.my[p] = M.y; A.P.mz[p] = M.z;
-  } else {
-    // force_to_accel, then combined_compute_epilog
-    const v3 acc = mk3(F.x / vm.w, F.y / vm.w, F.z / vm.w);
-    double4 w = ld4(A.P.wg + p);
-    const v3 ar = ang_accel(ldg4(A.P.q + p), M, mk3(w.x, w.y, w.z), mk3(A.P.ix[p], A.P.iy[p], A.P.iz[p]));
-    const v3 wn = mk3(w.x, w.y, w.z) + ar * A.hdt;
-    w.x = wn.x; w.y = wn.y; w.z = wn.z;
-    vm.x += acc.x * A.hdt; vm.y += acc.y * A.hdt; vm.z += acc.z * A.hdt;
+    return;
+  }
+  // force_to_accel, then combined_compute_epilog
+  const v3 acc = mk3(F.x / vm.w, F.y / vm.w, F.z / vm.w);
+  double4 w = ld4(A.P.wg + p);
+  double4 Q = ld4(A.P.q + p);
+  const v3 ar = ang_accel(Q, M, mk3(w.x, w.y, w.z), mk3(A.P.ix[p], A.P.iy[p], A.P.iz[p]));
+  const v3 wn = mk3(w.x, w.y, w.z) + ar * A.hdt;
+  w.x = wn.x; w.y = wn.y; w.z = wn.z;
+  vm.x += acc.x * A.hdt; vm.y += acc.y * A.hdt; vm.z += acc.z * A.hdt;
+  if (FUSE == 1) {
     A.P.fx[p] = acc.x; A.P.fy[p] = acc.y; A.P.fz[p] = acc.z;
     A.P.mx[p] = M.x; A.P.my[p] = M.y; A.P.mz[p] = M.z;
     A.P.ax[p] = ar.x; A.P.ay[p] = ar.y; A.P.az[p] = ar.z;
     st4(A.P.wg + p, w); st4(A.P.vm + p, vm);
+    return;
+  }
+  // combined_compute_prolog of the next step (same expressions as k_prolog, on the values k_prolog would have re-read)
+  double4 rn = pr;
+  rn.x += vm.x * A.dt + acc.x * A.dt2; rn.y += vm.y * A.dt + acc.y * A.dt2; rn.z += vm.z * A.dt + acc.z * A.dt2;
+  vm.x += acc.x * A.hdt; vm.y += acc.y * A.hdt; vm.z += acc.z * A.hdt;
+  const q4 q{Q.x, Q.y, Q.z, Q.w};
+  const q4 dq = qdot(q, mk3(w.x, w.y, w.z));
+  const q4 nq{q.w + dq.w * A.dt, q.x + dq.x * A.dt, q.y + dq.y * A.dt, q.z + dq.z * A.dt};
+  const double nn = sqrt(nq.w * nq.w + nq.x * nq.x + nq.y * nq.y + nq.z * nq.z);
+  Q = make_double4(nq.w / nn, nq.x / nn, nq.y / nn, nq.z / nn);
+  const v3 w2 = mk3(w.x, w.y, w.z) + A.hdt * ar;
+  w.x = w2.x; w.y = w2.y; w.z = w2.z;
+  st4(A.P.pr + p, rn); st4(A.P.vm + p, vm); st4(A.P.wg + p, w); st4(A.P.q + p, Q);
+  if (A.next_flag) {   // particle_displ_over (backup_dem.hpp:66-100) for the step that has just been started
+    unsigned int over = 0;
+    if (A.pr_backup) {
+      const double4 rb = ldg4(A.pr_backup + p);
+      const v3 d = mk3(rn.x, rn.y, rn.z) - mk3(rb.x, rb.y, rb.z);
+      over = dot(d, d) >= A.thr2 ? 1u : 0u;
+    }
+    over = __reduce_add_sync(0xffffffffu, over);
+    if ((threadIdx.x & 31) == 0 && over) atomicAdd(A.next_flag, (unsigned long long)over);
   }
 }
 

@@ -86,6 +86,22 @@ def test_drum_fused_run(product_lib, oracle_lib, rebuild_every):
     assert all(bit_identical(gpu.download_particles(), gpu2.download_particles()).values())
 
 
+def test_displacement_trigger_rebuilds_inside_run(product_lib, oracle_lib):
+    """The speculative step loop of edb_run_verlet (kernels gated on the device-side trigger, host one step behind): fast
+    spheres force a neighbour rebuild every ~10 steps; the rebuild count, the interaction set and the state must match the
+    oracle, which takes the decision synchronously (vertex/particle_displ_over -> update_particles_full)."""
+    wl = workloads.spheres_box((8, 8, 8), jitter=0.02, sigma_v=300.0, omega_sigma=0.3)
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 45, 0) for e in (gpu, cpu)]
+    assert nb[0] == nb[1] and nb[0] >= 3, nb
+    check(gpu, cpu)
+    # again in two calls (the loop state does not leak between calls)
+    nb2 = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 7, 0) + e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 1, 0) for e in (gpu, cpu)]
+    assert nb2[0] == nb2[1]
+    check(gpu, cpu)
+
+
 def test_history_survives_rebuild(product_lib, oracle_lib):
     wl = workloads.spheres_box((8, 8, 8), jitter=0.03, omega_sigma=0.3)
     gpu, cpu = pair(wl, product_lib, oracle_lib)
