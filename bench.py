@@ -6,7 +6,8 @@
 A "step" is one full Verlet time step of the hot path (prolog -> rebuild-or-ghost-refresh -> contact waves ->
 deterministic gather fused with gravity/force_to_accel/epilog) over the synthetic workload:
   N = 1 : BASELINE.json configs[1] — 1 M monodisperse spheres in a rotating drum (cylinder driver), fp64.
-  N > 1 : weak scaling, one 1 M-sphere brick per GPU of a periodic box (S5 topology), NCCL ghost exchange.
+  N > 1 : weak scaling of the same configuration: the drum is N times longer and cut into N slabs along its axis, one 1 M-sphere
+          slab per GPU, ghost exchange between neighbouring slabs (`--workload box`: S5 topology, periodic box of bricks).
 metric = interaction-updates/s (sum over waves of records processed by the contact kernels per wall second, whole job);
 particle-steps/s is reported beside it.  One JSON line is printed by rank 0.
 """
@@ -97,6 +98,9 @@ class ClockSampler:
 def make_workload(name, n, rank=0, nranks=1):
     from exadem_b200 import workloads
     if name == "drum":
+        if nranks > 1:
+            from exadem_b200 import parallel
+            return parallel.drum_slab_workload(n, rank, nranks)
         return workloads.rotating_drum(n)
     if name in ("box", "box8m"):
         side = int(round((8_000_000 if name == "box8m" else n) ** (1.0 / 3.0)))
@@ -157,7 +161,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    name = args.workload or ("drum" if args.gpus == 1 else "box")
+    name = args.workload or "drum"
     n_sample = min(args.particles, 200_000)
     wl = make_workload(name if name != "box8m" else "box", n_sample)
     sys.path.insert(0, str(ROOT / "tests"))
@@ -207,7 +211,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    name = args.workload or ("drum" if world == 1 else "box")
+    name = args.workload or "drum"
     wl = make_workload(name, args.particles, rank, world)
     lib = Library()
     cfg = wl.config(device=local) if world == 1 else parallel.brick_config(wl, rank, world, device=local)

@@ -52,8 +52,7 @@ struct edb_context {
   bool have_prev = false;
   DevBuf<uint32_t> inc_cnt, inc_off, inc;
   bool have_inc = false;
-  DevBuf<uint4> need;               // work list of the two-pass contact kernels (kernels_step.cuh)
-  uint32_t* d_need_count = nullptr;
+  uint32_t* d_need_count = nullptr;  // chunk queue of the persistent contact kernel (kernels_step.cuh)
   unsigned long long* d_sflag = nullptr;   // rebuild trigger of the speculative step loop (2 slots, device)
   unsigned long long* h_sflag = nullptr;   // ... pinned host copies
   cudaEvent_t ev_sflag[2] = {};
@@ -1155,11 +1154,8 @@ static void launch_contact_waves(edb_context* c, double dt, const unsigned long 
       ScopedTimer tpp(c, B_CONTACT_PP);
       if (poly) LAUNCH(c, k_contact_poly_pp<LAW>, nblk(w.n), BLK, 0, A);
       else {
-        c->need.ensure(w.n + 1);
-        const NeedList L{c->need.p, c->d_need_count};
         CK(cudaMemsetAsync(c->d_need_count, 0, 4, c->st));
-        LAUNCH(c, k_detect_sphere_pp<LAW>, nblk(w.n, BLK * DPT), BLK, 0, A, L);
-        LAUNCH(c, k_law_sphere_pp<LAW>, (uint32_t)std::min<uint64_t>(nblk(w.n), (uint64_t)c->n_sm * 2), BLK, 0, A, L);
+        LAUNCH(c, k_contact_sphere_pp<LAW>, (uint32_t)std::min<uint64_t>(nblk(w.n, CHUNK * (PP_BLK / 32)), (uint64_t)c->n_sm * PP_MINB), PP_BLK, 0, A, c->d_need_count);
       }
       c->ctr.contact_pp_launches++;
       c->ctr.contact_pp_records += w.n;

@@ -218,26 +218,26 @@ __device__ __forceinline__ void finish_record(const ContactArgs& A, uint32_t k, 
   if (nf != fl) A.w.flg[k] = nf;
 }
 
-// wave 0 of the sphere operator: sphere::ContactLawFunc (contact_sphere.hpp:121-203), as two launches.
-//
-// k_detect_sphere_pp (one thread per record, ~32 registers, full occupancy): reads ij + flg (9 B, coalesced).  A HOT record goes
-// straight to the work list; a cold one gathers the two position sectors and is listed only if the spheres touch (or are inside
-// the cohesive range).  A cold record that stays cold costs 9 B + two L1/L2-resident gathers and nothing else.  The list entry
-// carries (k, i, j, flg) so the second launch needs ONE dependent round trip (entry -> everything) instead of four.
-// Warp-aggregated append: one atomic per warp, a warp's entries are contiguous (512 B) and keep their record order.
-//
-// k_law_sphere_pp (persistent, one list entry per thread and iteration): all eight 32-byte operands of a record (r, v, w of both
-// particles, friction, moment) are issued back to back, then detection + Hooke law on dense warps, then the history / wrench
-// stores.  The order of the list does not influence any result: records are independent and the force sum is done by k_gather.
-struct NeedList {
-  uint4* ent;
-  uint32_t* count;
-};
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-constexpr int DPT = 4;  // records per thread of the detection pass
+// wave 0 of the sphere operator: sphere::ContactLawFunc (contact_sphere.hpp:121-203).
+//
+// Persistent kernel, warp-autonomous (no block barrier anywhere).  A warp takes chunks of CHUNK = 128 consecutive records from a
+// dynamic queue.  Per chunk:
+//   detect  lane l owns records [k0 + 4l, k0 + 4l + 4): one 32-byte ij load + one 4-byte flg load (coalesced, 9 B/record).
+//           HOT records (in contact at their last evaluation) are work by definition: their seven operand sectors (r, v, w of both
+//           particles, friction) are pulled into L2 at once with prefetch.global.L2 — no registers, no scoreboard — while the cold
+//           records gather the two position sectors and run detection_vertex_vertex.  A cold record that stays cold costs
+//           9 B + two mostly L1/L2-resident gathers and nothing else (no history read, no write).
+//   compact shuffle scan of the per-lane counts; the (k, i, j, flg) entries of the records that need the law go, in record order,
+//           to a 2 KB per-warp shared-memory list.
+//   law     dense: 32 entries per round, all eight operands of an entry issued back to back (L2 hits after the prefetch),
+//           detection + Hooke law + history / wrench stores on fully populated warps.
+// The id of the next chunk is fetched (one atomic per 128 records) before the current one is processed.
+constexpr int CHUNK = 128;
+
 template <int LAW>
-__device__ __forceinline__ bool detect_need(const ContactArgs& A, const uint2 ij, const uint8_t fl) {
-  if (fl & FLG_HOT) return true;
+__device__ __forceinline__ bool detect_need(const ContactArgs& A, const uint2 ij) {
   const double4 pi = ldg4(A.P.pr + ij.x), pj = ldg4(A.P.pr + ij.y);
   const Contact c = detect_vv(mk3(pi.x, pi.y, pi.z), pi.w, mk3(pj.x, pj.y, pj.z), pj.w);
   bool need = c.hit;
@@ -247,88 +247,89 @@ __device__ __forceinline__ bool detect_need(const ContactArgs& A, const uint2 ij
   }
   return need;
 }
+
+#ifndef EDB_PP_BLK
+#define EDB_PP_BLK 256
+#endif
+#ifndef EDB_PP_MINB
+#define EDB_PP_MINB 2
+#endif
+constexpr int PP_BLK = EDB_PP_BLK, PP_MINB = EDB_PP_MINB;   // tuning knobs of the sweep in profiles/ (registers vs resident warps)
 template <int LAW>
-__global__ void __launch_bounds__(BLK) k_detect_sphere_pp(ContactArgs A, NeedList L) {
-  // thread t of the block owns the DPT consecutive records [k0, k0 + DPT): one 32-byte ij load, one 4-byte flg load
-  const uint32_t k0 = (blockIdx.x * BLK + threadIdx.x) * DPT;
-  uint2 ij[DPT];
-  uint8_t fl[DPT];
-  bool need[DPT];
-  if (k0 + DPT <= A.w.n) {
-    const uint4 a = reinterpret_cast<const uint4*>(A.w.ij + k0)[0], b = reinterpret_cast<const uint4*>(A.w.ij + k0)[1];
-    const uint32_t f4 = *reinterpret_cast<const uint32_t*>(A.w.flg + k0);
-    ij[0] = make_uint2(a.x, a.y); ij[1] = make_uint2(a.z, a.w); ij[2] = make_uint2(b.x, b.y); ij[3] = make_uint2(b.z, b.w);
+__global__ void __launch_bounds__(PP_BLK, PP_MINB) k_contact_sphere_pp(ContactArgs A, uint32_t* __restrict__ queue) {
+  if (gated(A.gate)) return;
+  __shared__ uint4 s_ent[PP_BLK / 32][CHUNK];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint4* ents = s_ent[wid];
+  const uint32_t nchunk = (A.w.n + CHUNK - 1) / CHUNK;
+  const uint32_t nwarp = gridDim.x * (PP_BLK / 32);
+  uint32_t chunk = blockIdx.x * (PP_BLK / 32) + wid;
+  while (chunk < nchunk) {
+    uint32_t next = 0;
+    if (lane == 0) next = atomicAdd(queue, 1u);
+    const uint32_t k0 = chunk * CHUNK + lane * 4;
+    uint2 ij[4];
+    uint32_t f4 = 0;
+    if (k0 + 4 <= A.w.n) {
+      const uint4 a = reinterpret_cast<const uint4*>(A.w.ij + k0)[0], b = reinterpret_cast<const uint4*>(A.w.ij + k0)[1];
+      f4 = *reinterpret_cast<const uint32_t*>(A.w.flg + k0);
+      ij[0] = make_uint2(a.x, a.y); ij[1] = make_uint2(a.z, a.w); ij[2] = make_uint2(b.x, b.y); ij[3] = make_uint2(b.z, b.w);
+    } else {
 #pragma unroll
-    for (int u = 0; u < DPT; u++) fl[u] = (uint8_t)(f4 >> (8 * u));
-#pragma unroll
-    for (int u = 0; u < DPT; u++) need[u] = detect_need<LAW>(A, ij[u], fl[u]);
-  } else {
-#pragma unroll
-    for (int u = 0; u < DPT; u++) {
-      need[u] = false;
-      if (k0 + u < A.w.n) {
-        ij[u] = A.w.ij[k0 + u];
-        fl[u] = A.w.flg[k0 + u];
-        need[u] = detect_need<LAW>(A, ij[u], fl[u]);
+      for (int u = 0; u < 4; u++) {
+        ij[u] = make_uint2(0, 0);
+        if (k0 + u < A.w.n) {
+          ij[u] = A.w.ij[k0 + u];
+          f4 |= (uint32_t)A.w.flg[k0 + u] << (8 * u);
+        }
       }
     }
-  }
-  uint32_t c = 0;
+    bool need[4];
 #pragma unroll
-  for (int u = 0; u < DPT; u++) c += need[u] ? 1u : 0u;
-  // order-preserving compaction inside the block, one atomic per block (BLK * DPT records) for its range of the list
-  __shared__ uint32_t s_base;
-  uint32_t tot;
-  uint32_t pos = block_excl_scan(c, &tot);
-  if (threadIdx.x == 0) s_base = tot ? atomicAdd(L.count, tot) : 0u;
-  __syncthreads();
-  pos += s_base;
-#pragma unroll
-  for (int u = 0; u < DPT; u++)
-    if (need[u]) L.ent[pos++] = make_uint4(k0 + u, ij[u].x, ij[u].y, fl[u]);
-}
-
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-template <int LAW>
-__global__ void __launch_bounds__(BLK, 2) k_law_sphere_pp(ContactArgs A, NeedList L) {
-  if (gated(A.gate)) return;
-  const uint32_t cnt = *L.count;
-  const uint32_t stride = gridDim.x * BLK;
-  uint32_t t = blockIdx.x * BLK + threadIdx.x;
-  if (t >= cnt) return;
-  // software pipeline: the entry of the next iteration is already in registers, and its eight operand sectors are pulled into
-  // L2 while the current record is evaluated (prefetches hold no registers)
-  uint4 e = L.ent[t];
-  uint4 en = (t + stride < cnt) ? L.ent[t + stride] : make_uint4(0, 0, 0, 0);
-  for (; t < cnt; t += stride) {
-    const uint32_t k = e.x;
-    const uint8_t fl = (uint8_t)e.w;
-    const double4 pi = ldg4(A.P.pr + e.y), pj = ldg4(A.P.pr + e.z);
-    const double4 wi = ldg4(A.P.wg + e.y), wj = ldg4(A.P.wg + e.z);
-    const double4 vi = ldg4(A.P.vm + e.y), vj = ldg4(A.P.vm + e.z);
-    Hist H;
-    H.ft = ld4(A.w.ft + k);
-    H.mo = (fl & FLG_MOM) ? ld4(A.w.mo + k) : make_double4(0, 0, 0, 0);
-    const bool more = t + stride < cnt;
-    if (more) {
-      prefetch_l2(A.P.pr + en.y); prefetch_l2(A.P.pr + en.z);
-      prefetch_l2(A.P.wg + en.y); prefetch_l2(A.P.wg + en.z);
-      prefetch_l2(A.P.vm + en.y); prefetch_l2(A.P.vm + en.z);
-      prefetch_l2(A.w.ft + en.x);
+    for (int u = 0; u < 4; u++) {
+      need[u] = (f4 >> (8 * u)) & FLG_HOT;
+      if (need[u]) {
+        prefetch_l2(A.P.pr + ij[u].x); prefetch_l2(A.P.pr + ij[u].y);
+        prefetch_l2(A.P.vm + ij[u].x); prefetch_l2(A.P.vm + ij[u].y);
+        prefetch_l2(A.P.wg + ij[u].x); prefetch_l2(A.P.wg + ij[u].y);
+        prefetch_l2(A.w.ft + k0 + u);
+      }
     }
-    const uint4 en2 = (t + 2 * stride < cnt) ? L.ent[t + 2 * stride] : make_uint4(0, 0, 0, 0);
-    const v3 ri = mk3(pi.x, pi.y, pi.z), rj = mk3(pj.x, pj.y, pj.z);
-    const Contact c = detect_vv(ri, pi.w, rj, pj.w);
-    const Params& cp = cp_pp(A.prm, group_of(wi), group_of(wj));
-    bool contact = c.hit;
-    if (LAW == LAW_COHESIVE) contact = contact || c.dn <= cp.dncut;
-    const double meff = (vi.w * vj.w) / (vi.w + vj.w);   // common_kernels.hpp:93-96
-    const double reff = (pi.w * pj.w) / (pi.w + pj.w);   // :99-102
-    finish_record<LAW>(A, k, fl, contact, c, cp, meff, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), rj,
-                       mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z), H);
-    e = en;
-    en = en2;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (!need[u] && k0 + u < A.w.n) need[u] = detect_need<LAW>(A, ij[u]);
+    uint32_t c = 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) c += need[u] ? 1u : 0u;
+    const uint32_t inc = warp_incl_scan(c);
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t pos = inc - c;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (need[u]) ents[pos++] = make_uint4(k0 + u, ij[u].x, ij[u].y, (f4 >> (8 * u)) & 0xffu);
+    __syncwarp();
+    for (uint32_t i = lane; i < total; i += 32) {
+      const uint4 e = ents[i];
+      const uint32_t k = e.x;
+      const uint8_t fl = (uint8_t)e.w;
+      const double4 pi = ldg4(A.P.pr + e.y), pj = ldg4(A.P.pr + e.z);
+      const double4 wi = ldg4(A.P.wg + e.y), wj = ldg4(A.P.wg + e.z);
+      const double4 vi = ldg4(A.P.vm + e.y), vj = ldg4(A.P.vm + e.z);
+      Hist H;
+      H.ft = ld4(A.w.ft + k);
+      H.mo = (fl & FLG_MOM) ? ld4(A.w.mo + k) : make_double4(0, 0, 0, 0);
+      const v3 ri = mk3(pi.x, pi.y, pi.z), rj = mk3(pj.x, pj.y, pj.z);
+      const Contact ct = detect_vv(ri, pi.w, rj, pj.w);
+      const Params& cp = cp_pp(A.prm, group_of(wi), group_of(wj));
+      bool contact = ct.hit;
+      if (LAW == LAW_COHESIVE) contact = contact || ct.dn <= cp.dncut;
+      const double meff = (vi.w * vj.w) / (vi.w + vj.w);   // common_kernels.hpp:93-96
+      const double reff = (pi.w * pj.w) / (pi.w + pj.w);   // :99-102
+      finish_record<LAW>(A, k, fl, contact, ct, cp, meff, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), rj,
+                         mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z), H);
+    }
+    __syncwarp();
+    chunk = nwarp + __shfl_sync(0xffffffffu, next, 0);
   }
 }
 
@@ -572,9 +573,15 @@ __device__ __forceinline__ void add_wrench(const double4& fd, const double4& cp,
 //         already hold the particle: one pass over the particle arrays per time step instead of three.  The intermediate
 //         acceleration / moment / angular acceleration are not stored (nothing reads them before the next gather overwrites
 //         them; the last step of edb_run_verlet runs FUSE 1, so the state a caller can observe is complete).
-constexpr int GU = 4;
+#ifndef EDB_GU
+#define EDB_GU 2
+#endif
+#ifndef EDB_G_MINB
+#define EDB_G_MINB 3
+#endif
+constexpr int GU = EDB_GU;
 template <int FUSE>
-__global__ void __launch_bounds__(BLK, 2) k_gather(const __grid_constant__ GatherArgs A) {
+__global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constant__ GatherArgs A) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (gated(A.gate)) return;
   if (p >= A.nreal) return;   // (exited lanes are not waited for by the full-mask reduction of the FUSE 2 trigger)

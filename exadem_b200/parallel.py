@@ -86,6 +86,24 @@ def brick_workload(side: int, rank: int, nranks: int, seed=0xD3A5):
     return wl
 
 
+def drum_slab_workload(n_per_gpu: int, rank: int, nranks: int, seed=0xD3A2):
+    """Weak scaling of BASELINE configs[1]: the rotating drum made `nranks` times longer along its (periodic) axis and cut into
+    `nranks` slabs, one per GPU — per-GPU work is exactly the N=1 drum (same particle count, same cylinder, same number of
+    ghost cells: the two periodic end faces become faces shared with the neighbouring slabs).  pgrid = (1, nranks, 1)."""
+    from . import workloads
+    wl = workloads.rotating_drum(n_per_gpu, seed=seed + 7919 * rank, name=f"drum, {nranks} slabs along the axis")
+    L = wl.hi[1] - wl.lo[1]
+    n = wl.particles.n
+    wl.particles.ry += rank * L
+    wl.particles.id[:] = (np.uint64(rank) * np.uint64(n) + wl.particles.id).astype(np.uint64)
+    wl.glo = wl.lo
+    wl.ghi = (wl.hi[0], float(nranks * L), wl.hi[2])
+    wl.lo = (wl.lo[0], float(rank * L), wl.lo[2])
+    wl.hi = (wl.hi[0], float((rank + 1) * L), wl.hi[2])
+    wl.pgrid = (1, nranks, 1)
+    return wl
+
+
 def brick_config(wl, rank: int, nranks: int, device: int = 0):
     pg = getattr(wl, "pgrid", process_grid(nranks))
     glo = getattr(wl, "glo", wl.lo)
