@@ -97,6 +97,108 @@ __global__ void k_recv_cells(const uint32_t* __restrict__ gcell, uint32_t nent, 
   for (uint32_t s = b; s < e; s++) cidx[s] = gcell[k];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Per-step ghost refresh over NVLink peer memory (no NCCL on the per-step path).
+//
+// Every rank owns one "mailbox" allocation, exported to the other ranks with CUDA IPC:
+//     [ mail[2][64] u64 | landing[0] : pr | vm | wg | q (cap double4 each) | landing[1] : ... ]
+// k_ghost_push   (sender)   stores the refreshed sectors of its boundary particles straight into the receivers' landing zones
+//                           (256-bit stores over NVLink), and its last block then stores {epoch, local rebuild-trigger count}
+//                           into the mailbox of EVERY rank (release at system scope).
+// k_ghost_land   (receiver) waits until every rank's mail of this epoch has arrived, sums the trigger counts (this is the
+//                           all-reduce of `trigger_move_particles`, for free) and copies the landing zone into the ghost slots.
+// Landing zones and mail are double-buffered by epoch parity: a sender can be at most one exchange ahead of a receiver
+// (its next push comes after its own land, which needs the receiver's push of the current epoch), so no "ready" handshake is
+// needed.  The rebuild-time exchange (ids, homothety, variable counts) stays on NCCL.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int P2P_MAXR = 64;     // mailbox slots
+constexpr int P2P_MAXPEER = 26;  // neighbouring bricks
+struct PushPeer {
+  const uint32_t* smap;    // source slot per outgoing ghost
+  const uint32_t* sent;    // send-table entry per outgoing ghost (-> shift)
+  const double* sshift;
+  uint32_t start, n;       // range inside the combined launch
+  double4* land;           // receiver's landing zone of this epoch, already offset to our range; arrays are `cap` apart
+  uint32_t cap;
+};
+struct PushArgs {
+  PView P;
+  PushPeer peer[P2P_MAXPEER];
+  int npeer;
+  uint32_t total;
+  unsigned long long* mail[P2P_MAXR];  // mailbox slot [parity][me] of every other rank
+  int nmail;
+  unsigned int* done;                  // block counter (device, zero between launches)
+  const unsigned long long* count;     // local trigger count (nullptr: 0)
+  uint32_t epoch;
+};
+__global__ void __launch_bounds__(BLK) k_ghost_push(const __grid_constant__ PushArgs A) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < A.total) {
+    int pi = 0;
+    while (pi + 1 < A.npeer && k >= A.peer[pi + 1].start) pi++;
+    const PushPeer& p = A.peer[pi];
+    const uint32_t l = k - p.start;
+    const uint32_t s = p.smap[l], e = p.sent[l];
+    double4 r = ld4(A.P.pr + s);
+    r.x = r.x + p.sshift[3 * e]; r.y = r.y + p.sshift[3 * e + 1]; r.z = r.z + p.sshift[3 * e + 2];
+    st4(p.land + l, r);
+    st4(p.land + (size_t)p.cap + l, ld4(A.P.vm + s));
+    st4(p.land + 2 * (size_t)p.cap + l, ld4(A.P.wg + s));
+    st4(p.land + 3 * (size_t)p.cap + l, ld4(A.P.q + s));
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(A.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) *A.done = 0;
+  if ((int)threadIdx.x < A.nmail) {
+    unsigned long long c = A.count ? *A.count : 0ull;
+    if (c > 0xffffffffull) c = 0xffffffffull;
+    const unsigned long long v = ((unsigned long long)A.epoch << 32) | c;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.mail[threadIdx.x]), "l"(v) : "memory");
+  }
+}
+struct LandArgs {
+  PView P;
+  const unsigned long long* mail;   // our mailbox row of this parity: one slot per rank
+  int nranks, me;
+  uint32_t epoch;
+  unsigned long long* count;        // in: local trigger count, out: sum over the ranks (nullptr: not reduced)
+  const double4* land;              // landing zone of this parity
+  uint32_t cap, n, base;            // n remote ghosts -> slots [base, base + n)
+};
+__global__ void __launch_bounds__(BLK) k_ghost_land(const __grid_constant__ LandArgs A) {
+  __shared__ unsigned long long s_cnt[P2P_MAXR];
+  if ((int)threadIdx.x < A.nranks) {
+    unsigned long long v = 0;
+    if ((int)threadIdx.x != A.me) {
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(A.mail + threadIdx.x) : "memory");
+        if ((int32_t)((uint32_t)(v >> 32) - A.epoch) >= 0) break;
+        __nanosleep(64);
+      }
+    }
+    s_cnt[threadIdx.x] = v & 0xffffffffull;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && A.count) {
+    unsigned long long t = *A.count;
+    for (int r = 0; r < A.nranks; r++)
+      if (r != A.me) t += s_cnt[r];
+    *A.count = t;
+  }
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += gridDim.x * blockDim.x) {
+    st4(A.P.pr + A.base + k, ld4(A.land + k));
+    st4(A.P.vm + A.base + k, ld4(A.land + (size_t)A.cap + k));
+    st4(A.P.wg + A.base + k, ld4(A.land + 2 * (size_t)A.cap + k));
+    st4(A.P.q + A.base + k, ld4(A.land + 3 * (size_t)A.cap + k));
+  }
+}
+
 struct Peer {
   int rank;
   std::vector<GhostEntry> recv;  // our ghost cells fed by this peer (our table order)
@@ -104,6 +206,7 @@ struct Peer {
   DevBuf<uint32_t> d_rgcell, d_rcnt, d_roff, d_scell, d_scnt, d_soff, d_smap, d_sent;
   DevBuf<double> d_sshift;
   uint32_t n_send = 0, n_recv = 0, recv_base = 0;  // particles; recv_base = offset inside the ghost region
+  uint32_t remote_base = 0, remote_cap = 0;         // P2P: where our data lands in the peer's landing zone / its array stride
   DevBuf<double4> s_pr, s_vm, s_wg, s_q;
   DevBuf<double> s_h;
   DevBuf<uint64_t> s_id;
@@ -117,6 +220,132 @@ struct Comm {
   std::map<int, Peer> peers;
   DevBuf<unsigned long long> d_red;
   DevBuf<uint32_t> d_gather;
+  // NVLink peer-memory ghost refresh (see k_ghost_push / k_ghost_land)
+  struct P2P {
+    bool on = false, tried = false;
+    std::string why;                 // why it is off
+    char* base = nullptr;            // own mailbox allocation
+    uint32_t cap = 0;                // landing capacity (ghost particles per parity)
+    char* peer_base[P2P_MAXR] = {};  // opened peer allocations
+    uint32_t peer_cap[P2P_MAXR] = {};
+    cudaIpcMemHandle_t peer_handle[P2P_MAXR] = {};
+    uint32_t epoch = 0;
+    unsigned int* d_done = nullptr;
+    uint64_t exchanges = 0;
+  } p2p;
+  static size_t p2p_mail_bytes() { return 2 * P2P_MAXR * sizeof(unsigned long long); }
+  static size_t p2p_bytes(uint32_t cap) { return p2p_mail_bytes() + 2 * 4 * (size_t)cap * sizeof(double4); }
+  static unsigned long long* p2p_mail(char* b, int parity) { return (unsigned long long*)b + parity * P2P_MAXR; }
+  static double4* p2p_land(char* b, uint32_t cap, int parity) { return (double4*)(b + p2p_mail_bytes()) + (size_t)parity * 4 * cap; }
+  void p2p_close() {
+    for (int r = 0; r < P2P_MAXR; r++)
+      if (p2p.peer_base[r]) { cudaIpcCloseMemHandle(p2p.peer_base[r]); p2p.peer_base[r] = nullptr; }
+  }
+  // Collective, called at every rebuild once the ghost layout of all ranks is known: (re)allocates the mailbox when the ghost
+  // count outgrew it, exchanges IPC handles + landing offsets (one NCCL all-gather), opens what changed.
+  void p2p_prepare(uint32_t n_remote_ghost, cudaStream_t st) {
+    if (!comm || nranks > P2P_MAXR || (int)peers.size() > P2P_MAXPEER) { p2p.on = false; p2p.why = "rank/peer count over the mailbox size"; return; }
+    if (p2p.tried && !p2p.on) return;
+    if (getenv("EDB_NO_P2P")) { p2p.tried = true; p2p.on = false; p2p.why = "EDB_NO_P2P set"; return; }
+    CK(cudaStreamSynchronize(st));   // every push/land of the previous layout has completed on this rank
+    bool ok = true;
+    // 1. capacity: a rank reallocates only when it must; the others learn the new handle from the all-gather
+    bool fresh = false;
+    if (!p2p.base || n_remote_ghost > p2p.cap) {
+      if (p2p.base) {
+        // peers may still map the old allocation: it is released after the all-gather barrier below, when nobody pushes to it
+      }
+      const uint32_t ncap = n_remote_ghost + n_remote_ghost / 4 + 4096;
+      char* nb = nullptr;
+      if (cudaMalloc(&nb, p2p_bytes(ncap)) != cudaSuccess) { cudaGetLastError(); ok = false; }
+      else {
+        CK(cudaMemset(nb, 0, p2p_bytes(ncap)));
+        old_base = p2p.base;
+        p2p.base = nb;
+        p2p.cap = ncap;
+        fresh = true;
+      }
+      if (!p2p.d_done) { CK(cudaMalloc(&p2p.d_done, 4)); CK(cudaMemset(p2p.d_done, 0, 4)); }
+    }
+    // 2. blob: [ok][cap][handle 16 u32][recv_base per rank]
+    const uint32_t nb32 = 2 + 16 + (uint32_t)nranks;
+    std::vector<uint32_t> mine(nb32, 0), all((size_t)nb32 * nranks, 0);
+    cudaIpcMemHandle_t h{};
+    if (ok && cudaIpcGetMemHandle(&h, p2p.base) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    mine[0] = ok ? 1u : 0u;
+    mine[1] = p2p.cap;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(&mine[2], &h, 64);
+    for (auto& kv : peers) mine[18 + kv.first] = kv.second.recv_base;
+    allgather_u32(mine.data(), nb32, all.data(), st);
+    for (int r = 0; r < nranks; r++) ok = ok && all[(size_t)r * nb32] == 1u;
+    // 3. open what is new
+    if (ok)
+      for (int r = 0; r < nranks && ok; r++) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t hr;
+        memcpy(&hr, &all[(size_t)r * nb32 + 2], 64);
+        if (p2p.peer_base[r] && memcmp(&hr, &p2p.peer_handle[r], 64) == 0) continue;
+        if (p2p.peer_base[r]) { cudaIpcCloseMemHandle(p2p.peer_base[r]); p2p.peer_base[r] = nullptr; }
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        p2p.peer_base[r] = (char*)ptr;
+        p2p.peer_handle[r] = hr;
+        p2p.peer_cap[r] = all[(size_t)r * nb32 + 1];
+      }
+    // 4. agree (a second tiny all-gather doubles as the barrier after which replaced allocations can be freed)
+    std::vector<uint32_t> okv(nranks, 0);
+    const uint32_t myok = ok ? 1u : 0u;
+    allgather_u32(&myok, 1, okv.data(), st);
+    for (int r = 0; r < nranks; r++) ok = ok && okv[r] == 1u;
+    if (old_base) { cudaFree(old_base); old_base = nullptr; }
+    (void)fresh;
+    p2p.tried = true;
+    p2p.on = ok;
+    if (!ok) { p2p.why = "CUDA IPC peer mapping unavailable"; p2p_close(); return; }
+    for (auto& kv : peers) {
+      Peer& p = kv.second;
+      p.remote_base = all[(size_t)p.rank * nb32 + 18 + rank];
+      p.remote_cap = p2p.peer_cap[p.rank];
+    }
+  }
+  char* old_base = nullptr;
+  // per-step refresh over peer memory; `count` (device, nullable) is all-reduced (sum) in place as a by-product
+  void exchange_ghosts_p2p(PView P, uint32_t nreal, unsigned long long* count, cudaStream_t st, uint64_t* launches) {
+    const uint32_t e = ++p2p.epoch;
+    const int par = (int)(e & 1u);
+    PushArgs A{};
+    A.P = P;
+    uint32_t tot = 0, nrem = 0;
+    for (auto& kv : peers) {
+      Peer& p = kv.second;
+      nrem += p.n_recv;
+      if (!p.n_send) continue;
+      PushPeer& q = A.peer[A.npeer++];
+      q.smap = p.d_smap.p; q.sent = p.d_sent.p; q.sshift = p.d_sshift.p;
+      q.start = tot; q.n = p.n_send;
+      q.cap = p.remote_cap;
+      q.land = p2p_land(p2p.peer_base[p.rank], p.remote_cap, par) + p.remote_base;
+      tot += p.n_send;
+    }
+    A.total = tot;
+    for (int r = 0; r < nranks; r++)
+      if (r != rank) A.mail[A.nmail++] = p2p_mail(p2p.peer_base[r], par) + rank;
+    A.done = p2p.d_done;
+    A.count = count;
+    A.epoch = e;
+    k_ghost_push<<<tot ? (tot + BLK - 1) / BLK : 1, BLK, 0, st>>>(A);
+    LandArgs L{};
+    L.P = P;
+    L.mail = p2p_mail(p2p.base, par);
+    L.nranks = nranks; L.me = rank; L.epoch = e; L.count = count;
+    L.land = p2p_land(p2p.base, p2p.cap, par);
+    L.cap = p2p.cap; L.n = nrem; L.base = nreal + n_local_ghost;
+    const uint32_t nb = nrem ? std::min<uint32_t>((nrem + BLK - 1) / BLK, 592u) : 1u;
+    k_ghost_land<<<nb, BLK, 0, st>>>(L);
+    (*launches) += 2;
+    p2p.exchanges++;
+  }
 
   static int unique_id(uint8_t out[128]) {
     if (!g_nccl.load()) return EDB_ERR_NCCL;
@@ -133,6 +362,9 @@ struct Comm {
     NCK(g_nccl.CommInitRank(&comm, cfg.nranks, id, cfg.rank));
   }
   void destroy() {
+    p2p_close();
+    if (p2p.base) { cudaFree(p2p.base); p2p.base = nullptr; }
+    if (p2p.d_done) { cudaFree(p2p.d_done); p2p.d_done = nullptr; }
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     comm = nullptr;
     for (auto& kv : peers) {

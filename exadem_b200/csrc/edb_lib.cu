@@ -626,7 +626,8 @@ extern "C" int edb_num_particles(edb_context* c, uint64_t* nr, uint64_t* ng) {
 }
 
 // ---- rebuild -----------------------------------------------------------------------------------------------------
-static void ghost_refresh(edb_context* c, bool all) {
+// trig (device, nullable): the local rebuild-trigger count of the step, summed over the ranks in place on the way
+static void ghost_refresh(edb_context* c, bool all, unsigned long long* trig = nullptr) {
   if (c->nghost == 0 && c->cfg.nranks == 1) return;
   ScopedTimer tm(c, B_GHOST);
   const uint32_t nloc = c->comm.n_local_ghost;
@@ -634,7 +635,14 @@ static void ghost_refresh(edb_context* c, bool all) {
     if (all) LAUNCH(c, k_ghost_refresh<true>, nblk(nloc), BLK, 0, view(c->pa), c->g_src.p, c->g_ent.p, c->g_shift.p, c->nreal, nloc, c->cidx.p, c->g_cell.p);
     else LAUNCH(c, k_ghost_refresh<false>, nblk(nloc), BLK, 0, view(c->pa), c->g_src.p, c->g_ent.p, c->g_shift.p, c->nreal, nloc, c->cidx.p, c->g_cell.p);
   }
-  if (c->cfg.nranks > 1) c->comm.exchange_ghosts(view(c->pa), c->nreal, all, c->st, &c->ctr.kernel_launches);
+  if (c->cfg.nranks > 1) {
+    if (!all && c->comm.p2p.on) {
+      c->comm.exchange_ghosts_p2p(view(c->pa), c->nreal, trig, c->st, &c->ctr.kernel_launches);
+    } else {
+      c->comm.exchange_ghosts(view(c->pa), c->nreal, all, c->st, &c->ctr.kernel_launches);
+      if (trig) c->comm.allreduce_sum_u64_dev(trig, c->st);
+    }
+  }
 }
 
 static void compute_vertices(edb_context* c) {
@@ -958,6 +966,7 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
       p.s_h.ensure(p.n_send + 1); p.s_id.ensure(p.n_send + 1);
     }
     c->nghost += base;
+    c->comm.p2p_prepare(base, c->st);
   }
   const uint32_t ntot = n + c->nghost;
   c->pb.ensure(ntot + 1, false, c->st);
@@ -1244,10 +1253,10 @@ extern "C" int edb_displ_over(edb_context* c, double thr, uint64_t* over) {
   API_END(c)
 }
 
-// Rebuild trigger of the step whose prolog has just been enqueued: the count lands in d_sflag[slot] (device, read by the gated
-// kernels of that step) and, reduced over the ranks, in h_sflag[slot] (pinned) once ev_sflag[slot] has completed.
+// Rebuild trigger of a step: the producer (k_gather<2> of the previous step, or k_displ_over) leaves the local count in
+// d_sflag[slot]; the ghost refresh of the step sums it over the ranks in place; trigger_publish copies it to h_sflag[slot]
+// (pinned), valid once ev_sflag[slot] has completed.  The gated kernels of the step read d_sflag[slot] on the device.
 static void trigger_publish(edb_context* c, int slot) {
-  if (c->cfg.nranks > 1) c->comm.allreduce_sum_u64_dev(c->d_sflag + slot, c->st);
   CK(cudaMemcpyAsync(c->h_sflag + slot, c->d_sflag + slot, 8, cudaMemcpyDeviceToHost, c->st));
   CK(cudaEventRecord(c->ev_sflag[slot], c->st));
 }
@@ -1256,7 +1265,6 @@ static void trigger_standalone(edb_context* c, int slot, double thr) {
   CK(cudaMemsetAsync(c->d_sflag + slot, 0, 8, c->st));
   if (c->poly()) LAUNCH(c, k_displ_over<true>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, c->q_backup.p, c->nreal, c->S, thr * thr, c->d_sflag + slot, nullptr);
   else LAUNCH(c, k_displ_over<false>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, nullptr, c->nreal, c->S, thr * thr, c->d_sflag + slot, nullptr);
-  trigger_publish(c, slot);
 }
 
 // The Verlet loop of numerical_scheme_verlet_macro (config_numerical_schemes.msp:6-30).  Per step the device runs
@@ -1294,7 +1302,6 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
       CK(cudaMemsetAsync(c->d_sflag + nslot, 0, 8, c->st));
       gather<2>(c, g, dt, gate, c->d_sflag + nslot, thr);
       if (poly) LAUNCH(c, k_displ_over<true>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, c->q_backup.p, c->nreal, c->S, thr * thr, c->d_sflag + nslot, gate);
-      trigger_publish(c, nslot);
     };
     if (!trig) {
       const bool rb = rebuild_every > 0 && ((it + 1) % rebuild_every) == 0;
@@ -1303,7 +1310,8 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
       step_kernels(nullptr);
     } else {
       const edb_counters snap = c->ctr;
-      ghost_refresh(c, false);
+      ghost_refresh(c, false, c->d_sflag + slot);
+      trigger_publish(c, slot);
       compute_vertices(c);
       step_kernels(c->d_sflag + slot);
       CK(cudaEventSynchronize(c->ev_sflag[slot]));
