@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-poly", action="store_true", help="skip the polyhedra line reported alongside (N=1 only)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -92,6 +93,19 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+    def one_shot(self):
+        """A single synchronous sample (used when the timed region was shorter than the sampling period)."""
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device)],
+                                 capture_output=True, text=True, timeout=10).stdout
+        except Exception:
+            return None
+        f = [x.strip() for x in out.strip().split(",")]
+        try:
+            return float(f[1]), float(f[2])
+        except Exception:
+            return None
 
 
 # ------------------------------------------------------------------------------------------------ workloads
@@ -191,6 +205,39 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def polyhedra_line(lib, peak, device, n=500_000, steps=60, warmup=10):
+    """BASELINE configs[2] reported alongside (north_star): ~500 k octahedra, the vertex/edge/face contact path."""
+    from exadem_b200 import Engine
+    wl = make_workload("poly", n)
+    eng = wl.setup(Engine(lib, wl.config(device=device)))
+    eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)
+    eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, warmup, 0)
+    eng.sync()
+    eng.reset_counters()
+    eng.set_timing(True)
+    eng.event_record(0)
+    nreb = eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, steps, 0)
+    eng.event_record(1)
+    ms = eng.event_elapsed_ms(0, 1)
+    c = eng.counters()
+    counts, active = eng.interaction_counts()
+    eng.reset_counters()
+    eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)
+    eng.sync()
+    reb = eng.counters().rebuild_ms
+    eng.set_timing(False)
+    t = c.contact_pp_ms * 1e-3
+    achieved = c.bytes_contact_algorithmic / t / 1e9 if t > 0 else 0.0
+    eng.close()
+    return {"workload": f"{wl.particles.n} octahedra, periodic packing (configs[2])", "value": c.interaction_updates / (ms * 1e-3),
+            "unit": UNIT, "particle_steps_per_s": c.particle_steps / (ms * 1e-3), "steps": steps, "ms_per_step": ms / steps,
+            "interactions": int(counts.sum()), "active_interactions": int(active.sum()), "rebuilds_in_timed_region": int(nreb),
+            "rebuild_once_ms": reb,
+            "roofline": {"kernel": "k_contact_poly_pp (4 waves)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "note": "algorithmic bytes counted as for spheres (184 B/record + 92 B/particle per wave); vertex reads not counted"},
+            "per_step_ms": {"contact_all": c.contact_ms / steps, "gather_fused": c.gather_ms / steps, "ghost": c.ghost_ms / steps}}
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
@@ -245,6 +292,10 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
+    if rank == 0 and not clocks.get("samples"):
+        shot = sampler.one_shot()
+        if shot:
+            clocks.update({"sm_mhz": shot[0], "sm_max_mhz": shot[1], "samples": 1, "note": "timed region shorter than the sampling period: one sample right after it"})
     c = eng.counters()
     eng.set_timing(False)
     counts, active = eng.interaction_counts()
@@ -292,6 +343,14 @@ def main():
         e2e = {"value": iu_e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ke,
                "ms_per_step": 1e3 * dt / ke}
 
+    # ---- cost of one neighbour rebuild (outside the timed region; the drum moves too slowly to trigger one in K steps)
+    eng.reset_counters()
+    eng.set_timing(True)
+    eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)
+    barrier()
+    rebuild_once_ms = eng.counters().rebuild_ms
+    eng.set_timing(False)
+
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -313,6 +372,11 @@ def main():
             roof["traffic"] = json.loads(prof.read_text()).get(roof["kernel"])
         except Exception:
             pass
+    roof["rebuild_once_ms"] = rebuild_once_ms
+    poly = None
+    if world == 1 and not args.no_poly and (args.workload or "drum") == "drum":
+        eng.close()
+        poly = polyhedra_line(lib, peak, local)
     cpu = None
     if not args.no_cpu_baseline:
         n_sample = min(args.particles, 200_000)
@@ -329,6 +393,8 @@ def main():
                        "l2": "working set (particles + interaction waves) > 126 MB L2, no flush",
                        "timing": "CUDA events on the library stream, max over ranks", "wall_s": wall},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    if poly is not None:
+        line["polyhedra"] = poly
     print(json.dumps(line), flush=True)
 
 

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "kernels_rebuild.cuh"
 #include "kernels_step.cuh"
+#include "kernels_nbh_poly.cuh"
 #include "kernels_migrate.cuh"
 #include "kernels_twin.cuh"
 #include "comm.cuh"
@@ -57,6 +58,7 @@ struct edb_context {
   unsigned long long* h_sflag = nullptr;   // ... pinned host copies
   cudaEvent_t ev_sflag[2] = {};
   int n_sm = 148;
+  size_t smem_optin = 99 * 1024;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
   double rcut_inc = 0;
   int symetric = 1;
   // parameters
@@ -267,7 +269,8 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
     CK(cudaMalloc(&c->d_sflag, 16));
     CK(cudaMallocHost(&c->h_sflag, 16));
     for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&c->ev_sflag[i], cudaEventDisableTiming));
-    { int dev = 0, v = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) c->n_sm = v; }
+    { int dev = 0, v = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) c->n_sm = v;
+      if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && v > 0) c->smem_optin = (size_t)v; }
     CK(cudaMallocHost(&c->h_tot, sizeof(uint32_t) * (NT + 8)));
     for (int d = 0; d < 3; d++)
       if (c->cfg.periodic[d] && c->cfg.pgrid[d] <= 1) {
@@ -1017,10 +1020,35 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
       C.c[t] = c->wave[t].off.p;
     }
   }
-  NbhArgs A{view(c->pa), c->cidx.p, c->cbeg.p, c->cend.p, G, c->drv.p, (int)c->h_drv.size(), rcut_inc, symetric, n, c->vert.p, c->S, c->M};
+  NbhArgs A{view(c->pa), c->cidx.p, c->cbeg.p, c->cend.p, G, c->drv.p, (int)c->h_drv.size(), rcut_inc, symetric, n, c->vert.p, c->S, c->M, 0};
   WTab W{};
+  // polyhedra: the particle-particle waves go through the cell-block kernel (TMA-staged stencil, warp-shared pair tests) when the
+  // largest stencil fits the shared memory of an SM; drivers / meshes stay on the per-particle kernel
+  uint32_t cell_cap = 0;
+  size_t cell_smem = 0;
+  const uint32_t n_real_cells = (uint32_t)G.nc[0] * G.nc[1] * G.nc[2];
+  bool drv_waves = false;
+  for (int t = 4; t < NT; t++) drv_waves = drv_waves || active[t];
+  if (poly && c->S.nvmax <= 32 && !getenv("EDB_NBH_POLY_PER_THREAD")) {
+    CK(cudaMemsetAsync(c->d_flag + 1, 0, 8, c->st));
+    LAUNCH(c, k_stencil_max, nblk(n_real_cells), BLK, 0, G, c->cbeg.p, c->cend.p, c->d_flag + 1);
+    CK(cudaMemcpyAsync(c->h_flag + 1, c->d_flag + 1, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    const uint32_t cap = (uint32_t)c->h_flag[1] + 1;
+    const size_t bytes = (size_t)cap * npc_bytes_per_particle(c->S.nvmax) + 64;
+    if (bytes + 4096 <= c->smem_optin) {
+      cell_cap = cap;
+      cell_smem = bytes;
+      CK(cudaFuncSetAttribute(k_nbh_poly_cell<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      CK(cudaFuncSetAttribute(k_nbh_poly_cell<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+  }
+  A.skip_pp = cell_cap ? 1 : 0;
   if (!poly) LAUNCH(c, k_nbh_sphere<false>, nblk(n, 128), 128, 0, A, C, W);
-  else LAUNCH(c, k_nbh_poly<false>, nblk(n, 64), 64, 0, A, C, W);
+  else {
+    if (cell_cap) LAUNCH(c, k_nbh_poly_cell<false>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap);
+    if (!cell_cap || drv_waves) LAUNCH(c, k_nbh_poly<false>, nblk(n, 64), 64, 0, A, C, W);
+  }
   for (int t = 0; t < NT; t++)
     if (active[t]) {
       scan_u32(c, C.c[t], C.c[t], n);
@@ -1035,7 +1063,10 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
     W.w[t] = view(c->wave[t]);
   }
   if (!poly) LAUNCH(c, k_nbh_sphere<true>, nblk(n, 128), 128, 0, A, C, W);
-  else LAUNCH(c, k_nbh_poly<true>, nblk(n, 64), 64, 0, A, C, W);
+  else {
+    if (cell_cap) LAUNCH(c, k_nbh_poly_cell<true>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap);
+    if (!cell_cap || drv_waves) LAUNCH(c, k_nbh_poly<true>, nblk(n, 64), 64, 0, A, C, W);
+  }
   // 5. history carry-over
   if (had || c->n_imm) {
     const ImmHist H{c->imm_off.p, (const ImmRec*)c->imm_tab.p, c->n_imm};

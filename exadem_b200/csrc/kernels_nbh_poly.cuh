@@ -1,0 +1,295 @@
+// kernels_nbh_poly.cuh — polyhedron candidate enumeration (nbh_polyhedron, src/polyhedron/nbh_polyhedron.cpp:75-384), cell-block
+// version for sm_100a.  This is the expensive kernel of a polyhedron neighbour rebuild: ~420 filter evaluations (V-V, V-E, V-F,
+// E-E in both directions) per pair of octahedra whose enlarged OBBs intersect.
+//
+//   block  = one real cell of the grid; 16 warps.
+//   stage  = the world vertices, positions+radius and orientations of every particle of the 3x3x3 cell stencil are copied into
+//            shared memory by the TMA engine: one cp.async.bulk per (cell, array) — cell-sorted particles make each cell's block
+//            contiguous — completing on one mbarrier.  ids, homothety, shape type and slot follow with ordinary loads.
+//   warp   = one owner particle of the cell at a time.  Lanes scan the stencil 32 candidates at a time (distance + id-order
+//            filter of chunk_neighbors_contact.cpp:46-57 and nbh_polyhedron.cpp:234-236, then the 15-axis OBB test, :268-276);
+//            the survivors are taken in order (ballot), and for each pair the lanes SHARE the pair's filter tests: test index =
+//            base + lane, ballot + popc give every accepted test its place in the owner's record segment, so the records come out
+//            in exactly the order of the reference's nested loops (the gather's summation order depends on it).
+//   passes = FILL=false counts per (owner, wave); after the scan FILL=true repeats the tests and writes the records.
+// All arithmetic is the same dem_math.cuh functions on the same inputs as the per-thread kernel (k_nbh_poly), so membership is
+// bit-identical; only the work distribution changes.
+#pragma once
+#include "kernels_rebuild.cuh"
+
+namespace edb {
+
+constexpr int NPC_THREADS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (16-byte aligned, size multiple of 16)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct SV {  // world-vertex accessor over the staged (shared-memory) copy
+  const double4* p;
+  __device__ __forceinline__ v3 operator[](int i) const {
+    const double4 t = p[i];
+    return mk3(t.x, t.y, t.z);
+  }
+};
+
+__device__ __forceinline__ uint32_t type_of_bits(double w) { return (uint32_t)((unsigned long long)__double_as_longlong(w) & 0xffffffffu); }
+__host__ __device__ inline size_t npc_bytes_per_particle(int nvmax) { return (size_t)nvmax * 32 + 32 + 32 + 8 + 8 + 4 + 4 + 1; }
+
+// max over the real cells of the number of particles in the 3x3x3 stencil (sizes the staging area)
+__global__ void k_stencil_max(GridDev G, const uint32_t* __restrict__ cbeg, const uint32_t* __restrict__ cend, unsigned long long* __restrict__ out) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nreal_cells = (uint32_t)G.nc[0] * G.nc[1] * G.nc[2];
+  unsigned int s = 0;
+  if (c < nreal_cells) {
+    const int ci = c % G.nc[0] + 1, cj = (c / G.nc[0]) % G.nc[1] + 1, ck = c / (G.nc[0] * G.nc[1]) + 1;
+    if (cend[cell_lin(G, ci, cj, ck)] > cbeg[cell_lin(G, ci, cj, ck)])
+      for (int dk = -1; dk <= 1; dk++)
+        for (int dj = -1; dj <= 1; dj++)
+          for (int di = -1; di <= 1; di++) {
+            const uint32_t cb = cell_lin(G, ci + di, cj + dj, ck + dk);   // real cells are 1..nc: the shell always exists
+            s += cend[cb] - cbeg[cb];
+          }
+  }
+  s = __reduce_max_sync(0xffffffffu, s);
+  if ((threadIdx.x & 31) == 0 && s) atomicMax(out, (unsigned long long)s);
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, CntTab C, WTab W, uint32_t cap) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int nvmax = A.S.nvmax;
+  double4* s_vert = reinterpret_cast<double4*>(smem);
+  double4* s_pr = s_vert + (size_t)cap * nvmax;
+  double4* s_q = s_pr + cap;
+  unsigned long long* s_id = reinterpret_cast<unsigned long long*>(s_q + cap);
+  double* s_h = reinterpret_cast<double*>(s_id + cap);
+  uint32_t* s_slot = reinterpret_cast<uint32_t*>(s_h + cap);
+  uint32_t* s_type = s_slot + cap;
+  uint8_t* s_gc = reinterpret_cast<uint8_t*>(s_type + cap);
+  __shared__ unsigned long long s_bar;
+  __shared__ uint32_t s_cbase[28], s_cbeg[27];
+  __shared__ uint8_t s_cgc[27];
+  __shared__ uint16_t s_queue[NPC_THREADS / 32][64];
+
+  const GridDev& G = A.G;
+  const uint32_t c = blockIdx.x;
+  const int ci = c % G.nc[0] + 1, cj = (c / G.nc[0]) % G.nc[1] + 1, ck = c / (G.nc[0] * G.nc[1]) + 1;
+  {
+    const uint32_t lin = cell_lin(G, ci, cj, ck);
+    if (A.cend[lin] == A.cbeg[lin]) return;   // empty cell: nothing to own (uniform for the block)
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = NPC_THREADS / 32;
+
+  // ---- stage the stencil ------------------------------------------------------------------------------------------------
+  if (wid == 0) {
+    if (lane == 0) mbar_init(&s_bar, 1);
+    uint32_t cnt = 0, beg = 0;
+    if (lane < 27) {
+      const int dk = lane / 9 - 1, dj = (lane / 3) % 3 - 1, di = lane % 3 - 1;   // same visiting order as for_each_neighbor
+      const int i = ci + di, j = cj + dj, k = ck + dk;
+      const uint32_t cb = cell_lin(G, i, j, k);
+      beg = A.cbeg[cb];
+      cnt = A.cend[cb] - beg;
+      s_cbeg[lane] = beg;
+      s_cgc[lane] = is_ghost_cell(G, i, j, k) ? 1 : 0;
+    }
+    const uint32_t inc = warp_incl_scan(cnt);
+    if (lane < 27) s_cbase[lane] = inc - cnt;
+    const uint32_t nst = __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 0) {
+      s_cbase[27] = nst;
+      mbar_expect_tx(&s_bar, nst * (uint32_t)(nvmax * 32 + 64));
+    }
+    __syncwarp();
+    if (lane < 27 && cnt) {
+      const uint32_t o = inc - cnt;
+      tma_load_1d(s_vert + (size_t)o * nvmax, A.vert + (size_t)beg * nvmax, cnt * (uint32_t)nvmax * 32u, &s_bar);
+      tma_load_1d(s_pr + o, A.P.pr + beg, cnt * 32u, &s_bar);
+      tma_load_1d(s_q + o, A.P.q + beg, cnt * 32u, &s_bar);
+    }
+  }
+  __syncthreads();
+  const uint32_t nst = s_cbase[27];
+  for (int t = 0; t < 27; t++) {
+    const uint32_t o = s_cbase[t], n = s_cbase[t + 1] - o, beg = s_cbeg[t];
+    for (uint32_t x = threadIdx.x; x < n; x += NPC_THREADS) {
+      const uint32_t slot = beg + x;
+      s_slot[o + x] = slot;
+      s_id[o + x] = A.P.id[slot];
+      s_h[o + x] = A.P.h[slot];
+      s_type[o + x] = type_of_bits(A.P.wg[slot].w);
+      s_gc[o + x] = s_cgc[t];
+    }
+  }
+  mbar_wait(&s_bar, 0);
+  __syncthreads();
+
+  // ---- owners ------------------------------------------------------------------------------------------------------------
+  const double rV = A.rcut_inc;
+  for (uint32_t La = s_cbase[13] + wid; La < s_cbase[14]; La += nwarp) {
+    const uint32_t a = s_slot[La];
+    const double4 ra = s_pr[La], qa4 = s_q[La];
+    const unsigned long long ida = s_id[La];
+    const ShapeDev* __restrict__ psa = A.S.sh + s_type[La];
+    const struct { int nv, ne, nf, e0, f0, fi0; double radius; } sa{psa->nv, psa->ne, psa->nf, psa->e0, psa->f0, psa->fi0, psa->radius};
+    const double ha = s_h[La];
+    const q4 qa{qa4.x, qa4.y, qa4.z, qa4.w};
+    const SV va{s_vert + (size_t)La * nvmax};
+    const double rma = ha * sa.radius;
+    const int* ea = A.S.edges + 2 * sa.e0;
+    uint32_t run[4] = {0, 0, 0, 0};
+    uint32_t base[4] = {0, 0, 0, 0};
+    if (FILL) {
+#pragma unroll
+      for (int t = 0; t < 4; t++) base[t] = C.c[t][a];
+    }
+    // one group of tests of a pair: test index x in [0, N), lanes take x = b0 + lane; accepted tests are written in x order
+    auto group = [&](int t, uint32_t N, auto&& test, auto&& rec) {
+      for (uint32_t b0 = 0; b0 < N; b0 += 32) {
+        const uint32_t x = b0 + lane;
+        const bool ok = x < N && test(x);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (FILL && ok) rec(x, base[t] + run[t] + __popc(m & ((1u << lane) - 1u)));
+        run[t] += __popc(m);
+      }
+    };
+    // Candidates that pass the cheap distance + id-order filter are queued (stencil order kept) and the 15-axis OBB test runs on a
+    // full warp of queued candidates at a time instead of on the one or two lanes of a chunk that happen to be in range.
+    uint16_t* qu = s_queue[wid];
+    uint32_t nq = 0;
+    for (uint32_t ch = 0; ch < nst; ch += 32) {
+      const uint32_t L = ch + lane;
+      bool near = false;
+      if (L < nst && L != La) {
+        const double4 rb = s_pr[L];
+        const v3 d = mk3(rb.x, rb.y, rb.z) - mk3(ra.x, ra.y, ra.z);
+        const double d2 = dot(d, d);
+        const double rmax = ra.w + rb.w + rV;
+        near = d2 > 0.0 && d2 < rmax * rmax && ida < s_id[L];   // ContactNeighborFilterFunc, then nbh_polyhedron.cpp:234-236
+      }
+      const unsigned nm = __ballot_sync(0xffffffffu, near);
+      if (near) qu[nq + __popc(nm & ((1u << lane) - 1u))] = (uint16_t)L;
+      nq += __popc(nm);
+      __syncwarp();
+      const bool last_chunk = ch + 32 >= nst;
+      while (nq >= 32 || (last_chunk && nq > 0)) {
+        const uint32_t take = nq < 32 ? nq : 32;
+        const uint32_t Lc = lane < take ? qu[lane] : 0;
+        bool pass = false;
+        if (lane < take) {
+          const double4 rb = s_pr[Lc], qb4 = s_q[Lc];
+          Obb oi = obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha);
+          Obb oj = obb_world(A.S.sh[s_type[Lc]].obb, mk3(rb.x, rb.y, rb.z), q4{qb4.x, qb4.y, qb4.z, qb4.w}, s_h[Lc]);
+          obb_enlarge(oi, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
+          pass = obb_intersect(oi, oj);
+        }
+        unsigned pm = __ballot_sync(0xffffffffu, pass);
+        const uint32_t rest = nq - take;   // < 32: a chunk adds at most 32 and the queue is drained as soon as it holds 32
+        const uint16_t keep = lane < rest ? qu[take + lane] : (uint16_t)0;
+        __syncwarp();
+        if (lane < rest) qu[lane] = keep;
+        __syncwarp();
+        nq = rest;
+        while (pm) {
+        const int l = __ffs(pm) - 1;
+        pm &= pm - 1;
+        const uint32_t Lb = __shfl_sync(0xffffffffu, Lc, l);   // warp-uniform
+        const uint32_t b = s_slot[Lb];
+        const double4 rb = s_pr[Lb], qb4 = s_q[Lb];
+        const unsigned long long idb = s_id[Lb];
+        const ShapeDev* __restrict__ psb = A.S.sh + s_type[Lb];
+        const struct { int nv, ne, nf, e0, f0, fi0; double radius; } sb{psb->nv, psb->ne, psb->nf, psb->e0, psb->f0, psb->fi0, psb->radius};
+        const double hb = s_h[Lb];
+        const SV vb{s_vert + (size_t)Lb * nvmax};
+        const double rmb = hb * sb.radius;
+        const int* eb = A.S.edges + 2 * sb.e0;
+        // vertex-vs-OBB prefilters, one vertex per lane; the OBBs are enlarged in two half steps like the reference (:268-276, :305-310)
+        unsigned mA, mB;
+        {
+          Obb oj = obb_world(psb->obb, mk3(rb.x, rb.y, rb.z), q4{qb4.x, qb4.y, qb4.z, qb4.w}, hb);
+          obb_enlarge(oj, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
+          mA = __ballot_sync(0xffffffffu, lane < sa.nv && obb_intersect(oj, obb_point(va[lane < sa.nv ? lane : 0], rma)));
+        }
+        {
+          Obb oi = obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha);
+          obb_enlarge(oi, 0.5 * rV); obb_enlarge(oi, 0.5 * rV);
+          mB = __ballot_sync(0xffffffffu, lane < sb.nv && obb_intersect(oi, obb_point(vb[lane < sb.nv ? lane : 0], rmb)));
+        }
+        const uint8_t ghost = s_gc[Lb];
+        const uint8_t f0 = (uint8_t)(ghost << 1), f1 = (uint8_t)(1 | (ghost << 1));
+        auto write = [&](int t, uint32_t k, uint32_t i, uint32_t j, uint32_t si, uint32_t sj, uint8_t flg) {
+          W.w[t].ij[k] = make_uint2(i, j);
+          W.w[t].sub[k] = make_uint2(si, sj);
+          W.w[t].flg[k] = flg;
+          W.w[t].ft[k] = make_double4(0, 0, 0, __longlong_as_double((long long)idb));
+          W.w[t].mo[k] = make_double4(0, 0, 0, 0);
+        };
+        const uint32_t nvb = sb.nv, neb = sb.ne, nfb = sb.nf, nea = sa.ne, nfa = sa.nf;
+        // The vertex-vs-OBB prefilter usually keeps 1-3 of the vertices: the test index space is built over the KEPT vertices only
+        // (n-th set bit of the mask, ascending, so the emission order is unchanged) and the lanes stay busy.
+        const uint32_t nA = __popc(mA), nB = __popc(mB);
+        auto vtxA = [&](uint32_t n) { return (uint32_t)__fns(mA, 0, (int)n + 1); };
+        auto vtxB = [&](uint32_t n) { return (uint32_t)__fns(mB, 0, (int)n + 1); };
+        // A -> B (swap = 0): vertices of a against vertices / edges / faces of b
+        group(0, nA * nvb,
+              [&](uint32_t x) { const uint32_t i = vtxA(x / nvb), j = x % nvb; return filter_vv(rV, va[i], rma, vb[j], rmb); },
+              [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
+        group(1, nA * neb,
+              [&](uint32_t x) { const uint32_t i = vtxA(x / neb), j = x % neb; return filter_ve(rV, va[i], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb); },
+              [&](uint32_t x, uint32_t k) { write(1, k, a, b, vtxA(x / neb), x % neb, f0); });
+        group(2, nA * nfb,
+              [&](uint32_t x) {
+                const uint32_t i = vtxA(x / nfb), j = x % nfb;
+                return filter_vf(rV, va[i], rma, vb, rmb, A.S.fidx + sb.fi0 + A.S.foff[sb.f0 + j], A.S.fn[sb.f0 + j]);
+              },
+              [&](uint32_t x, uint32_t k) { write(2, k, a, b, vtxA(x / nfb), x % nfb, f0); });
+        group(3, nea * neb,
+              [&](uint32_t x) {
+                const uint32_t i = x / neb, j = x % neb;
+                return filter_ee(rV, va[ea[2 * i]], va[ea[2 * i + 1]], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb);
+              },
+              [&](uint32_t x, uint32_t k) { write(3, k, a, b, x / neb, x % neb, f0); });
+        // B -> A (swap = 1): pi = b, pj = a; the owner stays a (interaction_pair.hpp:75-90)
+        group(1, nB * nea,
+              [&](uint32_t x) { const uint32_t j = vtxB(x / nea), i = x % nea; return filter_ve(rV, vb[j], rmb, va[ea[2 * i]], va[ea[2 * i + 1]], rma); },
+              [&](uint32_t x, uint32_t k) { write(1, k, b, a, vtxB(x / nea), x % nea, f1); });
+        group(2, nB * nfa,
+              [&](uint32_t x) {
+                const uint32_t j = vtxB(x / nfa), i = x % nfa;
+                return filter_vf(rV, vb[j], rmb, va, rma, A.S.fidx + sa.fi0 + A.S.foff[sa.f0 + i], A.S.fn[sa.f0 + i]);
+              },
+              [&](uint32_t x, uint32_t k) { write(2, k, b, a, vtxB(x / nfa), x % nfa, f1); });
+        }
+      }
+    }
+    if (!FILL && lane == 0) {
+#pragma unroll
+      for (int t = 0; t < 4; t++) C.c[t][a] = run[t];
+    }
+  }
+}
+
+}  // namespace edb

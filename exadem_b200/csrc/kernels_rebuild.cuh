@@ -241,6 +241,7 @@ struct NbhArgs {
   const double4* vert;  // polyhedra: world vertices
   ShapesView S;
   MeshView M;
+  int skip_pp;   // polyhedra: the particle-particle waves are enumerated by k_nbh_poly_cell (kernels_nbh_poly.cuh)
 };
 
 __device__ __forceinline__ void cell_ijk(const GridDev& G, uint32_t lin, int& i, int& j, int& k) {
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(64) k_nbh_poly(NbhArgs A, CntTab C, WTab W) {
   }
   const double4 qa4 = A.P.q[a];
   const q4 qa{qa4.x, qa4.y, qa4.z, qa4.w};
-  for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
+  if (!A.skip_pp) for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
     const uint64_t idb = A.P.id[b];
     if (ida >= idb) return;  // nbh_polyhedron.cpp:234-236
     const uint8_t ghost = gc ? 1 : 0;
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(64) k_nbh_poly(NbhArgs A, CntTab C, WTab W) {
     }
   });
   if (!FILL) {
-    for (int t = 0; t < 13; t++)
+    for (int t = A.skip_pp ? 4 : 0; t < 13; t++)
       if (C.c[t]) C.c[t][a] = cnt[t];
   }
 }
