@@ -648,12 +648,14 @@ static void ghost_refresh(edb_context* c, bool all, unsigned long long* trig = n
   }
 }
 
-static void compute_vertices(edb_context* c) {
+// ghosts_only: the vertices of the real particles have just been written by k_gather<2> (fused compute_vertices)
+static void compute_vertices(edb_context* c, bool ghosts_only = false) {
   if (!c->poly()) return;
   const uint32_t ntot = c->nreal + c->nghost;
   if (c->S.nvmax <= 0) throw StateError{EDB_ERR_STATE, "polyhedron mode needs edb_set_shapes"};
-  c->vert.ensure((size_t)ntot * c->S.nvmax + 1);
-  LAUNCH(c, k_compute_vertices, nblk(ntot), BLK, 0, view(c->pa), ntot, c->S, c->vert.p);
+  c->vert.ensure((size_t)ntot * c->S.nvmax + 1, true, c->st);
+  const uint32_t first = ghosts_only ? c->nreal : 0;
+  LAUNCH(c, k_compute_vertices, nblk(ntot - first), BLK, 0, view(c->pa), first, ntot, c->S, c->vert.p);
 }
 
 // Per-cell primitive lists of the RShape meshes (host-built, rebuild-frequency; the reference builds them on the host too,
@@ -1246,9 +1248,13 @@ static void gather(edb_context* c, const double* g, double dt, const unsigned lo
   A.dt2 = dt * dt * 0.5;
   A.gate = gate;
   A.next_flag = next_flag;
-  A.pr_backup = (next_flag && !poly) ? c->pr_backup.p : nullptr;
+  A.pr_backup = next_flag ? c->pr_backup.p : nullptr;
+  A.q_backup = (next_flag && poly) ? c->q_backup.p : nullptr;
+  A.S = c->S;
+  A.vert = (FUSE == 2 && poly) ? c->vert.p : nullptr;
   A.thr2 = thr * thr;
-  LAUNCH(c, k_gather<FUSE>, nblk(c->nreal), BLK, 0, A);
+  if (poly) LAUNCH(c, (k_gather<FUSE, true>), nblk(c->nreal), BLK, 0, A);
+  else LAUNCH(c, (k_gather<FUSE, false>), nblk(c->nreal), BLK, 0, A);
   c->ctr.gather_launches++;
 }
 
@@ -1332,18 +1338,17 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
       }
       CK(cudaMemsetAsync(c->d_sflag + nslot, 0, 8, c->st));
       gather<2>(c, g, dt, gate, c->d_sflag + nslot, thr);
-      if (poly) LAUNCH(c, k_displ_over<true>, nblk(c->nreal), BLK, 0, view(c->pa), c->pr_backup.p, c->q_backup.p, c->nreal, c->S, thr * thr, c->d_sflag + nslot, gate);
     };
     if (!trig) {
       const bool rb = rebuild_every > 0 && ((it + 1) % rebuild_every) == 0;
       if (rb) { rebuild(c, rcut_inc, symetric); nb++; }
-      else { ghost_refresh(c, false); compute_vertices(c); }
+      else { ghost_refresh(c, false); compute_vertices(c, it > 0); }
       step_kernels(nullptr);
     } else {
       const edb_counters snap = c->ctr;
       ghost_refresh(c, false, c->d_sflag + slot);
       trigger_publish(c, slot);
-      compute_vertices(c);
+      compute_vertices(c, it > 0);
       step_kernels(c->d_sflag + slot);
       CK(cudaEventSynchronize(c->ev_sflag[slot]));
       if (c->h_sflag[slot] > 0) {

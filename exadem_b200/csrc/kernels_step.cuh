@@ -120,8 +120,8 @@ __global__ void k_freeze(PView P, uint32_t n) {  // freeze_particles.cu:33-88 (w
   P.vm[p] = v; P.wg[p] = w;
 }
 // compute_vertices.hpp:26-67: world vertex k of particle p = r + Q*(h*v_k)  (shape.hpp:259-262)
-__global__ void k_compute_vertices(PView P, uint32_t n, ShapesView S, double4* __restrict__ vert) {
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void k_compute_vertices(PView P, uint32_t first, uint32_t n, ShapesView S, double4* __restrict__ vert) {
+  const uint32_t p = first + blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const double4 r = P.pr[p], Q = P.q[p];
   const ShapeDev sh = S.sh[type_of(P.wg[p])];
@@ -546,6 +546,9 @@ struct GatherArgs {
   // FUSE 2 only: the prolog of the NEXT step and its rebuild trigger
   double dt, dt2;
   const double4* pr_backup;            // positions at the last neighbour build (nullptr: no trigger evaluation)
+  const double4* q_backup;             // polyhedra: orientations at the last build (vertex_displ_over, backup_dem.hpp:66-100)
+  ShapesView S;                        // polyhedra: FUSE 2 also runs compute_vertices for the real particles ...
+  double4* vert;                       // ... into the world-vertex array (nullptr for spheres)
   double thr2;
   unsigned long long* next_flag;       // += number of particles with |r - r_backup|^2 >= thr2 after the next prolog
   const unsigned long long* gate;      // see ContactArgs::gate
@@ -580,7 +583,7 @@ __device__ __forceinline__ void add_wrench(const double4& fd, const double4& cp,
 #define EDB_G_MINB 3
 #endif
 constexpr int GU = EDB_GU;
-template <int FUSE>
+template <int FUSE, bool POLY>
 __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constant__ GatherArgs A) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (gated(A.gate)) return;
@@ -677,9 +680,31 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
   const v3 w2 = mk3(w.x, w.y, w.z) + A.hdt * ar;
   w.x = w2.x; w.y = w2.y; w.z = w2.z;
   st4(A.P.pr + p, rn); st4(A.P.vm + p, vm); st4(A.P.wg + p, w); st4(A.P.q + p, Q);
+  unsigned int over = 0;
+  if (POLY && A.vert) {
+    // polyhedra: compute_vertices (compute_vertices.hpp:26-67) of the step that has just been started, and vertex_displ_over
+    // (vertex_displ_over.cu:74-134) on the same vertices — same expressions as k_compute_vertices / k_displ_over<true>
+    const ShapeDev& sh = A.S.sh[type_of(w)];
+    const double h = A.P.h[p];
+    const q4 qn{Q.x, Q.y, Q.z, Q.w};
+    const bool trig = A.next_flag && A.q_backup;
+    double4 rb = make_double4(0, 0, 0, 0), Qb = make_double4(1, 0, 0, 0);
+    if (trig) { rb = ldg4(A.pr_backup + p); Qb = ldg4(A.q_backup + p); }
+    const q4 qb{Qb.x, Qb.y, Qb.z, Qb.w};
+    const int nv = sh.nv, v0 = sh.v0;
+    for (int k = 0; k < nv; k++) {
+      const v3 lv = h * A.S.verts[v0 + k];
+      const v3 vn = mk3(rn.x, rn.y, rn.z) + qrot(qn, lv);
+      A.vert[(size_t)p * A.S.nvmax + k] = make_double4(vn.x, vn.y, vn.z, 0.0);
+      if (trig) {
+        const v3 vo = mk3(rb.x, rb.y, rb.z) + qrot(qb, lv);
+        const v3 d = vn - vo;
+        over += dot(d, d) >= A.thr2 ? 1u : 0u;
+      }
+    }
+  }
   if (A.next_flag) {   // particle_displ_over (backup_dem.hpp:66-100) for the step that has just been started
-    unsigned int over = 0;
-    if (A.pr_backup) {
+    if (!(POLY && A.vert) && A.pr_backup) {
       const double4 rb = ldg4(A.pr_backup + p);
       const v3 d = mk3(rn.x, rn.y, rn.z) - mk3(rb.x, rb.y, rb.z);
       over = dot(d, d) >= A.thr2 ? 1u : 0u;

@@ -179,6 +179,14 @@ def cube_shape(half=0.3, mink=0.1):
                 volume=side ** 3, inertia_on_mass=(side * side / 6.0,) * 3)
 
 
+def sphere_shape(r=0.3):
+    """A sphere as a one-vertex sphero-polyhedron (how the polyhedron operators carry spheres in mixed decks):
+    src/shape/include/exaDEM/shape/basic_shape/sphere.hpp:14-36 — one vertex at the origin, Minkowski radius r,
+    I/m = 0.5 r^2 and volume `4 / 3 * pi * r^3` evaluated with the integer quotient 4/3 = 1 exactly as the reference writes it."""
+    return dict(vertices=[[0.0, 0.0, 0.0]], edges=[], faces=[], obb=[0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1, r, r, r], radius=r,
+                volume=(4 // 3) * PI * r * r * r, inertia_on_mass=(0.5 * r * r,) * 3)
+
+
 def _rand_quat(rng, n):
     q = rng.normal(size=(n, 4))
     return q / np.linalg.norm(q, axis=1, keepdims=True)
@@ -189,7 +197,7 @@ def polyhedra_box(n_side=(8, 8, 8), seed=0xD3A3, shapes=("octahedron",), pitch=0
     """S3-like: sphero-polyhedra (octahedra and/or cubes) on a jittered SC lattice with random orientations.
     Law parameters: example/polyhedra/rotating_drum/rotating-drum-common.msp:24-29."""
     rng = np.random.default_rng(seed)
-    spec = [OCTAHEDRON if s == "octahedron" else cube_shape() for s in shapes]
+    spec = [OCTAHEDRON if s == "octahedron" else sphere_shape() if s == "sphere" else cube_shape() for s in shapes]
     hi = tuple(float(n) * pitch for n in n_side)
     pos = _lattice((0, 0, 0), hi, pitch)
     n = len(pos)

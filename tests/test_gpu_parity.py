@@ -298,3 +298,25 @@ def test_rshape_mesh_polyhedra(product_lib, oracle_lib):
     fg, mg = gpu.compute_driver_force_moment(1)
     fc, mc = cpu.compute_driver_force_moment(1)
     field_close(fg, fc, 1e-9, "mesh driver forces")
+
+
+def test_mixed_spheres_polyhedra_cohesion_mesh(product_lib, oracle_lib):
+    """BASELINE configs[3] in small: spheres (one-vertex shapes), octahedra and cubes in one polyhedron context, cohesive law,
+    closed STL-like mesh walls (waves 0-3 and 7-12 together)."""
+    wl = workloads.polyhedra_box((6, 6, 5), shapes=("octahedron", "cube", "sphere"), pitch=0.8, cell_size=2.0, seed=0xD3C4)
+    wl.lo, wl.hi = (-2.0, -2.0, -2.0), (7.0, 7.0, 6.0)
+    wl.law = capi.LAW_COHESIVE
+    wl.params = dict(wl.params, fc=0.05, dncut=0.02)
+    wl.params_driver = dict(wl.params_driver, fc=0.02, dncut=0.01)
+    _boxed(wl, (0.1, 0.12, 0.11), (4.7, 4.68, 3.91), 0.03, vrot=(0.0, 0.2, 0.0))
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    cg, _ = gpu.interaction_counts()
+    cc, _ = cpu.interaction_counts()
+    assert np.array_equal(cg, cc) and all(cg[t] > 0 for t in (0, 1, 2, 3, 7, 8, 9)), cg
+    check(gpu, cpu)
+    nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 15, 5) for e in (gpu, cpu)]
+    assert nb[0] == nb[1]
+    check(gpu, cpu)
+    _, ag = gpu.interaction_counts()
+    assert ag[:4].sum() > 0
