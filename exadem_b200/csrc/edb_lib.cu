@@ -53,7 +53,8 @@ struct edb_context {
   bool have_prev = false;
   DevBuf<uint32_t> inc_cnt, inc_off, inc;
   bool have_inc = false;
-  uint32_t* d_need_count = nullptr;  // chunk queue of the persistent contact kernel (kernels_step.cuh)
+  uint32_t* d_need_count = nullptr;  // chunk queue of the persistent sphere contact kernel / length of the polyhedron work list
+  DevBuf<uint32_t> need;             // work list of k_detect_poly_pp -> k_law_poly_pp
   unsigned long long* d_sflag = nullptr;   // rebuild trigger of the speculative step loop (2 slots, device)
   unsigned long long* h_sflag = nullptr;   // ... pinned host copies
   cudaEvent_t ev_sflag[2] = {};
@@ -1186,6 +1187,7 @@ static void launch_contact_waves(edb_context* c, double dt, const unsigned long 
   ContactArgs A{view(c->pa), WView{}, c->prm, c->drv.p, c->vert.p, c->S, dt, 0, c->symetric, c->M, gate};
   const int* order = poly ? ORDER_POLY : ORDER_SPHERE;
   const int norder = poly ? 13 : 7;
+  bool pp_done = false;
   for (int o = 0; o < norder; o++) {
     const int t = order[o];
     Wave& w = c->wave[t];
@@ -1194,8 +1196,20 @@ static void launch_contact_waves(edb_context* c, double dt, const unsigned long 
     A.type = t;
     if (t <= 3) {
       ScopedTimer tpp(c, B_CONTACT_PP);
-      if (poly) LAUNCH(c, k_contact_poly_pp<LAW>, nblk(w.n), BLK, 0, A);
-      else {
+      if (poly) {
+        if (t == order[0] || !pp_done) {   // one detection + one law launch cover the four particle-particle waves
+          PolyWaves PW{};
+          uint32_t tot = 0;
+          for (int q = 0; q < 4; q++) { PW.w[q] = view(c->wave[q]); PW.start[q] = tot; tot += (uint32_t)c->wave[q].n; }
+          PW.start[4] = tot;
+          c->need.ensure((size_t)tot + 1);
+          const NeedList L{c->need.p, c->d_need_count};
+          CK(cudaMemsetAsync(c->d_need_count, 0, 4, c->st));
+          LAUNCH(c, k_detect_poly_pp<LAW>, nblk(tot, BLK * PDPT), BLK, 0, A, PW, L);
+          LAUNCH(c, k_law_poly_pp<LAW>, (uint32_t)std::min<uint64_t>(nblk(tot), (uint64_t)c->n_sm * 2), BLK, 0, A, PW, L);
+          pp_done = true;
+        }
+      } else {
         CK(cudaMemsetAsync(c->d_need_count, 0, 4, c->st));
         LAUNCH(c, k_contact_sphere_pp<LAW>, (uint32_t)std::min<uint64_t>(nblk(w.n, CHUNK * (PP_BLK / 32)), (uint64_t)c->n_sm * PP_MINB), PP_BLK, 0, A, c->d_need_count);
       }

@@ -386,11 +386,22 @@ __device__ __forceinline__ Contact detect_poly_record(const ContactArgs& A, int 
   const int* ej = A.S.edges + 2 * (sj.e0 + sb.y);
   return detect_ee(vi_[ei[0]], vi_[ei[1]], rmi, vj_[ej[0]], vj_[ej[1]], rmj);
 }
-// waves 0..3 of the polyhedron operator: polyhedron::ContactLawFunc<type> (polyhedron/contact.hpp:124-211)
+// waves 0..3 of the polyhedron operator: polyhedron::ContactLawFunc<type> (polyhedron/contact.hpp:124-211).
+// Two launches cover the four waves together (their records form one concatenated index space):
+//   k_detect_poly_pp   light (<= 64 registers, 4 CTAs/SM): detection only, for every record — in a packing ~95 % of the records
+//                      are candidates that do not touch, so this pass IS the cost of the operator.  Records that need the law
+//                      (contact, cohesive range, or HOT: history to reset) are appended, in record order per block, to a list.
+//   k_law_poly_pp      persistent, one list entry per thread and iteration: the full record evaluation on dense warps.
+struct PolyWaves {
+  WView w[4];
+  uint32_t start[5];   // concatenated index space: wave t owns [start[t], start[t+1])
+};
+struct NeedList {
+  uint32_t* ent;       // (wave << 28) | record index
+  uint32_t* count;
+};
 template <int LAW>
-__global__ void __launch_bounds__(BLK) k_contact_poly_pp(ContactArgs A) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= A.w.n || gated(A.gate)) return;
+__device__ __forceinline__ void poly_pp_record(const ContactArgs& A, uint32_t k) {
   const uint2 ij = A.w.ij[k], sb = A.w.sub[k];
   const uint8_t fl = A.w.flg[k];
   const bool hot = fl & FLG_HOT;
@@ -415,6 +426,57 @@ __global__ void __launch_bounds__(BLK) k_contact_poly_pp(ContactArgs A) {
   }
   finish_record<LAW>(A, k, fl, contact, c, cp, meff, reff, mk3(pi.x, pi.y, pi.z), mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z),
                      mk3(pj.x, pj.y, pj.z), mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z), H);
+}
+constexpr int PDPT = 2;   // records per thread of the detection pass
+template <int LAW>
+__global__ void __launch_bounds__(BLK, 4) k_detect_poly_pp(ContactArgs A, PolyWaves PW, NeedList L) {
+  if (gated(A.gate)) return;
+  const uint32_t g0 = (blockIdx.x * BLK + threadIdx.x) * PDPT;
+  uint32_t ent[PDPT];
+  bool need[PDPT];
+#pragma unroll
+  for (int u = 0; u < PDPT; u++) {
+    need[u] = false;
+    const uint32_t g = g0 + u;
+    if (g >= PW.start[4]) continue;
+    const int t = g >= PW.start[2] ? (g >= PW.start[3] ? 3 : 2) : (g >= PW.start[1] ? 1 : 0);
+    const WView& w = PW.w[t];
+    const uint32_t k = g - PW.start[t];
+    ent[u] = ((uint32_t)t << 28) | k;
+    const uint8_t fl = w.flg[k];
+    if (fl & FLG_HOT) { need[u] = true; continue; }
+    const uint2 ij = w.ij[k], sb = w.sub[k];
+    const double4 wi = ldg4(A.P.wg + ij.x), wj = ldg4(A.P.wg + ij.y);
+    const ShapeDev& si = A.S.sh[type_of(wi)];
+    const ShapeDev& sj = A.S.sh[type_of(wj)];
+    const double rmi = A.P.h[ij.x] * si.radius, rmj = A.P.h[ij.y] * sj.radius;
+    const Contact c = detect_poly_record(A, t, ij, sb, si, sj, rmi, rmj);
+    need[u] = c.hit;
+    if (LAW == LAW_COHESIVE) need[u] = need[u] || c.dn <= cp_pp(A.prm, group_of(wi), group_of(wj)).dncut;
+  }
+  uint32_t c = 0;
+#pragma unroll
+  for (int u = 0; u < PDPT; u++) c += need[u] ? 1u : 0u;
+  __shared__ uint32_t s_base;
+  uint32_t tot;
+  uint32_t pos = block_excl_scan(c, &tot);
+  if (threadIdx.x == 0) s_base = tot ? atomicAdd(L.count, tot) : 0u;
+  __syncthreads();
+  pos += s_base;
+#pragma unroll
+  for (int u = 0; u < PDPT; u++)
+    if (need[u]) L.ent[pos++] = ent[u];
+}
+template <int LAW>
+__global__ void __launch_bounds__(BLK, 2) k_law_poly_pp(ContactArgs A, PolyWaves PW, NeedList L) {
+  if (gated(A.gate)) return;
+  const uint32_t cnt = *L.count;
+  for (uint32_t x = blockIdx.x * BLK + threadIdx.x; x < cnt; x += gridDim.x * BLK) {
+    const uint32_t e = L.ent[x];
+    A.type = (int)(e >> 28);
+    A.w = PW.w[e >> 28];
+    poly_pp_record<LAW>(A, e & 0x0fffffffu);
+  }
 }
 
 // detection of an RShape (mesh) driver record, waves 7..12: detect<7..12> (shape_detection_api.hpp:356-406) on the particle
