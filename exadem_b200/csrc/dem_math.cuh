@@ -337,10 +337,14 @@ __device__ __forceinline__ void contact_force(double dn, v3 n, double dt, const 
   v3 branch = cp - pos_i;
   const double r = dot(branch, w_i) / dot(w_i, w_i);       // NaN when w_i == 0 (quirk Q1): keep IEEE semantics
   branch = branch - r * w_i;
-  const double mur = 0;
-  const double thm = fabs(mur * norm(branch) * norm(fn));
+  // The reference hard-codes mur = 0 (contact_force.hpp:229-234):  thm = |0 * norm(branch) * norm(fn)|  is +0 unless one of the
+  // norms is NaN or Inf (quirk Q1: w_i = 0 makes r, hence branch, NaN), in which case it is NaN and `m2 > thm * thm` is false.
+  // With thm = +0 the update is mom * (0 / sqrt(m2)) = mom * (+0) for every m2 > 0.  Evaluated that way — bit-identical,
+  // three square roots and one division fewer per contact.
+  const double nb2 = dot(branch, branch), nf2 = dot(fn, fn);
+  const bool thm_is_zero = nb2 <= 1.7976931348623157e308 && nf2 <= 1.7976931348623157e308;   // false for NaN and +Inf
   const double m2 = dot(mom, mom);
-  if (m2 > 0.0 && m2 > thm * thm) mom = mom * (thm / sqrt(m2));
+  if (thm_is_zero && m2 > 0.0) mom = mom * 0.0;
 }
 EDB_HD v3 moments(v3 cp, v3 p, v3 f, v3 m) { return cross(cp - p, f) + m; }  // common_kernels.hpp:137-145
 

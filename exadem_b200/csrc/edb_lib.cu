@@ -53,6 +53,7 @@ struct edb_context {
   bool have_prev = false;
   DevBuf<uint32_t> inc_cnt, inc_off, inc;
   bool have_inc = false;
+  bool queue_clean = false;   // d_need_count is zero (left so by k_gather<2>)
   uint32_t* d_need_count = nullptr;  // chunk queue of the persistent sphere contact kernel / length of the polyhedron work list
   DevBuf<uint32_t> need;             // work list of k_detect_poly_pp -> k_law_poly_pp
   unsigned long long* d_sflag = nullptr;   // rebuild trigger of the speculative step loop (2 slots, device)
@@ -1182,9 +1183,12 @@ extern "C" int edb_freeze_particles(edb_context* c) {
 
 
 template <int LAW>
-static void launch_contact_waves(edb_context* c, double dt, const unsigned long long* gate) {
+static void launch_contact_waves(edb_context* c, double dt, const unsigned long long* gate, unsigned long long* zero_flag) {
   const bool poly = c->poly();
-  ContactArgs A{view(c->pa), WView{}, c->prm, c->drv.p, c->vert.p, c->S, dt, 0, c->symetric, c->M, gate};
+  ContactArgs A{view(c->pa), WView{}, c->prm, c->drv.p, c->vert.p, c->S, dt, 0, c->symetric, c->M, gate, zero_flag};
+  // the gather of the previous step left the chunk queue at zero when it ran as k_gather<2>; otherwise it is cleared here
+  const bool queue_clean = c->queue_clean;
+  c->queue_clean = false;
   const int* order = poly ? ORDER_POLY : ORDER_SPHERE;
   const int norder = poly ? 13 : 7;
   bool pp_done = false;
@@ -1210,7 +1214,7 @@ static void launch_contact_waves(edb_context* c, double dt, const unsigned long 
           pp_done = true;
         }
       } else {
-        CK(cudaMemsetAsync(c->d_need_count, 0, 4, c->st));
+        if (!queue_clean) CK(cudaMemsetAsync(c->d_need_count, 0, 4, c->st));
         LAUNCH(c, k_contact_sphere_pp<LAW>, (uint32_t)std::min<uint64_t>(nblk(w.n, CHUNK * (PP_BLK / 32)), (uint64_t)c->n_sm * PP_MINB), PP_BLK, 0, A, c->d_need_count);
       }
       c->ctr.contact_pp_launches++;
@@ -1230,12 +1234,17 @@ static void launch_contact_waves(edb_context* c, double dt, const unsigned long 
   }
 }
 
-static void contact_waves(edb_context* c, double dt, const unsigned long long* gate = nullptr) {
+// zero_flag: returns through *zeroed whether a launched kernel clears it (spheres with a wave-0 launch); else the caller memsets
+static void contact_waves(edb_context* c, double dt, const unsigned long long* gate = nullptr, unsigned long long* zero_flag = nullptr,
+                          bool* zeroed = nullptr) {
   ScopedTimer tm(c, B_CONTACT);
   if (!c->have_prev) throw StateError{EDB_ERR_STATE, "contact operator before update_particle_neighbors"};
-  if (c->law == 0) launch_contact_waves<0>(c, dt, gate);
-  else if (c->law == 1) launch_contact_waves<1>(c, dt, gate);
-  else launch_contact_waves<2>(c, dt, gate);
+  const bool can_zero = zero_flag && !c->poly() && c->wave[0].n > 0;   // (a gated-off step neither zeroes nor accumulates)
+  if (zeroed) *zeroed = can_zero;
+  unsigned long long* zf = can_zero ? zero_flag : nullptr;
+  if (c->law == 0) launch_contact_waves<0>(c, dt, gate, zf);
+  else if (c->law == 1) launch_contact_waves<1>(c, dt, gate, zf);
+  else launch_contact_waves<2>(c, dt, gate, zf);
 }
 
 // next_flag (FUSE 2 only): where the rebuild trigger of the next step is accumulated (nullptr: not evaluated)
@@ -1262,6 +1271,8 @@ static void gather(edb_context* c, const double* g, double dt, const unsigned lo
   A.dt2 = dt * dt * 0.5;
   A.gate = gate;
   A.next_flag = next_flag;
+  A.reset_queue = (FUSE == 2 && !poly) ? c->d_need_count : nullptr;
+  if (A.reset_queue) c->queue_clean = true;
   A.pr_backup = next_flag ? c->pr_backup.p : nullptr;
   A.q_backup = (next_flag && poly) ? c->q_backup.p : nullptr;
   A.S = c->S;
@@ -1341,7 +1352,8 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
     const bool last = it + 1 == nsteps;
     const int slot = it & 1, nslot = slot ^ 1;
     auto step_kernels = [&](const unsigned long long* gate) {
-      contact_waves(c, dt, gate);
+      bool zeroed = false;
+      contact_waves(c, dt, gate, (!last && trig) ? c->d_sflag + nslot : nullptr, &zeroed);
       if (last) {
         gather<1>(c, g, dt, gate);
         return;
@@ -1350,7 +1362,7 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
         gather<2>(c, g, dt, gate);
         return;
       }
-      CK(cudaMemsetAsync(c->d_sflag + nslot, 0, 8, c->st));
+      if (!zeroed) CK(cudaMemsetAsync(c->d_sflag + nslot, 0, 8, c->st));
       gather<2>(c, g, dt, gate, c->d_sflag + nslot, thr);
     };
     if (!trig) {
@@ -1371,6 +1383,7 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
         c->ctr.kernel_launches = launches;
         rebuild(c, rcut_inc, symetric);
         nb++;
+        c->queue_clean = false;   // the gated-off gather did not clear the chunk queue
         step_kernels(nullptr);
       }
     }

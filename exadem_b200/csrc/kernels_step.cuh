@@ -178,6 +178,7 @@ struct ContactArgs {
   MeshView M;
   // speculative step (edb_run_verlet): non-zero *gate = "this step needs a neighbour rebuild first" -> the kernel does nothing
   const unsigned long long* gate;
+  unsigned long long* zero_flag;   // spheres, speculative loop: the next trigger slot, zeroed by the wave-0 kernel (saves a memset)
 };
 __device__ __forceinline__ bool gated(const unsigned long long* gate) { return gate && *gate; }
 
@@ -258,6 +259,7 @@ constexpr int PP_BLK = EDB_PP_BLK, PP_MINB = EDB_PP_MINB;   // tuning knobs of t
 template <int LAW>
 __global__ void __launch_bounds__(PP_BLK, PP_MINB) k_contact_sphere_pp(ContactArgs A, uint32_t* __restrict__ queue) {
   if (gated(A.gate)) return;
+  if (A.zero_flag && blockIdx.x == 0 && threadIdx.x == 0) *A.zero_flag = 0;   // trigger accumulator of the gather that follows
   __shared__ uint4 s_ent[PP_BLK / 32][CHUNK];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint4* ents = s_ent[wid];
@@ -614,6 +616,7 @@ struct GatherArgs {
   double thr2;
   unsigned long long* next_flag;       // += number of particles with |r - r_backup|^2 >= thr2 after the next prolog
   const unsigned long long* gate;      // see ContactArgs::gate
+  uint32_t* reset_queue;               // FUSE 2: zeroed for the next step's k_contact_sphere_pp (saves a memset per step)
 };
 
 // role_i: particle acts as "i" of the record: F += f, M += (cp - r) x f + mom;  as "j": F += -f, M += (cp - r) x (-f) + (-mom)
@@ -667,34 +670,35 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
     F = mk3(A.P.fx[p], A.P.fy[p], A.P.fz[p]);
     M = mk3(A.P.mx[p], A.P.my[p], A.P.mz[p]);
   }
+  if (FUSE == 2) {   // the operands of the epilog / prolog tail: pulled into L2 now, read after the loop
+    prefetch_l2(A.P.wg + p); prefetch_l2(A.P.q + p);
+    if ((threadIdx.x & 3) == 0) { prefetch_l2(A.P.ix + p); prefetch_l2(A.P.iy + p); prefetch_l2(A.P.iz + p); }
+    if (A.next_flag && A.pr_backup) prefetch_l2(A.pr_backup + p);
+    if (p == 0 && A.reset_queue) *A.reset_queue = 0;   // chunk queue of the next step's contact kernel
+  }
   for (uint32_t e = e0; e < e1; e += GU) {
     uint32_t code[GU];
-    const WView* w[GU];
     uint8_t fl[GU];
-#pragma unroll
-    for (int u = 0; u < GU; u++) w[u] = &A.W.w[0];
     double4 fd[GU], cp[GU];
 #pragma unroll
     for (int u = 0; u < GU; u++) code[u] = (e + u < e1) ? A.inc[e + u] : 0xffffffffu;
 #pragma unroll
     for (int u = 0; u < GU; u++) {
       fl[u] = 0;
-      if (code[u] != 0xffffffffu) {
-        w[u] = &A.W.w[A.order[code[u] >> INC_SHIFT]];
-        fl[u] = w[u]->flg[code[u] & INC_MASK];
-      }
+      if (code[u] != 0xffffffffu) fl[u] = A.W.w[A.order[code[u] >> INC_SHIFT]].flg[code[u] & INC_MASK];
     }
 #pragma unroll
     for (int u = 0; u < GU; u++)
       if (fl[u] & FLG_HOT) {
-        fd[u] = ld4(w[u]->fd + (code[u] & INC_MASK));
-        cp[u] = ld4(w[u]->cp + (code[u] & INC_MASK));
+        const WView& w = A.W.w[A.order[code[u] >> INC_SHIFT]];
+        fd[u] = ld4(w.fd + (code[u] & INC_MASK));
+        cp[u] = ld4(w.cp + (code[u] & INC_MASK));
       }
 #pragma unroll
     for (int u = 0; u < GU; u++)
       if (fl[u] & FLG_HOT) {
         const uint32_t o = code[u] >> INC_SHIFT, k = code[u] & INC_MASK;
-        const double4 mo = (fl[u] & FLG_MOM) ? ld4(w[u]->mo + k) : make_double4(0, 0, 0, 0);
+        const double4 mo = (fl[u] & FLG_MOM) ? ld4(A.W.w[A.order[o]].mo + k) : make_double4(0, 0, 0, 0);
         bool role_i;
         if ((int)o < A.npp) {
           const uint32_t a = o == 0 ? oa[0] : o == 1 ? oa[1] : o == 2 ? oa[2] : oa[3];
