@@ -352,6 +352,14 @@ class Engine:
         self._call("compute_driver_force_moment", _as(f, _D), _as(m, _D))
         return f, m
 
+    def stress_tensor(self):
+        """[stress_tensor] per-particle 3x3 sum of f (x) (cp - r) over the contacts of the last step, upload order."""
+        nr = C.c_uint64()
+        self.lib.fn("num_particles")(self.h, C.byref(nr), None)
+        out = np.zeros((nr.value, 3, 3))
+        self._call("stress_tensor", _as(out, _D))
+        return out
+
     def run_verlet(self, dt, g, rcut_inc, symetric, nsteps, rebuild_every=0) -> int:
         nb = C.c_uint64()
         self._call("run_verlet", C.c_double(dt), (C.c_double * 3)(*g), C.c_double(rcut_inc),

@@ -1583,8 +1583,21 @@ extern "C" int edb_compute_driver_force_moment(edb_context* c, double* forces, d
 
 extern "C" int edb_stress_tensor(edb_context* c, double* stress9) {
   API_BEGIN(c)
-  (void)stress9;
-  throw StateError{EDB_ERR_STATE, "stress_tensor: not built yet (SURVEY 8f rank 2)"};
+  if (!c->have_inc) throw StateError{EDB_ERR_STATE, "stress_tensor before update_particle_neighbors"};
+  const bool poly = c->poly();
+  GatherArgs A{};
+  A.P = view(c->pa);
+  for (int t = 0; t < NT; t++) A.W.w[t] = view(c->wave[t]);
+  const int* order = poly ? ORDER_POLY : ORDER_SPHERE;
+  A.norder = poly ? 13 : 7;
+  for (int o = 0; o < A.norder; o++) A.order[o] = order[o];
+  A.inc_off = c->inc_off.p;
+  A.inc = c->inc.p;
+  A.nreal = c->nreal;
+  c->stage.ensure((size_t)c->nreal * 9 + 1);
+  LAUNCH(c, k_stress, nblk(c->nreal), BLK, 0, A, c->stage.p);
+  CK(cudaMemcpyAsync(stress9, c->stage.p, (size_t)c->nreal * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
   API_END(c)
 }
 

@@ -780,6 +780,41 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
   }
 }
 
+// stress_tensor (src/interaction/stress_tensor.cu:41-81): per particle, sum over the records in contact (dn < 0) of
+// tensor(fij, cp - r_i) on the i side and, for the particle-particle waves, tensor(-fij, cp - r_j) on the j side, with
+// fij = fn + ft of the ContactState.  One thread per real particle walks its incidence list (fixed order -> reproducible, no
+// atomics; the reference uses mat3d_atomic_add_contribution).  out: 9 doubles per particle, row-major, indexed by orig[p].
+__global__ void __launch_bounds__(BLK) k_stress(GatherArgs A, double* __restrict__ out) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= A.nreal) return;
+  const double4 pr = ldg4(A.P.pr + p);
+  const v3 r = mk3(pr.x, pr.y, pr.z);
+  double S[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const uint32_t e1 = A.inc_off[p + 1];
+  for (uint32_t e = A.inc_off[p]; e < e1; e++) {
+    const uint32_t code = A.inc[e], o = code >> INC_SHIFT, k = code & INC_MASK;
+    const int t = A.order[o];
+    const WView& w = A.W.w[t];
+    const uint8_t fl = w.flg[k];
+    if (!(fl & FLG_HOT)) continue;
+    const double4 fd = ld4(w.fd + k);
+    if (!(fd.w < 0.0)) continue;
+    const double4 f4 = ld4(w.ft + k), c4 = ld4(w.cp + k);
+    const v3 ft = mk3(f4.x, f4.y, f4.z);
+    // ContactState fn as the reference stores it (contact_sphere.hpp:180; contact.hpp:409 for the "j to i" mesh waves)
+    const v3 fn = (t == 11 || t == 12) ? (-ft) - mk3(fd.x, fd.y, fd.z) : mk3(fd.x, fd.y, fd.z) - ft;
+    v3 fij = fn + ft;
+    if (t <= 3 && w.ij[k].x != p) fij = -fij;   // this particle is the j of the record
+    const v3 c = mk3(c4.x, c4.y, c4.z) - r;
+    S[0] += fij.x * c.x; S[1] += fij.x * c.y; S[2] += fij.x * c.z;
+    S[3] += fij.y * c.x; S[4] += fij.y * c.y; S[5] += fij.y * c.z;
+    S[6] += fij.z * c.x; S[7] += fij.z * c.y; S[8] += fij.z * c.z;
+  }
+  double* dst = out + (size_t)A.P.orig[p] * 9;
+#pragma unroll
+  for (int q = 0; q < 9; q++) dst[q] = S[q];
+}
+
 // compute_driver_force_moment.cu:34-54 — per-driver sum of -(fn+ft) and of (cp - center) x (-(fn+ft)) - moment over the driver waves.
 // Deterministic: one block per driver wave chunk writes a partial; partials are summed in order on the host side buffer.
 __global__ void __launch_bounds__(BLK) k_driver_force(WView w, int type, const Driver* __restrict__ drv, int ndrv, double* __restrict__ partial) {

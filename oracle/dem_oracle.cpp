@@ -898,6 +898,28 @@ int orc_compute_driver_force_moment(orc_sim* h, double* forces, double* moments)
   return 0;
 }
 
+// stress_tensor.cu:41-81 (wave loop from NTypes-1 down to 0, :117-120): records with dn < 0 add tensor(fn + ft, cp - r_i) to
+// particle i and, for the particle-particle waves, tensor(-(fn + ft), cp - r_j) to particle j; shares of ghost copies are dropped
+int orc_stress_tensor(orc_sim* h, double* out) {
+  Sim& s = *(Sim*)h;
+  for (size_t q = 0; q < 9 * s.nreal; q++) out[q] = 0.0;
+  auto add = [&](uint32_t p, v3 f, v3 c) {
+    double* S = out + 9 * (size_t)p;
+    S[0] += f.x * c.x; S[1] += f.x * c.y; S[2] += f.x * c.z;
+    S[3] += f.y * c.x; S[4] += f.y * c.y; S[5] += f.y * c.z;
+    S[6] += f.z * c.x; S[7] += f.z * c.y; S[8] += f.z * c.z;
+  };
+  for (int t = EDB_NTYPES - 1; t >= 0; t--)
+    for (uint32_t k : s.wave[t]) {
+      const Inter& I = s.inter[k];
+      if (!(I.dn < 0.0)) continue;
+      const v3 fij = I.fn + I.ft;
+      if (I.i < s.nreal && !(I.foreign && I.swap) && !(I.drop_owner && !I.swap)) add(I.i, fij, I.cp - s.r[I.i]);
+      if (t <= 3 && I.j < s.nreal && !(I.foreign && !I.swap) && !(I.drop_owner && I.swap)) add(I.j, -fij, I.cp - s.r[I.j]);
+    }
+  return 0;
+}
+
 int orc_run_verlet(orc_sim* h, double dt, const double* g, double rcut_inc, int32_t symetric, int32_t nsteps, int32_t rebuild_every, uint64_t* n_rebuilds) {
   Sim& s = *(Sim*)h;
   uint64_t nb = 0;

@@ -320,3 +320,21 @@ def test_mixed_spheres_polyhedra_cohesion_mesh(product_lib, oracle_lib):
     check(gpu, cpu)
     _, ag = gpu.interaction_counts()
     assert ag[:4].sum() > 0
+
+
+@pytest.mark.parametrize("kind", ["drum", "poly"])
+def test_stress_tensor(product_lib, oracle_lib, kind):
+    """stress_tensor: per-particle sum of (fn + ft) (x) (cp - r) over the contacts of the step, on the device from the
+    resident contact state (no host copy of the waves), against the oracle's restatement of stress_tensor.cu:41-81."""
+    if kind == "drum":
+        wl = workloads.rotating_drum(6000, jitter=0.02)
+    else:
+        wl = workloads.polyhedra_box((6, 6, 6), shapes=("octahedron", "cube"), pitch=0.78, cell_size=2.0)
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    both((gpu, cpu), lambda e: e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 8, -1))
+    sg, sc = gpu.stress_tensor(), cpu.stress_tensor()
+    assert sg.shape == sc.shape and np.abs(sc).max() > 0
+    field_close(sg.ravel(), sc.ravel(), RTOL, "stress tensor")
+    # total stress is symmetric in exchange of i and j up to the contact-point lever arms: trace of the sum equals sum f.(cp-r)
+    assert np.isfinite(sg).all()

@@ -116,3 +116,52 @@ def test_process_grid():
         pg = parallel.process_grid(n)
         assert sorted(parallel.rank_coords(r, pg) for r in range(n)) == sorted(
             (x, y, z) for z in range(pg[2]) for y in range(pg[1]) for x in range(pg[0]))
+
+
+def _drum_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wl = parallel.drum_slab_workload(3000, rank, world)
+        assert wl.pgrid == (1, world, 1) and wl.periodic == (0, 1, 0)
+        L = wl.hi[1] - wl.lo[1]
+        # slabs tile the long drum along its axis; ids are globally unique; every slab holds the N=1 particle count
+        r = wl.particles.vec("r")
+        assert wl.lo[1] <= r[:, 1].min() and r[:, 1].max() < wl.hi[1]
+        info = [None] * world
+        dist.all_gather_object(info, {"lo": wl.lo, "hi": wl.hi, "ghi": wl.ghi, "n": wl.particles.n, "id": wl.particles.id})
+        assert all(abs(info[k]["lo"][1] - k * L) < 1e-12 and abs(info[k]["hi"][1] - (k + 1) * L) < 1e-12 for k in range(world))
+        assert all(i["ghi"] == wl.ghi and abs(wl.ghi[1] - world * L) < 1e-12 for i in info)
+        assert len({i["n"] for i in info}) == 1
+        allid = np.concatenate([i["id"] for i in info])
+        assert len(np.unique(allid)) == len(allid)
+        # ghost plan of a slab: only the two axis neighbours (one and the same peer when world == 2), periodic wrap at the ends
+        nc, _ = parallel.grid_dims(wl.lo, wl.hi, wl.cell_size)
+        rp = parallel.recv_plan(wl.glo, wl.ghi, wl.periodic, wl.pgrid, rank, nc)
+        sp = parallel.send_plan(wl.glo, wl.ghi, wl.periodic, wl.pgrid, rank, nc)
+        assert set(rp) == {(rank - 1) % world, (rank + 1) % world} == set(sp)
+        plans = [None] * world
+        dist.all_gather_object(plans, {"send": sp, "recv": rp})
+        for other in rp:
+            assert plans[other]["send"].get(rank, []) == rp[other]
+        shifts = {sh[1] for ent in rp.values() for (_, _, sh) in ent}
+        assert shifts <= {0.0, wl.ghi[1], -wl.ghi[1]} and (rank not in (0, world - 1) or len(shifts) == 2 or world == 1)
+        ret[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_drum_slab_decomposition_gloo(world):
+    """The N>1 bench workload (BASELINE configs[1] cut into N slabs along the drum axis): tiling, ids, ghost/send plans."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_drum_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    for p_ in procs:
+        p_.join(timeout=300)
+    assert all(p_.exitcode == 0 for p_ in procs), [p_.exitcode for p_ in procs]
+    assert len(ret) == world
