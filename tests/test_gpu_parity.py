@@ -338,3 +338,39 @@ def test_stress_tensor(product_lib, oracle_lib, kind):
     field_close(sg.ravel(), sc.ravel(), RTOL, "stress tensor")
     # total stress is symmetric in exchange of i and j up to the contact-point lever arms: trace of the sum equals sum f.(cp-r)
     assert np.isfinite(sg).all()
+
+
+@pytest.mark.parametrize("kind", ["drum", "poly"])
+def test_checkpoint_restart(product_lib, oracle_lib, kind):
+    """the interaction history leaves and re-enters the device in the reference's 104-byte `Interaction`
+    record layout (the payload of write_dump_particle_interaction): run -> export + download -> FRESH context -> upload + import ->
+    rebuild -> continue must equal the uninterrupted run bit for bit, and the oracle taken through the same restart."""
+    if kind == "drum":
+        wl = workloads.rotating_drum(5000, jitter=0.02)
+    else:
+        wl = workloads.polyhedra_box((6, 6, 6), shapes=("octahedron", "cube"), pitch=0.78, cell_size=2.0)
+
+    def run(lib, cls, restart):
+        e = wl.setup(cls(lib, wl.config()))
+        e.update_particle_neighbors(wl.rcut_inc, True)
+        e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 10, -1)
+        e.update_particle_neighbors(wl.rcut_inc, True)     # a dump is written right after a rebuild (config_iteration_dump.msp:68-86)
+        if restart:
+            pa, rec = e.download_particles(), e.export_interactions()
+            assert (np.abs(rec["friction"]).sum(axis=1) > 0).any()
+            e.close()
+            e = wl.setup(cls(lib, wl.config()))
+            e.upload_particles(pa)
+            e.import_interactions(rec)
+            e.update_particle_neighbors(wl.rcut_inc, True)
+        e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 10, -1)
+        return e
+
+    g0, g1 = run(product_lib, Engine, False), run(product_lib, Engine, True)
+    c1 = run(oracle_lib, OracleEngine, True)
+    p0, p1 = g0.download_particles(), g1.download_particles()
+    o0, o1 = np.argsort(p0.id), np.argsort(p1.id)
+    for f in capi.F64_FIELDS:
+        assert np.array_equal(getattr(p0, f)[o0], getattr(p1, f)[o1]), f
+    compare_interaction_sets(g0.export_interactions(), g1.export_interactions(), payload_rtol=0.0)
+    check(g1, c1)
