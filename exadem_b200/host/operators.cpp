@@ -148,6 +148,37 @@ class DisplOver : public OperatorNode {
   }
 };
 
+// src/interaction/stress_tensor.cu:142-178 — per-particle virial from the resident contact state; result in slot `stress`
+class StressTensor : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT_OUTPUT, REQUIRED);
+  ADD_SLOT(std::vector<double>, stress, OUTPUT, DocString{"9 doubles per particle, row-major, upload order"});
+ public:
+  std::string documentation() const final { return "This operator computes the total stress tensor and the stress tensor for each particles."; }
+  void execute() final {
+    uint64_t nr = 0;
+    ck(*grid, edb_num_particles(grid->ctx, &nr, nullptr), "stress_tensor");
+    std::vector<double> out(9 * nr);
+    ck(*grid, edb_stress_tensor(grid->ctx, out.data()), "stress_tensor");
+    stress.set(std::move(out));
+  }
+};
+// src/interaction/compute_driver_force_moment.cu:79-146 — results in slots `driver_forces` / `driver_moments` (3 doubles per driver)
+class ComputeDriverForceMoment : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT_OUTPUT, REQUIRED);
+  ADD_SLOT(double, n_drivers, INPUT, REQUIRED);
+  ADD_SLOT(std::vector<double>, driver_forces, OUTPUT);
+  ADD_SLOT(std::vector<double>, driver_moments, OUTPUT);
+ public:
+  std::string documentation() const final { return "Reduces -(fn+ft) and the torque about the driver centre over the driver waves of the classifier."; }
+  void execute() final {
+    const size_t nd = (size_t)*n_drivers;
+    std::vector<double> f(3 * nd), m(3 * nd);
+    ck(*grid, edb_compute_driver_force_moment(grid->ctx, f.data(), m.data()), "compute_driver_force_moment");
+    driver_forces.set(std::move(f));
+    driver_moments.set(std::move(m));
+  }
+};
+
 }  // namespace exaDEM
 
 // === register factories (same names as the reference's ONIKA_AUTORUN_INIT blocks) ===
@@ -157,7 +188,11 @@ ONIKA_AUTORUN_INIT(exadem_b200_hot_path) {
   f->register_factory("chunk_neighbors_contact", make_simple_operator<ChunkNeighborsContact>);
   f->register_factory("nbh_sphere", make_simple_operator<UpdateContactInteractionSphere>);
   f->register_factory("nbh_polyhedron", make_simple_operator<UpdateGridCellInteractionPolyhedron>);
-  for (const char* n : {"classify_interactions", "unclassify_interactions", "compress_interaction", "update_interaction_ghost", "update_traversals"})
+  f->register_factory("stress_tensor", make_simple_operator<StressTensor>);
+  f->register_factory("compute_driver_force_moment", make_simple_operator<ComputeDriverForceMoment>);
+  // bookkeeping operators of update_particles_full (config_move_particles.msp:141-154) that the device layout makes implicit
+  for (const char* n : {"classify_interactions", "unclassify_interactions", "compress_interaction", "update_interaction_ghost", "update_traversals",
+                        "backup_dem", "backup_r", "migrate_cell_particles_interaction", "move_particles_interaction"})
     f->register_factory(n, make_simple_operator<DeviceImplicit>);
   // src/sphere/CMakeLists.txt:62-107
   f->register_factory("contact_sphere", make_simple_operator<ComputeContactClassifier<false, false, 0>>);
@@ -230,6 +265,15 @@ void edbh_set_multimat(edbh_graph* g, int n_groups, const edb_contact_params* pp
   m.pp.assign(pp, pp + n_groups * n_groups);
   m.pd.assign(pd, pd + n_groups * n_drivers);
   g->put("multimat_cp", m);
+}
+// copies a std::vector<double> slot (e.g. `stress`, `driver_forces`) out; returns its length, or -1 when absent
+long long edbh_get_doubles(edbh_graph* g, const char* name, double* out, long long cap) {
+  auto it = g->pool.find(name);
+  if (it == g->pool.end() || !it->second->has_value()) return -1;
+  const auto* v = std::any_cast<std::vector<double>>(it->second.get());
+  if (!v) return -1;
+  if (out) memcpy(out, v->data(), sizeof(double) * (size_t)std::min<long long>(cap, (long long)v->size()));
+  return (long long)v->size();
 }
 int edbh_get_bool(edbh_graph* g, const char* name, int* out) {
   auto it = g->pool.find(name);
