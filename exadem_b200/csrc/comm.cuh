@@ -170,9 +170,21 @@ struct LandArgs {
   unsigned long long* count;        // in: local trigger count, out: sum over the ranks (nullptr: not reduced)
   const double4* land;              // landing zone of this parity
   uint32_t cap, n, base;            // n remote ghosts -> slots [base, base + n)
+  // fused push (k_gather<2> stored the ghosts): this launch also SENDS our mail, before it waits for the others'.  The gather has
+  // completed (stream order), a system-scope fence by the mailing threads then orders its peer stores before the mail.
+  unsigned long long* out_mail[P2P_MAXR];
+  int n_out;
 };
 __global__ void __launch_bounds__(BLK) k_ghost_land(const __grid_constant__ LandArgs A) {
   __shared__ unsigned long long s_cnt[P2P_MAXR];
+  if (blockIdx.x == 0 && (int)threadIdx.x < A.n_out) {
+    unsigned long long c = A.count ? *(volatile const unsigned long long*)A.count : 0ull;
+    if (c > 0xffffffffull) c = 0xffffffffull;
+    const unsigned long long v = ((unsigned long long)A.epoch << 32) | c;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.out_mail[threadIdx.x]), "l"(v) : "memory");
+  }
+  __syncthreads();   // (block 0: the local count has been read before thread 0 overwrites it with the sum below)
   if ((int)threadIdx.x < A.nranks) {
     unsigned long long v = 0;
     if ((int)threadIdx.x != A.me) {
@@ -199,6 +211,63 @@ __global__ void __launch_bounds__(BLK) k_ghost_land(const __grid_constant__ Land
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Ghost fan-out fused into the gather (k_gather<2>, kernels_step.cuh): every real particle that has images — periodic images in
+// the own brick and/or copies in neighbouring bricks — carries a list of destinations; the thread that has just finished the
+// particle's prolog stores the four refreshed sectors to each of them from its registers (own ghost slots, or the neighbours'
+// landing zones over NVLink).  The mail {epoch, trigger count} is sent by the k_ghost_land launch that follows in the stream.  Per
+// step this removes the ghost-refresh / push launches and overlaps the NVLink traffic with the rest of the gather.
+// ---------------------------------------------------------------------------------------------------------------
+struct FanEnt {
+  double sx, sy, sz;   // shift added to the position
+  uint32_t dst;        // peer < 0: ghost slot in the own arrays;  peer >= 0: index inside that peer's landing range
+  int32_t peer;        // index into FanArgs::peer, or -1
+};
+struct FanPeer {
+  double4* land;       // receiver's landing zone of this epoch, offset to our range; arrays `cap` apart
+  uint32_t cap, pad;
+};
+struct FanArgs {
+  const uint32_t* bits;  // one bit per real particle: has images (one word per warp; nullptr: no fan-out in this launch)
+  const uint32_t* off;   // nreal + 1
+  const FanEnt* ent;
+  FanPeer peer[P2P_MAXPEER];
+};
+// returns true when the particle was stored to a neighbour GPU (the caller then fences at system scope before the block signals)
+__device__ __forceinline__ bool fan_out(const FanArgs& F, const PView& P, uint32_t p, const double4& r, const double4& vm, const double4& wg,
+                                        const double4& q) {
+  bool remote = false;
+  const uint32_t e1 = F.off[p + 1];
+  for (uint32_t e = F.off[p]; e < e1; e++) {
+    const FanEnt d = F.ent[e];
+    const double4 rs = make_double4(r.x + d.sx, r.y + d.sy, r.z + d.sz, r.w);
+    if (d.peer < 0) {
+      st4(P.pr + d.dst, rs); st4(P.vm + d.dst, vm); st4(P.wg + d.dst, wg); st4(P.q + d.dst, q);
+    } else {
+      const FanPeer& t = F.peer[d.peer];
+      st4(t.land + d.dst, rs); st4(t.land + (size_t)t.cap + d.dst, vm); st4(t.land + 2 * (size_t)t.cap + d.dst, wg);
+      st4(t.land + 3 * (size_t)t.cap + d.dst, q);
+      remote = true;
+    }
+  }
+  return remote;
+}
+// fan-out table construction (rebuild): count / fill over the local image list and over each peer's send list
+template <bool FILL>
+__global__ void k_fan_build(const uint32_t* __restrict__ src, const uint32_t* __restrict__ ent, const double* __restrict__ shift, uint32_t n,
+                            uint32_t dst_base, int peer, uint32_t* __restrict__ cursor, const uint32_t* __restrict__ off, FanEnt* __restrict__ out,
+                            uint32_t* __restrict__ bits) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t s = src[k];
+  const uint32_t c = atomicAdd(&cursor[s], 1u);
+  if (!FILL && c == 0) atomicOr(&bits[s >> 5], 1u << (s & 31));
+  if (FILL) {
+    const uint32_t e = ent[k];
+    out[off[s] + c] = FanEnt{shift[3 * e], shift[3 * e + 1], shift[3 * e + 2], dst_base + k, peer};
+  }
+}
+
 struct Peer {
   int rank;
   std::vector<GhostEntry> recv;  // our ghost cells fed by this peer (our table order)
@@ -207,6 +276,7 @@ struct Peer {
   DevBuf<double> d_sshift;
   uint32_t n_send = 0, n_recv = 0, recv_base = 0;  // particles; recv_base = offset inside the ghost region
   uint32_t remote_base = 0, remote_cap = 0;         // P2P: where our data lands in the peer's landing zone / its array stride
+  int fan_index = -1;                                // slot in FanArgs::peer
   DevBuf<double4> s_pr, s_vm, s_wg, s_q;
   DevBuf<double> s_h;
   DevBuf<uint64_t> s_id;
@@ -310,6 +380,37 @@ struct Comm {
     }
   }
   char* old_base = nullptr;
+  // fused path: the gather of this step pushes (FanArgs) under a new epoch; the NEXT ghost refresh only lands
+  uint32_t fan_epoch_pending = 0;
+  void fan_begin(FanArgs& F) {
+    if (!(comm && p2p.on)) return;
+    const uint32_t e = ++p2p.epoch;
+    const int par = (int)(e & 1u);
+    for (auto& kv : peers) {
+      Peer& p = kv.second;   // fan_index was fixed when the fan-out table was built (rebuild)
+      if (p.fan_index >= 0) F.peer[p.fan_index] = FanPeer{p2p_land(p2p.peer_base[p.rank], p.remote_cap, par) + p.remote_base, p.remote_cap, 0};
+    }
+    fan_epoch_pending = e;
+  }
+  void land_pending(PView P, uint32_t nreal, unsigned long long* count, cudaStream_t st, uint64_t* launches) {
+    const uint32_t e = fan_epoch_pending;
+    fan_epoch_pending = 0;
+    const int par = (int)(e & 1u);
+    uint32_t nrem = 0;
+    for (auto& kv : peers) nrem += kv.second.n_recv;
+    LandArgs L{};
+    L.P = P;
+    L.mail = p2p_mail(p2p.base, par);
+    L.nranks = nranks; L.me = rank; L.epoch = e; L.count = count;
+    L.land = p2p_land(p2p.base, p2p.cap, par);
+    L.cap = p2p.cap; L.n = nrem; L.base = nreal + n_local_ghost;
+    for (int r = 0; r < nranks; r++)
+      if (r != rank) L.out_mail[L.n_out++] = p2p_mail(p2p.peer_base[r], par) + rank;
+    const uint32_t nb = nrem ? std::min<uint32_t>((nrem + BLK - 1) / BLK, 592u) : 1u;
+    k_ghost_land<<<nb, BLK, 0, st>>>(L);
+    (*launches)++;
+    p2p.exchanges++;
+  }
   // per-step refresh over peer memory; `count` (device, nullable) is all-reduced (sum) in place as a by-product
   void exchange_ghosts_p2p(PView P, uint32_t nreal, unsigned long long* count, cudaStream_t st, uint64_t* launches) {
     const uint32_t e = ++p2p.epoch;

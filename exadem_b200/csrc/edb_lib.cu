@@ -54,6 +54,10 @@ struct edb_context {
   DevBuf<uint32_t> inc_cnt, inc_off, inc;
   bool have_inc = false;
   bool queue_clean = false;   // d_need_count is zero (left so by k_gather<2>)
+  // ghost fan-out fused into k_gather<2> (comm.cuh): table built at rebuild; ghost_pushed = the last gather refreshed the ghosts
+  DevBuf<uint32_t> fan_cnt, fan_off, fan_bits;
+  DevBuf<FanEnt> fan_ent;
+  bool have_fan = false, ghost_pushed = false;
   uint32_t* d_need_count = nullptr;  // chunk queue of the persistent sphere contact kernel / length of the polyhedron work list
   DevBuf<uint32_t> need;             // work list of k_detect_poly_pp -> k_law_poly_pp
   unsigned long long* d_sflag = nullptr;   // rebuild trigger of the speculative step loop (2 slots, device)
@@ -307,7 +311,7 @@ extern "C" int edb_destroy(edb_context* c) {
   for (int t = 0; t < NT; t++) { c->wave[t].release(); c->prev[t].release(); }
   DevBuf<uint32_t>* u32s[] = {&c->cidx, &c->cidx2, &c->ccount, &c->cstart, &c->cfill, &c->tmp, &c->new2old, &c->old2new, &c->cbeg, &c->cend,
                               &c->scan_bsum, &c->scan_total, &c->g_cell, &c->g_src_cell, &c->g_count, &c->g_off, &c->g_src, &c->g_ent,
-                              &c->inc_cnt, &c->inc_off, &c->inc, &c->stage_u32};
+                              &c->inc_cnt, &c->inc_off, &c->inc, &c->stage_u32, &c->fan_cnt, &c->fan_off, &c->fan_bits, &c->need};
   for (auto* b : u32s) b->release();
   c->pr_backup.release(); c->q_backup.release(); c->vert.release(); c->g_shift.release(); c->tpp.release(); c->tpd.release();
   c->drv.release(); c->d_sh.release(); c->d_sv.release(); c->d_se.release(); c->d_sfoff.release(); c->d_sfn.release(); c->d_sfidx.release();
@@ -317,7 +321,7 @@ extern "C" int edb_destroy(edb_context* c) {
   c->mig_dest.release(); c->mig_midx.release(); c->mig_cnt.release(); c->mig_off.release(); c->imm_cnt.release(); c->imm_off.release();
   c->mig_sp.release(); c->mig_rp.release(); c->mig_sh.release(); c->mig_rh.release(); c->imm_tab.release();
   c->tw_cnt.release(); c->tw_flag.release(); c->tw_pos.release(); c->tw_own.release(); c->tw_par.release(); c->tw_tpos.release();
-  c->tw_s.release(); c->tw_r.release();
+  c->tw_s.release(); c->tw_r.release(); c->fan_ent.release();
   for (auto& e : c->ev_free) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto& e : c->ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto& e : c->user_ev) if (e) cudaEventDestroy(e);
@@ -634,6 +638,16 @@ extern "C" int edb_num_particles(edb_context* c, uint64_t* nr, uint64_t* ng) {
 // trig (device, nullable): the local rebuild-trigger count of the step, summed over the ranks in place on the way
 static void ghost_refresh(edb_context* c, bool all, unsigned long long* trig = nullptr) {
   if (c->nghost == 0 && c->cfg.nranks == 1) return;
+  if (!all && c->ghost_pushed) {   // the previous k_gather<2> stored the images itself; remote ones only have to land
+    c->ghost_pushed = false;
+    if (c->cfg.nranks > 1) {
+      ScopedTimer tm(c, B_GHOST);
+      c->comm.land_pending(view(c->pa), c->nreal, trig, c->st, &c->ctr.kernel_launches);
+    }
+    return;
+  }
+  c->ghost_pushed = false;
+  c->comm.fan_epoch_pending = 0;
   ScopedTimer tm(c, B_GHOST);
   const uint32_t nloc = c->comm.n_local_ghost;
   if (nloc) {
@@ -918,6 +932,9 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
 
   // 0. multi-GPU: particles that left the brick migrate (with their interaction history) before re-binning
   const bool multi = c->cfg.nranks > 1;
+  c->ghost_pushed = false;
+  c->comm.fan_epoch_pending = 0;
+  c->have_fan = false;
   const uint32_t n_before = c->nreal;   // slots the previous waves refer to
   uint32_t n_all = c->nreal, n = c->nreal;
   c->n_imm = 0;
@@ -996,6 +1013,35 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
     }
   ghost_refresh(c, true);
   compute_vertices(c);
+  // 2b. ghost fan-out table for the fused per-step refresh (single GPU: periodic images; multi-GPU: needs the peer-memory path)
+  if ((!multi && nloc_ghost) || (multi && c->comm.p2p.on)) {
+    c->fan_cnt.ensure(n + 2); c->fan_off.ensure(n + 2); c->fan_bits.ensure(n / 32 + 2);
+    CK(cudaMemsetAsync(c->fan_bits.p, 0, (n / 32 + 1) * 4, c->st));
+    int pi = 0;
+    if (multi)
+      for (auto& kv : c->comm.peers) kv.second.fan_index = kv.second.n_send ? pi++ : -1;
+    for (int fill = 0; fill < 2; fill++) {
+      CK(cudaMemsetAsync(c->fan_cnt.p, 0, (n + 1) * 4, c->st));
+      if (nloc_ghost) {
+        if (!fill) LAUNCH(c, k_fan_build<false>, nblk(nloc_ghost), BLK, 0, c->g_src.p, c->g_ent.p, c->g_shift.p, nloc_ghost, n, -1, c->fan_cnt.p, nullptr, nullptr, c->fan_bits.p);
+        else LAUNCH(c, k_fan_build<true>, nblk(nloc_ghost), BLK, 0, c->g_src.p, c->g_ent.p, c->g_shift.p, nloc_ghost, n, -1, c->fan_cnt.p, c->fan_off.p, c->fan_ent.p, c->fan_bits.p);
+      }
+      if (multi)
+        for (auto& kv : c->comm.peers) {
+          Peer& p = kv.second;
+          if (!p.n_send) continue;
+          if (!fill) LAUNCH(c, k_fan_build<false>, nblk(p.n_send), BLK, 0, p.d_smap.p, p.d_sent.p, p.d_sshift.p, p.n_send, 0u, p.fan_index, c->fan_cnt.p, nullptr, nullptr, c->fan_bits.p);
+          else LAUNCH(c, k_fan_build<true>, nblk(p.n_send), BLK, 0, p.d_smap.p, p.d_sent.p, p.d_sshift.p, p.n_send, 0u, p.fan_index, c->fan_cnt.p, c->fan_off.p, c->fan_ent.p, c->fan_bits.p);
+        }
+      if (!fill) {
+        scan_u32(c, c->fan_cnt.p, c->fan_off.p, n);
+        CK(cudaMemcpyAsync(c->h_tot, c->fan_off.p + n, 4, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        c->fan_ent.ensure((size_t)c->h_tot[0] + 1);
+      }
+    }
+    c->have_fan = true;
+  }
   // 3. backup for the displacement trigger (backup_r / backup_dem)
   c->pr_backup.ensure(n + 1);
   if (poly) c->q_backup.ensure(n + 1);
@@ -1278,8 +1324,16 @@ static void gather(edb_context* c, const double* g, double dt, const unsigned lo
   A.S = c->S;
   A.vert = (FUSE == 2 && poly) ? c->vert.p : nullptr;
   A.thr2 = thr * thr;
-  if (poly) LAUNCH(c, (k_gather<FUSE, true>), nblk(c->nreal), BLK, 0, A);
-  else LAUNCH(c, (k_gather<FUSE, false>), nblk(c->nreal), BLK, 0, A);
+  FanArgs F{};
+  if (FUSE == 2 && c->have_fan && !getenv("EDB_NO_FAN")) {
+    F.bits = c->fan_bits.p;
+    F.off = c->fan_off.p;
+    F.ent = c->fan_ent.p;
+    c->comm.fan_begin(F);
+    c->ghost_pushed = true;
+  }
+  if (poly) LAUNCH(c, (k_gather<FUSE, true>), nblk(c->nreal), BLK, 0, A, F);
+  else LAUNCH(c, (k_gather<FUSE, false>), nblk(c->nreal), BLK, 0, A, F);
   c->ctr.gather_launches++;
 }
 

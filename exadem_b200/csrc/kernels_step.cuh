@@ -10,6 +10,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_rebuild.cuh"
+#include "comm.cuh"
 
 namespace edb {
 
@@ -649,7 +650,7 @@ __device__ __forceinline__ void add_wrench(const double4& fd, const double4& cp,
 #endif
 constexpr int GU = EDB_GU;
 template <int FUSE, bool POLY>
-__global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constant__ GatherArgs A) {
+__global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constant__ GatherArgs A, const __grid_constant__ FanArgs FAN) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (gated(A.gate)) return;
   if (p >= A.nreal) return;   // (exited lanes are not waited for by the full-mask reduction of the FUSE 2 trigger)
@@ -746,6 +747,8 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
   const v3 w2 = mk3(w.x, w.y, w.z) + A.hdt * ar;
   w.x = w2.x; w.y = w2.y; w.z = w2.z;
   st4(A.P.pr + p, rn); st4(A.P.vm + p, vm); st4(A.P.wg + p, w); st4(A.P.q + p, Q);
+  // ghost images of this particle (own periodic copies, neighbour bricks): one bitmap word per warp says who has any
+  if (FAN.bits && ((FAN.bits[p >> 5] >> (p & 31)) & 1u)) fan_out(FAN, A.P, p, rn, vm, w, Q);
   unsigned int over = 0;
   if (POLY && A.vert) {
     // polyhedra: compute_vertices (compute_vertices.hpp:26-67) of the step that has just been started, and vertex_displ_over
