@@ -31,6 +31,8 @@ enum Bucket { B_CONTACT = 0, B_GATHER, B_PROLOG, B_EPILOG, B_REBUILD, B_GHOST, B
 struct edb_context {
   edb_config cfg{};
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;          // side stream: driver / mesh waves of the sphere operator run beside the wave-0 kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   int law = 0;
   bool timing = false;
@@ -122,6 +124,13 @@ struct edb_context {
   bool poly() const { return cfg.mode == EDB_MODE_POLYHEDRON; }
 };
 
+#define LAUNCH_ON(ctx, stream, kern, grid, block, smem, ...)       \
+  do {                                                            \
+    if ((grid) > 0) {                                             \
+      kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);   \
+      (ctx)->ctr.kernel_launches++;                               \
+    }                                                             \
+  } while (0)
 #define LAUNCH(ctx, kern, grid, block, smem, ...)                 \
   do {                                                            \
     if ((grid) > 0) {                                             \
@@ -269,6 +278,9 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
   try {
     CK(cudaSetDevice(cfg->device));
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CK(cudaMallocHost(&c->h_flag, sizeof(unsigned long long) * 4));
     CK(cudaMalloc(&c->d_flag, sizeof(unsigned long long) * 4));
     CK(cudaMalloc(&c->d_need_count, 16));
@@ -306,6 +318,9 @@ extern "C" int edb_destroy(edb_context* c) {
   if (!c) return EDB_ERR_INVALID;
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->st);
+  if (c->st2) { cudaStreamSynchronize(c->st2); cudaStreamDestroy(c->st2); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   c->comm.destroy();
   c->pa.release(); c->pb.release();
   for (int t = 0; t < NT; t++) { c->wave[t].release(); c->prev[t].release(); }
@@ -1238,6 +1253,17 @@ static void launch_contact_waves(edb_context* c, double dt, const unsigned long 
   const int* order = poly ? ORDER_POLY : ORDER_SPHERE;
   const int norder = poly ? 13 : 7;
   bool pp_done = false;
+  // spheres: the driver / mesh waves are small (one launch of a few blocks each) and independent of wave 0 — they run on a side
+  // stream beside the persistent wave-0 kernel instead of after it
+  bool side = false;
+  if (!poly && c->wave[0].n) {
+    for (int t = 4; t <= 9; t++) side = side || c->wave[t].n > 0;
+    if (side) {
+      CK(cudaEventRecord(c->ev_fork, c->st));
+      CK(cudaStreamWaitEvent(c->st2, c->ev_fork, 0));
+    }
+  }
+  cudaStream_t sd = side ? c->st2 : c->st;
   for (int o = 0; o < norder; o++) {
     const int t = order[o];
     Wave& w = c->wave[t];
@@ -1267,16 +1293,20 @@ static void launch_contact_waves(edb_context* c, double dt, const unsigned long 
       c->ctr.contact_pp_records += w.n;
     } else if (t <= 6) {
       if (poly) LAUNCH(c, (k_contact_driver<LAW, true>), nblk(w.n), BLK, 0, A);
-      else LAUNCH(c, (k_contact_driver<LAW, false>), nblk(w.n), BLK, 0, A);
+      else LAUNCH_ON(c, sd, (k_contact_driver<LAW, false>), nblk(w.n), BLK, 0, A);
     } else if (t <= 12) {
       if (poly) LAUNCH(c, (k_contact_mesh<LAW, true>), nblk(w.n), BLK, 0, A);
-      else LAUNCH(c, (k_contact_mesh<LAW, false>), nblk(w.n), BLK, 0, A);
+      else LAUNCH_ON(c, sd, (k_contact_mesh<LAW, false>), nblk(w.n), BLK, 0, A);
     }
     c->ctr.interaction_updates += w.n;
     c->ctr.contact_launches++;
     // algorithmic bytes of this launch: per record 8 (ij) + 48 r + 48 w history + 80 contact state;
     // per distinct particle touched 92 B of gathers (r, radius, vrot, group, v, mass) counted once per wave
     c->ctr.bytes_contact_algorithmic += w.n * 184ull + (uint64_t)c->nreal * 92ull;
+  }
+  if (side) {
+    CK(cudaEventRecord(c->ev_join, c->st2));
+    CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
   }
 }
 
