@@ -58,6 +58,11 @@ struct edb_context {
   bool queue_clean = false;   // d_need_count is zero (left so by k_gather<2>)
   // ghost fan-out fused into k_gather<2> (comm.cuh): table built at rebuild; ghost_pushed = the last gather refreshed the ghosts
   DevBuf<uint32_t> fan_cnt, fan_off, fan_bits;
+  // polyhedron neighbour build: stream pool of the count pass (kernels_nbh_poly.cuh)
+  DevBuf<uint32_t> nbh_pool, nbh_first, nbh_ctr;
+  uint32_t nbh_pool_chunks = 0;
+  uint32_t* h_nbh = nullptr;   // pinned copy of nbh_ctr
+  uint64_t nbh_replays = 0;
   DevBuf<FanEnt> fan_ent;
   bool have_fan = false, ghost_pushed = false;
   uint32_t* d_need_count = nullptr;  // chunk queue of the persistent sphere contact kernel / length of the polyhedron work list
@@ -286,6 +291,7 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
     CK(cudaMalloc(&c->d_need_count, 16));
     CK(cudaMalloc(&c->d_sflag, 16));
     CK(cudaMallocHost(&c->h_sflag, 16));
+    CK(cudaMallocHost(&c->h_nbh, 32));
     for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&c->ev_sflag[i], cudaEventDisableTiming));
     { int dev = 0, v = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) c->n_sm = v;
       if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && v > 0) c->smem_optin = (size_t)v; }
@@ -326,7 +332,7 @@ extern "C" int edb_destroy(edb_context* c) {
   for (int t = 0; t < NT; t++) { c->wave[t].release(); c->prev[t].release(); }
   DevBuf<uint32_t>* u32s[] = {&c->cidx, &c->cidx2, &c->ccount, &c->cstart, &c->cfill, &c->tmp, &c->new2old, &c->old2new, &c->cbeg, &c->cend,
                               &c->scan_bsum, &c->scan_total, &c->g_cell, &c->g_src_cell, &c->g_count, &c->g_off, &c->g_src, &c->g_ent,
-                              &c->inc_cnt, &c->inc_off, &c->inc, &c->stage_u32, &c->fan_cnt, &c->fan_off, &c->fan_bits, &c->need};
+                              &c->inc_cnt, &c->inc_off, &c->inc, &c->stage_u32, &c->fan_cnt, &c->fan_off, &c->fan_bits, &c->need, &c->nbh_pool, &c->nbh_first, &c->nbh_ctr};
   for (auto* b : u32s) b->release();
   c->pr_backup.release(); c->q_backup.release(); c->vert.release(); c->g_shift.release(); c->tpp.release(); c->tpd.release();
   c->drv.release(); c->d_sh.release(); c->d_sv.release(); c->d_se.release(); c->d_sfoff.release(); c->d_sfn.release(); c->d_sfidx.release();
@@ -345,6 +351,7 @@ extern "C" int edb_destroy(edb_context* c) {
   if (c->d_need_count) cudaFree(c->d_need_count);
   if (c->d_sflag) cudaFree(c->d_sflag);
   if (c->h_sflag) cudaFreeHost(c->h_sflag);
+  if (c->h_nbh) cudaFreeHost(c->h_nbh);
   for (int i = 0; i < 2; i++) if (c->ev_sflag[i]) cudaEventDestroy(c->ev_sflag[i]);
   if (c->h_tot) cudaFreeHost(c->h_tot);
   cudaStreamDestroy(c->st);
@@ -1104,14 +1111,31 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
     if (bytes + 4096 <= c->smem_optin) {
       cell_cap = cap;
       cell_smem = bytes;
-      CK(cudaFuncSetAttribute(k_nbh_poly_cell<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-      CK(cudaFuncSetAttribute(k_nbh_poly_cell<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      CK(cudaFuncSetAttribute(k_nbh_poly_cell<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      CK(cudaFuncSetAttribute(k_nbh_poly_cell<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      CK(cudaFuncSetAttribute(k_nbh_poly_cell<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     }
   }
   A.skip_pp = cell_cap ? 1 : 0;
+  // the count pass records its findings (pair headers + test ballots) when the pool sized by the previous rebuild is in place;
+  // the fill pass then replays them instead of repeating the tests
+  NbhPool PL{};
+  bool record = false;
+  if (cell_cap) {
+    c->nbh_ctr.ensure(8);   // [0] cursor  [1] overflow  [2,3] need (u64)
+    CK(cudaMemsetAsync(c->nbh_ctr.p, 0, 32, c->st));
+    c->nbh_first.ensure(n + 1);
+    record = c->nbh_pool_chunks > 0 && !getenv("EDB_NBH_NO_REPLAY");
+    PL = NbhPool{c->nbh_pool.p, c->nbh_ctr.p, record ? c->nbh_pool_chunks : 0u, c->nbh_first.p,
+                 reinterpret_cast<unsigned long long*>(c->nbh_ctr.p + 2), c->nbh_ctr.p + 1};
+  }
   if (!poly) LAUNCH(c, k_nbh_sphere<false>, nblk(n, 128), 128, 0, A, C, W);
   else {
-    if (cell_cap) LAUNCH(c, k_nbh_poly_cell<false>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap);
+    if (cell_cap) {
+      if (record) LAUNCH(c, k_nbh_poly_cell<1>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap, PL);
+      else LAUNCH(c, k_nbh_poly_cell<0>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap, PL);
+      CK(cudaMemcpyAsync(c->h_nbh, c->nbh_ctr.p, 32, cudaMemcpyDeviceToHost, c->st));
+    }
     if (!cell_cap || drv_waves) LAUNCH(c, k_nbh_poly<false>, nblk(n, 64), 64, 0, A, C, W);
   }
   for (int t = 0; t < NT; t++)
@@ -1129,7 +1153,23 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   }
   if (!poly) LAUNCH(c, k_nbh_sphere<true>, nblk(n, 128), 128, 0, A, C, W);
   else {
-    if (cell_cap) LAUNCH(c, k_nbh_poly_cell<true>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap);
+    if (cell_cap) {
+      const uint32_t overflow = c->h_nbh[1];
+      const unsigned long long need = *reinterpret_cast<unsigned long long*>(c->h_nbh + 2);
+      if (record && !overflow) {
+        LAUNCH(c, k_nbh_poly_replay, nblk(n, 8), 256, 0, A, C, W, PL);
+        c->nbh_replays++;
+      } else {
+        LAUNCH(c, k_nbh_poly_cell<2>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap, PL);
+      }
+      // size the pool for the next rebuild (25 % head room)
+      const unsigned long long want = need + need / 4 + 1024;
+      if (need + need / 16 + 64 > c->nbh_pool_chunks && want * CHW < (1ull << 32)) {   // grow only when the head room is used up
+        CK(cudaStreamSynchronize(c->st));
+        c->nbh_pool.ensure((size_t)want * CHW);
+        c->nbh_pool_chunks = (uint32_t)want;
+      }
+    }
     if (!cell_cap || drv_waves) LAUNCH(c, k_nbh_poly<true>, nblk(n, 64), 64, 0, A, C, W);
   }
   // 5. history carry-over

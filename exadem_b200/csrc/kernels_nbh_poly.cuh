@@ -2,7 +2,8 @@
 // version for sm_100a.  This is the expensive kernel of a polyhedron neighbour rebuild: ~420 filter evaluations (V-V, V-E, V-F,
 // E-E in both directions) per pair of octahedra whose enlarged OBBs intersect.
 //
-//   block  = one real cell of the grid; 16 warps.
+//   block  = one real cell of the grid; 16 warps; the warps take the cell's owner particles from a shared counter.
+//            (8 warps x 2 blocks per SM with orientations / ids read from global memory measured 13 % slower.)
 //   stage  = the world vertices, positions+radius and orientations of every particle of the 3x3x3 cell stencil are copied into
 //            shared memory by the TMA engine: one cp.async.bulk per (cell, array) — cell-sorted particles make each cell's block
 //            contiguous — completing on one mbarrier.  ids, homothety, shape type and slot follow with ordinary loads.
@@ -11,7 +12,10 @@
 //            the survivors are taken in order (ballot), and for each pair the lanes SHARE the pair's filter tests: test index =
 //            base + lane, ballot + popc give every accepted test its place in the owner's record segment, so the records come out
 //            in exactly the order of the reference's nested loops (the gather's summation order depends on it).
-//   passes = FILL=false counts per (owner, wave); after the scan FILL=true repeats the tests and writes the records.
+//   passes = the COUNT pass counts per (owner, wave) and records what it found — per pair a header and the 32-bit ballot of every
+//            round of tests — as a word stream in a chunked pool; after the scan the FILL pass (k_nbh_poly_replay, warp per owner)
+//            replays the streams and writes the records without evaluating a single filter.  (First rebuild, or pool overflow:
+//            the fill pass repeats the tests instead, MODE 2.)
 // All arithmetic is the same dem_math.cuh functions on the same inputs as the per-thread kernel (k_nbh_poly), so membership is
 // bit-identical; only the work distribution changes.
 #pragma once
@@ -20,6 +24,8 @@
 namespace edb {
 
 constexpr int NPC_THREADS = 512;
+constexpr int CHW = 64;                       // words per pool chunk; word 0 links to the next chunk
+constexpr uint32_t NPC_NONE = 0xffffffffu;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
@@ -58,6 +64,15 @@ struct SV {  // world-vertex accessor over the staged (shared-memory) copy
 __device__ __forceinline__ uint32_t type_of_bits(double w) { return (uint32_t)((unsigned long long)__double_as_longlong(w) & 0xffffffffu); }
 __host__ __device__ inline size_t npc_bytes_per_particle(int nvmax) { return (size_t)nvmax * 32 + 32 + 32 + 8 + 8 + 4 + 4 + 1; }
 
+struct NbhPool {
+  uint32_t* words;                // cap_chunks * CHW
+  uint32_t* cursor;               // next free chunk
+  uint32_t cap_chunks;
+  uint32_t* first;                // per owner slot: first chunk of its stream (NPC_NONE: no pair)
+  unsigned long long* need;       // += chunks every owner would need (sizes the pool for the next rebuild)
+  uint32_t* overflow;             // set when the pool ran out: the fill pass falls back to recomputation
+};
+
 // max over the real cells of the number of particles in the 3x3x3 stencil (sizes the staging area)
 __global__ void k_stencil_max(GridDev G, const uint32_t* __restrict__ cbeg, const uint32_t* __restrict__ cend, unsigned long long* __restrict__ out) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -77,8 +92,15 @@ __global__ void k_stencil_max(GridDev G, const uint32_t* __restrict__ cbeg, cons
   if ((threadIdx.x & 31) == 0 && s) atomicMax(out, (unsigned long long)s);
 }
 
-template <bool FILL>
-__global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, CntTab C, WTab W, uint32_t cap) {
+// per-pair test groups, shared by the count pass and the replay: (wave, number of tests, decode of a test index)
+struct PairDims {
+  uint32_t nva, nea, nfa, nvb, neb, nfb;
+};
+
+// MODE 0: count;  MODE 1: count + record the streams;  MODE 2: fill by repeating the tests
+template <int MODE>
+__global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, CntTab C, WTab W, uint32_t cap, NbhPool PL) {
+  constexpr bool FILL = MODE == 2;
   extern __shared__ __align__(128) unsigned char smem[];
   const int nvmax = A.S.nvmax;
   double4* s_vert = reinterpret_cast<double4*>(smem);
@@ -90,7 +112,7 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
   uint32_t* s_type = s_slot + cap;
   uint8_t* s_gc = reinterpret_cast<uint8_t*>(s_type + cap);
   __shared__ unsigned long long s_bar;
-  __shared__ uint32_t s_cbase[28], s_cbeg[27];
+  __shared__ uint32_t s_cbase[28], s_cbeg[27], s_next;
   __shared__ uint8_t s_cgc[27];
   __shared__ uint16_t s_queue[NPC_THREADS / 32][64];
 
@@ -101,11 +123,11 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
     const uint32_t lin = cell_lin(G, ci, cj, ck);
     if (A.cend[lin] == A.cbeg[lin]) return;   // empty cell: nothing to own (uniform for the block)
   }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = NPC_THREADS / 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
   // ---- stage the stencil ------------------------------------------------------------------------------------------------
   if (wid == 0) {
-    if (lane == 0) mbar_init(&s_bar, 1);
+    if (lane == 0) { mbar_init(&s_bar, 1); s_next = 0; }
     uint32_t cnt = 0, beg = 0;
     if (lane < 27) {
       const int dk = lane / 9 - 1, dj = (lane / 3) % 3 - 1, di = lane % 3 - 1;   // same visiting order as for_each_neighbor
@@ -118,10 +140,10 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
     }
     const uint32_t inc = warp_incl_scan(cnt);
     if (lane < 27) s_cbase[lane] = inc - cnt;
-    const uint32_t nst = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t nst0 = __shfl_sync(0xffffffffu, inc, 31);
     if (lane == 0) {
-      s_cbase[27] = nst;
-      mbar_expect_tx(&s_bar, nst * (uint32_t)(nvmax * 32 + 64));
+      s_cbase[27] = nst0;
+      mbar_expect_tx(&s_bar, nst0 * (uint32_t)(nvmax * 32 + 64));
     }
     __syncwarp();
     if (lane < 27 && cnt) {
@@ -147,9 +169,15 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
   mbar_wait(&s_bar, 0);
   __syncthreads();
 
-  // ---- owners ------------------------------------------------------------------------------------------------------------
+  // ---- owners (taken from a shared counter: the work per owner varies with its number of neighbours) -----------------------
   const double rV = A.rcut_inc;
-  for (uint32_t La = s_cbase[13] + wid; La < s_cbase[14]; La += nwarp) {
+  const uint32_t own0 = s_cbase[13], nown = s_cbase[14] - own0;
+  for (;;) {
+    uint32_t oi_ = 0;
+    if (lane == 0) oi_ = atomicAdd(&s_next, 1u);
+    oi_ = __shfl_sync(0xffffffffu, oi_, 0);
+    if (oi_ >= nown) break;
+    const uint32_t La = own0 + oi_;
     const uint32_t a = s_slot[La];
     const double4 ra = s_pr[La], qa4 = s_q[La];
     const unsigned long long ida = s_id[La];
@@ -166,6 +194,23 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
 #pragma unroll
       for (int t = 0; t < 4; t++) base[t] = C.c[t][a];
     }
+    // stream writer (lane 0 holds the state)
+    uint32_t nw = 0, wchunk = NPC_NONE, wfill = CHW;
+    bool wovf = false;
+    auto emit = [&](uint32_t wv) {
+      nw++;
+      if (MODE == 1 && lane == 0 && !wovf) {
+        if (wfill == CHW) {
+          const uint32_t nc = atomicAdd(PL.cursor, 1u);
+          if (nc >= PL.cap_chunks) { wovf = true; atomicExch(PL.overflow, 1u); return; }
+          if (wchunk == NPC_NONE) PL.first[a] = nc;
+          else PL.words[(size_t)wchunk * CHW] = nc;
+          wchunk = nc;
+          wfill = 1;
+        }
+        PL.words[(size_t)wchunk * CHW + wfill++] = wv;
+      }
+    };
     // one group of tests of a pair: test index x in [0, N), lanes take x = b0 + lane; accepted tests are written in x order
     auto group = [&](int t, uint32_t N, auto&& test, auto&& rec) {
       for (uint32_t b0 = 0; b0 < N; b0 += 32) {
@@ -173,6 +218,7 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
         const bool ok = x < N && test(x);
         const unsigned m = __ballot_sync(0xffffffffu, ok);
         if (FILL && ok) rec(x, base[t] + run[t] + __popc(m & ((1u << lane) - 1u)));
+        if (!FILL) emit(m);
         run[t] += __popc(m);
       }
     };
@@ -214,81 +260,142 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
         __syncwarp();
         nq = rest;
         while (pm) {
-        const int l = __ffs(pm) - 1;
-        pm &= pm - 1;
-        const uint32_t Lb = __shfl_sync(0xffffffffu, Lc, l);   // warp-uniform
-        const uint32_t b = s_slot[Lb];
-        const double4 rb = s_pr[Lb], qb4 = s_q[Lb];
-        const unsigned long long idb = s_id[Lb];
-        const ShapeDev* __restrict__ psb = A.S.sh + s_type[Lb];
-        const struct { int nv, ne, nf, e0, f0, fi0; double radius; } sb{psb->nv, psb->ne, psb->nf, psb->e0, psb->f0, psb->fi0, psb->radius};
-        const double hb = s_h[Lb];
-        const SV vb{s_vert + (size_t)Lb * nvmax};
-        const double rmb = hb * sb.radius;
-        const int* eb = A.S.edges + 2 * sb.e0;
-        // vertex-vs-OBB prefilters, one vertex per lane; the OBBs are enlarged in two half steps like the reference (:268-276, :305-310)
-        unsigned mA, mB;
-        {
-          Obb oj = obb_world(psb->obb, mk3(rb.x, rb.y, rb.z), q4{qb4.x, qb4.y, qb4.z, qb4.w}, hb);
-          obb_enlarge(oj, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
-          mA = __ballot_sync(0xffffffffu, lane < sa.nv && obb_intersect(oj, obb_point(va[lane < sa.nv ? lane : 0], rma)));
-        }
-        {
-          Obb oi = obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha);
-          obb_enlarge(oi, 0.5 * rV); obb_enlarge(oi, 0.5 * rV);
-          mB = __ballot_sync(0xffffffffu, lane < sb.nv && obb_intersect(oi, obb_point(vb[lane < sb.nv ? lane : 0], rmb)));
-        }
-        const uint8_t ghost = s_gc[Lb];
-        const uint8_t f0 = (uint8_t)(ghost << 1), f1 = (uint8_t)(1 | (ghost << 1));
-        auto write = [&](int t, uint32_t k, uint32_t i, uint32_t j, uint32_t si, uint32_t sj, uint8_t flg) {
-          W.w[t].ij[k] = make_uint2(i, j);
-          W.w[t].sub[k] = make_uint2(si, sj);
-          W.w[t].flg[k] = flg;
-          W.w[t].ft[k] = make_double4(0, 0, 0, __longlong_as_double((long long)idb));
-          W.w[t].mo[k] = make_double4(0, 0, 0, 0);
-        };
-        const uint32_t nvb = sb.nv, neb = sb.ne, nfb = sb.nf, nea = sa.ne, nfa = sa.nf;
-        // The vertex-vs-OBB prefilter usually keeps 1-3 of the vertices: the test index space is built over the KEPT vertices only
-        // (n-th set bit of the mask, ascending, so the emission order is unchanged) and the lanes stay busy.
-        const uint32_t nA = __popc(mA), nB = __popc(mB);
-        auto vtxA = [&](uint32_t n) { return (uint32_t)__fns(mA, 0, (int)n + 1); };
-        auto vtxB = [&](uint32_t n) { return (uint32_t)__fns(mB, 0, (int)n + 1); };
-        // A -> B (swap = 0): vertices of a against vertices / edges / faces of b
-        group(0, nA * nvb,
-              [&](uint32_t x) { const uint32_t i = vtxA(x / nvb), j = x % nvb; return filter_vv(rV, va[i], rma, vb[j], rmb); },
-              [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
-        group(1, nA * neb,
-              [&](uint32_t x) { const uint32_t i = vtxA(x / neb), j = x % neb; return filter_ve(rV, va[i], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb); },
-              [&](uint32_t x, uint32_t k) { write(1, k, a, b, vtxA(x / neb), x % neb, f0); });
-        group(2, nA * nfb,
-              [&](uint32_t x) {
-                const uint32_t i = vtxA(x / nfb), j = x % nfb;
-                return filter_vf(rV, va[i], rma, vb, rmb, A.S.fidx + sb.fi0 + A.S.foff[sb.f0 + j], A.S.fn[sb.f0 + j]);
-              },
-              [&](uint32_t x, uint32_t k) { write(2, k, a, b, vtxA(x / nfb), x % nfb, f0); });
-        group(3, nea * neb,
-              [&](uint32_t x) {
-                const uint32_t i = x / neb, j = x % neb;
-                return filter_ee(rV, va[ea[2 * i]], va[ea[2 * i + 1]], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb);
-              },
-              [&](uint32_t x, uint32_t k) { write(3, k, a, b, x / neb, x % neb, f0); });
-        // B -> A (swap = 1): pi = b, pj = a; the owner stays a (interaction_pair.hpp:75-90)
-        group(1, nB * nea,
-              [&](uint32_t x) { const uint32_t j = vtxB(x / nea), i = x % nea; return filter_ve(rV, vb[j], rmb, va[ea[2 * i]], va[ea[2 * i + 1]], rma); },
-              [&](uint32_t x, uint32_t k) { write(1, k, b, a, vtxB(x / nea), x % nea, f1); });
-        group(2, nB * nfa,
-              [&](uint32_t x) {
-                const uint32_t j = vtxB(x / nfa), i = x % nfa;
-                return filter_vf(rV, vb[j], rmb, va, rma, A.S.fidx + sa.fi0 + A.S.foff[sa.f0 + i], A.S.fn[sa.f0 + i]);
-              },
-              [&](uint32_t x, uint32_t k) { write(2, k, b, a, vtxB(x / nfa), x % nfa, f1); });
+          const int l = __ffs(pm) - 1;
+          pm &= pm - 1;
+          const uint32_t Lb = __shfl_sync(0xffffffffu, Lc, l);   // warp-uniform
+          const uint32_t b = s_slot[Lb];
+          const double4 rb = s_pr[Lb], qb4 = s_q[Lb];
+          const unsigned long long idb = s_id[Lb];
+          const ShapeDev* __restrict__ psb = A.S.sh + s_type[Lb];
+          const struct { int nv, ne, nf, e0, f0, fi0; double radius; } sb{psb->nv, psb->ne, psb->nf, psb->e0, psb->f0, psb->fi0, psb->radius};
+          const double hb = s_h[Lb];
+          const SV vb{s_vert + (size_t)Lb * nvmax};
+          const double rmb = hb * sb.radius;
+          const int* eb = A.S.edges + 2 * sb.e0;
+          // vertex-vs-OBB prefilters, one vertex per lane; the OBBs are enlarged in two half steps like the reference (:268-276, :305-310)
+          unsigned mA, mB;
+          {
+            Obb oj = obb_world(psb->obb, mk3(rb.x, rb.y, rb.z), q4{qb4.x, qb4.y, qb4.z, qb4.w}, hb);
+            obb_enlarge(oj, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
+            mA = __ballot_sync(0xffffffffu, lane < sa.nv && obb_intersect(oj, obb_point(va[lane < sa.nv ? lane : 0], rma)));
+          }
+          {
+            Obb oi = obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha);
+            obb_enlarge(oi, 0.5 * rV); obb_enlarge(oi, 0.5 * rV);
+            mB = __ballot_sync(0xffffffffu, lane < sb.nv && obb_intersect(oi, obb_point(vb[lane < sb.nv ? lane : 0], rmb)));
+          }
+          const uint8_t ghost = s_gc[Lb];
+          const uint8_t f0 = (uint8_t)(ghost << 1), f1 = (uint8_t)(1 | (ghost << 1));
+          if (!FILL) {   // pair header of the stream
+            emit(b); emit((uint32_t)idb); emit((uint32_t)(idb >> 32)); emit((uint32_t)ghost | (s_type[Lb] << 8)); emit(mA); emit(mB);
+          }
+          auto write = [&](int t, uint32_t k, uint32_t i, uint32_t j, uint32_t si, uint32_t sj, uint8_t flg) {
+            W.w[t].ij[k] = make_uint2(i, j);
+            W.w[t].sub[k] = make_uint2(si, sj);
+            W.w[t].flg[k] = flg;
+            W.w[t].ft[k] = make_double4(0, 0, 0, __longlong_as_double((long long)idb));
+            W.w[t].mo[k] = make_double4(0, 0, 0, 0);
+          };
+          const uint32_t nvb = sb.nv, neb = sb.ne, nfb = sb.nf, nea = sa.ne, nfa = sa.nf;
+          // The vertex-vs-OBB prefilter usually keeps 1-3 of the vertices: the test index space is built over the KEPT vertices only
+          // (n-th set bit of the mask, ascending, so the emission order is unchanged) and the lanes stay busy.
+          const uint32_t nA = __popc(mA), nB = __popc(mB);
+          auto vtxA = [&](uint32_t n) { return (uint32_t)__fns(mA, 0, (int)n + 1); };
+          auto vtxB = [&](uint32_t n) { return (uint32_t)__fns(mB, 0, (int)n + 1); };
+          // A -> B (swap = 0): vertices of a against vertices / edges / faces of b
+          group(0, nA * nvb,
+                [&](uint32_t x) { const uint32_t i = vtxA(x / nvb), j = x % nvb; return filter_vv(rV, va[i], rma, vb[j], rmb); },
+                [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
+          group(1, nA * neb,
+                [&](uint32_t x) { const uint32_t i = vtxA(x / neb), j = x % neb; return filter_ve(rV, va[i], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb); },
+                [&](uint32_t x, uint32_t k) { write(1, k, a, b, vtxA(x / neb), x % neb, f0); });
+          group(2, nA * nfb,
+                [&](uint32_t x) {
+                  const uint32_t i = vtxA(x / nfb), j = x % nfb;
+                  return filter_vf(rV, va[i], rma, vb, rmb, A.S.fidx + sb.fi0 + A.S.foff[sb.f0 + j], A.S.fn[sb.f0 + j]);
+                },
+                [&](uint32_t x, uint32_t k) { write(2, k, a, b, vtxA(x / nfb), x % nfb, f0); });
+          group(3, nea * neb,
+                [&](uint32_t x) {
+                  const uint32_t i = x / neb, j = x % neb;
+                  return filter_ee(rV, va[ea[2 * i]], va[ea[2 * i + 1]], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb);
+                },
+                [&](uint32_t x, uint32_t k) { write(3, k, a, b, x / neb, x % neb, f0); });
+          // B -> A (swap = 1): pi = b, pj = a; the owner stays a (interaction_pair.hpp:75-90)
+          group(1, nB * nea,
+                [&](uint32_t x) { const uint32_t j = vtxB(x / nea), i = x % nea; return filter_ve(rV, vb[j], rmb, va[ea[2 * i]], va[ea[2 * i + 1]], rma); },
+                [&](uint32_t x, uint32_t k) { write(1, k, b, a, vtxB(x / nea), x % nea, f1); });
+          group(2, nB * nfa,
+                [&](uint32_t x) {
+                  const uint32_t j = vtxB(x / nfa), i = x % nfa;
+                  return filter_vf(rV, vb[j], rmb, va, rma, A.S.fidx + sa.fi0 + A.S.foff[sa.f0 + i], A.S.fn[sa.f0 + i]);
+                },
+                [&](uint32_t x, uint32_t k) { write(2, k, b, a, vtxB(x / nfa), x % nfa, f1); });
         }
       }
     }
-    if (!FILL && lane == 0) {
+    if (!FILL) {
+      if (nw) emit(NPC_NONE);   // end of the owner's stream
+      if (lane == 0) {
 #pragma unroll
-      for (int t = 0; t < 4; t++) C.c[t][a] = run[t];
+        for (int t = 0; t < 4; t++) C.c[t][a] = run[t];
+        if (nw) atomicAdd(PL.need, (unsigned long long)((nw + CHW - 2) / (CHW - 1)));
+        if (MODE == 1 && wchunk == NPC_NONE) PL.first[a] = NPC_NONE;
+      }
     }
+  }
+}
+
+// FILL pass by replay: warp per owner, reads the owner's stream (pair headers + ballots of the count pass) and writes the records
+// at the owner's CSR offsets — the same control flow as k_nbh_poly_cell with every filter test replaced by its recorded bit.
+__global__ void __launch_bounds__(256) k_nbh_poly_replay(NbhArgs A, CntTab C, WTab W, NbhPool PL) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (a >= A.nreal) return;
+  uint32_t chunk = PL.first[a];
+  if (chunk == NPC_NONE) return;
+  uint32_t pos = 1;
+  auto rd = [&]() {
+    if (pos == CHW) { chunk = PL.words[(size_t)chunk * CHW]; pos = 1; }
+    return PL.words[(size_t)chunk * CHW + pos++];
+  };
+  const ShapeDev* __restrict__ psa = A.S.sh + type_of_bits(A.P.wg[a].w);
+  const uint32_t nea = psa->ne, nfa = psa->nf;
+  uint32_t run[4] = {0, 0, 0, 0}, base[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) base[t] = C.c[t][a];
+  for (;;) {
+    const uint32_t b = rd();
+    if (b == NPC_NONE) break;
+    const uint32_t idlo = rd(), idhi = rd(), gt = rd(), mA = rd(), mB = rd();
+    const unsigned long long idb = ((unsigned long long)idhi << 32) | idlo;
+    const uint8_t ghost = (uint8_t)(gt & 0xffu);
+    const ShapeDev* __restrict__ psb = A.S.sh + (gt >> 8);
+    const uint32_t nvb = psb->nv, neb = psb->ne, nfb = psb->nf;
+    const uint8_t f0 = (uint8_t)(ghost << 1), f1 = (uint8_t)(1 | (ghost << 1));
+    const uint32_t nA = __popc(mA), nB = __popc(mB);
+    auto group = [&](int t, uint32_t N, auto&& rec) {
+      for (uint32_t b0 = 0; b0 < N; b0 += 32) {
+        const unsigned m = rd();
+        if ((m >> lane) & 1u) rec(b0 + lane, base[t] + run[t] + __popc(m & ((1u << lane) - 1u)));
+        run[t] += __popc(m);
+      }
+    };
+    auto write = [&](int t, uint32_t k, uint32_t i, uint32_t j, uint32_t si, uint32_t sj, uint8_t flg) {
+      W.w[t].ij[k] = make_uint2(i, j);
+      W.w[t].sub[k] = make_uint2(si, sj);
+      W.w[t].flg[k] = flg;
+      W.w[t].ft[k] = make_double4(0, 0, 0, __longlong_as_double((long long)idb));
+      W.w[t].mo[k] = make_double4(0, 0, 0, 0);
+    };
+    auto vtxA = [&](uint32_t n) { return (uint32_t)__fns(mA, 0, (int)n + 1); };
+    auto vtxB = [&](uint32_t n) { return (uint32_t)__fns(mB, 0, (int)n + 1); };
+    group(0, nA * nvb, [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
+    group(1, nA * neb, [&](uint32_t x, uint32_t k) { write(1, k, a, b, vtxA(x / neb), x % neb, f0); });
+    group(2, nA * nfb, [&](uint32_t x, uint32_t k) { write(2, k, a, b, vtxA(x / nfb), x % nfb, f0); });
+    group(3, nea * neb, [&](uint32_t x, uint32_t k) { write(3, k, a, b, x / neb, x % neb, f0); });
+    group(1, nB * nea, [&](uint32_t x, uint32_t k) { write(1, k, b, a, vtxB(x / nea), x % nea, f1); });
+    group(2, nB * nfa, [&](uint32_t x, uint32_t k) { write(2, k, b, a, vtxB(x / nfa), x % nfa, f1); });
   }
 }
 
