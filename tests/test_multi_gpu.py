@@ -16,10 +16,10 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-def _run(n, *extra):
+def _run(n, *extra, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(29500 + (os.getpid() % 400)), str(ROOT / "tests" / "mgpu_worker.py"), *extra]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "mgpu parity OK" in r.stdout
     return r.stdout
@@ -30,6 +30,15 @@ def test_two_gpu_spheres(rebuild_every):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     _run(2, "--mode", "sphere", "--steps", "60", "--rebuild-every", str(rebuild_every))
+
+
+@pytest.mark.parametrize("env", [{"EDB_NO_FAN": "1"}, {"EDB_NO_P2P": "1"}], ids=["push-kernel", "nccl"])
+def test_two_gpu_spheres_other_ghost_paths(env):
+    """The per-step ghost refresh has three implementations: stores fused into the gather (default), a separate push kernel over
+    peer memory (EDB_NO_FAN), and NCCL send/recv + all-reduce (EDB_NO_P2P, also the path when CUDA IPC is unavailable)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, "--mode", "sphere", "--steps", "60", "--rebuild-every", "0", env=env)
 
 
 def test_two_gpu_polyhedra():
