@@ -83,6 +83,11 @@ class Counters(C.Structure):
                 ("gather_launches", C.c_uint64)]
 
 
+class SimState(C.Structure):
+    _fields_ = [("kinetic_energy", C.c_double * 3), ("rotation_energy", C.c_double * 3), ("mass", C.c_double), ("min_dn", C.c_double),
+                ("n_particles", C.c_uint64), ("n_active_interactions", C.c_uint64), ("n_total_interactions", C.c_uint64)]
+
+
 class EdbError(RuntimeError):
     pass
 
@@ -351,6 +356,12 @@ class Engine:
         m = np.zeros((n_drivers, 3))
         self._call("compute_driver_force_moment", _as(f, _D), _as(m, _D))
         return f, m
+
+    def simulation_state(self, symetric=True) -> SimState:
+        """[simulation_state] energies, mass, interaction counts and min dn of this rank (the log line's reductions)."""
+        out = SimState()
+        self._call("simulation_state", C.c_int32(1 if symetric else 0), C.byref(out))
+        return out
 
     def stress_tensor(self):
         """[stress_tensor] per-particle 3x3 sum of f (x) (cp - r) over the contacts of the last step, upload order."""

@@ -1725,6 +1725,36 @@ extern "C" int edb_stress_tensor(edb_context* c, double* stress9) {
   API_END(c)
 }
 
+extern "C" int edb_simulation_state(edb_context* c, int32_t symetric, edb_sim_state* out) {
+  API_BEGIN(c)
+  memset(out, 0, sizeof(*out));
+  const uint32_t n = c->nreal, nb = nblk(n);
+  c->stage.ensure((size_t)nb * 7 + 8);
+  std::vector<double> part((size_t)nb * 7);
+  if (nb) {
+    LAUNCH(c, k_sim_state_particles, nb, BLK, 0, view(c->pa), n, c->stage.p);
+    CK(cudaMemcpyAsync(part.data(), c->stage.p, part.size() * 8, cudaMemcpyDeviceToHost, c->st));
+  }
+  CK(cudaMemsetAsync(c->d_flag, 0, 24, c->st));
+  for (int t = 0; t < NT; t++)
+    if (c->wave[t].n) LAUNCH(c, k_sim_state_wave, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), (unsigned long long)((t <= 3 && symetric) ? 2 : 1), c->d_flag);
+  CK(cudaMemcpyAsync(c->h_flag, c->d_flag, 24, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (uint32_t b = 0; b < nb; b++)
+    for (int q = 0; q < 7; q++) acc[q] += part[(size_t)b * 7 + q];
+  for (int q = 0; q < 3; q++) { out->kinetic_energy[q] = acc[q]; out->rotation_energy[q] = acc[3 + q]; }
+  out->mass = acc[6];
+  out->n_particles = n;
+  out->n_total_interactions = c->h_flag[0];
+  out->n_active_interactions = c->h_flag[1];
+  long long bits = (long long)c->h_flag[2];
+  double dn;
+  memcpy(&dn, &bits, 8);
+  out->min_dn = c->h_flag[2] ? dn : 0.0;
+  API_END(c)
+}
+
 // ---- multi-GPU -----------------------------------------------------------------------------------------------------
 extern "C" int edb_comm_unique_id(uint8_t id_out[128]) { return Comm::unique_id(id_out); }
 extern "C" int edb_comm_init(edb_context* c, const uint8_t id[128]) {

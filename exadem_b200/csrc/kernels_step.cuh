@@ -818,6 +818,66 @@ __global__ void __launch_bounds__(BLK) k_stress(GatherArgs A, double* __restrict
   for (int q = 0; q < 9; q++) dst[q] = S[q];
 }
 
+// simulation_state (src/io/simulation_state.cu:80-175): particle part — per block, a fixed-order tree sum of
+// {0.5 m v^2 (xyz), 0.5 m vrot^2 (xyz), m}; the host adds the block partials in block order (reproducible).
+__global__ void __launch_bounds__(BLK) k_sim_state_particles(PView P, uint32_t n, double* __restrict__ partial) {
+  __shared__ double sm[7][BLK];
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (p < n) {
+    const double4 vm = ld4(P.vm + p), w = ld4(P.wg + p);
+    const double m = vm.w;
+    v[0] = 0.5 * vm.x * vm.x * m; v[1] = 0.5 * vm.y * vm.y * m; v[2] = 0.5 * vm.z * vm.z * m;   // simulation_state.hpp:52-55
+    v[3] = 0.5 * w.x * w.x * m; v[4] = 0.5 * w.y * w.y * m; v[5] = 0.5 * w.z * w.z * m;
+    v[6] = m;
+  }
+#pragma unroll
+  for (int q = 0; q < 7; q++) sm[q][threadIdx.x] = v[q];
+  __syncthreads();
+  for (int s = BLK / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s)
+#pragma unroll
+      for (int q = 0; q < 7; q++) sm[q][threadIdx.x] += sm[q][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x < 7) partial[(size_t)blockIdx.x * 7 + threadIdx.x] = sm[threadIdx.x][0];
+}
+// interaction part (itools/counter.hpp:125-152): out[0] += total, out[1] += active (integer atomics: order-independent),
+// out[2] = min over the active records of dn, kept as the bit pattern of a non-positive double (larger pattern = smaller value)
+__global__ void __launch_bounds__(BLK) k_sim_state_wave(WView w, unsigned long long coef, unsigned long long* __restrict__ out) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int tot = 0, act = 0;
+  double dn = 0.0;
+  if (k < w.n) {
+    const uint8_t fl = w.flg[k];
+    if (((fl >> 1) & 3) != 2) {   // PartnerGhost twins are not counted
+      tot = 1;
+      if (fl & FLG_HOT) {
+        const double4 fd = ld4(w.fd + k), ft = ld4(w.ft + k);
+        bool active = fd.w < 0.0 || ft.x != 0.0 || ft.y != 0.0 || ft.z != 0.0;
+        if (!active && (fl & FLG_MOM)) {
+          const double4 mo = ld4(w.mo + k);
+          active = mo.x != 0.0 || mo.y != 0.0 || mo.z != 0.0;
+        }
+        if (active) { act = 1; dn = fd.w; }
+      }
+    }
+  }
+  tot = __reduce_add_sync(0xffffffffu, tot);
+  act = __reduce_add_sync(0xffffffffu, act);
+  // min(0, dn): dn <= 0 values order inversely to their bit patterns
+  unsigned long long bits = dn < 0.0 ? (unsigned long long)__double_as_longlong(dn) : 0ull;
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o);
+    bits = other > bits ? other : bits;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (tot) atomicAdd(out, coef * tot);
+    if (act) atomicAdd(out + 1, coef * act);
+    if (bits) atomicMax(out + 2, bits);
+  }
+}
+
 // compute_driver_force_moment.cu:34-54 — per-driver sum of -(fn+ft) and of (cp - center) x (-(fn+ft)) - moment over the driver waves.
 // Deterministic: one block per driver wave chunk writes a partial; partials are summed in order on the host side buffer.
 __global__ void __launch_bounds__(BLK) k_driver_force(WView w, int type, const Driver* __restrict__ drv, int ndrv, double* __restrict__ partial) {

@@ -162,6 +162,24 @@ class StressTensor : public OperatorNode {
     stress.set(std::move(out));
   }
 };
+// src/io/simulation_state.cu:80-175 — the reductions of the log line (this rank's share); result in slot `simulation_state` as
+// {kinetic xyz, rotation xyz, mass, min_dn, n_particles, n_active, n_total}
+class SimulationStateNode : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(bool, symetric, INPUT, REQUIRED, DocString{"Use of symetric feature (contact law)"});
+  ADD_SLOT(std::vector<double>, simulation_state, OUTPUT);
+  ADD_SLOT(double, system_mass, OUTPUT);
+ public:
+  std::string documentation() const final { return "Computes the kinetic / rotation energies, the mass, the particle and interaction counts and the largest overlap."; }
+  void execute() final {
+    edb_sim_state st;
+    ck(*grid, edb_simulation_state(grid->ctx, *symetric ? 1 : 0, &st), "simulation_state");
+    simulation_state.set(std::vector<double>{st.kinetic_energy[0], st.kinetic_energy[1], st.kinetic_energy[2], st.rotation_energy[0],
+                                             st.rotation_energy[1], st.rotation_energy[2], st.mass, st.min_dn, (double)st.n_particles,
+                                             (double)st.n_active_interactions, (double)st.n_total_interactions});
+    system_mass.set(st.mass);
+  }
+};
 // src/interaction/compute_driver_force_moment.cu:79-146 — results in slots `driver_forces` / `driver_moments` (3 doubles per driver)
 class ComputeDriverForceMoment : public OperatorNode {
   ADD_SLOT(GridB200, grid, INPUT_OUTPUT, REQUIRED);
@@ -189,6 +207,7 @@ ONIKA_AUTORUN_INIT(exadem_b200_hot_path) {
   f->register_factory("nbh_sphere", make_simple_operator<UpdateContactInteractionSphere>);
   f->register_factory("nbh_polyhedron", make_simple_operator<UpdateGridCellInteractionPolyhedron>);
   f->register_factory("stress_tensor", make_simple_operator<StressTensor>);
+  f->register_factory("simulation_state", make_simple_operator<SimulationStateNode>);
   f->register_factory("compute_driver_force_moment", make_simple_operator<ComputeDriverForceMoment>);
   // bookkeeping operators of update_particles_full (config_move_particles.msp:141-154) that the device layout makes implicit
   for (const char* n : {"classify_interactions", "unclassify_interactions", "compress_interaction", "update_interaction_ghost", "update_traversals",

@@ -165,6 +165,16 @@ int edb_displ_over(edb_context*, double threshold, uint64_t* over);
 int edb_compute_driver_force_moment(edb_context*, double* forces, double* moments);
 /* [stress_tensor] src/interaction/stress_tensor.cu:142-178: per-particle 3x3 (row-major, upload order), scaled by 1/volume outside */
 int edb_stress_tensor(edb_context*, double* stress9);
+/* [simulation_state] src/io/simulation_state.cu:80-175 (+ simulation_state.hpp:48-57, itools/counter.hpp:125-152): the reductions
+ * behind the log line, on the device — per-axis kinetic 0.5 m v^2 and rotation 0.5 m vrot^2 energies, mass and particle count over
+ * the real particles; interaction totals over the waves (PartnerGhost records skipped, particle-particle waves counted twice when
+ * `symetric`), active = dn < 0 or non-zero friction/moment history, min_dn over the active ones.  Values of THIS rank (the
+ * reference's operator then MPI_Allreduce's them). */
+typedef struct edb_sim_state {
+  double kinetic_energy[3], rotation_energy[3], mass, min_dn;
+  uint64_t n_particles, n_active_interactions, n_total_interactions;
+} edb_sim_state;
+int edb_simulation_state(edb_context*, int32_t symetric, edb_sim_state* out);
 
 /* Fused fast path = numerical_scheme_verlet (data/config/config_numerical_schemes.msp:6-30), `nsteps` iterations:
  * prolog -> (rebuild if displacement >= rcut_inc/2 | ghost_update_rq) -> [compute_vertices] -> reset+gravity+contact

@@ -920,6 +920,35 @@ int orc_stress_tensor(orc_sim* h, double* out) {
   return 0;
 }
 
+// simulation_state.cu:80-175 + simulation_state.hpp:48-57 + itools/counter.hpp:125-152
+int orc_simulation_state(orc_sim* h, int32_t symetric, edb_sim_state* out) {
+  Sim& s = *(Sim*)h;
+  memset(out, 0, sizeof(*out));
+  for (size_t p = 0; p < s.nreal; p++) {
+    const double m = s.mass[p];
+    out->mass += m;
+    out->rotation_energy[0] += 0.5 * s.w[p].x * s.w[p].x * m; out->rotation_energy[1] += 0.5 * s.w[p].y * s.w[p].y * m;
+    out->rotation_energy[2] += 0.5 * s.w[p].z * s.w[p].z * m;
+    out->kinetic_energy[0] += 0.5 * s.v[p].x * s.v[p].x * m; out->kinetic_energy[1] += 0.5 * s.v[p].y * s.v[p].y * m;
+    out->kinetic_energy[2] += 0.5 * s.v[p].z * s.v[p].z * m;
+    out->n_particles += 1;
+  }
+  for (int t = 0; t < EDB_NTYPES; t++) {
+    const uint64_t coef = (t <= 3 && symetric) ? 2 : 1;
+    for (uint32_t k : s.wave[t]) {
+      const Inter& I = s.inter[k];
+      if (I.ghost == 2) continue;   // PartnerGhost
+      out->n_total_interactions += coef;
+      const bool active = I.ft.x != 0 || I.ft.y != 0 || I.ft.z != 0 || I.mom.x != 0 || I.mom.y != 0 || I.mom.z != 0;
+      if (I.dn < 0.0 || active) {
+        out->n_active_interactions += coef;
+        out->min_dn = std::min(out->min_dn, I.dn);
+      }
+    }
+  }
+  return 0;
+}
+
 int orc_run_verlet(orc_sim* h, double dt, const double* g, double rcut_inc, int32_t symetric, int32_t nsteps, int32_t rebuild_every, uint64_t* n_rebuilds) {
   Sim& s = *(Sim*)h;
   uint64_t nb = 0;

@@ -374,3 +374,23 @@ def test_checkpoint_restart(product_lib, oracle_lib, kind):
         assert np.array_equal(getattr(p0, f)[o0], getattr(p1, f)[o1]), f
     compare_interaction_sets(g0.export_interactions(), g1.export_interactions(), payload_rtol=0.0)
     check(g1, c1)
+
+
+@pytest.mark.parametrize("kind", ["drum", "poly"])
+def test_simulation_state(product_lib, oracle_lib, kind):
+    """simulation_state: the log line's reductions on the device — energies, mass, interaction totals (PartnerGhost
+    skipped, particle-particle waves x2 when symetric), active count and min dn — against the oracle's restatement."""
+    if kind == "drum":
+        wl = workloads.rotating_drum(6000, jitter=0.02)
+    else:
+        wl = workloads.polyhedra_box((6, 6, 6), shapes=("octahedron", "cube"), pitch=0.78, cell_size=2.0)
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    both((gpu, cpu), lambda e: e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 8, -1))
+    a, b = gpu.simulation_state(True), cpu.simulation_state(True)
+    assert a.n_particles == b.n_particles == wl.particles.n
+    assert a.n_total_interactions == b.n_total_interactions > 0
+    assert a.n_active_interactions == b.n_active_interactions > 0
+    assert b.min_dn < 0 and abs(a.min_dn - b.min_dn) <= 1e-10 * abs(b.min_dn)
+    for x, y in zip(list(a.kinetic_energy) + list(a.rotation_energy) + [a.mass], list(b.kinetic_energy) + list(b.rotation_energy) + [b.mass]):
+        assert abs(x - y) <= 1e-12 * max(abs(y), 1e-300)
