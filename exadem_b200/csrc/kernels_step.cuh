@@ -251,10 +251,10 @@ __device__ __forceinline__ bool detect_need(const ContactArgs& A, const uint2 ij
 }
 
 #ifndef EDB_PP_BLK
-#define EDB_PP_BLK 256
+#define EDB_PP_BLK 160
 #endif
 #ifndef EDB_PP_MINB
-#define EDB_PP_MINB 2
+#define EDB_PP_MINB 4
 #endif
 constexpr int PP_BLK = EDB_PP_BLK, PP_MINB = EDB_PP_MINB;   // tuning knobs of the sweep in profiles/ (registers vs resident warps)
 template <int LAW>
