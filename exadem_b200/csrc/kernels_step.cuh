@@ -677,6 +677,47 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
     if (A.next_flag && A.pr_backup) prefetch_l2(A.pr_backup + p);
     if (p == 0 && A.reset_queue) *A.reset_queue = 0;   // chunk queue of the next step's contact kernel
   }
+  // sum of one hot record's wrench in the role this particle plays in it
+  auto accumulate = [&](uint32_t code, uint8_t flg, const double4& fd, const double4& cp) {
+    const uint32_t o = code >> INC_SHIFT, k = code & INC_MASK;
+    const double4 mo = (flg & FLG_MOM) ? ld4(A.W.w[A.order[o]].mo + k) : make_double4(0, 0, 0, 0);
+    bool role_i;
+    if ((int)o < A.npp) {
+      const uint32_t a = o == 0 ? oa[0] : o == 1 ? oa[1] : o == 2 ? oa[2] : oa[3];
+      const uint32_t b = o == 0 ? ob[0] : o == 1 ? ob[1] : o == 2 ? ob[2] : ob[3];
+      const bool owner = k >= a && k < b;
+      const bool owner_is_i = A.has_swap ? !(flg & FLG_SWAP) : true;
+      role_i = owner ? owner_is_i : !owner_is_i;
+    } else {
+      // mesh waves 11/12 ("j to i", contact.hpp:405-421): the particle receives -f, -mom
+      const int t = A.order[o];
+      role_i = !(t == 11 || t == 12);
+    }
+    add_wrench(fd, cp, mo, role_i, r, F, M);
+  };
+  if (POLY) {
+    // polyhedra: a particle has a dozen-plus incident records of which few are in contact — eight codes, then eight flag bytes in
+    // flight at a time; the rare hot record fetches its wrench on demand
+    constexpr int PU = 8;
+    for (uint32_t e = e0; e < e1; e += PU) {
+      uint32_t code[PU];
+      uint8_t fl[PU];
+#pragma unroll
+      for (int u = 0; u < PU; u++) code[u] = (e + u < e1) ? A.inc[e + u] : 0xffffffffu;
+#pragma unroll
+      for (int u = 0; u < PU; u++) {
+        fl[u] = 0;
+        if (code[u] != 0xffffffffu) fl[u] = A.W.w[A.order[code[u] >> INC_SHIFT]].flg[code[u] & INC_MASK];
+      }
+#pragma unroll
+      for (int u = 0; u < PU; u++)
+        if (fl[u] & FLG_HOT) {
+          const WView& w = A.W.w[A.order[code[u] >> INC_SHIFT]];
+          const double4 fd = ld4(w.fd + (code[u] & INC_MASK)), cp = ld4(w.cp + (code[u] & INC_MASK));
+          accumulate(code[u], fl[u], fd, cp);
+        }
+    }
+  } else
   for (uint32_t e = e0; e < e1; e += GU) {
     uint32_t code[GU];
     uint8_t fl[GU];
@@ -697,23 +738,7 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
       }
 #pragma unroll
     for (int u = 0; u < GU; u++)
-      if (fl[u] & FLG_HOT) {
-        const uint32_t o = code[u] >> INC_SHIFT, k = code[u] & INC_MASK;
-        const double4 mo = (fl[u] & FLG_MOM) ? ld4(A.W.w[A.order[o]].mo + k) : make_double4(0, 0, 0, 0);
-        bool role_i;
-        if ((int)o < A.npp) {
-          const uint32_t a = o == 0 ? oa[0] : o == 1 ? oa[1] : o == 2 ? oa[2] : oa[3];
-          const uint32_t b = o == 0 ? ob[0] : o == 1 ? ob[1] : o == 2 ? ob[2] : ob[3];
-          const bool owner = k >= a && k < b;
-          const bool owner_is_i = A.has_swap ? !(fl[u] & FLG_SWAP) : true;
-          role_i = owner ? owner_is_i : !owner_is_i;
-        } else {
-          // mesh waves 11/12 ("j to i", contact.hpp:405-421): the particle receives -f, -mom
-          const int t = A.order[o];
-          role_i = !(t == 11 || t == 12);
-        }
-        add_wrench(fd[u], cp[u], mo, role_i, r, F, M);
-      }
+      if (fl[u] & FLG_HOT) accumulate(code[u], fl[u], fd[u], cp[u]);
   }
   if (!FUSE) {
     A.P.fx[p] = F.x; A.P.fy[p] = F.y; A.P.fz[p] = F.z;
