@@ -25,7 +25,13 @@ for p in (str(ROOT), str(ROOT / "tests")):
 def global_workload(mode, world):
     from exadem_b200 import parallel, workloads
     pg = parallel.process_grid(world)
-    if mode == "sphere":
+    if mode == "drum":
+        # the bench's N>1 workload in small: a rotating drum (cylinder driver, periodic along its axis) cut into slabs along the axis
+        pg = (1, world, 1)
+        wl = workloads.rotating_drum(12000 * world, jitter=0.02, length=10.0 * world, seed=0xD3B4 + world)
+        wl.particles.vy[:] *= 40.0                      # particles cross the slab faces (and the periodic end) within the run
+        wl.particles.ry[:] = np.mod(wl.particles.ry + 0.4995, wl.hi[1])
+    elif mode == "sphere":
         side = [10 * pg[d] for d in range(3)]
         wl = workloads.spheres_box(tuple(side), jitter=0.03, omega_sigma=0.3, sigma_v=0.1, seed=0xD3B0 + world)
         # lattice planes 5e-4 below the brick faces: particles cross brick (and periodic) boundaries within ~50 steps

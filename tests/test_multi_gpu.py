@@ -41,6 +41,13 @@ def test_two_gpu_spheres_other_ghost_paths(env):
     _run(2, "--mode", "sphere", "--steps", "60", "--rebuild-every", "0", env=env)
 
 
+def test_two_gpu_drum_slabs():
+    """The N>1 bench workload (drum cut into slabs along its periodic axis, cylinder driver on every rank), parity vs the oracle."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, "--mode", "drum", "--steps", "60", "--rebuild-every", "0")
+
+
 def test_two_gpu_polyhedra():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
