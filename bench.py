@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, help="drum (N=1 default) | box (N>1 default) | box8m | poly")
+    ap.add_argument("--workload", default=None, help="drum (default; N>1: slabs) | box | box8m | poly | mixed")
     ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -124,6 +124,22 @@ def make_workload(name, n, rank=0, nranks=1):
     if name == "poly":
         side = int(round(n ** (1.0 / 3.0)))
         return workloads.polyhedra_box((side, side, side), pitch=0.78)
+    if name == "mixed":
+        # BASELINE configs[3]: spheres (one-vertex shapes) + octahedra + cubes in one polyhedron context, cohesive law, closed
+        # STL-like mesh walls (an RShape driver) around the packing
+        from exadem_b200 import capi
+        side = int(round(n ** (1.0 / 3.0)))
+        wl = workloads.polyhedra_box((side, side, side), shapes=("octahedron", "cube", "sphere"), pitch=0.78, name="mixed")
+        L = side * 0.78
+        wl.lo, wl.hi = (-2.0, -2.0, -2.0), (L + 2.0, L + 2.0, L + 2.0)
+        wl.periodic = (0, 0, 0)
+        wl.law = capi.LAW_COHESIVE
+        wl.params = dict(wl.params, fc=0.05, dncut=0.02)
+        wl.params_driver = dict(wl.params_driver, fc=0.02, dncut=0.01)
+        spec, centre = workloads.box_mesh((-0.45, -0.45, -0.45), (L - 0.33, L - 0.33, L - 0.33), 0.03)
+        wl.mesh_spec = [spec]
+        wl.drivers = list(wl.drivers) + [dict(kind=capi.DRIVER_RSHAPE, shape=0, center=centre)]
+        return wl
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -233,7 +249,7 @@ def polyhedra_line(lib, peak, device, n=500_000, steps=60, warmup=10):
             "unit": UNIT, "particle_steps_per_s": c.particle_steps / (ms * 1e-3), "steps": steps, "ms_per_step": ms / steps,
             "interactions": int(counts.sum()), "active_interactions": int(active.sum()), "rebuilds_in_timed_region": int(nreb),
             "rebuild_once_ms": reb,
-            "roofline": {"kernel": "k_contact_poly_pp (4 waves)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_detect_poly_pp + k_law_poly_pp (4 waves)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "note": "algorithmic bytes counted as for spheres (184 B/record + 92 B/particle per wave); vertex reads not counted"},
             "per_step_ms": {"contact_all": c.contact_ms / steps, "gather_fused": c.gather_ms / steps, "ghost": c.ghost_ms / steps}}
 
@@ -359,7 +375,7 @@ def main():
     alg_bytes = rec_per_launch * 184.0 + wl.particles.n * 92.0
     t_launch = (c.contact_pp_ms / max(c.contact_pp_launches, 1)) * 1e-3
     achieved = alg_bytes / t_launch / 1e9 if t_launch > 0 else 0.0
-    roof = {"kernel": "k_contact_sphere_pp" if wl.mode == 0 else "k_contact_poly_pp", "bound": "hbm", "achieved": achieved,
+    roof = {"kernel": "k_contact_sphere_pp" if wl.mode == 0 else "k_detect_poly_pp + k_law_poly_pp", "bound": "hbm", "achieved": achieved,
             "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": t_launch * 1e3,
             "share_of_step": c.contact_pp_ms / ms if ms > 0 else None,
@@ -397,7 +413,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "particle_steps_per_s": ps / (ms * 1e-3),
-            "config": {"workload": f"{name}: {wl.particles.n * world} spheres ({wl.particles.n}/GPU), {wl.name}", "particles_per_gpu": int(wl.particles.n),
+            "config": {"workload": f"{name}: {wl.particles.n * world} particles ({wl.particles.n}/GPU), {wl.name}", "particles_per_gpu": int(wl.particles.n),
                        "interactions_per_gpu": int(counts.sum()), "active_interactions_per_gpu": int(active.sum()),
                        "rebuilds_in_timed_region": int(nreb), "rebuild": "displacement trigger rcut_inc/2",
                        "l2": "working set (particles + interaction waves) > 126 MB L2, no flush",
