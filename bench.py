@@ -33,7 +33,7 @@ UNIT = "interaction-updates/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="drum (default; N>1: slabs) | box | box8m | poly | mixed")
@@ -55,7 +55,7 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------ clocks sampling
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device=0):
@@ -69,7 +69,17 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(stamp):
+        import datetime
+        try:
+            return datetime.datetime.strptime(stamp.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
+
+    def stop(self, window=None):
+        """window = (t0, t1) wall-clock seconds of the timed region: only the samples taken inside it count (nvidia-smi needs a
+        few hundred ms to start, so the sampler is launched well before the region and left running through it)."""
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -83,6 +93,10 @@ class ClockSampler:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
+            if window is not None:
+                ts = self._epoch(f[0])
+                if ts is None or ts < window[0] - 0.005 or ts > window[1] + 0.005:
+                    continue
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
@@ -276,6 +290,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sampler = ClockSampler(local)   # started now: nvidia-smi needs a few hundred ms before its first sample
+    if rank == 0:
+        sampler.start()
     name = args.workload or "drum"
     wl = make_workload(name, args.particles, rank, world)
     lib = Library()
@@ -298,18 +315,16 @@ def main():
     barrier()
     eng.reset_counters()
     eng.set_timing(True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     barrier()
     eng.event_record(0)
+    w0 = time.time()
     t0 = time.perf_counter()
     nreb = eng.run_verlet(wl.dt, g, wl.rcut_inc, wl.symetric, args.steps, 0)
     eng.event_record(1)
     ms = eng.event_elapsed_ms(0, 1)
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop((w0, time.time())) if rank == 0 else None
     if rank == 0 and not clocks.get("samples"):
         shot = sampler.one_shot()
         if shot:
