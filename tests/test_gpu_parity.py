@@ -394,3 +394,17 @@ def test_simulation_state(product_lib, oracle_lib, kind):
     assert b.min_dn < 0 and abs(a.min_dn - b.min_dn) <= 1e-10 * abs(b.min_dn)
     for x, y in zip(list(a.kinetic_energy) + list(a.rotation_energy) + [a.mass], list(b.kinetic_energy) + list(b.rotation_energy) + [b.mass]):
         assert abs(x - y) <= 1e-12 * max(abs(y), 1e-300)
+
+
+def test_polyhedra_vertex_trigger_inside_run(product_lib, oracle_lib):
+    """vertex_displ_over evaluated inside the fused gather (k_gather<2,true>) and the speculative step loop, for polyhedra: fast,
+    spinning particles force rebuilds; rebuild count, interaction set and state must match the oracle's synchronous decision."""
+    wl = workloads.polyhedra_box((6, 6, 6), shapes=("octahedron", "cube"), pitch=0.8, cell_size=2.0, seed=0xD3C7)
+    wl.particles.vx[:] *= 1500.0
+    wl.particles.vy[:] *= 1500.0
+    wl.particles.vrotz[:] += 60.0
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    both((gpu, cpu), lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 40, 0) for e in (gpu, cpu)]
+    assert nb[0] == nb[1] and nb[0] >= 2, nb
+    check(gpu, cpu)

@@ -48,10 +48,11 @@ def test_two_gpu_drum_slabs():
     _run(2, "--mode", "drum", "--steps", "60", "--rebuild-every", "0")
 
 
-def test_two_gpu_polyhedra():
+@pytest.mark.parametrize("rebuild_every", [10, 0])
+def test_two_gpu_polyhedra(rebuild_every):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    _run(2, "--mode", "poly", "--steps", "30", "--rebuild-every", "10")
+    _run(2, "--mode", "poly", "--steps", "30", "--rebuild-every", str(rebuild_every))
 
 
 def test_eight_gpu_spheres():
