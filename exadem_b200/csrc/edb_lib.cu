@@ -65,6 +65,8 @@ struct edb_context {
   uint64_t nbh_replays = 0;
   DevBuf<FanEnt> fan_ent;
   bool have_fan = false, ghost_pushed = false;
+  // debugging switches read once at creation: EDB_NO_FAN (separate ghost kernels), EDB_NBH_POLY_PER_THREAD, EDB_NBH_NO_REPLAY
+  bool env_no_fan = false, env_nbh_per_thread = false, env_nbh_no_replay = false;
   uint32_t* d_need_count = nullptr;  // chunk queue of the persistent sphere contact kernel / length of the polyhedron work list
   DevBuf<uint32_t> need;             // work list of k_detect_poly_pp -> k_law_poly_pp
   unsigned long long* d_sflag = nullptr;   // rebuild trigger of the speculative step loop (2 slots, device)
@@ -280,6 +282,9 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
   edb_context* c = new edb_context();
   c->cfg = *cfg;
   if (c->cfg.nranks < 1) c->cfg.nranks = 1;
+  c->env_no_fan = getenv("EDB_NO_FAN") != nullptr;
+  c->env_nbh_per_thread = getenv("EDB_NBH_POLY_PER_THREAD") != nullptr;
+  c->env_nbh_no_replay = getenv("EDB_NBH_NO_REPLAY") != nullptr;
   try {
     CK(cudaSetDevice(cfg->device));
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
@@ -1101,7 +1106,7 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   const uint32_t n_real_cells = (uint32_t)G.nc[0] * G.nc[1] * G.nc[2];
   bool drv_waves = false;
   for (int t = 4; t < NT; t++) drv_waves = drv_waves || active[t];
-  if (poly && c->S.nvmax <= 32 && !getenv("EDB_NBH_POLY_PER_THREAD")) {
+  if (poly && c->S.nvmax <= 32 && !c->env_nbh_per_thread) {
     CK(cudaMemsetAsync(c->d_flag + 1, 0, 8, c->st));
     LAUNCH(c, k_stencil_max, nblk(n_real_cells), BLK, 0, G, c->cbeg.p, c->cend.p, c->d_flag + 1);
     CK(cudaMemcpyAsync(c->h_flag + 1, c->d_flag + 1, 8, cudaMemcpyDeviceToHost, c->st));
@@ -1125,7 +1130,7 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
     c->nbh_ctr.ensure(8);   // [0] cursor  [1] overflow  [2,3] need (u64)
     CK(cudaMemsetAsync(c->nbh_ctr.p, 0, 32, c->st));
     c->nbh_first.ensure(n + 1);
-    record = c->nbh_pool_chunks > 0 && !getenv("EDB_NBH_NO_REPLAY");
+    record = c->nbh_pool_chunks > 0 && !c->env_nbh_no_replay;
     PL = NbhPool{c->nbh_pool.p, c->nbh_ctr.p, record ? c->nbh_pool_chunks : 0u, c->nbh_first.p,
                  reinterpret_cast<unsigned long long*>(c->nbh_ctr.p + 2), c->nbh_ctr.p + 1};
   }
@@ -1395,7 +1400,7 @@ static void gather(edb_context* c, const double* g, double dt, const unsigned lo
   A.vert = (FUSE == 2 && poly) ? c->vert.p : nullptr;
   A.thr2 = thr * thr;
   FanArgs F{};
-  if (FUSE == 2 && c->have_fan && !getenv("EDB_NO_FAN")) {
+  if (FUSE == 2 && c->have_fan && !c->env_no_fan) {
     F.bits = c->fan_bits.p;
     F.off = c->fan_off.p;
     F.ent = c->fan_ent.p;
