@@ -408,3 +408,43 @@ def test_polyhedra_vertex_trigger_inside_run(product_lib, oracle_lib):
     nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 40, 0) for e in (gpu, cpu)]
     assert nb[0] == nb[1] and nb[0] >= 2, nb
     check(gpu, cpu)
+
+
+@pytest.mark.parametrize("law", [capi.LAW_NONE, capi.LAW_DMT])
+def test_polyhedra_homothety_multimat_cylinder(product_lib, oracle_lib, law):
+    """Polyhedra whose size varies (homothety 0.8..1.2 scales vertices, Minkowski radius and OBB), three material groups with a
+    full multi-material parameter table, a cylinder driver around the packing (wave 4), Hooke and Hooke+DMT."""
+    wl = workloads.polyhedra_box((6, 6, 6), shapes=("octahedron", "cube"), pitch=0.95, cell_size=2.5, seed=0xD3C9)
+    rng = np.random.default_rng(5)
+    n = wl.particles.n
+    wl.particles.homothety[:] = rng.uniform(0.8, 1.2, n)
+    wl.particles.radius[:] *= wl.particles.homothety      # bounding radius follows the homothety (radius_from_shape)
+    wl.particles.group[:] = (np.arange(n) % 3).astype(np.uint32)
+    L = 6 * 0.95
+    wl.periodic = (0, 1, 0)
+    wl.lo, wl.hi = (-2.5, 0.0, -2.5), (L + 2.5, L, L + 2.5)
+    c = 0.5 * L - 0.475
+    wl.drivers = [dict(kind=capi.DRIVER_CYLINDER, radius=0.5 * L + 0.2, center=(c, c, c), axis=(1, 0, 1), vrot=(0, 0.5, 0))]
+    wl.law = law
+    base = dict(wl.params, gamma=0.02 if law == capi.LAW_DMT else 0.0)
+    pp = [dict(base, kn=base["kn"] * (1 + 0.1 * (a + b)), mu=0.1 * (1 + a * b)) for a in range(3) for b in range(3)]
+    pd = [dict(base, kt=5e3 * (1 + a)) for a in range(3)]
+    es = []
+    for mk in (lambda: Engine(product_lib, wl.config()), lambda: OracleEngine(oracle_lib, wl.config())):
+        e = mk()
+        e.set_law(wl.law)
+        e.set_shapes(wl.shapes())
+        e.set_drivers(wl.drivers)
+        e.set_contact_params_multimat(3, pp, 1, pd)
+        e.upload_particles(wl.particles)
+        es.append(e)
+    gpu, cpu = es
+    both(es, lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    cg, _ = gpu.interaction_counts()
+    cc, _ = cpu.interaction_counts()
+    assert np.array_equal(cg, cc) and cg[:4].sum() > 0 and cg[4] > 0, cg
+    nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 12, 5) for e in es]
+    assert nb[0] == nb[1]
+    check(gpu, cpu)
+    _, ag = gpu.interaction_counts()
+    assert ag[:4].sum() > 0
