@@ -220,20 +220,19 @@ __device__ __forceinline__ void finish_record(const ContactArgs& A, uint32_t k, 
   if (nf != fl) A.w.flg[k] = nf;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // wave 0 of the sphere operator: sphere::ContactLawFunc (contact_sphere.hpp:121-203).
 //
 // Persistent kernel, warp-autonomous (no block barrier anywhere).  A warp takes chunks of CHUNK = 128 consecutive records from a
 // dynamic queue.  Per chunk:
 //   detect  lane l owns records [k0 + 4l, k0 + 4l + 4): one 32-byte ij load + one 4-byte flg load (coalesced, 9 B/record).
-//           HOT records (in contact at their last evaluation) are work by definition: their seven operand sectors (r, v, w of both
-//           particles, friction) are pulled into L2 at once with prefetch.global.L2 — no registers, no scoreboard — while the cold
-//           records gather the two position sectors and run detection_vertex_vertex.  A cold record that stays cold costs
+//           HOT records (in contact at their last evaluation) are work by definition; the cold records gather the two position
+//           sectors and run detection_vertex_vertex.  (prefetch.global.L2 of the hot records' operands at this point was
+//           measured 5 % SLOWER than no prefetch: profiles/r1_ncu_session4.txt.)  A cold record that stays cold costs
 //           9 B + two mostly L1/L2-resident gathers and nothing else (no history read, no write).
 //   compact shuffle scan of the per-lane counts; the (k, i, j, flg) entries of the records that need the law go, in record order,
 //           to a 2 KB per-warp shared-memory list.
-//   law     dense: 32 entries per round, all eight operands of an entry issued back to back (L2 hits after the prefetch),
+//   law     dense: 32 entries per round, all eight operands of an entry issued back to back,
 //           detection + Hooke law + history / wrench stores on fully populated warps.
 // The id of the next chunk is fetched (one atomic per 128 records) before the current one is processed.
 constexpr int CHUNK = 128;
@@ -289,15 +288,7 @@ __global__ void __launch_bounds__(PP_BLK, PP_MINB) k_contact_sphere_pp(ContactAr
     }
     bool need[4];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      need[u] = (f4 >> (8 * u)) & FLG_HOT;
-      if (need[u]) {
-        prefetch_l2(A.P.pr + ij[u].x); prefetch_l2(A.P.pr + ij[u].y);
-        prefetch_l2(A.P.vm + ij[u].x); prefetch_l2(A.P.vm + ij[u].y);
-        prefetch_l2(A.P.wg + ij[u].x); prefetch_l2(A.P.wg + ij[u].y);
-        prefetch_l2(A.w.ft + k0 + u);
-      }
-    }
+    for (int u = 0; u < 4; u++) need[u] = (f4 >> (8 * u)) & FLG_HOT;
 #pragma unroll
     for (int u = 0; u < 4; u++)
       if (!need[u] && k0 + u < A.w.n) need[u] = detect_need<LAW>(A, ij[u]);
@@ -671,12 +662,7 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
     F = mk3(A.P.fx[p], A.P.fy[p], A.P.fz[p]);
     M = mk3(A.P.mx[p], A.P.my[p], A.P.mz[p]);
   }
-  if (FUSE == 2) {   // the operands of the epilog / prolog tail: pulled into L2 now, read after the loop
-    prefetch_l2(A.P.wg + p); prefetch_l2(A.P.q + p);
-    if ((threadIdx.x & 3) == 0) { prefetch_l2(A.P.ix + p); prefetch_l2(A.P.iy + p); prefetch_l2(A.P.iz + p); }
-    if (A.next_flag && A.pr_backup) prefetch_l2(A.pr_backup + p);
-    if (p == 0 && A.reset_queue) *A.reset_queue = 0;   // chunk queue of the next step's contact kernel
-  }
+  if (FUSE == 2 && p == 0 && A.reset_queue) *A.reset_queue = 0;   // chunk queue of the next step's contact kernel
   // sum of one hot record's wrench in the role this particle plays in it
   auto accumulate = [&](uint32_t code, uint8_t flg, const double4& fd, const double4& cp) {
     const uint32_t o = code >> INC_SHIFT, k = code & INC_MASK;
