@@ -52,6 +52,68 @@ class Driver(C.Structure):
                 ("quat", C.c_double * 4)]
 
 
+_V3 = C.c_double * 3
+MOTION = {n: i for i, n in enumerate(("STATIONARY", "LINEAR_MOTION", "COMPRESSIVE_FORCE", "LINEAR_FORCE_MOTION", "PARTICLE",
+                                      "LINEAR_COMPRESSIVE_MOTION", "TABULATED", "SHAKER", "PENDULUM_MOTION", "EXPRESSION", "UNKNOWN"))}
+
+
+class DriverMotion(C.Structure):
+    """edb_driver_motion (include/exadem_b200.h): Driver_params + integrator state of one driver."""
+    _fields_ = [("motion_type", C.c_int32), ("n_tab", C.c_int32), ("motion_vector", _V3),
+                ("motion_start_threshold", C.c_double), ("motion_end_threshold", C.c_double),
+                ("const_vel", C.c_double), ("const_force", C.c_double), ("sigma", C.c_double), ("damprate", C.c_double),
+                ("tab_time", _D), ("tab_pos", _D), ("omega", C.c_double), ("amplitude", C.c_double), ("shaker_dir", _V3),
+                ("pendulum_anchor_point", _V3), ("pendulum_initial_position", _V3), ("pendulum_swing_dir", _V3),
+                ("expr_use_v", C.c_int32), ("expr_use_vrot", C.c_int32), ("expr_use_mom", C.c_int32), ("drive_by_mom", C.c_int32),
+                ("mass", C.c_double), ("surface", C.c_double), ("acc", _V3), ("rv", C.c_double), ("ra", C.c_double),
+                ("inertia", _V3), ("applied_mom", _V3), ("mom_axis", _V3), ("mom", _V3), ("forces", _V3)]
+
+
+def make_motion(d: dict, keep: list) -> DriverMotion:
+    """dict -> DriverMotion with the reference's defaults (driver_params.hpp:33-66, *Fields structs)."""
+    M = DriverMotion()
+    mt = d.get("motion_type", "STATIONARY")
+    M.motion_type = MOTION[mt] if isinstance(mt, str) else int(mt)
+    M.motion_start_threshold = d.get("motion_start_threshold", 0.0)
+    M.motion_end_threshold = d.get("motion_end_threshold", 1e300)
+    for k in ("const_vel", "const_force", "sigma", "damprate", "omega", "amplitude", "rv", "ra"):
+        setattr(M, k, float(d.get(k, 0.0)))
+    M.mass = d.get("mass", 1.7976931348623157e308 / 4)
+    M.surface = d.get("surface", -1.0)
+    for k, dflt in (("motion_vector", (0, 0, 0)), ("shaker_dir", (0, 0, 1)), ("pendulum_anchor_point", (0, 0, 0)),
+                    ("pendulum_initial_position", (0, 0, 0)), ("pendulum_swing_dir", (0, 0, 0)), ("acc", (0, 0, 0)),
+                    ("inertia", (0, 0, 0)), ("applied_mom", (0, 0, 0)), ("mom_axis", (0, 0, 0)), ("mom", (0, 0, 0)),
+                    ("forces", (0, 0, 0))):
+        v = d.get(k, dflt)
+        for c in range(3):
+            getattr(M, k)[c] = float(v[c])
+    for k in ("expr_use_v", "expr_use_vrot", "expr_use_mom", "drive_by_mom"):
+        setattr(M, k, int(d.get(k, 0)))
+    if "tab_time" in d:
+        t = np.ascontiguousarray(d["tab_time"], dtype=np.float64)
+        x = np.ascontiguousarray(d["tab_pos"], dtype=np.float64).reshape(-1, 3)
+        assert len(t) == len(x)
+        keep += [t, x]
+        M.n_tab = len(t)
+        M.tab_time = t.ctypes.data_as(_D)
+        M.tab_pos = x.ctypes.data_as(_D)
+    return M
+
+
+def driver_to_dict(D, M=None) -> dict:
+    out = {"kind": D.kind, "need_forces": D.need_forces, "radius": D.radius, "offset": D.offset, "shape": D.shape}
+    for k in ("axis", "center", "normal", "vel", "vrot"):
+        out[k] = np.array(getattr(D, k)[:])
+    out["quat"] = np.array(D.quat[:])
+    if M is not None:
+        out["motion_type"] = M.motion_type
+        for k in ("mass", "surface", "rv", "ra"):
+            out[k] = getattr(M, k)
+        for k in ("acc", "inertia", "applied_mom", "mom_axis", "mom", "forces"):
+            out[k] = np.array(getattr(M, k)[:])
+    return out
+
+
 class Shape(C.Structure):
     _fields_ = [("nv", C.c_int32), ("ne", C.c_int32), ("nf", C.c_int32), ("faces_len", C.c_int32),
                 ("vertices", _D), ("edges", C.POINTER(C.c_int32)), ("faces", C.POINTER(C.c_int32)),
@@ -261,6 +323,62 @@ class Engine:
                 D.quat[c] = float(qv)
             arr[k] = D
         self._call("set_drivers", C.c_int32(len(drivers)), arr)
+
+    def set_driver_motions(self, motions):
+        """motions: one dict per driver (keys of edb_driver_motion; motion_type by name)."""
+        self._keep_motion = []
+        arr = (DriverMotion * max(1, len(motions)))(*[make_motion(m, self._keep_motion) for m in motions])
+        self._call("set_driver_motions", C.c_int32(len(motions)), arr)
+
+    def set_driver_expr(self, driver, v=None, vrot=None, mom=None):
+        p = [(_V3)(*map(float, x)) if x is not None else None for x in (v, vrot, mom)]
+        self._call("set_driver_expr", C.c_int32(driver), *p)
+
+    def get_drivers(self, n):
+        D, M = (Driver * max(1, n))(), (DriverMotion * max(1, n))()
+        self._call("get_drivers", C.c_int32(n), D, M)
+        return [driver_to_dict(D[i], M[i]) for i in range(n)]
+
+    # -- driver operators of the time loop (config_numerical_schemes.msp:13-24)
+    def push_f_v_r_driver(self, time, dt):
+        self._call("push_f_v_r_driver", C.c_double(time), C.c_double(dt))
+
+    def push_f_v_driver(self, dt):
+        self._call("push_f_v_driver", C.c_double(dt))
+
+    def push_av_to_quat_driver(self, time, dt):
+        self._call("push_av_to_quat_driver", C.c_double(time), C.c_double(dt))
+
+    def reset_force_driver(self):
+        self._call("reset_force_driver")
+
+    def force_to_accel_driver(self, dt, system_mass):
+        self._call("force_to_accel_driver", C.c_double(dt), C.c_double(system_mass))
+
+    def driver_vertices(self):
+        self._call("driver_vertices")
+
+    def grid_rshape_driver(self):
+        self._call("grid_rshape_driver")
+
+    def backup_drivers(self):
+        self._call("backup_drivers")
+
+    def driver_displ_over(self, threshold):
+        r = C.c_uint64()
+        self._call("driver_displ_over", C.c_double(threshold), C.byref(r))
+        return r.value
+
+    def set_physical_time(self, t):
+        self._call("set_physical_time", C.c_double(t))
+
+    def get_physical_time(self):
+        t = C.c_double()
+        self._call("get_physical_time", C.byref(t))
+        return t.value
+
+    def set_system_mass(self, m):
+        self._call("set_system_mass", C.c_double(m))
 
     def set_shapes(self, shapes):
         arr = (Shape * len(shapes))(*shapes)

@@ -91,6 +91,41 @@ typedef struct edb_driver {
   double quat[4];      /* RSHAPE: orientation (w,x,y,z), rshape.hpp:370-384 */
 } edb_driver;
 
+/* MotionType: src/driver/include/exaDEM/motion_type.hpp:23-35 (same numbering) */
+enum { EDB_MOTION_STATIONARY = 0, EDB_MOTION_LINEAR_MOTION = 1, EDB_MOTION_COMPRESSIVE_FORCE = 2, EDB_MOTION_LINEAR_FORCE_MOTION = 3,
+       EDB_MOTION_PARTICLE = 4, EDB_MOTION_LINEAR_COMPRESSIVE_MOTION = 5, EDB_MOTION_TABULATED = 6, EDB_MOTION_SHAKER = 7,
+       EDB_MOTION_PENDULUM_MOTION = 8, EDB_MOTION_EXPRESSION = 9, EDB_MOTION_UNKNOWN = 10 };
+#define EDB_MAX_TAB 64 /* entries of a TABULATED trajectory kept on the device per driver */
+
+/* Motion of one driver = `Driver_params` (src/driver/include/exaDEM/driver_params.hpp:33-66) + the integrator state the
+ * reference keeps in the driver's own fields (SurfaceFields surface.hpp:30-46, BallFields ball.hpp, RShapeDriverFields
+ * rshape.hpp:37-52).  Entry i belongs to driver i of edb_set_drivers.  The values are taken AFTER the reference's
+ * `initialize()` checks (normalised motion_vector / shaker_dir, surface motion_vector aligned with the normal). */
+typedef struct edb_driver_motion {
+  int32_t motion_type;             /* EDB_MOTION_* */
+  int32_t n_tab;                   /* TABULATED: number of (time, position) entries, <= EDB_MAX_TAB */
+  double motion_vector[3];
+  double motion_start_threshold, motion_end_threshold;
+  double const_vel, const_force;   /* LINEAR_MOTION / LINEAR_FORCE_MOTION */
+  double sigma, damprate;          /* compressive motions */
+  const double* tab_time;          /* n_tab, sorted, tab_time[0] == 0 (driver_params.hpp:141-166) */
+  const double* tab_pos;           /* n_tab * 3 */
+  double omega, amplitude;         /* SHAKER, PENDULUM_MOTION */
+  double shaker_dir[3];
+  double pendulum_anchor_point[3], pendulum_initial_position[3], pendulum_swing_dir[3];
+  /* EXPRESSION (expr.hpp: tinyexpr strings): the strings stay on the host; the binding evaluates them at
+   * `time - motion_start_threshold` and hands the values over with edb_set_driver_expr before push_f_v_r_driver. */
+  int32_t expr_use_v, expr_use_vrot, expr_use_mom;
+  int32_t drive_by_mom;            /* RShapeDriverFields::drive_by_mom_ */
+  /* integrator state */
+  double mass;                     /* fields_.mass_ (surface, ball, rshape) */
+  double surface;                  /* fields_.surface_ (surface, rshape) */
+  double acc[3];                   /* fields_.acc_ (surface: scalar in acc[0]) */
+  double rv, ra;                   /* ball: radius velocity / acceleration */
+  double inertia[3], applied_mom[3], mom_axis[3], mom[3]; /* rshape */
+  double forces[3];                /* fields_.forces_: reaction summed by force_to_accel_driver (output of edb_get_drivers) */
+} edb_driver_motion;
+
 /* `shape` (src/shape/include/exaDEM/shape.hpp:50-69) flattened: faces as the [n0, v.., n1, v..] stream. */
 typedef struct edb_shape {
   int32_t nv, ne, nf, faces_len;
@@ -131,6 +166,13 @@ int edb_set_shapes(edb_context*, int32_t n, const edb_shape* shapes);         /*
  * The mesh shape arrays are an input (quirk Q12: the reference's STL->shape numbering is thread-order dependent). */
 int edb_set_driver_shapes(edb_context*, int32_t n, const edb_shape* shapes);
 
+/* motions of the drivers of the last edb_set_drivers call (n must match).  Without this call every driver is STATIONARY. */
+int edb_set_driver_motions(edb_context*, int32_t n, const edb_driver_motion* motions);
+/* EXPRESSION motion: values of the v / vrot / mom expressions for the coming push (Driver_params::driver_expr_*, driver_params.hpp:373-389) */
+int edb_set_driver_expr(edb_context*, int32_t driver, const double v[3], const double vrot[3], const double mom[3]);
+/* read the drivers back (state of the device-resident `drivers` slot): out / motions may be NULL; tab pointers are not filled */
+int edb_get_drivers(edb_context*, int32_t n, edb_driver* out, edb_driver_motion* motions);
+
 /* ---- slots: grid ------------------------------------------------------------------------------------- */
 int edb_upload_particles(edb_context*, const edb_particles* host);   /* full DEMFieldSet, any order */
 int edb_download_particles(edb_context*, edb_particles* host);       /* same order as uploaded/last rebuilt; see edb_get_order */
@@ -161,6 +203,33 @@ int edb_freeze_particles(edb_context*);                      /* [freeze_particle
 /* [particle_displ_over | vertex_displ_over] rebuild trigger: *over = #particles (vertices) moved >= threshold since
  * the last edb_update_particle_neighbors (which takes the backup, backup_dem.cpp:40-80); all-reduced over ranks. */
 int edb_displ_over(edb_context*, double threshold, uint64_t* over);
+/* ---- driver operators of the time loop (config_numerical_schemes.msp:13-24), SURVEY 8(f) rank 3.  The `drivers` slot lives on
+ * the device: these run as one small kernel each on the context stream, no host round trip. ---------------------------- */
+/* [push_f_v_r_driver] src/driver/push_f_v_r_driver.cpp:28-37 (only when is_motion_triggered(time + dt)); delta_t = dt * dt_scale */
+int edb_push_f_v_r_driver(edb_context*, double physical_time, double delta_t);
+int edb_push_f_v_driver(edb_context*, double delta_t);                          /* [push_f_v_driver] src/driver/push_f_v_driver.cpp:28-35 */
+int edb_push_av_to_quat_driver(edb_context*, double physical_time, double delta_t); /* [push_av_to_quat_driver] src/driver/push_av_to_quat_driver.cpp:27-36 */
+int edb_reset_force_driver(edb_context*);                                       /* [reset_force_driver] src/driver/reset_force_driver.cpp:38-42 */
+/* [force_to_accel_driver] src/driver/force_to_accel_driver.cpp:30-146: sums the reaction -f (and moment) of the driver waves of the
+ * last contact operator into the drivers that need them (deterministic block-ordered sum, all-reduced over the ranks), then
+ * Ball::f_ra / force_to_accel of every driver.  system_mass = the `system_mass` slot. */
+int edb_force_to_accel_driver(edb_context*, double dt, double system_mass);
+/* [driver_vertices] src/driver/driver_vertices.cu:28-35: world vertices of the non-stationary RShape drivers */
+int edb_driver_vertices(edb_context*);
+/* [grid_rshape_driver] src/driver/grid_stl_mesh.cpp:89-258: per-cell vertex / edge / face lists of the RShape drivers, built on the
+ * device (count -> scan -> fill -> per-list sort) from the current world vertices.  Also run by edb_update_particle_neighbors. */
+int edb_grid_rshape_driver(edb_context*);
+/* `physical_time` slot used by edb_run_verlet for the driver operators; advanced by dt per step (next_time_step) */
+int edb_set_physical_time(edb_context*, double t);
+int edb_get_physical_time(edb_context*, double* t);
+/* `system_mass` slot (output of simulation_state, simulation_state.cu:199) used by edb_run_verlet for force_to_accel_driver;
+ * when never set, the loop takes the mass sum of edb_simulation_state at its first step */
+int edb_set_system_mass(edb_context*, double m);
+int edb_backup_drivers(edb_context*);                                           /* [backup_drivers] src/driver/backup_drivers.cu */
+/* [driver_displ_over] src/driver/driver_displ_over.cu:60-243: *result = number of drivers (mesh: vertices) that moved >= threshold
+ * since the last backup (taken by edb_update_particle_neighbors / edb_backup_drivers) */
+int edb_driver_displ_over(edb_context*, double threshold, uint64_t* result);
+
 /* [compute_driver_force_moment] src/interaction/compute_driver_force_moment.cu:79-146: forces[n_drivers*3], moments[n_drivers*3] */
 int edb_compute_driver_force_moment(edb_context*, double* forces, double* moments);
 /* [stress_tensor] src/interaction/stress_tensor.cu:142-178: per-particle 3x3 (row-major, upload order), scaled by 1/volume outside */
@@ -179,7 +248,12 @@ int edb_simulation_state(edb_context*, int32_t symetric, edb_sim_state* out);
 /* Fused fast path = numerical_scheme_verlet (data/config/config_numerical_schemes.msp:6-30), `nsteps` iterations:
  * prolog -> (rebuild if displacement >= rcut_inc/2 | ghost_update_rq) -> [compute_vertices] -> reset+gravity+contact
  * +force_to_accel -> epilog.  rebuild_every > 0 forces a fixed rebuild schedule instead of the displacement trigger
- * (parity runs make the schedule an explicit input); 0 = trigger; <0 = never rebuild. */
+ * (parity runs make the schedule an explicit input); 0 = trigger; <0 = never rebuild.
+ * When a driver has a motion (edb_set_driver_motions) the loop runs the full macro operator by operator instead — prolog,
+ * push_f_v_r_driver, push_f_v_driver(dt/2), push_av_to_quat_driver, trigger (particle_displ_over | driver_displ_over), rebuild
+ * (backup_drivers, grid_rshape_driver) | ghost_update_rq + driver_vertices, reset_force_driver, contact, force_to_accel,
+ * force_to_accel_driver(system mass = sum of the particle masses), push_f_v_driver(dt/2), epilog — with one host read of the
+ * trigger per step. */
 int edb_run_verlet(edb_context*, double dt, const double g[3], double rcut_inc, int32_t symetric, int32_t nsteps,
                    int32_t rebuild_every, uint64_t* n_rebuilds);
 

@@ -337,8 +337,216 @@ struct Driver {
   int need_forces = 0;    // motion_type.hpp:133-141
   int shape = -1;         // RSHAPE: index into the mesh-shape table
   q4 quat{1, 0, 0, 0};    // RSHAPE: orientation
-  v3 center_proj() const { return offset * normal; }  // surface.hpp:149
+  v3 cproj{0, 0, 0};      // surface: center_proj_ = offset * normal at initialize() (surface.hpp:149), then moved by push_f_v_r
+  v3 center_proj() const { return cproj; }
+  // ---- motion: Driver_params (driver_params.hpp:33-66) + integrator state of the driver's fields_ ----
+  int motion = 0;         // MotionType (motion_type.hpp:23-35)
+  v3 motion_vector{0, 0, 0};
+  double t_start = 0, t_end = 1e300, const_vel = 0, const_force = 0, sigma = 0, damprate = 0, pmass = 0 /* Driver_params::mass_ */;
+  std::vector<double> tab_time;
+  std::vector<v3> tab_pos;
+  double omega = 0, amplitude = 0;
+  v3 shaker_dir{0, 0, 1}, pend_anchor{0, 0, 0}, pend_init{0, 0, 0}, pend_dir{0, 0, 0};
+  int expr_use_v = 0, expr_use_vrot = 0, expr_use_mom = 0, drive_by_mom = 0;
+  v3 expr_v{0, 0, 0}, expr_vrot{0, 0, 0}, expr_mom{0, 0, 0};
+  double mass = 1e300, surface = -1, rv = 0, ra = 0;
+  v3 acc{0, 0, 0}, inertia{0, 0, 0}, applied_mom{0, 0, 0}, mom_axis{0, 0, 0}, mom{0, 0, 0};
 };
+enum Motion { M_STATIONARY, M_LINEAR_MOTION, M_COMPRESSIVE_FORCE, M_LINEAR_FORCE_MOTION, M_PARTICLE, M_LINEAR_COMPRESSIVE_MOTION, M_TABULATED,
+              M_SHAKER, M_PENDULUM_MOTION, M_EXPRESSION, M_UNKNOWN };
+// motion_type.hpp:84-141
+static inline bool m_linear(int m) { return m == M_LINEAR_MOTION || m == M_LINEAR_FORCE_MOTION || m == M_LINEAR_COMPRESSIVE_MOTION; }
+static inline bool m_compressive(int m) { return m == M_COMPRESSIVE_FORCE || m == M_LINEAR_COMPRESSIVE_MOTION; }
+static inline bool m_force_motion(int m) { return m == M_PARTICLE || m == M_LINEAR_FORCE_MOTION; }
+static inline bool m_need_forces(int m) { return m_compressive(m) || m == M_PARTICLE || m == M_LINEAR_FORCE_MOTION; }
+// driver_params.hpp:82-84
+static inline bool motion_triggered(const Driver& d, double t) { return t >= d.t_start && t <= d.t_end; }
+// driver_params.hpp:277-310 (std::lower_bound = first entry >= time)
+static inline size_t tab_lower(const Driver& d, double time) {
+  size_t i = 0;
+  while (i < d.tab_time.size() && d.tab_time[i] < time) i++;
+  return i;
+}
+static inline v3 tab_to_position(const Driver& d, double time) {
+  const size_t it = tab_lower(d, time);
+  if (it == d.tab_time.size()) return d.tab_pos.back();
+  if (it == 0) return d.tab_pos[0];        // time <= tab_time[0]: the reference indexes tab_time_[-1] here (:284-288, UB); defined as the first entry
+  const size_t lo = it - 1, up = lo + 1;
+  if (up >= d.tab_time.size()) return d.tab_pos.back();
+  const double Dt = (time - d.tab_time[lo]) / (d.tab_time[up] - d.tab_time[lo]);
+  return (d.tab_pos[up] - d.tab_pos[lo]) * Dt + d.tab_pos[lo];
+}
+static inline v3 tab_to_velocity(const Driver& d, double time) {
+  const size_t it = tab_lower(d, time);
+  if (it == d.tab_time.size() || it == 0) return v3{0, 0, 0};   // it == 0: same UB as above, defined as "not moving yet"
+  const size_t lo = it - 1, up = lo + 1;
+  if (up >= d.tab_time.size()) return v3{0, 0, 0};
+  const double Dt = d.tab_time[up] - d.tab_time[lo];
+  return (d.tab_pos[up] - d.tab_pos[lo]) / Dt;
+}
+// driver_params.hpp:313-329
+static inline double shaker_signal(const Driver& d, double time) { time -= d.t_start; return d.amplitude * std::sin(d.omega * time); }
+static inline v3 shaker_velocity(const Driver& d, double time) { time -= d.t_start; return d.amplitude * d.omega * std::cos(d.omega * time) * d.shaker_dir; }
+// driver_params.hpp:340-371
+static inline void pendulum_offset_normal(const Driver& d, double time, double& offset, v3& normal) {
+  const v3 v1 = d.pend_anchor, v2 = d.pend_init;
+  const v3 v3_ = d.pend_init + d.pend_dir * shaker_signal(d, time);   // pendulum_signal == shaker_signal formula (:366-370)
+  if (dot(v3_, v2) < 1e-16) { offset = 0.0; normal = d.pend_dir; return; }
+  v3 v1v3 = v3_ - v1;
+  v1v3 = v1v3 / norm(v1v3);
+  const v3 proj = dot(v1v3, v2 - v1) * v1v3 + v1;
+  const v3 dir = proj - v2;
+  normal = dir / norm(dir);
+  offset = dot(v1, normal);
+}
+// driver_params.hpp:68-74
+static inline void update_forces(const Driver& d, v3& forces) {
+  if (d.motion == M_LINEAR_FORCE_MOTION) forces = (dot(forces, d.motion_vector) + d.const_force) * d.motion_vector;
+  else if (d.motion != M_PARTICLE) forces = v3{0, 0, 0};
+}
+static inline bool rshape_need_moment(const Driver& d) { return d.drive_by_mom || d.motion == M_PARTICLE; }   // rshape.hpp:406-413
+
+// push_f_v_r of every driver kind: cylinder.hpp:160-173, surface.hpp:262-299, ball.hpp:203-213, rshape.hpp:283-320
+static inline void driver_push_f_v_r(Driver& d, double time, double dt) {
+  const int m = d.motion;
+  if (d.kind == DRV_CYLINDER) {
+    if (m != M_STATIONARY && m == M_SHAKER) {
+      const double displ = shaker_signal(d, time + dt) - shaker_signal(d, time);
+      d.center = d.center + displ * d.shaker_dir;
+      d.vel = shaker_velocity(d, time + dt);
+    }
+  } else if (d.kind == DRV_SURFACE) {
+    if (m == M_STATIONARY) return;
+    if (m == M_PENDULUM_MOTION) {
+      double off; v3 nrm;
+      pendulum_offset_normal(d, time + dt, off, nrm);
+      d.normal = nrm; d.offset = off;
+      d.vel = v3{0, 0, 0};
+      d.cproj = d.normal * d.offset;
+      return;
+    }
+    double displ = dt * dot(d.vel, d.normal) + 0.5 * dt * dt * d.acc.x;
+    if (m == M_SHAKER) {
+      const double sn = shaker_signal(d, time + dt), sc = shaker_signal(d, time);
+      const double af = dot(d.shaker_dir, d.normal);
+      displ = (sn - sc) * af;
+      d.vel = shaker_velocity(d, time + dt);
+    }
+    d.center = d.center + displ * d.normal;
+    d.offset += displ;
+    d.cproj = d.cproj + displ * d.normal;
+  } else if (d.kind == DRV_BALL) {
+    if (m == M_TABULATED) {
+      d.center = tab_to_position(d, time);
+      d.vel = tab_to_velocity(d, time);
+    } else if (m != M_STATIONARY) {
+      if (m_compressive(m)) d.radius += dt * d.rv + 0.5 * dt * dt * d.ra;
+      d.center = d.center + dt * d.vel;
+    }
+  } else if (d.kind == DRV_RSHAPE) {
+    if (m == M_TABULATED) {
+      d.center = tab_to_position(d, time);
+      d.vel = tab_to_velocity(d, time);
+    } else if (m != M_STATIONARY) {
+      if (m == M_SHAKER) {
+        d.vel = cmul(shaker_velocity(d, time + dt), d.shaker_dir);   // Vec3d * Vec3d, rshape.hpp:302
+        d.acc = v3{0, 0, 0};
+      }
+      if (m == M_EXPRESSION && motion_triggered(d, time)) {
+        if (d.expr_use_v) d.vel = d.expr_v;
+        if (d.expr_use_vrot) d.vrot = d.expr_vrot;
+      }
+      d.center = d.center + (dt * d.vel + 0.5 * dt * dt * d.acc);
+    }
+  }
+}
+// push_f_v: cylinder.hpp:149-151 (nothing), surface.hpp:232-252, ball.hpp:219-234, rshape.hpp:262-281
+static inline void driver_push_f_v(Driver& d, double dt) {
+  const int m = d.motion;
+  if (d.kind == DRV_SURFACE) {
+    if (m == M_STATIONARY) d.vel = v3{0, 0, 0};
+    else if (m_compressive(m)) { if (d.sigma != 0) d.vel = d.vel + (dt * d.acc.x) * d.motion_vector; }
+    else if (m == M_LINEAR_MOTION) d.vel = d.const_vel * d.motion_vector;
+  } else if (d.kind == DRV_BALL) {
+    if (m_force_motion(m)) d.vel = d.acc * dt;
+    if (m == M_LINEAR_MOTION) d.vel = d.motion_vector * d.const_vel;
+    if (m_compressive(m)) {
+      if (m == M_COMPRESSIVE_FORCE) d.vel = v3{0, 0, 0};
+      if (d.sigma != 0) d.rv += dt * d.ra;
+    }
+  } else if (d.kind == DRV_RSHAPE) {
+    if (m == M_STATIONARY) d.vel = v3{0, 0, 0};
+    else {
+      if (m_force_motion(m)) d.vel = d.vel + d.acc * dt;
+      if (m == M_LINEAR_MOTION) d.vel = d.motion_vector * d.const_vel;
+      if (m_compressive(m) && d.sigma != 0) d.vel = d.vel + 0.5 * dt * d.acc;
+    }
+  }
+}
+// push_av_to_quat (RShape only, DriverProperty::use_quaternion): rshape.hpp:337-377 + driver_numerical_scheme_kernel.hpp:26-56
+static inline void driver_push_av_to_quat(Driver& d, double time, double dt) {
+  if (d.kind != DRV_RSHAPE) return;
+  auto push_q = [&](double dtq) {
+    const q4 dq = qdot(d.quat, d.vrot);
+    q4 Q{d.quat.w + dq.w * dtq, d.quat.x + dq.x * dtq, d.quat.y + dq.y * dtq, d.quat.z + dq.z * dtq};
+    const double nn = std::sqrt(Q.w * Q.w + Q.x * Q.x + Q.y * Q.y + Q.z * Q.z);
+    d.quat = {Q.w / nn, Q.x / nn, Q.y / nn, Q.z / nn};
+  };
+  if (rshape_need_moment(d)) {
+    if (d.motion == M_EXPRESSION && motion_triggered(d, time) && d.expr_use_mom) {
+      d.applied_mom = d.expr_mom;
+      const double mn = norm(d.applied_mom);
+      d.mom_axis = mn > 1e-12 ? d.applied_mom / mn : v3{0, 0, 0};
+    }
+    const v3 pm = d.motion == M_PARTICLE ? d.mom : dot(d.applied_mom + d.mom, d.mom_axis) * d.mom_axis;
+    const q4 Qi = qconj(d.quat);
+    const v3 o = qrot(Qi, d.vrot), M = qrot(Qi, pm), I = d.inertia;
+    const v3 dw{(M.x - (I.z - I.y) * o.y * o.z) / I.x, (M.y - (I.x - I.z) * o.z * o.x) / I.y, (M.z - (I.y - I.x) * o.x * o.y) / I.z};
+    const v3 arot = qrot(d.quat, dw);
+    d.vrot = d.vrot + arot * (dt * 0.5);
+    push_q(dt);
+    d.vrot = d.vrot + (dt * 0.5) * arot;
+    d.mom = v3{0, 0, 0};
+  } else {
+    push_q(dt);
+  }
+}
+// force_to_accel_driver.cpp:30-45 (+ Ball::f_ra ball.hpp:273-283, Surface surface.hpp:208-225, RShape rshape.hpp:220-259)
+static inline void driver_force_to_accel(Driver& d, double system_mass) {
+  const int m = d.motion;
+  if (d.kind == DRV_BALL) {
+    d.pmass = system_mass;
+    if (m_compressive(m) && d.pmass != 0) {
+      const double pi = 4 * std::atan(1);
+      const double s = 4 * pi * d.radius * d.radius;
+      d.ra = (norm(d.forces) - d.sigma * s - (d.damprate * d.rv)) / (d.pmass * 0.5);
+    }
+    if (m_force_motion(m)) { update_forces(d, d.forces); d.acc = d.forces / d.mass; }
+    else d.acc = v3{0, 0, 0};
+  } else if (d.kind == DRV_SURFACE) {
+    d.pmass = system_mass;
+    if (m_compressive(m)) {
+      if (d.pmass != 0) {
+        const v3 tmp = (d.forces - d.sigma * d.surface * d.motion_vector) / (d.pmass * 0.5);
+        d.acc.x = dot(tmp, d.motion_vector);
+      } else d.acc.x = 0;
+    }
+  } else if (d.kind == DRV_RSHAPE) {
+    if (m_compressive(m)) {
+      if (d.mass != 0) {
+        // Vec3d - double: the scalar is subtracted from every component (exanb operator, working definition)
+        const double ss = d.sigma * d.surface;
+        const v3 dv = d.damprate * d.vel;
+        const v3 num{d.forces.x - ss - dv.x, d.forces.y - ss - dv.y, d.forces.z - ss - dv.z};
+        const v3 tmp = num / (d.mass * 0.5);
+        d.acc = dot(tmp, d.motion_vector) * d.motion_vector;
+      }
+    } else if (m_force_motion(m)) {
+      update_forces(d, d.forces);
+      d.acc = d.forces / d.mass;
+    } else d.acc = v3{0, 0, 0};
+  }
+}
 // cylinder.hpp:225-235, surface.hpp:320-324, ball.hpp:292-296
 static inline bool driver_filter(const Driver& d, double rcut, v3 p) {
   if (d.kind == DRV_CYLINDER) {

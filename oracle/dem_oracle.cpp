@@ -85,6 +85,9 @@ struct Sim {
   std::vector<Driver> drivers;
   std::vector<Shape> shapes;
   int nvmax = 0;
+  std::vector<Driver> drivers_backup;           // backup_drvs slot (backup_drivers.cu)
+  double physical_time = 0, system_mass = 0;
+  bool have_system_mass = false;
   std::vector<Shape> mesh_shapes;               // RShapeDriver::shp_ (rshape.hpp)
   std::vector<std::vector<v3>> mesh_verts;      // per driver: RShapeDriver::vertices_ = position + orientation * v (rshape.hpp:381-384)
 
@@ -578,8 +581,11 @@ static inline void contact_one(Sim& s, Inter& I, double dt, Acc& acc) {
         acc.add(s.mom[j], moments(c.cp, pj, -f, -I.mom));
         acc.add(s.f[j], -f);
       }
-    } else if (s.drivers[I.id_j].need_forces) {
-      acc.add(s.drivers[I.id_j].forces, -f);
+    } else {
+      Driver& D = s.drivers[I.id_j];
+      if (D.need_forces) acc.add(D.forces, -f);
+      // contact_sphere.hpp:387-389 (spheres against an RShape that needs its moment)
+      if (!poly && t >= 7 && D.kind == DRV_RSHAPE && rshape_need_moment(D)) acc.add(D.mom, moments(c.cp, D.center, -f, -I.mom));
     }
   } else {
     I.ft = {0, 0, 0}; I.mom = {0, 0, 0};
@@ -759,8 +765,10 @@ int orc_set_drivers(orc_sim* h, int32_t n, const edb_driver* d) {
     D.vel = {d[i].vel[0], d[i].vel[1], d[i].vel[2]}; D.vrot = {d[i].vrot[0], d[i].vrot[1], d[i].vrot[2]};
     D.shape = d[i].shape;
     D.quat = {d[i].quat[0], d[i].quat[1], d[i].quat[2], d[i].quat[3]};
+    D.cproj = D.offset * D.normal;   // surface.hpp:149
     s.drivers.push_back(D);
   }
+  s.drivers_backup.clear();
   s.mesh_verts.assign(s.drivers.size(), {});
   for (size_t k = 0; k < s.drivers.size(); k++) {
     const Driver& D = s.drivers[k];
@@ -949,27 +957,190 @@ int orc_simulation_state(orc_sim* h, int32_t symetric, edb_sim_state* out) {
   return 0;
 }
 
+// ---- driver operators of the time loop (src/driver/*.cpp), SURVEY 8(f) rank 3 ----
+static bool drivers_move(const Sim& s) {
+  for (const Driver& d : s.drivers) if (d.motion != M_STATIONARY || (d.kind == DRV_RSHAPE && rshape_need_moment(d))) return true;
+  return false;
+}
+static void push_f_v_r_driver(Sim& s, double time, double dt) {   // push_f_v_r_driver.cpp:28-37
+  for (Driver& d : s.drivers) if (motion_triggered(d, time + dt)) driver_push_f_v_r(d, time, dt);
+}
+static void push_f_v_driver(Sim& s, double dt) { for (Driver& d : s.drivers) driver_push_f_v(d, dt); }   // push_f_v_driver.cpp:28-35
+static void push_av_to_quat_driver(Sim& s, double time, double dt) { for (Driver& d : s.drivers) driver_push_av_to_quat(d, time, dt); }
+static void reset_force_driver(Sim& s) { for (Driver& d : s.drivers) d.forces = {0, 0, 0}; }   // reset_force_driver.cpp:38-42
+static void force_to_accel_driver(Sim& s, double system_mass) { for (Driver& d : s.drivers) driver_force_to_accel(d, system_mass); }
+// driver_vertices.cu:28-35,62-78: vertices = center + quat * v for the non-stationary meshes (rshape.hpp:419)
+static void driver_vertices(Sim& s) {
+  for (size_t k = 0; k < s.drivers.size(); k++) {
+    const Driver& D = s.drivers[k];
+    if (D.kind != DRV_RSHAPE) continue;
+    if (D.motion == M_STATIONARY && is_zero(D.vrot)) continue;
+    const auto& lv = s.mesh_shapes[D.shape].v;
+    for (size_t i = 0; i < lv.size(); i++) s.mesh_verts[k][i] = D.center + qrot(D.quat, lv[i]);
+  }
+}
+// driver_displ_over.cu:60-243 (stops at the first driver that moved, :233-236)
+static uint64_t driver_displ_over(Sim& s, double thr) {
+  const double r2 = thr * thr;
+  uint64_t local = 0;
+  for (size_t i = 0; i < s.drivers_backup.size() && local == 0; i++) {
+    const Driver &a = s.drivers[i], &b = s.drivers_backup[i];
+    if (a.kind == DRV_SURFACE) {
+      v3 d = a.cproj - b.cproj;
+      if (b.motion == M_PENDULUM_MOTION) {
+        auto isect = [](v3 pp, v3 pn, v3 lp, v3 ld) { const v3 delta = pp - lp; const double t = dot(delta, pn) / dot(ld, pn); return lp + t * ld; };
+        const v3 pa = isect(a.pend_anchor, a.normal, a.pend_init, a.pend_dir), pb = isect(a.pend_anchor, b.normal, a.pend_init, a.pend_dir);
+        d = pb - pa;
+      }
+      local += dot(d, d) >= r2 ? 1 : 0;
+    } else if (a.kind == DRV_BALL) {
+      const v3 d = a.center - b.center;
+      if (m_compressive(a.motion)) { const double rd = a.radius - b.radius; local += rd * rd >= r2 ? 1 : 0; }
+      else local += dot(d, d) >= r2 ? 1 : 0;
+    } else if (a.kind == DRV_RSHAPE) {
+      if (a.center.x == b.center.x && a.center.y == b.center.y && a.center.z == b.center.z && a.quat.w == b.quat.w && a.quat.x == b.quat.x &&
+          a.quat.y == b.quat.y && a.quat.z == b.quat.z) continue;
+      for (const v3& lv : s.mesh_shapes[a.shape].v) {
+        const v3 d = (a.center + qrot(a.quat, 1.0 * lv)) - (b.center + qrot(b.quat, 1.0 * lv));
+        if (dot(d, d) >= r2) local++;
+      }
+    }   // cylinder: 0 (quirk Q14)
+  }
+  return local;
+}
+static double mass_sum(const Sim& s) { double m = 0; for (size_t p = 0; p < s.nreal; p++) m += s.mass[p]; return m; }
+
 int orc_run_verlet(orc_sim* h, double dt, const double* g, double rcut_inc, int32_t symetric, int32_t nsteps, int32_t rebuild_every, uint64_t* n_rebuilds) {
   Sim& s = *(Sim*)h;
   uint64_t nb = 0;
+  const bool moving = drivers_move(s);
+  if (moving && !s.have_system_mass) { s.system_mass = mass_sum(s); s.have_system_mass = true; }
+  if (moving && s.drivers_backup.empty()) s.drivers_backup = s.drivers;
   for (int it = 0; it < nsteps; it++) {
     prolog(s, dt);
+    if (moving) {   // config_numerical_schemes.msp:13-15
+      push_f_v_r_driver(s, s.physical_time, dt);
+      push_f_v_driver(s, 0.5 * dt);
+      push_av_to_quat_driver(s, s.physical_time, dt);
+    }
     bool rb;
     if (rebuild_every > 0) rb = ((it + 1) % rebuild_every) == 0;
     else if (rebuild_every < 0) rb = false;
-    else rb = displ_over(s, 0.5 * rcut_inc) > 0;
-    if (rb) { rebuild(s, rcut_inc, symetric); nb++; }
-    else { ghost_refresh(s, false); compute_vertices(s); }
+    else rb = displ_over(s, 0.5 * rcut_inc) > 0 || (moving && driver_displ_over(s, 0.5 * rcut_inc) > 0);
+    if (rb) {
+      if (moving) { s.drivers_backup = s.drivers; driver_vertices(s); }   // backup_drivers; ghost_full_update -> compute_all_vertices
+      rebuild(s, rcut_inc, symetric); nb++;
+    } else { ghost_refresh(s, false); compute_vertices(s); if (moving) driver_vertices(s); }
+    if (moving) reset_force_driver(s);
     reset_fm(s);
     gravity(s, g);
     contact_all(s, dt);
     force_to_accel(s);
+    if (moving) { force_to_accel_driver(s, s.system_mass); push_f_v_driver(s, 0.5 * dt); }
     epilog(s, dt);
     s.particle_steps += s.nreal;
+    s.physical_time += dt;
   }
   if (n_rebuilds) *n_rebuilds = nb;
   return 0;
 }
+
+static inline v3 V3(const double* p) { return {p[0], p[1], p[2]}; }
+static inline void S3(double* o, v3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+int orc_set_driver_motions(orc_sim* h, int32_t n, const edb_driver_motion* m) {
+  Sim& s = *(Sim*)h;
+  if (n != (int)s.drivers.size()) { s.err = "edb_set_driver_motions: n differs from the driver count"; return EDB_ERR_INVALID; }
+  for (int i = 0; i < n; i++) {
+    Driver& D = s.drivers[i];
+    D.motion = m[i].motion_type;
+    D.motion_vector = V3(m[i].motion_vector);
+    D.t_start = m[i].motion_start_threshold; D.t_end = m[i].motion_end_threshold;
+    D.const_vel = m[i].const_vel; D.const_force = m[i].const_force; D.sigma = m[i].sigma; D.damprate = m[i].damprate;
+    D.tab_time.assign(m[i].tab_time, m[i].tab_time + (m[i].tab_time ? m[i].n_tab : 0));
+    D.tab_pos.clear();
+    for (int k = 0; k < (m[i].tab_pos ? m[i].n_tab : 0); k++) D.tab_pos.push_back(V3(m[i].tab_pos + 3 * k));
+    D.omega = m[i].omega; D.amplitude = m[i].amplitude; D.shaker_dir = V3(m[i].shaker_dir);
+    D.pend_anchor = V3(m[i].pendulum_anchor_point); D.pend_init = V3(m[i].pendulum_initial_position); D.pend_dir = V3(m[i].pendulum_swing_dir);
+    D.expr_use_v = m[i].expr_use_v; D.expr_use_vrot = m[i].expr_use_vrot; D.expr_use_mom = m[i].expr_use_mom; D.drive_by_mom = m[i].drive_by_mom;
+    D.mass = m[i].mass; D.surface = m[i].surface; D.acc = V3(m[i].acc); D.rv = m[i].rv; D.ra = m[i].ra;
+    D.inertia = V3(m[i].inertia); D.applied_mom = V3(m[i].applied_mom); D.mom_axis = V3(m[i].mom_axis); D.mom = V3(m[i].mom);
+    D.need_forces = m_need_forces(D.motion) ? 1 : 0;
+  }
+  return 0;
+}
+int orc_set_driver_expr(orc_sim* h, int32_t d, const double* v, const double* vrot, const double* mom) {
+  Sim& s = *(Sim*)h;
+  if (d < 0 || d >= (int)s.drivers.size()) return EDB_ERR_INVALID;
+  if (v) s.drivers[d].expr_v = V3(v);
+  if (vrot) s.drivers[d].expr_vrot = V3(vrot);
+  if (mom) s.drivers[d].expr_mom = V3(mom);
+  return 0;
+}
+int orc_get_drivers(orc_sim* h, int32_t n, edb_driver* out, edb_driver_motion* mo) {
+  Sim& s = *(Sim*)h;
+  if (n != (int)s.drivers.size()) return EDB_ERR_INVALID;
+  for (int i = 0; i < n; i++) {
+    const Driver& D = s.drivers[i];
+    if (out) {
+      edb_driver& o = out[i];
+      o = edb_driver{};
+      o.kind = D.kind; o.need_forces = D.need_forces; o.radius = D.radius; S3(o.axis, D.axis); S3(o.center, D.center);
+      o.offset = D.offset; S3(o.normal, D.normal); S3(o.vel, D.vel); S3(o.vrot, D.vrot); o.shape = D.shape;
+      o.quat[0] = D.quat.w; o.quat[1] = D.quat.x; o.quat[2] = D.quat.y; o.quat[3] = D.quat.z;
+    }
+    if (mo) {
+      edb_driver_motion& o = mo[i];
+      o = edb_driver_motion{};
+      o.motion_type = D.motion; o.n_tab = (int)D.tab_time.size(); S3(o.motion_vector, D.motion_vector);
+      o.motion_start_threshold = D.t_start; o.motion_end_threshold = D.t_end; o.const_vel = D.const_vel; o.const_force = D.const_force;
+      o.sigma = D.sigma; o.damprate = D.damprate; o.omega = D.omega; o.amplitude = D.amplitude; S3(o.shaker_dir, D.shaker_dir);
+      S3(o.pendulum_anchor_point, D.pend_anchor); S3(o.pendulum_initial_position, D.pend_init); S3(o.pendulum_swing_dir, D.pend_dir);
+      o.expr_use_v = D.expr_use_v; o.expr_use_vrot = D.expr_use_vrot; o.expr_use_mom = D.expr_use_mom; o.drive_by_mom = D.drive_by_mom;
+      o.mass = D.mass; o.surface = D.surface; S3(o.acc, D.acc); o.rv = D.rv; o.ra = D.ra;
+      S3(o.inertia, D.inertia); S3(o.applied_mom, D.applied_mom); S3(o.mom_axis, D.mom_axis); S3(o.mom, D.mom); S3(o.forces, D.forces);
+    }
+  }
+  return 0;
+}
+// One operator on one driver through the structs of the ABI (test interface mirrored by oracle/ref_math.cpp:ref_driver_motion_op; for a
+// surface center_proj_ travels in the mom slot).  op 0 push_f_v_r (trigger-gated), 1 push_f_v, 2 push_av_to_quat, 3 force_to_accel.
+int orc_driver_motion_op(int op, double time, double dt, double system_mass, edb_driver* d, edb_driver_motion* m) {
+  Sim s;
+  edb_driver din = *d;
+  if (din.kind == EDB_DRIVER_RSHAPE) { s.mesh_shapes.resize(1); din.shape = 0; }
+  double cyl_center[3] = {d->center[0], d->center[1], d->center[2]};
+  if (orc_set_drivers((orc_sim*)&s, 1, &din)) return EDB_ERR_INVALID;
+  Driver& D = s.drivers[0];
+  if (D.kind == DRV_CYLINDER) D.center = V3(cyl_center);   // the test passes the initialised centre (already multiplied by the axis)
+  orc_set_driver_motions((orc_sim*)&s, 1, m);
+  D.forces = V3(m->forces);
+  if (D.kind == DRV_SURFACE) { D.cproj = V3(m->mom); D.mom = {0, 0, 0}; }
+  if (op == 0) { if (motion_triggered(D, time + dt)) driver_push_f_v_r(D, time, dt); }
+  else if (op == 1) driver_push_f_v(D, dt);
+  else if (op == 2) driver_push_av_to_quat(D, time, dt);
+  else driver_force_to_accel(D, system_mass);
+  const v3 cproj = D.cproj;
+  orc_get_drivers((orc_sim*)&s, 1, d, m);
+  if (D.kind == DRV_SURFACE) S3(m->mom, cproj);
+  return 0;
+}
+int orc_push_f_v_r_driver(orc_sim* h, double t, double dt) { push_f_v_r_driver(*(Sim*)h, t, dt); return 0; }
+int orc_push_f_v_driver(orc_sim* h, double dt) { push_f_v_driver(*(Sim*)h, dt); return 0; }
+int orc_push_av_to_quat_driver(orc_sim* h, double t, double dt) { push_av_to_quat_driver(*(Sim*)h, t, dt); return 0; }
+int orc_reset_force_driver(orc_sim* h) { reset_force_driver(*(Sim*)h); return 0; }
+int orc_force_to_accel_driver(orc_sim* h, double, double system_mass) { force_to_accel_driver(*(Sim*)h, system_mass); return 0; }
+int orc_driver_vertices(orc_sim* h) { driver_vertices(*(Sim*)h); return 0; }
+int orc_grid_rshape_driver(orc_sim*) { return 0; }   // the oracle enumerates mesh primitives exhaustively: the set is defined by the filters
+int orc_backup_drivers(orc_sim* h) { Sim& s = *(Sim*)h; s.drivers_backup = s.drivers; return 0; }
+int orc_driver_displ_over(orc_sim* h, double thr, uint64_t* r) {
+  Sim& s = *(Sim*)h;
+  if (s.drivers_backup.empty()) s.drivers_backup = s.drivers;
+  *r = driver_displ_over(s, thr);
+  return 0;
+}
+int orc_set_physical_time(orc_sim* h, double t) { ((Sim*)h)->physical_time = t; return 0; }
+int orc_get_physical_time(orc_sim* h, double* t) { *t = ((Sim*)h)->physical_time; return 0; }
+int orc_set_system_mass(orc_sim* h, double m) { Sim& s = *(Sim*)h; s.system_mass = m; s.have_system_mass = true; return 0; }
 
 int orc_interaction_counts(orc_sim* h, uint64_t* counts, uint64_t* active) {
   Sim& s = *(Sim*)h;

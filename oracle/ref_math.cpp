@@ -11,6 +11,8 @@
 //   src/shape/include/exaDEM/type/OBB.hpp, basic_types.hpp (OBB::intersect, compute_obb)
 //   src/forcefield/include/exaDEM/forcefield/{common_kernels,contact_force}.hpp (Hooke law)
 //   src/driver/include/exaDEM/{cylinder,surface,ball}.hpp (driver filter/detector)
+//   src/driver/include/exaDEM/{cylinder,surface,ball,rshape,driver_params}.hpp (driver motion integrators: push_f_v_r, push_f_v,
+//     push_av_to_quat, force_to_accel / f_ra) — applied exactly as the operators of src/driver/push_*_driver.cpp, force_to_accel_driver.cpp do
 // The Onika/exaNBody/yaml-cpp/tinyexpr/MPI headers they include are absent from /root/reference;
 // oracle/shim/ provides minimal stand-ins (vector algebra = working definition, parity risk R1).
 #include <exaDEM/shape_detection.hpp>
@@ -19,6 +21,8 @@
 #include <exaDEM/cylinder.hpp>
 #include <exaDEM/surface.hpp>
 #include <exaDEM/ball.hpp>
+#include <exaDEM/rshape.hpp>
+#include "../include/exadem_b200.h"
 #include <cstring>
 
 using exanb::Vec3d;
@@ -156,6 +160,72 @@ int ref_driver_detector(int kind, const double* prm, double rcut, const double* 
   else { exaDEM::BallFields bf; bf.radius_ = prm[0]; bf.center_ = V(prm + 1); exaDEM::MotionType mt = exaDEM::STATIONARY; exaDEM::Ball d(bf, mt); r = d.detector(rcut, V(p)); }
   out7[0] = std::get<1>(r); S(out7 + 1, std::get<2>(r)); S(out7 + 4, std::get<3>(r));
   return std::get<0>(r) ? 1 : 0;
+}
+
+// ---- driver motion: one operator of the time loop applied to ONE driver by the reference's own member functions ----
+// op 0 = push_f_v_r_driver (PushFVRDriverFunc, push_f_v_r_driver.cpp:28-37), 1 = push_f_v_driver (push_f_v_driver.cpp:28-35),
+// 2 = push_av_to_quat_driver (push_av_to_quat_driver.cpp:27-36), 3 = force_to_accel_driver's ForceToAccelDriverFunc
+// (force_to_accel_driver.cpp:30-45) with fields_.forces_ = forces.  In/out through the edb_driver / edb_driver_motion structs.
+}  // extern "C"
+static exaDEM::Driver_params mk_params(const edb_driver_motion& m) {
+  exaDEM::Driver_params p;
+  p.motion_vector_ = V(m.motion_vector); p.motion_start_threshold_ = m.motion_start_threshold; p.motion_end_threshold_ = m.motion_end_threshold;
+  p.const_vel_ = m.const_vel; p.const_force_ = m.const_force; p.sigma_ = m.sigma; p.damprate_ = m.damprate;
+  for (int k = 0; k < m.n_tab; k++) { p.tab_time_.push_back(m.tab_time[k]); p.tab_pos_.push_back(V(m.tab_pos + 3 * k)); }
+  p.omega_ = m.omega; p.amplitude_ = m.amplitude; p.shaker_dir_ = V(m.shaker_dir);
+  p.pendulum_anchor_point_ = V(m.pendulum_anchor_point); p.pendulum_initial_position_ = V(m.pendulum_initial_position);
+  p.pendulum_swing_dir_ = V(m.pendulum_swing_dir);
+  return p;
+}
+template <class D>
+static void apply_op(D& drv, exaDEM::Driver_params& p, int op, double time, double dt, double system_mass) {
+  if (op == 0) { if (p.is_motion_triggered(time + dt)) drv.push_f_v_r(p, time, dt); }
+  else if (op == 1) drv.push_f_v(p, dt);
+  else if (op == 3) {
+    if constexpr (std::is_same_v<D, exaDEM::Ball>) { p.mass_ = system_mass; drv.f_ra(p, dt); }
+    if constexpr (std::is_same_v<D, exaDEM::Surface>) { p.mass_ = system_mass; }
+    drv.force_to_accel(p);
+  }
+}
+extern "C" {
+int ref_driver_motion_op(int op, double time, double dt, double system_mass, edb_driver* d, edb_driver_motion* m) {
+  exaDEM::Driver_params p = mk_params(*m);
+  const exaDEM::MotionType mt = (exaDEM::MotionType)m->motion_type;
+  if (d->kind == EDB_DRIVER_CYLINDER) {
+    exaDEM::Cylinder c; c.motion_type_ = mt;
+    c.fields_.radius_ = d->radius; c.fields_.axis_ = V(d->axis); c.fields_.center_ = V(d->center); c.fields_.vel_ = V(d->vel); c.fields_.vrot_ = V(d->vrot);
+    apply_op(c, p, op, time, dt, system_mass);
+    S(d->center, c.fields_.center_); S(d->vel, c.fields_.vel_);
+  } else if (d->kind == EDB_DRIVER_SURFACE) {
+    exaDEM::Surface s; s.motion_type_ = mt;
+    s.fields_.offset_ = d->offset; s.fields_.normal_ = V(d->normal); s.fields_.center_ = V(d->center); s.fields_.vel_ = V(d->vel); s.fields_.vrot_ = V(d->vrot);
+    s.fields_.forces_ = V(m->forces); s.fields_.mass_ = m->mass; s.fields_.surface_ = m->surface; s.fields_.acc_ = m->acc[0];
+    s.fields_.center_proj_ = V(m->mom);   // center_proj_ travels in the (otherwise unused for a surface) mom slot of this test interface
+    apply_op(s, p, op, time, dt, system_mass);
+    d->offset = s.fields_.offset_; S(d->normal, s.fields_.normal_); S(d->center, s.fields_.center_); S(d->vel, s.fields_.vel_);
+    m->acc[0] = s.fields_.acc_; S(m->mom, s.fields_.center_proj_);
+  } else if (d->kind == EDB_DRIVER_BALL) {
+    exaDEM::BallFields bf; bf.radius_ = d->radius; bf.center_ = V(d->center); bf.vel_ = V(d->vel); bf.vrot_ = V(d->vrot);
+    bf.forces_ = V(m->forces); bf.mass_ = m->mass; bf.rv_ = m->rv; bf.ra_ = m->ra; bf.acc_ = V(m->acc);
+    exaDEM::MotionType mtv = mt;
+    exaDEM::Ball b(bf, mtv);
+    apply_op(b, p, op, time, dt, system_mass);
+    d->radius = b.fields_.radius_; S(d->center, b.fields_.center_); S(d->vel, b.fields_.vel_);
+    m->rv = b.fields_.rv_; m->ra = b.fields_.ra_; S(m->acc, b.fields_.acc_); S(m->forces, b.fields_.forces_);
+  } else if (d->kind == EDB_DRIVER_RSHAPE) {
+    exaDEM::RShapeDriver r; r.motion_type_ = mt;
+    auto& f = r.fields_;
+    f.center_ = V(d->center); f.vel_ = V(d->vel); f.vrot_ = V(d->vrot); f.forces_ = V(m->forces);
+    f.quat_ = Quaternion{d->quat[0], d->quat[1], d->quat[2], d->quat[3]};
+    f.acc_ = V(m->acc); f.surface_ = m->surface; f.mass_ = m->mass; f.drive_by_mom_ = m->drive_by_mom != 0;
+    f.applied_mom_ = V(m->applied_mom); f.mom_ = V(m->mom); f.inertia_ = V(m->inertia); f.mom_axis_ = V(m->mom_axis);
+    if (op == 2) r.push_av_to_quat(p, time, dt);
+    else apply_op(r, p, op, time, dt, system_mass);
+    S(d->center, f.center_); S(d->vel, f.vel_); S(d->vrot, f.vrot_);
+    d->quat[0] = f.quat_.w; d->quat[1] = f.quat_.x; d->quat[2] = f.quat_.y; d->quat[3] = f.quat_.z;
+    S(m->acc, f.acc_); S(m->forces, f.forces_); S(m->mom, f.mom_); S(m->applied_mom, f.applied_mom_); S(m->mom_axis, f.mom_axis_);
+  }
+  return 0;
 }
 
 }  // extern "C"

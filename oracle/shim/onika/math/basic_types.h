@@ -31,6 +31,8 @@ inline bool operator!=(const Vec3d& a, const Vec3d& b) { return !(a == b); }
 inline Vec3d operator+(const Vec3d& a, const Vec3d& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
 inline Vec3d operator-(const Vec3d& a, const Vec3d& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
 inline Vec3d operator-(const Vec3d& a) { return {-a.x, -a.y, -a.z}; }
+// Vec3d - double (used by RShapeDriver::force_to_accel, rshape.hpp:230): working definition = component-wise (risk R1)
+inline Vec3d operator-(const Vec3d& a, double s) { return {a.x - s, a.y - s, a.z - s}; }
 inline Vec3d operator*(const Vec3d& a, double s) { return {a.x * s, a.y * s, a.z * s}; }
 inline Vec3d operator*(double s, const Vec3d& a) { return {s * a.x, s * a.y, s * a.z}; }
 inline Vec3d operator*(const Vec3d& a, const Vec3d& b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }

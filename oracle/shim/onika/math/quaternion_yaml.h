@@ -1,0 +1,2 @@
+#pragma once
+#include <onika/math/basic_types.h>
