@@ -597,6 +597,11 @@ struct Comm {
     if (!comm) return;
     NCK(g_nccl.AllReduce(d, d, 1, ncclUint64, ncclSum, comm, st));
   }
+  // driver reactions (force_to_accel_driver.cpp:128-139: MPI_Allreduce of 6 doubles per driver), in place on the stream
+  void allreduce_sum_f64_dev(double* d, size_t n, cudaStream_t st) {
+    if (!comm || n == 0) return;
+    NCK(g_nccl.AllReduce(d, d, n, ncclFloat64, ncclSum, comm, st));
+  }
   uint64_t allreduce_sum_u64(uint64_t v, cudaStream_t st) {
     if (!comm) return v;
     d_red.ensure(2);

@@ -143,7 +143,7 @@ struct ShapesView {
 // cell_off/cell_data: per (mesh, grid cell, kind in {vertex, edge, face}) the primitives that can reach a particle of the cell —
 // the role of the reference's RShapeDriverGridCellIndexes (rshape_grid.hpp, grid_stl_mesh.cpp:150-251).
 struct MeshDev {
-  int nv, ne, nf, pad;
+  int nv, ne, nf, drv;  // drv = index of the owning driver
   int v0, e0, f0, fi0;  // offsets into the pooled mesh arrays
   double radius;        // Minkowski radius (homothety 1)
 };

@@ -12,13 +12,14 @@
 #include "kernels_nbh_poly.cuh"
 #include "kernels_migrate.cuh"
 #include "kernels_twin.cuh"
+#include "kernels_driver.cuh"
 #include "comm.cuh"
 
 using namespace edb;
 
 static thread_local std::string g_create_error;
 static_assert(sizeof(edb_config) == 152 && sizeof(edb_interaction) == 104 && sizeof(edb_contact_params) == 64 &&
-                  sizeof(edb_particles) == 8 + 31 * 8,
+                  sizeof(edb_particles) == 8 + 31 * 8 && sizeof(edb_driver) == 184 && sizeof(edb_driver_motion) == 400,
               "C ABI struct layout changed: update include/exadem_b200.h users and exadem_b200/capi.py");
 
 // wave order of the contact operators (classifier_for_all.hpp:116-156 as called by contact_force_sphere.cu.in:132-188 and
@@ -101,6 +102,18 @@ struct edb_context {
   DevBuf<uint32_t> d_mcell_off;
   MeshView M{};
   bool mesh_dirty = false;
+  // device-resident `drivers` slot: motions + integrator state (kernels_driver.cuh), backup for driver_displ_over
+  std::vector<DriverMotion> h_mo;
+  std::vector<int> h_drv_shape;                   // per driver: the caller's mesh-shape index (Driver::shape holds the mesh slot)
+  DevBuf<DriverMotion> mo, mo_backup;
+  DevBuf<Driver> drv_backup;
+  DevBuf<double4> d_mlocal;                       // pooled local mesh vertices (same offsets as d_mverts)
+  std::vector<double4> h_mlocal;
+  DevBuf<uint32_t> d_mprim_start, d_mcell_cnt;
+  DevBuf<double> drv_sums;
+  bool drivers_moving = false, have_drv_backup = false;
+  double physical_time = 0, system_mass = 0;
+  bool have_system_mass = false;
   // staging for host transfers
   DevBuf<double> stage;
   DevBuf<uint64_t> stage_u64;
@@ -399,6 +412,61 @@ extern "C" int edb_set_law(edb_context* c, int32_t law) {
   c->law = law;
   API_END(c)
 }
+// Static tables of the RShape meshes (topology, local vertices) + the world vertices at the pose given to edb_set_drivers.  From here on
+// the world vertices are owned by the device (k_driver_vertices follows the drivers' motion).
+static void upload_mesh_tables(edb_context* c) {
+  const int nm = (int)c->h_md.size();
+  c->M = MeshView{};
+  if (nm == 0) return;
+  c->d_md.ensure(nm); c->d_mverts.ensure(c->h_mverts.size() + 1); c->d_mlocal.ensure(c->h_mlocal.size() + 1);
+  c->d_medges.ensure(c->h_medges.size() + 1);
+  c->d_mfoff.ensure(c->h_mfoff.size() + 1); c->d_mfn.ensure(c->h_mfn.size() + 1); c->d_mfidx.ensure(c->h_mfidx.size() + 1);
+  CK(cudaMemcpy(c->d_md.p, c->h_md.data(), nm * sizeof(MeshDev), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_mverts.p, c->h_mverts.data(), c->h_mverts.size() * sizeof(double4), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_mlocal.p, c->h_mlocal.data(), c->h_mlocal.size() * sizeof(double4), cudaMemcpyHostToDevice));
+  if (!c->h_medges.empty()) CK(cudaMemcpy(c->d_medges.p, c->h_medges.data(), c->h_medges.size() * 4, cudaMemcpyHostToDevice));
+  if (!c->h_mfn.empty()) {
+    CK(cudaMemcpy(c->d_mfoff.p, c->h_mfoff.data(), c->h_mfoff.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_mfn.p, c->h_mfn.data(), c->h_mfn.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_mfidx.p, c->h_mfidx.data(), c->h_mfidx.size() * 4, cudaMemcpyHostToDevice));
+  }
+  std::vector<uint32_t> ps(nm + 1, 0);
+  for (int m = 0; m < nm; m++) ps[m + 1] = ps[m] + (uint32_t)(c->h_md[m].nv + c->h_md[m].ne + c->h_md[m].nf);
+  c->d_mprim_start.ensure(nm + 1);
+  CK(cudaMemcpy(c->d_mprim_start.p, ps.data(), (nm + 1) * 4, cudaMemcpyHostToDevice));
+}
+
+// [grid_rshape_driver] per-cell primitive lists of the RShape meshes, built on the device from the current world vertices
+// (kernels_driver.cuh: count -> scan -> fill -> per-list sort).  The reference builds them on the host with OpenMP locks
+// (grid_stl_mesh.cpp:150-251) at every update_particles_full (config_move_particles.msp:92-94).
+static void build_mesh_grid(edb_context* c) {
+  const GridDev& G = c->G;
+  const int nm = (int)c->h_md.size();
+  c->M = MeshView{};
+  c->mesh_dirty = false;
+  if (nm == 0) return;
+  uint32_t nprim = 0;
+  for (int m = 0; m < nm; m++) nprim += (uint32_t)(c->h_md[m].nv + c->h_md[m].ne + c->h_md[m].nf);
+  const size_t nlists = (size_t)nm * G.ncell * 3;
+  if (nlists + 1 > 0xffffffffull) throw StateError{EDB_ERR_CAPACITY, "mesh cell table exceeds 2^32 lists"};
+  MeshGridArgs A{c->d_md.p, c->d_mverts.p, c->d_medges.p, c->d_mfoff.p, c->d_mfn.p, c->d_mfidx.p, nm, nprim, c->d_mprim_start.p, G,
+                 std::max(c->cfg.cell_size, std::max(G.cs[0], std::max(G.cs[1], G.cs[2])))};
+  c->d_mcell_cnt.ensure(nlists + 1);
+  c->d_mcell_off.ensure(nlists + 2);
+  CK(cudaMemsetAsync(c->d_mcell_cnt.p, 0, (nlists + 1) * 4, c->st));
+  LAUNCH(c, k_mesh_cells<0>, nblk(nprim), BLK, 0, A, c->d_mcell_cnt.p, nullptr, nullptr);
+  scan_u32(c, c->d_mcell_cnt.p, c->d_mcell_off.p, (uint32_t)nlists);
+  uint32_t total = 0;
+  CK(cudaMemcpyAsync(&total, c->d_mcell_off.p + nlists, 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  c->d_mcell_data.ensure((size_t)total + 1);
+  CK(cudaMemsetAsync(c->d_mcell_cnt.p, 0, (nlists + 1) * 4, c->st));
+  LAUNCH(c, k_mesh_cells<1>, nblk(nprim), BLK, 0, A, c->d_mcell_cnt.p, c->d_mcell_off.p, c->d_mcell_data.p);
+  LAUNCH(c, k_mesh_list_sort, nblk(nlists), BLK, 0, c->d_mcell_off.p, (uint32_t)nlists, c->d_mcell_data.p);
+  c->M = MeshView{c->d_md.p, c->d_mverts.p, c->d_medges.p, c->d_mfoff.p, c->d_mfn.p, c->d_mfidx.p, c->d_mcell_off.p, c->d_mcell_data.p, nm,
+                  (uint32_t)G.ncell};
+}
+
 extern "C" int edb_set_drivers(edb_context* c, int32_t n, const edb_driver* d) {
   API_BEGIN(c)
   c->h_drv.clear();
@@ -417,7 +485,8 @@ extern "C" int edb_set_drivers(edb_context* c, int32_t n, const edb_driver* d) {
     c->h_drv.push_back(D);
   }
   // RShape drivers: world vertices = position + orientation * v (rshape.hpp:381-384), pooled per driver
-  c->h_md.clear(); c->h_mverts.clear(); c->h_medges.clear(); c->h_mfoff.clear(); c->h_mfn.clear(); c->h_mfidx.clear();
+  c->h_drv_shape.assign(n, -1);
+  c->h_md.clear(); c->h_mverts.clear(); c->h_mlocal.clear(); c->h_medges.clear(); c->h_mfoff.clear(); c->h_mfn.clear(); c->h_mfidx.clear();
   for (int i = 0; i < n; i++) {
     Driver& D = c->h_drv[i];
     if (D.kind != EDB_DRIVER_RSHAPE) continue;
@@ -426,17 +495,20 @@ extern "C" int edb_set_drivers(edb_context* c, int32_t n, const edb_driver* d) {
     MeshDev md{};
     const auto& lv = c->h_mesh_v[sidx];
     md.nv = (int)lv.size() / 3; md.ne = (int)c->h_mesh_e[sidx].size() / 2; md.nf = (int)c->h_mesh_fn[sidx].size();
+    md.drv = i;
     md.v0 = (int)c->h_mverts.size(); md.e0 = (int)c->h_medges.size() / 2; md.f0 = (int)c->h_mfn.size(); md.fi0 = (int)c->h_mfidx.size();
     md.radius = c->h_mesh_radius[sidx];
     const q4 q{d[i].quat[0], d[i].quat[1], d[i].quat[2], d[i].quat[3]};
     for (int k = 0; k < md.nv; k++) {
       const v3 w = D.center + qrot(q, 1.0 * mk3(lv[3 * k], lv[3 * k + 1], lv[3 * k + 2]));
       c->h_mverts.push_back(make_double4(w.x, w.y, w.z, 0.0));
+      c->h_mlocal.push_back(make_double4(lv[3 * k], lv[3 * k + 1], lv[3 * k + 2], 0.0));
     }
     c->h_medges.insert(c->h_medges.end(), c->h_mesh_e[sidx].begin(), c->h_mesh_e[sidx].end());
     c->h_mfoff.insert(c->h_mfoff.end(), c->h_mesh_foff[sidx].begin(), c->h_mesh_foff[sidx].end());
     c->h_mfn.insert(c->h_mfn.end(), c->h_mesh_fn[sidx].begin(), c->h_mesh_fn[sidx].end());
     c->h_mfidx.insert(c->h_mfidx.end(), c->h_mesh_fidx[sidx].begin(), c->h_mesh_fidx[sidx].end());
+    c->h_drv_shape[i] = sidx;
     D.shape = (int)c->h_md.size();   // device: slot of this driver's mesh
     c->h_md.push_back(md);
   }
@@ -444,6 +516,104 @@ extern "C" int edb_set_drivers(edb_context* c, int32_t n, const edb_driver* d) {
   c->drv.ensure(n + 1);
   if (n) CK(cudaMemcpy(c->drv.p, c->h_drv.data(), n * sizeof(Driver), cudaMemcpyHostToDevice));
   if (!c->prm.tpd) c->prm.n_drivers = n;
+  // every driver starts STATIONARY (no edb_set_driver_motions yet); the orientation of an RShape lives with the motion state
+  c->h_mo.assign(n, DriverMotion{});
+  for (int i = 0; i < n; i++) {
+    DriverMotion& m = c->h_mo[i];
+    m.t_end = 1e300; m.shaker_dir = mk3(0, 0, 1); m.mass = 1.7976931348623157e308 / 4; m.surface = -1;
+    m.quat = q4{d[i].quat[0], d[i].quat[1], d[i].quat[2], d[i].quat[3]};
+  }
+  c->mo.ensure(n + 1);
+  if (n) CK(cudaMemcpy(c->mo.p, c->h_mo.data(), n * sizeof(DriverMotion), cudaMemcpyHostToDevice));
+  c->drivers_moving = false;
+  c->have_drv_backup = false;
+  upload_mesh_tables(c);
+  API_END(c)
+}
+static bool any_driver_moves(const edb_context* c) {
+  for (size_t i = 0; i < c->h_drv.size(); i++)
+    if (driver_moves(c->h_drv[i], c->h_mo[i])) return true;
+  return false;
+}
+extern "C" int edb_set_driver_motions(edb_context* c, int32_t n, const edb_driver_motion* mo) {
+  API_BEGIN(c)
+  if (n != (int)c->h_drv.size()) throw StateError{EDB_ERR_INVALID, "edb_set_driver_motions: n differs from the driver count of edb_set_drivers"};
+  for (int i = 0; i < n; i++) {
+    const edb_driver_motion& s = mo[i];
+    DriverMotion& m = c->h_mo[i];
+    const q4 keep = m.quat;
+    if (s.motion_type < 0 || s.motion_type > EDB_MOTION_UNKNOWN) throw StateError{EDB_ERR_INVALID, "unknown motion type"};
+    if (s.motion_type == EDB_MOTION_TABULATED && (s.n_tab < 1 || s.n_tab > EDB_MAX_TAB || !s.tab_time || !s.tab_pos))
+      throw StateError{EDB_ERR_INVALID, "TABULATED motion needs 1..EDB_MAX_TAB (time, position) entries"};
+    m = DriverMotion{};
+    m.quat = keep;
+    m.motion = s.motion_type; m.n_tab = s.motion_type == EDB_MOTION_TABULATED ? s.n_tab : 0;
+    m.expr_use_v = s.expr_use_v; m.expr_use_vrot = s.expr_use_vrot; m.expr_use_mom = s.expr_use_mom; m.drive_by_mom = s.drive_by_mom;
+    auto V = [](const double* p) { return mk3(p[0], p[1], p[2]); };
+    m.motion_vector = V(s.motion_vector); m.t_start = s.motion_start_threshold; m.t_end = s.motion_end_threshold;
+    m.const_vel = s.const_vel; m.const_force = s.const_force; m.sigma = s.sigma; m.damprate = s.damprate;
+    m.omega = s.omega; m.amplitude = s.amplitude; m.shaker_dir = V(s.shaker_dir);
+    m.pend_anchor = V(s.pendulum_anchor_point); m.pend_init = V(s.pendulum_initial_position); m.pend_dir = V(s.pendulum_swing_dir);
+    m.mass = s.mass; m.surface = s.surface; m.rv = s.rv; m.ra = s.ra;
+    m.acc = V(s.acc); m.inertia = V(s.inertia); m.applied_mom = V(s.applied_mom); m.mom_axis = V(s.mom_axis); m.mom = V(s.mom);
+    for (int k = 0; k < m.n_tab; k++) { m.tab_time[k] = s.tab_time[k]; m.tab_pos[k] = V(s.tab_pos + 3 * k); }
+    c->h_drv[i].need_forces = m_need_forces(m.motion) ? 1 : 0;   // motion_type.hpp:133-141
+  }
+  // the device copy of the drivers may already have moved: only the need_forces flag is refreshed there
+  if (n) {
+    std::vector<Driver> cur(n);
+    CK(cudaMemcpy(cur.data(), c->drv.p, n * sizeof(Driver), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) cur[i].need_forces = c->h_drv[i].need_forces;
+    CK(cudaMemcpy(c->drv.p, cur.data(), n * sizeof(Driver), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->mo.p, c->h_mo.data(), n * sizeof(DriverMotion), cudaMemcpyHostToDevice));
+  }
+  c->drivers_moving = any_driver_moves(c);
+  API_END(c)
+}
+extern "C" int edb_set_driver_expr(edb_context* c, int32_t d, const double v[3], const double vrot[3], const double mom[3]) {
+  API_BEGIN(c)
+  if (d < 0 || d >= (int)c->h_drv.size()) throw StateError{EDB_ERR_INVALID, "driver index out of range"};
+  CK(cudaStreamSynchronize(c->st));
+  DriverMotion m;
+  CK(cudaMemcpy(&m, c->mo.p + d, sizeof(DriverMotion), cudaMemcpyDeviceToHost));
+  if (v) m.expr_v = mk3(v[0], v[1], v[2]);
+  if (vrot) m.expr_vrot = mk3(vrot[0], vrot[1], vrot[2]);
+  if (mom) m.expr_mom = mk3(mom[0], mom[1], mom[2]);
+  CK(cudaMemcpy(c->mo.p + d, &m, sizeof(DriverMotion), cudaMemcpyHostToDevice));
+  API_END(c)
+}
+extern "C" int edb_get_drivers(edb_context* c, int32_t n, edb_driver* out, edb_driver_motion* mo) {
+  API_BEGIN(c)
+  if (n != (int)c->h_drv.size()) throw StateError{EDB_ERR_INVALID, "edb_get_drivers: n differs from the driver count"};
+  if (n == 0) return EDB_OK;
+  CK(cudaStreamSynchronize(c->st));
+  std::vector<Driver> D(n);
+  std::vector<DriverMotion> M(n);
+  CK(cudaMemcpy(D.data(), c->drv.p, n * sizeof(Driver), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(M.data(), c->mo.p, n * sizeof(DriverMotion), cudaMemcpyDeviceToHost));
+  auto S = [](double* o, v3 v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; };
+  for (int i = 0; i < n; i++) {
+    if (out) {
+      edb_driver& o = out[i];
+      o = edb_driver{};
+      o.kind = D[i].kind; o.need_forces = D[i].need_forces; o.radius = D[i].radius; S(o.axis, D[i].axis); S(o.center, D[i].center);
+      o.offset = D[i].offset; S(o.normal, D[i].normal); S(o.vel, D[i].vel); S(o.vrot, D[i].vrot);
+      o.shape = D[i].kind == EDB_DRIVER_RSHAPE ? c->h_drv_shape[i] : D[i].shape;
+      o.quat[0] = M[i].quat.w; o.quat[1] = M[i].quat.x; o.quat[2] = M[i].quat.y; o.quat[3] = M[i].quat.z;
+    }
+    if (mo) {
+      edb_driver_motion& o = mo[i];
+      o = edb_driver_motion{};
+      const DriverMotion& m = M[i];
+      o.motion_type = m.motion; o.n_tab = m.n_tab; S(o.motion_vector, m.motion_vector);
+      o.motion_start_threshold = m.t_start; o.motion_end_threshold = m.t_end; o.const_vel = m.const_vel; o.const_force = m.const_force;
+      o.sigma = m.sigma; o.damprate = m.damprate; o.omega = m.omega; o.amplitude = m.amplitude; S(o.shaker_dir, m.shaker_dir);
+      S(o.pendulum_anchor_point, m.pend_anchor); S(o.pendulum_initial_position, m.pend_init); S(o.pendulum_swing_dir, m.pend_dir);
+      o.expr_use_v = m.expr_use_v; o.expr_use_vrot = m.expr_use_vrot; o.expr_use_mom = m.expr_use_mom; o.drive_by_mom = m.drive_by_mom;
+      o.mass = m.mass; o.surface = m.surface; S(o.acc, m.acc); o.rv = m.rv; o.ra = m.ra;
+      S(o.inertia, m.inertia); S(o.applied_mom, m.applied_mom); S(o.mom_axis, m.mom_axis); S(o.mom, m.mom); S(o.forces, m.forces);
+    }
+  }
   API_END(c)
 }
 extern "C" int edb_set_driver_shapes(edb_context* c, int32_t n, const edb_shape* sh) {
@@ -701,70 +871,6 @@ static void compute_vertices(edb_context* c, bool ghosts_only = false) {
   LAUNCH(c, k_compute_vertices, nblk(ntot - first), BLK, 0, view(c->pa), first, ntot, c->S, c->vert.p);
 }
 
-// Per-cell primitive lists of the RShape meshes (host-built, rebuild-frequency; the reference builds them on the host too,
-// grid_stl_mesh.cpp:150-251).  A primitive is listed in every real cell its bounding box, enlarged by Minkowski radius + cell
-// size, overlaps: conservative for any particle of the cell because cell_size >= 2 r_max + rcut_inc (check_rcut.cpp:72).
-static void build_mesh_grid(edb_context* c) {
-  const GridDev& G = c->G;
-  const int nm = (int)c->h_md.size();
-  c->M = MeshView{};
-  c->mesh_dirty = false;
-  if (nm == 0) return;
-  const size_t ncell = G.ncell;
-  std::vector<std::vector<int>> lists((size_t)nm * ncell * 3);
-  const double Rmax = std::max(c->cfg.cell_size, std::max(G.cs[0], std::max(G.cs[1], G.cs[2])));
-  for (int m = 0; m < nm; m++) {
-    const MeshDev& md = c->h_md[m];
-    auto add = [&](int kind, int id, const int* vidx, int nvtx) {
-      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-      for (int k = 0; k < nvtx; k++) {
-        const double4 v = c->h_mverts[md.v0 + vidx[k]];
-        const double x[3] = {v.x, v.y, v.z};
-        for (int d = 0; d < 3; d++) { lo[d] = std::min(lo[d], x[d]); hi[d] = std::max(hi[d], x[d]); }
-      }
-      int a[3], b[3];
-      for (int d = 0; d < 3; d++) {
-        const double e = md.radius + Rmax;
-        a[d] = (int)std::floor((lo[d] - e - G.lo[d]) / G.cs[d]) + 1;
-        b[d] = (int)std::floor((hi[d] + e - G.lo[d]) / G.cs[d]) + 1;
-        a[d] = std::max(a[d], 1); b[d] = std::min(b[d], G.nc[d]);
-        if (a[d] > b[d]) return;
-      }
-      for (int z = a[2]; z <= b[2]; z++)
-        for (int y = a[1]; y <= b[1]; y++)
-          for (int x = a[0]; x <= b[0]; x++) {
-            const size_t cell = (size_t)x + (size_t)G.g[0] * ((size_t)y + (size_t)G.g[1] * (size_t)z);
-            lists[((size_t)m * ncell + cell) * 3 + kind].push_back(id);
-          }
-    };
-    for (int v = 0; v < md.nv; v++) add(0, v, &v, 1);
-    for (int e = 0; e < md.ne; e++) add(1, e, &c->h_medges[2 * (md.e0 + e)], 2);
-    for (int f = 0; f < md.nf; f++) add(2, f, &c->h_mfidx[md.fi0 + c->h_mfoff[md.f0 + f]], c->h_mfn[md.f0 + f]);
-  }
-  std::vector<uint32_t> off(lists.size() + 1, 0);
-  std::vector<int> data;
-  for (size_t i = 0; i < lists.size(); i++) {
-    off[i] = (uint32_t)data.size();
-    data.insert(data.end(), lists[i].begin(), lists[i].end());
-  }
-  off[lists.size()] = (uint32_t)data.size();
-  c->d_md.ensure(nm); c->d_mverts.ensure(c->h_mverts.size() + 1); c->d_medges.ensure(c->h_medges.size() + 1);
-  c->d_mfoff.ensure(c->h_mfoff.size() + 1); c->d_mfn.ensure(c->h_mfn.size() + 1); c->d_mfidx.ensure(c->h_mfidx.size() + 1);
-  c->d_mcell_off.ensure(off.size()); c->d_mcell_data.ensure(data.size() + 1);
-  CK(cudaMemcpy(c->d_md.p, c->h_md.data(), nm * sizeof(MeshDev), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d_mverts.p, c->h_mverts.data(), c->h_mverts.size() * sizeof(double4), cudaMemcpyHostToDevice));
-  if (!c->h_medges.empty()) CK(cudaMemcpy(c->d_medges.p, c->h_medges.data(), c->h_medges.size() * 4, cudaMemcpyHostToDevice));
-  if (!c->h_mfn.empty()) {
-    CK(cudaMemcpy(c->d_mfoff.p, c->h_mfoff.data(), c->h_mfoff.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_mfn.p, c->h_mfn.data(), c->h_mfn.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_mfidx.p, c->h_mfidx.data(), c->h_mfidx.size() * 4, cudaMemcpyHostToDevice));
-  }
-  CK(cudaMemcpy(c->d_mcell_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
-  if (!data.empty()) CK(cudaMemcpy(c->d_mcell_data.p, data.data(), data.size() * 4, cudaMemcpyHostToDevice));
-  c->M = MeshView{c->d_md.p, c->d_mverts.p, c->d_medges.p, c->d_mfoff.p, c->d_mfn.p, c->d_mfidx.p, c->d_mcell_off.p, c->d_mcell_data.p, nm,
-                  (uint32_t)ncell};
-}
-
 // Multi-GPU: particles that left the brick move to their new owner together with their active interaction records.
 // Returns the number of occupied slots (stayers + leavers' dead slots + immigrants); *n_live = particles now owned.
 static uint32_t migrate(edb_context* c, uint32_t* n_live) {
@@ -949,6 +1055,11 @@ static void update_interaction_ghost(edb_context* c) {
   }
 }
 
+static void driver_op(edb_context* c, int op, double time, double dt, double system_mass);
+static void driver_force_reduce(edb_context* c);
+static void driver_vertices(edb_context* c, bool all);
+static void backup_drivers(edb_context* c);
+static void driver_displ_launch(edb_context* c, double thr, unsigned long long* d_out);
 static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   ScopedTimer tm(c, B_REBUILD);
   const GridDev& G = c->G;
@@ -1085,7 +1196,8 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   active[0] = true;
   if (poly) active[1] = active[2] = active[3] = true;
   for (int k = 0; k < 3; k++) active[4 + k] = has_drv[k];
-  if (c->mesh_dirty) build_mesh_grid(c);
+  if (c->drivers_moving) backup_drivers(c);                     // update_particles_full: backup_drivers (config_move_particles.msp:150-153)
+  if (c->mesh_dirty || c->drivers_moving) build_mesh_grid(c);   // grid_rshape_driver { force_reset: true } (:92-94)
   if (c->M.nmesh)
     for (int t = 7; t <= (poly ? 12 : 9); t++) active[t] = true;
   CntTab C{};
@@ -1465,11 +1577,81 @@ static void trigger_standalone(edb_context* c, int slot, double thr) {
 // kernels that change state are launched gated on the device-side flag, and the host reads the flag (already copied to pinned
 // memory, one step behind the launch front) afterwards.  When the flag says "rebuild", the gated kernels have done nothing and
 // the step is enqueued again behind the rebuild.  The GPU never idles on the host in the common no-rebuild case.
+
+// The same macro with moving drivers (edb_set_driver_motions): operator by operator in the reference's order
+// (config_numerical_schemes.msp:12-29, check_and_update_particles of config_move_particles.msp:186-189), drivers integrated on the
+// device.  One host read of the rebuild trigger per step (particle_displ_over | driver_displ_over, all-reduced).
+static uint64_t run_verlet_moving(edb_context* c, double dt, const double g[3], double rcut_inc, int symetric, int nsteps, int rebuild_every) {
+  uint64_t nb = 0;
+  if (!c->have_system_mass) {
+    if (c->cfg.nranks > 1) throw StateError{EDB_ERR_STATE, "moving drivers on several ranks: call edb_set_system_mass first"};
+    const uint32_t n = c->nreal, nbk = nblk(n);
+    c->stage.ensure((size_t)nbk * 7 + 8);
+    std::vector<double> part((size_t)nbk * 7);
+    if (nbk) {
+      LAUNCH(c, k_sim_state_particles, nbk, BLK, 0, view(c->pa), n, c->stage.p);
+      CK(cudaMemcpyAsync(part.data(), c->stage.p, part.size() * 8, cudaMemcpyDeviceToHost, c->st));
+      CK(cudaStreamSynchronize(c->st));
+    }
+    double m = 0;
+    for (uint32_t b = 0; b < nbk; b++) m += part[(size_t)b * 7 + 6];
+    c->system_mass = m;
+    c->have_system_mass = true;
+  }
+  if (!c->have_drv_backup) backup_drivers(c);
+  const double thr = 0.5 * rcut_inc;
+  for (int it = 0; it < nsteps; it++) {
+    const double t = c->physical_time;
+    prolog(c, dt);
+    driver_op(c, DOP_PUSH_F_V_R, t, dt, 0.0);
+    driver_op(c, DOP_PUSH_F_V, 0.0, 0.5 * dt, 0.0);
+    driver_op(c, DOP_PUSH_AV_TO_QUAT, t, dt, 0.0);
+    bool rb;
+    if (rebuild_every > 0) rb = ((it + 1) % rebuild_every) == 0;
+    else if (rebuild_every < 0) rb = false;
+    else {
+      uint64_t over = displ_over(c, thr);          // all-reduced over the ranks
+      if (!over) {
+        CK(cudaMemsetAsync(c->d_flag, 0, 8, c->st));
+        driver_displ_launch(c, thr, c->d_flag);
+        CK(cudaMemcpyAsync(c->h_flag, c->d_flag, 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        over = c->h_flag[0];
+      }
+      rb = over > 0;
+    }
+    if (rb) {
+      backup_drivers(c);
+      driver_vertices(c, false);       // ghost_full_update -> compute_all_vertices -> driver_vertices
+      rebuild(c, rcut_inc, symetric);  // grid_rshape_driver inside (drivers_moving)
+      nb++;
+    } else {
+      ghost_refresh(c, false);
+      compute_vertices(c);
+      driver_vertices(c, false);
+    }
+    driver_op(c, DOP_RESET_FORCE, 0.0, 0.0, 0.0);
+    contact_waves(c, dt);
+    gather<1>(c, g, dt);               // reset + gravity + contact wrenches + force_to_accel + epilog of the particles
+    driver_force_reduce(c);            // force_to_accel_driver: reaction sums, then Ball::f_ra / force_to_accel
+    driver_op(c, DOP_FORCE_TO_ACCEL, 0.0, dt, c->system_mass);
+    driver_op(c, DOP_PUSH_F_V, 0.0, 0.5 * dt, 0.0);
+    c->ctr.particle_steps += c->nreal;
+    c->physical_time += dt;
+  }
+  return nb;
+}
+
 extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], double rcut_inc, int32_t symetric, int32_t nsteps,
                               int32_t rebuild_every, uint64_t* n_rebuilds) {
   API_BEGIN(c)
   uint64_t nb = 0;
   if (!c->have_prev) { rebuild(c, rcut_inc, symetric); }
+  if (c->drivers_moving) {
+    nb = run_verlet_moving(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every);
+    if (n_rebuilds) *n_rebuilds = nb;
+    return EDB_OK;
+  }
   const bool trig = rebuild_every == 0;
   const double thr = 0.5 * rcut_inc;
   const bool poly = c->poly();
@@ -1707,6 +1889,126 @@ extern "C" int edb_compute_driver_force_moment(edb_context* c, double* forces, d
       forces[3 * d + k] = acc[d * 6 + k];
       moments[3 * d + k] = acc[d * 6 + 3 + k];
     }
+  API_END(c)
+}
+
+// ---- driver operators of the time loop (config_numerical_schemes.msp:13-24), device-resident drivers ----------------------------
+static void driver_op(edb_context* c, int op, double time, double dt, double system_mass) {
+  const int nd = (int)c->h_drv.size();
+  if (nd) LAUNCH(c, k_driver_op, nblk(nd, 64), 64, 0, c->drv.p, c->mo.p, nd, op, time, dt, system_mass);
+}
+// reaction of the driver waves of the last contact operator -> DriverMotion::forces / mom (deterministic block-ordered sums)
+static void driver_force_reduce(edb_context* c) {
+  const int nd = (int)c->h_drv.size();
+  if (!nd) return;
+  c->drv_sums.ensure((size_t)nd * 6 + 1);
+  CK(cudaMemsetAsync(c->drv_sums.p, 0, (size_t)nd * 6 * sizeof(double), c->st));
+  for (int t = 4; t <= 12; t++) {
+    Wave& w = c->wave[t];
+    if (!w.n) continue;
+    const uint32_t nb = nblk(w.n);
+    c->stage.ensure((size_t)nb * nd * 6 + 1);
+    const size_t smem = (size_t)(BLK / 32) * nd * 6 * sizeof(double);
+    LAUNCH(c, k_driver_force, nb, BLK, smem, view(w), t, c->drv.p, nd, c->stage.p);
+    LAUNCH(c, k_driver_force_sum, nblk((uint64_t)nd * 6, 64), 64, 0, c->stage.p, nb, nd, c->drv_sums.p);
+  }
+  if (c->cfg.nranks > 1) c->comm.allreduce_sum_f64_dev(c->drv_sums.p, (size_t)nd * 6, c->st);
+  LAUNCH(c, k_driver_force_apply, nblk(nd, 64), 64, 0, c->drv_sums.p, nd, c->drv.p, c->mo.p, c->poly() ? 0 : 1);
+}
+static void driver_vertices(edb_context* c, bool all) {
+  const int nm = (int)c->h_md.size();
+  if (!nm) return;
+  int nvmax = 1;
+  for (auto& m : c->h_md) nvmax = std::max(nvmax, m.nv);
+  dim3 grid(std::min<uint32_t>(nblk(nvmax), 1024u), nm);
+  k_driver_vertices<<<grid, BLK, 0, c->st>>>(c->d_md.p, nm, c->drv.p, c->mo.p, c->d_mlocal.p, c->d_mverts.p, all ? 1 : 0);
+  c->ctr.kernel_launches++;
+}
+static void backup_drivers(edb_context* c) {
+  const int nd = (int)c->h_drv.size();
+  c->drv_backup.ensure(nd + 1); c->mo_backup.ensure(nd + 1);
+  if (nd) {
+    CK(cudaMemcpyAsync(c->drv_backup.p, c->drv.p, nd * sizeof(Driver), cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync(c->mo_backup.p, c->mo.p, nd * sizeof(DriverMotion), cudaMemcpyDeviceToDevice, c->st));
+  }
+  c->have_drv_backup = true;
+}
+// adds the count to *d_out (device); the caller zeroes / reads it
+static void driver_displ_launch(edb_context* c, double thr, unsigned long long* d_out) {
+  const int nd = (int)c->h_drv.size();
+  if (!nd) return;
+  if (!c->have_drv_backup) backup_drivers(c);
+  int nvmax = 1;
+  for (auto& m : c->h_md) nvmax = std::max(nvmax, m.nv);
+  dim3 grid(std::min<uint32_t>(nblk(nvmax), 1024u), nd);
+  k_driver_displ<<<grid, BLK, 0, c->st>>>(c->drv.p, c->mo.p, c->drv_backup.p, c->mo_backup.p, nd, c->d_md.p, c->d_mlocal.p, thr * thr, d_out);
+  c->ctr.kernel_launches++;
+}
+extern "C" int edb_push_f_v_r_driver(edb_context* c, double time, double dt) {
+  API_BEGIN(c)
+  driver_op(c, DOP_PUSH_F_V_R, time, dt, 0.0);
+  API_END(c)
+}
+extern "C" int edb_push_f_v_driver(edb_context* c, double dt) {
+  API_BEGIN(c)
+  driver_op(c, DOP_PUSH_F_V, 0.0, dt, 0.0);
+  API_END(c)
+}
+extern "C" int edb_push_av_to_quat_driver(edb_context* c, double time, double dt) {
+  API_BEGIN(c)
+  driver_op(c, DOP_PUSH_AV_TO_QUAT, time, dt, 0.0);
+  API_END(c)
+}
+extern "C" int edb_reset_force_driver(edb_context* c) {
+  API_BEGIN(c)
+  driver_op(c, DOP_RESET_FORCE, 0.0, 0.0, 0.0);
+  API_END(c)
+}
+extern "C" int edb_force_to_accel_driver(edb_context* c, double dt, double system_mass) {
+  API_BEGIN(c)
+  driver_force_reduce(c);
+  driver_op(c, DOP_FORCE_TO_ACCEL, 0.0, dt, system_mass);
+  API_END(c)
+}
+extern "C" int edb_driver_vertices(edb_context* c) {
+  API_BEGIN(c)
+  driver_vertices(c, false);
+  API_END(c)
+}
+extern "C" int edb_grid_rshape_driver(edb_context* c) {
+  API_BEGIN(c)
+  build_mesh_grid(c);
+  API_END(c)
+}
+extern "C" int edb_backup_drivers(edb_context* c) {
+  API_BEGIN(c)
+  backup_drivers(c);
+  API_END(c)
+}
+extern "C" int edb_driver_displ_over(edb_context* c, double thr, uint64_t* result) {
+  API_BEGIN(c)
+  CK(cudaMemsetAsync(c->d_flag, 0, 8, c->st));
+  driver_displ_launch(c, thr, c->d_flag);
+  CK(cudaMemcpyAsync(c->h_flag, c->d_flag, 8, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  // every rank holds the same drivers: no reduction needed (the reference's MPI_Allreduce sums identical per-rank flags, :238)
+  *result = c->h_flag[0];
+  API_END(c)
+}
+extern "C" int edb_set_physical_time(edb_context* c, double t) {
+  API_BEGIN(c)
+  c->physical_time = t;
+  API_END(c)
+}
+extern "C" int edb_get_physical_time(edb_context* c, double* t) {
+  API_BEGIN(c)
+  *t = c->physical_time;
+  API_END(c)
+}
+extern "C" int edb_set_system_mass(edb_context* c, double m) {
+  API_BEGIN(c)
+  c->system_mass = m;
+  c->have_system_mass = true;
   API_END(c)
 }
 

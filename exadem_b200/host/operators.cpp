@@ -97,6 +97,93 @@ class ComputeContactClassifier : public OperatorNode {
 // -------------------------------------------------------------------------------------------------------------------
 // per-particle operators
 // -------------------------------------------------------------------------------------------------------------------
+// driver operators of the time loop (config_numerical_schemes.msp:13-24, config_move_particles.msp:17-24,61,92,152): the `drivers`
+// slot is device-resident (edb_set_drivers / edb_set_driver_motions), the operators keep the reference's names and slots
+// -------------------------------------------------------------------------------------------------------------------
+// src/driver/push_f_v_r_driver.cpp:40-64
+class PushAccVelocityToPositionDriver : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(double, physical_time, INPUT, REQUIRED);
+  ADD_SLOT(double, dt, INPUT, REQUIRED, DocString{"dt is the time increment of the timeloop"});
+  ADD_SLOT(double, dt_scale, INPUT, 1.0);
+ public:
+  std::string documentation() const final { return "This operator updates driver centers using their velocities. Not that accelerations are not used."; }
+  void execute() final { ck(*grid, edb_push_f_v_r_driver(grid->ctx, *physical_time, (*dt) * (*dt_scale)), "push_f_v_r_driver"); }
+};
+// src/driver/push_f_v_driver.cpp:42-70
+class PushAccelToVelocityDriver : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(double, dt, INPUT, REQUIRED, DocString{"dt is the time increment of the timeloop"});
+  ADD_SLOT(double, dt_scale, INPUT, 1.0);
+ public:
+  std::string documentation() const final { return "This operator updates driver velocities.\n\nParameter:\n  - dt_scale [double]: apply a scale factor.\n\nYAML example:\n\n  - push_f_v_driver"; }
+  void execute() final { ck(*grid, edb_push_f_v_driver(grid->ctx, (*dt) * (*dt_scale)), "push_f_v_driver"); }
+};
+// src/driver/push_av_to_quat_driver.cpp:43-70
+class PushAngularVelocityToQuaternionDriver : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(double, physical_time, INPUT, REQUIRED);
+  ADD_SLOT(double, dt, INPUT, REQUIRED, DocString{"dt is the time increment of the timeloop"});
+  ADD_SLOT(double, dt_scale, INPUT, 1.0);
+ public:
+  std::string documentation() const final { return "This operator compute the new orientation using the angular velocity.\n\nYAML example [no option]:\n\n  - push_av_to_quat_driver"; }
+  void execute() final { ck(*grid, edb_push_av_to_quat_driver(grid->ctx, *physical_time, (*dt) * (*dt_scale)), "push_av_to_quat_driver"); }
+};
+// src/driver/reset_force_driver.cpp:27-43
+class ResetForceDriverFunctor : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+ public:
+  std::string documentation() const final { return "This operator reset the forces of drivers."; }
+  void execute() final { ck(*grid, edb_reset_force_driver(grid->ctx), "reset_force_driver"); }
+};
+// src/driver/force_to_accel_driver.cpp:100-146
+class ForceToAccelDriverFunctor : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(double, dt, INPUT, REQUIRED, DocString{"dt is the time increment of the timeloop"});
+  ADD_SLOT(double, system_mass, INPUT, REQUIRED);
+ public:
+  std::string documentation() const final { return "force_to_accel_driver: sums the reaction of the contacts on the drivers that need it (all ranks), then converts forces to accelerations."; }
+  void execute() final { ck(*grid, edb_force_to_accel_driver(grid->ctx, *dt, *system_mass), "force_to_accel_driver"); }
+};
+// src/driver/driver_vertices.cu:42-117 (force_host is meaningless here: there is no host path)
+class DriverVertices : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(bool, force_host, INPUT, false, DocString{"Force computations on the host"});
+ public:
+  std::string documentation() const final { return "This operator calculates new vertex positions.\nIf rshape mesh velocity and angular velocity are equal to [0,0,0], vertices are not calculated."; }
+  void execute() final { ck(*grid, edb_driver_vertices(grid->ctx), "driver_vertices"); }
+};
+// src/driver/grid_stl_mesh.cpp:35-269
+class UpdateGridSTLMeshOperator : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(double, rcut_inc, INPUT, 0.0);
+  ADD_SLOT(bool, force_reset, INPUT, false);
+ public:
+  std::string documentation() const final { return "grid_rshape_driver: update the list of mesh vertices / edges / faces of every cell (device build)."; }
+  void execute() final { ck(*grid, edb_grid_rshape_driver(grid->ctx), "grid_rshape_driver"); }
+};
+// src/driver/backup_drivers.cu
+class BackupDrivers : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+ public:
+  std::string documentation() const final { return "backup_drivers: copy the drivers into backup_drvs for driver_displ_over."; }
+  void execute() final { ck(*grid, edb_backup_drivers(grid->ctx), "backup_drivers"); }
+};
+// src/driver/driver_displ_over.cu:196-243
+class DriverDisplacementOver : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(double, threshold, INPUT, 0.0);
+  ADD_SLOT(bool, result, OUTPUT);
+ public:
+  std::string documentation() const final { return "Compute the distance between each driver and its backup; sets result to true if a driver (a vertex of a mesh) has moved further than threshold."; }
+  void execute() final {
+    uint64_t over = 0;
+    ck(*grid, edb_driver_displ_over(grid->ctx, *threshold, &over), "driver_displ_over");
+    *result = over > 0;
+  }
+};
+
+// -------------------------------------------------------------------------------------------------------------------
 #define EDB_SIMPLE_OP(Class, call, doc)                                   \
   class Class : public OperatorNode {                                     \
     ADD_SLOT(GridB200, grid, INPUT_OUTPUT, REQUIRED);                     \
@@ -246,6 +333,15 @@ ONIKA_AUTORUN_INIT(exadem_b200_hot_path) {
   f->register_factory("ghost_update_rq", make_simple_operator<UpdateGhostsRQ>);
   f->register_factory("vertex_displ_over", make_simple_operator<DisplOver>);
   f->register_factory("particle_displ_over", make_simple_operator<DisplOver>);
+  f->register_factory("push_f_v_r_driver", make_simple_operator<PushAccVelocityToPositionDriver>);
+  f->register_factory("push_f_v_driver", make_simple_operator<PushAccelToVelocityDriver>);
+  f->register_factory("push_av_to_quat_driver", make_simple_operator<PushAngularVelocityToQuaternionDriver>);
+  f->register_factory("reset_force_driver", make_simple_operator<ResetForceDriverFunctor>);
+  f->register_factory("force_to_accel_driver", make_simple_operator<ForceToAccelDriverFunctor>);
+  f->register_factory("driver_vertices", make_simple_operator<DriverVertices>);
+  f->register_factory("grid_rshape_driver", make_simple_operator<UpdateGridSTLMeshOperator>);
+  f->register_factory("backup_drivers", make_simple_operator<BackupDrivers>);
+  f->register_factory("driver_displ_over", make_simple_operator<DriverDisplacementOver>);
 }
 
 // -------------------------------------------------------------------------------------------------------------------

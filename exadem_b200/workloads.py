@@ -29,6 +29,7 @@ class Workload:
     drivers: list = field(default_factory=list)
     shapes_spec: list = field(default_factory=list)  # list of dicts(vertices, edges, faces, obb, radius)
     mesh_spec: list = field(default_factory=list)    # shapes of the RShape (mesh) drivers, same dict layout
+    motions: list = field(default_factory=list)      # one dict per driver (edb_driver_motion keys); empty = all STATIONARY
     mode: int = capi.MODE_SPHERE
     law: int = capi.LAW_NONE
     dt: float = 1e-4
@@ -64,6 +65,8 @@ class Workload:
         if self.mesh_spec:
             engine.set_driver_shapes([capi.make_shape(s["vertices"], s["edges"], s["faces"], s["obb"], s["radius"]) for s in self.mesh_spec])
         engine.set_drivers(self.drivers)
+        if self.motions:
+            engine.set_driver_motions(self.motions)
         engine.upload_particles(self.particles)
         return engine
 

@@ -20,7 +20,9 @@ def test_header_declares_the_operator_surface():
     syms = declared_symbols()
     for need in ("edb_update_particle_neighbors", "edb_contact_sphere", "edb_contact_polyhedron", "edb_combined_compute_prolog",
                  "edb_combined_compute_epilog", "edb_ghost_update_rq", "edb_compute_vertices", "edb_run_verlet",
-                 "edb_export_interactions", "edb_comm_init"):
+                 "edb_export_interactions", "edb_comm_init", "edb_set_driver_motions", "edb_push_f_v_r_driver", "edb_push_f_v_driver",
+                 "edb_push_av_to_quat_driver", "edb_reset_force_driver", "edb_force_to_accel_driver", "edb_driver_vertices",
+                 "edb_grid_rshape_driver", "edb_backup_drivers", "edb_driver_displ_over"):
         assert need in syms
 
 
@@ -36,6 +38,9 @@ def test_struct_layouts():
     assert C.sizeof(capi.ContactParams) == 64
     assert C.sizeof(capi.Particles) == 8 + 31 * 8
     assert C.sizeof(capi.Config) == 13 * 8 + 12 * 4
+    # edb_driver / edb_driver_motion (static_assert'ed to the same numbers in csrc/edb_lib.cu)
+    assert C.sizeof(capi.Driver) == 184 and C.sizeof(capi.DriverMotion) == 400
+    assert capi.DriverMotion.tab_time.offset == 80 and capi.DriverMotion.mass.offset == 224
 
 
 def test_no_cpu_fallback(product_lib):

@@ -23,7 +23,9 @@ contact_singlemat_polyhedron_hooke_cohesive contact_singlemat_polyhedron_hooke_d
 contact_multimat_polyhedron_hooke_cohesive contact_multimat_polyhedron_hooke_dmt gravity_force reset_force_moment force_to_accel
 combined_compute_prolog combined_compute_epilog push_to_quaternion push_to_angular_velocity push_to_angular_acceleration
 freeze_particles pas_libere_pas_delivre ghost_update_rq vertex_displ_over particle_displ_over backup_dem
-migrate_cell_particles_interaction move_particles_interaction compute_driver_force_moment stress_tensor simulation_state""".split()
+migrate_cell_particles_interaction move_particles_interaction compute_driver_force_moment stress_tensor simulation_state
+push_f_v_r_driver push_f_v_driver push_av_to_quat_driver reset_force_driver force_to_accel_driver driver_vertices grid_rshape_driver
+backup_drivers driver_displ_over""".split()
 
 
 def host_lib(product_lib):
