@@ -1258,7 +1258,7 @@ void orc_compute_moments(const double* cp, const double* p, const double* f, con
 static Driver mkdrv(int kind, const double* prm) {
   Driver d; d.kind = kind;
   if (kind == 0) { d.radius = prm[0]; d.axis = V(prm + 1); d.center = V(prm + 4); }
-  else if (kind == 1) { d.offset = prm[0]; d.normal = V(prm + 1); }
+  else if (kind == 1) { d.offset = prm[0]; d.normal = V(prm + 1); d.cproj = d.offset * d.normal; }
   else { d.radius = prm[0]; d.center = V(prm + 1); }
   return d;
 }
