@@ -68,6 +68,7 @@ struct edb_context {
   bool have_fan = false, ghost_pushed = false;
   // debugging switches read once at creation: EDB_NO_FAN (separate ghost kernels), EDB_NBH_POLY_PER_THREAD, EDB_NBH_NO_REPLAY
   bool env_no_fan = false, env_nbh_per_thread = false, env_nbh_no_replay = false;
+  bool env_drivers_unfused = false;   // EDB_DRIVERS_UNFUSED: moving drivers through the operator-by-operator loop on one rank too
   uint32_t* d_need_count = nullptr;  // chunk queue of the persistent sphere contact kernel / length of the polyhedron work list
   DevBuf<uint32_t> need;             // work list of k_detect_poly_pp -> k_law_poly_pp
   unsigned long long* d_sflag = nullptr;   // rebuild trigger of the speculative step loop (2 slots, device)
@@ -112,6 +113,7 @@ struct edb_context {
   DevBuf<uint32_t> d_mprim_start, d_mcell_cnt;
   DevBuf<double> drv_sums;
   bool drivers_moving = false, have_drv_backup = false;
+  bool drivers_need_reaction = false, mesh_moving = false;   // set with the motions
   double physical_time = 0, system_mass = 0;
   bool have_system_mass = false;
   // staging for host transfers
@@ -298,6 +300,7 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
   c->env_no_fan = getenv("EDB_NO_FAN") != nullptr;
   c->env_nbh_per_thread = getenv("EDB_NBH_POLY_PER_THREAD") != nullptr;
   c->env_nbh_no_replay = getenv("EDB_NBH_NO_REPLAY") != nullptr;
+  c->env_drivers_unfused = getenv("EDB_DRIVERS_UNFUSED") != nullptr;
   try {
     CK(cudaSetDevice(cfg->device));
     CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
@@ -525,7 +528,7 @@ extern "C" int edb_set_drivers(edb_context* c, int32_t n, const edb_driver* d) {
   }
   c->mo.ensure(n + 1);
   if (n) CK(cudaMemcpy(c->mo.p, c->h_mo.data(), n * sizeof(DriverMotion), cudaMemcpyHostToDevice));
-  c->drivers_moving = false;
+  c->drivers_moving = false; c->drivers_need_reaction = false; c->mesh_moving = false;
   c->have_drv_backup = false;
   upload_mesh_tables(c);
   API_END(c)
@@ -568,6 +571,12 @@ extern "C" int edb_set_driver_motions(edb_context* c, int32_t n, const edb_drive
     CK(cudaMemcpy(c->mo.p, c->h_mo.data(), n * sizeof(DriverMotion), cudaMemcpyHostToDevice));
   }
   c->drivers_moving = any_driver_moves(c);
+  c->drivers_need_reaction = false; c->mesh_moving = false;
+  for (int i = 0; i < n; i++) {
+    const bool mesh = c->h_drv[i].kind == EDB_DRIVER_RSHAPE;
+    if (m_need_forces(c->h_mo[i].motion) || (mesh && rshape_need_moment(c->h_mo[i]))) c->drivers_need_reaction = true;
+    if (mesh && driver_moves(c->h_drv[i], c->h_mo[i])) c->mesh_moving = true;
+  }
   API_END(c)
 }
 extern "C" int edb_set_driver_expr(edb_context* c, int32_t d, const double v[3], const double vrot[3], const double mom[3]) {
@@ -1059,7 +1068,8 @@ static void driver_op(edb_context* c, int op, double time, double dt, double sys
 static void driver_force_reduce(edb_context* c);
 static void driver_vertices(edb_context* c, bool all);
 static void backup_drivers(edb_context* c);
-static void driver_displ_launch(edb_context* c, double thr, unsigned long long* d_out);
+static void driver_displ_launch(edb_context* c, double thr, unsigned long long* d_out, const unsigned long long* gate);
+static void driver_force_sums(edb_context* c);
 static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   ScopedTimer tm(c, B_REBUILD);
   const GridDev& G = c->G;
@@ -1613,7 +1623,7 @@ static uint64_t run_verlet_moving(edb_context* c, double dt, const double g[3], 
       uint64_t over = displ_over(c, thr);          // all-reduced over the ranks
       if (!over) {
         CK(cudaMemsetAsync(c->d_flag, 0, 8, c->st));
-        driver_displ_launch(c, thr, c->d_flag);
+        driver_displ_launch(c, thr, c->d_flag, nullptr);
         CK(cudaMemcpyAsync(c->h_flag, c->d_flag, 8, cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
         over = c->h_flag[0];
@@ -1642,12 +1652,47 @@ static uint64_t run_verlet_moving(edb_context* c, double dt, const double g[3], 
   return nb;
 }
 
+static void ensure_system_mass(edb_context* c) {
+  if (c->have_system_mass) return;
+  if (c->cfg.nranks > 1) throw StateError{EDB_ERR_STATE, "moving drivers on several ranks: call edb_set_system_mass first"};
+  const uint32_t n = c->nreal, nbk = nblk(n);
+  c->stage.ensure((size_t)nbk * 7 + 8);
+  std::vector<double> part((size_t)nbk * 7);
+  if (nbk) {
+    LAUNCH(c, k_sim_state_particles, nbk, BLK, 0, view(c->pa), n, c->stage.p);
+    CK(cudaMemcpyAsync(part.data(), c->stage.p, part.size() * 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+  }
+  double m = 0;
+  for (uint32_t b = 0; b < nbk; b++) m += part[(size_t)b * 7 + 6];
+  c->system_mass = m;
+  c->have_system_mass = true;
+}
+// the fused driver operators of one step boundary (k_driver_cycle) + what follows them: mesh vertices and the drivers' share of the
+// rebuild trigger of the next step
+static void driver_cycle(edb_context* c, double dt, double time_next, bool do_end, bool do_begin, const unsigned long long* gate,
+                         unsigned long long* next_flag, double thr) {
+  const int nd = (int)c->h_drv.size();
+  if (!nd) return;
+  const bool sums = do_end && c->drivers_need_reaction;
+  if (sums) driver_force_sums(c);   // reads the contact state of the step; harmless on a gated-off step (the cycle kernel is gated)
+  DriverCycleArgs A{c->drv.p, c->mo.p, nd, sums ? c->drv_sums.p : nullptr, c->poly() ? 0 : 1, do_end ? 1 : 0, do_begin ? 1 : 0,
+                    dt, c->system_mass, time_next, gate};
+  LAUNCH(c, k_driver_cycle, nblk(nd, 64), 64, 0, A);
+  if (do_begin) {
+    if (c->mesh_moving) driver_vertices(c, false);   // idempotent on a gated-off step (drivers unchanged)
+    if (next_flag) driver_displ_launch(c, thr, next_flag, gate);
+  }
+}
+
 extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], double rcut_inc, int32_t symetric, int32_t nsteps,
                               int32_t rebuild_every, uint64_t* n_rebuilds) {
   API_BEGIN(c)
   uint64_t nb = 0;
   if (!c->have_prev) { rebuild(c, rcut_inc, symetric); }
-  if (c->drivers_moving) {
+  const bool mv = c->drivers_moving;
+  if (mv && (c->cfg.nranks > 1 || c->env_drivers_unfused)) {
+    // several ranks: the reaction sums need an all-reduce and the trigger of the drivers rides outside the mailbox exchange
     nb = run_verlet_moving(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every);
     if (n_rebuilds) *n_rebuilds = nb;
     return EDB_OK;
@@ -1655,9 +1700,15 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
   const bool trig = rebuild_every == 0;
   const double thr = 0.5 * rcut_inc;
   const bool poly = c->poly();
+  double tcur = c->physical_time;   // physical time of the step being enqueued (advanced by repeated addition like next_time_step)
+  if (mv) {
+    ensure_system_mass(c);
+    if (!c->have_drv_backup) backup_drivers(c);
+  }
   if (nsteps > 0) {
     prolog(c, dt);
     if (trig) trigger_standalone(c, 0, thr);
+    if (mv) driver_cycle(c, dt, tcur, false, true, nullptr, trig ? c->d_sflag + 0 : nullptr, thr);
   }
   for (int it = 0; it < nsteps; it++) {
     const bool last = it + 1 == nsteps;
@@ -1667,14 +1718,17 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
       contact_waves(c, dt, gate, (!last && trig) ? c->d_sflag + nslot : nullptr, &zeroed);
       if (last) {
         gather<1>(c, g, dt, gate);
+        if (mv) driver_cycle(c, dt, tcur + dt, true, false, gate, nullptr, thr);
         return;
       }
       if (!trig) {
         gather<2>(c, g, dt, gate);
+        if (mv) driver_cycle(c, dt, tcur + dt, true, true, gate, nullptr, thr);
         return;
       }
       if (!zeroed) CK(cudaMemsetAsync(c->d_sflag + nslot, 0, 8, c->st));
       gather<2>(c, g, dt, gate, c->d_sflag + nslot, thr);
+      if (mv) driver_cycle(c, dt, tcur + dt, true, true, gate, c->d_sflag + nslot, thr);
     };
     if (!trig) {
       const bool rb = rebuild_every > 0 && ((it + 1) % rebuild_every) == 0;
@@ -1692,14 +1746,16 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
         const uint64_t launches = c->ctr.kernel_launches;
         c->ctr = snap;   // the gated launches did nothing
         c->ctr.kernel_launches = launches;
-        rebuild(c, rcut_inc, symetric);
+        rebuild(c, rcut_inc, symetric);   // with moving drivers: backup_drivers + grid_rshape_driver inside
         nb++;
         c->queue_clean = false;   // the gated-off gather did not clear the chunk queue
         step_kernels(nullptr);
       }
     }
     c->ctr.particle_steps += c->nreal;
+    tcur += dt;
   }
+  c->physical_time = tcur;
   if (n_rebuilds) *n_rebuilds = nb;
   API_END(c)
 }
@@ -1898,7 +1954,8 @@ static void driver_op(edb_context* c, int op, double time, double dt, double sys
   if (nd) LAUNCH(c, k_driver_op, nblk(nd, 64), 64, 0, c->drv.p, c->mo.p, nd, op, time, dt, system_mass);
 }
 // reaction of the driver waves of the last contact operator -> DriverMotion::forces / mom (deterministic block-ordered sums)
-static void driver_force_reduce(edb_context* c) {
+// block partials of the driver waves summed into drv_sums[nd * 6] in a fixed order (this rank's share)
+static void driver_force_sums(edb_context* c) {
   const int nd = (int)c->h_drv.size();
   if (!nd) return;
   c->drv_sums.ensure((size_t)nd * 6 + 1);
@@ -1912,6 +1969,11 @@ static void driver_force_reduce(edb_context* c) {
     LAUNCH(c, k_driver_force, nb, BLK, smem, view(w), t, c->drv.p, nd, c->stage.p);
     LAUNCH(c, k_driver_force_sum, nblk((uint64_t)nd * 6, 64), 64, 0, c->stage.p, nb, nd, c->drv_sums.p);
   }
+}
+static void driver_force_reduce(edb_context* c) {
+  const int nd = (int)c->h_drv.size();
+  if (!nd) return;
+  driver_force_sums(c);
   if (c->cfg.nranks > 1) c->comm.allreduce_sum_f64_dev(c->drv_sums.p, (size_t)nd * 6, c->st);
   LAUNCH(c, k_driver_force_apply, nblk(nd, 64), 64, 0, c->drv_sums.p, nd, c->drv.p, c->mo.p, c->poly() ? 0 : 1);
 }
@@ -1934,14 +1996,14 @@ static void backup_drivers(edb_context* c) {
   c->have_drv_backup = true;
 }
 // adds the count to *d_out (device); the caller zeroes / reads it
-static void driver_displ_launch(edb_context* c, double thr, unsigned long long* d_out) {
+static void driver_displ_launch(edb_context* c, double thr, unsigned long long* d_out, const unsigned long long* gate = nullptr) {
   const int nd = (int)c->h_drv.size();
   if (!nd) return;
   if (!c->have_drv_backup) backup_drivers(c);
   int nvmax = 1;
   for (auto& m : c->h_md) nvmax = std::max(nvmax, m.nv);
   dim3 grid(std::min<uint32_t>(nblk(nvmax), 1024u), nd);
-  k_driver_displ<<<grid, BLK, 0, c->st>>>(c->drv.p, c->mo.p, c->drv_backup.p, c->mo_backup.p, nd, c->d_md.p, c->d_mlocal.p, thr * thr, d_out);
+  k_driver_displ<<<grid, BLK, 0, c->st>>>(c->drv.p, c->mo.p, c->drv_backup.p, c->mo_backup.p, nd, c->d_md.p, c->d_mlocal.p, thr * thr, d_out, gate);
   c->ctr.kernel_launches++;
 }
 extern "C" int edb_push_f_v_r_driver(edb_context* c, double time, double dt) {

@@ -264,6 +264,42 @@ __global__ void k_driver_force_apply(const double* __restrict__ sums, int ndrv, 
   if (sphere_mode && drv[d].kind == EDB_DRIVER_RSHAPE && rshape_need_moment(m)) m.mom = m.mom + mk3(sums[d * 6 + 3], sums[d * 6 + 4], sums[d * 6 + 5]);
 }
 
+// The driver operators between two contact evaluations, fused for the speculative step loop of edb_run_verlet (one thread per driver):
+//   end of step n   : reset_force_driver + the reaction sums of the step's contacts, force_to_accel_driver, push_f_v_driver(dt/2)
+//   begin of step n+1: push_f_v_r_driver(t, dt) when is_motion_triggered(t + dt), push_f_v_driver(dt/2), push_av_to_quat_driver(t, dt)
+// in the order of config_numerical_schemes.msp:13-15,23-24.  Gated like every state-changing kernel of the loop: a step that turns out to
+// need a neighbour rebuild first does nothing and is enqueued again.
+struct DriverCycleArgs {
+  Driver* drv;
+  DriverMotion* mo;
+  int n;
+  const double* sums;   // n * 6 reaction sums of step n (nullptr: no driver needs them)
+  int sphere_mode, do_end, do_begin;
+  double dt, system_mass, time_next;
+  const unsigned long long* gate;
+};
+__global__ void k_driver_cycle(DriverCycleArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n || (A.gate && *A.gate)) return;
+  Driver d = A.drv[i];
+  DriverMotion& m = A.mo[i];
+  if (A.do_end) {
+    m.forces = mk3(0, 0, 0);   // reset_force_driver ran before the contacts of the step
+    if (A.sums) {
+      if (m_need_forces(m.motion)) m.forces = m.forces + mk3(A.sums[i * 6], A.sums[i * 6 + 1], A.sums[i * 6 + 2]);
+      if (A.sphere_mode && d.kind == EDB_DRIVER_RSHAPE && rshape_need_moment(m)) m.mom = m.mom + mk3(A.sums[i * 6 + 3], A.sums[i * 6 + 4], A.sums[i * 6 + 5]);
+    }
+    driver_force_to_accel(d, m, A.system_mass);
+    driver_push_f_v(d, m, 0.5 * A.dt);
+  }
+  if (A.do_begin) {
+    if (motion_triggered(m, A.time_next + A.dt)) driver_push_f_v_r(d, m, A.time_next, A.dt);
+    driver_push_f_v(d, m, 0.5 * A.dt);
+    driver_push_av_to_quat(d, m, A.time_next, A.dt);
+  }
+  A.drv[i] = d;
+}
+
 // driver_vertices.cu:28-35: vertices_[i] = center + quat * shp_vertices[i] for the non-stationary meshes (rshape.hpp:419); `all` forces
 // every mesh (initialisation, RShapeDriver::initialize rshape.hpp:160-165 uses update_vertex = get_vertex(i, center, 1.0, quat))
 __global__ void k_driver_vertices(const MeshDev* __restrict__ md, int nmesh, const Driver* __restrict__ drv, const DriverMotion* __restrict__ mo,
@@ -284,9 +320,9 @@ __global__ void k_driver_vertices(const MeshDev* __restrict__ md, int nmesh, con
 // first driver that moved (:233-236); only "> 0" is consumed, so every driver is counted here.
 __global__ void k_driver_displ(const Driver* __restrict__ drv, const DriverMotion* __restrict__ mo, const Driver* __restrict__ bdrv,
                                const DriverMotion* __restrict__ bmo, int n, const MeshDev* __restrict__ md, const double4* __restrict__ local,
-                               double r2, unsigned long long* __restrict__ out) {
+                               double r2, unsigned long long* __restrict__ out, const unsigned long long* gate) {
   const int d = blockIdx.y;
-  if (d >= n) return;
+  if (d >= n || (gate && *gate)) return;
   const Driver &a = drv[d], &b = bdrv[d];
   const DriverMotion &ma = mo[d], &mb = bmo[d];
   unsigned int cnt = 0;

@@ -283,3 +283,33 @@ def test_gpu_expression_motion(product_lib, oracle_lib):
             e.push_av_to_quat_driver(t, wl.dt)
         compare_drivers(*engines, nd, what=f"expression step {it}")
         t += wl.dt
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_gpu_fused_loop_equals_operator_loop(product_lib, monkeypatch, name):
+    """edb_run_verlet with moving drivers: the speculative fused loop (k_driver_cycle between gather and contact, no host sync per
+    step) against the operator-by-operator loop (EDB_DRIVERS_UNFUSED=1, read at context creation) — bit-identical state."""
+    from exadem_b200 import Engine
+    from parity import bit_identical
+    make, nsteps, _ = SCENARIOS[name]
+    wl = make()
+    fused = wl.setup(Engine(product_lib, wl.config()))
+    monkeypatch.setenv("EDB_DRIVERS_UNFUSED", "1")
+    loop = wl.setup(Engine(product_lib, wl.config()))
+    monkeypatch.delenv("EDB_DRIVERS_UNFUSED")
+    nb = []
+    for e in (fused, loop):
+        e.update_particle_neighbors(wl.rcut_inc, True)
+        n1 = e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, nsteps // 2, 0)
+        n2 = e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, nsteps - nsteps // 2, 0)   # call boundary inside the run
+        nb.append(n1 + n2)
+    assert nb[0] == nb[1], nb
+    assert fused.counters().kernel_launches < loop.counters().kernel_launches
+    same = bit_identical(fused.download_particles(), loop.download_particles())
+    assert all(same.values()), same
+    da, db = fused.get_drivers(len(wl.drivers)), loop.get_drivers(len(wl.drivers))
+    for a, b in zip(da, db):
+        for k in DRIVER_FIELDS:
+            assert np.array_equal(np.atleast_1d(a[k]), np.atleast_1d(b[k])), k
+    assert fused.get_physical_time() == loop.get_physical_time()
