@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--rebuild-every", type=int, default=10)
     ap.add_argument("--rtol", type=float, default=1e-10)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--moving", action="store_true", help="add a stress-controlled floor (surface, LINEAR_COMPRESSIVE_MOTION): reaction all-reduce")
     args = ap.parse_args()
 
     import torch
@@ -67,6 +68,14 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     wl, pg = global_workload(args.mode, world)
+    if args.moving:
+        # every rank holds the same drivers; the floor is touched by particles of every brick, so its reaction is a sum over ranks
+        # (force_to_accel_driver.cpp:128-139) and its motion must come out identical on all of them
+        area = (wl.hi[0] - wl.lo[0]) * (wl.hi[1] - wl.lo[1])
+        wl.drivers = list(wl.drivers) + [dict(kind=capi.DRIVER_SURFACE, offset=0.03, normal=(0, 0, 1), center=(0, 0, 0.03))]
+        wl.motions = [dict(motion_type="STATIONARY")] * (len(wl.drivers) - 1) + [
+            dict(motion_type="LINEAR_COMPRESSIVE_MOTION", motion_vector=(0, 0, -1), sigma=2000.0, damprate=0.0, surface=area)]
+    system_mass = float(wl.particles.mass.sum())
     pos = wl.particles.vec("r")
     mine = parallel.owner_rank(pos, wl.lo, wl.hi, pg) == rank
     lo, hi = parallel.brick_bounds(wl.lo, wl.hi, pg, rank)
@@ -80,6 +89,9 @@ def main():
     if wl.shapes_spec:
         eng.set_shapes(wl.shapes())
     eng.set_drivers(wl.drivers)
+    if wl.motions:
+        eng.set_driver_motions(wl.motions)
+        eng.set_system_mass(system_mass)
     eng.upload_particles(parallel.select(wl.particles, mine))
     sym = wl.symetric
     eng.update_particle_neighbors(wl.rcut_inc, sym)
@@ -87,8 +99,9 @@ def main():
     pa = eng.download_particles()
     rec = eng.export_interactions()
     ctr = eng.counters()
+    drv_state = eng.get_drivers(len(wl.drivers)) if wl.motions else []
     payload = {"pa": {f: getattr(pa, f) for f in capi.F64_FIELDS + ["id", "type", "group"]}, "rec": rec, "nreb": nreb,
-               "n": pa.n, "launches": ctr.kernel_launches}
+               "n": pa.n, "launches": ctr.kernel_launches, "drv": drv_state}
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(payload, gathered, dst=0)
     ok = True
@@ -97,11 +110,22 @@ def main():
         ref = wl.setup(OracleEngine(OracleLibrary(), wl.config()))
         ref.set_threads(os.cpu_count() or 1)
         ref.set_virtual_bricks(pg)   # same both-sides enumeration of brick-straddling pairs as the N ranks (quirk Q6)
+        if wl.motions:
+            ref.set_system_mass(system_mass)
         ref.update_particle_neighbors(wl.rcut_inc, sym)
         nreb_ref = ref.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, sym, args.steps, args.rebuild_every)
         pr = ref.download_particles()
         rr = ref.export_interactions()
         try:
+            if wl.motions:
+                dref = ref.get_drivers(len(wl.drivers))
+                moved_drv = False
+                for g_ in gathered:
+                    for a_, b_ in zip(g_["drv"], dref):
+                        for k_ in ("center", "offset", "normal", "vel", "acc", "forces", "radius"):
+                            field_close(np.atleast_1d(a_[k_]), np.atleast_1d(b_[k_]), 1e-9, f"driver {k_}")
+                moved_drv = abs(dref[-1]["offset"] - 0.03) > 0 and np.abs(dref[-1]["forces"]).sum() > 0
+                assert moved_drv, "the stress-controlled floor neither moved nor felt a reaction"
             counts = [g["n"] for g in gathered]
             assert sum(counts) == pr.n, f"particle count {counts} != {pr.n}"
             assert all(g["nreb"] == nreb_ref for g in gathered), f"rebuild counts {[g['nreb'] for g in gathered]} vs {nreb_ref}"
