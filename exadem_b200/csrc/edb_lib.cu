@@ -1675,7 +1675,12 @@ static void driver_cycle(edb_context* c, double dt, double time_next, bool do_en
   const int nd = (int)c->h_drv.size();
   if (!nd) return;
   const bool sums = do_end && c->drivers_need_reaction;
-  if (sums) driver_force_sums(c);   // reads the contact state of the step; harmless on a gated-off step (the cycle kernel is gated)
+  if (sums) {
+    driver_force_sums(c);   // reads the contact state of the step; harmless on a gated-off step (the cycle kernel is gated)
+    // force_to_accel_driver.cpp:128-139 (MPI_Allreduce of 6 doubles per driver): stream-ordered NCCL all-reduce, no host round trip.
+    // Every rank enqueues the same sequence because the rebuild trigger that steers the loop is itself all-reduced.
+    if (c->cfg.nranks > 1) c->comm.allreduce_sum_f64_dev(c->drv_sums.p, (size_t)nd * 6, c->st);
+  }
   DriverCycleArgs A{c->drv.p, c->mo.p, nd, sums ? c->drv_sums.p : nullptr, c->poly() ? 0 : 1, do_end ? 1 : 0, do_begin ? 1 : 0,
                     dt, c->system_mass, time_next, gate};
   LAUNCH(c, k_driver_cycle, nblk(nd, 64), 64, 0, A);
@@ -1691,8 +1696,7 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
   uint64_t nb = 0;
   if (!c->have_prev) { rebuild(c, rcut_inc, symetric); }
   const bool mv = c->drivers_moving;
-  if (mv && (c->cfg.nranks > 1 || c->env_drivers_unfused)) {
-    // several ranks: the reaction sums need an all-reduce and the trigger of the drivers rides outside the mailbox exchange
+  if (mv && c->env_drivers_unfused) {
     nb = run_verlet_moving(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every);
     if (n_rebuilds) *n_rebuilds = nb;
     return EDB_OK;

@@ -48,12 +48,13 @@ def test_two_gpu_drum_slabs():
     _run(2, "--mode", "drum", "--steps", "60", "--rebuild-every", "0")
 
 
-def test_two_gpu_moving_driver():
+@pytest.mark.parametrize("env", [{}, {"EDB_DRIVERS_UNFUSED": "1"}], ids=["fused-loop", "operator-loop"])
+def test_two_gpu_moving_driver(env):
     """A stress-controlled floor under a two-brick box: the reaction of the contacts is all-reduced (NCCL) before force_to_accel_driver,
     every rank integrates the same driver; drivers, particles and interactions against the single-domain oracle."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    _run(2, "--mode", "sphere", "--steps", "60", "--rebuild-every", "0", "--moving")
+    _run(2, "--mode", "sphere", "--steps", "60", "--rebuild-every", "0", "--moving", env=env)
 
 
 @pytest.mark.parametrize("rebuild_every", [10, 0])
