@@ -418,6 +418,24 @@ def main():
     if roof["frac"] > 1.0:
         roof["note"] = ("frac > 1: the reference algorithm's compulsory bytes (184 B/record) divided by this kernel's time exceed the peak "
                         "because records not in contact cost this kernel 9 B; see frac_dram_model / traffic for the bytes it really moves")
+    # The other half of the step: k_gather<2> (deterministic force sum + gravity + force_to_accel + epilog + next prolog + trigger).
+    # Algorithmic bytes: 312 B per particle (r, v, vrot, Q, inertia, r_backup in; r, v, vrot, Q out) + 5 B per incidence
+    # (code + flag byte; a particle-particle record is incident to two particles) + 64 B per incident side of a record in contact.
+    roof_g = None
+    if c.gather_launches > 0 and c.gather_ms > 0:
+        npp = 1 if wl.mode == 0 else 4
+        inc = 2.0 * float(counts[:npp].sum()) + float(counts[npp if npp == 4 else 4:].sum())
+        hot = 2.0 * float(active[:npp].sum()) + float(active[4:].sum())
+        g_bytes = 312.0 * wl.particles.n + 5.0 * inc + 64.0 * hot
+        tg = c.gather_ms / c.gather_launches * 1e-3
+        roof_g = {"kernel": "k_gather", "bound": "hbm", "achieved": g_bytes / tg / 1e9, "peak": peak, "unit": "GB/s",
+                  "frac": g_bytes / tg / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": g_bytes,
+                  "mean_launch_ms": tg * 1e3, "share_of_step": c.gather_ms / ms if ms > 0 else None}
+        if prof.exists():
+            try:
+                roof_g["traffic"] = json.loads(prof.read_text()).get("k_gather")
+            except Exception:
+                pass
     poly = None
     if world == 1 and not args.no_poly and (args.workload or "drum") == "drum":
         eng.close()
@@ -438,6 +456,8 @@ def main():
                        "l2": "working set (particles + interaction waves) > 126 MB L2, no flush",
                        "timing": "CUDA events on the library stream, max over ranks", "wall_s": wall},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    if roof_g is not None:
+        line["roofline_gather"] = roof_g
     if poly is not None:
         line["polyhedra"] = poly
     print(json.dumps(line), flush=True)

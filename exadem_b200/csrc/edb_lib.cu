@@ -360,6 +360,8 @@ extern "C" int edb_destroy(edb_context* c) {
   c->stage.release(); c->stage_u64.release(); c->l2buf.release();
   c->d_md.release(); c->d_mverts.release(); c->d_medges.release(); c->d_mfoff.release(); c->d_mfn.release(); c->d_mfidx.release();
   c->d_mcell_data.release(); c->d_mcell_off.release();
+  c->mo.release(); c->mo_backup.release(); c->drv_backup.release(); c->d_mlocal.release(); c->d_mprim_start.release();
+  c->d_mcell_cnt.release(); c->drv_sums.release();
   c->mig_dest.release(); c->mig_midx.release(); c->mig_cnt.release(); c->mig_off.release(); c->imm_cnt.release(); c->imm_off.release();
   c->mig_sp.release(); c->mig_rp.release(); c->mig_sh.release(); c->mig_rh.release(); c->imm_tab.release();
   c->tw_cnt.release(); c->tw_flag.release(); c->tw_pos.release(); c->tw_own.release(); c->tw_par.release(); c->tw_tpos.release();
@@ -1927,23 +1929,15 @@ extern "C" int edb_import_interactions(edb_context* c, const edb_interaction* in
   API_END(c)
 }
 
+static void driver_force_sums(edb_context* c);
 extern "C" int edb_compute_driver_force_moment(edb_context* c, double* forces, double* moments) {
   API_BEGIN(c)
   const int nd = (int)c->h_drv.size();
+  if (nd == 0) return EDB_OK;
+  driver_force_sums(c);   // per wave: block partials (k_driver_force) summed in block order on the device (k_driver_force_sum)
   std::vector<double> acc((size_t)nd * 6, 0.0);
-  for (int t = 4; t <= 12; t++) {
-    Wave& w = c->wave[t];
-    if (!w.n || !nd) continue;
-    const uint32_t nb = nblk(w.n);
-    c->stage.ensure((size_t)nb * nd * 6 + 1);
-    const size_t smem = (size_t)(BLK / 32) * nd * 6 * sizeof(double);
-    LAUNCH(c, k_driver_force, nb, BLK, smem, view(w), t, c->drv.p, nd, c->stage.p);
-    std::vector<double> part((size_t)nb * nd * 6);
-    CK(cudaMemcpyAsync(part.data(), c->stage.p, part.size() * 8, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    for (uint32_t b = 0; b < nb; b++)
-      for (int i = 0; i < nd * 6; i++) acc[i] += part[(size_t)b * nd * 6 + i];
-  }
+  CK(cudaMemcpyAsync(acc.data(), c->drv_sums.p, acc.size() * 8, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
   for (int d = 0; d < nd; d++)
     for (int k = 0; k < 3; k++) {
       forces[3 * d + k] = acc[d * 6 + k];
