@@ -144,6 +144,26 @@ def scenario_polyhedra_mesh_shaker():
     return wl
 
 
+def scenario_pendulum():
+    """A wall hinged above the bed that swings through the vertical (surface, PENDULUM_MOTION): normal and offset are recomputed from
+    the pendulum every step and the normal flips when the swing changes side (driver_params.hpp:340-364)."""
+    wl = workloads.deposit((7, 7, 4))
+    anchor = (0.02, 3.5, 8.0)
+    wl.drivers.append(dict(kind=capi.DRIVER_SURFACE, offset=0.02, normal=(1, 0, 0), center=anchor))
+    wl.motions = [dict(motion_type="STATIONARY"),
+                  dict(motion_type="PENDULUM_MOTION", omega=500.0, amplitude=0.3, pendulum_anchor_point=anchor,
+                       pendulum_initial_position=(0.02, 3.5, 0.0), pendulum_swing_dir=(1, 0, 0))]
+    return wl
+
+
+def scenario_mesh_force_motion():
+    """The small mesh pushed by a constant force along x plus the projection of the contact reaction (LINEAR_FORCE_MOTION)."""
+    wl = scenario_moving_mesh()
+    wl.name = "mesh_force_motion"
+    wl.motions[-1] = dict(motion_type="LINEAR_FORCE_MOTION", motion_vector=(1, 0, 0), const_force=40.0, mass=3.0)
+    return wl
+
+
 def run_scenario(wl, engines, nsteps, expect_driver_waves, min_rebuilds=1):
     """rebuild + run_verlet with the displacement trigger on every engine; parity of the interaction set, the particles and the drivers."""
     a, b = engines
@@ -214,6 +234,8 @@ SCENARIOS = {
     "walls_and_balls": (scenario_walls_and_balls, 40, (5, 6)),
     "moving_mesh": (scenario_moving_mesh, 30, (7, 8, 9)),
     "polyhedra_mesh_shaker": (scenario_polyhedra_mesh_shaker, 24, (7, 8, 9, 10, 11, 12)),
+    "pendulum": (scenario_pendulum, 80, (5,)),
+    "mesh_force_motion": (scenario_mesh_force_motion, 30, (7, 8, 9)),
 }
 
 
@@ -232,7 +254,7 @@ def test_scenarios_are_meaningful_on_the_oracle(name):
     wl = make()
     engines = _oracle_pair(wl)
     before = engines[0].get_drivers(len(wl.drivers))
-    drv, cnt, act = run_scenario(wl, engines, nsteps, waves, min_rebuilds=1 if name != "walls_and_balls" else 0)
+    drv, cnt, act = run_scenario(wl, engines, nsteps, waves, min_rebuilds=0 if name in ("walls_and_balls", "pendulum") else 1)
     moved = [i for i in range(len(drv)) if not all(np.array_equal(np.atleast_1d(before[i][k]), np.atleast_1d(drv[i][k])) for k in DRIVER_FIELDS)]
     assert moved, "no driver changed state"
     assert sum(act[t] for t in waves) > 0, (act, "no active driver contact")
@@ -255,7 +277,7 @@ def _gpu_pair(wl, product_lib, oracle_lib):
 def test_gpu_run_verlet_with_moving_drivers(product_lib, oracle_lib, name):
     make, nsteps, waves = SCENARIOS[name]
     wl = make()
-    run_scenario(wl, _gpu_pair(wl, product_lib, oracle_lib), nsteps, waves, min_rebuilds=1 if name != "walls_and_balls" else 0)
+    run_scenario(wl, _gpu_pair(wl, product_lib, oracle_lib), nsteps, waves, min_rebuilds=0 if name in ("walls_and_balls", "pendulum") else 1)
 
 
 @pytest.mark.gpu
