@@ -114,6 +114,17 @@ def driver_to_dict(D, M=None) -> dict:
     return out
 
 
+class InnerBondParams(C.Structure):
+    _fields_ = [("kn", C.c_double), ("kt", C.c_double), ("damp_rate", C.c_double), ("mode", C.c_int32), ("pad", C.c_int32),
+                ("crit1", C.c_double), ("crit2", C.c_double)]
+
+
+INNER_BOND_DTYPE = np.dtype([("id_i", "<u8"), ("id_j", "<u8"), ("sub_i", "<u4"), ("sub_j", "<u4"), ("friction", "<f8", 3), ("en", "<f8"),
+                             ("tds", "<f8", 3), ("et", "<f8"), ("dn0", "<f8"), ("weight", "<f8"), ("criteria_1", "<f8"),
+                             ("criteria_2", "<f8"), ("mode", "<i4"), ("unbroken", "u1"), ("ghost", "u1"), ("pad", "<u2")])
+assert INNER_BOND_DTYPE.itemsize == 128
+
+
 class Shape(C.Structure):
     _fields_ = [("nv", C.c_int32), ("ne", C.c_int32), ("nf", C.c_int32), ("faces_len", C.c_int32),
                 ("vertices", _D), ("edges", C.POINTER(C.c_int32)), ("faces", C.POINTER(C.c_int32)),
@@ -379,6 +390,42 @@ class Engine:
 
     def set_system_mass(self, m):
         self._call("set_system_mass", C.c_double(m))
+
+    # -- inner bonds (wave 13)
+    def set_inner_bond_params(self, n_groups, params):
+        arr = (InnerBondParams * (n_groups * n_groups))(*[InnerBondParams(**p) for p in params])
+        self._call("set_inner_bond_params", C.c_int32(n_groups), arr)
+
+    def import_inner_bonds(self, rec: np.ndarray):
+        rec = np.ascontiguousarray(rec, dtype=INNER_BOND_DTYPE)
+        self._call("import_inner_bonds", rec.ctypes.data_as(C.c_void_p), C.c_uint64(len(rec)))
+
+    def export_inner_bonds(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._call("export_inner_bonds", C.c_void_p(), C.c_uint64(0), C.byref(n))
+        rec = np.zeros(n.value, dtype=INNER_BOND_DTYPE)
+        if n.value:
+            self._call("export_inner_bonds", rec.ctypes.data_as(C.c_void_p), C.c_uint64(n.value), C.byref(n))
+        return rec
+
+    def update_interfaces(self):
+        n = C.c_uint64()
+        self._call("update_interfaces", C.byref(n))
+        return n.value
+
+    def inner_bond_polyhedron(self, dt):
+        self._call("inner_bond_polyhedron", C.c_double(dt))
+
+    def apply_interface_fracture_criterion(self):
+        n = C.c_uint64()
+        self._call("apply_interface_fracture_criterion", C.byref(n))
+        return n.value
+
+    def get_inner_bond_state(self, n):
+        dn, cp, fn, ft = np.zeros(n), np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+        p = lambda a: a.ctypes.data_as(_D)
+        self._call("get_inner_bond_state", p(dn), p(cp), p(fn), p(ft))
+        return dn, cp, fn, ft
 
     def set_shapes(self, shapes):
         arr = (Shape * len(shapes))(*shapes)

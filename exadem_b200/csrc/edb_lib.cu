@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -13,13 +14,15 @@
 #include "kernels_migrate.cuh"
 #include "kernels_twin.cuh"
 #include "kernels_driver.cuh"
+#include "kernels_bond.cuh"
 #include "comm.cuh"
 
 using namespace edb;
 
 static thread_local std::string g_create_error;
 static_assert(sizeof(edb_config) == 152 && sizeof(edb_interaction) == 104 && sizeof(edb_contact_params) == 64 &&
-                  sizeof(edb_particles) == 8 + 31 * 8 && sizeof(edb_driver) == 184 && sizeof(edb_driver_motion) == 400,
+                  sizeof(edb_particles) == 8 + 31 * 8 && sizeof(edb_driver) == 184 && sizeof(edb_driver_motion) == 400 &&
+                  sizeof(edb_inner_bond) == 128 && sizeof(edb_inner_bond_params) == 48,
               "C ABI struct layout changed: update include/exadem_b200.h users and exadem_b200/capi.py");
 
 // wave order of the contact operators (classifier_for_all.hpp:116-156 as called by contact_force_sphere.cu.in:132-188 and
@@ -114,6 +117,16 @@ struct edb_context {
   DevBuf<double> drv_sums;
   bool drivers_moving = false, have_drv_backup = false;
   bool drivers_need_reaction = false, mesh_moving = false;   // set with the motions
+  // inner bonds (wave 13, kernels_bond.cuh): host mirror in device order + SoA on the device
+  std::vector<edb_inner_bond> h_bonds;
+  bool bonds_on_device = false;                   // the dynamic fields (friction, tds, en, et, unbroken) of h_bonds are stale
+  DevBuf<uint2> b_ij, b_sub, b_itf;
+  DevBuf<double4> b_par, b_fr, b_tds, b_fd, b_cp;
+  DevBuf<uint8_t> b_mode, b_unbroken, b_itf_broken;
+  DevBuf<uint32_t> b_plist, b_inc_off, b_inc;
+  uint32_t n_bond_particles = 0, n_interfaces = 0;
+  DevBuf<BondParams> d_ibp;
+  int ibp_groups = 0;
   double physical_time = 0, system_mass = 0;
   bool have_system_mass = false;
   // staging for host transfers
@@ -362,6 +375,9 @@ extern "C" int edb_destroy(edb_context* c) {
   c->d_mcell_data.release(); c->d_mcell_off.release();
   c->mo.release(); c->mo_backup.release(); c->drv_backup.release(); c->d_mlocal.release(); c->d_mprim_start.release();
   c->d_mcell_cnt.release(); c->drv_sums.release();
+  c->b_ij.release(); c->b_sub.release(); c->b_itf.release(); c->b_par.release(); c->b_fr.release(); c->b_tds.release(); c->b_fd.release();
+  c->b_cp.release(); c->b_mode.release(); c->b_unbroken.release(); c->b_itf_broken.release(); c->b_plist.release(); c->b_inc_off.release();
+  c->b_inc.release(); c->d_ibp.release();
   c->mig_dest.release(); c->mig_midx.release(); c->mig_cnt.release(); c->mig_off.release(); c->imm_cnt.release(); c->imm_off.release();
   c->mig_sp.release(); c->mig_rp.release(); c->mig_sh.release(); c->mig_rh.release(); c->imm_tab.release();
   c->tw_cnt.release(); c->tw_flag.release(); c->tw_pos.release(); c->tw_own.release(); c->tw_par.release(); c->tw_tpos.release();
@@ -2069,6 +2085,188 @@ extern "C" int edb_set_system_mass(edb_context* c, double m) {
   API_BEGIN(c)
   c->system_mass = m;
   c->have_system_mass = true;
+  API_END(c)
+}
+
+// ---- inner bonds (per-step operators) --------------------------------------------------------------------------
+static BondView bond_view(edb_context* c) {
+  return BondView{(uint32_t)c->h_bonds.size(), c->b_ij.p, c->b_sub.p, c->b_par.p, c->b_mode.p, c->b_unbroken.p, c->b_fr.p, c->b_tds.p, c->b_fd.p, c->b_cp.p};
+}
+// device -> host mirror of the fields the kernels change
+static void bonds_download(edb_context* c) {
+  const size_t n = c->h_bonds.size();
+  if (!c->bonds_on_device || n == 0) return;
+  std::vector<double4> fr(n), td(n);
+  std::vector<uint8_t> ub(n);
+  CK(cudaStreamSynchronize(c->st));
+  CK(cudaMemcpy(fr.data(), c->b_fr.p, n * sizeof(double4), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(td.data(), c->b_tds.p, n * sizeof(double4), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ub.data(), c->b_unbroken.p, n, cudaMemcpyDeviceToHost));
+  for (size_t k = 0; k < n; k++) {
+    edb_inner_bond& b = c->h_bonds[k];
+    b.friction[0] = fr[k].x; b.friction[1] = fr[k].y; b.friction[2] = fr[k].z; b.en = fr[k].w;
+    b.tds[0] = td[k].x; b.tds[1] = td[k].y; b.tds[2] = td[k].z; b.et = td[k].w;
+    b.unbroken = ub[k];
+  }
+}
+// Resolves the particle slots by id in the current device order (rebuild-frequency, like update_persistent_interactions), sorts the
+// bonds by (owner slot, partner id, sub_i, sub_j), uploads the SoA, the per-particle incidence lists and the interfaces.
+static void bonds_upload(edb_context* c) {
+  const size_t n = c->h_bonds.size();
+  c->n_bond_particles = 0; c->n_interfaces = 0;
+  c->bonds_on_device = false;
+  if (n == 0) return;
+  const uint32_t np = c->nreal;
+  std::vector<uint64_t> ids(np);
+  CK(cudaStreamSynchronize(c->st));
+  if (np) CK(cudaMemcpy(ids.data(), c->pa.id.p, (size_t)np * 8, cudaMemcpyDeviceToHost));
+  std::unordered_map<uint64_t, uint32_t> slot;
+  slot.reserve((size_t)np * 2);
+  for (uint32_t p = 0; p < np; p++) slot[ids[p]] = p;
+  std::vector<uint2> ij(n);
+  std::vector<uint32_t> order(n);
+  auto find = [&](uint64_t id) { auto it = slot.find(id); return it == slot.end() ? 0xffffffffu : it->second; };
+  std::vector<uint32_t> si(n), sj(n);
+  for (size_t k = 0; k < n; k++) { si[k] = find(c->h_bonds[k].id_i); sj[k] = find(c->h_bonds[k].id_j); order[k] = (uint32_t)k; }
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    const edb_inner_bond &x = c->h_bonds[a], &y = c->h_bonds[b];
+    return std::tie(si[a], x.id_j, x.sub_i, x.sub_j) < std::tie(si[b], y.id_j, y.sub_i, y.sub_j);
+  });
+  std::vector<edb_inner_bond> sorted(n);
+  for (size_t k = 0; k < n; k++) { sorted[k] = c->h_bonds[order[k]]; ij[k] = make_uint2(si[order[k]], sj[order[k]]); }
+  c->h_bonds.swap(sorted);
+  std::vector<uint2> sub(n);
+  std::vector<double4> par(n), fr(n), td(n);
+  std::vector<uint8_t> mode(n), ub(n);
+  for (size_t k = 0; k < n; k++) {
+    const edb_inner_bond& b = c->h_bonds[k];
+    sub[k] = make_uint2(b.sub_i, b.sub_j);
+    par[k] = make_double4(b.dn0, b.weight, b.criteria_1, b.criteria_2);
+    fr[k] = make_double4(b.friction[0], b.friction[1], b.friction[2], b.en);
+    td[k] = make_double4(b.tds[0], b.tds[1], b.tds[2], b.et);
+    mode[k] = (uint8_t)b.mode; ub[k] = b.unbroken;
+  }
+  c->b_ij.ensure(n); c->b_sub.ensure(n); c->b_par.ensure(n); c->b_fr.ensure(n); c->b_tds.ensure(n); c->b_fd.ensure(n); c->b_cp.ensure(n);
+  c->b_mode.ensure(n); c->b_unbroken.ensure(n);
+  CK(cudaMemcpy(c->b_ij.p, ij.data(), n * sizeof(uint2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->b_sub.p, sub.data(), n * sizeof(uint2), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->b_par.p, par.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->b_fr.p, fr.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->b_tds.p, td.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->b_mode.p, mode.data(), n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->b_unbroken.p, ub.data(), n, cudaMemcpyHostToDevice));
+  CK(cudaMemset(c->b_fd.p, 0, n * sizeof(double4)));
+  CK(cudaMemset(c->b_cp.p, 0, n * sizeof(double4)));
+  // incidence lists: for every particle that carries bonds, its bonds in bond order (side 0 = i, 1 = j)
+  std::vector<std::pair<uint32_t, uint32_t>> inc;   // (particle, code)
+  for (size_t k = 0; k < n; k++) {
+    if (ij[k].x == 0xffffffffu || ij[k].y == 0xffffffffu) continue;
+    inc.push_back({ij[k].x, (uint32_t)(k << 1)});
+    inc.push_back({ij[k].y, (uint32_t)(k << 1) | 1u});
+  }
+  std::stable_sort(inc.begin(), inc.end(), [](auto& a, auto& b) { return a.first < b.first; });
+  std::vector<uint32_t> plist, off, codes;
+  for (size_t q = 0; q < inc.size(); q++) {
+    if (q == 0 || inc[q].first != inc[q - 1].first) { plist.push_back(inc[q].first); off.push_back((uint32_t)q); }
+    codes.push_back(inc[q].second);
+  }
+  off.push_back((uint32_t)inc.size());
+  c->n_bond_particles = (uint32_t)plist.size();
+  c->b_plist.ensure(plist.size() + 1); c->b_inc_off.ensure(off.size() + 1); c->b_inc.ensure(codes.size() + 1);
+  if (!plist.empty()) {
+    CK(cudaMemcpy(c->b_plist.p, plist.data(), plist.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->b_inc_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->b_inc.p, codes.data(), codes.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // update_interfaces.cpp:44-84: maximal runs of bonds between the same two particles, PartnerGhost records skipped
+  std::vector<uint2> itf;
+  size_t loc = 0;
+  while (loc < n) {
+    if (c->h_bonds[loc].ghost == 2) { loc++; continue; }
+    size_t m = 1;
+    while (loc + m < n && c->h_bonds[loc + m].id_i == c->h_bonds[loc].id_i && c->h_bonds[loc + m].id_j == c->h_bonds[loc].id_j) m++;
+    itf.push_back(make_uint2((uint32_t)loc, (uint32_t)m));
+    loc += m;
+  }
+  c->n_interfaces = (uint32_t)itf.size();
+  c->b_itf.ensure(itf.size() + 1); c->b_itf_broken.ensure(itf.size() + 1);
+  if (!itf.empty()) {
+    CK(cudaMemcpy(c->b_itf.p, itf.data(), itf.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CK(cudaMemset(c->b_itf_broken.p, 0, itf.size()));
+  }
+  c->bonds_on_device = true;
+}
+extern "C" int edb_set_inner_bond_params(edb_context* c, int32_t ng, const edb_inner_bond_params* p) {
+  API_BEGIN(c)
+  if (ng < 1) throw StateError{EDB_ERR_INVALID, "n_groups < 1"};
+  std::vector<BondParams> t((size_t)ng * ng);
+  for (size_t i = 0; i < t.size(); i++) t[i] = BondParams{p[i].kn, p[i].kt, p[i].damp_rate, p[i].mode, 0, p[i].crit1, p[i].crit2};
+  c->d_ibp.ensure(t.size());
+  CK(cudaMemcpy(c->d_ibp.p, t.data(), t.size() * sizeof(BondParams), cudaMemcpyHostToDevice));
+  c->ibp_groups = ng;
+  API_END(c)
+}
+extern "C" int edb_import_inner_bonds(edb_context* c, const edb_inner_bond* in, uint64_t n) {
+  API_BEGIN(c)
+  if (!c->poly()) throw StateError{EDB_ERR_STATE, "inner bonds need a polyhedron context"};
+  c->h_bonds.assign(in, in + n);
+  bonds_upload(c);
+  API_END(c)
+}
+extern "C" int edb_export_inner_bonds(edb_context* c, edb_inner_bond* out, uint64_t cap, uint64_t* n) {
+  API_BEGIN(c)
+  *n = c->h_bonds.size();
+  if (!out) return EDB_OK;
+  if (cap < c->h_bonds.size()) throw StateError{EDB_ERR_CAPACITY, "edb_export_inner_bonds: capacity too small"};
+  bonds_download(c);
+  if (!c->h_bonds.empty()) memcpy(out, c->h_bonds.data(), c->h_bonds.size() * sizeof(edb_inner_bond));
+  API_END(c)
+}
+extern "C" int edb_update_interfaces(edb_context* c, uint64_t* n_interfaces) {
+  API_BEGIN(c)
+  bonds_download(c);
+  bonds_upload(c);
+  if (n_interfaces) *n_interfaces = c->n_interfaces;
+  API_END(c)
+}
+extern "C" int edb_inner_bond_polyhedron(edb_context* c, double dt) {
+  API_BEGIN(c)
+  const uint32_t n = (uint32_t)c->h_bonds.size();
+  if (n == 0) return EDB_OK;
+  if (!c->bonds_on_device) throw StateError{EDB_ERR_STATE, "inner_bond_polyhedron before edb_import_inner_bonds / edb_update_interfaces"};
+  if (!c->ibp_groups) throw StateError{EDB_ERR_STATE, "inner_bond_polyhedron before edb_set_inner_bond_params"};
+  if (c->S.nvmax <= 0 || !c->vert.p) throw StateError{EDB_ERR_STATE, "inner_bond_polyhedron needs the world vertices (edb_compute_vertices)"};
+  LAUNCH(c, k_bond_force, nblk(n), BLK, 0, bond_view(c), view(c->pa), c->vert.p, c->S, c->d_ibp.p, c->ibp_groups, dt);
+  LAUNCH(c, k_bond_gather, nblk(c->n_bond_particles), BLK, 0, bond_view(c), view(c->pa), c->b_plist.p, c->b_inc_off.p, c->b_inc.p, c->n_bond_particles);
+  c->ctr.interaction_updates += n;
+  API_END(c)
+}
+extern "C" int edb_apply_interface_fracture_criterion(edb_context* c, uint64_t* n_broken) {
+  API_BEGIN(c)
+  *n_broken = 0;
+  if (c->n_interfaces == 0) return EDB_OK;
+  CK(cudaMemsetAsync(c->d_flag, 0, 8, c->st));
+  LAUNCH(c, k_interface_criterion, nblk(c->n_interfaces), BLK, 0, bond_view(c), c->b_itf.p, c->n_interfaces, c->b_itf_broken.p, c->d_flag);
+  CK(cudaMemcpyAsync(c->h_flag, c->d_flag, 8, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  *n_broken = c->h_flag[0];
+  API_END(c)
+}
+extern "C" int edb_get_inner_bond_state(edb_context* c, double* dn, double* cp, double* fn, double* ft) {
+  API_BEGIN(c)
+  const size_t n = c->h_bonds.size();
+  if (n == 0 || !c->bonds_on_device) return EDB_OK;
+  std::vector<double4> fd(n), cpv(n), fr(n);
+  CK(cudaStreamSynchronize(c->st));
+  CK(cudaMemcpy(fd.data(), c->b_fd.p, n * sizeof(double4), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cpv.data(), c->b_cp.p, n * sizeof(double4), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(fr.data(), c->b_fr.p, n * sizeof(double4), cudaMemcpyDeviceToHost));
+  for (size_t k = 0; k < n; k++) {
+    if (dn) dn[k] = fd[k].w;
+    if (cp) { cp[3 * k] = cpv[k].x; cp[3 * k + 1] = cpv[k].y; cp[3 * k + 2] = cpv[k].z; }
+    if (fn) { fn[3 * k] = fd[k].x - fr[k].x; fn[3 * k + 1] = fd[k].y - fr[k].y; fn[3 * k + 2] = fd[k].z - fr[k].z; }
+    if (ft) { ft[3 * k] = fr[k].x; ft[3 * k + 1] = fr[k].y; ft[3 * k + 2] = fr[k].z; }
+  }
   API_END(c)
 }
 

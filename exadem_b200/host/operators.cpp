@@ -162,6 +162,38 @@ class UpdateGridSTLMeshOperator : public OperatorNode {
   std::string documentation() const final { return "grid_rshape_driver: update the list of mesh vertices / edges / faces of every cell (device build)."; }
   void execute() final { ck(*grid, edb_grid_rshape_driver(grid->ctx), "grid_rshape_driver"); }
 };
+// -------------------------------------------------------------------------------------------------------------------
+// inner bonds (fragmentation decks, data/config/config_fragmentation.msp): per-step operators
+// -------------------------------------------------------------------------------------------------------------------
+// src/polyhedron/inner_bond_force.cu:44-139
+class ComputeInnerBondForce : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(double, dt, INPUT, REQUIRED);
+ public:
+  std::string documentation() const final { return "This operator computes forces between inner_bonded particles using the contact law.\n\nYAML example:\n\n  - inner_bond_polyhedron"; }
+  void execute() final { ck(*grid, edb_inner_bond_polyhedron(grid->ctx, *dt), "inner_bond_polyhedron"); }
+};
+// src/interaction/update_interfaces.cpp:28-95
+class UpdateInterfaces : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+ public:
+  std::string documentation() const final { return "update_interfaces: rebuilds the interfaces (runs of inner bonds between the same two particles) and re-resolves the bonds by particle id."; }
+  void execute() final { ck(*grid, edb_update_interfaces(grid->ctx, nullptr), "update_interfaces"); }
+};
+// src/interaction/apply_interface_fracture_criterion.cpp + include/exaDEM/interface/apply_interface_fracture_criterion.hpp:40-73
+class ApplyInterfaceFractureCriterion : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(bool, display, INPUT, false);
+  ADD_SLOT(bool, result, OUTPUT);
+ public:
+  std::string documentation() const final { return "apply_interface_fracture_criterion: breaks the interfaces whose energies exceed their criterion; result = true if at least one interface broke."; }
+  void execute() final {
+    uint64_t nb = 0;
+    ck(*grid, edb_apply_interface_fracture_criterion(grid->ctx, &nb), "apply_interface_fracture_criterion");
+    *result = nb > 0;
+  }
+};
+
 // src/driver/backup_drivers.cu
 class BackupDrivers : public OperatorNode {
   ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
@@ -342,6 +374,9 @@ ONIKA_AUTORUN_INIT(exadem_b200_hot_path) {
   f->register_factory("grid_rshape_driver", make_simple_operator<UpdateGridSTLMeshOperator>);
   f->register_factory("backup_drivers", make_simple_operator<BackupDrivers>);
   f->register_factory("driver_displ_over", make_simple_operator<DriverDisplacementOver>);
+  f->register_factory("inner_bond_polyhedron", make_simple_operator<ComputeInnerBondForce>);
+  f->register_factory("update_interfaces", make_simple_operator<UpdateInterfaces>);
+  f->register_factory("apply_interface_fracture_criterion", make_simple_operator<ApplyInterfaceFractureCriterion>);
 }
 
 // -------------------------------------------------------------------------------------------------------------------

@@ -126,6 +126,26 @@ typedef struct edb_driver_motion {
   double forces[3];                /* fields_.forces_: reaction summed by force_to_accel_driver (output of edb_get_drivers) */
 } edb_driver_motion;
 
+/* InnerBondParams (src/forcefield/include/exaDEM/forcefield/inner_bond_parameters.hpp:33-45), the `multimat_ibp` slot entries */
+enum { EDB_RUPTURE_ENERGY_MIXED = 0, EDB_RUPTURE_ENERGY_SEPARATE = 1, EDB_RUPTURE_STRESS_ENERGY_SEPARATE = 2, EDB_RUPTURE_NONE = 3 };
+typedef struct edb_inner_bond_params {
+  double kn, kt, damp_rate;
+  int32_t mode;     /* EDB_RUPTURE_* (rupture_criterion.hpp:26) */
+  int32_t pad;
+  double crit1, crit2;
+} edb_inner_bond_params;
+/* One inner bond = the fields of InnerBondInteraction (src/interaction/include/exaDEM/interaction/inner_bond_interaction.hpp:33-41)
+ * with the particles named by id (the reference's (cell, p) addressing is rebuilt by update_persistent_interactions at every move) */
+typedef struct edb_inner_bond {
+  uint64_t id_i, id_j;
+  uint32_t sub_i, sub_j;        /* glued vertices */
+  double friction[3], en, tds[3], et, dn0, weight;
+  double criteria_1, criteria_2; /* RuptureCriteria */
+  int32_t mode;
+  uint8_t unbroken, ghost;
+  uint16_t pad;
+} edb_inner_bond;
+
 /* `shape` (src/shape/include/exaDEM/shape.hpp:50-69) flattened: faces as the [n0, v.., n1, v..] stream. */
 typedef struct edb_shape {
   int32_t nv, ne, nf, faces_len;
@@ -244,6 +264,26 @@ typedef struct edb_sim_state {
   uint64_t n_particles, n_active_interactions, n_total_interactions;
 } edb_sim_state;
 int edb_simulation_state(edb_context*, int32_t symetric, edb_sim_state* out);
+
+/* ---- inner bonds (fragmentation, wave 13), SURVEY 8(f) rank 4: the per-step operators.  Bond creation (stick_polyhedra, a one-off
+ * preprocessing) and the fragmentation dump reader stay on the host side of the binding: the bonds enter through
+ * edb_import_inner_bonds.  NOT built yet: suppression of the regular contacts between bonded particles
+ * (InteractionManager::update_ignore_interaction) and the conversion of broken bonds into vertex-vertex contacts at the next
+ * rebuild (unclassify_interactions.cpp:135-145); bonds across periodic / brick boundaries. ------------------------------------ */
+int edb_set_inner_bond_params(edb_context*, int32_t n_groups, const edb_inner_bond_params* ibp /* n_groups^2 */);
+int edb_import_inner_bonds(edb_context*, const edb_inner_bond* in, uint64_t n);
+int edb_export_inner_bonds(edb_context*, edb_inner_bond* out, uint64_t cap, uint64_t* n); /* owner-sorted; out may be NULL to query n */
+/* [update_interfaces] src/interaction/update_interfaces.cpp:44-84: interfaces = runs of bonds between the same two particles; also
+ * re-resolves the particle slots of the bonds by id (to be called after every edb_update_particle_neighbors, like the deck does) */
+int edb_update_interfaces(edb_context*, uint64_t* n_interfaces);
+/* [inner_bond_polyhedron] src/polyhedron/inner_bond_force.cu + include/exaDEM/polyhedron/inner_bond.hpp:106-185: the bond law
+ * (inner_bond_force.hpp:26-70) on every bond, forces and torques ADDED to the particles in a fixed order (no atomics) */
+int edb_inner_bond_polyhedron(edb_context*, double dt);
+/* [apply_interface_fracture_criterion] apply_interface_fracture_criterion.hpp:40-73: breaks the interfaces whose energies exceed
+ * their criterion (all their bonds become unbroken = 0); *n_broken = interfaces broken by this call */
+int edb_apply_interface_fracture_criterion(edb_context*, uint64_t* n_broken);
+/* ContactState of wave 13 (dn, cp, fn, ft), one entry per bond in export order */
+int edb_get_inner_bond_state(edb_context*, double* dn, double* cp, double* fn, double* ft);
 
 /* Fused fast path = numerical_scheme_verlet (data/config/config_numerical_schemes.msp:6-30), `nsteps` iterations:
  * prolog -> (rebuild if displacement >= rcut_inc/2 | ghost_update_rq) -> [compute_vertices] -> reset+gravity+contact

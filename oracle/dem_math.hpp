@@ -323,6 +323,44 @@ static inline void contact_force(int law, double dn, v3 n, double dt, const Para
 // common_kernels.hpp:137-145
 static inline v3 moments(v3 cp, v3 p, v3 f, v3 m) { return cross(cp - p, f) + m; }
 
+// ---- inner bonds (fragmentation, wave 13): src/forcefield/include/exaDEM/forcefield/inner_bond_force.hpp:26-70 ----
+struct BondParams {   // InnerBondParams (inner_bond_parameters.hpp:33-45)
+  double kn = 0, kt = 0, damp_rate = 0;
+  int mode = 3;       // RuptureMode (rupture_criterion.hpp:26): 0 EnergyMixedMode, 1 EnergySeparateMode, 2 StressEnergySeparateMode, 3 None
+  double crit1 = 0, crit2 = 0;
+};
+static inline void inner_bond_force_core(double dn, v3 n, double dn0, double weight, double dt, const BondParams& p, double meff, double& En,
+                                         v3& tds, double& Et, v3& ft, v3 cp, v3 pi, v3 vi, v3& fi, v3 wi, v3 pj, v3 vj, v3 wj) {
+  const double damp = p.damp_rate * 2.0 * std::sqrt(p.kn * meff);                       // common_kernels.hpp:28-31
+  const v3 vel = (vj - cross(cp - pj, wj)) - (vi - cross(cp - pi, wi));                 // :34-41
+  const double vn = dot(vel, n);
+  const double delta = dn - dn0;
+  const double kn_w = p.kn * weight, kt_w = p.kt * weight;
+  const double fne = -kn_w * delta, fnv = damp * vn;
+  const double fn = fne + fnv;
+  const v3 vfn = fn * n;
+  const v3 ds = dt * (vel - vn * n);                                                    // compute_tangential_force, :80-85
+  tds = tds + ds;
+  ft = kt_w * tds;
+  fi = vfn + ft;
+  En = (fne <= 0 ? 1.0 : 0.0) * (0.5 * kn_w * delta * delta);
+  Et = 0.5 * kt_w * dot(tds, tds);
+}
+// apply_interface_fracture_criterion.hpp:40-73: one interface = `size` consecutive bonds; returns true when it breaks
+static inline bool interface_breaks(int mode, double c1, double c2, const double* en, const double* et, const double* dn, const v3* fn, size_t size) {
+  double En = 0.0, Et = 0.0, S = 0.0;
+  for (size_t j = 0; j < size; j++) {
+    En += en[j];
+    Et += et[j];
+    if (dn[j] > 0.0) S += norm(fn[j]);
+  }
+  S /= size;
+  if (mode == 0) return En + Et > c1;
+  if (mode == 1) return En > c1 || Et > c2;
+  if (mode == 2) return (En > c1) && (S > c2);
+  return false;
+}
+
 // ---- drivers: src/driver/include/exaDEM/{cylinder,surface,ball}.hpp ----
 enum DriverKind { DRV_CYLINDER = 0, DRV_SURFACE = 1, DRV_BALL = 2, DRV_RSHAPE = 3, DRV_UNDEFINED = 4 };
 struct Driver {

@@ -26,6 +26,7 @@
 #include "dem_math.hpp"
 #include "../include/exadem_b200.h"
 
+#include <unordered_map>
 #include <algorithm>
 #include <array>
 #include <chrono>
@@ -85,6 +86,23 @@ struct Sim {
   std::vector<Driver> drivers;
   std::vector<Shape> shapes;
   int nvmax = 0;
+  // inner bonds (wave 13, InnerBondInteraction inner_bond_interaction.hpp:49-66) + interfaces (interface.hpp:28-33)
+  struct Bond {
+    uint64_t id_i = 0, id_j = 0;
+    uint32_t sub_i = 0, sub_j = 0, i = 0, j = 0;
+    v3 friction{0, 0, 0}, tds{0, 0, 0};
+    double en = 0, et = 0, dn0 = 0, weight = 1, c1 = 0, c2 = 0;
+    int mode = 3;
+    uint8_t unbroken = 1, ghost = 0;
+    double dn = 0;                 // ContactState of the wave
+    v3 cp{0, 0, 0}, fn{0, 0, 0};
+  };
+  std::vector<Bond> bonds;
+  std::vector<BondParams> ibp{BondParams()};
+  int ibp_groups = 1;
+  std::vector<double> cluster;                  // field::cluster per particle (index = particle index)
+  std::vector<std::pair<size_t, size_t>> interfaces;   // (loc, size)
+  std::vector<uint8_t> interface_broken;
   std::vector<Driver> drivers_backup;           // backup_drvs slot (backup_drivers.cu)
   double physical_time = 0, system_mass = 0;
   bool have_system_mass = false;
@@ -957,6 +975,143 @@ int orc_simulation_state(orc_sim* h, int32_t symetric, edb_sim_state* out) {
   return 0;
 }
 
+// ---- inner bonds: SURVEY 8(f) rank 4 (checker side) ----
+static void resolve_bonds(Sim& s) {   // persistent interactions follow their particles by id (update_persistent_interactions.cpp)
+  std::unordered_map<uint64_t, uint32_t> slot;
+  for (uint32_t p = 0; p < s.nreal; p++) slot[s.id[p]] = p;
+  for (auto& b : s.bonds) {
+    auto a = slot.find(b.id_i), c = slot.find(b.id_j);
+    b.i = a == slot.end() ? 0xffffffffu : a->second;
+    b.j = c == slot.end() ? 0xffffffffu : c->second;
+  }
+  std::stable_sort(s.bonds.begin(), s.bonds.end(), [](const Sim::Bond& x, const Sim::Bond& y) {
+    return std::tie(x.i, x.id_j, x.sub_i, x.sub_j) < std::tie(y.i, y.id_j, y.sub_i, y.sub_j);
+  });
+}
+static double face_area(const Shape& sh, int f, double h = 1.0) {   // shape.hpp:673-697 (fan triangulation), :359-362 (h^2 scaling)
+  double surface = 0;
+  const int* idx = &sh.fidx[sh.foff[f]];
+  const v3 v0 = sh.v[idx[0]];
+  for (int j = 1; j < sh.fn[f] - 1; j++) surface += 0.5 * norm(cross(sh.v[idx[j]] - v0, sh.v[idx[j + 1]] - v0));
+  return surface * h * h;
+}
+// stick_polyhedra.cpp:88-360: bonds between the matching faces of two polyhedra of the same cluster (id_i < id_j), one bond per
+// vertex pair closer than the sticking threshold, weight 1/#bonds, rupture criterion from the face area
+static void stick_polyhedra(Sim& s, double dn_crit) {
+  s.bonds.clear();
+  for (int ck = 1; ck <= s.nc[2]; ck++)
+    for (int cj = 1; cj <= s.nc[1]; cj++)
+      for (int ci = 1; ci <= s.nc[0]; ci++) {
+        const size_t ca = s.cell_of(ci, cj, ck);
+        for (uint32_t ia = s.cstart[ca]; ia < s.cstart[ca + 1]; ia++) {
+          const uint32_t a = s.citems[ia];
+          if (a >= s.nreal) continue;
+          const Shape& sa = s.shapes[s.type[a]];
+          const v3* va = s.pv(a);
+          for_each_neighbor(s, ci, cj, ck, a, [&](uint32_t b, bool ghostc) {
+            if (s.cluster[b] != s.cluster[a]) return;
+            if (s.id[a] >= s.id[b]) return;
+            const Shape& sb = s.shapes[s.type[b]];
+            const v3* vb = s.pv(b);
+            const BondParams& P = s.ibp[(size_t)s.group[a] * s.ibp_groups + s.group[b]];
+            std::vector<Sim::Bond> local;
+            bool found = false;
+            for (int i = 0; i < sa.nf() && !found; i++) {
+              const int* fi = &sa.fidx[sa.foff[i]];
+              const int ni_ = sa.fn[i];
+              if (ni_ < 3) continue;
+              v3 ni = cross(va[fi[1]] - va[fi[0]], va[fi[2]] - va[fi[0]]);
+              ni = ni * (1.0 / norm(ni));
+              const double area_i = face_area(sa, i);
+              for (int j = 0; j < sb.nf() && !found; j++) {
+                const int* fj = &sb.fidx[sb.foff[j]];
+                const int nj_ = sb.fn[j];
+                if (nj_ < 3 || ni_ != nj_) continue;
+                const double ratio = area_i / face_area(sb, j);
+                if (ratio > 1.01 || ratio < 0.99) continue;
+                v3 nj = cross(vb[fj[1]] - vb[fj[0]], vb[fj[2]] - vb[fj[0]]);
+                nj = nj * (1.0 / norm(nj));
+                if (norm(cross(ni, nj)) > 1.e-10) continue;
+                const double area = face_area(sa, i, s.h[a]);   // pi.id_ < pj.id_ always holds here
+                Sim::Bond B;
+                B.id_i = s.id[a]; B.id_j = s.id[b]; B.i = a; B.j = b; B.ghost = ghostc ? 1 : 0; B.mode = P.mode;
+                if (P.mode == 0) B.c1 = 2 * area * P.crit1;
+                else if (P.mode == 1) { B.c1 = 2 * area * P.crit1; B.c2 = 2 * area * P.crit2; }
+                else if (P.mode == 2) { B.c1 = 2 * area * P.crit1; B.c2 = area * P.crit2; }
+                found = true;
+                for (int iv = 0; iv < ni_; iv++)
+                  for (int jv = 0; jv < nj_; jv++) {
+                    const Contact c = detect_vv(va[fi[iv]], s.h[a] * sa.radius, vb[fj[jv]], s.h[b] * sb.radius);
+                    if (c.dn <= dn_crit) { B.sub_i = fi[iv]; B.sub_j = fj[jv]; B.dn0 = c.dn; local.push_back(B); break; }
+                  }
+                if (local.size() <= 2) { local.clear(); found = false; }
+              }
+            }
+            for (auto& B : local) B.weight = 1. / static_cast<double>(local.size());
+            // check_stiked_face (interaction_manager.hpp:226-276): the glued vertices of i are coplanar
+            bool ok = true;
+            if (local.size() >= 3) {
+              const v3 p0 = va[local[0].sub_i], nrm = cross(va[local[1].sub_i] - p0, va[local[2].sub_i] - p0);
+              for (size_t k = 3; k < local.size(); k++)
+                if (std::fabs(dot(va[local[k].sub_i] - p0, nrm)) > 1.e-10) ok = false;
+            }
+            if (ok) s.bonds.insert(s.bonds.end(), local.begin(), local.end());
+          });
+        }
+      }
+  resolve_bonds(s);
+}
+// update_interfaces.cpp:44-84: maximal runs of bonds between the same two particles (PartnerGhost records skipped)
+static void update_interfaces(Sim& s) {
+  s.interfaces.clear();
+  size_t loc = 0;
+  const size_t n = s.bonds.size();
+  while (loc < n) {
+    if (s.bonds[loc].ghost == 2) { loc++; continue; }
+    size_t m = 1;
+    while (loc + m < n && s.bonds[loc + m].id_i == s.bonds[loc].id_i && s.bonds[loc + m].id_j == s.bonds[loc].id_j) m++;
+    s.interfaces.push_back({loc, m});
+    loc += m;
+  }
+  s.interface_broken.assign(s.interfaces.size(), 0);
+}
+// inner_bond.hpp:106-185 (polyhedron::inner_bond_law) over wave 13, serial canonical order
+static void inner_bond_force(Sim& s, double dt) {
+  for (auto& B : s.bonds) {
+    if (B.i == 0xffffffffu || B.j == 0xffffffffu || !B.unbroken) { B.dn = 0; B.cp = {0, 0, 0}; B.fn = -B.friction; continue; }
+    const uint32_t i = B.i, j = B.j;
+    const Shape &si = s.shapes[s.type[i]], &sj = s.shapes[s.type[j]];
+    const Contact c = detect_vv(s.pv(i)[B.sub_i], s.h[i] * si.radius, s.pv(j)[B.sub_j], s.h[j] * sj.radius);
+    const BondParams& P = s.ibp[(size_t)s.group[i] * s.ibp_groups + s.group[j]];
+    const double meff = (s.mass[i] * s.mass[j]) / (s.mass[i] + s.mass[j]);
+    v3 fi{0, 0, 0};
+    inner_bond_force_core(c.dn, c.n, B.dn0, B.weight, dt, P, meff, B.en, B.tds, B.et, B.friction, c.cp, s.r[i], s.v[i], fi, s.w[i], s.r[j],
+                          s.v[j], s.w[j]);
+    B.fn = fi - B.friction;
+    B.dn = c.dn; B.cp = c.cp;
+    s.mom[i] = s.mom[i] + moments(c.cp, s.r[i], fi, v3{0, 0, 0});
+    s.f[i] = s.f[i] + fi;
+    s.mom[j] = s.mom[j] + moments(c.cp, s.r[j], -fi, v3{0, 0, 0});
+    s.f[j] = s.f[j] + -fi;
+  }
+}
+static uint64_t apply_interface_fracture_criterion(Sim& s) {
+  uint64_t broken = 0;
+  for (size_t k = 0; k < s.interfaces.size(); k++) {
+    const auto [loc, size] = s.interfaces[k];
+    std::vector<double> en(size), et(size), dn(size);
+    std::vector<v3> fn(size);
+    for (size_t j = 0; j < size; j++) { const auto& B = s.bonds[loc + j]; en[j] = B.en; et[j] = B.et; dn[j] = B.dn; fn[j] = B.fn; }
+    const auto& B0 = s.bonds[loc];
+    if (interface_breaks(B0.mode, B0.c1, B0.c2, en.data(), et.data(), dn.data(), fn.data(), size)) {
+      s.interface_broken[k] = 1;
+      broken++;
+      for (size_t j = 0; j < size; j++) s.bonds[loc + j].unbroken = 0;
+    }
+  }
+  return broken;
+}
+
 // ---- driver operators of the time loop (src/driver/*.cpp), SURVEY 8(f) rank 3 ----
 static bool drivers_move(const Sim& s) {
   for (const Driver& d : s.drivers) if (d.motion != M_STATIONARY || (d.kind == DRV_RSHAPE && rshape_need_moment(d))) return true;
@@ -1123,6 +1278,84 @@ int orc_driver_motion_op(int op, double time, double dt, double system_mass, edb
   orc_get_drivers((orc_sim*)&s, 1, d, m);
   if (D.kind == DRV_SURFACE) S3(m->mom, cproj);
   return 0;
+}
+int orc_set_inner_bond_params(orc_sim* h, int32_t n_groups, const edb_inner_bond_params* p) {
+  Sim& s = *(Sim*)h;
+  s.ibp_groups = n_groups;
+  s.ibp.clear();
+  for (int i = 0; i < n_groups * n_groups; i++) s.ibp.push_back(BondParams{p[i].kn, p[i].kt, p[i].damp_rate, p[i].mode, p[i].crit1, p[i].crit2});
+  return 0;
+}
+int orc_set_particle_clusters(orc_sim* h, uint64_t n, const uint64_t* ids, const double* cluster) {   // field::cluster (oracle-only: stick_polyhedra)
+  Sim& s = *(Sim*)h;
+  std::unordered_map<uint64_t, double> m;
+  for (uint64_t k = 0; k < n; k++) m[ids[k]] = cluster[k];
+  s.cluster.assign(s.ntot, -1.0);
+  for (size_t p = 0; p < s.ntot; p++) { auto it = m.find(s.id[p]); if (it != m.end()) s.cluster[p] = it->second; }
+  return 0;
+}
+int orc_stick_polyhedra(orc_sim* h, double threshold) {
+  Sim& s = *(Sim*)h;
+  if (s.cluster.size() != s.ntot) { s.err = "stick_polyhedra: clusters not set (or stale after a rebuild)"; return EDB_ERR_STATE; }
+  compute_vertices(s);
+  stick_polyhedra(s, threshold);
+  return 0;
+}
+int orc_import_inner_bonds(orc_sim* h, const edb_inner_bond* in, uint64_t n) {
+  Sim& s = *(Sim*)h;
+  s.bonds.clear();
+  for (uint64_t k = 0; k < n; k++) {
+    Sim::Bond B;
+    B.id_i = in[k].id_i; B.id_j = in[k].id_j; B.sub_i = in[k].sub_i; B.sub_j = in[k].sub_j;
+    B.friction = V3(in[k].friction); B.tds = V3(in[k].tds); B.en = in[k].en; B.et = in[k].et; B.dn0 = in[k].dn0; B.weight = in[k].weight;
+    B.c1 = in[k].criteria_1; B.c2 = in[k].criteria_2; B.mode = in[k].mode; B.unbroken = in[k].unbroken; B.ghost = in[k].ghost;
+    s.bonds.push_back(B);
+  }
+  resolve_bonds(s);
+  return 0;
+}
+int orc_export_inner_bonds(orc_sim* h, edb_inner_bond* out, uint64_t cap, uint64_t* n) {
+  Sim& s = *(Sim*)h;
+  *n = s.bonds.size();
+  if (!out) return 0;
+  if (cap < s.bonds.size()) return EDB_ERR_CAPACITY;
+  for (size_t k = 0; k < s.bonds.size(); k++) {
+    const auto& B = s.bonds[k];
+    edb_inner_bond& o = out[k];
+    o = edb_inner_bond{};
+    o.id_i = B.id_i; o.id_j = B.id_j; o.sub_i = B.sub_i; o.sub_j = B.sub_j; S3(o.friction, B.friction); o.en = B.en; S3(o.tds, B.tds);
+    o.et = B.et; o.dn0 = B.dn0; o.weight = B.weight; o.criteria_1 = B.c1; o.criteria_2 = B.c2; o.mode = B.mode; o.unbroken = B.unbroken;
+    o.ghost = B.ghost;
+  }
+  return 0;
+}
+int orc_update_interfaces(orc_sim* h, uint64_t* n) { Sim& s = *(Sim*)h; resolve_bonds(s); update_interfaces(s); if (n) *n = s.interfaces.size(); return 0; }
+int orc_inner_bond_polyhedron(orc_sim* h, double dt) { Sim& s = *(Sim*)h; inner_bond_force(s, dt); return 0; }
+int orc_apply_interface_fracture_criterion(orc_sim* h, uint64_t* n_broken) { *n_broken = apply_interface_fracture_criterion(*(Sim*)h); return 0; }
+int orc_get_inner_bond_state(orc_sim* h, double* dn, double* cp, double* fn, double* ft) {
+  Sim& s = *(Sim*)h;
+  for (size_t k = 0; k < s.bonds.size(); k++) {
+    const auto& B = s.bonds[k];
+    if (dn) dn[k] = B.dn;
+    if (cp) S3(cp + 3 * k, B.cp);
+    if (fn) S3(fn + 3 * k, B.fn);
+    if (ft) S3(ft + 3 * k, B.friction);
+  }
+  return 0;
+}
+// the law alone through flat arrays (mirrored by oracle/ref_math.cpp:ref_inner_bond_force_core)
+void orc_inner_bond_force_core(double dn, const double* n, double dn0, double weight, double dt, const edb_inner_bond_params* p, double meff,
+                               double* en_et /* 2 */, double* tds, double* ft, const double* cp, const double* pi, const double* vi, double* fi,
+                               const double* wi, const double* pj, const double* vj, const double* wj) {
+  BondParams P{p->kn, p->kt, p->damp_rate, p->mode, p->crit1, p->crit2};
+  v3 T = V3(tds), F = V3(ft), f{0, 0, 0};
+  inner_bond_force_core(dn, V3(n), dn0, weight, dt, P, meff, en_et[0], T, en_et[1], F, V3(cp), V3(pi), V3(vi), f, V3(wi), V3(pj), V3(vj), V3(wj));
+  S3(tds, T); S3(ft, F); S3(fi, f);
+}
+int orc_interface_breaks(int mode, double c1, double c2, const double* en, const double* et, const double* dn, const double* fn3, uint64_t size) {
+  std::vector<v3> fn(size);
+  for (uint64_t k = 0; k < size; k++) fn[k] = V3(fn3 + 3 * k);
+  return interface_breaks(mode, c1, c2, en, et, dn, fn.data(), size) ? 1 : 0;
 }
 int orc_push_f_v_r_driver(orc_sim* h, double t, double dt) { push_f_v_r_driver(*(Sim*)h, t, dt); return 0; }
 int orc_push_f_v_driver(orc_sim* h, double dt) { push_f_v_driver(*(Sim*)h, dt); return 0; }

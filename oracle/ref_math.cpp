@@ -22,6 +22,8 @@
 #include <exaDEM/surface.hpp>
 #include <exaDEM/ball.hpp>
 #include <exaDEM/rshape.hpp>
+#include <exaDEM/forcefield/inner_bond_parameters.hpp>
+#include <exaDEM/forcefield/inner_bond_force.hpp>
 #include "../include/exadem_b200.h"
 #include <cstring>
 
@@ -226,6 +228,17 @@ int ref_driver_motion_op(int op, double time, double dt, double system_mass, edb
     S(m->acc, f.acc_); S(m->forces, f.forces_); S(m->mom, f.mom_); S(m->applied_mom, f.applied_mom_); S(m->mom_axis, f.mom_axis_);
   }
   return 0;
+}
+
+// inner bond law (src/forcefield/include/exaDEM/forcefield/inner_bond_force.hpp:26-70), the reference's own force_law_core
+void ref_inner_bond_force_core(double dn, const double* n, double dn0, double weight, double dt, const edb_inner_bond_params* p, double meff,
+                               double* en_et, double* tds, double* ft, const double* cp, const double* pi, const double* vi, double* fi,
+                               const double* wi, const double* pj, const double* vj, const double* wj) {
+  exaDEM::InnerBondParams P;
+  P.kn_ = p->kn; P.kt_ = p->kt; P.damp_rate_ = p->damp_rate; P.mode_ = (exaDEM::RuptureMode)p->mode; P.crit1_ = p->crit1; P.crit2_ = p->crit2;
+  Vec3d T = V(tds), F = V(ft), f{0, 0, 0};
+  exaDEM::force_law_core(dn, V(n), dn0, weight, dt, P, meff, en_et[0], T, en_et[1], F, V(cp), V(pi), V(vi), f, V(wi), V(pj), V(vj), V(wj));
+  S(tds, T); S(ft, F); S(fi, f);
 }
 
 }  // extern "C"

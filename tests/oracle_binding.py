@@ -43,6 +43,16 @@ class OracleEngine(capi.Engine):
         """Multi-rank emulation: treat cells of another brick like the ghost cells they would be on the owning rank."""
         self._call("set_virtual_bricks", (C.c_int32 * 3)(*pgrid))
 
+    def set_particle_clusters(self, ids, cluster):
+        """field::cluster per particle id (oracle-only input of stick_polyhedra)."""
+        import numpy as np
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        cl = np.ascontiguousarray(cluster, dtype=np.float64)
+        self._call("set_particle_clusters", C.c_uint64(len(ids)), ids.ctypes.data_as(C.c_void_p), cl.ctypes.data_as(C.c_void_p))
+
+    def stick_polyhedra(self, threshold):
+        self._call("stick_polyhedra", C.c_double(threshold))
+
     def sync(self):
         pass
 

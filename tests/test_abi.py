@@ -41,6 +41,7 @@ def test_struct_layouts():
     # edb_driver / edb_driver_motion (static_assert'ed to the same numbers in csrc/edb_lib.cu)
     assert C.sizeof(capi.Driver) == 184 and C.sizeof(capi.DriverMotion) == 400
     assert capi.DriverMotion.tab_time.offset == 80 and capi.DriverMotion.mass.offset == 224
+    assert capi.INNER_BOND_DTYPE.itemsize == 128 and C.sizeof(capi.InnerBondParams) == 48   # edb_inner_bond, edb_inner_bond_params
 
 
 def test_no_cpu_fallback(product_lib):

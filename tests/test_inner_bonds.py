@@ -1,0 +1,205 @@
+"""Inner bonds (fragmentation, wave 13), SURVEY 8(f) rank 4 — the per-step operators: inner_bond_polyhedron (bond law + deterministic
+force accumulation), update_interfaces, apply_interface_fracture_criterion.
+
+CPU: the oracle's law equals the reference's own force_law_core bit for bit (oracle/_ref + golden vectors); the product's law compiled
+for the host equals the oracle; the glued-block scenario is meaningful.  GPU: the block through the C ABI against the oracle."""
+import ctypes as C
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from exadem_b200 import capi, workloads
+from oracle_binding import OracleEngine, OracleLibrary, ref_math
+from parity import compare_particles, field_close
+
+GOLD = Path(__file__).parent / "golden" / "inner_bond_golden.npz"
+RTOL = 1e-10
+_p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def law_cases(seed=11, n=400):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(n):
+        nrm = rng.normal(size=3)
+        nrm /= np.linalg.norm(nrm)
+        cases.append(dict(dn=float(rng.normal() * 1e-3), n=nrm, dn0=float(rng.normal() * 1e-4), weight=float(rng.choice([0.25, 1 / 3, 0.5, 1.0])),
+                          dt=float(rng.choice([1e-5, 1e-4])), prm=(float(rng.uniform(1e3, 1e6)), float(rng.uniform(1e3, 1e6)), float(rng.uniform(0, 1)),
+                                                                    int(rng.integers(0, 3)), float(rng.uniform(0.1, 10)), float(rng.uniform(0.1, 10))),
+                          meff=float(rng.uniform(0.01, 2.0)), tds=rng.normal(size=3) * 1e-4, vec=rng.normal(size=(7, 3))))
+    return cases
+
+
+def run_law(fn, cases):
+    out = []
+    for c in cases:
+        prm = capi.InnerBondParams(kn=c["prm"][0], kt=c["prm"][1], damp_rate=c["prm"][2], mode=c["prm"][3], crit1=c["prm"][4], crit2=c["prm"][5])
+        en_et, tds, ft, fi = np.zeros(2), c["tds"].copy(), np.zeros(3), np.zeros(3)
+        cp, pi, vi, wi, pj, vj, wj = [np.ascontiguousarray(v) for v in c["vec"]]
+        nn = np.ascontiguousarray(c["n"])
+        fn.restype = None
+        fn(C.c_double(c["dn"]), _p(nn), C.c_double(c["dn0"]), C.c_double(c["weight"]), C.c_double(c["dt"]), C.byref(prm), C.c_double(c["meff"]),
+           _p(en_et), _p(tds), _p(ft), _p(cp), _p(pi), _p(vi), _p(fi), _p(wi), _p(pj), _p(vj), _p(wj))
+        out.append(np.concatenate([en_et, tds, ft, fi]))
+    return np.array(out)
+
+
+def test_oracle_bond_law_vs_golden():
+    cases = law_cases()
+    g = np.load(GOLD)["out"]
+    assert np.array_equal(run_law(OracleLibrary().dll.orc_inner_bond_force_core, cases), g)
+
+
+def test_oracle_bond_law_vs_reference():
+    ref = ref_math()
+    if ref is None or not hasattr(ref, "ref_inner_bond_force_core"):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    cases = law_cases(seed=12, n=800)
+    a, b = run_law(OracleLibrary().dll.orc_inner_bond_force_core, cases), run_law(ref.ref_inner_bond_force_core, cases)
+    assert np.array_equal(a, b) and np.abs(a).sum() > 0
+
+
+def test_product_bond_law_compiled_for_host_vs_oracle(tmp_path):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        pytest.skip("nvcc not available")
+    so = tmp_path / "libhost_check_bond.so"
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-fmad=false", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared",
+                    str(Path(__file__).parent / "host_check_bond.cu"), "-o", str(so)], check=True, capture_output=True)
+    chk, orc = C.CDLL(str(so)), OracleLibrary().dll
+    cases = law_cases(seed=13, n=600)
+    assert np.array_equal(run_law(orc.orc_inner_bond_force_core, cases), run_law(chk.chk_inner_bond_force_core, cases))
+    rng = np.random.default_rng(5)
+    hits = 0
+    for _ in range(400):
+        size = int(rng.integers(3, 6))
+        en, et, dn, fn = rng.uniform(0, 1, size), rng.uniform(0, 1, size), rng.normal(size=size), np.ascontiguousarray(rng.normal(size=(size, 3)))
+        mode, c1, c2 = int(rng.integers(0, 4)), float(rng.uniform(0, size)), float(rng.uniform(0, 1.5))
+        args = (C.c_int(mode), C.c_double(c1), C.c_double(c2), _p(en), _p(et), _p(dn), _p(fn), C.c_uint64(size))
+        a, b = orc.orc_interface_breaks(*args), chk.chk_interface_breaks(*args)
+        assert a == b
+        hits += a
+    assert 50 < hits < 350
+
+
+# ---- the glued block --------------------------------------------------------------------------------------------------------------
+def glued_block():
+    """4 x 4 x 3 cubes (side 0.6 + Minkowski radius 0.1) on an exact lattice of pitch 0.8 so that neighbouring faces touch: one cluster,
+    glued by stick_polyhedra (4 bonds of weight 1/4 per shared face).  The top layer is pulled up and sheared so that interfaces break."""
+    wl = workloads.polyhedra_box((4, 4, 3), shapes=("cube",), pitch=0.8, jitter=0.0, periodic=(0, 0, 0), cell_size=2.0)
+    pa = wl.particles
+    pa.qw[:], pa.qx[:], pa.qy[:], pa.qz[:] = 1.0, 0.0, 0.0, 0.0
+    pa.vrotx[:], pa.vroty[:], pa.vrotz[:] = 0.0, 0.0, 0.0
+    pa.vx[:], pa.vy[:], pa.vz[:] = 0.0, 0.0, 0.0
+    top = pa.rz > 1.7
+    pa.vz[top] = 6.0
+    pa.vx[top] = 3.0
+    wl.lo, wl.hi = (-2.0, -2.0, -2.0), (6.0, 6.0, 6.0)
+    wl.periodic = (0, 0, 0)
+    wl.name = "glued_block"
+    ibp = [dict(kn=2e5, kt=1e5, damp_rate=0.1, mode=0, crit1=0.004, crit2=0.0)]
+    return wl, ibp
+
+
+def setup_block(engines, wl, ibp):
+    """bonds are created by the oracle's stick_polyhedra (a one-off preprocessing that stays on the host side of the binding) and imported
+    by every engine"""
+    orc = engines[-1]
+    for e in engines:
+        e.set_inner_bond_params(1, ibp)
+        e.update_particle_neighbors(wl.rcut_inc, True)
+    orc.set_particle_clusters(wl.particles.id, np.zeros(wl.particles.n))
+    orc.stick_polyhedra(2e-5)
+    bonds = orc.export_inner_bonds()
+    for e in engines:
+        e.import_inner_bonds(bonds)
+    n_itf = [e.update_interfaces() for e in engines]
+    assert len(set(n_itf)) == 1
+    return bonds, n_itf[0]
+
+
+def step_block(e, wl):
+    e.combined_compute_prolog(wl.dt)
+    e.ghost_update_rq()
+    e.compute_vertices()
+    e.reset_force_moment()
+    e.gravity_force(wl.gravity)
+    e.inner_bond_polyhedron(wl.dt)
+    e.contact_polyhedron(wl.dt)
+    e.force_to_accel()
+    e.combined_compute_epilog(wl.dt)
+    return e.apply_interface_fracture_criterion()
+
+
+def bond_key(rec):
+    return np.lexsort((rec["sub_j"], rec["sub_i"], rec["id_j"], rec["id_i"]))
+
+
+def compare_bonds(a, b, rtol=RTOL):
+    ra, rb = a.export_inner_bonds(), b.export_inner_bonds()
+    ra, rb = ra[bond_key(ra)], rb[bond_key(rb)]
+    for k in ("id_i", "id_j", "sub_i", "sub_j", "unbroken", "mode"):
+        assert np.array_equal(ra[k], rb[k]), k
+    for k in ("friction", "tds", "en", "et", "dn0", "weight", "criteria_1"):
+        field_close(ra[k], rb[k], rtol, f"bond {k}")
+    return ra
+
+
+def run_block(engines, nsteps=40):
+    wl, ibp = glued_block()
+    engines = [wl.setup(e(wl)) for e in engines]
+    bonds, n_itf = setup_block(engines, wl, ibp)
+    # 4 x 4 x 3 cubes: 3*4*3 + 4*3*3 + 4*4*2 = 104 shared faces, 4 bonds each
+    assert n_itf == 104 and len(bonds) == 416 and np.allclose(bonds["weight"], 0.25) and bonds["unbroken"].all()
+    broken_total = [0] * len(engines)
+    for it in range(nsteps):
+        nb = [step_block(e, wl) for e in engines]
+        assert len(set(nb)) == 1, (it, nb)
+        for k, v in enumerate(nb):
+            broken_total[k] += v
+    return wl, engines, broken_total
+
+
+def test_glued_block_on_the_oracle():
+    lib = OracleLibrary()
+    wl, engines, broken = run_block([lambda wl: OracleEngine(lib, wl.config())] * 2)
+    rec = compare_bonds(*engines)
+    assert broken[0] > 0 and not rec["unbroken"].all() and rec["unbroken"].any()   # the top layer tears off, the rest stays glued
+    assert rec["en"].max() > 0 and rec["et"].max() > 0
+    dn, cp, fn, ft = engines[0].get_inner_bond_state(len(rec))
+    assert np.abs(fn).sum() > 0
+
+
+@pytest.mark.gpu
+def test_gpu_glued_block(product_lib, oracle_lib):
+    from exadem_b200 import Engine
+    wl, (gpu, cpu), broken = run_block([lambda wl: Engine(product_lib, wl.config()), lambda wl: OracleEngine(oracle_lib, wl.config())])
+    assert broken[0] == broken[1] and broken[0] > 0
+    rec = compare_bonds(gpu, cpu)
+    compare_particles(gpu.download_particles(), cpu.download_particles(), rtol=RTOL)
+    n = len(rec)
+    sg, sc = gpu.get_inner_bond_state(n), cpu.get_inner_bond_state(n)
+    og, oc = bond_key(gpu.export_inner_bonds()), bond_key(cpu.export_inner_bonds())
+    for a, b, name in zip(sg, sc, ("dn", "cp", "fn", "ft")):
+        field_close(a[og], b[oc], RTOL, f"bond state {name}")
+
+
+@pytest.mark.gpu
+def test_gpu_bonds_follow_their_particles_across_a_rebuild(product_lib, oracle_lib):
+    """persistent interactions: after a neighbour rebuild re-sorts the particles, edb_update_interfaces re-resolves the bonds by id"""
+    from exadem_b200 import Engine
+    wl, ibp = glued_block()
+    engines = [wl.setup(Engine(product_lib, wl.config())), wl.setup(OracleEngine(oracle_lib, wl.config()))]
+    setup_block(engines, wl, ibp)
+    for it in range(12):
+        for e in engines:
+            step_block(e, wl)
+        if it == 5:
+            for e in engines:
+                e.update_particle_neighbors(wl.rcut_inc, True)
+                assert e.update_interfaces() > 0
+    compare_bonds(*engines)
+    compare_particles(engines[0].download_particles(), engines[1].download_particles(), rtol=RTOL)
