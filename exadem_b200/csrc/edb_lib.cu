@@ -125,6 +125,9 @@ struct edb_context {
   DevBuf<uint8_t> b_mode, b_unbroken, b_itf_broken;
   DevBuf<uint32_t> b_plist, b_inc_off, b_inc;
   uint32_t n_bond_particles = 0, n_interfaces = 0;
+  DevBuf<uint32_t> b_ign_off;
+  DevBuf<unsigned long long> b_ign_ids;
+  bool have_ignore = false;
   DevBuf<BondParams> d_ibp;
   int ibp_groups = 0;
   double physical_time = 0, system_mass = 0;
@@ -377,7 +380,7 @@ extern "C" int edb_destroy(edb_context* c) {
   c->d_mcell_cnt.release(); c->drv_sums.release();
   c->b_ij.release(); c->b_sub.release(); c->b_itf.release(); c->b_par.release(); c->b_fr.release(); c->b_tds.release(); c->b_fd.release();
   c->b_cp.release(); c->b_mode.release(); c->b_unbroken.release(); c->b_itf_broken.release(); c->b_plist.release(); c->b_inc_off.release();
-  c->b_inc.release(); c->d_ibp.release();
+  c->b_inc.release(); c->d_ibp.release(); c->b_ign_off.release(); c->b_ign_ids.release();
   c->mig_dest.release(); c->mig_midx.release(); c->mig_cnt.release(); c->mig_off.release(); c->imm_cnt.release(); c->imm_off.release();
   c->mig_sp.release(); c->mig_rp.release(); c->mig_sh.release(); c->mig_rh.release(); c->imm_tab.release();
   c->tw_cnt.release(); c->tw_flag.release(); c->tw_pos.release(); c->tw_own.release(); c->tw_par.release(); c->tw_tpos.release();
@@ -1088,6 +1091,8 @@ static void driver_vertices(edb_context* c, bool all);
 static void backup_drivers(edb_context* c);
 static void driver_displ_launch(edb_context* c, double thr, unsigned long long* d_out, const unsigned long long* gate);
 static void driver_force_sums(edb_context* c);
+static void bonds_download(edb_context* c);
+static void bonds_upload(edb_context* c);
 static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   ScopedTimer tm(c, B_REBUILD);
   const GridDev& G = c->G;
@@ -1237,7 +1242,15 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
       C.c[t] = c->wave[t].off.p;
     }
   }
-  NbhArgs A{view(c->pa), c->cidx.p, c->cbeg.p, c->cend.p, G, c->drv.p, (int)c->h_drv.size(), rcut_inc, symetric, n, c->vert.p, c->S, c->M, 0};
+  NbhArgs A{view(c->pa), c->cidx.p, c->cbeg.p, c->cend.p, G, c->drv.p, (int)c->h_drv.size(), rcut_inc, symetric, n, c->vert.p, c->S, c->M, 0,
+            nullptr, nullptr};
+  if (!c->h_bonds.empty()) {
+    // persistent interactions (nbh_polyhedron.cpp:146-149): the bonds follow their particles into the new order by id, and the pairs
+    // they glue are ignored by the contact enumeration while they hold
+    bonds_download(c);
+    bonds_upload(c);
+    if (c->have_ignore) { A.ign_off = c->b_ign_off.p; A.ign_ids = c->b_ign_ids.p; }
+  }
   WTab W{};
   // polyhedra: the particle-particle waves go through the cell-block kernel (TMA-staged stencil, warp-shared pair tests) when the
   // largest stencil fits the shared memory of an SM; drivers / meshes stay on the per-particle kernel
@@ -2114,7 +2127,7 @@ static void bonds_download(edb_context* c) {
 static void bonds_upload(edb_context* c) {
   const size_t n = c->h_bonds.size();
   c->n_bond_particles = 0; c->n_interfaces = 0;
-  c->bonds_on_device = false;
+  c->bonds_on_device = false; c->have_ignore = false;
   if (n == 0) return;
   const uint32_t np = c->nreal;
   std::vector<uint64_t> ids(np);
@@ -2157,6 +2170,27 @@ static void bonds_upload(edb_context* c) {
   CK(cudaMemcpy(c->b_unbroken.p, ub.data(), n, cudaMemcpyHostToDevice));
   CK(cudaMemset(c->b_fd.p, 0, n * sizeof(double4)));
   CK(cudaMemset(c->b_cp.p, 0, n * sizeof(double4)));
+  // ignore lists of the neighbour build (InteractionManager::update_ignore_interaction): unique partner ids of the unbroken bonds per owner
+  {
+    std::vector<uint32_t> ioff((size_t)np + 1, 0);
+    std::vector<unsigned long long> iids;
+    size_t k = 0;
+    for (uint32_t p = 0; p < np; p++) {
+      ioff[p] = (uint32_t)iids.size();
+      const size_t first = iids.size();
+      for (; k < n && ij[k].x == p; k++) {
+        if (!c->h_bonds[k].unbroken || ij[k].y == 0xffffffffu) continue;
+        bool dup = false;
+        for (size_t q = first; q < iids.size(); q++) dup = dup || iids[q] == c->h_bonds[k].id_j;
+        if (!dup) iids.push_back(c->h_bonds[k].id_j);
+      }
+    }
+    ioff[np] = (uint32_t)iids.size();
+    c->b_ign_off.ensure(ioff.size() + 1); c->b_ign_ids.ensure(iids.size() + 1);
+    CK(cudaMemcpy(c->b_ign_off.p, ioff.data(), ioff.size() * 4, cudaMemcpyHostToDevice));
+    if (!iids.empty()) CK(cudaMemcpy(c->b_ign_ids.p, iids.data(), iids.size() * 8, cudaMemcpyHostToDevice));
+    c->have_ignore = !iids.empty();
+  }
   // incidence lists: for every particle that carries bonds, its bonds in bond order (side 0 = i, 1 = j)
   std::vector<std::pair<uint32_t, uint32_t>> inc;   // (particle, code)
   for (size_t k = 0; k < n; k++) {

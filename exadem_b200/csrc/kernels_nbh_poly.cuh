@@ -235,6 +235,7 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
         const double d2 = dot(d, d);
         const double rmax = ra.w + rb.w + rV;
         near = d2 > 0.0 && d2 < rmax * rmax && ida < s_id[L];   // ContactNeighborFilterFunc, then nbh_polyhedron.cpp:234-236
+        if (near && A.ign_off) near = !bond_ignored(A, a, s_id[L]);   // bonded pair: InteractionManager::skip_ignored_interactions
       }
       const unsigned nm = __ballot_sync(0xffffffffu, near);
       if (near) qu[nq + __popc(nm & ((1u << lane) - 1u))] = (uint16_t)L;

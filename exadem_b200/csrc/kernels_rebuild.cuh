@@ -242,7 +242,17 @@ struct NbhArgs {
   ShapesView S;
   MeshView M;
   int skip_pp;   // polyhedra: the particle-particle waves are enumerated by k_nbh_poly_cell (kernels_nbh_poly.cuh)
+  // InteractionManager::ignore_ (interaction_manager.hpp:114-160): per owner slot, the ids of the partners it holds an unbroken inner bond
+  // with — no regular contact is enumerated between the two while the bond holds.  CSR over the real slots; nullptr without bonds.
+  const uint32_t* ign_off;
+  const unsigned long long* ign_ids;
 };
+__device__ __forceinline__ bool bond_ignored(const NbhArgs& A, uint32_t owner, unsigned long long partner_id) {
+  if (!A.ign_off) return false;
+  for (uint32_t q = A.ign_off[owner]; q < A.ign_off[owner + 1]; q++)
+    if (A.ign_ids[q] == partner_id) return true;
+  return false;
+}
 
 __device__ __forceinline__ void cell_ijk(const GridDev& G, uint32_t lin, int& i, int& j, int& k) {
   i = lin % G.g[0];
@@ -464,6 +474,7 @@ __global__ void __launch_bounds__(64) k_nbh_poly(NbhArgs A, CntTab C, WTab W) {
   if (!A.skip_pp) for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
     const uint64_t idb = A.P.id[b];
     if (ida >= idb) return;  // nbh_polyhedron.cpp:234-236
+    if (bond_ignored(A, a, idb)) return;   // InteractionManager::skip_ignored_interactions
     const uint8_t ghost = gc ? 1 : 0;
     const double4 rb = A.P.pr[b];
     const double4 wgb = A.P.wg[b];

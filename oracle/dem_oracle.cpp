@@ -33,6 +33,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <tuple>
 #ifdef _OPENMP
@@ -98,6 +99,7 @@ struct Sim {
     v3 cp{0, 0, 0}, fn{0, 0, 0};
   };
   std::vector<Bond> bonds;
+  std::set<std::pair<uint64_t, uint64_t>> glued;   // (id_i, id_j) of the unbroken bonds at the last rebuild (InteractionManager::ignore_)
   std::vector<BondParams> ibp{BondParams()};
   int ibp_groups = 1;
   std::vector<double> cluster;                  // field::cluster per particle (index = particle index)
@@ -381,6 +383,9 @@ static void enumerate_polyhedron(Sim& s, uint32_t a, int ci, int cj, int ck, std
   }
   for_each_neighbor(s, ci, cj, ck, a, [&](uint32_t b, bool ghostc) {
     if (s.id[a] >= s.id[b]) return;  // nbh_polyhedron.cpp:234-236
+    // InteractionManager::skip_ignored_interactions (interaction_manager.hpp:114-160): no regular contact with a partner glued by an
+    // unbroken inner bond
+    if (!s.glued.empty() && s.glued.count({s.id[a], s.id[b]})) return;
     Inter n;
     n.ghost = ghostc ? 1 : 0;        // :237-239 OwnerGhost
     n.foreign = (ghostc && b < s.nreal) ? 1 : 0;
@@ -428,6 +433,18 @@ static void classify(Sim& s) {
   for (size_t k = 0; k < s.inter.size(); k++) s.wave[s.inter[k].type].push_back((uint32_t)k);
 }
 
+static void resolve_bonds(Sim& s) {   // persistent interactions follow their particles by id (update_persistent_interactions.cpp)
+  std::unordered_map<uint64_t, uint32_t> slot;
+  for (uint32_t p = 0; p < s.nreal; p++) slot[s.id[p]] = p;
+  for (auto& b : s.bonds) {
+    auto a = slot.find(b.id_i), c = slot.find(b.id_j);
+    b.i = a == slot.end() ? 0xffffffffu : a->second;
+    b.j = c == slot.end() ? 0xffffffffu : c->second;
+  }
+  std::stable_sort(s.bonds.begin(), s.bonds.end(), [](const Sim::Bond& x, const Sim::Bond& y) {
+    return std::tie(x.i, x.id_j, x.sub_i, x.sub_j) < std::tie(y.i, y.id_j, y.sub_i, y.sub_j);
+  });
+}
 static void rebuild(Sim& s, double rcut_inc, int symetric) {
   s.rcut_inc = rcut_inc;
   s.symetric = symetric;
@@ -441,6 +458,12 @@ static void rebuild(Sim& s, double rcut_inc, int symetric) {
   build_grid(s);
   ghost_refresh(s, true);
   compute_vertices(s);
+  if (!s.bonds.empty()) {   // persistent interactions follow their particles (nbh_polyhedron.cpp:146-149); glued pairs are ignored below
+    resolve_bonds(s);
+    s.glued.clear();
+    for (const auto& B : s.bonds)
+      if (B.unbroken) s.glued.insert({B.id_i, B.id_j});
+  }
   s.r_backup.assign(s.r.begin(), s.r.begin() + s.nreal);
   s.q_backup.assign(s.q.begin(), s.q.begin() + s.nreal);
   s.inter.clear();
@@ -976,18 +999,6 @@ int orc_simulation_state(orc_sim* h, int32_t symetric, edb_sim_state* out) {
 }
 
 // ---- inner bonds: SURVEY 8(f) rank 4 (checker side) ----
-static void resolve_bonds(Sim& s) {   // persistent interactions follow their particles by id (update_persistent_interactions.cpp)
-  std::unordered_map<uint64_t, uint32_t> slot;
-  for (uint32_t p = 0; p < s.nreal; p++) slot[s.id[p]] = p;
-  for (auto& b : s.bonds) {
-    auto a = slot.find(b.id_i), c = slot.find(b.id_j);
-    b.i = a == slot.end() ? 0xffffffffu : a->second;
-    b.j = c == slot.end() ? 0xffffffffu : c->second;
-  }
-  std::stable_sort(s.bonds.begin(), s.bonds.end(), [](const Sim::Bond& x, const Sim::Bond& y) {
-    return std::tie(x.i, x.id_j, x.sub_i, x.sub_j) < std::tie(y.i, y.id_j, y.sub_i, y.sub_j);
-  });
-}
 static double face_area(const Shape& sh, int f, double h = 1.0) {   // shape.hpp:673-697 (fan triangulation), :359-362 (h^2 scaling)
   double surface = 0;
   const int* idx = &sh.fidx[sh.foff[f]];

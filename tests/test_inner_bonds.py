@@ -116,9 +116,20 @@ def setup_block(engines, wl, ibp):
     bonds = orc.export_inner_bonds()
     for e in engines:
         e.import_inner_bonds(bonds)
+        e.update_particle_neighbors(wl.rcut_inc, True)   # init_update_particle_neighbors: stick_polyhedra, then nbh_polyhedron (config_fragmentation.msp)
     n_itf = [e.update_interfaces() for e in engines]
     assert len(set(n_itf)) == 1
     return bonds, n_itf[0]
+
+
+def glued_pairs_in_contact_list(e):
+    """regular contact records (waves 0-3) between two particles that hold an unbroken bond: must be none (InteractionManager::ignore_)"""
+    b = e.export_inner_bonds()
+    glued = {(int(r["id_i"]), int(r["id_j"])) for r in b[b["unbroken"] != 0]}
+    rec = e.export_interactions()
+    pp = rec[rec["type"] <= 3]
+    lo, hi = np.minimum(pp["id_i"], pp["id_j"]), np.maximum(pp["id_i"], pp["id_j"])
+    return sum((int(a), int(c)) in glued for a, c in zip(lo, hi)), len(pp)
 
 
 def step_block(e, wl):
@@ -171,6 +182,14 @@ def test_glued_block_on_the_oracle():
     assert rec["en"].max() > 0 and rec["et"].max() > 0
     dn, cp, fn, ft = engines[0].get_inner_bond_state(len(rec))
     assert np.abs(fn).sum() > 0
+    # while they hold, glued pairs have no regular contact records; after the break and a rebuild the torn-off faces do
+    e = engines[0]
+    n_glued, n_pp_before = glued_pairs_in_contact_list(e)
+    assert n_glued == 0 and n_pp_before > 0          # (edge / corner neighbours are not glued and keep their contact candidates)
+    e.update_particle_neighbors(wl.rcut_inc, True)
+    assert e.update_interfaces() == 104
+    n_glued, n_pp_after = glued_pairs_in_contact_list(e)
+    assert n_glued == 0 and n_pp_after > n_pp_before
 
 
 @pytest.mark.gpu
@@ -185,6 +204,16 @@ def test_gpu_glued_block(product_lib, oracle_lib):
     og, oc = bond_key(gpu.export_inner_bonds()), bond_key(cpu.export_inner_bonds())
     for a, b, name in zip(sg, sc, ("dn", "cp", "fn", "ft")):
         field_close(a[og], b[oc], RTOL, f"bond state {name}")
+    # the contact enumeration ignores glued pairs on both sides, and re-admits the torn-off faces after the next rebuild
+    from parity import compare_interaction_sets
+    assert glued_pairs_in_contact_list(gpu)[0] == 0
+    compare_interaction_sets(gpu.export_interactions(), cpu.export_interactions(), payload_rtol=RTOL)
+    for e in (gpu, cpu):
+        e.update_particle_neighbors(wl.rcut_inc, True)
+        e.update_interfaces()
+    assert glued_pairs_in_contact_list(gpu) == glued_pairs_in_contact_list(cpu)
+    compare_interaction_sets(gpu.export_interactions(), cpu.export_interactions(), payload_rtol=RTOL)
+    compare_bonds(gpu, cpu)
 
 
 @pytest.mark.gpu
