@@ -421,6 +421,9 @@ class Engine:
         self._call("apply_interface_fracture_criterion", C.byref(n))
         return n.value
 
+    def broken_interface_friction_updater(self):
+        self._call("broken_interface_friction_updater")
+
     def get_inner_bond_state(self, n):
         dn, cp, fn, ft = np.zeros(n), np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
         p = lambda a: a.ctypes.data_as(_D)

@@ -128,6 +128,8 @@ struct edb_context {
   DevBuf<uint32_t> b_ign_off;
   DevBuf<unsigned long long> b_ign_ids;
   bool have_ignore = false;
+  std::vector<BondConv> h_conv;                   // broken bonds waiting to become vertex-vertex history at this rebuild
+  DevBuf<BondConv> d_conv;
   DevBuf<BondParams> d_ibp;
   int ibp_groups = 0;
   double physical_time = 0, system_mass = 0;
@@ -380,7 +382,7 @@ extern "C" int edb_destroy(edb_context* c) {
   c->d_mcell_cnt.release(); c->drv_sums.release();
   c->b_ij.release(); c->b_sub.release(); c->b_itf.release(); c->b_par.release(); c->b_fr.release(); c->b_tds.release(); c->b_fd.release();
   c->b_cp.release(); c->b_mode.release(); c->b_unbroken.release(); c->b_itf_broken.release(); c->b_plist.release(); c->b_inc_off.release();
-  c->b_inc.release(); c->d_ibp.release(); c->b_ign_off.release(); c->b_ign_ids.release();
+  c->b_inc.release(); c->d_ibp.release(); c->b_ign_off.release(); c->b_ign_ids.release(); c->d_conv.release();
   c->mig_dest.release(); c->mig_midx.release(); c->mig_cnt.release(); c->mig_off.release(); c->imm_cnt.release(); c->imm_off.release();
   c->mig_sp.release(); c->mig_rp.release(); c->mig_sh.release(); c->mig_rh.release(); c->imm_tab.release();
   c->tw_cnt.release(); c->tw_flag.release(); c->tw_pos.release(); c->tw_own.release(); c->tw_par.release(); c->tw_tpos.release();
@@ -1093,6 +1095,7 @@ static void driver_displ_launch(edb_context* c, double thr, unsigned long long* 
 static void driver_force_sums(edb_context* c);
 static void bonds_download(edb_context* c);
 static void bonds_upload(edb_context* c);
+static void bonds_retire_broken(edb_context* c);
 static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   ScopedTimer tm(c, B_REBUILD);
   const GridDev& G = c->G;
@@ -1248,6 +1251,7 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
     // persistent interactions (nbh_polyhedron.cpp:146-149): the bonds follow their particles into the new order by id, and the pairs
     // they glue are ignored by the contact enumeration while they hold
     bonds_download(c);
+    bonds_retire_broken(c);   // broken bonds leave wave 13; those with friction are queued as vertex-vertex history (below, after k_history)
     bonds_upload(c);
     if (c->have_ignore) { A.ign_off = c->b_ign_off.p; A.ign_ids = c->b_ign_ids.p; }
   }
@@ -1339,6 +1343,15 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
         if (!had) ow.n = 0;
         LAUNCH(c, k_history, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), ow, c->new2old.p, had ? c->n_old_real : n_before, poly || t >= 7, t, H);
       }
+  }
+  if (!c->h_conv.empty()) {
+    if (c->wave[0].n) {
+      c->d_conv.ensure(c->h_conv.size());
+      CK(cudaMemcpyAsync(c->d_conv.p, c->h_conv.data(), c->h_conv.size() * sizeof(BondConv), cudaMemcpyHostToDevice, c->st));
+      LAUNCH(c, k_bond_convert, nblk(c->h_conv.size()), BLK, 0, c->d_conv.p, (uint32_t)c->h_conv.size(), view(c->wave[0]));
+      CK(cudaStreamSynchronize(c->st));   // (h_conv is pageable host memory)
+    }
+    c->h_conv.clear();
   }
   c->have_prev = true;
   c->n_old_real = n;
@@ -2229,6 +2242,37 @@ static void bonds_upload(edb_context* c) {
     CK(cudaMemset(c->b_itf_broken.p, 0, itf.size()));
   }
   c->bonds_on_device = true;
+}
+// At a rebuild: broken bonds are no longer persistent (inner_bond_interaction.hpp:125).  They leave the bond list; the ones whose
+// friction is non-zero (Interaction::active, interaction.hpp:129-136) are queued to become the history of the vertex-vertex record of
+// the same two vertices in the new wave 0 (unclassify_interactions.cpp:135-145, broke_interaction).  Needs the particles' new order.
+static void bonds_retire_broken(edb_context* c) {
+  c->h_conv.clear();
+  bool any = false;
+  for (auto& b : c->h_bonds) any = any || !b.unbroken;
+  if (!any) return;
+  const uint32_t np = c->nreal;
+  std::vector<uint64_t> ids(np);
+  CK(cudaStreamSynchronize(c->st));
+  if (np) CK(cudaMemcpy(ids.data(), c->pa.id.p, (size_t)np * 8, cudaMemcpyDeviceToHost));
+  std::unordered_map<uint64_t, uint32_t> slot;
+  slot.reserve((size_t)np * 2);
+  for (uint32_t p = 0; p < np; p++) slot[ids[p]] = p;
+  std::vector<edb_inner_bond> keep;
+  for (auto& b : c->h_bonds) {
+    if (b.unbroken) { keep.push_back(b); continue; }
+    if (b.friction[0] == 0.0 && b.friction[1] == 0.0 && b.friction[2] == 0.0) continue;
+    auto it = slot.find(b.id_i);
+    if (it == slot.end()) continue;
+    c->h_conv.push_back(BondConv{it->second, b.sub_i, b.sub_j, (long long)b.id_j, b.friction[0], b.friction[1], b.friction[2]});
+  }
+  c->h_bonds.swap(keep);
+}
+extern "C" int edb_broken_interface_friction_updater(edb_context* c) {
+  API_BEGIN(c)
+  if (c->n_interfaces == 0 || !c->bonds_on_device) return EDB_OK;
+  LAUNCH(c, k_bond_friction_updater, nblk(c->n_interfaces), BLK, 0, bond_view(c), c->b_itf.p, c->n_interfaces, c->b_itf_broken.p, view(c->pa), c->prm);
+  API_END(c)
 }
 extern "C" int edb_set_inner_bond_params(edb_context* c, int32_t ng, const edb_inner_bond_params* p) {
   API_BEGIN(c)

@@ -106,6 +106,55 @@ __global__ void __launch_bounds__(BLK) k_bond_gather(BondView B, PView P, const 
   P.mx[p] = m.x; P.my[p] = m.y; P.mz[p] = m.z;
 }
 
+// broken_interface_friction_updater.cpp:58-98: the bonds of a broken interface will become vertex-vertex contacts; their cumulated
+// friction is capped by the Coulomb threshold of the CONTACT parameters (mu * |fn|) and zeroed when the two vertices are apart
+__global__ void __launch_bounds__(BLK) k_bond_friction_updater(BondView B, const uint2* __restrict__ itf, uint32_t nitf, const uint8_t* __restrict__ broken,
+                                                               PView P, ParamsDev prm) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nitf || !broken[t]) return;
+  const uint2 I = itf[t];
+  const uint2 ij0 = B.ij[I.x];
+  if (ij0.x == 0xffffffffu || ij0.y == 0xffffffffu) return;
+  const double4 wi = ldg4(P.wg + ij0.x), wj = ldg4(P.wg + ij0.y);
+  const uint32_t ga = (uint32_t)(((unsigned long long)__double_as_longlong(wi.w)) >> 32), gb = (uint32_t)(((unsigned long long)__double_as_longlong(wj.w)) >> 32);
+  const double mu = (prm.tpp ? prm.tpp[ga * prm.n_groups + gb] : prm.pp).mu;
+  for (uint32_t j = I.x; j < I.x + I.y; j++) {
+    B.unbroken[j] = 0;
+    double4 fr = B.fr[j];
+    const double4 fd = B.fd[j];
+    const v3 ftv = xyz(fr), fn = xyz(fd) - ftv;
+    const double ft = norm(ftv);
+    const double thr = mu * norm(fn);
+    v3 nf = ftv;
+    if (ft > thr && ft > 0) nf = ftv * thr / ft;
+    if (fd.w > 0) nf = mk3(0, 0, 0);
+    B.fr[j] = mk4(nf, fr.w);
+  }
+}
+
+// unclassify_interactions.cpp:135-145 + broke_interaction (inner_bond_interaction.hpp:202-210): at the rebuild that follows a break, a
+// broken bond with a non-zero friction becomes the history of the vertex-vertex contact record between the same two vertices.
+struct BondConv {
+  uint32_t owner;              // slot of particle i in the new order
+  uint32_t sub_i, sub_j;
+  long long pid;               // id of particle j
+  double fx, fy, fz;
+};
+__global__ void k_bond_convert(const BondConv* __restrict__ cv, uint32_t n, WView w) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const BondConv b = cv[t];
+  for (uint32_t s = w.off[b.owner]; s < w.off[b.owner + 1]; s++) {
+    const double4 ft = w.ft[s];
+    if (__double_as_longlong(ft.w) != b.pid || (w.flg[s] & 1)) continue;
+    const uint2 sb = w.sub[s];
+    if (sb.x != b.sub_i || sb.y != b.sub_j) continue;
+    w.ft[s] = make_double4(b.fx, b.fy, b.fz, ft.w);
+    w.flg[s] = w.flg[s] | 8;   // FLG_HOT: the record carries history
+    return;
+  }
+}
+
 // one thread per interface (loc, size): sums in bond order, breaks every bond of the interface when the criterion is exceeded
 __global__ void __launch_bounds__(BLK) k_interface_criterion(BondView B, const uint2* __restrict__ itf, uint32_t nitf, uint8_t* __restrict__ broken,
                                                              unsigned long long* __restrict__ count) {

@@ -194,6 +194,14 @@ class ApplyInterfaceFractureCriterion : public OperatorNode {
   }
 };
 
+// src/interaction/broken_interface_friction_updater.cpp:30-100
+class BrokenInterfaceFrictionUpdater : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+ public:
+  std::string documentation() const final { return "This operator modify the cumulated friction [stored in interfactions] if an interface is broken: frition = max(friction, mu * fn)."; }
+  void execute() final { ck(*grid, edb_broken_interface_friction_updater(grid->ctx), "broken_interface_friction_updater"); }
+};
+
 // src/driver/backup_drivers.cu
 class BackupDrivers : public OperatorNode {
   ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
@@ -377,6 +385,7 @@ ONIKA_AUTORUN_INIT(exadem_b200_hot_path) {
   f->register_factory("inner_bond_polyhedron", make_simple_operator<ComputeInnerBondForce>);
   f->register_factory("update_interfaces", make_simple_operator<UpdateInterfaces>);
   f->register_factory("apply_interface_fracture_criterion", make_simple_operator<ApplyInterfaceFractureCriterion>);
+  f->register_factory("broken_interface_friction_updater", make_simple_operator<BrokenInterfaceFrictionUpdater>);
 }
 
 // -------------------------------------------------------------------------------------------------------------------

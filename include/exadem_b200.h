@@ -267,9 +267,9 @@ int edb_simulation_state(edb_context*, int32_t symetric, edb_sim_state* out);
 
 /* ---- inner bonds (fragmentation, wave 13), SURVEY 8(f) rank 4: the per-step operators.  Bond creation (stick_polyhedra, a one-off
  * preprocessing) and the fragmentation dump reader stay on the host side of the binding: the bonds enter through
- * edb_import_inner_bonds.  NOT built yet: suppression of the regular contacts between bonded particles
- * (InteractionManager::update_ignore_interaction) and the conversion of broken bonds into vertex-vertex contacts at the next
- * rebuild (unclassify_interactions.cpp:135-145); bonds across periodic / brick boundaries. ------------------------------------ */
+ * edb_import_inner_bonds.  While a bond holds, the polyhedron contact enumeration ignores the pair it glues
+ * (InteractionManager::update_ignore_interaction).  NOT built yet: bonds across periodic / brick boundaries (OwnerGhost bonds), the
+ * bonds inside edb_run_verlet (fragmentation decks run operator by operator). ------------------------------------------------- */
 int edb_set_inner_bond_params(edb_context*, int32_t n_groups, const edb_inner_bond_params* ibp /* n_groups^2 */);
 int edb_import_inner_bonds(edb_context*, const edb_inner_bond* in, uint64_t n);
 int edb_export_inner_bonds(edb_context*, edb_inner_bond* out, uint64_t cap, uint64_t* n); /* owner-sorted; out may be NULL to query n */
@@ -282,6 +282,11 @@ int edb_inner_bond_polyhedron(edb_context*, double dt);
 /* [apply_interface_fracture_criterion] apply_interface_fracture_criterion.hpp:40-73: breaks the interfaces whose energies exceed
  * their criterion (all their bonds become unbroken = 0); *n_broken = interfaces broken by this call */
 int edb_apply_interface_fracture_criterion(edb_context*, uint64_t* n_broken);
+/* [broken_interface_friction_updater] src/interaction/broken_interface_friction_updater.cpp:58-98: caps the cumulated friction of the
+ * bonds of the broken interfaces at mu * |fn| (CONTACT parameters) and zeroes it where the vertices are apart.  At the next
+ * edb_update_particle_neighbors the broken bonds leave wave 13 and those with a non-zero friction become the history of the
+ * vertex-vertex contact between the same two vertices (unclassify_interactions.cpp:135-145). */
+int edb_broken_interface_friction_updater(edb_context*);
 /* ContactState of wave 13 (dn, cp, fn, ft), one entry per bond in export order */
 int edb_get_inner_bond_state(edb_context*, double* dn, double* cp, double* fn, double* ft);
 

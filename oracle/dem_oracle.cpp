@@ -459,6 +459,14 @@ static void rebuild(Sim& s, double rcut_inc, int symetric) {
   ghost_refresh(s, true);
   compute_vertices(s);
   if (!s.bonds.empty()) {   // persistent interactions follow their particles (nbh_polyhedron.cpp:146-149); glued pairs are ignored below
+    // broken bonds are no longer persistent: unclassify turns them into vertex-vertex interactions (unclassify_interactions.cpp:135-145,
+    // broke_interaction inner_bond_interaction.hpp:202-210) whose friction, if any, is the history of that record in this rebuild
+    std::vector<Sim::Bond> keep;
+    for (const auto& B : s.bonds) {
+      if (B.unbroken) { keep.push_back(B); continue; }
+      if (!is_zero(B.friction)) hist.emplace(Key{B.id_i, B.id_j, 0, 0, B.sub_i, B.sub_j}, std::make_pair(B.friction, v3{0, 0, 0}));
+    }
+    s.bonds.swap(keep);
     resolve_bonds(s);
     s.glued.clear();
     for (const auto& B : s.bonds)
@@ -1106,6 +1114,24 @@ static void inner_bond_force(Sim& s, double dt) {
     s.f[j] = s.f[j] + -fi;
   }
 }
+// broken_interface_friction_updater.cpp:58-98
+static void broken_interface_friction_updater(Sim& s) {
+  for (size_t k = 0; k < s.interfaces.size(); k++) {
+    if (!s.interface_broken[k]) continue;
+    const auto [loc, size] = s.interfaces[k];
+    const auto& B0 = s.bonds[loc];
+    if (B0.i == 0xffffffffu || B0.j == 0xffffffffu) continue;
+    const double mu = s.cp_pp(s.group[B0.i], s.group[B0.j]).mu;
+    for (size_t j = 0; j < size; j++) {
+      auto& B = s.bonds[loc + j];
+      B.unbroken = 0;
+      const double ft = norm(B.friction);
+      const double thr = mu * norm(B.fn);
+      if (ft > thr && ft > 0) B.friction = B.friction * thr / ft;
+      if (B.dn > 0) B.friction = v3{0, 0, 0};
+    }
+  }
+}
 static uint64_t apply_interface_fracture_criterion(Sim& s) {
   uint64_t broken = 0;
   for (size_t k = 0; k < s.interfaces.size(); k++) {
@@ -1343,6 +1369,7 @@ int orc_export_inner_bonds(orc_sim* h, edb_inner_bond* out, uint64_t cap, uint64
 int orc_update_interfaces(orc_sim* h, uint64_t* n) { Sim& s = *(Sim*)h; resolve_bonds(s); update_interfaces(s); if (n) *n = s.interfaces.size(); return 0; }
 int orc_inner_bond_polyhedron(orc_sim* h, double dt) { Sim& s = *(Sim*)h; inner_bond_force(s, dt); return 0; }
 int orc_apply_interface_fracture_criterion(orc_sim* h, uint64_t* n_broken) { *n_broken = apply_interface_fracture_criterion(*(Sim*)h); return 0; }
+int orc_broken_interface_friction_updater(orc_sim* h) { broken_interface_friction_updater(*(Sim*)h); return 0; }
 int orc_get_inner_bond_state(orc_sim* h, double* dn, double* cp, double* fn, double* ft) {
   Sim& s = *(Sim*)h;
   for (size_t k = 0; k < s.bonds.size(); k++) {

@@ -88,19 +88,19 @@ def test_product_bond_law_compiled_for_host_vs_oracle(tmp_path):
 # ---- the glued block --------------------------------------------------------------------------------------------------------------
 def glued_block():
     """4 x 4 x 3 cubes (side 0.6 + Minkowski radius 0.1) on an exact lattice of pitch 0.8 so that neighbouring faces touch: one cluster,
-    glued by stick_polyhedra (4 bonds of weight 1/4 per shared face).  The top layer is pulled up and sheared so that interfaces break."""
+    glued by stick_polyhedra (4 bonds of weight 1/4 per shared face).  The top layer is sheared off so that its interfaces break."""
     wl = workloads.polyhedra_box((4, 4, 3), shapes=("cube",), pitch=0.8, jitter=0.0, periodic=(0, 0, 0), cell_size=2.0)
     pa = wl.particles
     pa.qw[:], pa.qx[:], pa.qy[:], pa.qz[:] = 1.0, 0.0, 0.0, 0.0
     pa.vrotx[:], pa.vroty[:], pa.vrotz[:] = 0.0, 0.0, 0.0
     pa.vx[:], pa.vy[:], pa.vz[:] = 0.0, 0.0, 0.0
     top = pa.rz > 1.7
-    pa.vz[top] = 6.0
-    pa.vx[top] = 3.0
+    pa.vz[top] = -0.3     # sheared off under slight compression: the bonds break with a non-zero (capped) friction to hand over
+    pa.vx[top] = 4.0
     wl.lo, wl.hi = (-2.0, -2.0, -2.0), (6.0, 6.0, 6.0)
     wl.periodic = (0, 0, 0)
     wl.name = "glued_block"
-    ibp = [dict(kn=2e5, kt=1e5, damp_rate=0.1, mode=0, crit1=0.004, crit2=0.0)]
+    ibp = [dict(kn=2e5, kt=1e5, damp_rate=0.1, mode=0, crit1=0.5, crit2=0.0)]
     return wl, ibp
 
 
@@ -132,17 +132,28 @@ def glued_pairs_in_contact_list(e):
     return sum((int(a), int(c)) in glued for a, c in zip(lo, hi)), len(pp)
 
 
-def step_block(e, wl):
+def step_block(e, wl, on_break=None):
+    """one iteration of a fragmentation deck (config_fragmentation.msp:11-41 inside check_and_update_particles): the fracture criterion
+    is evaluated on the state of the previous step; a broken interface caps its friction and forces the neighbour rebuild
+    (displ_or_break), where the broken bonds turn into vertex-vertex contacts"""
     e.combined_compute_prolog(wl.dt)
-    e.ghost_update_rq()
-    e.compute_vertices()
+    nb = e.apply_interface_fracture_criterion()
+    if nb:
+        e.broken_interface_friction_updater()
+        e.update_particle_neighbors(wl.rcut_inc, True)
+        e.update_interfaces()
+        if on_break is not None:
+            on_break(e)
+    else:
+        e.ghost_update_rq()
+        e.compute_vertices()
     e.reset_force_moment()
     e.gravity_force(wl.gravity)
     e.inner_bond_polyhedron(wl.dt)
     e.contact_polyhedron(wl.dt)
     e.force_to_accel()
     e.combined_compute_epilog(wl.dt)
-    return e.apply_interface_fracture_criterion()
+    return nb
 
 
 def bond_key(rec):
@@ -159,7 +170,7 @@ def compare_bonds(a, b, rtol=RTOL):
     return ra
 
 
-def run_block(engines, nsteps=40):
+def run_block(engines, nsteps=40, on_break=None):
     wl, ibp = glued_block()
     engines = [wl.setup(e(wl)) for e in engines]
     bonds, n_itf = setup_block(engines, wl, ibp)
@@ -167,35 +178,49 @@ def run_block(engines, nsteps=40):
     assert n_itf == 104 and len(bonds) == 416 and np.allclose(bonds["weight"], 0.25) and bonds["unbroken"].all()
     broken_total = [0] * len(engines)
     for it in range(nsteps):
-        nb = [step_block(e, wl) for e in engines]
+        nb = [step_block(e, wl, on_break) for e in engines]
         assert len(set(nb)) == 1, (it, nb)
         for k, v in enumerate(nb):
             broken_total[k] += v
-    return wl, engines, broken_total
+    return wl, engines, broken_total, bonds
 
 
 def test_glued_block_on_the_oracle():
     lib = OracleLibrary()
-    wl, engines, broken = run_block([lambda wl: OracleEngine(lib, wl.config())] * 2)
+    handed = []
+    wl, engines, broken, bonds0 = run_block([lambda wl: OracleEngine(lib, wl.config())] * 2, on_break=lambda e: handed.append(e.export_interactions()))
+    # right after the rebuild that follows the break, the vertex-vertex records of the torn faces carry the friction of their bonds
+    vv0 = handed[0][handed[0]["type"] == 0]
+    assert int((np.abs(vv0["friction"]).sum(axis=1) > 0).sum()) >= 4 * broken[0] > 0
     rec = compare_bonds(*engines)
-    assert broken[0] > 0 and not rec["unbroken"].all() and rec["unbroken"].any()   # the top layer tears off, the rest stays glued
+    # the top layer tears off (its 16 interfaces break and leave wave 13 at the rebuild that follows), the rest stays glued
+    assert 0 < broken[0] < 104 and len(rec) == 4 * (104 - broken[0]) and rec["unbroken"].all()
     assert rec["en"].max() > 0 and rec["et"].max() > 0
     dn, cp, fn, ft = engines[0].get_inner_bond_state(len(rec))
     assert np.abs(fn).sum() > 0
-    # while they hold, glued pairs have no regular contact records; after the break and a rebuild the torn-off faces do
+    # glued pairs have no regular contact records; the torn-off faces do, some of them with the friction inherited from their bonds
     e = engines[0]
-    n_glued, n_pp_before = glued_pairs_in_contact_list(e)
-    assert n_glued == 0 and n_pp_before > 0          # (edge / corner neighbours are not glued and keep their contact candidates)
-    e.update_particle_neighbors(wl.rcut_inc, True)
-    assert e.update_interfaces() == 104
-    n_glued, n_pp_after = glued_pairs_in_contact_list(e)
-    assert n_glued == 0 and n_pp_after > n_pp_before
+    n_glued, n_pp = glued_pairs_in_contact_list(e)
+    assert n_glued == 0 and n_pp > 0
+    inter = e.export_interactions()
+    vv = inter[inter["type"] == 0]
+    torn = {(int(a), int(b)) for a, b in zip(bonds0["id_i"], bonds0["id_j"])} - {(int(a), int(b)) for a, b in zip(rec["id_i"], rec["id_j"])}
+    from_bonds = [r for r in vv if (int(r["id_i"]), int(r["id_j"])) in torn]
+    assert len(torn) == broken[0] and len(from_bonds) > 0
 
 
 @pytest.mark.gpu
 def test_gpu_glued_block(product_lib, oracle_lib):
     from exadem_b200 import Engine
-    wl, (gpu, cpu), broken = run_block([lambda wl: Engine(product_lib, wl.config()), lambda wl: OracleEngine(oracle_lib, wl.config())])
+    handed = []
+    wl, (gpu, cpu), broken, _ = run_block([lambda wl: Engine(product_lib, wl.config()), lambda wl: OracleEngine(oracle_lib, wl.config())],
+                                          on_break=lambda e: handed.append(e.export_interactions()))
+    # the friction handed over from the broken bonds to the vertex-vertex records, right after the rebuild: GPU vs oracle
+    from parity import compare_interaction_sets as cmp_sets
+    assert len(handed) == 2
+    cmp_sets(handed[0], handed[1], payload_rtol=RTOL)
+    vv0 = handed[0][handed[0]["type"] == 0]
+    assert int((np.abs(vv0["friction"]).sum(axis=1) > 0).sum()) >= 4 * broken[0] > 0
     assert broken[0] == broken[1] and broken[0] > 0
     rec = compare_bonds(gpu, cpu)
     compare_particles(gpu.download_particles(), cpu.download_particles(), rtol=RTOL)
