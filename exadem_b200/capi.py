@@ -400,6 +400,12 @@ class Engine:
         rec = np.ascontiguousarray(rec, dtype=INNER_BOND_DTYPE)
         self._call("import_inner_bonds", rec.ctypes.data_as(C.c_void_p), C.c_uint64(len(rec)))
 
+    def stick_polyhedra_ids(self, threshold, ids, cluster):
+        """[stick_polyhedra] on the device; cluster given per particle id."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        cl = np.ascontiguousarray(cluster, dtype=np.float64)
+        self._call("stick_polyhedra", C.c_double(threshold), C.c_uint64(len(ids)), ids.ctypes.data_as(C.c_void_p), cl.ctypes.data_as(C.c_void_p))
+
     def export_inner_bonds(self) -> np.ndarray:
         n = C.c_uint64()
         self._call("export_inner_bonds", C.c_void_p(), C.c_uint64(0), C.byref(n))

@@ -128,6 +128,7 @@ struct edb_context {
   DevBuf<uint32_t> b_ign_off;
   DevBuf<unsigned long long> b_ign_ids;
   bool have_ignore = false;
+  std::vector<double> h_farea;                    // face areas of the particle shapes at homothety 1, pooled by ShapeDev::f0
   std::vector<BondConv> h_conv;                   // broken bonds waiting to become vertex-vertex history at this rebuild
   DevBuf<BondConv> d_conv;
   DevBuf<BondParams> d_ibp;
@@ -673,6 +674,7 @@ extern "C" int edb_set_shapes(edb_context* c, int32_t n, const edb_shape* sh) {
   std::vector<v3> sv;
   std::vector<int> se, sfoff, sfn, sfidx;
   c->h_sh.clear();
+  c->h_farea.clear();
   int nvmax = 0;
   for (int i = 0; i < n; i++) {
     ShapeDev S{};
@@ -687,6 +689,14 @@ extern "C" int edb_set_shapes(edb_context* c, int32_t n, const edb_shape* sh) {
       sfoff.push_back((int)sfidx.size() - S.fi0);
       sfn.push_back(nfv);
       for (int k = 0; k < nfv; k++) sfidx.push_back(sh[i].faces[pos++]);
+    }
+    // face areas at homothety 1 (shape.hpp:673-697: fan triangulation from the first vertex), used by stick_polyhedra
+    for (int f = 0; f < S.nf; f++) {
+      const int* idx = &sfidx[S.fi0 + sfoff[S.f0 + f]];
+      const v3 v0 = sv[S.v0 + idx[0]];
+      double surface = 0;
+      for (int j = 1; j < sfn[S.f0 + f] - 1; j++) surface += 0.5 * norm(cross(sv[S.v0 + idx[j]] - v0, sv[S.v0 + idx[j + 1]] - v0));
+      c->h_farea.push_back(surface);
     }
     const double* o = sh[i].obb;
     S.obb = Obb{mk3(o[0], o[1], o[2]), mk3(o[3], o[4], o[5]), mk3(o[6], o[7], o[8]), mk3(o[9], o[10], o[11]), mk3(o[12], o[13], o[14])};
@@ -2267,6 +2277,58 @@ static void bonds_retire_broken(edb_context* c) {
     c->h_conv.push_back(BondConv{it->second, b.sub_i, b.sub_j, (long long)b.id_j, b.friction[0], b.friction[1], b.friction[2]});
   }
   c->h_bonds.swap(keep);
+}
+// [stick_polyhedra] on the device.  `cluster` (field::cluster, not part of the resident field set) is given per particle id.
+extern "C" int edb_stick_polyhedra(edb_context* c, double sticking_threshold, uint64_t n, const uint64_t* ids, const double* cluster) {
+  API_BEGIN(c)
+  if (!c->poly()) throw StateError{EDB_ERR_STATE, "stick_polyhedra needs a polyhedron context"};
+  if (!c->have_inc) throw StateError{EDB_ERR_STATE, "stick_polyhedra after chunk_neighbors_contact: call edb_update_particle_neighbors first"};
+  if (!c->ibp_groups) throw StateError{EDB_ERR_STATE, "stick_polyhedra before edb_set_inner_bond_params"};
+  const uint32_t np = c->nreal;
+  std::vector<uint64_t> pid(np);
+  CK(cudaStreamSynchronize(c->st));
+  if (np) CK(cudaMemcpy(pid.data(), c->pa.id.p, (size_t)np * 8, cudaMemcpyDeviceToHost));
+  std::unordered_map<uint64_t, double> cl;
+  cl.reserve((size_t)n * 2);
+  for (uint64_t k = 0; k < n; k++) cl[ids[k]] = cluster[k];
+  std::vector<double> hc(np, -1.0);
+  for (uint32_t p = 0; p < np; p++) {
+    auto it = cl.find(pid[p]);
+    if (it == cl.end()) throw StateError{EDB_ERR_INVALID, "stick_polyhedra: a particle has no cluster value"};
+    hc[p] = it->second;
+  }
+  const std::vector<double>& fa = c->h_farea;
+  DevBuf<double> d_cl, d_fa;
+  DevBuf<uint32_t> d_cnt, d_off;
+  DevBuf<StickBond> d_out;
+  d_cl.ensure(np + 1); d_fa.ensure(fa.size() + 1); d_cnt.ensure(np + 1); d_off.ensure(np + 2);
+  if (np) CK(cudaMemcpy(d_cl.p, hc.data(), (size_t)np * 8, cudaMemcpyHostToDevice));
+  if (!fa.empty()) CK(cudaMemcpy(d_fa.p, fa.data(), fa.size() * 8, cudaMemcpyHostToDevice));
+  StickArgs T{NbhArgs{view(c->pa), c->cidx.p, c->cbeg.p, c->cend.p, c->G, c->drv.p, 0, c->rcut_inc, c->symetric, np, c->vert.p, c->S, MeshView{}, 0,
+                      nullptr, nullptr},
+              d_cl.p, d_fa.p, c->d_ibp.p, c->ibp_groups, sticking_threshold};
+  LAUNCH(c, k_stick<0>, nblk(np, 64), 64, 0, T, d_cnt.p, nullptr, nullptr);
+  scan_u32(c, d_cnt.p, d_off.p, np);
+  uint32_t total = 0;
+  CK(cudaMemcpyAsync(&total, d_off.p + np, 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  std::vector<StickBond> hb(total);
+  if (total) {
+    d_out.ensure(total);
+    LAUNCH(c, k_stick<1>, nblk(np, 64), 64, 0, T, d_cnt.p, d_off.p, d_out.p);
+    CK(cudaStreamSynchronize(c->st));
+    CK(cudaMemcpy(hb.data(), d_out.p, (size_t)total * sizeof(StickBond), cudaMemcpyDeviceToHost));
+  }
+  c->h_bonds.clear();
+  for (const StickBond& b : hb) {
+    edb_inner_bond o{};
+    o.id_i = pid[b.a]; o.id_j = pid[b.b]; o.sub_i = b.sub_i; o.sub_j = b.sub_j; o.dn0 = b.dn0; o.weight = b.weight;
+    o.criteria_1 = b.c1; o.criteria_2 = b.c2; o.mode = b.mode; o.unbroken = 1; o.ghost = 0;
+    c->h_bonds.push_back(o);
+  }
+  d_cl.release(); d_fa.release(); d_cnt.release(); d_off.release(); d_out.release();
+  bonds_upload(c);
+  API_END(c)
 }
 extern "C" int edb_broken_interface_friction_updater(edb_context* c) {
   API_BEGIN(c)

@@ -7,6 +7,7 @@
 // stored per bond and summed per particle through an incidence list in a fixed order — no float atomics (the reference uses 12 per bond).
 #pragma once
 #include "common.cuh"
+#include "kernels_rebuild.cuh"
 
 namespace edb {
 
@@ -153,6 +154,105 @@ __global__ void k_bond_convert(const BondConv* __restrict__ cv, uint32_t n, WVie
     w.flg[s] = w.flg[s] | 8;   // FLG_HOT: the record carries history
     return;
   }
+}
+
+// ---- stick_polyhedra (src/polyhedron/stick_polyhedra.cpp:88-360) on the device ------------------------------------------------------
+// One thread per real particle a walks its neighbour cells like the contact enumeration does (same ContactNeighborFilterFunc); for a
+// partner b of the same cluster with id_a < id_b it looks for the first pair of faces (i of a, j of b) with the same vertex count, areas
+// within 1 %, parallel normals, and glues every vertex of face i to the first vertex of face j closer than the sticking threshold;
+// faces with fewer than 3 glued vertices are rejected and the search goes on; the glued vertices of a must be coplanar
+// (check_stiked_face, interaction_manager.hpp:226-276).  Pass 0 counts, pass 1 writes at the particle's offset.  Partners in ghost cells
+// (periodic images / other bricks) are skipped: OwnerGhost bonds are not built.
+constexpr int STICK_MAXV = 16;   // vertices per face handled
+struct StickBond {
+  uint32_t a, b, sub_i, sub_j;
+  double dn0, weight, c1, c2;
+  int mode, pad;
+};
+struct StickArgs {
+  NbhArgs N;
+  const double* cluster;      // per slot
+  const double* farea;        // face areas at homothety 1, pooled like the face tables (ShapeDev::f0)
+  const BondParams* ibp;
+  int n_groups;
+  double dn_crit;
+};
+template <int FILL>
+__global__ void __launch_bounds__(64) k_stick(StickArgs T, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ off, StickBond* __restrict__ out) {
+  const NbhArgs& A = T.N;
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= A.nreal) return;
+  const double4 ra = A.P.pr[a], wga = A.P.wg[a];
+  const uint64_t ida = A.P.id[a];
+  const uint32_t ta = (uint32_t)((unsigned long long)__double_as_longlong(wga.w) & 0xffffffffu), ga = (uint32_t)(((unsigned long long)__double_as_longlong(wga.w)) >> 32);
+  const ShapeDev sa = A.S.sh[ta];
+  const double ha = A.P.h[a], ca = T.cluster[a];
+  const VA va{A.vert + (size_t)a * A.S.nvmax};
+  uint32_t nout = 0;
+  for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
+    if (gc || b >= A.nreal) return;
+    if (T.cluster[b] != ca) return;
+    const uint64_t idb = A.P.id[b];
+    if (ida >= idb) return;
+    const double4 wgb = A.P.wg[b];
+    const uint32_t tb = (uint32_t)((unsigned long long)__double_as_longlong(wgb.w) & 0xffffffffu), gb = (uint32_t)(((unsigned long long)__double_as_longlong(wgb.w)) >> 32);
+    const ShapeDev sb = A.S.sh[tb];
+    const double hb = A.P.h[b];
+    const VA vb{A.vert + (size_t)b * A.S.nvmax};
+    const BondParams P = T.ibp[(size_t)ga * T.n_groups + gb];
+    StickBond loc[STICK_MAXV];
+    int nloc = 0;
+    bool found = false;
+    for (int i = 0; i < sa.nf && !found; i++) {
+      const int ni_ = A.S.fn[sa.f0 + i];
+      if (ni_ < 3 || ni_ > STICK_MAXV) continue;
+      const int* fi = A.S.fidx + sa.fi0 + A.S.foff[sa.f0 + i];
+      v3 ni = cross(va[fi[1]] - va[fi[0]], va[fi[2]] - va[fi[0]]);
+      ni = ni * (1.0 / norm(ni));
+      const double area_i = T.farea[sa.f0 + i];
+      for (int j = 0; j < sb.nf && !found; j++) {
+        const int nj_ = A.S.fn[sb.f0 + j];
+        if (nj_ < 3 || ni_ != nj_) continue;
+        const double ratio = area_i / T.farea[sb.f0 + j];
+        if (ratio > 1.01 || ratio < 0.99) continue;
+        const int* fj = A.S.fidx + sb.fi0 + A.S.foff[sb.f0 + j];
+        v3 nj = cross(vb[fj[1]] - vb[fj[0]], vb[fj[2]] - vb[fj[0]]);
+        nj = nj * (1.0 / norm(nj));
+        if (norm(cross(ni, nj)) > 1.e-10) continue;
+        const double area = area_i * ha * ha;   // shape::get_face_area(i, h), pi.id_ < pj.id_ here
+        StickBond B{a, b, 0, 0, 0.0, 1.0, 0.0, 0.0, P.mode, 0};
+        if (P.mode == 0) B.c1 = 2 * area * P.crit1;
+        else if (P.mode == 1) { B.c1 = 2 * area * P.crit1; B.c2 = 2 * area * P.crit2; }
+        else if (P.mode == 2) { B.c1 = 2 * area * P.crit1; B.c2 = area * P.crit2; }
+        found = true;
+        nloc = 0;
+        for (int iv = 0; iv < ni_; iv++)
+          for (int jv = 0; jv < nj_; jv++) {
+            const Contact c = detect_vv(va[fi[iv]], ha * sa.radius, vb[fj[jv]], hb * sb.radius);
+            if (c.dn <= T.dn_crit) {
+              B.sub_i = (uint32_t)fi[iv]; B.sub_j = (uint32_t)fj[jv]; B.dn0 = c.dn;
+              loc[nloc++] = B;
+              break;
+            }
+          }
+        if (nloc <= 2) { nloc = 0; found = false; }
+      }
+    }
+    if (nloc == 0) return;
+    bool ok = true;
+    if (nloc >= 3) {
+      const v3 p0 = va[loc[0].sub_i], nrm = cross(va[loc[1].sub_i] - p0, va[loc[2].sub_i] - p0);
+      for (int k = 3; k < nloc; k++)
+        if (fabs(dot(va[loc[k].sub_i] - p0, nrm)) > 1.e-10) ok = false;
+    }
+    if (!ok) return;
+    if (FILL) {
+      const double w = 1. / static_cast<double>(nloc);
+      for (int k = 0; k < nloc; k++) { loc[k].weight = w; out[off[a] + nout + k] = loc[k]; }
+    }
+    nout += (uint32_t)nloc;
+  });
+  if (!FILL) cnt[a] = nout;
 }
 
 // one thread per interface (loc, size): sums in bond order, breaks every bond of the interface when the criterion is exceeded

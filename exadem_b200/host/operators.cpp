@@ -165,6 +165,20 @@ class UpdateGridSTLMeshOperator : public OperatorNode {
 // -------------------------------------------------------------------------------------------------------------------
 // inner bonds (fragmentation decks, data/config/config_fragmentation.msp): per-step operators
 // -------------------------------------------------------------------------------------------------------------------
+// src/polyhedron/stick_polyhedra.cpp:45-365.  field::cluster is not part of the device-resident field set: the binding hands it over
+// per particle id (two vectors copied from the grid's id / cluster fields).
+class StickPolyhedraOperator : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(double, sticking_threshold, INPUT, REQUIRED);
+  ADD_SLOT(std::vector<uint64_t>, cluster_particle_ids, INPUT, REQUIRED);
+  ADD_SLOT(std::vector<double>, cluster, INPUT, REQUIRED);
+ public:
+  std::string documentation() const final { return "stick_polyhedra: glue the matching faces of neighbouring polyhedra of the same cluster with inner bonds."; }
+  void execute() final {
+    if (cluster_particle_ids->size() != cluster->size()) throw std::runtime_error("stick_polyhedra: ids / cluster size mismatch");
+    ck(*grid, edb_stick_polyhedra(grid->ctx, *sticking_threshold, cluster->size(), cluster_particle_ids->data(), cluster->data()), "stick_polyhedra");
+  }
+};
 // src/polyhedron/inner_bond_force.cu:44-139
 class ComputeInnerBondForce : public OperatorNode {
   ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
@@ -382,6 +396,7 @@ ONIKA_AUTORUN_INIT(exadem_b200_hot_path) {
   f->register_factory("grid_rshape_driver", make_simple_operator<UpdateGridSTLMeshOperator>);
   f->register_factory("backup_drivers", make_simple_operator<BackupDrivers>);
   f->register_factory("driver_displ_over", make_simple_operator<DriverDisplacementOver>);
+  f->register_factory("stick_polyhedra", make_simple_operator<StickPolyhedraOperator>);
   f->register_factory("inner_bond_polyhedron", make_simple_operator<ComputeInnerBondForce>);
   f->register_factory("update_interfaces", make_simple_operator<UpdateInterfaces>);
   f->register_factory("apply_interface_fracture_criterion", make_simple_operator<ApplyInterfaceFractureCriterion>);

@@ -265,13 +265,17 @@ typedef struct edb_sim_state {
 } edb_sim_state;
 int edb_simulation_state(edb_context*, int32_t symetric, edb_sim_state* out);
 
-/* ---- inner bonds (fragmentation, wave 13), SURVEY 8(f) rank 4: the per-step operators.  Bond creation (stick_polyhedra, a one-off
- * preprocessing) and the fragmentation dump reader stay on the host side of the binding: the bonds enter through
- * edb_import_inner_bonds.  While a bond holds, the polyhedron contact enumeration ignores the pair it glues
+/* ---- inner bonds (fragmentation, wave 13), SURVEY 8(f) rank 4.  Bonds are created by edb_stick_polyhedra or enter through
+ * edb_import_inner_bonds (the fragmentation dump reader stays on the host side of the binding).  While a bond holds, the polyhedron contact enumeration ignores the pair it glues
  * (InteractionManager::update_ignore_interaction).  NOT built yet: bonds across periodic / brick boundaries (OwnerGhost bonds), the
  * bonds inside edb_run_verlet (fragmentation decks run operator by operator). ------------------------------------------------- */
 int edb_set_inner_bond_params(edb_context*, int32_t n_groups, const edb_inner_bond_params* ibp /* n_groups^2 */);
 int edb_import_inner_bonds(edb_context*, const edb_inner_bond* in, uint64_t n);
+/* [stick_polyhedra] src/polyhedron/stick_polyhedra.cpp:88-360 on the device: glues the matching faces of neighbouring polyhedra of the
+ * same cluster (id_i < id_j) — one bond per vertex pair closer than the threshold, weight 1/#bonds, rupture criterion from the face
+ * area and the bond parameters.  Call after edb_update_particle_neighbors (it walks the same neighbour cells); `cluster` is
+ * field::cluster given per particle id (ids[n], cluster[n]).  Replaces the bond list.  Partners in ghost cells are skipped. */
+int edb_stick_polyhedra(edb_context*, double sticking_threshold, uint64_t n, const uint64_t* ids, const double* cluster);
 int edb_export_inner_bonds(edb_context*, edb_inner_bond* out, uint64_t cap, uint64_t* n); /* owner-sorted; out may be NULL to query n */
 /* [update_interfaces] src/interaction/update_interfaces.cpp:44-84: interfaces = runs of bonds between the same two particles; also
  * re-resolves the particle slots of the bonds by id (to be called after every edb_update_particle_neighbors, like the deck does) */

@@ -53,6 +53,11 @@ class OracleEngine(capi.Engine):
     def stick_polyhedra(self, threshold):
         self._call("stick_polyhedra", C.c_double(threshold))
 
+    def stick_polyhedra_ids(self, threshold, ids, cluster):
+        """same call shape as the product's edb_stick_polyhedra"""
+        self.set_particle_clusters(ids, cluster)
+        self.stick_polyhedra(threshold)
+
     def sync(self):
         pass
 

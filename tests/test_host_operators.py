@@ -25,7 +25,7 @@ combined_compute_prolog combined_compute_epilog push_to_quaternion push_to_angul
 freeze_particles pas_libere_pas_delivre ghost_update_rq vertex_displ_over particle_displ_over backup_dem
 migrate_cell_particles_interaction move_particles_interaction compute_driver_force_moment stress_tensor simulation_state
 push_f_v_r_driver push_f_v_driver push_av_to_quat_driver reset_force_driver force_to_accel_driver driver_vertices grid_rshape_driver
-backup_drivers driver_displ_over inner_bond_polyhedron update_interfaces apply_interface_fracture_criterion
+backup_drivers driver_displ_over stick_polyhedra inner_bond_polyhedron update_interfaces apply_interface_fracture_criterion
 broken_interface_friction_updater""".split()
 
 

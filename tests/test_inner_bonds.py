@@ -257,3 +257,40 @@ def test_gpu_bonds_follow_their_particles_across_a_rebuild(product_lib, oracle_l
                 assert e.update_interfaces() > 0
     compare_bonds(*engines)
     compare_particles(engines[0].download_particles(), engines[1].download_particles(), rtol=RTOL)
+
+
+def two_clusters(wl):
+    """left and right halves of the block are different clusters: no bond across x = 1.6"""
+    return np.where(wl.particles.rx < 1.6, 1.0, 2.0)
+
+
+def test_stick_polyhedra_respects_clusters_on_the_oracle():
+    wl, ibp = glued_block()
+    e = wl.setup(OracleEngine(OracleLibrary(), wl.config()))
+    e.set_inner_bond_params(1, ibp)
+    e.update_particle_neighbors(wl.rcut_inc, True)
+    e.stick_polyhedra_ids(2e-5, wl.particles.id, two_clusters(wl))
+    b = e.export_inner_bonds()
+    assert len(b) == 4 * (104 - 12) and e.update_interfaces() == 92   # the 4 x 3 faces across the cut are not glued
+
+
+@pytest.mark.gpu
+def test_gpu_stick_polyhedra(product_lib, oracle_lib):
+    """bond creation on the device (k_stick) against the oracle's restatement of stick_polyhedra.cpp: same bonds, dn0 / weight / criterion"""
+    from exadem_b200 import Engine
+    wl, ibp = glued_block()
+    out = []
+    for e in (wl.setup(Engine(product_lib, wl.config())), wl.setup(OracleEngine(oracle_lib, wl.config()))):
+        e.set_inner_bond_params(1, ibp)
+        e.update_particle_neighbors(wl.rcut_inc, True)
+        e.stick_polyhedra_ids(2e-5, wl.particles.id, two_clusters(wl))
+        assert e.update_interfaces() == 92
+        rec = e.export_inner_bonds()
+        out.append(rec[bond_key(rec)])
+    a, b = out
+    assert len(a) == len(b) == 368
+    for k in ("id_i", "id_j", "sub_i", "sub_j", "unbroken", "mode"):
+        assert np.array_equal(a[k], b[k]), k
+    for k in ("weight", "criteria_1", "criteria_2"):
+        assert np.array_equal(a[k], b[k]), k     # same expressions on the same inputs: bit-identical
+    assert np.abs(a["dn0"] - b["dn0"]).max() < 1e-12 and np.abs(b["dn0"]).max() < 2e-5
