@@ -1390,6 +1390,14 @@ void orc_inner_bond_force_core(double dn, const double* n, double dn0, double we
   inner_bond_force_core(dn, V3(n), dn0, weight, dt, P, meff, en_et[0], T, en_et[1], F, V3(cp), V3(pi), V3(vi), f, V3(wi), V3(pj), V3(vj), V3(wj));
   S3(tds, T); S3(ft, F); S3(fi, f);
 }
+// the oracle's sort / match key against InteractionPair::operator< and operator== (mirrored by oracle/ref_math.cpp:ref_pair_less/equal)
+static Inter mk_inter(const unsigned long long* r) {
+  Inter I;
+  I.id_i = r[0]; I.id_j = r[1]; I.sub_i = (uint32_t)r[2]; I.sub_j = (uint32_t)r[3]; I.type = (uint16_t)r[4]; I.swap = (uint8_t)r[5];
+  return I;
+}
+int orc_pair_less(const unsigned long long* a, const unsigned long long* b) { return key_of(mk_inter(a)) < key_of(mk_inter(b)) ? 1 : 0; }
+int orc_pair_equal(const unsigned long long* a, const unsigned long long* b) { return key_of(mk_inter(a)) == key_of(mk_inter(b)) ? 1 : 0; }
 int orc_interface_breaks(int mode, double c1, double c2, const double* en, const double* et, const double* dn, const double* fn3, uint64_t size) {
   std::vector<v3> fn(size);
   for (uint64_t k = 0; k < size; k++) fn[k] = V3(fn3 + 3 * k);

@@ -22,6 +22,7 @@
 #include <exaDEM/surface.hpp>
 #include <exaDEM/ball.hpp>
 #include <exaDEM/rshape.hpp>
+#include <exaDEM/interaction/interaction_pair.hpp>
 #include <exaDEM/forcefield/inner_bond_parameters.hpp>
 #include <exaDEM/forcefield/inner_bond_force.hpp>
 #include "../include/exadem_b200.h"
@@ -240,5 +241,16 @@ void ref_inner_bond_force_core(double dn, const double* n, double dn0, double we
   exaDEM::force_law_core(dn, V(n), dn0, weight, dt, P, meff, en_et[0], T, en_et[1], F, V(cp), V(pi), V(vi), f, V(wi), V(pj), V(vj), V(wj));
   S(tds, T); S(ft, F); S(fi, f);
 }
+
+// InteractionPair ordering / equality (src/interaction/include/exaDEM/interaction/interaction_pair.hpp:186-249): the sort key of the
+// per-particle interaction lists and the match key of the history carry-over.  rec = {id_i, id_j, sub_i, sub_j, type, swap}
+static exaDEM::InteractionPair mk_pair(const unsigned long long* r) {
+  exaDEM::InteractionPair p;
+  p.pi_.id_ = r[0]; p.pj_.id_ = r[1]; p.pi_.sub_ = (uint32_t)r[2]; p.pj_.sub_ = (uint32_t)r[3]; p.type_ = (uint16_t)r[4]; p.swap_ = (uint8_t)r[5];
+  p.pi_.cell_ = 0; p.pj_.cell_ = 0; p.pi_.p_ = 0; p.pj_.p_ = 0; p.ghost_ = 0;
+  return p;
+}
+int ref_pair_less(const unsigned long long* a, const unsigned long long* b) { return mk_pair(a) < mk_pair(b) ? 1 : 0; }
+int ref_pair_equal(const unsigned long long* a, const unsigned long long* b) { return mk_pair(a) == mk_pair(b) ? 1 : 0; }
 
 }  // extern "C"

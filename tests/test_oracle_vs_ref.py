@@ -202,3 +202,28 @@ def test_drivers(orc, kind):
         assert REF.ref_driver_filter(kind, p(prm), C.c_double(rcut), p(pt)) == \
             orc.orc_driver_filter(kind, p(prm), C.c_double(rcut), p(pt))
     assert hits > 100
+
+
+def test_interaction_pair_order_and_equality():
+    """The oracle's sort / history-match key (owner id, partner id, type, swap, owner sub, partner sub) against the reference's own
+    InteractionPair::operator< and operator== (interaction_pair.hpp:186-249) — ties in every field exercised."""
+    import ctypes as C
+    import numpy as np
+    from oracle_binding import OracleLibrary, ref_math
+    ref = ref_math()
+    if ref is None or not hasattr(ref, "ref_pair_less"):
+        import pytest
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    orc = OracleLibrary().dll
+    rng = np.random.default_rng(3)
+    n_less = n_eq = 0
+    for _ in range(20000):
+        a = np.array([rng.integers(0, 3), rng.integers(0, 3), rng.integers(0, 2), rng.integers(0, 2), rng.integers(0, 4), rng.integers(0, 2)], dtype=np.uint64)
+        b = np.array([rng.integers(0, 3), rng.integers(0, 3), rng.integers(0, 2), rng.integers(0, 2), rng.integers(0, 4), rng.integers(0, 2)], dtype=np.uint64)
+        pa, pb = a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)
+        l_ref, l_orc = ref.ref_pair_less(pa, pb), orc.orc_pair_less(pa, pb)
+        e_ref, e_orc = ref.ref_pair_equal(pa, pb), orc.orc_pair_equal(pa, pb)
+        assert l_ref == l_orc and e_ref == e_orc, (a, b, l_ref, l_orc, e_ref, e_orc)
+        n_less += l_ref
+        n_eq += e_ref
+    assert n_less > 5000 and n_eq > 20
