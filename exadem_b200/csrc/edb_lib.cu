@@ -443,6 +443,7 @@ extern "C" int edb_set_law(edb_context* c, int32_t law) {
 // the world vertices are owned by the device (k_driver_vertices follows the drivers' motion).
 static void upload_mesh_tables(edb_context* c) {
   const int nm = (int)c->h_md.size();
+  const MeshView old = c->M;
   c->M = MeshView{};
   if (nm == 0) return;
   c->d_md.ensure(nm); c->d_mverts.ensure(c->h_mverts.size() + 1); c->d_mlocal.ensure(c->h_mlocal.size() + 1);
@@ -461,6 +462,10 @@ static void upload_mesh_tables(edb_context* c) {
   for (int m = 0; m < nm; m++) ps[m + 1] = ps[m] + (uint32_t)(c->h_md[m].nv + c->h_md[m].ne + c->h_md[m].nf);
   c->d_mprim_start.ensure(nm + 1);
   CK(cudaMemcpy(c->d_mprim_start.p, ps.data(), (nm + 1) * 4, cudaMemcpyHostToDevice));
+  // a host-driven update of the same drivers between two rebuilds (edb_set_drivers called again): the contact operators keep working on
+  // the cell lists of the last rebuild with the refreshed tables; anything else waits for the next rebuild (mesh_dirty)
+  if (old.nmesh == nm && old.cell_off)
+    c->M = MeshView{c->d_md.p, c->d_mverts.p, c->d_medges.p, c->d_mfoff.p, c->d_mfn.p, c->d_mfidx.p, old.cell_off, old.cell_data, nm, old.ncell};
 }
 
 // [grid_rshape_driver] per-cell primitive lists of the RShape meshes, built on the device from the current world vertices
