@@ -1103,6 +1103,7 @@ static void update_interaction_ghost(edb_context* c) {
 }
 
 static void driver_op(edb_context* c, int op, double time, double dt, double system_mass);
+static void driver_gravity_launch(edb_context* c, const double g[3]);
 static void driver_force_reduce(edb_context* c);
 static void driver_vertices(edb_context* c, bool all);
 static void backup_drivers(edb_context* c);
@@ -1425,6 +1426,7 @@ extern "C" int edb_reset_force_moment(edb_context* c) {
 extern "C" int edb_gravity_force(edb_context* c, const double g[3]) {
   API_BEGIN(c)
   LAUNCH(c, k_gravity, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, g[0], g[1], g[2]);
+  driver_gravity_launch(c, g);   // "particles and drivers": PARTICLE RShape drivers (gravity_force.cu:72-83)
   API_END(c)
 }
 extern "C" int edb_force_to_accel(edb_context* c) {
@@ -1700,6 +1702,7 @@ static uint64_t run_verlet_moving(edb_context* c, double dt, const double g[3], 
       driver_vertices(c, false);
     }
     driver_op(c, DOP_RESET_FORCE, 0.0, 0.0, 0.0);
+    driver_gravity_launch(c, g);       // gravity_force also acts on the PARTICLE RShape drivers (gravity_force.cu:72-83)
     contact_waves(c, dt);
     gather<1>(c, g, dt);               // reset + gravity + contact wrenches + force_to_accel + epilog of the particles
     driver_force_reduce(c);            // force_to_accel_driver: reaction sums, then Ball::f_ra / force_to_accel
@@ -1729,7 +1732,7 @@ static void ensure_system_mass(edb_context* c) {
 }
 // the fused driver operators of one step boundary (k_driver_cycle) + what follows them: mesh vertices and the drivers' share of the
 // rebuild trigger of the next step
-static void driver_cycle(edb_context* c, double dt, double time_next, bool do_end, bool do_begin, const unsigned long long* gate,
+static void driver_cycle(edb_context* c, const double g[3], double dt, double time_next, bool do_end, bool do_begin, const unsigned long long* gate,
                          unsigned long long* next_flag, double thr) {
   const int nd = (int)c->h_drv.size();
   if (!nd) return;
@@ -1741,7 +1744,7 @@ static void driver_cycle(edb_context* c, double dt, double time_next, bool do_en
     if (c->cfg.nranks > 1) c->comm.allreduce_sum_f64_dev(c->drv_sums.p, (size_t)nd * 6, c->st);
   }
   DriverCycleArgs A{c->drv.p, c->mo.p, nd, sums ? c->drv_sums.p : nullptr, c->poly() ? 0 : 1, do_end ? 1 : 0, do_begin ? 1 : 0,
-                    dt, c->system_mass, time_next, gate};
+                    dt, c->system_mass, time_next, gate, g ? mk3(g[0], g[1], g[2]) : mk3(0, 0, 0)};
   LAUNCH(c, k_driver_cycle, nblk(nd, 64), 64, 0, A);
   if (do_begin) {
     if (c->mesh_moving) driver_vertices(c, false);   // idempotent on a gated-off step (drivers unchanged)
@@ -1771,7 +1774,7 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
   if (nsteps > 0) {
     prolog(c, dt);
     if (trig) trigger_standalone(c, 0, thr);
-    if (mv) driver_cycle(c, dt, tcur, false, true, nullptr, trig ? c->d_sflag + 0 : nullptr, thr);
+    if (mv) driver_cycle(c, g, dt, tcur, false, true, nullptr, trig ? c->d_sflag + 0 : nullptr, thr);
   }
   for (int it = 0; it < nsteps; it++) {
     const bool last = it + 1 == nsteps;
@@ -1781,17 +1784,17 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
       contact_waves(c, dt, gate, (!last && trig) ? c->d_sflag + nslot : nullptr, &zeroed);
       if (last) {
         gather<1>(c, g, dt, gate);
-        if (mv) driver_cycle(c, dt, tcur + dt, true, false, gate, nullptr, thr);
+        if (mv) driver_cycle(c, g, dt, tcur + dt, true, false, gate, nullptr, thr);
         return;
       }
       if (!trig) {
         gather<2>(c, g, dt, gate);
-        if (mv) driver_cycle(c, dt, tcur + dt, true, true, gate, nullptr, thr);
+        if (mv) driver_cycle(c, g, dt, tcur + dt, true, true, gate, nullptr, thr);
         return;
       }
       if (!zeroed) CK(cudaMemsetAsync(c->d_sflag + nslot, 0, 8, c->st));
       gather<2>(c, g, dt, gate, c->d_sflag + nslot, thr);
-      if (mv) driver_cycle(c, dt, tcur + dt, true, true, gate, c->d_sflag + nslot, thr);
+      if (mv) driver_cycle(c, g, dt, tcur + dt, true, true, gate, c->d_sflag + nslot, thr);
     };
     if (!trig) {
       const bool rb = rebuild_every > 0 && ((it + 1) % rebuild_every) == 0;
@@ -2007,6 +2010,10 @@ extern "C" int edb_compute_driver_force_moment(edb_context* c, double* forces, d
 static void driver_op(edb_context* c, int op, double time, double dt, double system_mass) {
   const int nd = (int)c->h_drv.size();
   if (nd) LAUNCH(c, k_driver_op, nblk(nd, 64), 64, 0, c->drv.p, c->mo.p, nd, op, time, dt, system_mass);
+}
+static void driver_gravity_launch(edb_context* c, const double g[3]) {
+  const int nd = (int)c->h_drv.size();
+  if (nd && c->drivers_moving) LAUNCH(c, k_driver_gravity, nblk(nd, 64), 64, 0, c->drv.p, c->mo.p, nd, mk3(g[0], g[1], g[2]));
 }
 // reaction of the driver waves of the last contact operator -> DriverMotion::forces / mom (deterministic block-ordered sums)
 // block partials of the driver waves summed into drv_sums[nd * 6] in a fixed order (this rank's share)

@@ -228,6 +228,16 @@ EDB_HD void driver_force_to_accel(Driver& d, DriverMotion& m, double system_mass
   }
 }
 
+// gravity_force.hpp:26-37 (GravityForceDriverFunctor, applied by gravity_force.cu:72-83): gravity acts on the RShape drivers whose motion
+// type is PARTICLE (the reference adds it on rank 0 before the all-reduce of the driver forces; here every rank holds the reduced value)
+EDB_HD void driver_gravity(const Driver& d, DriverMotion& m, v3 g) {
+  if (d.kind == EDB_DRIVER_RSHAPE && m.motion == M_PARTICLE) m.forces = m.forces + g * m.mass;
+}
+__global__ void k_driver_gravity(const Driver* __restrict__ drv, DriverMotion* __restrict__ mo, int n, v3 g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) driver_gravity(drv[i], mo[i], g);
+}
+
 enum DriverOp { DOP_PUSH_F_V_R = 0, DOP_PUSH_F_V = 1, DOP_PUSH_AV_TO_QUAT = 2, DOP_RESET_FORCE = 3, DOP_FORCE_TO_ACCEL = 4 };
 
 // One operator of the time loop over the drivers, one thread per driver.
@@ -277,6 +287,7 @@ struct DriverCycleArgs {
   int sphere_mode, do_end, do_begin;
   double dt, system_mass, time_next;
   const unsigned long long* gate;
+  v3 g;                 // gravity of the step (gravity_force acts on PARTICLE RShape drivers)
 };
 __global__ void k_driver_cycle(DriverCycleArgs A) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,7 +295,8 @@ __global__ void k_driver_cycle(DriverCycleArgs A) {
   Driver d = A.drv[i];
   DriverMotion& m = A.mo[i];
   if (A.do_end) {
-    m.forces = mk3(0, 0, 0);   // reset_force_driver ran before the contacts of the step
+    m.forces = mk3(0, 0, 0);   // reset_force_driver ran before the forces of the step
+    driver_gravity(d, m, A.g);  // gravity_force comes first in compute_force
     if (A.sums) {
       if (m_need_forces(m.motion)) m.forces = m.forces + mk3(A.sums[i * 6], A.sums[i * 6 + 1], A.sums[i * 6 + 2]);
       if (A.sphere_mode && d.kind == EDB_DRIVER_RSHAPE && rshape_need_moment(m)) m.mom = m.mom + mk3(A.sums[i * 6 + 3], A.sums[i * 6 + 4], A.sums[i * 6 + 5]);

@@ -726,6 +726,9 @@ static void reset_fm(Sim& s) {
 }
 static void gravity(Sim& s, const double* g) {
   PFOR(s.nreal) { s.f[p].x += g[0] * s.mass[p]; s.f[p].y += g[1] * s.mass[p]; s.f[p].z += g[2] * s.mass[p]; }
+  // drivers (gravity_force.cu:72-83, GravityForceDriverFunctor gravity_force.hpp:26-37): only RShape drivers with the PARTICLE motion
+  for (Driver& d : s.drivers)
+    if (d.kind == DRV_RSHAPE && d.motion == M_PARTICLE) d.forces = d.forces + v3{g[0], g[1], g[2]} * d.mass;
 }
 static void force_to_accel(Sim& s) {
   PFOR(s.nreal) { s.f[p].x /= s.mass[p]; s.f[p].y /= s.mass[p]; s.f[p].z /= s.mass[p]; }
