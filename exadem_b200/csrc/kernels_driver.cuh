@@ -289,9 +289,7 @@ struct DriverCycleArgs {
   const unsigned long long* gate;
   v3 g;                 // gravity of the step (gravity_force acts on PARTICLE RShape drivers)
 };
-__global__ void k_driver_cycle(DriverCycleArgs A) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= A.n || (A.gate && *A.gate)) return;
+EDB_HD void driver_cycle_body(const DriverCycleArgs& A, int i) {
   Driver d = A.drv[i];
   DriverMotion& m = A.mo[i];
   if (A.do_end) {
@@ -310,6 +308,11 @@ __global__ void k_driver_cycle(DriverCycleArgs A) {
     driver_push_av_to_quat(d, m, A.time_next, A.dt);
   }
   A.drv[i] = d;
+}
+__global__ void k_driver_cycle(DriverCycleArgs A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n || (A.gate && *A.gate)) return;
+  driver_cycle_body(A, i);
 }
 
 // driver_vertices.cu:28-35: vertices_[i] = center + quat * shp_vertices[i] for the non-stationary meshes (rshape.hpp:419); `all` forces

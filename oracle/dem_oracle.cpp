@@ -1406,6 +1406,40 @@ int orc_interface_breaks(int mode, double c1, double c2, const double* en, const
   for (uint64_t k = 0; k < size; k++) fn[k] = V3(fn3 + 3 * k);
   return interface_breaks(mode, c1, c2, en, et, dn, fn.data(), size) ? 1 : 0;
 }
+// One step boundary on one driver, composed from the operators in the macro's order (config_numerical_schemes.msp:13-24): the reference
+// sequence that the product's fused k_driver_cycle has to reproduce.  sums6 = what the contacts of the step add to forces / moment.
+int orc_driver_cycle(edb_driver* d, edb_driver_motion* m, const double* g, const double* sums6, int sphere_mode, double system_mass, double dt,
+                     double time_next, int do_end, int do_begin) {
+  Sim s;
+  edb_driver din = *d;
+  if (din.kind == EDB_DRIVER_RSHAPE) { s.mesh_shapes.resize(1); din.shape = 0; }
+  const double c0[3] = {d->center[0], d->center[1], d->center[2]};
+  if (orc_set_drivers((orc_sim*)&s, 1, &din)) return EDB_ERR_INVALID;
+  Driver& D = s.drivers[0];
+  if (D.kind == DRV_CYLINDER) D.center = V3(c0);
+  orc_set_driver_motions((orc_sim*)&s, 1, m);
+  D.forces = V3(m->forces);
+  if (D.kind == DRV_SURFACE) { D.cproj = V3(m->mom); D.mom = {0, 0, 0}; }
+  if (do_end) {
+    reset_force_driver(s);                                   // (before the forces of the step)
+    gravity(s, g);                                           // compute_force: gravity_force first (no particles here)
+    if (sums6) {                                             // ... then the contacts
+      if (m_need_forces(D.motion)) D.forces = D.forces + V3(sums6);
+      if (sphere_mode && D.kind == DRV_RSHAPE && rshape_need_moment(D)) D.mom = D.mom + V3(sums6 + 3);
+    }
+    force_to_accel_driver(s, system_mass);
+    push_f_v_driver(s, 0.5 * dt);
+  }
+  if (do_begin) {
+    push_f_v_r_driver(s, time_next, dt);
+    push_f_v_driver(s, 0.5 * dt);
+    push_av_to_quat_driver(s, time_next, dt);
+  }
+  const v3 cproj = D.cproj;
+  orc_get_drivers((orc_sim*)&s, 1, d, m);
+  if (D.kind == DRV_SURFACE) S3(m->mom, cproj);
+  return 0;
+}
 int orc_push_f_v_r_driver(orc_sim* h, double t, double dt) { push_f_v_r_driver(*(Sim*)h, t, dt); return 0; }
 int orc_push_f_v_driver(orc_sim* h, double dt) { push_f_v_driver(*(Sim*)h, dt); return 0; }
 int orc_push_av_to_quat_driver(orc_sim* h, double t, double dt) { push_av_to_quat_driver(*(Sim*)h, t, dt); return 0; }

@@ -62,6 +62,44 @@ def test_product_integrators_compiled_for_host_vs_oracle(tmp_path):
     _assert_bitwise(_oracle_rows(cases), driver_cases.run_cases(chk.chk_driver_motion_op, cases), cases)
 
 
+def test_product_cycle_kernel_body_compiled_for_host_vs_oracle_sequence(tmp_path):
+    """The body of the fused step-boundary kernel (driver_cycle_body = what k_driver_cycle runs per driver: reset, gravity on PARTICLE
+    meshes, contact reaction, force_to_accel_driver, push_f_v(dt/2) | push_f_v_r, push_f_v(dt/2), push_av_to_quat) compiled for the host
+    against the same sequence composed from the oracle's operators: bit-identical for every driver kind and motion type."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        pytest.skip("nvcc not available")
+    so = tmp_path / "libhost_check_driver.so"
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-fmad=false", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+                    "-shared", str(Path(__file__).parent / "host_check_driver.cu"), "-o", str(so)], check=True, capture_output=True)
+    chk, orc = C.CDLL(str(so)), OracleLibrary().dll
+    rng = np.random.default_rng(99)
+    n = 0
+    for kind, motions in driver_cases.VALID.items():
+        for motion in motions:
+            for do_end, do_begin in ((1, 1), (1, 0), (0, 1)):
+                for _ in range(6):
+                    d, m, time, dt, smass = driver_cases.make_case(rng, kind, motion)
+                    g = np.array([0.1, -0.2, -9.807])
+                    sums = np.ascontiguousarray(rng.normal(size=6) * 5.0)
+                    sphere = int(rng.integers(0, 2))
+                    rows = []
+                    for fn in (orc.orc_driver_cycle, chk.chk_driver_cycle):
+                        keep = []
+                        D, M = driver_cases.to_structs(d, m, keep)
+                        rc = fn(C.byref(D), C.byref(M), g.ctypes.data_as(C.c_void_p), sums.ctypes.data_as(C.c_void_p), C.c_int(sphere),
+                                C.c_double(smass), C.c_double(dt), C.c_double(time), C.c_int(do_end), C.c_int(do_begin))
+                        assert rc == 0
+                        rows.append(driver_cases.flatten(D, M))
+                    same = (rows[0] == rows[1]) | (np.isnan(rows[0]) & np.isnan(rows[1]))
+                    assert same.all(), (kind, motion, do_end, do_begin, np.argwhere(~same).ravel(), rows[0][~same], rows[1][~same])
+                    n += 1
+    assert n > 300
+
+
 # ---------------------------------------------------------------------------------------------------------------------------------
 # scenarios with moving drivers, run on two engines (GPU vs oracle in the gpu tests; oracle vs oracle as a CPU self-check of the
 # scenario itself: drivers are touched, rebuilds are triggered by the drivers, ...)
