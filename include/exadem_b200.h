@@ -298,11 +298,11 @@ int edb_get_inner_bond_state(edb_context*, double* dn, double* cp, double* fn, d
  * prolog -> (rebuild if displacement >= rcut_inc/2 | ghost_update_rq) -> [compute_vertices] -> reset+gravity+contact
  * +force_to_accel -> epilog.  rebuild_every > 0 forces a fixed rebuild schedule instead of the displacement trigger
  * (parity runs make the schedule an explicit input); 0 = trigger; <0 = never rebuild.
- * When a driver has a motion (edb_set_driver_motions) the loop runs the full macro operator by operator instead — prolog,
- * push_f_v_r_driver, push_f_v_driver(dt/2), push_av_to_quat_driver, trigger (particle_displ_over | driver_displ_over), rebuild
- * (backup_drivers, grid_rshape_driver) | ghost_update_rq + driver_vertices, reset_force_driver, contact, force_to_accel,
- * force_to_accel_driver(system mass = sum of the particle masses), push_f_v_driver(dt/2), epilog — with one host read of the
- * trigger per step. */
+ * When a driver has a motion (edb_set_driver_motions) the loop also runs the driver operators of the macro in the reference's order —
+ * push_f_v_r_driver, push_f_v_driver(dt/2), push_av_to_quat_driver after the prolog; driver_displ_over in the trigger; backup_drivers,
+ * driver_vertices, grid_rshape_driver in the rebuild; reset_force_driver, gravity on PARTICLE meshes, force_to_accel_driver (system mass:
+ * edb_set_system_mass, default = sum of the particle masses), push_f_v_driver(dt/2) before the epilog — fused into one small kernel per
+ * step boundary, still without a host round trip per step.  `physical_time` (edb_set_physical_time) advances by dt per step. */
 int edb_run_verlet(edb_context*, double dt, const double g[3], double rcut_inc, int32_t symetric, int32_t nsteps,
                    int32_t rebuild_every, uint64_t* n_rebuilds);
 
