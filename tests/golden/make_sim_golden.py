@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Generates tests/golden/sim_golden.npz: end states of three small simulations run by the ORACLE (serial canonical order) —
+"""Generates tests/golden/sim_golden.npz: end states of five small simulations run by the ORACLE (serial canonical order) —
 a regression anchor for the operator-loop layer that the reference's own tests do not pin: any change to the
 oracle's loops, to the workload generators or to the CUDA path that moves a result shows up against these vectors.
 
@@ -24,6 +24,11 @@ def cases():
     yield "drum", workloads.rotating_drum(900, jitter=0.02), 30, 0
     yield "deposit", workloads.deposit((8, 8, 6)), 30, 10
     yield "poly", workloads.polyhedra_box((6, 6, 6), shapes=("octahedron", "cube"), pitch=0.8, cell_size=1.6), 20, 5
+    # moving drivers (scenarios of tests/test_driver_motion.py without trigonometric motions, so that the device's
+    # sin / cos do not enter): a roof descending at constant velocity, a translating + spinning mesh around a free-body mesh
+    import test_driver_motion as T
+    yield "piston", T.scenario_piston(), 60, 0
+    yield "moving_mesh", T.scenario_moving_mesh(), 30, 0
 
 
 def run(engine_cls, lib, wl, steps, rebuild_every):

@@ -1,6 +1,7 @@
 """Simulation-level golden vectors (tests/golden/sim_golden.npz, made by tests/golden/make_sim_golden.py with the oracle in its
-serial canonical order): three small runs — rotating drum (BASELINE configs[0]/[1] family), deposit on a surface driver
-(configs[0]), octahedra + cubes (configs[2] family).  The reference ships no expected values for the operator loops (SURVEY.md
+serial canonical order): five small runs — rotating drum (BASELINE configs[0]/[1] family), deposit on a surface driver
+(configs[0]), octahedra + cubes (configs[2] family), and two runs with moving drivers (a descending roof; a translating and
+spinning mesh around a free-body mesh).  The reference ships no expected values for the operator loops (SURVEY.md
 8c), so these pin the oracle against ITSELF over time (CPU test) and the CUDA path against the committed numbers (GPU test):
 interaction keys bit-exact, state and friction history within 1e-10."""
 import sys
