@@ -294,3 +294,83 @@ def test_gpu_stick_polyhedra(product_lib, oracle_lib):
     for k in ("weight", "criteria_1", "criteria_2"):
         assert np.array_equal(a[k], b[k]), k     # same expressions on the same inputs: bit-identical
     assert np.abs(a["dn0"] - b["dn0"]).max() < 1e-12 and np.abs(b["dn0"]).max() < 2e-5
+
+
+# ---- the reference's traction verification deck (example/polyhedra/fragmentation/verification_test/traction/traction.msp) -------------
+def traction_pair(gc, speed=10.0, dt=1e-5):
+    """Two cubes of side 0.98 + Minkowski radius 0.01 one lattice step (1.0) apart, bonded at their common face, kn = 1e3, kt = 8e2,
+    damp_rate = 0.87, g = Gc (EnergyMixedMode), sticking threshold 1.5e-4 — the traction deck.  The deck freezes cube 1 and imposes the
+    velocity of cube 2 with region operators; here both are made so heavy that the forces do not move them (same kinematics), and
+    the pull is faster so that the break comes after tens of steps instead of 10^5."""
+    wl = workloads.polyhedra_box((2, 1, 1), shapes=("cube",), pitch=1.0, jitter=0.0, periodic=(0, 0, 0), cell_size=2.0)
+    wl.shapes_spec = [workloads.cube_shape(half=0.49, mink=0.01)]
+    pa = wl.particles
+    pa.qw[:], pa.qx[:], pa.qy[:], pa.qz[:] = 1.0, 0.0, 0.0, 0.0
+    for f in ("vx", "vy", "vz", "vrotx", "vroty", "vrotz"):
+        getattr(pa, f)[:] = 0.0
+    pa.radius[:] = np.sqrt(3) * 0.49 + 0.01
+    pa.mass[:] = 1e15
+    pa.inertiax[:] = pa.inertiay[:] = pa.inertiaz[:] = 1e15
+    right = pa.rx > 1.0
+    pa.vx[right] = speed
+    wl.lo, wl.hi = (-2.0, -2.0, -2.0), (4.0, 4.0, 4.0)
+    wl.periodic = (0, 0, 0)
+    wl.gravity = (0.0, 0.0, 0.0)
+    wl.dt = dt
+    wl.params = dict(kn=1e4, kt=8e3, kr=0.0, mu=0.1, damp_rate=0.87, fc=0.0, dncut=0.0, gamma=0.0)
+    wl.params_driver = wl.params
+    wl.name = "traction"
+    return wl, [dict(kn=1e3, kt=8e2, damp_rate=0.87, mode=0, crit1=gc, crit2=0.0)]
+
+
+@pytest.mark.parametrize("gc", [5e-3, 2e-2, 8e-2])
+def test_traction_deck_breaks_at_the_analytic_displacement(gc):
+    """Known answer from the source: 4 bonds of weight 1/4 give the interface the stiffness kn, En = kn dn^2 / 2, and the interface
+    breaks when En exceeds 2 A Gc with A = 0.98^2 (stick_polyhedra.cpp:290-296, inner_bond_force.hpp:50-68), i.e. at
+    dn = sqrt(4 A Gc / kn).  (The table in the deck's README quotes half of that, i.e. an interface stiffness of 4 kn — bond weight 1 —
+    which is not what the v1.2.2 source computes; the oracle follows the source.)"""
+    wl, ibp = traction_pair(gc)
+    e = wl.setup(OracleEngine(OracleLibrary(), wl.config()))
+    e.set_inner_bond_params(1, ibp)
+    e.update_particle_neighbors(wl.rcut_inc, True)
+    e.stick_polyhedra_ids(1.5e-4, wl.particles.id, np.zeros(wl.particles.n))
+    b = e.export_inner_bonds()
+    assert len(b) == 4 and np.allclose(b["weight"], 0.25) and np.allclose(b["criteria_1"], 2 * 0.98 ** 2 * gc, rtol=1e-12)
+    e.update_particle_neighbors(wl.rcut_inc, True)
+    assert e.update_interfaces() == 1
+    dn_fail = np.sqrt(4 * 0.98 ** 2 * gc / 1e3)
+    step_dn = 10.0 * wl.dt
+    broke_at = None
+    for it in range(int(dn_fail / step_dn) + 10):
+        if step_block(e, wl):
+            broke_at = it
+            break
+        dn, _, fn, _ = e.get_inner_bond_state(4)
+        # the normal force of the interface grows linearly with the opening (elastic part kn * dn / 4 per bond + the viscous term)
+        assert np.allclose(dn, dn[0]) and abs(dn[0] - (it + 1) * step_dn) < 1e-9
+    # the criterion is evaluated at the start of step k on the energies of step k-1, where dn = k * step_dn
+    assert broke_at is not None and abs(broke_at * step_dn - dn_fail) <= step_dn, (broke_at, dn_fail / step_dn)
+
+
+@pytest.mark.gpu
+def test_gpu_traction_deck(product_lib):
+    """the same known answer through the C ABI: bonds created by edb_stick_polyhedra, the interface breaks at dn = sqrt(4 A Gc / kn)"""
+    from exadem_b200 import Engine
+    gc = 2e-2
+    wl, ibp = traction_pair(gc)
+    e = wl.setup(Engine(product_lib, wl.config()))
+    e.set_inner_bond_params(1, ibp)
+    e.update_particle_neighbors(wl.rcut_inc, True)
+    e.stick_polyhedra_ids(1.5e-4, wl.particles.id, np.zeros(wl.particles.n))
+    b = e.export_inner_bonds()
+    assert len(b) == 4 and np.allclose(b["weight"], 0.25) and np.allclose(b["criteria_1"], 2 * 0.98 ** 2 * gc, rtol=1e-12)
+    e.update_particle_neighbors(wl.rcut_inc, True)
+    assert e.update_interfaces() == 1
+    dn_fail, step_dn = np.sqrt(4 * 0.98 ** 2 * gc / 1e3), 10.0 * wl.dt
+    broke_at = None
+    for it in range(int(dn_fail / step_dn) + 10):
+        if step_block(e, wl):
+            broke_at = it
+            break
+    assert broke_at is not None and abs(broke_at * step_dn - dn_fail) <= step_dn, (broke_at, dn_fail / step_dn)
+    assert len(e.export_inner_bonds()) == 0      # the broken bonds left wave 13 at the rebuild
