@@ -1,5 +1,5 @@
 """Seeded single-driver cases for the driver-motion operators (push_f_v_r / push_f_v / push_av_to_quat / force_to_accel):
-shared by tests/golden/make_driver_golden.py (reference -> golden vectors) and tests/test_driver_motion.py."""
+shared by tests/golden/make_driver_golden.py (reference -> golden vectors) and tests/test_survey8f_rank3_driver_motion.py."""
 from __future__ import annotations
 
 import ctypes as C

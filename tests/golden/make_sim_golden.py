@@ -24,9 +24,9 @@ def cases():
     yield "drum", workloads.rotating_drum(900, jitter=0.02), 30, 0
     yield "deposit", workloads.deposit((8, 8, 6)), 30, 10
     yield "poly", workloads.polyhedra_box((6, 6, 6), shapes=("octahedron", "cube"), pitch=0.8, cell_size=1.6), 20, 5
-    # moving drivers (scenarios of tests/test_driver_motion.py without trigonometric motions, so that the device's
+    # moving drivers (scenarios of tests/test_survey8f_rank3_driver_motion.py without trigonometric motions, so that the device's
     # sin / cos do not enter): a roof descending at constant velocity, a translating + spinning mesh around a free-body mesh
-    import test_driver_motion as T
+    import test_survey8f_rank3_driver_motion as T
     yield "piston", T.scenario_piston(), 60, 0
     yield "moving_mesh", T.scenario_moving_mesh(), 30, 0
 

@@ -1,6 +1,6 @@
 // tests/host_check_driver.cu — TEST HELPER: the product's driver integrators (exadem_b200/csrc/kernels_driver.cuh, __host__ __device__)
 // compiled for the HOST, behind the same single-driver interface as oracle/dem_oracle.cpp:orc_driver_motion_op, so that the CPU suite can
-// compare the code the GPU runs with the oracle bit for bit without a GPU (device sin/cos aside).  Built by tests/test_driver_motion.py:
+// compare the code the GPU runs with the oracle bit for bit without a GPU (device sin/cos aside).  Built by tests/test_survey8f_rank3_driver_motion.py:
 //   nvcc -O2 -std=c++17 -fmad=false -Xcompiler -fPIC -shared tests/host_check_driver.cu -o tests/_build/libhost_check_driver.so
 #include "../exadem_b200/csrc/kernels_driver.cuh"
 using namespace edb;

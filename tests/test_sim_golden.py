@@ -36,8 +36,12 @@ def test_oracle_reproduces_its_golden_runs(oracle_lib, case):
     compare(name, run(OracleEngine, oracle_lib, wl, steps, reb), 1e-13)
 
 
+# the two moving-driver runs were added after the round's last GPU run: their GPU form lives in tests/test_zz_gpu_added_after_last_run.py
+GPU_VERIFIED = ("drum", "deposit", "poly")
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", list(cases()), ids=lambda c: c[0])
+@pytest.mark.parametrize("case", [c for c in cases() if c[0] in GPU_VERIFIED], ids=lambda c: c[0])
 def test_cuda_path_matches_golden_runs(product_lib, case):
     from exadem_b200 import Engine
     name, wl, steps, reb = case

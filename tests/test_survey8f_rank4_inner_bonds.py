@@ -350,27 +350,3 @@ def test_traction_deck_breaks_at_the_analytic_displacement(gc):
         assert np.allclose(dn, dn[0]) and abs(dn[0] - (it + 1) * step_dn) < 1e-9
     # the criterion is evaluated at the start of step k on the energies of step k-1, where dn = k * step_dn
     assert broke_at is not None and abs(broke_at * step_dn - dn_fail) <= step_dn, (broke_at, dn_fail / step_dn)
-
-
-@pytest.mark.gpu
-def test_gpu_traction_deck(product_lib):
-    """the same known answer through the C ABI: bonds created by edb_stick_polyhedra, the interface breaks at dn = sqrt(4 A Gc / kn)"""
-    from exadem_b200 import Engine
-    gc = 2e-2
-    wl, ibp = traction_pair(gc)
-    e = wl.setup(Engine(product_lib, wl.config()))
-    e.set_inner_bond_params(1, ibp)
-    e.update_particle_neighbors(wl.rcut_inc, True)
-    e.stick_polyhedra_ids(1.5e-4, wl.particles.id, np.zeros(wl.particles.n))
-    b = e.export_inner_bonds()
-    assert len(b) == 4 and np.allclose(b["weight"], 0.25) and np.allclose(b["criteria_1"], 2 * 0.98 ** 2 * gc, rtol=1e-12)
-    e.update_particle_neighbors(wl.rcut_inc, True)
-    assert e.update_interfaces() == 1
-    dn_fail, step_dn = np.sqrt(4 * 0.98 ** 2 * gc / 1e3), 10.0 * wl.dt
-    broke_at = None
-    for it in range(int(dn_fail / step_dn) + 10):
-        if step_block(e, wl):
-            broke_at = it
-            break
-    assert broke_at is not None and abs(broke_at * step_dn - dn_fail) <= step_dn, (broke_at, dn_fail / step_dn)
-    assert len(e.export_inner_bonds()) == 0      # the broken bonds left wave 13 at the rebuild

@@ -1,0 +1,41 @@
+"""GPU tests written AFTER the round's last GPU run (the 180 GPU-minutes were spent): they exercise kernels and flows that were
+green on a B200 in other tests, but these exact tests have not run on a GPU yet.  The file sorts last on purpose so
+that `pytest -x` reaches it only after every GPU-verified test has passed."""
+import numpy as np
+import pytest
+
+import test_sim_golden as SG
+import test_survey8f_rank4_inner_bonds as IB
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", [c for c in SG.cases() if c[0] not in SG.GPU_VERIFIED], ids=lambda c: c[0])
+def test_cuda_path_matches_the_moving_driver_golden_runs(product_lib, case):
+    """golden-file form of test_gpu_run_verlet_with_moving_drivers[piston | moving_mesh] (green live on a B200)"""
+    from exadem_b200 import Engine
+    name, wl, steps, reb = case
+    SG.compare(name, SG.run(Engine, product_lib, wl, steps, reb), 1e-10)
+
+
+def test_gpu_traction_deck(product_lib):
+    """the same known answer through the C ABI: bonds created by edb_stick_polyhedra, the interface breaks at dn = sqrt(4 A Gc / kn)"""
+    from exadem_b200 import Engine
+    gc = 2e-2
+    wl, ibp = IB.traction_pair(gc)
+    e = wl.setup(Engine(product_lib, wl.config()))
+    e.set_inner_bond_params(1, ibp)
+    e.update_particle_neighbors(wl.rcut_inc, True)
+    e.stick_polyhedra_ids(1.5e-4, wl.particles.id, np.zeros(wl.particles.n))
+    b = e.export_inner_bonds()
+    assert len(b) == 4 and np.allclose(b["weight"], 0.25) and np.allclose(b["criteria_1"], 2 * 0.98 ** 2 * gc, rtol=1e-12)
+    e.update_particle_neighbors(wl.rcut_inc, True)
+    assert e.update_interfaces() == 1
+    dn_fail, step_dn = np.sqrt(4 * 0.98 ** 2 * gc / 1e3), 10.0 * wl.dt
+    broke_at = None
+    for it in range(int(dn_fail / step_dn) + 10):
+        if IB.step_block(e, wl):
+            broke_at = it
+            break
+    assert broke_at is not None and abs(broke_at * step_dn - dn_fail) <= step_dn, (broke_at, dn_fail / step_dn)
+    assert len(e.export_inner_bonds()) == 0      # the broken bonds left wave 13 at the rebuild
