@@ -1401,6 +1401,14 @@ static Inter mk_inter(const unsigned long long* r) {
 }
 int orc_pair_less(const unsigned long long* a, const unsigned long long* b) { return key_of(mk_inter(a)) < key_of(mk_inter(b)) ? 1 : 0; }
 int orc_pair_equal(const unsigned long long* a, const unsigned long long* b) { return key_of(mk_inter(a)) == key_of(mk_inter(b)) ? 1 : 0; }
+// face areas through the flat shape arrays (mirrored by oracle/ref_math.cpp:ref_face_areas)
+void orc_face_areas(int nv, const double* verts, int ne, const int* edges, int nf, const int* faces_stream, int faces_len, double h, double* out) {
+  edb_shape sh{};
+  sh.nv = nv; sh.ne = ne; sh.nf = nf; sh.faces_len = faces_len; sh.vertices = verts; sh.edges = edges; sh.faces = faces_stream;
+  std::vector<Shape> v;
+  load_shapes(v, 1, &sh);
+  for (int f = 0; f < nf; f++) out[f] = face_area(v[0], f, h);
+}
 int orc_interface_breaks(int mode, double c1, double c2, const double* en, const double* et, const double* dn, const double* fn3, uint64_t size) {
   std::vector<v3> fn(size);
   for (uint64_t k = 0; k < size; k++) fn[k] = V3(fn3 + 3 * k);

@@ -253,4 +253,11 @@ static exaDEM::InteractionPair mk_pair(const unsigned long long* r) {
 int ref_pair_less(const unsigned long long* a, const unsigned long long* b) { return mk_pair(a) < mk_pair(b) ? 1 : 0; }
 int ref_pair_equal(const unsigned long long* a, const unsigned long long* b) { return mk_pair(a) == mk_pair(b) ? 1 : 0; }
 
+// face areas of a shape (shape.hpp:673-697 compute_face_areas, :359-362 get_face_area(i, h)) — input of the rupture criterion
+void ref_face_areas(int nv, const double* verts, int ne, const int* edges, int nf, const int* faces_stream, int faces_len, double h, double* out) {
+  exaDEM::shape s = make_shape(nv, verts, ne, edges, nf, faces_stream, faces_len, 0.0);
+  s.compute_face_areas();
+  for (int f = 0; f < nf; f++) out[f] = s.get_face_area(f, h);
+}
+
 }  // extern "C"

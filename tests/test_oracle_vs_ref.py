@@ -227,3 +227,30 @@ def test_interaction_pair_order_and_equality():
         n_less += l_ref
         n_eq += e_ref
     assert n_less > 5000 and n_eq > 20
+
+
+def test_face_areas():
+    """shape::compute_face_areas / get_face_area(i, h) (shape.hpp:673-697, :359-362) — the area that enters the rupture criterion of the
+    inner bonds (stick_polyhedra.cpp:290-305) — against the oracle's fan triangulation, on the octahedron, the cube and random
+    distortions of them."""
+    import ctypes as C
+    import numpy as np
+    from exadem_b200 import capi, workloads
+    from oracle_binding import OracleLibrary, ref_math
+    ref = ref_math()
+    if ref is None or not hasattr(ref, "ref_face_areas"):
+        import pytest
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    orc = OracleLibrary().dll
+    rng = np.random.default_rng(17)
+    for spec in (workloads.OCTAHEDRON, workloads.cube_shape(), workloads.cube_shape(0.49, 0.01)):
+        for rep in range(20):
+            v = np.asarray(spec["vertices"], dtype=np.float64) * (1.0 + (0.2 * rng.normal(size=(len(spec["vertices"]), 3)) if rep else 0.0))
+            s = capi.make_shape(v, spec["edges"], spec["faces"], spec["obb"], spec["radius"])
+            h = float(rng.uniform(0.5, 2.0))
+            a, b = np.zeros(s.nf), np.zeros(s.nf)
+            for fn, out in ((ref.ref_face_areas, a), (orc.orc_face_areas, b)):
+                fn.restype = None
+                fn(C.c_int(s.nv), s.vertices, C.c_int(s.ne), s.edges, C.c_int(s.nf), s.faces, C.c_int(s.faces_len), C.c_double(h),
+                   out.ctypes.data_as(C.POINTER(C.c_double)))
+            assert np.array_equal(a, b) and (a > 0).all()
