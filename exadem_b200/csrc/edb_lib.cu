@@ -1714,6 +1714,39 @@ static uint64_t run_verlet_moving(edb_context* c, double dt, const double g[3], 
   return nb;
 }
 
+static void bond_force_launch(edb_context* c, double dt);
+static uint64_t interface_criterion_launch(edb_context* c);
+static void bond_friction_updater_launch(edb_context* c);
+// The macro of a fragmentation deck (config_fragmentation.msp:11-41 inside check_and_update_particles + compute_force with
+// inner_bond_polyhedron): operator by operator, one host read per step (interfaces broken | particles moved).  A broken interface caps
+// its friction and forces the neighbour rebuild (displ_or_break), where its bonds turn into vertex-vertex contacts.
+static uint64_t run_verlet_bonds(edb_context* c, double dt, const double g[3], double rcut_inc, int symetric, int nsteps, int rebuild_every) {
+  if (c->drivers_moving) throw StateError{EDB_ERR_STATE, "edb_run_verlet: inner bonds together with moving drivers are not supported yet"};
+  if (c->cfg.nranks > 1) throw StateError{EDB_ERR_STATE, "edb_run_verlet: inner bonds on several ranks are not supported yet"};
+  uint64_t nb = 0;
+  const double thr = 0.5 * rcut_inc;
+  for (int it = 0; it < nsteps; it++) {
+    prolog(c, dt);
+    const uint64_t broken = interface_criterion_launch(c);
+    if (broken) bond_friction_updater_launch(c);
+    bool rb = broken > 0;
+    if (rebuild_every > 0) rb = rb || ((it + 1) % rebuild_every) == 0;
+    else if (rebuild_every == 0) rb = rb || displ_over(c, thr) > 0;
+    if (rb) { rebuild(c, rcut_inc, symetric); nb++; }   // bonds follow their particles, broken ones retire (update_interfaces inside bonds_upload)
+    else { ghost_refresh(c, false); compute_vertices(c); }
+    LAUNCH(c, k_reset_fm, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal);
+    LAUNCH(c, k_gravity, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, g[0], g[1], g[2]);
+    bond_force_launch(c, dt);
+    contact_waves(c, dt);
+    gather<0>(c, nullptr, dt);
+    LAUNCH(c, k_force_to_accel, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal);
+    LAUNCH(c, k_epilog<2>, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, dt * 0.5);
+    c->ctr.particle_steps += c->nreal;
+    c->physical_time += dt;
+  }
+  return nb;
+}
+
 static void ensure_system_mass(edb_context* c) {
   if (c->have_system_mass) return;
   if (c->cfg.nranks > 1) throw StateError{EDB_ERR_STATE, "moving drivers on several ranks: call edb_set_system_mass first"};
@@ -1757,6 +1790,11 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
   API_BEGIN(c)
   uint64_t nb = 0;
   if (!c->have_prev) { rebuild(c, rcut_inc, symetric); }
+  if (!c->h_bonds.empty()) {
+    nb = run_verlet_bonds(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every);
+    if (n_rebuilds) *n_rebuilds = nb;
+    return EDB_OK;
+  }
   const bool mv = c->drivers_moving;
   if (mv && c->env_drivers_unfused) {
     nb = run_verlet_moving(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every);
@@ -2342,10 +2380,10 @@ extern "C" int edb_stick_polyhedra(edb_context* c, double sticking_threshold, ui
   bonds_upload(c);
   API_END(c)
 }
+static void bond_friction_updater_launch(edb_context* c);
 extern "C" int edb_broken_interface_friction_updater(edb_context* c) {
   API_BEGIN(c)
-  if (c->n_interfaces == 0 || !c->bonds_on_device) return EDB_OK;
-  LAUNCH(c, k_bond_friction_updater, nblk(c->n_interfaces), BLK, 0, bond_view(c), c->b_itf.p, c->n_interfaces, c->b_itf_broken.p, view(c->pa), c->prm);
+  bond_friction_updater_launch(c);
   API_END(c)
 }
 extern "C" int edb_set_inner_bond_params(edb_context* c, int32_t ng, const edb_inner_bond_params* p) {
@@ -2381,27 +2419,36 @@ extern "C" int edb_update_interfaces(edb_context* c, uint64_t* n_interfaces) {
   if (n_interfaces) *n_interfaces = c->n_interfaces;
   API_END(c)
 }
-extern "C" int edb_inner_bond_polyhedron(edb_context* c, double dt) {
-  API_BEGIN(c)
+static void bond_force_launch(edb_context* c, double dt) {
   const uint32_t n = (uint32_t)c->h_bonds.size();
-  if (n == 0) return EDB_OK;
+  if (n == 0) return;
   if (!c->bonds_on_device) throw StateError{EDB_ERR_STATE, "inner_bond_polyhedron before edb_import_inner_bonds / edb_update_interfaces"};
   if (!c->ibp_groups) throw StateError{EDB_ERR_STATE, "inner_bond_polyhedron before edb_set_inner_bond_params"};
   if (c->S.nvmax <= 0 || !c->vert.p) throw StateError{EDB_ERR_STATE, "inner_bond_polyhedron needs the world vertices (edb_compute_vertices)"};
   LAUNCH(c, k_bond_force, nblk(n), BLK, 0, bond_view(c), view(c->pa), c->vert.p, c->S, c->d_ibp.p, c->ibp_groups, dt);
   LAUNCH(c, k_bond_gather, nblk(c->n_bond_particles), BLK, 0, bond_view(c), view(c->pa), c->b_plist.p, c->b_inc_off.p, c->b_inc.p, c->n_bond_particles);
   c->ctr.interaction_updates += n;
-  API_END(c)
 }
-extern "C" int edb_apply_interface_fracture_criterion(edb_context* c, uint64_t* n_broken) {
-  API_BEGIN(c)
-  *n_broken = 0;
-  if (c->n_interfaces == 0) return EDB_OK;
+static uint64_t interface_criterion_launch(edb_context* c) {
+  if (c->n_interfaces == 0) return 0;
   CK(cudaMemsetAsync(c->d_flag, 0, 8, c->st));
   LAUNCH(c, k_interface_criterion, nblk(c->n_interfaces), BLK, 0, bond_view(c), c->b_itf.p, c->n_interfaces, c->b_itf_broken.p, c->d_flag);
   CK(cudaMemcpyAsync(c->h_flag, c->d_flag, 8, cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
-  *n_broken = c->h_flag[0];
+  return c->h_flag[0];
+}
+static void bond_friction_updater_launch(edb_context* c) {
+  if (c->n_interfaces == 0 || !c->bonds_on_device) return;
+  LAUNCH(c, k_bond_friction_updater, nblk(c->n_interfaces), BLK, 0, bond_view(c), c->b_itf.p, c->n_interfaces, c->b_itf_broken.p, view(c->pa), c->prm);
+}
+extern "C" int edb_inner_bond_polyhedron(edb_context* c, double dt) {
+  API_BEGIN(c)
+  bond_force_launch(c, dt);
+  API_END(c)
+}
+extern "C" int edb_apply_interface_fracture_criterion(edb_context* c, uint64_t* n_broken) {
+  API_BEGIN(c)
+  *n_broken = interface_criterion_launch(c);
   API_END(c)
 }
 extern "C" int edb_get_inner_bond_state(edb_context* c, double* dn, double* cp, double* fn, double* ft) {

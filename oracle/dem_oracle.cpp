@@ -1208,6 +1208,30 @@ static double mass_sum(const Sim& s) { double m = 0; for (size_t p = 0; p < s.nr
 int orc_run_verlet(orc_sim* h, double dt, const double* g, double rcut_inc, int32_t symetric, int32_t nsteps, int32_t rebuild_every, uint64_t* n_rebuilds) {
   Sim& s = *(Sim*)h;
   uint64_t nb = 0;
+  if (!s.bonds.empty()) {
+    // fragmentation deck (config_fragmentation.msp:11-41 inside check_and_update_particles; compute_force with inner_bond_polyhedron):
+    // the fracture criterion is evaluated on the state of the previous step; a broken interface caps its friction and forces the rebuild
+    for (int it = 0; it < nsteps; it++) {
+      prolog(s, dt);
+      const uint64_t broken = apply_interface_fracture_criterion(s);
+      if (broken) broken_interface_friction_updater(s);
+      bool rb = broken > 0;
+      if (rebuild_every > 0) rb = rb || ((it + 1) % rebuild_every) == 0;
+      else if (rebuild_every == 0) rb = rb || displ_over(s, 0.5 * rcut_inc) > 0;
+      if (rb) { rebuild(s, rcut_inc, symetric); update_interfaces(s); nb++; }
+      else { ghost_refresh(s, false); compute_vertices(s); }
+      reset_fm(s);
+      gravity(s, g);
+      inner_bond_force(s, dt);
+      contact_all(s, dt);
+      force_to_accel(s);
+      epilog(s, dt);
+      s.particle_steps += s.nreal;
+      s.physical_time += dt;
+    }
+    if (n_rebuilds) *n_rebuilds = nb;
+    return 0;
+  }
   const bool moving = drivers_move(s);
   if (moving && !s.have_system_mass) { s.system_mass = mass_sum(s); s.have_system_mass = true; }
   if (moving && s.drivers_backup.empty()) s.drivers_backup = s.drivers;

@@ -350,3 +350,18 @@ def test_traction_deck_breaks_at_the_analytic_displacement(gc):
         assert np.allclose(dn, dn[0]) and abs(dn[0] - (it + 1) * step_dn) < 1e-9
     # the criterion is evaluated at the start of step k on the energies of step k-1, where dn = k * step_dn
     assert broke_at is not None and abs(broke_at * step_dn - dn_fail) <= step_dn, (broke_at, dn_fail / step_dn)
+
+
+def test_run_verlet_with_inner_bonds_on_the_oracle():
+    """run_verlet runs the fragmentation macro when bonds exist: identical to the same steps driven operator by operator"""
+    from parity import bit_identical
+    lib = OracleLibrary()
+    wl, ibp = glued_block()
+    engines = [wl.setup(OracleEngine(lib, wl.config())) for _ in range(2)]
+    setup_block(engines, wl, ibp)
+    a, ops = engines
+    nb = a.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 20, -1)
+    broken = sum(step_block(ops, wl) for _ in range(20))
+    assert nb == 1 and broken == 16
+    assert all(bit_identical(a.download_particles(), ops.download_particles()).values())
+    compare_bonds(a, ops, rtol=0.0)

@@ -39,3 +39,24 @@ def test_gpu_traction_deck(product_lib):
             break
     assert broke_at is not None and abs(broke_at * step_dn - dn_fail) <= step_dn, (broke_at, dn_fail / step_dn)
     assert len(e.export_inner_bonds()) == 0      # the broken bonds left wave 13 at the rebuild
+
+
+def test_gpu_run_verlet_with_inner_bonds(product_lib, oracle_lib):
+    """edb_run_verlet runs the fragmentation macro (criterion -> friction cap -> rebuild on a break, inner_bond_polyhedron in
+    compute_force) when bonds exist: against the oracle, and against the same steps driven operator by operator."""
+    from exadem_b200 import Engine
+    from oracle_binding import OracleEngine
+    from parity import compare_interaction_sets, compare_particles
+    wl, ibp = IB.glued_block()
+    engines = [wl.setup(Engine(product_lib, wl.config())), wl.setup(OracleEngine(oracle_lib, wl.config())),
+               wl.setup(Engine(product_lib, wl.config()))]
+    IB.setup_block(engines, wl, ibp)
+    gpu, cpu, ops = engines
+    nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 20, -1) for e in (gpu, cpu)]
+    broken = sum(IB.step_block(ops, wl) for _ in range(20))
+    assert nb[0] == nb[1] == 1 and broken == 16      # the top layer tears off once; that break is the only rebuild
+    IB.compare_bonds(gpu, cpu)
+    compare_particles(gpu.download_particles(), cpu.download_particles(), rtol=1e-10)
+    compare_interaction_sets(gpu.export_interactions(), cpu.export_interactions(), payload_rtol=1e-10)
+    same = __import__("parity").bit_identical(gpu.download_particles(), ops.download_particles())
+    assert all(same.values()), same
