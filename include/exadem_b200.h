@@ -265,12 +265,13 @@ typedef struct edb_sim_state {
 } edb_sim_state;
 int edb_simulation_state(edb_context*, int32_t symetric, edb_sim_state* out);
 
-/* ---- inner bonds (fragmentation, wave 13), SURVEY 8(f) rank 4.  Bonds are created by edb_stick_polyhedra or enter through
- * edb_import_inner_bonds (the fragmentation dump reader stays on the host side of the binding).  While a bond holds, the polyhedron contact enumeration ignores the pair it glues
- * (InteractionManager::update_ignore_interaction).  With bonds present edb_run_verlet runs the fragmentation macro (fracture criterion on the
- * previous step's energies, friction cap + neighbour rebuild on a break, inner_bond_polyhedron inside compute_force) operator by
- * operator.  NOT built yet: bonds across periodic / brick boundaries (OwnerGhost bonds, several ranks), bonds together with moving
- * drivers inside edb_run_verlet. -------------------------------------------------------------------------------------------------- */
+/* ---- inner bonds (fragmentation, wave 13), SURVEY 8(f) rank 4 ---------------------------------------------------------------
+ * Bonds are created by edb_stick_polyhedra or enter through edb_import_inner_bonds (the fragmentation dump reader stays on the host
+ * side of the binding).  While a bond holds, the polyhedron contact enumeration ignores the pair it glues
+ * (InteractionManager::update_ignore_interaction).  With bonds present edb_run_verlet runs the fragmentation macro (fracture
+ * criterion on the previous step's energies, friction cap + neighbour rebuild on a break, inner_bond_polyhedron inside
+ * compute_force) operator by operator.  NOT built yet: bonds across periodic / brick boundaries (OwnerGhost bonds, several ranks),
+ * bonds together with moving drivers inside edb_run_verlet. */
 int edb_set_inner_bond_params(edb_context*, int32_t n_groups, const edb_inner_bond_params* ibp /* n_groups^2 */);
 int edb_import_inner_bonds(edb_context*, const edb_inner_bond* in, uint64_t n);
 /* [stick_polyhedra] src/polyhedron/stick_polyhedra.cpp:88-360 on the device: glues the matching faces of neighbouring polyhedra of the
