@@ -1649,6 +1649,9 @@ static void trigger_standalone(edb_context* c, int slot, double thr) {
 // memory, one step behind the launch front) afterwards.  When the flag says "rebuild", the gated kernels have done nothing and
 // the step is enqueued again behind the rebuild.  The GPU never idles on the host in the common no-rebuild case.
 
+static void bond_force_launch(edb_context* c, double dt);
+static uint64_t interface_criterion_launch(edb_context* c);
+static void bond_friction_updater_launch(edb_context* c);
 // The same macro with moving drivers (edb_set_driver_motions): operator by operator in the reference's order
 // (config_numerical_schemes.msp:12-29, check_and_update_particles of config_move_particles.msp:186-189), drivers integrated on the
 // device.  One host read of the rebuild trigger per step (particle_displ_over | driver_displ_over, all-reduced).
@@ -1677,6 +1680,11 @@ static uint64_t run_verlet_moving(edb_context* c, double dt, const double g[3], 
     driver_op(c, DOP_PUSH_F_V_R, t, dt, 0.0);
     driver_op(c, DOP_PUSH_F_V, 0.0, 0.5 * dt, 0.0);
     driver_op(c, DOP_PUSH_AV_TO_QUAT, t, dt, 0.0);
+    // fragmentation operators when bonds exist (config_fragmentation.msp:11-41): criterion on the previous step's energies, a broken
+    // interface caps its friction and forces the rebuild (displ_or_break)
+    const bool bonds = !c->h_bonds.empty();
+    const uint64_t broken = bonds ? interface_criterion_launch(c) : 0;
+    if (broken) bond_friction_updater_launch(c);
     bool rb;
     if (rebuild_every > 0) rb = ((it + 1) % rebuild_every) == 0;
     else if (rebuild_every < 0) rb = false;
@@ -1691,6 +1699,7 @@ static uint64_t run_verlet_moving(edb_context* c, double dt, const double g[3], 
       }
       rb = over > 0;
     }
+    rb = rb || broken > 0;
     if (rb) {
       backup_drivers(c);
       driver_vertices(c, false);       // ghost_full_update -> compute_all_vertices -> driver_vertices
@@ -1703,25 +1712,31 @@ static uint64_t run_verlet_moving(edb_context* c, double dt, const double g[3], 
     }
     driver_op(c, DOP_RESET_FORCE, 0.0, 0.0, 0.0);
     driver_gravity_launch(c, g);       // gravity_force also acts on the PARTICLE RShape drivers (gravity_force.cu:72-83)
-    contact_waves(c, dt);
-    gather<1>(c, g, dt);               // reset + gravity + contact wrenches + force_to_accel + epilog of the particles
+    if (!bonds) {
+      contact_waves(c, dt);
+      gather<1>(c, g, dt);             // reset + gravity + contact wrenches + force_to_accel + epilog of the particles
+    } else {                           // compute_force with inner_bond_polyhedron: the particle operators one by one
+      LAUNCH(c, k_reset_fm, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal);
+      LAUNCH(c, k_gravity, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, g[0], g[1], g[2]);
+      bond_force_launch(c, dt);
+      contact_waves(c, dt);
+      gather<0>(c, nullptr, dt);
+      LAUNCH(c, k_force_to_accel, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal);
+    }
     driver_force_reduce(c);            // force_to_accel_driver: reaction sums, then Ball::f_ra / force_to_accel
     driver_op(c, DOP_FORCE_TO_ACCEL, 0.0, dt, c->system_mass);
     driver_op(c, DOP_PUSH_F_V, 0.0, 0.5 * dt, 0.0);
+    if (bonds) LAUNCH(c, k_epilog<2>, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, dt * 0.5);
     c->ctr.particle_steps += c->nreal;
     c->physical_time += dt;
   }
   return nb;
 }
 
-static void bond_force_launch(edb_context* c, double dt);
-static uint64_t interface_criterion_launch(edb_context* c);
-static void bond_friction_updater_launch(edb_context* c);
 // The macro of a fragmentation deck (config_fragmentation.msp:11-41 inside check_and_update_particles + compute_force with
 // inner_bond_polyhedron): operator by operator, one host read per step (interfaces broken | particles moved).  A broken interface caps
 // its friction and forces the neighbour rebuild (displ_or_break), where its bonds turn into vertex-vertex contacts.
 static uint64_t run_verlet_bonds(edb_context* c, double dt, const double g[3], double rcut_inc, int symetric, int nsteps, int rebuild_every) {
-  if (c->drivers_moving) throw StateError{EDB_ERR_STATE, "edb_run_verlet: inner bonds together with moving drivers are not supported yet"};
   if (c->cfg.nranks > 1) throw StateError{EDB_ERR_STATE, "edb_run_verlet: inner bonds on several ranks are not supported yet"};
   uint64_t nb = 0;
   const double thr = 0.5 * rcut_inc;
@@ -1791,7 +1806,9 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
   uint64_t nb = 0;
   if (!c->have_prev) { rebuild(c, rcut_inc, symetric); }
   if (!c->h_bonds.empty()) {
-    nb = run_verlet_bonds(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every);
+    if (c->cfg.nranks > 1) throw StateError{EDB_ERR_STATE, "edb_run_verlet: inner bonds on several ranks are not supported yet"};
+    nb = c->drivers_moving ? run_verlet_moving(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every)
+                           : run_verlet_bonds(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every);
     if (n_rebuilds) *n_rebuilds = nb;
     return EDB_OK;
   }

@@ -270,8 +270,8 @@ int edb_simulation_state(edb_context*, int32_t symetric, edb_sim_state* out);
  * side of the binding).  While a bond holds, the polyhedron contact enumeration ignores the pair it glues
  * (InteractionManager::update_ignore_interaction).  With bonds present edb_run_verlet runs the fragmentation macro (fracture
  * criterion on the previous step's energies, friction cap + neighbour rebuild on a break, inner_bond_polyhedron inside
- * compute_force) operator by operator.  NOT built yet: bonds across periodic / brick boundaries (OwnerGhost bonds, several ranks),
- * bonds together with moving drivers inside edb_run_verlet. */
+ * compute_force) operator by operator, together with the driver operators when drivers move.  NOT built yet: bonds across periodic /
+ * brick boundaries (OwnerGhost bonds, several ranks). */
 int edb_set_inner_bond_params(edb_context*, int32_t n_groups, const edb_inner_bond_params* ibp /* n_groups^2 */);
 int edb_import_inner_bonds(edb_context*, const edb_inner_bond* in, uint64_t n);
 /* [stick_polyhedra] src/polyhedron/stick_polyhedra.cpp:88-360 on the device: glues the matching faces of neighbouring polyhedra of the

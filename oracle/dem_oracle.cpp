@@ -1206,53 +1206,36 @@ static uint64_t driver_displ_over(Sim& s, double thr) {
 static double mass_sum(const Sim& s) { double m = 0; for (size_t p = 0; p < s.nreal; p++) m += s.mass[p]; return m; }
 
 int orc_run_verlet(orc_sim* h, double dt, const double* g, double rcut_inc, int32_t symetric, int32_t nsteps, int32_t rebuild_every, uint64_t* n_rebuilds) {
+  // numerical_scheme_verlet_macro (config_numerical_schemes.msp:6-30) with, when present, the driver operators (:13-15,17,23-24) and the
+  // fragmentation operators (config_fragmentation.msp:11-41 inside check_and_update_particles; inner_bond_polyhedron in compute_force):
+  // the fracture criterion is evaluated on the state of the previous step; a broken interface caps its friction and forces the rebuild
   Sim& s = *(Sim*)h;
   uint64_t nb = 0;
-  if (!s.bonds.empty()) {
-    // fragmentation deck (config_fragmentation.msp:11-41 inside check_and_update_particles; compute_force with inner_bond_polyhedron):
-    // the fracture criterion is evaluated on the state of the previous step; a broken interface caps its friction and forces the rebuild
-    for (int it = 0; it < nsteps; it++) {
-      prolog(s, dt);
-      const uint64_t broken = apply_interface_fracture_criterion(s);
-      if (broken) broken_interface_friction_updater(s);
-      bool rb = broken > 0;
-      if (rebuild_every > 0) rb = rb || ((it + 1) % rebuild_every) == 0;
-      else if (rebuild_every == 0) rb = rb || displ_over(s, 0.5 * rcut_inc) > 0;
-      if (rb) { rebuild(s, rcut_inc, symetric); update_interfaces(s); nb++; }
-      else { ghost_refresh(s, false); compute_vertices(s); }
-      reset_fm(s);
-      gravity(s, g);
-      inner_bond_force(s, dt);
-      contact_all(s, dt);
-      force_to_accel(s);
-      epilog(s, dt);
-      s.particle_steps += s.nreal;
-      s.physical_time += dt;
-    }
-    if (n_rebuilds) *n_rebuilds = nb;
-    return 0;
-  }
   const bool moving = drivers_move(s);
   if (moving && !s.have_system_mass) { s.system_mass = mass_sum(s); s.have_system_mass = true; }
   if (moving && s.drivers_backup.empty()) s.drivers_backup = s.drivers;
   for (int it = 0; it < nsteps; it++) {
+    const bool bonds = !s.bonds.empty();
     prolog(s, dt);
-    if (moving) {   // config_numerical_schemes.msp:13-15
+    if (moving) {
       push_f_v_r_driver(s, s.physical_time, dt);
       push_f_v_driver(s, 0.5 * dt);
       push_av_to_quat_driver(s, s.physical_time, dt);
     }
-    bool rb;
-    if (rebuild_every > 0) rb = ((it + 1) % rebuild_every) == 0;
-    else if (rebuild_every < 0) rb = false;
-    else rb = displ_over(s, 0.5 * rcut_inc) > 0 || (moving && driver_displ_over(s, 0.5 * rcut_inc) > 0);
+    const uint64_t broken = bonds ? apply_interface_fracture_criterion(s) : 0;
+    if (broken) broken_interface_friction_updater(s);
+    bool rb = broken > 0;   // displ_or_break
+    if (rebuild_every > 0) rb = rb || ((it + 1) % rebuild_every) == 0;
+    else if (rebuild_every == 0) rb = rb || displ_over(s, 0.5 * rcut_inc) > 0 || (moving && driver_displ_over(s, 0.5 * rcut_inc) > 0);
     if (rb) {
       if (moving) { s.drivers_backup = s.drivers; driver_vertices(s); }   // backup_drivers; ghost_full_update -> compute_all_vertices
       rebuild(s, rcut_inc, symetric); nb++;
+      if (bonds) update_interfaces(s);
     } else { ghost_refresh(s, false); compute_vertices(s); if (moving) driver_vertices(s); }
     if (moving) reset_force_driver(s);
     reset_fm(s);
     gravity(s, g);
+    if (bonds) inner_bond_force(s, dt);
     contact_all(s, dt);
     force_to_accel(s);
     if (moving) { force_to_accel_driver(s, s.system_mass); push_f_v_driver(s, 0.5 * dt); }

@@ -365,3 +365,30 @@ def test_run_verlet_with_inner_bonds_on_the_oracle():
     assert nb == 1 and broken == 16
     assert all(bit_identical(a.download_particles(), ops.download_particles()).values())
     compare_bonds(a, ops, rtol=0.0)
+
+
+def block_hit_by_a_ball():
+    """the glued block at rest, a ball driver (LINEAR_MOTION) ramming its top layer from the side: moving drivers and inner bonds in one
+    run — the deck family of example/polyhedra/fragmentation (a bonded sample loaded by a moving driver)"""
+    wl, ibp = glued_block()
+    wl.particles.vx[:] = 0.0
+    wl.particles.vz[:] = 0.0
+    wl.drivers = list(wl.drivers) + [dict(kind=capi.DRIVER_BALL, radius=0.6, center=(-0.6, 1.6, 2.0), vel=(30.0, 0, 0))]
+    wl.motions = [dict(motion_type="STATIONARY")] * (len(wl.drivers) - 1) + [
+        dict(motion_type="LINEAR_MOTION", motion_vector=(1, 0, 0), const_vel=30.0)]
+    ibp[0]["crit1"] = 0.02
+    wl.name = "block_hit_by_a_ball"
+    return wl, ibp
+
+
+def test_bonds_and_moving_driver_on_the_oracle():
+    lib = OracleLibrary()
+    wl, ibp = block_hit_by_a_ball()
+    e = wl.setup(OracleEngine(lib, wl.config()))
+    setup_block([e], wl, ibp)
+    nb = e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 40, 0)
+    b = e.export_inner_bonds()
+    cnt, act = e.interaction_counts()
+    ball = e.get_drivers(len(wl.drivers))[-1]
+    assert nb >= 3 and 0 < len(b) < 416 and b["unbroken"].all()          # interfaces broke one after the other, each forcing a rebuild
+    assert act[6] > 0 and abs(ball["center"][0] - (-0.6 + 40 * 30.0 * wl.dt)) < 1e-12

@@ -60,3 +60,25 @@ def test_gpu_run_verlet_with_inner_bonds(product_lib, oracle_lib):
     compare_interaction_sets(gpu.export_interactions(), cpu.export_interactions(), payload_rtol=1e-10)
     same = __import__("parity").bit_identical(gpu.download_particles(), ops.download_particles())
     assert all(same.values()), same
+
+
+def test_gpu_run_verlet_with_inner_bonds_and_a_moving_driver(product_lib, oracle_lib):
+    """moving drivers and inner bonds in one edb_run_verlet call (operator loop: driver pushes, fracture criterion, rebuild on a break or
+    on a displacement, bond law + contacts, driver reaction) against the oracle"""
+    from exadem_b200 import Engine
+    from oracle_binding import OracleEngine
+    from parity import compare_interaction_sets, compare_particles, field_close
+    wl, ibp = IB.block_hit_by_a_ball()
+    engines = [wl.setup(Engine(product_lib, wl.config())), wl.setup(OracleEngine(oracle_lib, wl.config()))]
+    IB.setup_block(engines, wl, ibp)
+    nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 40, 0) for e in engines]
+    assert nb[0] == nb[1] >= 3
+    gpu, cpu = engines
+    rec = IB.compare_bonds(gpu, cpu)
+    assert 0 < len(rec) < 416
+    compare_particles(gpu.download_particles(), cpu.download_particles(), rtol=1e-10)
+    compare_interaction_sets(gpu.export_interactions(), cpu.export_interactions(), payload_rtol=1e-10)
+    nd = len(wl.drivers)
+    for a, b in zip(gpu.get_drivers(nd), cpu.get_drivers(nd)):
+        for k in ("center", "vel", "forces"):
+            field_close(np.atleast_1d(a[k]), np.atleast_1d(b[k]), 1e-10, f"driver {k}")
