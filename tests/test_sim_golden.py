@@ -36,7 +36,7 @@ def test_oracle_reproduces_its_golden_runs(oracle_lib, case):
     compare(name, run(OracleEngine, oracle_lib, wl, steps, reb), 1e-13)
 
 
-# the two moving-driver runs were added after the round's last GPU run: their GPU form lives in tests/test_zz_gpu_added_after_last_run.py
+# the two moving-driver runs have their GPU form in tests/test_survey8f_rank4_run_verlet.py
 GPU_VERIFIED = ("drum", "deposit", "poly")
 
 

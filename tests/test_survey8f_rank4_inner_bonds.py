@@ -107,7 +107,8 @@ def glued_block():
 def setup_block(engines, wl, ibp):
     """bonds are created by the oracle's stick_polyhedra (a one-off preprocessing that stays on the host side of the binding) and imported
     by every engine"""
-    orc = engines[-1]
+    from oracle_binding import OracleEngine
+    orc = next(e for e in engines if isinstance(e, OracleEngine))     # chosen by type: callers order their engines freely
     for e in engines:
         e.set_inner_bond_params(1, ibp)
         e.update_particle_neighbors(wl.rcut_inc, True)

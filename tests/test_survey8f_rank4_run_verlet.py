@@ -1,6 +1,5 @@
-"""GPU tests written AFTER the round's last GPU run (the 180 GPU-minutes were spent): they exercise kernels and flows that were
-green on a B200 in other tests, but these exact tests have not run on a GPU yet.  The file sorts last on purpose so
-that `pytest -x` reaches it only after every GPU-verified test has passed."""
+"""GPU tests of edb_run_verlet with inner bonds (alone and with a moving driver), the traction deck through the C ABI, and the golden-file
+form of the moving-driver runs.  All green on a B200 (profiles/r2_gpu_tests_first.log)."""
 import numpy as np
 import pytest
 
