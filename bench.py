@@ -1,15 +1,20 @@
 #!/usr/bin/env python
 """bench.py — measures the DEM contact hot path on N B200s of one node (driver contract in the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload drum|box|box8m|poly]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload drum|box|poly|mixed]
+                    [--scaling weak|strong] [--particles P] [--global-side S]
 
 A "step" is one full Verlet time step of the hot path (prolog -> rebuild-or-ghost-refresh -> contact waves ->
 deterministic gather fused with gravity/force_to_accel/epilog) over the synthetic workload:
   N = 1 : BASELINE.json configs[1] — 1 M monodisperse spheres in a rotating drum (cylinder driver), fp64.
-  N > 1 : weak scaling of the same configuration: the drum is N times longer and cut into N slabs along its axis, one 1 M-sphere
-          slab per GPU, ghost exchange between neighbouring slabs (`--workload box`: S5 topology, periodic box of bricks).
+  N > 1 : BASELINE.json configs[4] topology — fully periodic box of spheres cut into 2x1x1 / 2x2x1 / 2x2x2 bricks (7 peers per rank
+          at N = 8), one 1 M-sphere brick per GPU (weak, the default) or a FIXED global box divided by N (`--scaling strong`,
+          `--global-side 200` = 8 M, `400` = 64 M).  `--workload drum` at N > 1: the drum N times longer cut into N slabs (2 peers).
+          The line also carries `single_gpu_same_brick` (rank 0 runs one brick alone, periodic onto itself: the denominator of the
+          weak-scaling efficiency on THIS topology) and, at N > 1 with the default workload, the drum slabs as `drum_slabs`.
 metric = interaction-updates/s (sum over waves of records processed by the contact kernels per wall second, whole job);
 particle-steps/s is reported beside it.  One JSON line is printed by rank 0.
+`--impl reference`: the CPU arm (the oracle port of the reference operators, OpenMP on all host cores) on the SAME workload.
 """
 from __future__ import annotations
 
@@ -28,6 +33,8 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "interaction-updates/s"
 UNIT = "interaction-updates/s"
+L2_NOTE = "inputs larger than L2: the working set of a step (particles + interaction waves, > 0.7 GB per GPU) exceeds the 126 MB L2; no flush"
+CPU_ARM_MAX_PARTICLES = 9_000_000     # the CPU arm runs the whole N-GPU workload up to this size, a whole-brick sample beyond
 
 
 def parse():
@@ -36,11 +43,15 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=None, help="drum (default; N>1: slabs) | box | box8m | poly | mixed")
-    ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU")
+    ap.add_argument("--workload", default=None, help="drum (default at N=1) | box (default at N>1) | poly | mixed")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU (weak scaling)")
+    ap.add_argument("--global-side", type=int, default=200, help="strong scaling: side of the fixed global periodic box (200 = 8 M, 400 = 64 M)")
+    ap.add_argument("--jitter", type=float, default=2e-5, help="box workload: uniform position jitter of the SC lattice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-poly", action="store_true", help="skip the polyhedra line reported alongside (N=1 only)")
+    ap.add_argument("--no-secondary", action="store_true", help="N>1: skip the single-brick and drum-slab lines reported alongside")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -64,7 +75,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10",
                                        "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -77,9 +88,9 @@ class ClockSampler:
         except Exception:
             return None
 
-    def stop(self, window=None):
-        """window = (t0, t1) wall-clock seconds of the timed region: only the samples taken inside it count (nvidia-smi needs a
-        few hundred ms to start, so the sampler is launched well before the region and left running through it)."""
+    def stop(self, windows=None):
+        """windows = [(t0, t1), ...] wall-clock seconds of the timed regions: only the samples taken inside one of them count
+        (nvidia-smi needs a few hundred ms to start, so the sampler is launched well before and left running through them)."""
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -93,9 +104,9 @@ class ClockSampler:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
-            if window is not None:
+            if windows is not None:
                 ts = self._epoch(f[0])
-                if ts is None or ts < window[0] - 0.005 or ts > window[1] + 0.005:
+                if ts is None or not any(w[0] - 0.005 <= ts <= w[1] + 0.005 for w in windows):
                     continue
             try:
                 sm.append(float(f[1]))
@@ -108,53 +119,66 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
-    def one_shot(self):
-        """A single synchronous sample (used when the timed region was shorter than the sampling period)."""
-        try:
-            out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device)],
-                                 capture_output=True, text=True, timeout=10).stdout
-        except Exception:
-            return None
-        f = [x.strip() for x in out.strip().split(",")]
-        try:
-            return float(f[1]), float(f[2])
-        except Exception:
-            return None
-
 
 # ------------------------------------------------------------------------------------------------ workloads
-def make_workload(name, n, rank=0, nranks=1):
-    from exadem_b200 import workloads
+def resolve_workload(args, world):
+    """-> (name, make(rank, nranks) -> Workload, description shared by both arms, scaling)"""
+    from exadem_b200 import parallel, workloads
+    name = args.workload or ("drum" if world == 1 else "box")
+    scaling = args.scaling
     if name == "drum":
-        if nranks > 1:
-            from exadem_b200 import parallel
-            return parallel.drum_slab_workload(n, rank, nranks)
-        return workloads.rotating_drum(n)
-    if name in ("box", "box8m"):
-        side = int(round((8_000_000 if name == "box8m" else n) ** (1.0 / 3.0)))
-        side = max(8, int(round(side / 5.0)) * 5)  # multiple of 2 cells of 2.5
-        from exadem_b200 import parallel
-        return parallel.brick_workload(side, rank, nranks)
+        if scaling == "strong":
+            raise SystemExit("--scaling strong is defined for the box workload")
+        def make(rank, nranks):
+            return parallel.drum_slab_workload(args.particles, rank, nranks) if nranks > 1 else workloads.rotating_drum(args.particles)
+        desc = (f"drum: ~{args.particles} monodisperse spheres per GPU in a rotating cylinder driver (BASELINE configs[1])"
+                + (f", {world} slabs along the periodic axis" if world > 1 else ""))
+        return name, make, desc, scaling
+    if name == "box":
+        if scaling == "strong":
+            dims = parallel.strong_brick_dims(args.global_side, world)
+            desc = (f"box: fixed {args.global_side}^3 = {args.global_side ** 3} spheres, fully periodic (BASELINE configs[4]), strong scaling: "
+                    f"{'x'.join(map(str, parallel.process_grid(world)))} bricks of {dims[0]}x{dims[1]}x{dims[2]}")
+        else:
+            side = max(10, int(round(round(args.particles ** (1.0 / 3.0)) / 5.0)) * 5)   # whole 2.5-wide cells, even count
+            dims = (side, side, side)
+            desc = (f"box: {side}^3 = {side ** 3} spheres per GPU, fully periodic (BASELINE configs[4] topology), weak scaling: "
+                    f"{'x'.join(map(str, parallel.process_grid(world)))} bricks")
+        def make(rank, nranks, dims=dims):
+            return parallel.brick_workload(dims, rank, nranks, jitter=args.jitter)
+        return name, make, desc, scaling
+    if world > 1:
+        raise SystemExit(f"workload {name} is single-GPU")
     if name == "poly":
-        side = int(round(n ** (1.0 / 3.0)))
-        return workloads.polyhedra_box((side, side, side), pitch=0.78)
+        side = int(round(args.particles ** (1.0 / 3.0)))
+        return name, (lambda rank, nranks: workloads.polyhedra_box((side, side, side), pitch=0.78)), \
+            f"poly: {side ** 3} octahedra, periodic packing (BASELINE configs[2])", scaling
     if name == "mixed":
-        # BASELINE configs[3]: spheres (one-vertex shapes) + octahedra + cubes in one polyhedron context, cohesive law, closed
-        # STL-like mesh walls (an RShape driver) around the packing
-        from exadem_b200 import capi
-        side = int(round(n ** (1.0 / 3.0)))
-        wl = workloads.polyhedra_box((side, side, side), shapes=("octahedron", "cube", "sphere"), pitch=0.78, name="mixed")
-        L = side * 0.78
-        wl.lo, wl.hi = (-2.0, -2.0, -2.0), (L + 2.0, L + 2.0, L + 2.0)
-        wl.periodic = (0, 0, 0)
-        wl.law = capi.LAW_COHESIVE
-        wl.params = dict(wl.params, fc=0.05, dncut=0.02)
-        wl.params_driver = dict(wl.params_driver, fc=0.02, dncut=0.01)
-        spec, centre = workloads.box_mesh((-0.45, -0.45, -0.45), (L - 0.33, L - 0.33, L - 0.33), 0.03)
-        wl.mesh_spec = [spec]
-        wl.drivers = list(wl.drivers) + [dict(kind=capi.DRIVER_RSHAPE, shape=0, center=centre)]
-        return wl
+        return name, (lambda rank, nranks: mixed_workload(args.particles)), \
+            f"mixed: ~{args.particles} spheres + octahedra + cubes, cohesive law, closed mesh walls (BASELINE configs[3])", scaling
     raise SystemExit(f"unknown workload {name}")
+
+
+def mixed_workload(n):
+    """BASELINE configs[3]: spheres (one-vertex shapes) + octahedra + cubes in one polyhedron context, cohesive law, closed
+    STL-like mesh walls (an RShape driver) around the packing"""
+    from exadem_b200 import capi, workloads
+    side = int(round(n ** (1.0 / 3.0)))
+    wl = workloads.polyhedra_box((side, side, side), shapes=("octahedron", "cube", "sphere"), pitch=0.78, name="mixed")
+    L = side * 0.78
+    wl.lo, wl.hi = (-2.0, -2.0, -2.0), (L + 2.0, L + 2.0, L + 2.0)
+    wl.periodic = (0, 0, 0)
+    wl.law = capi.LAW_COHESIVE
+    wl.params = dict(wl.params, fc=0.05, dncut=0.02)
+    wl.params_driver = dict(wl.params_driver, fc=0.02, dncut=0.01)
+    spec, centre = workloads.box_mesh((-0.45, -0.45, -0.45), (L - 0.33, L - 0.33, L - 0.33), 0.03)
+    wl.mesh_spec = [spec]
+    wl.drivers = list(wl.drivers) + [dict(kind=capi.DRIVER_RSHAPE, shape=0, center=centre)]
+    return wl
+
+
+DYN_FIELDS = ("rx", "ry", "rz", "vx", "vy", "vz", "vrotx", "vroty", "vrotz", "qw", "qx", "qy", "qz", "fx", "fy", "fz",
+              "momx", "momy", "momz", "arotx", "aroty", "arotz")
 
 
 def pinned_like(pa):
@@ -162,8 +186,7 @@ def pinned_like(pa):
     import torch
     out = pa.copy()
     keep = []
-    for f in ("rx", "ry", "rz", "vx", "vy", "vz", "vrotx", "vroty", "vrotz", "qw", "qx", "qy", "qz", "fx", "fy", "fz",
-              "momx", "momy", "momz", "arotx", "aroty", "arotz"):
+    for f in DYN_FIELDS:
         t = torch.empty(pa.n, dtype=torch.float64, pin_memory=torch.cuda.is_available())
         a = t.numpy()
         a[:] = getattr(pa, f)
@@ -174,48 +197,93 @@ def pinned_like(pa):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_run(wl, seconds, threads=None, max_steps=10_000):
-    """Times the oracle (the CPU restatement of the reference path, OpenMP over all host cores) on `wl`.
-    Returns (interaction-updates/s, particle-steps/s, steps, wall seconds, threads)."""
+def host_threads():
+    """All host cores, whatever the launcher did to this process: torchrun exports OMP_NUM_THREADS=1 and a launcher may have pinned
+    the rank to a few cores — the CPU arm undoes both BEFORE the oracle library (libgomp) is loaded."""
+    os.environ.pop("OMP_NUM_THREADS", None)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    os.environ.pop("GOMP_CPU_AFFINITY", None)
+    os.environ["OMP_PROC_BIND"] = "false"
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except Exception:
+        pass
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_engine(wl, nthr):
     sys.path.insert(0, str(ROOT / "tests"))
+    import ctypes
     from oracle_binding import OracleEngine, OracleLibrary
     lib = OracleLibrary()
-    nthr = threads or (os.cpu_count() or 1)
     e = wl.setup(OracleEngine(lib, wl.config()))
     e.set_threads(nthr)
+    got = nthr
+    try:
+        f = lib.dll.orc_threads_in_parallel
+        f.restype = ctypes.c_int
+        got = int(f(ctypes.c_int(nthr)))
+    except Exception:
+        pass
+    return e, got
+
+
+def cpu_warm(e, wl, min_steps, min_seconds=1.0):
+    """warm-up: at least `min_steps` steps AND `min_seconds` of stepping (page faults, thread pool, caches)"""
     e.update_particle_neighbors(wl.rcut_inc, wl.symetric)
-    e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, 2, 0)
+    t0 = time.perf_counter()
+    done = 0
+    while done < max(min_steps, 1) or time.perf_counter() - t0 < min_seconds:
+        e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, 2, 0)
+        done += 2
+    return done
+
+
+def cpu_baseline_leg(wl, seconds):
+    """cpu_baseline of the GPU arm: the oracle on all host cores, the N=1 workload, a bounded number of steps (~`seconds`)."""
+    nthr = host_threads()
+    e, got = cpu_engine(wl, nthr)
+    warm = cpu_warm(e, wl, 3)
     e.reset_counters()
     t0 = time.perf_counter()
     steps = 0
-    chunk = 5
-    while steps < max_steps:
-        e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, chunk, 0)
-        steps += chunk
-        if time.perf_counter() - t0 >= seconds:
+    while True:
+        e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, 5, 0)
+        steps += 5
+        if time.perf_counter() - t0 >= seconds or steps >= 10_000:
             break
     dt = time.perf_counter() - t0
     c = e.counters()
-    return c.interaction_updates / dt, c.particle_steps / dt, steps, dt, nthr
+    return {"value": c.interaction_updates / dt, "unit": UNIT, "cores": got, "kind": "port",
+            "particle_steps_per_s": c.particle_steps / dt,
+            "sample": f"the whole workload ({wl.particles.n} particles), {steps} steps in {dt:.1f} s after {warm} warm-up steps, "
+                      f"oracle OpenMP ({got} threads)"}
 
 
 def reference_arm(args):
     """`--impl reference`: the reference's CPU implementation of the path.  The real exaDEM cannot be built here
-    (needs exaNBody + Onika + MPI + yaml-cpp, none present) so this is the oracle port, all host threads."""
+    (needs exaNBody + Onika + MPI + yaml-cpp, none present) so this is the oracle port, all host threads, on the SAME workload as
+    the GPU arm at this N (the N bricks / slabs as one domain)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    name = args.workload or "drum"
-    n_sample = min(args.particles, 200_000)
-    wl = make_workload(name if name != "box8m" else "box", n_sample)
-    sys.path.insert(0, str(ROOT / "tests"))
-    from oracle_binding import OracleEngine, OracleLibrary
-    lib = OracleLibrary()
-    nthr = os.cpu_count() or 1
-    e = wl.setup(OracleEngine(lib, wl.config()))
-    e.set_threads(nthr)
-    e.update_particle_neighbors(wl.rcut_inc, wl.symetric)
-    e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, max(args.warmup, 1), 0)
+    nthr = host_threads()
+    from exadem_b200 import parallel
+    world = args.gpus
+    name, make, desc, scaling = resolve_workload(args, world)
+    n_run = world
+    per = make(0, world).particles.n if world > 1 else None
+    sample = "the whole workload"
+    if world > 1 and per * world > CPU_ARM_MAX_PARTICLES:
+        # bounded sample: as many whole bricks as fit the cap, run as their own periodic domain
+        n_run = max(1, [k for k in (8, 4, 2, 1) if k <= world and per * k <= CPU_ARM_MAX_PARTICLES][0]) if per <= CPU_ARM_MAX_PARTICLES else 1
+        sample = f"bounded sample: {n_run} of the {world} bricks as one periodic domain"
+    wl = parallel.global_workload(make, n_run) if n_run > 1 else make(0, 1)
+    e, got = cpu_engine(wl, nthr)
+    warm = cpu_warm(e, wl, args.warmup)
     e.reset_counters()
     t0 = time.perf_counter()
     e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, args.steps, 0)
@@ -223,22 +291,87 @@ def reference_arm(args):
     c = e.counters()
     val = c.interaction_updates / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "particle_steps_per_s": c.particle_steps / dt,
-            "config": {"workload": f"{name}: bounded sample of {wl.particles.n} spheres of the {args.particles}-particle-per-GPU workload",
-                       "particles": int(wl.particles.n), "rebuild": "displacement trigger rcut_inc/2"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthr, "kind": "port",
-                             "sample": f"{wl.particles.n} particles x {args.steps} steps, oracle OpenMP"},
+            "config": {"workload": desc, "rebuild": "displacement trigger rcut_inc/2", "l2": L2_NOTE},
+            "run": {"particles": int(wl.particles.n), "warmup_steps_done": warm, "threads_requested": nthr, "threads_in_parallel_region": got,
+                    "affinity_cpus": nthr, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": got, "kind": "port",
+                             "sample": f"{sample}: {wl.particles.n} particles x {args.steps} steps after {warm} warm-up steps, oracle OpenMP ({got} threads)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def polyhedra_line(lib, peak, device, n=500_000, steps=60, warmup=10):
-    """BASELINE configs[2] reported alongside (north_star): ~500 k octahedra, the vertex/edge/face contact path."""
-    from exadem_b200 import Engine
-    wl = make_workload("poly", n)
+# ------------------------------------------------------------------------------------------------ rooflines
+def load_traffic():
+    """ncu `--set full` DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), keyed by kernel and operating point;
+    written by scripts/ncu_traffic.py from the captures summarised in profiles/ (the capture command is recorded in the file)."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return {}
+    try:
+        return json.loads(p.read_text())
+    except Exception:
+        return {}
+
+
+def traffic_for(tr, kernel, workload, steps, warmup):
+    """traffic of `kernel` captured at the operating point nearest to (steps, warmup) of this run; None when no capture of this
+    workload exists"""
+    best = None
+    for pt in tr.get("points", []):
+        if pt.get("workload") != workload or kernel not in pt.get("kernels", {}):
+            continue
+        d = abs(pt.get("step_index", 0) - (warmup + steps // 2))
+        if best is None or d < best[0]:
+            best = (d, pt)
+    if best is None:
+        return None, None
+    pt = best[1]
+    return pt["kernels"][kernel], {"step_index": pt.get("step_index"), "capture": pt.get("capture")}
+
+
+def sphere_rooflines(c, counts, active, n_real, ms, steps, peak, peak_src, tr, wname, warmup):
+    """Both per-step kernels on equal footing.  `achieved` = bytes this kernel has to move for the state that was timed (its own
+    compulsory-traffic model, DESIGN.md 3) / mean launch duration (CUDA events on the library stream, inside the timed region);
+    `frac_algorithmic` keeps the SURVEY 8(d) figure (184 B/record + 92 B/particle of the REFERENCE algorithm, which this kernel
+    undercuts for records that are not in contact); `traffic` = ncu DRAM bytes of one launch at the nearest captured operating point."""
+    out = {}
+    n_pp = max(c.contact_pp_launches, 1)
+    rec = c.contact_pp_records / n_pp
+    t_pp = (c.contact_pp_ms / n_pp) * 1e-3
+    hot0 = float(active[0])
+    own = 9.0 * rec + 128.0 * hot0 + 96.0 * n_real      # ij+flg per record; friction r/w + wrench w per hot record; 3 sectors per particle
+    alg = rec * 184.0 + n_real * 92.0
+    tpp, cap = traffic_for(tr, "k_contact_sphere_pp", wname, steps, warmup)
+    out["contact"] = {"kernel": "k_contact_sphere_pp", "bound": "hbm", "achieved": own / t_pp / 1e9 if t_pp > 0 else 0.0, "peak": peak,
+                      "peak_source": peak_src, "unit": "GB/s", "frac": own / t_pp / 1e9 / peak if t_pp > 0 else 0.0,
+                      "bytes_model": "9 B/record + 128 B/record in contact + 96 B/particle", "bytes_per_launch": own,
+                      "traffic": tpp, "traffic_capture": cap, "frac_traffic": (tpp / t_pp / 1e9 / peak) if (tpp and t_pp > 0) else None,
+                      "algorithmic_bytes_per_launch": alg, "frac_algorithmic": alg / t_pp / 1e9 / peak if t_pp > 0 else None,
+                      "mean_launch_ms": t_pp * 1e3, "share_of_step": c.contact_pp_ms / ms if ms > 0 else None}
+    if c.gather_launches > 0 and c.gather_ms > 0:
+        inc = 2.0 * float(counts[0]) + float(counts[4:].sum())
+        hot = 2.0 * float(active[0]) + float(active[4:].sum())
+        gb = 312.0 * n_real + 5.0 * inc + 64.0 * hot
+        tg = c.gather_ms / c.gather_launches * 1e-3
+        tgt, cap = traffic_for(tr, "k_gather", wname, steps, warmup)
+        out["gather"] = {"kernel": "k_gather<2>", "bound": "hbm", "achieved": gb / tg / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": gb / tg / 1e9 / peak,
+                         "bytes_model": "312 B/particle + 5 B/incidence + 64 B per incident side of a record in contact", "bytes_per_launch": gb,
+                         "traffic": tgt, "traffic_capture": cap, "frac_traffic": (tgt / tg / 1e9 / peak) if tgt else None,
+                         "mean_launch_ms": tg * 1e3, "share_of_step": c.gather_ms / ms if ms > 0 else None}
+    return out
+
+
+def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=60, warmup=10):
+    """BASELINE configs[2] reported alongside (north_star): ~500 k octahedra, the vertex/edge/face contact path.  The timed region is a
+    FLOWING state (the packing falls under gravity with random angular velocities) so that it contains neighbour rebuilds."""
+    from exadem_b200 import Engine, workloads
+    side = int(round(n ** (1.0 / 3.0)))
+    wl = workloads.polyhedra_box((side, side, side), pitch=0.78)
     eng = wl.setup(Engine(lib, wl.config(device=device)))
     eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)
     eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, warmup, 0)
@@ -258,26 +391,97 @@ def polyhedra_line(lib, peak, device, n=500_000, steps=60, warmup=10):
     eng.sync()
     reb = eng.counters().rebuild_ms
     eng.set_timing(False)
-    t = c.contact_pp_ms * 1e-3
-    achieved = c.bytes_contact_algorithmic / t / 1e9 if t > 0 else 0.0
+    n_real = wl.particles.n
     eng.close()
-    return {"workload": f"{wl.particles.n} octahedra, periodic packing (configs[2])", "value": c.interaction_updates / (ms * 1e-3),
+    npp = max(c.contact_pp_launches, 1)
+    t = c.contact_pp_ms / npp * 1e-3
+    rec = float(counts[:4].sum())
+    hot = float(active[:4].sum())
+    # the two launches' own traffic: detection reads ij + sub + flg (17 B) per record and, through L1/L2, the two vertex sets of every
+    # owner-partner pair (counted once per particle and wave family: 32 B x nv); the law pass moves 128 B + 6 sectors per record in contact
+    own = 17.0 * rec + 4.0 * hot + (128.0 + 192.0) * hot + n_real * (32.0 * 6 + 64.0)
+    alg = c.bytes_contact_algorithmic / npp
+    tp, cap = traffic_for(tr, "k_detect_poly_pp+k_law_poly_pp", "poly", steps, warmup)
+    return {"workload": f"{n_real} octahedra, periodic packing (configs[2])", "value": c.interaction_updates / (ms * 1e-3),
             "unit": UNIT, "particle_steps_per_s": c.particle_steps / (ms * 1e-3), "steps": steps, "ms_per_step": ms / steps,
             "interactions": int(counts.sum()), "active_interactions": int(active.sum()), "rebuilds_in_timed_region": int(nreb),
             "rebuild_once_ms": reb,
-            "roofline": {"kernel": "k_detect_poly_pp + k_law_poly_pp (4 waves)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "note": "algorithmic bytes counted as for spheres (184 B/record + 92 B/particle per wave); vertex reads not counted"},
-            "per_step_ms": {"contact_all": c.contact_ms / steps, "gather_fused": c.gather_ms / steps, "ghost": c.ghost_ms / steps}}
+            "roofline": {"kernel": "k_detect_poly_pp + k_law_poly_pp (4 waves)", "bound": "hbm", "achieved": own / t / 1e9 if t > 0 else 0.0,
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": own / t / 1e9 / peak if t > 0 else 0.0,
+                         "bytes_model": "17 B/record + 324 B/record in contact + 256 B/particle (vertices, type, homothety)",
+                         "bytes_per_launch": own, "traffic": tp, "traffic_capture": cap,
+                         "frac_traffic": (tp / t / 1e9 / peak) if (tp and t > 0) else None,
+                         "algorithmic_bytes_per_launch": alg, "frac_algorithmic": alg / t / 1e9 / peak if t > 0 else None,
+                         "algorithmic_note": "SURVEY 8(d): 184 B/record + 8 (sub) + 24 k vertex bytes (k = 2 V-V, 3 V-E, 1+n_face V-F, 4 E-E) + 92 B/particle per wave",
+                         "mean_launch_ms": t * 1e3},
+            "per_step_ms": {"contact_all": c.contact_ms / steps, "gather_fused": c.gather_ms / steps, "ghost": c.ghost_ms / steps,
+                            "rebuild_amortised": c.rebuild_ms / steps}}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+class Job:
+    """one engine per rank on a workload, with the barrier / timing helpers of the contract"""
+
+    def __init__(self, lib, make, rank, world, local, comm=True):
+        from exadem_b200 import Engine, parallel
+        self.world, self.rank = world, rank
+        self.wl = make(rank, world)
+        cfg = self.wl.config(device=local) if world == 1 else parallel.brick_config(self.wl, rank, world, device=local)
+        self.eng = Engine(lib, cfg)
+        if world > 1 and comm:
+            parallel.init_comm(self.eng, lib, rank)
+        self.wl.setup(self.eng)
+
+    def barrier(self):
+        self.eng.sync()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.eng.sync()
+
+    def timed(self, steps, warmup):
+        """W warm-up steps, then EXACTLY `steps` steps bracketed by barrier + synchronize; CUDA events on the library stream.
+        -> (ms on this rank, counters, rebuilds, (wall t0, t1))"""
+        wl, eng = self.wl, self.eng
+        eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)
+        eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, max(warmup, 3), 0)
+        self.barrier()
+        eng.reset_counters()
+        eng.set_timing(True)
+        self.barrier()
+        eng.event_record(0)
+        w0 = time.time()
+        nreb = eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, steps, 0)
+        eng.event_record(1)
+        ms = eng.event_elapsed_ms(0, 1)
+        self.barrier()
+        w1 = time.time()
+        c = eng.counters()
+        eng.set_timing(False)
+        return ms, c, nreb, (w0, w1)
+
+
+def reduce_stats(world, ms, c, nreb):
+    """max over ranks of the time, sums of the work -> (ms, interaction updates, particle steps, launches, rebuilds max)"""
+    stats = np.array([ms, float(c.interaction_updates), float(c.particle_steps), float(c.kernel_launches), float(nreb)], dtype=np.float64)
+    if world == 1:
+        return tuple(stats)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(stats, device="cuda")
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(tmax[0]), float(t[1]), float(t[2]), float(t[3]), float(tmax[4])
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         reference_arm(args)
         return
     import torch
-    from exadem_b200 import Engine, Library, capi, parallel
+    from exadem_b200 import Library
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -293,56 +497,17 @@ def main():
     sampler = ClockSampler(local)   # started now: nvidia-smi needs a few hundred ms before its first sample
     if rank == 0:
         sampler.start()
-    name = args.workload or "drum"
-    wl = make_workload(name, args.particles, rank, world)
+    name, make, desc, scaling = resolve_workload(args, world)
     lib = Library()
-    cfg = wl.config(device=local) if world == 1 else parallel.brick_config(wl, rank, world, device=local)
-    eng = Engine(lib, cfg)
-    if world > 1:
-        parallel.init_comm(eng, lib, rank)
-    wl.setup(eng)
+    job = Job(lib, make, rank, world, local)
+    wl, eng = job.wl, job.eng
     g = wl.gravity
+    windows = []
 
-    def barrier():
-        eng.sync()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        eng.sync()
-
-    eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)
-    eng.run_verlet(wl.dt, g, wl.rcut_inc, wl.symetric, max(args.warmup, 3), 0)
-    barrier()
-    eng.reset_counters()
-    eng.set_timing(True)
-    barrier()
-    eng.event_record(0)
-    w0 = time.time()
-    t0 = time.perf_counter()
-    nreb = eng.run_verlet(wl.dt, g, wl.rcut_inc, wl.symetric, args.steps, 0)
-    eng.event_record(1)
-    ms = eng.event_elapsed_ms(0, 1)
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop((w0, time.time())) if rank == 0 else None
-    if rank == 0 and not clocks.get("samples"):
-        shot = sampler.one_shot()
-        if shot:
-            clocks.update({"sm_mhz": shot[0], "sm_max_mhz": shot[1], "samples": 1, "note": "timed region shorter than the sampling period: one sample right after it"})
-    c = eng.counters()
-    eng.set_timing(False)
+    ms, c, nreb, win = job.timed(args.steps, args.warmup)
+    windows.append(win)
     counts, active = eng.interaction_counts()
-    stats = np.array([ms, float(c.interaction_updates), float(c.particle_steps), float(c.kernel_launches), float(nreb)], dtype=np.float64)
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor(stats, device="cuda")
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms = float(tmax[0])
-        iu, ps, launches = float(t[1]), float(t[2]), float(t[3])
-    else:
-        iu, ps, launches = stats[1], stats[2], stats[3]
+    ms, iu, ps, launches, nreb_max = reduce_stats(world, ms, c, nreb)
     value = iu / (ms * 1e-3)
 
     # ---- e2e: the host owns the grid; every step ships the dynamic fields in and the results out (pinned memory)
@@ -353,7 +518,8 @@ def main():
         d2h = 22 * 8 * host.n
         ke = max(5, min(args.steps, 40))
         eng.reset_counters()
-        barrier()
+        job.barrier()
+        w0 = time.time()
         t0 = time.perf_counter()
         for _ in range(ke):
             eng.upload_dynamic(host)
@@ -362,104 +528,107 @@ def main():
                 host = pinned_like(eng.download_particles())
             else:
                 eng.download_dynamic(host)
-        barrier()
+        job.barrier()
         dt = time.perf_counter() - t0
+        windows.append((w0, time.time()))
         ce = eng.counters()
         iu_e = float(ce.interaction_updates)
         if world > 1:
             import torch.distributed as dist
-            t = torch.tensor([iu_e, dt], device="cuda", dtype=torch.float64)
+            t = torch.tensor([iu_e, dt, float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
             tm = t.clone()
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            iu_e, dt = float(t[0]), float(tm[1])
+            iu_e, dt, h2d, d2h = float(t[0]), float(tm[1]), float(t[2]), float(t[3])
         e2e = {"value": iu_e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ke,
-               "ms_per_step": 1e3 * dt / ke}
+               "ms_per_step": 1e3 * dt / ke,
+               "what": "edb_upload_dynamic (r, v, vrot, orient from pinned host memory) -> edb_run_verlet(1 step) -> edb_download_dynamic "
+                       "(r, v, vrot, orient, f, mom, arot to pinned host memory), every step, all ranks"}
 
     # ---- cost of one neighbour rebuild (outside the timed region; the drum moves too slowly to trigger one in K steps)
     eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)   # (the first explicit rebuild allocates the second set of wave buffers)
-    barrier()
+    job.barrier()
     eng.reset_counters()
     eng.set_timing(True)
     eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)
-    barrier()
+    job.barrier()
     rebuild_once_ms = eng.counters().rebuild_ms
     eng.set_timing(False)
+    n_real = wl.particles.n
+    eng.close()
+
+    # ---- N > 1: the same brick alone on one GPU (weak-scaling denominator on this topology) and the drum slabs, reported alongside
+    single = None
+    slabs = None
+    if world > 1 and not args.no_secondary and name == "box":
+        if rank == 0:
+            j1 = Job(lib, lambda r, n: make(0, 1), 0, 1, local)
+            ms1, c1, nreb1, win1 = j1.timed(args.steps, args.warmup)
+            windows.append(win1)
+            single = {"workload": "one brick of the same size alone on one GPU (periodic onto itself)", "particles": int(j1.wl.particles.n),
+                      "value": c1.interaction_updates / (ms1 * 1e-3), "ms_per_step": ms1 / args.steps, "rebuilds_in_timed_region": int(nreb1),
+                      "per_step_ms": {"contact_all": c1.contact_ms / args.steps, "gather_fused": c1.gather_ms / args.steps}}
+            j1.eng.close()
+        import torch.distributed as dist
+        dist.barrier()
+        if args.scaling == "weak":
+            from exadem_b200 import parallel
+            js = Job(lib, lambda r, n: parallel.drum_slab_workload(args.particles, r, n), rank, world, local)
+            ms2, c2, nreb2, win2 = js.timed(args.steps, args.warmup)
+            windows.append(win2)
+            ms2, iu2, ps2, _, nr2 = reduce_stats(world, ms2, c2, nreb2)
+            slabs = {"workload": f"drum (BASELINE configs[1]) {world} times longer, cut into {world} slabs along its periodic axis (2 peers per rank)",
+                     "particles_per_gpu": int(js.wl.particles.n), "value": iu2 / (ms2 * 1e-3), "ms_per_step": ms2 / args.steps,
+                     "rebuilds_in_timed_region": int(nr2),
+                     "per_step_ms": {"contact_all": c2.contact_ms / args.steps, "gather_fused": c2.gather_ms / args.steps, "ghost": c2.ghost_ms / args.steps}}
+            js.eng.close()
 
     if rank != 0:
         return
+    clocks = sampler.stop(windows)
     peak, peak_src = peaks()
-    # roofline of the dominant kernel (wave 0 contact kernel): algorithmic bytes per launch / mean launch duration
-    rec_per_launch = c.contact_pp_records / max(c.contact_pp_launches, 1)
-    alg_bytes = rec_per_launch * 184.0 + wl.particles.n * 92.0
-    t_launch = (c.contact_pp_ms / max(c.contact_pp_launches, 1)) * 1e-3
-    achieved = alg_bytes / t_launch / 1e9 if t_launch > 0 else 0.0
-    roof = {"kernel": "k_contact_sphere_pp" if wl.mode == 0 else "k_detect_poly_pp + k_law_poly_pp", "bound": "hbm", "achieved": achieved,
-            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": t_launch * 1e3,
-            "share_of_step": c.contact_pp_ms / ms if ms > 0 else None,
-            "per_step_ms": {"contact_all": c.contact_ms / args.steps, "gather_fused": c.gather_ms / args.steps,
-                            "prolog": c.prolog_ms / args.steps, "ghost": c.ghost_ms / args.steps,
-                            "rebuild_amortised": c.rebuild_ms / args.steps}}
-    prof = ROOT / "profiles" / "ncu_traffic.json"
-    if prof.exists():
-        try:
-            roof["traffic"] = json.loads(prof.read_text()).get(roof["kernel"])
-        except Exception:
-            pass
+    tr = load_traffic()
+    per_step = {"contact_all": c.contact_ms / args.steps, "gather_fused": c.gather_ms / args.steps, "prolog": c.prolog_ms / args.steps,
+                "ghost": c.ghost_ms / args.steps, "rebuild_amortised": c.rebuild_ms / args.steps}
+    roof = roof_other = None
+    if wl.mode == 0:
+        rf = sphere_rooflines(c, counts, active, n_real, ms, args.steps, peak, peak_src, tr, name, max(args.warmup, 3))
+        # `roofline` = the kernel with the larger share of the step; the other one rides beside it under its own key
+        keys = sorted(rf, key=lambda k: -(rf[k]["share_of_step"] or 0.0))
+        roof = rf[keys[0]]
+        roof_other = rf[keys[1]] if len(keys) > 1 else None
+    else:
+        npp = max(c.contact_pp_launches, 1)
+        t = c.contact_pp_ms / npp * 1e-3
+        alg = c.bytes_contact_algorithmic / npp
+        roof = {"kernel": "k_detect_poly_pp + k_law_poly_pp", "bound": "hbm", "achieved": alg / t / 1e9 if t > 0 else 0.0, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": alg / t / 1e9 / peak if t > 0 else 0.0, "traffic": None,
+                "bytes_model": "SURVEY 8(d) algorithmic bytes incl. vertices", "mean_launch_ms": t * 1e3,
+                "share_of_step": c.contact_pp_ms / ms if ms > 0 else None}
+    roof["per_step_ms"] = per_step
     roof["rebuild_once_ms"] = rebuild_once_ms
-    # The kernel's OWN compulsory traffic: 9 B per record, + 128 B per record that needs the law (friction r/w, wrench),
-    # + 96 B per particle (three gathered sectors).  `achieved` above uses the reference algorithm's 184 B/record, which
-    # this kernel undercuts for records that are not in contact — so `frac` can exceed what the DRAM actually delivers.
-    n_act = float(active[0]) if wl.mode == 0 else float(active[:4].sum())
-    own_bytes = 9.0 * rec_per_launch + 128.0 * n_act + 96.0 * wl.particles.n
-    roof["own_bytes_per_launch"] = own_bytes
-    roof["frac_dram_model"] = (own_bytes / t_launch / 1e9 / peak) if t_launch > 0 else None
-    if roof["frac"] > 1.0:
-        roof["note"] = ("frac > 1: the reference algorithm's compulsory bytes (184 B/record) divided by this kernel's time exceed the peak "
-                        "because records not in contact cost this kernel 9 B; see frac_dram_model / traffic for the bytes it really moves")
-    # The other half of the step: k_gather<2> (deterministic force sum + gravity + force_to_accel + epilog + next prolog + trigger).
-    # Algorithmic bytes: 312 B per particle (r, v, vrot, Q, inertia, r_backup in; r, v, vrot, Q out) + 5 B per incidence
-    # (code + flag byte; a particle-particle record is incident to two particles) + 64 B per incident side of a record in contact.
-    roof_g = None
-    if c.gather_launches > 0 and c.gather_ms > 0:
-        npp = 1 if wl.mode == 0 else 4
-        inc = 2.0 * float(counts[:npp].sum()) + float(counts[npp if npp == 4 else 4:].sum())
-        hot = 2.0 * float(active[:npp].sum()) + float(active[4:].sum())
-        g_bytes = 312.0 * wl.particles.n + 5.0 * inc + 64.0 * hot
-        tg = c.gather_ms / c.gather_launches * 1e-3
-        roof_g = {"kernel": "k_gather", "bound": "hbm", "achieved": g_bytes / tg / 1e9, "peak": peak, "unit": "GB/s",
-                  "frac": g_bytes / tg / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_launch": g_bytes,
-                  "mean_launch_ms": tg * 1e3, "share_of_step": c.gather_ms / ms if ms > 0 else None}
-        if prof.exists():
-            try:
-                roof_g["traffic"] = json.loads(prof.read_text()).get("k_gather")
-            except Exception:
-                pass
     poly = None
-    if world == 1 and not args.no_poly and (args.workload or "drum") == "drum":
-        eng.close()
-        poly = polyhedra_line(lib, peak, local)
+    if world == 1 and not args.no_poly and name == "drum":
+        poly = polyhedra_line(lib, peak, peak_src, local, tr)
     cpu = None
-    if not args.no_cpu_baseline:
-        n_sample = min(args.particles, 200_000)
-        wls = make_workload(name if name != "box8m" else "box", n_sample)
-        v, pss, st, dt, nthr = cpu_run(wls, args.cpu_seconds)
-        cpu = {"value": v, "unit": UNIT, "cores": nthr, "kind": "port", "particle_steps_per_s": pss,
-               "sample": f"{wls.particles.n}-particle sample of the workload, {st} steps in {dt:.1f} s, oracle OpenMP ({nthr} threads)"}
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_baseline_leg(make(0, 1), args.cpu_seconds)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "particle_steps_per_s": ps / (ms * 1e-3),
-            "config": {"workload": f"{name}: {wl.particles.n * world} particles ({wl.particles.n}/GPU), {wl.name}", "particles_per_gpu": int(wl.particles.n),
-                       "interactions_per_gpu": int(counts.sum()), "active_interactions_per_gpu": int(active.sum()),
-                       "rebuilds_in_timed_region": int(nreb), "rebuild": "displacement trigger rcut_inc/2",
-                       "l2": "working set (particles + interaction waves) > 126 MB L2, no flush",
-                       "timing": "CUDA events on the library stream, max over ranks", "wall_s": wall},
+            "config": {"workload": desc, "rebuild": "displacement trigger rcut_inc/2", "l2": L2_NOTE},
+            "run": {"particles_per_gpu": int(n_real), "particles": int(ps / args.steps), "interactions_per_gpu": int(counts.sum()),
+                    "active_interactions_per_gpu": int(active.sum()), "rebuilds_in_timed_region": int(nreb_max),
+                    "timing": "CUDA events on the library stream, max over ranks", "wall_s": windows[0][1] - windows[0][0]},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-    if roof_g is not None:
-        line["roofline_gather"] = roof_g
+    if roof_other is not None:
+        line["roofline_" + ("gather" if roof_other["kernel"].startswith("k_gather") else "contact")] = roof_other
     if poly is not None:
         line["polyhedra"] = poly
+    if single is not None:
+        line["single_gpu_same_brick"] = single
+    if slabs is not None:
+        line["drum_slabs"] = slabs
     print(json.dumps(line), flush=True)
 
 

@@ -81,6 +81,8 @@ struct edb_context {
   size_t smem_optin = 99 * 1024;   // cudaDevAttrMaxSharedMemoryPerBlockOptin
   double rcut_inc = 0;
   int symetric = 1;
+  double mean_face_nv = 3;  // mean vertex count of the particle shapes' faces (algorithmic bytes of the vertex-face waves)
+  double rmax_upload = 0;   // largest `radius` given to edb_upload_particles (check_rcut.cpp:72-100)
   // parameters
   ParamsDev prm{};
   DevBuf<Params> tpp, tpd;
@@ -404,6 +406,13 @@ extern "C" int edb_destroy(edb_context* c) {
   return EDB_OK;
 }
 
+// Host setters that touch device-resident state (driver / motion / parameter / mesh tables) wait for the kernels already enqueued:
+// the library streams are non-blocking, so a blocking cudaMemcpy on the legacy stream is NOT ordered behind them.
+static void quiesce(edb_context* c) {
+  if (c->st) CK(cudaStreamSynchronize(c->st));
+  if (c->st2) CK(cudaStreamSynchronize(c->st2));
+}
+
 extern "C" int edb_sync(edb_context* c) {
   API_BEGIN(c)
   CK(cudaStreamSynchronize(c->st));
@@ -424,6 +433,7 @@ extern "C" int edb_set_contact_params(edb_context* c, const edb_contact_params* 
 extern "C" int edb_set_contact_params_multimat(edb_context* c, int32_t ng, const edb_contact_params* pp, int32_t nd, const edb_contact_params* pd) {
   API_BEGIN(c)
   if (ng < 1 || !pp) throw StateError{EDB_ERR_INVALID, "multimat table is empty"};
+  quiesce(c);
   std::vector<Params> A, B;
   for (int i = 0; i < ng * ng; i++) A.push_back(to_params(pp[i]));
   for (int i = 0; i < ng * nd; i++) B.push_back(to_params(pd[i]));
@@ -501,6 +511,7 @@ static void build_mesh_grid(edb_context* c) {
 
 extern "C" int edb_set_drivers(edb_context* c, int32_t n, const edb_driver* d) {
   API_BEGIN(c)
+  quiesce(c);
   c->h_drv.clear();
   for (int i = 0; i < n; i++) {
     Driver D{};
@@ -570,10 +581,14 @@ static bool any_driver_moves(const edb_context* c) {
 extern "C" int edb_set_driver_motions(edb_context* c, int32_t n, const edb_driver_motion* mo) {
   API_BEGIN(c)
   if (n != (int)c->h_drv.size()) throw StateError{EDB_ERR_INVALID, "edb_set_driver_motions: n differs from the driver count of edb_set_drivers"};
+  quiesce(c);
+  // the orientation of an RShape lives with the motion state on the device and may have moved since edb_set_drivers: keep the device's
+  std::vector<DriverMotion> dev_mo(n);
+  if (n) CK(cudaMemcpy(dev_mo.data(), c->mo.p, n * sizeof(DriverMotion), cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; i++) {
     const edb_driver_motion& s = mo[i];
     DriverMotion& m = c->h_mo[i];
-    const q4 keep = m.quat;
+    const q4 keep = dev_mo[i].quat;
     if (s.motion_type < 0 || s.motion_type > EDB_MOTION_UNKNOWN) throw StateError{EDB_ERR_INVALID, "unknown motion type"};
     if (s.motion_type == EDB_MOTION_TABULATED && (s.n_tab < 1 || s.n_tab > EDB_MAX_TAB || !s.tab_time || !s.tab_pos))
       throw StateError{EDB_ERR_INVALID, "TABULATED motion needs 1..EDB_MAX_TAB (time, position) entries"};
@@ -611,7 +626,7 @@ extern "C" int edb_set_driver_motions(edb_context* c, int32_t n, const edb_drive
 extern "C" int edb_set_driver_expr(edb_context* c, int32_t d, const double v[3], const double vrot[3], const double mom[3]) {
   API_BEGIN(c)
   if (d < 0 || d >= (int)c->h_drv.size()) throw StateError{EDB_ERR_INVALID, "driver index out of range"};
-  CK(cudaStreamSynchronize(c->st));
+  quiesce(c);
   DriverMotion m;
   CK(cudaMemcpy(&m, c->mo.p + d, sizeof(DriverMotion), cudaMemcpyDeviceToHost));
   if (v) m.expr_v = mk3(v[0], v[1], v[2]);
@@ -656,6 +671,7 @@ extern "C" int edb_get_drivers(edb_context* c, int32_t n, edb_driver* out, edb_d
 }
 extern "C" int edb_set_driver_shapes(edb_context* c, int32_t n, const edb_shape* sh) {
   API_BEGIN(c)
+  quiesce(c);
   c->h_mesh_v.clear(); c->h_mesh_e.clear(); c->h_mesh_foff.clear(); c->h_mesh_fn.clear(); c->h_mesh_fidx.clear(); c->h_mesh_radius.clear();
   for (int i = 0; i < n; i++) {
     c->h_mesh_v.emplace_back(sh[i].vertices, sh[i].vertices + 3 * (size_t)sh[i].nv);
@@ -676,6 +692,7 @@ extern "C" int edb_set_driver_shapes(edb_context* c, int32_t n, const edb_shape*
 }
 extern "C" int edb_set_shapes(edb_context* c, int32_t n, const edb_shape* sh) {
   API_BEGIN(c)
+  quiesce(c);
   std::vector<v3> sv;
   std::vector<int> se, sfoff, sfn, sfidx;
   c->h_sh.clear();
@@ -720,6 +737,7 @@ extern "C" int edb_set_shapes(edb_context* c, int32_t n, const edb_shape* sh) {
     CK(cudaMemcpy(c->d_sfidx.p, sfidx.data(), sfidx.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
   c->S = ShapesView{c->d_sh.p, c->d_sv.p, c->d_se.p, c->d_sfoff.p, c->d_sfn.p, c->d_sfidx.p, nvmax};
+  c->mean_face_nv = sfn.empty() ? 3.0 : (double)sfidx.size() / (double)sfn.size();
   API_END(c)
 }
 
@@ -797,6 +815,8 @@ static void clear_interactions(edb_context* c) {
   c->have_prev = false;
   c->have_inc = false;
   c->have_backup = false;
+  // tables of the last rebuild refer to slots that no longer exist
+  c->have_fan = false; c->ghost_pushed = false; c->bonds_on_device = false; c->have_drv_backup = false;
 }
 
 extern "C" int edb_upload_particles(edb_context* c, const edb_particles* P) {
@@ -820,6 +840,9 @@ extern "C" int edb_upload_particles(edb_context* c, const edb_particles* P) {
   LAUNCH(c, k_pack_upload, nblk(n), BLK, 0, view(c->pa), c->stage.p, P->id ? c->stage_u64.p : nullptr,
          P->type ? c->stage_u32.p : nullptr, P->group ? c->stage_u32.p + n : nullptr, (uint32_t)n, have);
   CK(cudaStreamSynchronize(c->st));
+  c->rmax_upload = 0;
+  if (P->radius)
+    for (uint64_t i = 0; i < n; i++) c->rmax_upload = std::max(c->rmax_upload, P->radius[i]);
   c->nreal = (uint32_t)n;
   c->nghost = 0;
   clear_interactions(c);
@@ -1119,6 +1142,16 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   c->symetric = symetric;
   const bool poly = c->poly();
   if (poly && c->h_sh.empty()) throw StateError{EDB_ERR_STATE, "polyhedron mode needs edb_set_shapes"};
+  // [check_rcut] (src/field/check_rcut.cpp:72-100): the neighbour kernels, the ghost layer and the mesh cell lists assume a one-cell
+  // stencil, i.e. a pair within 2 r_max + rcut_inc never spans more than one cell.  A smaller cell would silently drop contacts.
+  {
+    const double need = 2.0 * c->rmax_upload + rcut_inc, have = std::min(G.cs[0], std::min(G.cs[1], G.cs[2]));
+    if (c->rmax_upload > 0 && have < need * (1.0 - 1e-12)) {
+      char b[256];
+      snprintf(b, sizeof b, "cell size %.6g < 2 r_max + rcut_inc = %.6g: the one-cell neighbour stencil would miss contacts (check_rcut)", have, need);
+      throw StateError{EDB_ERR_INVALID, b};
+    }
+  }
 
   // 0. multi-GPU: particles that left the brick migrate (with their interaction history) before re-binning
   const bool multi = c->cfg.nranks > 1;
@@ -1528,9 +1561,16 @@ static void launch_contact_waves(edb_context* c, double dt, const unsigned long 
     }
     c->ctr.interaction_updates += w.n;
     c->ctr.contact_launches++;
-    // algorithmic bytes of this launch: per record 8 (ij) + 48 r + 48 w history + 80 contact state;
-    // per distinct particle touched 92 B of gathers (r, radius, vrot, group, v, mass) counted once per wave
-    c->ctr.bytes_contact_algorithmic += w.n * 184ull + (uint64_t)c->nreal * 92ull;
+    // algorithmic bytes of this launch (SURVEY 8d / DESIGN.md): per record 8 (ij) + 48 r + 48 w history + 80 contact state;
+    // per distinct particle touched 92 B of gathers (r, radius, vrot, group, v, mass) counted once per wave.  Polyhedra add per
+    // record 8 (sub) + 24 k of vertices, k = 2 V-V, 3 V-E, 1 + n_face V-F, 4 E-E (mesh waves alike; 1 vertex for a driver wave).
+    uint64_t per_rec = 184;
+    if (poly) {
+      const double nf = c->mean_face_nv;
+      const double k = (t == 0 || t == 7) ? 2 : (t == 1 || t == 8 || t == 11) ? 3 : (t == 2 || t == 9 || t == 12) ? 1 + nf : (t == 3 || t == 10) ? 4 : 1;
+      per_rec += 8 + (uint64_t)(24.0 * k);
+    }
+    c->ctr.bytes_contact_algorithmic += w.n * per_rec + (uint64_t)c->nreal * 92ull;
   }
   if (side) {
     CK(cudaEventRecord(c->ev_join, c->st2));

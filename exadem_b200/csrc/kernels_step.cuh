@@ -650,7 +650,9 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
 #pragma unroll
   for (int t = 0; t < 4; t++)
     if (t < A.npp && A.W.w[t].n) { oa[t] = A.W.w[t].off[p]; ob[t] = A.W.w[t].off[p + 1]; }
-  const double4 pr = ldg4(A.P.pr + p);
+  // FUSE 2 stores pr (own slot and ghost images) in this kernel: the non-coherent path is only legal for data that is read-only
+  // for the whole kernel
+  const double4 pr = FUSE == 2 ? ld4(A.P.pr + p) : ldg4(A.P.pr + p);
   const v3 r = mk3(pr.x, pr.y, pr.z);
   v3 F, M;
   double4 vm;

@@ -65,24 +65,55 @@ def select(pa: ParticleArrays, mask: np.ndarray) -> ParticleArrays:
     return out
 
 
-def brick_workload(side: int, rank: int, nranks: int, seed=0xD3A5):
-    """Weak-scaling workload: every rank owns a side^3 brick (side^3 spheres on the jittered SC lattice) of a fully
-    periodic global box of pgrid*side cells.  Each rank generates ONLY its own brick (seeded per brick)."""
+def brick_workload(side, rank: int, nranks: int, seed=0xD3A5, jitter=2e-5):
+    """Periodic-box workload cut into uniform bricks (S5 topology): every rank owns a brick of `side` = (sx, sy, sz) cells of pitch 1.0
+    (an int means a cube) holding sx*sy*sz spheres on the jittered SC lattice, inside a fully periodic global box of pgrid*side.
+    Each rank generates ONLY its own brick (seeded per brick).  Weak scaling keeps `side` fixed; strong scaling divides a fixed global
+    box by the process grid (`strong_brick_dims`)."""
     from . import workloads
+    dims = (side, side, side) if np.isscalar(side) else tuple(int(x) for x in side)
     pg = process_grid(nranks)
     c = rank_coords(rank, pg)
-    wl = workloads.spheres_box((side, side, side), seed=seed + 7919 * rank, name=f"periodic box, {pg[0]}x{pg[1]}x{pg[2]} bricks of {side}^3")
-    off = [c[d] * side for d in range(3)]
+    wl = workloads.spheres_box(dims, seed=seed + 7919 * rank, jitter=jitter,
+                               name=f"periodic box, {pg[0]}x{pg[1]}x{pg[2]} bricks of {dims[0]}x{dims[1]}x{dims[2]}")
+    off = [c[d] * dims[d] for d in range(3)]
     wl.particles.rx += off[0]
     wl.particles.ry += off[1]
     wl.particles.rz += off[2]
     n = wl.particles.n
     wl.particles.id[:] = (np.uint64(rank) * np.uint64(n) + wl.particles.id).astype(np.uint64)
     wl.lo = tuple(float(o) for o in off)
-    wl.hi = tuple(float(o + side) for o in off)
+    wl.hi = tuple(float(off[d] + dims[d]) for d in range(3))
     wl.glo = (0.0, 0.0, 0.0)
-    wl.ghi = tuple(float(pg[d] * side) for d in range(3))
+    wl.ghi = tuple(float(pg[d] * dims[d]) for d in range(3))
     wl.pgrid = pg
+    return wl
+
+
+def strong_brick_dims(global_side, nranks: int):
+    """Brick of a FIXED global cube of `global_side`^3 cells cut by process_grid(nranks) (strong scaling).  The global side must be
+    divisible by every pgrid factor into bricks holding whole 2.5-wide cells."""
+    pg = process_grid(nranks)
+    dims = []
+    for d in range(3):
+        if global_side % pg[d]:
+            raise ValueError(f"global side {global_side} not divisible by process grid {pg}")
+        dims.append(global_side // pg[d])
+    return tuple(dims)
+
+
+def global_workload(make_rank_workload, nranks: int):
+    """The whole N-rank workload as ONE domain (what a single process — the CPU reference arm, a parity test — runs): the per-rank
+    generators are seeded per brick, so concatenating them reproduces exactly the particles the N GPU ranks hold together."""
+    parts = [make_rank_workload(r, nranks) for r in range(nranks)]
+    wl = parts[0]
+    if nranks == 1:
+        return wl
+    pa = ParticleArrays(sum(p.particles.n for p in parts))
+    for f in capi.F64_FIELDS + ["id", "type", "group"]:
+        setattr(pa, f, np.ascontiguousarray(np.concatenate([getattr(p.particles, f) for p in parts])))
+    wl.particles = pa
+    wl.lo, wl.hi = tuple(wl.glo), tuple(wl.ghi)
     return wl
 
 
@@ -113,6 +144,10 @@ def brick_config(wl, rank: int, nranks: int, device: int = 0):
         ln = wl.hi[d] - wl.lo[d]
         if wl.periodic[d] and pg[d] == 1:
             cs = min(cs, ln / 3.0)
+    rmax = float(wl.particles.radius.max()) if wl.particles.n else 0.0
+    if cs < 2.0 * rmax + wl.rcut_inc:
+        raise ValueError(f"brick_config: a periodic axis shorter than 3 cells of 2 r_max + rcut_inc = {2.0 * rmax + wl.rcut_inc:.4g} "
+                         f"cannot be run with a one-cell stencil (cell size would be {cs:.4g})")
     return capi.make_config(wl.lo, wl.hi, cs, wl.periodic, wl.mode, device, glo=glo, ghi=ghi, rank=rank, nranks=nranks, pgrid=pg)
 
 

@@ -139,6 +139,67 @@ def rotating_drum(n_target=1_000_000, seed=0xD3A2, jitter=2e-5, length=None, nam
                     dict(prm, kt=8e4), [drv], dt=1e-4, rcut_inc=0.4)
 
 
+# ---- counter-based generator ("generator = counter-based (splitmix64) so CPU and GPU produce identical inputs") -----------
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def splitmix64(seed: int, counter) -> np.ndarray:
+    """splitmix64 output function applied to seed + (counter+1)*golden-gamma: value k of the stream never depends on how many values
+    were drawn before it or on the order of the draws (Steele, Lea, Flood 2014)."""
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + (np.asarray(counter, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)) & _M64
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return z ^ (z >> np.uint64(31))
+
+
+def counter_uniform(seed: int, counter) -> np.ndarray:
+    """uniform doubles in [0, 1) from the top 53 bits of splitmix64"""
+    return (splitmix64(seed, counter) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def counter_normal(seed: int, counter) -> np.ndarray:
+    """standard normals by Box-Muller on counters (2k, 2k+1) of the stream"""
+    c = np.asarray(counter, dtype=np.uint64)
+    u1 = 1.0 - counter_uniform(seed, 2 * c)          # (0, 1]
+    u2 = counter_uniform(seed, 2 * c + np.uint64(1))
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * PI * u2)
+
+
+def deposit_xyz(base_xyz: np.ndarray, tiles=(4, 4), variant="hooke", seed=0xD300 + 1, name="deposit_xyz") -> Workload:
+    """S1 of SURVEY 8(d) (= BASELINE configs[0], the reference's own CPU-runnable deck example/spheres/deposit/add_xyz.msp): the 736
+    sphere centres of `input_deposit_xyz.xyz` (box 10^3; passed in as `base_xyz`, see tests/golden/make_deposit_fixture.py) tiled
+    `tiles` times in x and y (4 x 4 -> 11 776 spheres), r = 0.4, density 0.02, v = (0, 0, -0.5) + N(0, 0.1^2) per component
+    (add_xyz.msp:31-44), surface driver z = -1 (:46-53), kn = kt = 1e4, kr = 0.1, mu = 0.2, damp = 0.9, dt = 1e-4, rcut_inc = 0.2,
+    cell_size 1 (:59-75), periodic x and y.  variant "hooke" = plain contact_sphere (BASELINE configs[0]); "dmt" = the deck's own
+    contact_singlemat_sphere_hooke_dmt with gamma = 10 and its config_driver (kt 8000, mu 0.5).  Velocities come from the
+    counter-based generator keyed by particle id."""
+    base = np.asarray(base_xyz, dtype=np.float64).reshape(-1, 3)
+    nb = len(base)
+    tx, ty = tiles
+    pos = np.concatenate([base + np.array([10.0 * i, 10.0 * j, 0.0]) for j in range(ty) for i in range(tx)])
+    n = len(pos)
+    pa = ParticleArrays(n)
+    pa.rx[:], pa.ry[:], pa.rz[:] = pos[:, 0], pos[:, 1], pos[:, 2]
+    ids = np.arange(n, dtype=np.uint64)
+    pa.vx[:] = 0.1 * counter_normal(seed, 3 * ids)
+    pa.vy[:] = 0.1 * counter_normal(seed, 3 * ids + np.uint64(1))
+    pa.vz[:] = -0.5 + 0.1 * counter_normal(seed, 3 * ids + np.uint64(2))
+    pa.radius[:] = 0.4
+    sphere_mass_inertia(pa, 0.02)
+    pa.id[:] = ids
+    prm = dict(kn=1e4, kt=1e4, kr=0.1, mu=0.2, damp_rate=0.9, fc=0.0, dncut=0.0, gamma=0.0)
+    prd = dict(prm)
+    law = capi.LAW_NONE
+    if variant == "dmt":
+        prm = dict(prm, gamma=10.0)
+        prd = dict(prm, kt=8e3, mu=0.5)
+        law = capi.LAW_DMT
+    drv = dict(kind=capi.DRIVER_SURFACE, offset=-1.0, normal=(0, 0, 1), center=(0, 0, -1.0))
+    return Workload(f"{name}[{variant}] {tx}x{ty} tiles of {nb}", (0.0, 0.0, -2.0), (10.0 * tx, 10.0 * ty, 13.0), 1.0, (1, 1, 0), pa, prm, prd, [drv],
+                    law=law, dt=1e-4, rcut_inc=0.2)
+
+
 def deposit(n_side=(22, 22, 22), seed=0xD3A1, name="deposit") -> Workload:
     """S1 (= BASELINE configs[0], the reference's CPU-runnable case): ~10 k spheres r=0.4 falling on a surface driver.
     Deck parameters: example/spheres/deposit/add_xyz.msp:31-59 (plain Hooke variant)."""

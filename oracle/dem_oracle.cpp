@@ -775,6 +775,18 @@ int orc_set_virtual_bricks(orc_sim* h, const int32_t* pg) {
   return 0;
 }
 int orc_set_threads(orc_sim* h, int n) { ((Sim*)h)->omp_threads = n < 1 ? 1 : n; return 0; }
+// threads a parallel region really gets when `n` are requested (affinity masks, OMP_THREAD_LIMIT ... can make it fewer)
+int orc_threads_in_parallel(int n) {
+  int got = 1;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n < 1 ? 1 : n)
+  {
+#pragma omp single
+    got = omp_get_num_threads();
+  }
+#endif
+  return got;
+}
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

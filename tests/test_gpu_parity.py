@@ -507,3 +507,40 @@ def test_full_size_polyhedra_properties(product_lib):
     ma = pa.vec("f") * pa.mass[:, None]
     expect = pa.mass.sum() * np.array(wl.gravity)
     assert np.abs(ma.sum(axis=0) - expect).max() <= 1e-9 * np.abs(ma).sum()
+
+
+def _full_size_vs_oracle(wl, product_lib, oracle_lib, more_steps):
+    """CUDA path against the oracle AT THE BENCH SIZE: neighbour build + 1 step with the oracle's canonical serial accumulation order,
+    then `more_steps` further steps with the oracle on all host threads (its atomic accumulation order varies at the 1e-16 level,
+    far below the 1e-10 bar; the candidate set stays bit-exact).  Sets bit-exact, every field within 1e-10 per element."""
+    import os
+    gpu, cpu = pair(wl, product_lib, oracle_lib)
+    es = (gpu, cpu)
+    both(es, lambda e: e.update_particle_neighbors(wl.rcut_inc, True))
+    cg, _ = gpu.interaction_counts()
+    cc, _ = cpu.interaction_counts()
+    assert np.array_equal(cg, cc), (cg, cc)
+    both(es, lambda e: e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, 1, 0))
+    n1, _ = check(gpu, cpu)
+    cpu.set_threads(os.cpu_count() or 1)
+    nb = [e.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, True, more_steps, 0) for e in es]
+    assert nb[0] == nb[1]
+    n2, errs = check(gpu, cpu)
+    _, ag = gpu.interaction_counts()
+    _, ac = cpu.interaction_counts()
+    assert np.array_equal(ag, ac)
+    return n1, n2, ag, errs
+
+
+def test_full_size_drum_vs_oracle(product_lib, oracle_lib):
+    """BASELINE configs[1] as bench.py runs it (1 M spheres in the rotating drum, ~3 M records): 1 step and 25 steps against the oracle"""
+    wl = workloads.rotating_drum(1_000_000)
+    n1, n2, active, errs = _full_size_vs_oracle(wl, product_lib, oracle_lib, 24)
+    assert n1 > 2_900_000 and active[0] > 1_000_000 and active[4] > 0, (n1, active)
+
+
+def test_full_size_octahedra_vs_oracle(product_lib, oracle_lib):
+    """BASELINE configs[2] as bench.py runs it (0.49 M octahedra, ~3 M records in the four particle-particle waves): 1 + 24 steps"""
+    wl = workloads.polyhedra_box((79, 79, 79), pitch=0.78)
+    n1, n2, active, errs = _full_size_vs_oracle(wl, product_lib, oracle_lib, 24)
+    assert n1 > 2_500_000 and active[:4].sum() > 10_000, (n1, active)
