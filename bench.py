@@ -393,14 +393,15 @@ def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=60, warmup=
     eng.set_timing(False)
     n_real = wl.particles.n
     eng.close()
-    npp = max(c.contact_pp_launches, 1)
-    t = c.contact_pp_ms / npp * 1e-3
+    t = c.contact_pp_ms / steps * 1e-3            # the two launches that cover the four particle-particle waves, per step
     rec = float(counts[:4].sum())
     hot = float(active[:4].sum())
     # the two launches' own traffic: detection reads ij + sub + flg (17 B) per record and, through L1/L2, the two vertex sets of every
-    # owner-partner pair (counted once per particle and wave family: 32 B x nv); the law pass moves 128 B + 6 sectors per record in contact
-    own = 17.0 * rec + 4.0 * hot + (128.0 + 192.0) * hot + n_real * (32.0 * 6 + 64.0)
-    alg = c.bytes_contact_algorithmic / npp
+    # owner-partner pair (counted once per particle: 32 B x 6 vertices + type/homothety sectors); the law pass moves 128 B of history /
+    # wrench + 6 particle sectors + the 4 B list entry per record in contact
+    own = 17.0 * rec + (128.0 + 192.0 + 4.0) * hot + n_real * (32.0 * 6 + 64.0)
+    # 184 B/record + 8 (sub) + 24 k of vertices (k = 2 V-V, 3 V-E, 1 + 3 V-F on triangles, 4 E-E) + 92 B/particle per wave
+    alg = sum(float(counts[w]) * (192.0 + 24.0 * k) for w, k in ((0, 2), (1, 3), (2, 4), (3, 4))) + 4 * 92.0 * n_real
     tp, cap = traffic_for(tr, "k_detect_poly_pp+k_law_poly_pp", "poly", steps, warmup)
     return {"workload": f"{n_real} octahedra, periodic packing (configs[2])", "value": c.interaction_updates / (ms * 1e-3),
             "unit": UNIT, "particle_steps_per_s": c.particle_steps / (ms * 1e-3), "steps": steps, "ms_per_step": ms / steps,
@@ -413,7 +414,8 @@ def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=60, warmup=
                          "frac_traffic": (tp / t / 1e9 / peak) if (tp and t > 0) else None,
                          "algorithmic_bytes_per_launch": alg, "frac_algorithmic": alg / t / 1e9 / peak if t > 0 else None,
                          "algorithmic_note": "SURVEY 8(d): 184 B/record + 8 (sub) + 24 k vertex bytes (k = 2 V-V, 3 V-E, 1+n_face V-F, 4 E-E) + 92 B/particle per wave",
-                         "mean_launch_ms": t * 1e3},
+                         "mean_launch_ms": t * 1e3,
+                         "note": "the detection pass is fp64-arithmetic bound (V-E / V-F / E-E closest-point tests on ~95 % records that do not touch), not HBM-bound"},
             "per_step_ms": {"contact_all": c.contact_ms / steps, "gather_fused": c.gather_ms / steps, "ghost": c.ghost_ms / steps,
                             "rebuild_amortised": c.rebuild_ms / steps}}
 
@@ -522,12 +524,16 @@ def main():
         w0 = time.time()
         t0 = time.perf_counter()
         for _ in range(ke):
-            eng.upload_dynamic(host)
+            # asynchronous entry points: the download of step n (all 22 fields), the upload of step n+1 (the arrays step n filled) and
+            # the kernels of step n+1 overlap on the full-duplex link; the host only waits at the end (and inside edb_run_verlet for
+            # the rebuild decision of the step)
+            eng.upload_dynamic_async(host)
             nr = eng.run_verlet(wl.dt, g, wl.rcut_inc, wl.symetric, 1, 0)
             if nr and world > 1:   # a rebuild may have migrated particles between bricks: the host mirror follows
+                eng.sync()
                 host = pinned_like(eng.download_particles())
             else:
-                eng.download_dynamic(host)
+                eng.download_dynamic_async(host)
         job.barrier()
         dt = time.perf_counter() - t0
         windows.append((w0, time.time()))
@@ -542,8 +548,9 @@ def main():
             iu_e, dt, h2d, d2h = float(t[0]), float(tm[1]), float(t[2]), float(t[3])
         e2e = {"value": iu_e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ke,
                "ms_per_step": 1e3 * dt / ke,
-               "what": "edb_upload_dynamic (r, v, vrot, orient from pinned host memory) -> edb_run_verlet(1 step) -> edb_download_dynamic "
-                       "(r, v, vrot, orient, f, mom, arot to pinned host memory), every step, all ranks"}
+               "what": "edb_upload_dynamic_async (r, v, vrot, orient from pinned host memory) -> edb_run_verlet(1 step) -> "
+                       "edb_download_dynamic_async (r, v, vrot, orient, f, mom, arot to pinned host memory), every step, all ranks; "
+                       "PCIe floor = d2h bytes / link bandwidth (the copies of consecutive steps overlap, the download is the longer leg)"}
 
     # ---- cost of one neighbour rebuild (outside the timed region; the drum moves too slowly to trigger one in K steps)
     eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)   # (the first explicit rebuild allocates the second set of wave buffers)

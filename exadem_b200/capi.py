@@ -25,6 +25,9 @@ _U64 = C.POINTER(C.c_uint64)
 _U32 = C.POINTER(C.c_uint32)
 
 
+DYN_ALL, DYN_STATE = 0x7F, 0x0F   # field masks of edb_download_dynamic_async
+
+
 class Config(C.Structure):
     _fields_ = [("lo", C.c_double * 3), ("hi", C.c_double * 3), ("glo", C.c_double * 3), ("ghi", C.c_double * 3),
                 ("cell_size", C.c_double), ("periodic", C.c_int32 * 3), ("mode", C.c_int32), ("device", C.c_int32),
@@ -468,6 +471,15 @@ class Engine:
     def download_dynamic(self, pa: ParticleArrays):
         v = pa.view()
         self._call("download_dynamic", C.byref(v))
+
+    def upload_dynamic_async(self, pa: ParticleArrays):
+        """pinned host arrays; returns once the copies are enqueued (see include/exadem_b200.h)"""
+        v = pa.view()
+        self._call("upload_dynamic_async", C.byref(v))
+
+    def download_dynamic_async(self, pa: ParticleArrays, field_mask: int = DYN_ALL):
+        v = pa.view()
+        self._call("download_dynamic_async", C.byref(v), C.c_uint32(field_mask))
 
     def num_particles(self):
         a, b = C.c_uint64(), C.c_uint64()

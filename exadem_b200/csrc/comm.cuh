@@ -392,7 +392,24 @@ struct Comm {
     }
     fan_epoch_pending = e;
   }
-  void land_pending(PView P, uint32_t nreal, unsigned long long* count, cudaStream_t st, uint64_t* launches) {
+  const double4* landing_of(uint32_t epoch) const { return p2p_land(p2p.base, p2p.cap, (int)(epoch & 1u)); }
+  // the remote ghosts of `epoch` (already landed: its mail was waited for) copied into the ghost slots; no mail, no count
+  void land_copy(PView P, uint32_t nreal, uint32_t epoch, cudaStream_t st, uint64_t* launches) {
+    uint32_t nrem = 0;
+    for (auto& kv : peers) nrem += kv.second.n_recv;
+    if (!nrem) return;
+    LandArgs L{};
+    L.P = P;
+    L.mail = p2p_mail(p2p.base, (int)(epoch & 1u));
+    L.nranks = nranks; L.me = rank; L.epoch = epoch; L.count = nullptr;
+    L.land = landing_of(epoch);
+    L.cap = p2p.cap; L.n = nrem; L.base = nreal + n_local_ghost;
+    k_ghost_land<<<std::min<uint32_t>((nrem + BLK - 1) / BLK, 592u), BLK, 0, st>>>(L);
+    (*launches)++;
+  }
+  // copy = false: only the mail is exchanged (our mail out, everybody's in, trigger counts summed); the caller reads the ghosts in
+  // the landing zone.  Returns the epoch that landed.
+  uint32_t land_pending(PView P, uint32_t nreal, unsigned long long* count, cudaStream_t st, uint64_t* launches, bool copy = true) {
     const uint32_t e = fan_epoch_pending;
     fan_epoch_pending = 0;
     const int par = (int)(e & 1u);
@@ -403,13 +420,14 @@ struct Comm {
     L.mail = p2p_mail(p2p.base, par);
     L.nranks = nranks; L.me = rank; L.epoch = e; L.count = count;
     L.land = p2p_land(p2p.base, p2p.cap, par);
-    L.cap = p2p.cap; L.n = nrem; L.base = nreal + n_local_ghost;
+    L.cap = p2p.cap; L.n = copy ? nrem : 0; L.base = nreal + n_local_ghost;
     for (int r = 0; r < nranks; r++)
       if (r != rank) L.out_mail[L.n_out++] = p2p_mail(p2p.peer_base[r], par) + rank;
-    const uint32_t nb = nrem ? std::min<uint32_t>((nrem + BLK - 1) / BLK, 592u) : 1u;
+    const uint32_t nb = L.n ? std::min<uint32_t>((L.n + BLK - 1) / BLK, 592u) : 1u;
     k_ghost_land<<<nb, BLK, 0, st>>>(L);
     (*launches)++;
     p2p.exchanges++;
+    return e;
   }
   // per-step refresh over peer memory; `count` (device, nullable) is all-reduced (sum) in place as a by-product
   void exchange_ghosts_p2p(PView P, uint32_t nreal, unsigned long long* count, cudaStream_t st, uint64_t* launches) {

@@ -96,30 +96,34 @@ inline PView view(PArr& a) {
 //   flg  = bit0 swap, bits1-2 ghost
 //   ft   = (friction.xyz, bits{partner id})     history + the key used to carry it across rebuilds
 //   mo   = (moment.xyz, 0)                      history
-//   fd   = (f.xyz, dn)   cp = (contact point.xyz, 0)     ContactState (fn is derived as f - ft on export)
+//   fc   = the wrench of the last evaluation, 64 bytes per record: fc[2k] = fd = (f.xyz, dn), fc[2k+1] = cp = (contact point.xyz, 0)
+//          ContactState (fn is derived as f - ft on export).  One aligned 64-byte unit: the contact kernel writes it with two
+//          adjacent 32-byte stores and the gather fetches both halves of a partner's wrench from one 128-byte line.
 struct Wave {
   DevBuf<uint2> ij, sub;
   DevBuf<uint8_t> flg;
-  DevBuf<double4> ft, mo, fd, cp;
+  DevBuf<double4> ft, mo, fc;
   DevBuf<uint32_t> off;  // nreal+1 : CSR by owner slot
   uint64_t n = 0;
   void ensure(size_t nn, bool need_sub) {
-    ij.ensure(nn); if (need_sub) sub.ensure(nn); flg.ensure(nn); ft.ensure(nn); mo.ensure(nn); fd.ensure(nn); cp.ensure(nn);
+    ij.ensure(nn); if (need_sub) sub.ensure(nn); flg.ensure(nn); ft.ensure(nn); mo.ensure(nn); fc.ensure(2 * nn);
   }
   void ensure_keep(size_t nn, bool need_sub, cudaStream_t s) {  // grows and preserves the records (twins are appended)
     ij.ensure(nn, true, s); if (need_sub) sub.ensure(nn, true, s); flg.ensure(nn, true, s); ft.ensure(nn, true, s); mo.ensure(nn, true, s);
-    fd.ensure(nn, true, s); cp.ensure(nn, true, s);
+    fc.ensure(2 * nn, true, s);
   }
-  void release() { ij.release(); sub.release(); flg.release(); ft.release(); mo.release(); fd.release(); cp.release(); off.release(); n = 0; }
+  void release() { ij.release(); sub.release(); flg.release(); ft.release(); mo.release(); fc.release(); off.release(); n = 0; }
 };
 struct WView {
   uint2 *ij, *sub;
   uint8_t* flg;
-  double4 *ft, *mo, *fd, *cp;
+  double4 *ft, *mo, *fc;
   uint32_t* off;
   uint32_t n;
+  __host__ __device__ __forceinline__ double4* fd(size_t k) const { return fc + 2 * k; }
+  __host__ __device__ __forceinline__ double4* cp(size_t k) const { return fc + 2 * k + 1; }
 };
-inline WView view(Wave& w) { return WView{w.ij.p, w.sub.p, w.flg.p, w.ft.p, w.mo.p, w.fd.p, w.cp.p, w.off.p, (uint32_t)w.n}; }
+inline WView view(Wave& w) { return WView{w.ij.p, w.sub.p, w.flg.p, w.ft.p, w.mo.p, w.fc.p, w.off.p, (uint32_t)w.n}; }
 
 // shapes flattened for the device
 struct ShapeDev {

@@ -37,7 +37,58 @@ __device__ __forceinline__ double4 ldg4(const double4* p) {
 __device__ __forceinline__ void st4(double4* p, const double4 v) {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
 }
+// L2 residency hints (createpolicy + .L2::cache_hint).  The per-step working set of a 1 M-particle brick is ~0.8 GB, the L2 126 MB:
+// plain LRU keeps nothing from one kernel to the next.  The three gathered particle sectors (pr, vm, wg: 96 MB per 1 M particles)
+// are what both per-step kernels touch — the contact kernel by scattered gathers, the gather by streaming read + write — so they
+// are loaded and stored evict_last, and everything that is touched once per step (history, incidence codes, inertia, backup
+// positions, orientations) evict_first.  With bricks too large for the L2 the hints cost nothing.
+struct L2Pol {
+  unsigned long long keep, stream;
+};
+__device__ __forceinline__ L2Pol l2_policies() {
+  L2Pol p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+  return p;
+}
+__device__ __forceinline__ double4 ld4h(const double4* p, unsigned long long pol) {
+  double4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ double4 ldg4h(const double4* p, unsigned long long pol) {
+  double4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st4h(double4* p, const double4 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double ld1h(const double* p, unsigned long long pol) {
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ldu32h(const uint32_t* p, unsigned long long pol) {
+  uint32_t v;
+  asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+// L1 / L2 prefetch of the line holding *p: a load the thread will issue later finds it on chip; holds no register meanwhile
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #else
+struct L2Pol {
+  unsigned long long keep, stream;
+};
+inline L2Pol l2_policies() { return L2Pol{0, 0}; }
+inline double4 ld4h(const double4* p, unsigned long long) { return *p; }
+inline double4 ldg4h(const double4* p, unsigned long long) { return *p; }
+inline void st4h(double4* p, const double4 v, unsigned long long) { *p = v; }
+inline double ld1h(const double* p, unsigned long long) { return *p; }
+inline uint32_t ldu32h(const uint32_t* p, unsigned long long) { return *p; }
+inline void prefetch_l1(const void*) {}
+inline void prefetch_l2(const void*) {}
 inline double4 ld4(const double4* p) { return *p; }
 inline double4 ldg4(const double4* p) { return *p; }
 inline void st4(double4* p, const double4 v) { *p = v; }

@@ -69,8 +69,10 @@ struct edb_context {
   uint64_t nbh_replays = 0;
   DevBuf<FanEnt> fan_ent;
   bool have_fan = false, ghost_pushed = false;
+  uint32_t ghost_in_landing = 0;   // epoch whose remote ghosts live in the landing zone only (0: the ghost slots are current)
   // debugging switches read once at creation: EDB_NO_FAN (separate ghost kernels), EDB_NBH_POLY_PER_THREAD, EDB_NBH_NO_REPLAY
   bool env_no_fan = false, env_nbh_per_thread = false, env_nbh_no_replay = false;
+  bool env_land_copy = false;         // EDB_LAND_COPY: always copy the landing zone into the ghost slots (the round-1 path)
   bool env_drivers_unfused = false;   // EDB_DRIVERS_UNFUSED: moving drivers through the operator-by-operator loop on one rank too
   uint32_t* d_need_count = nullptr;  // chunk queue of the persistent sphere contact kernel / length of the polyhedron work list
   DevBuf<uint32_t> need;             // work list of k_detect_poly_pp -> k_law_poly_pp
@@ -137,6 +139,13 @@ struct edb_context {
   int ibp_groups = 0;
   double physical_time = 0, system_mass = 0;
   bool have_system_mass = false;
+  // asynchronous host <-> device path of a host-owned grid (edb_upload_dynamic_async / edb_download_dynamic_async): own copy
+  // streams so that the download of step n, the upload of step n+1 and the kernels of step n+1 overlap on a full-duplex link
+  cudaStream_t st_up = nullptr, st_dn = nullptr;
+  cudaEvent_t ev_up_done = nullptr, ev_up_consumed = nullptr, ev_dn_ready[2] = {}, ev_dn_done[2] = {}, ev_field[22] = {};
+  bool up_consumed_valid = false, dn_done_valid[2] = {false, false}, field_valid[22] = {};
+  int dn_parity = 0;
+  DevBuf<double> stage_up, stage_dn[2];
   // staging for host transfers
   DevBuf<double> stage;
   DevBuf<uint64_t> stage_u64;
@@ -319,6 +328,7 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
   c->cfg = *cfg;
   if (c->cfg.nranks < 1) c->cfg.nranks = 1;
   c->env_no_fan = getenv("EDB_NO_FAN") != nullptr;
+  c->env_land_copy = getenv("EDB_LAND_COPY") != nullptr;
   c->env_nbh_per_thread = getenv("EDB_NBH_POLY_PER_THREAD") != nullptr;
   c->env_nbh_no_replay = getenv("EDB_NBH_NO_REPLAY") != nullptr;
   c->env_drivers_unfused = getenv("EDB_DRIVERS_UNFUSED") != nullptr;
@@ -367,6 +377,14 @@ extern "C" int edb_destroy(edb_context* c) {
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->st);
   if (c->st2) { cudaStreamSynchronize(c->st2); cudaStreamDestroy(c->st2); }
+  if (c->st_up) {
+    cudaStreamSynchronize(c->st_up); cudaStreamSynchronize(c->st_dn);
+    cudaStreamDestroy(c->st_up); cudaStreamDestroy(c->st_dn);
+    cudaEventDestroy(c->ev_up_done); cudaEventDestroy(c->ev_up_consumed);
+    for (int k = 0; k < 2; k++) { cudaEventDestroy(c->ev_dn_ready[k]); cudaEventDestroy(c->ev_dn_done[k]); }
+    for (int k = 0; k < 22; k++) cudaEventDestroy(c->ev_field[k]);
+    c->stage_up.release(); c->stage_dn[0].release(); c->stage_dn[1].release();
+  }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   c->comm.destroy();
@@ -411,11 +429,15 @@ extern "C" int edb_destroy(edb_context* c) {
 static void quiesce(edb_context* c) {
   if (c->st) CK(cudaStreamSynchronize(c->st));
   if (c->st2) CK(cudaStreamSynchronize(c->st2));
+  if (c->st_up) CK(cudaStreamSynchronize(c->st_up));
+  if (c->st_dn) CK(cudaStreamSynchronize(c->st_dn));
 }
 
 extern "C" int edb_sync(edb_context* c) {
   API_BEGIN(c)
   CK(cudaStreamSynchronize(c->st));
+  if (c->st_up) CK(cudaStreamSynchronize(c->st_up));   // asynchronous host copies, if any were issued
+  if (c->st_dn) CK(cudaStreamSynchronize(c->st_dn));
   API_END(c)
 }
 
@@ -894,6 +916,70 @@ extern "C" int edb_download_dynamic(edb_context* c, edb_particles* P) {
   API_END(c)
 }
 
+// ---- asynchronous forms (pinned host buffers) ------------------------------------------------------------------------------------
+static void async_streams(edb_context* c) {
+  if (c->st_up) return;
+  CK(cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->st_dn, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_up_done, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_up_consumed, cudaEventDisableTiming));
+  for (int k = 0; k < 2; k++) {
+    CK(cudaEventCreateWithFlags(&c->ev_dn_ready[k], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_dn_done[k], cudaEventDisableTiming));
+  }
+  for (int k = 0; k < 22; k++) CK(cudaEventCreateWithFlags(&c->ev_field[k], cudaEventDisableTiming));
+}
+extern "C" int edb_upload_dynamic_async(edb_context* c, const edb_particles* P) {
+  API_BEGIN(c)
+  const uint64_t n = c->nreal;
+  if (!P || P->n != n) throw StateError{EDB_ERR_INVALID, "particle count mismatch"};
+  async_streams(c);
+  double* f[13] = {P->rx, P->ry, P->rz, P->vx, P->vy, P->vz, P->vrotx, P->vroty, P->vrotz, P->qw, P->qx, P->qy, P->qz};
+  for (int i = 0; i < 13; i++)
+    if (!f[i]) throw StateError{EDB_ERR_INVALID, "upload_dynamic needs r, v, vrot and orient"};
+  if (c->stage_up.cap < 13 * n + 1) { quiesce(c); c->stage_up.ensure(13 * n + 1); }
+  // the staging area is free once the scatter kernel of the previous upload has read it
+  if (c->up_consumed_valid) CK(cudaStreamWaitEvent(c->st_up, c->ev_up_consumed, 0));
+  for (int i = 0; i < 13; i++) {
+    // the same host array may still be the target of the previous asynchronous download: field by field, so that on a full-duplex
+    // link this upload runs one field behind that download instead of after it
+    if (c->field_valid[i]) CK(cudaStreamWaitEvent(c->st_up, c->ev_field[i], 0));
+    CK(cudaMemcpyAsync(c->stage_up.p + (size_t)i * n, f[i], n * 8, cudaMemcpyHostToDevice, c->st_up));
+  }
+  CK(cudaEventRecord(c->ev_up_done, c->st_up));
+  CK(cudaStreamWaitEvent(c->st, c->ev_up_done, 0));
+  LAUNCH(c, k_scatter_dynamic, nblk(n), BLK, 0, view(c->pa), c->stage_up.p, (uint32_t)n);
+  CK(cudaEventRecord(c->ev_up_consumed, c->st));
+  c->up_consumed_valid = true;
+  API_END(c)
+}
+extern "C" int edb_download_dynamic_async(edb_context* c, edb_particles* P, uint32_t field_mask) {
+  API_BEGIN(c)
+  const uint64_t n = c->nreal;
+  if (!P || P->n != n) throw StateError{EDB_ERR_INVALID, "particle count mismatch"};
+  async_streams(c);
+  const int par = (c->dn_parity ^= 1);
+  if (c->stage_dn[par].cap < 22 * n + 1) { quiesce(c); c->stage_dn[par].ensure(22 * n + 1); }
+  // two staging areas: the snapshot of step n+1 is taken while the copy of step n is still draining
+  if (c->dn_done_valid[par]) CK(cudaStreamWaitEvent(c->st, c->ev_dn_done[par], 0));
+  LAUNCH(c, k_gather_dynamic, nblk(n), BLK, 0, view(c->pa), c->stage_dn[par].p, (uint32_t)n);
+  CK(cudaEventRecord(c->ev_dn_ready[par], c->st));
+  CK(cudaStreamWaitEvent(c->st_dn, c->ev_dn_ready[par], 0));
+  double* f[22] = {P->rx, P->ry, P->rz, P->vx, P->vy, P->vz, P->vrotx, P->vroty, P->vrotz, P->qw, P->qx, P->qy, P->qz,
+                   P->fx, P->fy, P->fz, P->momx, P->momy, P->momz, P->arotx, P->aroty, P->arotz};
+  // groups: bit 0 r, 1 v, 2 vrot, 3 orient, 4 f (acceleration), 5 mom, 6 arot
+  static const int group_of_field[22] = {0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 5, 5, 5, 6, 6, 6};
+  for (int i = 0; i < 22; i++) {
+    if (!f[i] || !((field_mask >> group_of_field[i]) & 1u)) continue;
+    CK(cudaMemcpyAsync(f[i], c->stage_dn[par].p + (size_t)i * n, n * 8, cudaMemcpyDeviceToHost, c->st_dn));
+    CK(cudaEventRecord(c->ev_field[i], c->st_dn));
+    c->field_valid[i] = true;
+  }
+  CK(cudaEventRecord(c->ev_dn_done[par], c->st_dn));
+  c->dn_done_valid[par] = true;
+  API_END(c)
+}
+
 extern "C" int edb_num_particles(edb_context* c, uint64_t* nr, uint64_t* ng) {
   if (!c) return EDB_ERR_INVALID;
   if (nr) *nr = c->nreal;
@@ -903,16 +989,28 @@ extern "C" int edb_num_particles(edb_context* c, uint64_t* nr, uint64_t* ng) {
 
 // ---- rebuild -----------------------------------------------------------------------------------------------------
 // trig (device, nullable): the local rebuild-trigger count of the step, summed over the ranks in place on the way
-static void ghost_refresh(edb_context* c, bool all, unsigned long long* trig = nullptr) {
+// Copies the remote ghosts of the last landed epoch from the landing zone into the ghost slots (they were being read in place).
+static void ghosts_home(edb_context* c) {
+  if (!c->ghost_in_landing) return;
+  ScopedTimer tm(c, B_GHOST);
+  c->comm.land_copy(view(c->pa), c->nreal, c->ghost_in_landing, c->st, &c->ctr.kernel_launches);
+  c->ghost_in_landing = 0;
+}
+// in_place: the caller's contact kernels can read remote ghosts from the landing zone (the wave-0 sphere kernel inside
+// edb_run_verlet) — the landing launch then only exchanges the mail (epoch + rebuild-trigger count) and copies nothing.
+static void ghost_refresh(edb_context* c, bool all, unsigned long long* trig = nullptr, bool in_place = false) {
   if (c->nghost == 0 && c->cfg.nranks == 1) return;
   if (!all && c->ghost_pushed) {   // the previous k_gather<2> stored the images itself; remote ones only have to land
     c->ghost_pushed = false;
     if (c->cfg.nranks > 1) {
       ScopedTimer tm(c, B_GHOST);
-      c->comm.land_pending(view(c->pa), c->nreal, trig, c->st, &c->ctr.kernel_launches);
+      const bool stay = in_place && !c->poly() && !c->env_land_copy;
+      const uint32_t e = c->comm.land_pending(view(c->pa), c->nreal, trig, c->st, &c->ctr.kernel_launches, !stay);
+      c->ghost_in_landing = stay ? e : 0;
     }
     return;
   }
+  ghosts_home(c);
   c->ghost_pushed = false;
   c->comm.fan_epoch_pending = 0;
   ScopedTimer tm(c, B_GHOST);
@@ -1156,6 +1254,7 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   // 0. multi-GPU: particles that left the brick migrate (with their interaction history) before re-binning
   const bool multi = c->cfg.nranks > 1;
   c->ghost_pushed = false;
+  c->ghost_in_landing = 0;   // the ghost layer is rebuilt from scratch below
   c->comm.fan_epoch_pending = 0;
   c->have_fan = false;
   const uint32_t n_before = c->nreal;   // slots the previous waves refer to
@@ -1507,7 +1606,14 @@ extern "C" int edb_freeze_particles(edb_context* c) {
 template <int LAW>
 static void launch_contact_waves(edb_context* c, double dt, const unsigned long long* gate, unsigned long long* zero_flag) {
   const bool poly = c->poly();
-  ContactArgs A{view(c->pa), WView{}, c->prm, c->drv.p, c->vert.p, c->S, dt, 0, c->symetric, c->M, gate, zero_flag};
+  ContactArgs A{view(c->pa), WView{}, c->prm, c->drv.p, c->vert.p, c->S, dt, 0, c->symetric, c->M, gate, zero_flag,
+                nullptr, nullptr, nullptr, 0xffffffffu};
+  if (c->ghost_in_landing) {   // spheres on several GPUs, inside edb_run_verlet: remote ghosts are read from the landing zone
+    const uint32_t lo = c->nreal + c->comm.n_local_ghost;
+    const double4* land = c->comm.landing_of(c->ghost_in_landing);
+    A.rem_lo = lo;
+    A.g_pr = land - lo; A.g_vm = land + (size_t)c->comm.p2p.cap - lo; A.g_wg = land + 2 * (size_t)c->comm.p2p.cap - lo;
+  }
   // the gather of the previous step left the chunk queue at zero when it ran as k_gather<2>; otherwise it is cleared here
   const bool queue_clean = c->queue_clean;
   c->queue_clean = false;
@@ -1894,11 +2000,11 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
     if (!trig) {
       const bool rb = rebuild_every > 0 && ((it + 1) % rebuild_every) == 0;
       if (rb) { rebuild(c, rcut_inc, symetric); nb++; }
-      else { ghost_refresh(c, false); compute_vertices(c, it > 0); }
+      else { ghost_refresh(c, false, nullptr, true); compute_vertices(c, it > 0); }
       step_kernels(nullptr);
     } else {
       const edb_counters snap = c->ctr;
-      ghost_refresh(c, false, c->d_sflag + slot);
+      ghost_refresh(c, false, c->d_sflag + slot, true);
       trigger_publish(c, slot);
       compute_vertices(c, it > 0);
       step_kernels(c->d_sflag + slot);
@@ -1916,6 +2022,7 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
     c->ctr.particle_steps += c->nreal;
     tcur += dt;
   }
+  ghosts_home(c);   // the ghost slots are current again for whoever reads them next (operators, views, the next rebuild)
   c->physical_time = tcur;
   if (n_rebuilds) *n_rebuilds = nb;
   API_END(c)
@@ -2073,8 +2180,7 @@ extern "C" int edb_import_interactions(edb_context* c, const edb_interaction* in
       CK(cudaMemcpy(w.flg.p, flg.data(), m, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(w.ft.p, ft.data(), m * sizeof(double4), cudaMemcpyHostToDevice));
       CK(cudaMemcpy(w.mo.p, mo.data(), m * sizeof(double4), cudaMemcpyHostToDevice));
-      CK(cudaMemset(w.fd.p, 0, m * sizeof(double4)));
-      CK(cudaMemset(w.cp.p, 0, m * sizeof(double4)));
+      CK(cudaMemset(w.fc.p, 0, 2 * m * sizeof(double4)));
     }
   }
   c->have_prev = true;   // valid history source; contact operators still require a rebuild (have_inc = false)

@@ -582,8 +582,8 @@ __global__ void k_history(WView nw, WView ow, const uint32_t* __restrict__ new2o
     if (!(ofl & 8)) return;  // the old record was not in contact: no history (its payload is zero)
     nw.ft[k] = make_double4(oft.x, oft.y, oft.z, ft.w);
     if (ofl & 16) nw.mo[k] = ow.mo[s];
-    nw.fd[k] = make_double4(0, 0, 0, 0);  // the wrench of the old evaluation does not survive the rebuild
-    nw.cp[k] = make_double4(0, 0, 0, 0);
+    *nw.fd(k) = make_double4(0, 0, 0, 0);  // the wrench of the old evaluation does not survive the rebuild
+    *nw.cp(k) = make_double4(0, 0, 0, 0);
     nw.flg[k] = fl | 8 | (ofl & 16);
     return;
   }

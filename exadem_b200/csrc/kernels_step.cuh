@@ -14,6 +14,39 @@
 
 namespace edb {
 
+// ---- tuning switches (profiles/r2_sweep_*.log: measured on the 1 M-sphere drum, 200 steps) ---------------------------------------
+// None of the latency / residency devices below pays on this workload; they stay as switches so that the measurement can be repeated:
+//   EDB_G_PREFETCH   L1 prefetch of the gather's own sectors used after the incidence walk        gather 0.115 -> 0.120 ms
+//   EDB_G_WIDE       all incidence codes, then all flag bytes, then the wrenches (EDB_G_CU wide)  0.115 -> 0.114 (6), 0.124 (8: spills)
+//   EDB_PP_PREFETCH  L1 prefetch of the next law round's operands in the contact kernel           contact 0.104 -> 0.104 ms
+//   EDB_L2_KEEP      pr / vm / wg evict_last (createpolicy + .L2::cache_hint) in both kernels     step 0.2486 -> 0.2488 ms
+//   EDB_L2_STREAM    once-per-step data (history, codes, inertia, backup, orientation) evict_first  0.2486 -> 0.2489 ms
+//   EDB_G_REVERSE    gather walks the blocks from last to first (what the contact kernel wrote last)  0.2486 -> 0.2491 ms
+#ifndef EDB_GU
+#define EDB_GU 2
+#endif
+#ifndef EDB_G_PREFETCH
+#define EDB_G_PREFETCH 0
+#endif
+#ifndef EDB_G_WIDE
+#define EDB_G_WIDE 0
+#endif
+#ifndef EDB_G_CU
+#define EDB_G_CU 6
+#endif
+#ifndef EDB_PP_PREFETCH
+#define EDB_PP_PREFETCH 0
+#endif
+#ifndef EDB_L2_KEEP
+#define EDB_L2_KEEP 0
+#endif
+#ifndef EDB_L2_STREAM
+#define EDB_L2_STREAM 0
+#endif
+#ifndef EDB_G_REVERSE
+#define EDB_G_REVERSE 0
+#endif
+
 __device__ __forceinline__ uint32_t group_of(const double4& wg) {
   return (uint32_t)(((unsigned long long)__double_as_longlong(wg.w)) >> 32);
 }
@@ -180,6 +213,11 @@ struct ContactArgs {
   // speculative step (edb_run_verlet): non-zero *gate = "this step needs a neighbour rebuild first" -> the kernel does nothing
   const unsigned long long* gate;
   unsigned long long* zero_flag;   // spheres, speculative loop: the next trigger slot, zeroed by the wave-0 kernel (saves a memset)
+  // multi-GPU, inside edb_run_verlet: the ghosts of neighbour bricks are read where the peers' gathers stored them — this rank's
+  // landing zone of the step's parity (comm.cuh) — instead of being copied into the ghost slots first.  Slots >= rem_lo are remote
+  // ghosts; g_pr / g_vm / g_wg are already offset by -rem_lo.  rem_lo = 0xffffffff: everything is read from the particle arrays.
+  const double4 *g_pr, *g_vm, *g_wg;
+  uint32_t rem_lo;
 };
 __device__ __forceinline__ bool gated(const unsigned long long* gate) { return gate && *gate; }
 
@@ -197,17 +235,18 @@ struct Hist {
 };
 
 // finish one record.  `contact` already includes the cohesive extension.  H is valid when `have_h`.
-template <int LAW>
+template <int LAW, bool HINT = false>
 __device__ __forceinline__ void finish_record(const ContactArgs& A, uint32_t k, uint8_t fl, bool contact, const Contact& c,
                                               const Params& cp, double meff, double reff, v3 ri, v3 vi, v3 wi, v3 pj, v3 vj, v3 wj,
-                                              const Hist& H) {
+                                              const Hist& H, unsigned long long pol_stream = 0) {
   uint8_t nf = fl;
   if (contact) {
     v3 ft = mk3(H.ft.x, H.ft.y, H.ft.z), mom = mk3(H.mo.x, H.mo.y, H.mo.z), f = mk3(0, 0, 0);
     contact_force<LAW>(c.dn, c.n, A.dt, cp, meff, reff, ft, c.cp, ri, vi, f, mom, wi, pj, vj, wj);
-    st4(A.w.ft + k, make_double4(ft.x, ft.y, ft.z, H.ft.w));
-    st4(A.w.fd + k, make_double4(f.x, f.y, f.z, c.dn));
-    st4(A.w.cp + k, make_double4(c.cp.x, c.cp.y, c.cp.z, 0));
+    if (HINT) st4h(A.w.ft + k, make_double4(ft.x, ft.y, ft.z, H.ft.w), pol_stream);   // the history is next read one step from now
+    else st4(A.w.ft + k, make_double4(ft.x, ft.y, ft.z, H.ft.w));
+    st4(A.w.fd(k), make_double4(f.x, f.y, f.z, c.dn));
+    st4(A.w.cp(k), make_double4(c.cp.x, c.cp.y, c.cp.z, 0));
     const bool live = !is_zero(mom);   // NaN components count as live (x == 0.0 is false for NaN)
     if (live || (fl & FLG_MOM)) st4(A.w.mo + k, make_double4(mom.x, mom.y, mom.z, 0.0));
     nf = (uint8_t)((fl | FLG_HOT) & ~FLG_MOM) | (live ? FLG_MOM : 0);
@@ -238,8 +277,12 @@ __device__ __forceinline__ void finish_record(const ContactArgs& A, uint32_t k, 
 constexpr int CHUNK = 128;
 
 template <int LAW>
-__device__ __forceinline__ bool detect_need(const ContactArgs& A, const uint2 ij) {
-  const double4 pi = ldg4(A.P.pr + ij.x), pj = ldg4(A.P.pr + ij.y);
+__device__ __forceinline__ bool detect_need(const ContactArgs& A, const uint2 ij, unsigned long long pol_keep) {
+#if EDB_L2_KEEP
+  const double4 pi = ldg4h(A.P.pr + ij.x, pol_keep), pj = ldg4h((ij.y >= A.rem_lo ? A.g_pr : A.P.pr) + ij.y, pol_keep);
+#else
+  const double4 pi = ldg4(A.P.pr + ij.x), pj = ldg4((ij.y >= A.rem_lo ? A.g_pr : A.P.pr) + ij.y);
+#endif
   const Contact c = detect_vv(mk3(pi.x, pi.y, pi.z), pi.w, mk3(pj.x, pj.y, pj.z), pj.w);
   bool need = c.hit;
   if (LAW == LAW_COHESIVE) {
@@ -261,6 +304,7 @@ __global__ void __launch_bounds__(PP_BLK, PP_MINB) k_contact_sphere_pp(ContactAr
   if (gated(A.gate)) return;
   if (A.zero_flag && blockIdx.x == 0 && threadIdx.x == 0) *A.zero_flag = 0;   // trigger accumulator of the gather that follows
   __shared__ uint4 s_ent[PP_BLK / 32][CHUNK];
+  const L2Pol pol = l2_policies();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint4* ents = s_ent[wid];
   const uint32_t nchunk = (A.w.n + CHUNK - 1) / CHUNK;
@@ -291,7 +335,7 @@ __global__ void __launch_bounds__(PP_BLK, PP_MINB) k_contact_sphere_pp(ContactAr
     for (int u = 0; u < 4; u++) need[u] = (f4 >> (8 * u)) & FLG_HOT;
 #pragma unroll
     for (int u = 0; u < 4; u++)
-      if (!need[u] && k0 + u < A.w.n) need[u] = detect_need<LAW>(A, ij[u]);
+      if (!need[u] && k0 + u < A.w.n) need[u] = detect_need<LAW>(A, ij[u], EDB_L2_KEEP ? pol.keep : 0ull);
     uint32_t c = 0;
 #pragma unroll
     for (int u = 0; u < 4; u++) c += need[u] ? 1u : 0u;
@@ -306,11 +350,31 @@ __global__ void __launch_bounds__(PP_BLK, PP_MINB) k_contact_sphere_pp(ContactAr
       const uint4 e = ents[i];
       const uint32_t k = e.x;
       const uint8_t fl = (uint8_t)e.w;
-      const double4 pi = ldg4(A.P.pr + e.y), pj = ldg4(A.P.pr + e.z);
-      const double4 wi = ldg4(A.P.wg + e.y), wj = ldg4(A.P.wg + e.z);
-      const double4 vi = ldg4(A.P.vm + e.y), vj = ldg4(A.P.vm + e.z);
+#if EDB_PP_PREFETCH
+      if (i + 32 < total) {   // operands of this lane's entry of the NEXT round: on their way while this round's law is evaluated
+        const uint4 en = ents[i + 32];
+        const bool rem = en.z >= A.rem_lo;
+        prefetch_l1(A.P.pr + en.y); prefetch_l1((rem ? A.g_pr : A.P.pr) + en.z); prefetch_l1(A.P.wg + en.y);
+        prefetch_l1((rem ? A.g_wg : A.P.wg) + en.z); prefetch_l1(A.P.vm + en.y); prefetch_l1((rem ? A.g_vm : A.P.vm) + en.z);
+        prefetch_l1(A.w.ft + en.x);
+      }
+#endif
+      const bool remj = e.z >= A.rem_lo;   // j is a neighbour brick's particle: its sectors are in the landing zone
+#if EDB_L2_KEEP
+      const double4 pi = ldg4h(A.P.pr + e.y, pol.keep), pj = ldg4h((remj ? A.g_pr : A.P.pr) + e.z, pol.keep);
+      const double4 wi = ldg4h(A.P.wg + e.y, pol.keep), wj = ldg4h((remj ? A.g_wg : A.P.wg) + e.z, pol.keep);
+      const double4 vi = ldg4h(A.P.vm + e.y, pol.keep), vj = ldg4h((remj ? A.g_vm : A.P.vm) + e.z, pol.keep);
+#else
+      const double4 pi = ldg4(A.P.pr + e.y), pj = ldg4((remj ? A.g_pr : A.P.pr) + e.z);
+      const double4 wi = ldg4(A.P.wg + e.y), wj = ldg4((remj ? A.g_wg : A.P.wg) + e.z);
+      const double4 vi = ldg4(A.P.vm + e.y), vj = ldg4((remj ? A.g_vm : A.P.vm) + e.z);
+#endif
       Hist H;
+#if EDB_L2_STREAM
+      H.ft = ld4h(A.w.ft + k, pol.stream);
+#else
       H.ft = ld4(A.w.ft + k);
+#endif
       H.mo = (fl & FLG_MOM) ? ld4(A.w.mo + k) : make_double4(0, 0, 0, 0);
       const v3 ri = mk3(pi.x, pi.y, pi.z), rj = mk3(pj.x, pj.y, pj.z);
       const Contact ct = detect_vv(ri, pi.w, rj, pj.w);
@@ -319,8 +383,13 @@ __global__ void __launch_bounds__(PP_BLK, PP_MINB) k_contact_sphere_pp(ContactAr
       if (LAW == LAW_COHESIVE) contact = contact || ct.dn <= cp.dncut;
       const double meff = (vi.w * vj.w) / (vi.w + vj.w);   // common_kernels.hpp:93-96
       const double reff = (pi.w * pj.w) / (pi.w + pj.w);   // :99-102
+#if EDB_L2_STREAM
+      finish_record<LAW, true>(A, k, fl, contact, ct, cp, meff, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), rj,
+                               mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z), H, pol.stream);
+#else
       finish_record<LAW>(A, k, fl, contact, ct, cp, meff, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), rj,
                          mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z), H);
+#endif
     }
     __syncwarp();
     chunk = nwarp + __shfl_sync(0xffffffffu, next, 0);
@@ -531,8 +600,8 @@ __global__ void __launch_bounds__(BLK) k_contact_mesh(ContactArgs A) {
     contact_force<LAW>(c.dn, c.n, A.dt, cp, vi.w, reff, ft, c.cp, D.center, D.vel, f, mom, D.vrot, ri, v_i, w_i);
     // stored: fd = f of the law (the particle receives -f, see the gather), friction negated (contact.hpp:417)
     st4(A.w.ft + k, make_double4(-ft.x, -ft.y, -ft.z, H.ft.w));
-    st4(A.w.fd + k, make_double4(f.x, f.y, f.z, c.dn));
-    st4(A.w.cp + k, make_double4(c.cp.x, c.cp.y, c.cp.z, 0));
+    st4(A.w.fd(k), make_double4(f.x, f.y, f.z, c.dn));
+    st4(A.w.cp(k), make_double4(c.cp.x, c.cp.y, c.cp.z, 0));
     const bool live = !is_zero(mom);
     if (live || (fl & FLG_MOM)) st4(A.w.mo + k, make_double4(mom.x, mom.y, mom.z, 0.0));
     const uint8_t nf = (uint8_t)((fl | FLG_HOT) & ~FLG_MOM) | (live ? FLG_MOM : 0);
@@ -549,7 +618,7 @@ __global__ void k_state(ContactArgs A, double* __restrict__ dn, double* __restri
   if (k >= A.w.n) return;
   const uint8_t fl = A.w.flg[k];
   if (fl & FLG_HOT) {
-    const double4 fd = ld4(A.w.fd + k), c4 = ld4(A.w.cp + k), f4 = ld4(A.w.ft + k);
+    const double4 fd = ld4(A.w.fd(k)), c4 = ld4(A.w.cp(k)), f4 = ld4(A.w.ft + k);
     dn[k] = fd.w;
     cp[3 * k] = c4.x; cp[3 * k + 1] = c4.y; cp[3 * k + 2] = c4.z;
     if (A.type == 11 || A.type == 12) {  // fn = friction - f with the friction BEFORE its sign flip (contact.hpp:409,417)
@@ -633,31 +702,46 @@ __device__ __forceinline__ void add_wrench(const double4& fd, const double4& cp,
 //         already hold the particle: one pass over the particle arrays per time step instead of three.  The intermediate
 //         acceleration / moment / angular acceleration are not stored (nothing reads them before the next gather overwrites
 //         them; the last step of edb_run_verlet runs FUSE 1, so the state a caller can observe is complete).
-#ifndef EDB_GU
-#define EDB_GU 2
-#endif
 #ifndef EDB_G_MINB
 #define EDB_G_MINB 3
 #endif
 constexpr int GU = EDB_GU;
 template <int FUSE, bool POLY>
 __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constant__ GatherArgs A, const __grid_constant__ FanArgs FAN) {
+#if EDB_G_REVERSE
+  const uint32_t p = (gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x;
+#else
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+#endif
   if (gated(A.gate)) return;
   if (p >= A.nreal) return;   // (exited lanes are not waited for by the full-mask reduction of the FUSE 2 trigger)
+  const L2Pol pol = l2_policies();
+  constexpr bool KEEP = EDB_L2_KEEP && FUSE == 2 && !POLY, STREAM = EDB_L2_STREAM && FUSE == 2 && !POLY;
   const uint32_t e0 = A.inc_off[p], e1 = A.inc_off[p + 1];
-  uint32_t oa[4] = {0, 0, 0, 0}, ob[4] = {0, 0, 0, 0};   // owner ranges of the pp waves (order positions 0..npp-1 = waves 0..npp-1)
+#if EDB_G_PREFETCH
+  // the particle's own sectors that are only needed after the incidence walk (and the backup position of the trigger): start their
+  // trip from DRAM now — a prefetch holds no register, a hoisted load would cost 22 and a resident CTA
+  if (FUSE) {
+    prefetch_l1(A.P.wg + p); prefetch_l1(A.P.q + p);
+    prefetch_l1(A.P.ix + p); prefetch_l1(A.P.iy + p); prefetch_l1(A.P.iz + p);
+    if (FUSE == 2 && A.pr_backup && A.next_flag) prefetch_l1(A.pr_backup + p);
+  }
+#endif
+  constexpr int NPP = POLY ? 4 : 1;   // particle-particle waves of the operator (spheres: wave 0 only)
+  uint32_t oa[NPP], ob[NPP];          // owner ranges of the pp waves (order positions 0..npp-1 = waves 0..npp-1)
 #pragma unroll
-  for (int t = 0; t < 4; t++)
+  for (int t = 0; t < NPP; t++) {
+    oa[t] = 0; ob[t] = 0;
     if (t < A.npp && A.W.w[t].n) { oa[t] = A.W.w[t].off[p]; ob[t] = A.W.w[t].off[p + 1]; }
+  }
   // FUSE 2 stores pr (own slot and ghost images) in this kernel: the non-coherent path is only legal for data that is read-only
   // for the whole kernel
-  const double4 pr = FUSE == 2 ? ld4(A.P.pr + p) : ldg4(A.P.pr + p);
+  const double4 pr = KEEP ? ld4h(A.P.pr + p, pol.keep) : FUSE == 2 ? ld4(A.P.pr + p) : ldg4(A.P.pr + p);
   const v3 r = mk3(pr.x, pr.y, pr.z);
   v3 F, M;
   double4 vm;
   if (FUSE) {
-    vm = ld4(A.P.vm + p);
+    vm = KEEP ? ld4h(A.P.vm + p, pol.keep) : ld4(A.P.vm + p);
     F = mk3(0.0 + A.g[0] * vm.w, 0.0 + A.g[1] * vm.w, 0.0 + A.g[2] * vm.w);
     M = mk3(0, 0, 0);
   } else {
@@ -671,10 +755,13 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
     const double4 mo = (flg & FLG_MOM) ? ld4(A.W.w[A.order[o]].mo + k) : make_double4(0, 0, 0, 0);
     bool role_i;
     if ((int)o < A.npp) {
-      const uint32_t a = o == 0 ? oa[0] : o == 1 ? oa[1] : o == 2 ? oa[2] : oa[3];
-      const uint32_t b = o == 0 ? ob[0] : o == 1 ? ob[1] : o == 2 ? ob[2] : ob[3];
+      uint32_t a = oa[0], b = ob[0];
+      if (POLY) {
+        a = o == 0 ? oa[0] : o == 1 ? oa[NPP > 1 ? 1 : 0] : o == 2 ? oa[NPP > 2 ? 2 : 0] : oa[NPP > 3 ? 3 : 0];
+        b = o == 0 ? ob[0] : o == 1 ? ob[NPP > 1 ? 1 : 0] : o == 2 ? ob[NPP > 2 ? 2 : 0] : ob[NPP > 3 ? 3 : 0];
+      }
       const bool owner = k >= a && k < b;
-      const bool owner_is_i = A.has_swap ? !(flg & FLG_SWAP) : true;
+      const bool owner_is_i = (POLY && A.has_swap) ? !(flg & FLG_SWAP) : true;
       role_i = owner ? owner_is_i : !owner_is_i;
     } else {
       // mesh waves 11/12 ("j to i", contact.hpp:405-421): the particle receives -f, -mom
@@ -701,32 +788,64 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
       for (int u = 0; u < PU; u++)
         if (fl[u] & FLG_HOT) {
           const WView& w = A.W.w[A.order[code[u] >> INC_SHIFT]];
-          const double4 fd = ld4(w.fd + (code[u] & INC_MASK)), cp = ld4(w.cp + (code[u] & INC_MASK));
+          const double4 fd = ld4(w.fd(code[u] & INC_MASK)), cp = ld4(w.cp(code[u] & INC_MASK));
           accumulate(code[u], fl[u], fd, cp);
         }
     }
-  } else
-  for (uint32_t e = e0; e < e1; e += GU) {
-    uint32_t code[GU];
-    uint8_t fl[GU];
-    double4 fd[GU], cp[GU];
+  } else {
+#if EDB_G_WIDE
+    // spheres: all the codes of the particle (8 at a time; a particle of a packing has ~6 incident records), then all their flag bytes,
+    // then the wrenches of the hot ones pair by pair — three dependent round trips per particle instead of three per pair of records
+    constexpr int CU = EDB_G_CU;
+    for (uint32_t e = e0; e < e1; e += CU) {
+      uint32_t code[CU];
+      uint8_t fl[CU];
 #pragma unroll
-    for (int u = 0; u < GU; u++) code[u] = (e + u < e1) ? A.inc[e + u] : 0xffffffffu;
+      for (int u = 0; u < CU; u++) code[u] = (e + u < e1) ? (STREAM ? ldu32h(A.inc + e + u, pol.stream) : A.inc[e + u]) : 0xffffffffu;
 #pragma unroll
-    for (int u = 0; u < GU; u++) {
-      fl[u] = 0;
-      if (code[u] != 0xffffffffu) fl[u] = A.W.w[A.order[code[u] >> INC_SHIFT]].flg[code[u] & INC_MASK];
-    }
-#pragma unroll
-    for (int u = 0; u < GU; u++)
-      if (fl[u] & FLG_HOT) {
-        const WView& w = A.W.w[A.order[code[u] >> INC_SHIFT]];
-        fd[u] = ld4(w.fd + (code[u] & INC_MASK));
-        cp[u] = ld4(w.cp + (code[u] & INC_MASK));
+      for (int u = 0; u < CU; u++) {
+        fl[u] = 0;
+        if (code[u] != 0xffffffffu) fl[u] = A.W.w[A.order[code[u] >> INC_SHIFT]].flg[code[u] & INC_MASK];
       }
 #pragma unroll
-    for (int u = 0; u < GU; u++)
-      if (fl[u] & FLG_HOT) accumulate(code[u], fl[u], fd[u], cp[u]);
+      for (int u = 0; u < CU; u += GU) {
+        double4 fd[GU], cp[GU];
+#pragma unroll
+        for (int v = 0; v < GU; v++)
+          if (fl[u + v] & FLG_HOT) {
+            const WView& w = A.W.w[A.order[code[u + v] >> INC_SHIFT]];
+            fd[v] = ld4(w.fd(code[u + v] & INC_MASK));
+            cp[v] = ld4(w.cp(code[u + v] & INC_MASK));
+          }
+#pragma unroll
+        for (int v = 0; v < GU; v++)
+          if (fl[u + v] & FLG_HOT) accumulate(code[u + v], fl[u + v], fd[v], cp[v]);
+      }
+    }
+#else
+    for (uint32_t e = e0; e < e1; e += GU) {
+      uint32_t code[GU];
+      uint8_t fl[GU];
+      double4 fd[GU], cp[GU];
+#pragma unroll
+      for (int u = 0; u < GU; u++) code[u] = (e + u < e1) ? (STREAM ? ldu32h(A.inc + e + u, pol.stream) : A.inc[e + u]) : 0xffffffffu;
+#pragma unroll
+      for (int u = 0; u < GU; u++) {
+        fl[u] = 0;
+        if (code[u] != 0xffffffffu) fl[u] = A.W.w[A.order[code[u] >> INC_SHIFT]].flg[code[u] & INC_MASK];
+      }
+#pragma unroll
+      for (int u = 0; u < GU; u++)
+        if (fl[u] & FLG_HOT) {
+          const WView& w = A.W.w[A.order[code[u] >> INC_SHIFT]];
+          fd[u] = ld4(w.fd(code[u] & INC_MASK));
+          cp[u] = ld4(w.cp(code[u] & INC_MASK));
+        }
+#pragma unroll
+      for (int u = 0; u < GU; u++)
+        if (fl[u] & FLG_HOT) accumulate(code[u], fl[u], fd[u], cp[u]);
+    }
+#endif
   }
   if (!FUSE) {
     A.P.fx[p] = F.x; A.P.fy[p] = F.y; A.P.fz[p] = F.z;
@@ -735,9 +854,11 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
   }
   // force_to_accel, then combined_compute_epilog
   const v3 acc = mk3(F.x / vm.w, F.y / vm.w, F.z / vm.w);
-  double4 w = ld4(A.P.wg + p);
-  double4 Q = ld4(A.P.q + p);
-  const v3 ar = ang_accel(Q, M, mk3(w.x, w.y, w.z), mk3(A.P.ix[p], A.P.iy[p], A.P.iz[p]));
+  double4 w = KEEP ? ld4h(A.P.wg + p, pol.keep) : ld4(A.P.wg + p);
+  double4 Q = STREAM ? ld4h(A.P.q + p, pol.stream) : ld4(A.P.q + p);
+  const v3 I = STREAM ? mk3(ld1h(A.P.ix + p, pol.stream), ld1h(A.P.iy + p, pol.stream), ld1h(A.P.iz + p, pol.stream))
+                      : mk3(A.P.ix[p], A.P.iy[p], A.P.iz[p]);
+  const v3 ar = ang_accel(Q, M, mk3(w.x, w.y, w.z), I);
   const v3 wn = mk3(w.x, w.y, w.z) + ar * A.hdt;
   w.x = wn.x; w.y = wn.y; w.z = wn.z;
   vm.x += acc.x * A.hdt; vm.y += acc.y * A.hdt; vm.z += acc.z * A.hdt;
@@ -759,7 +880,10 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
   Q = make_double4(nq.w / nn, nq.x / nn, nq.y / nn, nq.z / nn);
   const v3 w2 = mk3(w.x, w.y, w.z) + A.hdt * ar;
   w.x = w2.x; w.y = w2.y; w.z = w2.z;
-  st4(A.P.pr + p, rn); st4(A.P.vm + p, vm); st4(A.P.wg + p, w); st4(A.P.q + p, Q);
+  if (KEEP) { st4h(A.P.pr + p, rn, pol.keep); st4h(A.P.vm + p, vm, pol.keep); st4h(A.P.wg + p, w, pol.keep); }
+  else { st4(A.P.pr + p, rn); st4(A.P.vm + p, vm); st4(A.P.wg + p, w); }
+  if (STREAM) st4h(A.P.q + p, Q, pol.stream);
+  else st4(A.P.q + p, Q);
   // ghost images of this particle (own periodic copies, neighbour bricks): one bitmap word per warp says who has any
   if (FAN.bits && ((FAN.bits[p >> 5] >> (p & 31)) & 1u)) fan_out(FAN, A.P, p, rn, vm, w, Q);
   unsigned int over = 0;
@@ -787,7 +911,7 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
   }
   if (A.next_flag) {   // particle_displ_over (backup_dem.hpp:66-100) for the step that has just been started
     if (!(POLY && A.vert) && A.pr_backup) {
-      const double4 rb = ldg4(A.pr_backup + p);
+      const double4 rb = STREAM ? ldg4h(A.pr_backup + p, pol.stream) : ldg4(A.pr_backup + p);
       const v3 d = mk3(rn.x, rn.y, rn.z) - mk3(rb.x, rb.y, rb.z);
       over = dot(d, d) >= A.thr2 ? 1u : 0u;
     }
@@ -813,9 +937,9 @@ __global__ void __launch_bounds__(BLK) k_stress(GatherArgs A, double* __restrict
     const WView& w = A.W.w[t];
     const uint8_t fl = w.flg[k];
     if (!(fl & FLG_HOT)) continue;
-    const double4 fd = ld4(w.fd + k);
+    const double4 fd = ld4(w.fd(k));
     if (!(fd.w < 0.0)) continue;
-    const double4 f4 = ld4(w.ft + k), c4 = ld4(w.cp + k);
+    const double4 f4 = ld4(w.ft + k), c4 = ld4(w.cp(k));
     const v3 ft = mk3(f4.x, f4.y, f4.z);
     // ContactState fn as the reference stores it (contact_sphere.hpp:180; contact.hpp:409 for the "j to i" mesh waves)
     const v3 fn = (t == 11 || t == 12) ? (-ft) - mk3(fd.x, fd.y, fd.z) : mk3(fd.x, fd.y, fd.z) - ft;
@@ -866,7 +990,7 @@ __global__ void __launch_bounds__(BLK) k_sim_state_wave(WView w, unsigned long l
     if (((fl >> 1) & 3) != 2) {   // PartnerGhost twins are not counted
       tot = 1;
       if (fl & FLG_HOT) {
-        const double4 fd = ld4(w.fd + k), ft = ld4(w.ft + k);
+        const double4 fd = ld4(w.fd(k)), ft = ld4(w.ft + k);
         bool active = fd.w < 0.0 || ft.x != 0.0 || ft.y != 0.0 || ft.z != 0.0;
         if (!active && (fl & FLG_MOM)) {
           const double4 mo = ld4(w.mo + k);
@@ -905,7 +1029,7 @@ __global__ void __launch_bounds__(BLK) k_driver_force(WView w, int type, const D
   int d = -1;
   if (k < w.n) {
     if (w.flg[k] & FLG_HOT) {
-      const double4 mo = w.mo[k], fd = w.fd[k], cp = w.cp[k], ft4 = w.ft[k];
+      const double4 mo = w.mo[k], fd = *w.fd(k), cp = *w.cp(k), ft4 = w.ft[k];
       d = (int)w.ij[k].y;
       const v3 ft = mk3(ft4.x, ft4.y, ft4.z);
       // ContactState fn (contact_sphere.hpp:180; contact.hpp:409 for the "j to i" mesh waves whose stored friction is negated)

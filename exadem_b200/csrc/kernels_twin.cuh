@@ -134,8 +134,8 @@ __global__ void k_twin_append(const TwinMsg* __restrict__ msg, const uint32_t* _
   w.flg[k] = (uint8_t)((t.flg & (1 | 8 | 16)) | (2u << 1));  // PartnerGhost
   w.ft[k] = make_double4(t.ft[0], t.ft[1], t.ft[2], __longlong_as_double((long long)id[bp]));
   w.mo[k] = make_double4(t.mo[0], t.mo[1], t.mo[2], 0.0);
-  w.fd[k] = make_double4(0, 0, 0, 0);
-  w.cp[k] = make_double4(0, 0, 0, 0);
+  *w.fd(k) = make_double4(0, 0, 0, 0);
+  *w.cp(k) = make_double4(0, 0, 0, 0);
 }
 
 }  // namespace edb

@@ -200,6 +200,16 @@ int edb_num_particles(edb_context*, uint64_t* n_real, uint64_t* n_ghost);
 /* dynamic fields only (r, v, vrot, orient in; + f, mom, arot out) — the per-step host<->device traffic of a host-owned grid */
 int edb_upload_dynamic(edb_context*, const edb_particles* host);
 int edb_download_dynamic(edb_context*, edb_particles* host);
+/* Asynchronous forms for host arrays in PINNED memory: the calls return once the copies are enqueued (own copy streams, ordered against
+   the kernels by events).  An upload whose host arrays are the target of the previous asynchronous download waits for that download
+   field by field, so on a full-duplex link the download of step n, the upload of step n+1 and the kernels of step n+1 overlap
+   (the exaNBody grid a host operator hands over between two steps is exactly that: the arrays the previous step filled).
+   field_mask of the download: bit 0 r, 1 v, 2 vrot, 3 orient, 4 f (acceleration), 5 mom, 6 arot; EDB_DYN_ALL = everything
+   edb_download_dynamic returns.  edb_sync() (or any blocking entry point) before the host reads or writes the arrays. */
+#define EDB_DYN_ALL 0x7fu
+#define EDB_DYN_STATE 0x0fu /* r, v, vrot, orient: what the next step needs back */
+int edb_upload_dynamic_async(edb_context*, const edb_particles* host_pinned);
+int edb_download_dynamic_async(edb_context*, edb_particles* host_pinned, uint32_t field_mask);
 
 /* ---- operators (reference YAML name in brackets) ----------------------------------------------------- */
 /* [chunk_neighbors_contact + nbh_sphere | nbh_polyhedron + update_interaction_ghost + classify_interactions]

@@ -7,7 +7,9 @@ own scale (max |x| over the field), i.e. |a-b| <= rtol * max(1e-300, max|b|), AN
 at rtol = 1e-10) only absorbs the rounding of a component that is the small residual of large cancelling contributions (a net
 acceleration of 0.35 left over from contact forces of a few thousand moves by 1e-10 when the summation order changes — measured
 between the oracle's serial and OpenMP orders, tests/test_oracle_sim.py); a small-magnitude component that is wrong by more than
-that fails even though the field-scaled check alone would let it pass."""
+that fails even though the field-scaled check alone would let it pass.  `abs_floor` (default 0) is for quantities that are
+DIFFERENCES of much larger operands (an overlap dn = |r_i - r_j| - R of 1e-7 between coordinates of order 1 cannot be known better
+than an ulp of the coordinates): the caller passes a few ulps of the operand scale."""
 from __future__ import annotations
 
 import numpy as np
@@ -27,7 +29,7 @@ def keys_of(rec: np.ndarray) -> np.ndarray:
 ELEM_FLOOR = 1e-2
 
 
-def field_close(a, b, rtol, what="", elementwise=True):
+def field_close(a, b, rtol, what="", elementwise=True, abs_floor=0.0):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
@@ -41,7 +43,7 @@ def field_close(a, b, rtol, what="", elementwise=True):
     err = float(np.max(diff)) / scale
     assert err <= rtol, f"{what}: max scaled error {err:.3e} > {rtol:.1e} (scale {scale:.3e})"
     if elementwise and rtol > 0:
-        bar = rtol * np.abs(b) + ELEM_FLOOR * rtol * scale
+        bar = rtol * np.abs(b) + max(ELEM_FLOOR * rtol * scale, abs_floor)
         bad = diff > bar
         if bad.any():
             i = int(np.argmax(diff / bar))
