@@ -196,6 +196,25 @@ def pinned_like(pa):
     return out
 
 
+def link_bandwidth(nbytes=128 << 20, reps=3):
+    """pinned host <-> device copy bandwidth of this box (GB/s), one direction at a time: the floor of the e2e leg"""
+    import torch
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    out = {}
+    for name, (dst, src) in (("h2d_gbs", (d, h)), ("d2h_gbs", (h, d))):
+        best = 0.0
+        for _ in range(reps + 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            dst.copy_(src, non_blocking=True)
+            b.record()
+            b.synchronize()
+            best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
+        out[name] = best
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 def host_threads():
     """All host cores, whatever the launcher did to this process: torchrun exports OMP_NUM_THREADS=1 and a launcher may have pinned
@@ -546,8 +565,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             iu_e, dt, h2d, d2h = float(t[0]), float(tm[1]), float(t[2]), float(t[3])
+        link = link_bandwidth() if rank == 0 else {}
         e2e = {"value": iu_e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ke,
-               "ms_per_step": 1e3 * dt / ke,
+               "ms_per_step": 1e3 * dt / ke, "link": link,
+               "floor_ms_per_step": (1e3 * (d2h / world) / (link["d2h_gbs"] * 1e9)) if link.get("d2h_gbs") else None,
                "what": "edb_upload_dynamic_async (r, v, vrot, orient from pinned host memory) -> edb_run_verlet(1 step) -> "
                        "edb_download_dynamic_async (r, v, vrot, orient, f, mom, arot to pinned host memory), every step, all ranks; "
                        "PCIe floor = d2h bytes / link bandwidth (the copies of consecutive steps overlap, the download is the longer leg)"}

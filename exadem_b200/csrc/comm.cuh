@@ -232,7 +232,30 @@ struct FanArgs {
   const uint32_t* off;   // nreal + 1
   const FanEnt* ent;
   FanPeer peer[P2P_MAXPEER];
+  // several ranks: the LAST block of the gather to finish mails {epoch, local rebuild-trigger count} to every other rank — the
+  // neighbours' landing launch finds it already there instead of waiting for this rank's next launch to send it
+  unsigned long long* mail[P2P_MAXR];
+  int nmail;
+  unsigned int* done;    // block counter (zero between launches)
+  uint32_t epoch;
 };
+// Tail of k_gather<2>: every block fences its peer stores at system scope and counts itself; the last one sends the mail.
+__device__ __forceinline__ void fan_mail(const FanArgs& F, const unsigned long long* count) {
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) s_last = atomicAdd(F.done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) *F.done = 0;
+  if ((int)threadIdx.x < F.nmail) {
+    unsigned long long c = count ? *(volatile const unsigned long long*)count : 0ull;
+    if (c > 0xffffffffull) c = 0xffffffffull;
+    const unsigned long long v = ((unsigned long long)F.epoch << 32) | c;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(F.mail[threadIdx.x]), "l"(v) : "memory");
+  }
+}
 // returns true when the particle was stored to a neighbour GPU (the caller then fences at system scope before the block signals)
 __device__ __forceinline__ bool fan_out(const FanArgs& F, const PView& P, uint32_t p, const double4& r, const double4& vm, const double4& wg,
                                         const double4& q) {
@@ -382,7 +405,8 @@ struct Comm {
   char* old_base = nullptr;
   // fused path: the gather of this step pushes (FanArgs) under a new epoch; the NEXT ghost refresh only lands
   uint32_t fan_epoch_pending = 0;
-  void fan_begin(FanArgs& F) {
+  bool fan_mailed = false;   // the pending epoch's mail was sent by the gather itself
+  void fan_begin(FanArgs& F, bool mail_from_gather) {
     if (!(comm && p2p.on)) return;
     const uint32_t e = ++p2p.epoch;
     const int par = (int)(e & 1u);
@@ -391,6 +415,14 @@ struct Comm {
       if (p.fan_index >= 0) F.peer[p.fan_index] = FanPeer{p2p_land(p2p.peer_base[p.rank], p.remote_cap, par) + p.remote_base, p.remote_cap, 0};
     }
     fan_epoch_pending = e;
+    fan_mailed = mail_from_gather;
+    F.nmail = 0;
+    if (mail_from_gather) {
+      for (int r = 0; r < nranks; r++)
+        if (r != rank) F.mail[F.nmail++] = p2p_mail(p2p.peer_base[r], par) + rank;
+      F.done = p2p.d_done;
+      F.epoch = e;
+    }
   }
   const double4* landing_of(uint32_t epoch) const { return p2p_land(p2p.base, p2p.cap, (int)(epoch & 1u)); }
   // the remote ghosts of `epoch` (already landed: its mail was waited for) copied into the ghost slots; no mail, no count
@@ -421,8 +453,10 @@ struct Comm {
     L.nranks = nranks; L.me = rank; L.epoch = e; L.count = count;
     L.land = p2p_land(p2p.base, p2p.cap, par);
     L.cap = p2p.cap; L.n = copy ? nrem : 0; L.base = nreal + n_local_ghost;
-    for (int r = 0; r < nranks; r++)
-      if (r != rank) L.out_mail[L.n_out++] = p2p_mail(p2p.peer_base[r], par) + rank;
+    if (!fan_mailed)
+      for (int r = 0; r < nranks; r++)
+        if (r != rank) L.out_mail[L.n_out++] = p2p_mail(p2p.peer_base[r], par) + rank;
+    fan_mailed = false;
     const uint32_t nb = L.n ? std::min<uint32_t>((L.n + BLK - 1) / BLK, 592u) : 1u;
     k_ghost_land<<<nb, BLK, 0, st>>>(L);
     (*launches)++;

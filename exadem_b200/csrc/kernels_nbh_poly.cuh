@@ -64,6 +64,26 @@ struct SV {  // world-vertex accessor over the staged (shared-memory) copy
 __device__ __forceinline__ uint32_t type_of_bits(double w) { return (uint32_t)((unsigned long long)__double_as_longlong(w) & 0xffffffffu); }
 __host__ __device__ inline size_t npc_bytes_per_particle(int nvmax) { return (size_t)nvmax * 32 + 32 + 32 + 8 + 8 + 4 + 4 + 1; }
 
+// Conservative reach test used to cull edge-edge filter evaluations: squared distance from point c to the segment p0-p1.
+// filter_ee accepts a pair of edges only if two points ON the segments are within R = ri + rj + rV of each other (ee_closest returns
+// parameters strictly inside (0,1)), and every point of b's edges lies within bnd_b of b's centre, so an edge of a whose distance to
+// b's centre exceeds bnd_b + R cannot pass against ANY edge of b.  The cull compares with a relative + absolute safety margin many
+// orders above the rounding of either computation, so it never removes a test the reference would have accepted: the candidate set
+// is unchanged, only the number of evaluated edge pairs drops (octahedra in a packing: ~16-25 of 144).
+__device__ __forceinline__ double seg_point_d2(v3 p0, v3 p1, v3 c) {
+  const v3 d = p1 - p0, w = c - p0;
+  const double dd = dot(d, d);
+  double t = dd > 0.0 ? dot(w, d) / dd : 0.0;
+  t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+  const v3 q = w - d * t;
+  return dot(q, q);
+}
+__device__ __forceinline__ double reach2(double bnd, double R, v3 c) {
+  const double m = fmax(fmax(fabs(c.x), fabs(c.y)), fmax(fabs(c.z), 1.0));
+  const double r = (bnd + R) * 1.000001 + 1e-9 * m;
+  return r * r;
+}
+
 struct NbhPool {
   uint32_t* words;                // cap_chunks * CHW
   uint32_t* cursor;               // next free chunk
@@ -188,6 +208,10 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
     const SV va{s_vert + (size_t)La * nvmax};
     const double rma = ha * sa.radius;
     const int* ea = A.S.edges + 2 * sa.e0;
+    // bounding radius of the owner's vertex set about its position (edge-edge cull)
+    double bnda = 0.0;
+    if (lane < sa.nv) bnda = norm(va[lane] - mk3(ra.x, ra.y, ra.z));
+    for (int o = 16; o > 0; o >>= 1) bnda = fmax(bnda, __shfl_xor_sync(0xffffffffu, bnda, o));
     uint32_t run[4] = {0, 0, 0, 0};
     uint32_t base[4] = {0, 0, 0, 0};
     if (FILL) {
@@ -285,10 +309,27 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
             obb_enlarge(oi, 0.5 * rV); obb_enlarge(oi, 0.5 * rV);
             mB = __ballot_sync(0xffffffffu, lane < sb.nv && obb_intersect(oi, obb_point(vb[lane < sb.nv ? lane : 0], rmb)));
           }
+          // edge reach masks (see seg_point_d2): lanes [0, ne_a) test a's edges against b's bounding sphere, lanes [16, 16 + ne_b)
+          // b's edges against a's; shapes with more than 16 edges keep every edge
+          unsigned eA = sa.ne >= 32 ? 0xffffffffu : ((1u << sa.ne) - 1u), eB = sb.ne >= 32 ? 0xffffffffu : ((1u << sb.ne) - 1u);
+          if (sa.ne <= 16 && sb.ne <= 16) {
+            double bndb = 0.0;
+            if (lane < sb.nv) bndb = norm(vb[lane] - mk3(rb.x, rb.y, rb.z));
+            for (int o = 16; o > 0; o >>= 1) bndb = fmax(bndb, __shfl_xor_sync(0xffffffffu, bndb, o));
+            const double Rr = rma + rmb + rV;
+            bool keep = false;
+            if (lane < sa.ne) keep = seg_point_d2(va[ea[2 * lane]], va[ea[2 * lane + 1]], mk3(rb.x, rb.y, rb.z)) <= reach2(bndb, Rr, mk3(rb.x, rb.y, rb.z));
+            else if (lane >= 16 && lane - 16 < sb.ne)
+              keep = seg_point_d2(vb[eb[2 * (lane - 16)]], vb[eb[2 * (lane - 16) + 1]], mk3(ra.x, ra.y, ra.z)) <= reach2(bnda, Rr, mk3(ra.x, ra.y, ra.z));
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            eA = km & 0xffffu;
+            eB = km >> 16;
+          }
           const uint8_t ghost = s_gc[Lb];
           const uint8_t f0 = (uint8_t)(ghost << 1), f1 = (uint8_t)(1 | (ghost << 1));
           if (!FILL) {   // pair header of the stream
             emit(b); emit((uint32_t)idb); emit((uint32_t)(idb >> 32)); emit((uint32_t)ghost | (s_type[Lb] << 8)); emit(mA); emit(mB);
+            emit(eA); emit(eB);
           }
           auto write = [&](int t, uint32_t k, uint32_t i, uint32_t j, uint32_t si, uint32_t sj, uint8_t flg) {
             W.w[t].ij[k] = make_uint2(i, j);
@@ -303,6 +344,9 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
           const uint32_t nA = __popc(mA), nB = __popc(mB);
           auto vtxA = [&](uint32_t n) { return (uint32_t)__fns(mA, 0, (int)n + 1); };
           auto vtxB = [&](uint32_t n) { return (uint32_t)__fns(mB, 0, (int)n + 1); };
+          const uint32_t nEA = __popc(eA), nEB = __popc(eB);
+          auto edgA = [&](uint32_t n) { return (uint32_t)__fns(eA, 0, (int)n + 1); };
+          auto edgB = [&](uint32_t n) { return (uint32_t)__fns(eB, 0, (int)n + 1); };
           // A -> B (swap = 0): vertices of a against vertices / edges / faces of b
           group(0, nA * nvb,
                 [&](uint32_t x) { const uint32_t i = vtxA(x / nvb), j = x % nvb; return filter_vv(rV, va[i], rma, vb[j], rmb); },
@@ -316,12 +360,13 @@ __global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, Cnt
                   return filter_vf(rV, va[i], rma, vb, rmb, A.S.fidx + sb.fi0 + A.S.foff[sb.f0 + j], A.S.fn[sb.f0 + j]);
                 },
                 [&](uint32_t x, uint32_t k) { write(2, k, a, b, vtxA(x / nfb), x % nfb, f0); });
-          group(3, nea * neb,
+          // edge-edge over the edges within reach only (ascending in both indices: the emission order of the full double loop)
+          group(3, nEA * nEB,
                 [&](uint32_t x) {
-                  const uint32_t i = x / neb, j = x % neb;
+                  const uint32_t i = edgA(x / nEB), j = edgB(x % nEB);
                   return filter_ee(rV, va[ea[2 * i]], va[ea[2 * i + 1]], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb);
                 },
-                [&](uint32_t x, uint32_t k) { write(3, k, a, b, x / neb, x % neb, f0); });
+                [&](uint32_t x, uint32_t k) { write(3, k, a, b, edgA(x / nEB), edgB(x % nEB), f0); });
           // B -> A (swap = 1): pi = b, pj = a; the owner stays a (interaction_pair.hpp:75-90)
           group(1, nB * nea,
                 [&](uint32_t x) { const uint32_t j = vtxB(x / nea), i = x % nea; return filter_ve(rV, vb[j], rmb, va[ea[2 * i]], va[ea[2 * i + 1]], rma); },
@@ -368,7 +413,7 @@ __global__ void __launch_bounds__(256) k_nbh_poly_replay(NbhArgs A, CntTab C, WT
   for (;;) {
     const uint32_t b = rd();
     if (b == NPC_NONE) break;
-    const uint32_t idlo = rd(), idhi = rd(), gt = rd(), mA = rd(), mB = rd();
+    const uint32_t idlo = rd(), idhi = rd(), gt = rd(), mA = rd(), mB = rd(), eA = rd(), eB = rd();
     const unsigned long long idb = ((unsigned long long)idhi << 32) | idlo;
     const uint8_t ghost = (uint8_t)(gt & 0xffu);
     const ShapeDev* __restrict__ psb = A.S.sh + (gt >> 8);
@@ -394,7 +439,9 @@ __global__ void __launch_bounds__(256) k_nbh_poly_replay(NbhArgs A, CntTab C, WT
     group(0, nA * nvb, [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
     group(1, nA * neb, [&](uint32_t x, uint32_t k) { write(1, k, a, b, vtxA(x / neb), x % neb, f0); });
     group(2, nA * nfb, [&](uint32_t x, uint32_t k) { write(2, k, a, b, vtxA(x / nfb), x % nfb, f0); });
-    group(3, nea * neb, [&](uint32_t x, uint32_t k) { write(3, k, a, b, x / neb, x % neb, f0); });
+    const uint32_t nEB = __popc(eB);
+    group(3, __popc(eA) * nEB,
+          [&](uint32_t x, uint32_t k) { write(3, k, a, b, (uint32_t)__fns(eA, 0, (int)(x / nEB) + 1), (uint32_t)__fns(eB, 0, (int)(x % nEB) + 1), f0); });
     group(1, nB * nea, [&](uint32_t x, uint32_t k) { write(1, k, b, a, vtxB(x / nea), x % nea, f1); });
     group(2, nB * nfa, [&](uint32_t x, uint32_t k) { write(2, k, b, a, vtxB(x / nfa), x % nfa, f1); });
   }

@@ -918,6 +918,7 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
     over = __reduce_add_sync(0xffffffffu, over);
     if ((threadIdx.x & 31) == 0 && over) atomicAdd(A.next_flag, (unsigned long long)over);
   }
+  if (FUSE == 2 && FAN.nmail) fan_mail(FAN, A.next_flag);
 }
 
 // stress_tensor (src/interaction/stress_tensor.cu:41-81): per particle, sum over the records in contact (dn < 0) of

@@ -9,7 +9,9 @@ acceleration of 0.35 left over from contact forces of a few thousand moves by 1e
 between the oracle's serial and OpenMP orders, tests/test_oracle_sim.py); a small-magnitude component that is wrong by more than
 that fails even though the field-scaled check alone would let it pass.  `abs_floor` (default 0) is for quantities that are
 DIFFERENCES of much larger operands (an overlap dn = |r_i - r_j| - R of 1e-7 between coordinates of order 1 cannot be known better
-than an ulp of the coordinates): the caller passes a few ulps of the operand scale."""
+than an ulp of the coordinates): the caller passes a few ulps of the operand scale.  `elem_floor` replaces ELEM_FLOOR where the
+two sides legitimately sum in different orders over many steps (N bricks against one domain, 60 steps: measured up to 8e-12 of the
+field scale on components 1e-3 of it)."""
 from __future__ import annotations
 
 import numpy as np
@@ -29,7 +31,7 @@ def keys_of(rec: np.ndarray) -> np.ndarray:
 ELEM_FLOOR = 1e-2
 
 
-def field_close(a, b, rtol, what="", elementwise=True, abs_floor=0.0):
+def field_close(a, b, rtol, what="", elementwise=True, abs_floor=0.0, elem_floor=None):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
@@ -43,16 +45,17 @@ def field_close(a, b, rtol, what="", elementwise=True, abs_floor=0.0):
     err = float(np.max(diff)) / scale
     assert err <= rtol, f"{what}: max scaled error {err:.3e} > {rtol:.1e} (scale {scale:.3e})"
     if elementwise and rtol > 0:
-        bar = rtol * np.abs(b) + max(ELEM_FLOOR * rtol * scale, abs_floor)
+        ef = ELEM_FLOOR if elem_floor is None else elem_floor
+        bar = rtol * np.abs(b) + max(ef * rtol * scale, abs_floor)
         bad = diff > bar
         if bad.any():
             i = int(np.argmax(diff / bar))
-            raise AssertionError(f"{what}: {int(bad.sum())} of {a.size} elements outside |a-b| <= {rtol:.0e}*|b| + {ELEM_FLOOR * rtol:.0e}*scale; "
+            raise AssertionError(f"{what}: {int(bad.sum())} of {a.size} elements outside |a-b| <= {rtol:.0e}*|b| + {ef * rtol:.0e}*scale; "
                                  f"worst flat index {i}: {a.flat[i]!r} vs {b.flat[i]!r} (scale {scale:.3e})")
     return err
 
 
-def compare_interaction_sets(a: np.ndarray, b: np.ndarray, payload_rtol: float | None = 1e-10):
+def compare_interaction_sets(a: np.ndarray, b: np.ndarray, payload_rtol: float | None = 1e-10, elem_floor=None):
     """a, b: arrays of capi.INTERACTION_DTYPE. Keys must match exactly; payloads within payload_rtol."""
     assert len(a) == len(b), f"interaction count differs: {len(a)} vs {len(b)}"
     sa, sb = sort_interactions(a), sort_interactions(b)
@@ -61,8 +64,8 @@ def compare_interaction_sets(a: np.ndarray, b: np.ndarray, payload_rtol: float |
         bad = np.nonzero((ka != kb).any(axis=1))[0]
         raise AssertionError(f"interaction sets differ at {len(bad)} sorted positions; first: {ka[bad[0]]} vs {kb[bad[0]]}")
     if payload_rtol is not None and len(a):
-        field_close(sa["friction"], sb["friction"], payload_rtol, "friction history")
-        field_close(sa["moment"], sb["moment"], payload_rtol, "moment history")
+        field_close(sa["friction"], sb["friction"], payload_rtol, "friction history", elem_floor=elem_floor)
+        field_close(sa["moment"], sb["moment"], payload_rtol, "moment history", elem_floor=elem_floor)
     return len(a)
 
 
