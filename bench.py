@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU (weak scaling)")
     ap.add_argument("--global-side", type=int, default=200, help="strong scaling: side of the fixed global periodic box (200 = 8 M, 400 = 64 M)")
     ap.add_argument("--jitter", type=float, default=2e-5, help="box workload: uniform position jitter of the SC lattice")
+    ap.add_argument("--cell-size", type=float, default=None, help="poly / mixed workloads: grid cell size (default: the workload's own, 2.0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-poly", action="store_true", help="skip the polyhedra line reported alongside (N=1 only)")
@@ -151,7 +152,8 @@ def resolve_workload(args, world):
         raise SystemExit(f"workload {name} is single-GPU")
     if name == "poly":
         side = int(round(args.particles ** (1.0 / 3.0)))
-        return name, (lambda rank, nranks: workloads.polyhedra_box((side, side, side), pitch=0.78)), \
+        kw = {"cell_size": args.cell_size} if args.cell_size else {}
+        return name, (lambda rank, nranks: workloads.polyhedra_box((side, side, side), pitch=0.78, **kw)), \
             f"poly: {side ** 3} octahedra, periodic packing (BASELINE configs[2])", scaling
     if name == "mixed":
         return name, (lambda rank, nranks: mixed_workload(args.particles)), \

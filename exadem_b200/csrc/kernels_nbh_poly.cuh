@@ -23,7 +23,13 @@
 
 namespace edb {
 
-constexpr int NPC_THREADS = 512;
+#ifndef EDB_NPC_THREADS
+#define EDB_NPC_THREADS 512
+#endif
+#ifndef EDB_NPC_MINB
+#define EDB_NPC_MINB 1
+#endif
+constexpr int NPC_THREADS = EDB_NPC_THREADS;
 constexpr int CHW = 64;                       // words per pool chunk; word 0 links to the next chunk
 constexpr uint32_t NPC_NONE = 0xffffffffu;
 
@@ -119,7 +125,7 @@ struct PairDims {
 
 // MODE 0: count;  MODE 1: count + record the streams;  MODE 2: fill by repeating the tests
 template <int MODE>
-__global__ void __launch_bounds__(NPC_THREADS, 1) k_nbh_poly_cell(NbhArgs A, CntTab C, WTab W, uint32_t cap, NbhPool PL) {
+__global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(NbhArgs A, CntTab C, WTab W, uint32_t cap, NbhPool PL) {
   constexpr bool FILL = MODE == 2;
   extern __shared__ __align__(128) unsigned char smem[];
   const int nvmax = A.S.nvmax;

