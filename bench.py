@@ -7,11 +7,12 @@
 A "step" is one full Verlet time step of the hot path (prolog -> rebuild-or-ghost-refresh -> contact waves ->
 deterministic gather fused with gravity/force_to_accel/epilog) over the synthetic workload:
   N = 1 : BASELINE.json configs[1] — 1 M monodisperse spheres in a rotating drum (cylinder driver), fp64.
-  N > 1 : BASELINE.json configs[4] topology — fully periodic box of spheres cut into 2x1x1 / 2x2x1 / 2x2x2 bricks (7 peers per rank
-          at N = 8), one 1 M-sphere brick per GPU (weak, the default) or a FIXED global box divided by N (`--scaling strong`,
-          `--global-side 200` = 8 M, `400` = 64 M).  `--workload drum` at N > 1: the drum N times longer cut into N slabs (2 peers).
-          The line also carries `single_gpu_same_brick` (rank 0 runs one brick alone, periodic onto itself: the denominator of the
-          weak-scaling efficiency on THIS topology) and, at N > 1 with the default workload, the drum slabs as `drum_slabs`.
+  N > 1 : weak scaling of THE SAME configuration (the contract: per-GPU work fixed as N grows): the drum N times longer, cut into N slabs
+          along its periodic axis, one 1 M-sphere slab per GPU.  The line also carries `box_bricks`: the BASELINE configs[4] topology —
+          a fully periodic box cut into 2x1x1 / 2x2x1 / 2x2x2 bricks of 1 M spheres (7 peers per rank at N = 8) — measured in the same
+          job together with one such brick alone on one GPU (`single_gpu_same_brick`, the denominator of the weak-scaling efficiency
+          on that topology).  `--workload box` makes the bricks the headline; `--scaling strong --global-side 200|400` divides a FIXED
+          8 M / 64 M box by N.
 metric = interaction-updates/s (sum over waves of records processed by the contact kernels per wall second, whole job);
 particle-steps/s is reported beside it.  One JSON line is printed by rank 0.
 `--impl reference`: the CPU arm (the oracle port of the reference operators, OpenMP on all host cores) on the SAME workload.
@@ -52,7 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-poly", action="store_true", help="skip the polyhedra line reported alongside (N=1 only)")
-    ap.add_argument("--no-secondary", action="store_true", help="N>1: skip the single-brick and drum-slab lines reported alongside")
+    ap.add_argument("--no-secondary", action="store_true", help="N>1: skip the box-brick / single-brick lines reported alongside")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -125,7 +126,7 @@ class ClockSampler:
 def resolve_workload(args, world):
     """-> (name, make(rank, nranks) -> Workload, description shared by both arms, scaling)"""
     from exadem_b200 import parallel, workloads
-    name = args.workload or ("drum" if world == 1 else "box")
+    name = args.workload or "drum"
     scaling = args.scaling
     if name == "drum":
         if scaling == "strong":
@@ -587,10 +588,40 @@ def main():
     n_real = wl.particles.n
     eng.close()
 
-    # ---- N > 1: the same brick alone on one GPU (weak-scaling denominator on this topology) and the drum slabs, reported alongside
+    # ---- N > 1, default workload: the BASELINE configs[4] topology reported alongside — a fully periodic box cut into 2x1x1 / 2x2x1 /
+    # 2x2x2 bricks of 1 M spheres (7 peers per rank at N = 8) — together with one such brick alone on one GPU (periodic onto itself),
+    # the denominator of the weak-scaling efficiency on that topology
+    box = None
+    if world > 1 and not args.no_secondary and name == "drum" and args.scaling == "weak":
+        import copy
+        import torch.distributed as dist
+        bargs = copy.copy(args)
+        bargs.workload = "box"
+        _, bmake, bdesc, _ = resolve_workload(bargs, world)
+        jb = Job(lib, bmake, rank, world, local)
+        msb, cb, nrb, winb = jb.timed(args.steps, args.warmup)
+        windows.append(winb)
+        bcounts, bactive = jb.eng.interaction_counts()
+        msb, iub, psb, _, nrbm = reduce_stats(world, msb, cb, nrb)
+        box = {"workload": bdesc, "particles_per_gpu": int(jb.wl.particles.n), "value": iub / (msb * 1e-3), "ms_per_step": msb / args.steps,
+               "rebuilds_in_timed_region": int(nrbm), "interactions_per_gpu": int(bcounts.sum()), "active_interactions_per_gpu": int(bactive.sum()),
+               "per_step_ms": {"contact_all": cb.contact_ms / args.steps, "gather_fused": cb.gather_ms / args.steps, "ghost": cb.ghost_ms / args.steps}}
+        jb.eng.close()
+        dist.barrier()
+        if rank == 0:
+            j1 = Job(lib, lambda r, n: bmake(0, 1), 0, 1, local)
+            ms1, c1, nreb1, win1 = j1.timed(args.steps, args.warmup)
+            windows.append(win1)
+            box["single_gpu_same_brick"] = {"workload": "one brick of the same size alone on one GPU (periodic onto itself)",
+                                            "particles": int(j1.wl.particles.n), "value": c1.interaction_updates / (ms1 * 1e-3),
+                                            "ms_per_step": ms1 / args.steps, "rebuilds_in_timed_region": int(nreb1),
+                                            "per_step_ms": {"contact_all": c1.contact_ms / args.steps, "gather_fused": c1.gather_ms / args.steps}}
+            j1.eng.close()
+        dist.barrier()
+
     single = None
-    slabs = None
-    if world > 1 and not args.no_secondary and name == "box":
+    if world > 1 and not args.no_secondary and name == "box" and args.scaling == "weak":
+        import torch.distributed as dist
         if rank == 0:
             j1 = Job(lib, lambda r, n: make(0, 1), 0, 1, local)
             ms1, c1, nreb1, win1 = j1.timed(args.steps, args.warmup)
@@ -599,20 +630,7 @@ def main():
                       "value": c1.interaction_updates / (ms1 * 1e-3), "ms_per_step": ms1 / args.steps, "rebuilds_in_timed_region": int(nreb1),
                       "per_step_ms": {"contact_all": c1.contact_ms / args.steps, "gather_fused": c1.gather_ms / args.steps}}
             j1.eng.close()
-        import torch.distributed as dist
         dist.barrier()
-        if args.scaling == "weak":
-            from exadem_b200 import parallel
-            js = Job(lib, lambda r, n: parallel.drum_slab_workload(args.particles, r, n), rank, world, local)
-            ms2, c2, nreb2, win2 = js.timed(args.steps, args.warmup)
-            windows.append(win2)
-            ms2, iu2, ps2, _, nr2 = reduce_stats(world, ms2, c2, nreb2)
-            slabs = {"workload": f"drum (BASELINE configs[1]) {world} times longer, cut into {world} slabs along its periodic axis (2 peers per rank)",
-                     "particles_per_gpu": int(js.wl.particles.n), "value": iu2 / (ms2 * 1e-3), "ms_per_step": ms2 / args.steps,
-                     "rebuilds_in_timed_region": int(nr2),
-                     "per_step_ms": {"contact_all": c2.contact_ms / args.steps, "gather_fused": c2.gather_ms / args.steps, "ghost": c2.ghost_ms / args.steps}}
-            js.eng.close()
-
     if rank != 0:
         return
     clocks = sampler.stop(windows)
@@ -655,10 +673,10 @@ def main():
         line["roofline_" + ("gather" if roof_other["kernel"].startswith("k_gather") else "contact")] = roof_other
     if poly is not None:
         line["polyhedra"] = poly
+    if box is not None:
+        line["box_bricks"] = box
     if single is not None:
         line["single_gpu_same_brick"] = single
-    if slabs is not None:
-        line["drum_slabs"] = slabs
     print(json.dumps(line), flush=True)
 
 

@@ -64,6 +64,7 @@ struct edb_context {
   DevBuf<uint32_t> fan_cnt, fan_off, fan_bits;
   // polyhedron neighbour build: stream pool of the count pass (kernels_nbh_poly.cuh)
   DevBuf<uint32_t> nbh_pool, nbh_first, nbh_ctr;
+  DevBuf<uint2> pp_tmp;              // spheres: candidates recorded by the count pass of the neighbour build (kernels_rebuild.cuh)
   uint32_t nbh_pool_chunks = 0;
   uint32_t* h_nbh = nullptr;   // pinned copy of nbh_ctr
   uint64_t nbh_replays = 0;
@@ -72,6 +73,7 @@ struct edb_context {
   uint32_t ghost_in_landing = 0;   // epoch whose remote ghosts live in the landing zone only (0: the ghost slots are current)
   // debugging switches read once at creation: EDB_NO_FAN (separate ghost kernels), EDB_NBH_POLY_PER_THREAD, EDB_NBH_NO_REPLAY
   bool env_no_fan = false, env_nbh_per_thread = false, env_nbh_no_replay = false;
+  bool env_nbh_two_pass = false;     // EDB_NBH_TWO_PASS: spheres enumerate twice (count, fill) like round 1
   bool env_gather_mail = false;       // EDB_GATHER_MAIL: the gather's last block sends the mail instead of the landing launch
   bool env_land_copy = false;         // EDB_LAND_COPY: always copy the landing zone into the ghost slots (the round-1 path)
   bool env_drivers_unfused = false;   // EDB_DRIVERS_UNFUSED: moving drivers through the operator-by-operator loop on one rank too
@@ -329,6 +331,7 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
   c->cfg = *cfg;
   if (c->cfg.nranks < 1) c->cfg.nranks = 1;
   c->env_no_fan = getenv("EDB_NO_FAN") != nullptr;
+  c->env_nbh_two_pass = getenv("EDB_NBH_TWO_PASS") != nullptr;
   c->env_land_copy = getenv("EDB_LAND_COPY") != nullptr;
   c->env_gather_mail = getenv("EDB_GATHER_MAIL") != nullptr;
   c->env_nbh_per_thread = getenv("EDB_NBH_POLY_PER_THREAD") != nullptr;
@@ -418,6 +421,7 @@ extern "C" int edb_destroy(edb_context* c) {
   if (c->d_need_count) cudaFree(c->d_need_count);
   if (c->d_sflag) cudaFree(c->d_sflag);
   if (c->h_sflag) cudaFreeHost(c->h_sflag);
+  c->pp_tmp.release();
   if (c->h_nbh) cudaFreeHost(c->h_nbh);
   for (int i = 0; i < 2; i++) if (c->ev_sflag[i]) cudaEventDestroy(c->ev_sflag[i]);
   if (c->h_tot) cudaFreeHost(c->h_tot);
@@ -1441,8 +1445,17 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
     PL = NbhPool{c->nbh_pool.p, c->nbh_ctr.p, record ? c->nbh_pool_chunks : 0u, c->nbh_first.p,
                  reinterpret_cast<unsigned long long*>(c->nbh_ctr.p + 2), c->nbh_ctr.p + 1};
   }
-  if (!poly) LAUNCH(c, k_nbh_sphere<false>, nblk(n, 128), 128, 0, A, C, W);
-  else {
+  if (!poly) {
+    if (!c->env_nbh_two_pass && (size_t)n * PP_TMP_CAP * sizeof(uint2) <= ((size_t)3 << 30)) {
+      c->pp_tmp.ensure((size_t)n * PP_TMP_CAP + 1);
+      c->nbh_ctr.ensure(8);
+      CK(cudaMemsetAsync(c->nbh_ctr.p, 0, 32, c->st));
+      A.pp_tmp = c->pp_tmp.p;
+      A.pp_overflow = c->nbh_ctr.p + 1;
+    }
+    LAUNCH(c, k_nbh_sphere<false>, nblk(n, 128), 128, 0, A, C, W);
+    if (A.pp_tmp) CK(cudaMemcpyAsync(c->h_nbh, c->nbh_ctr.p, 32, cudaMemcpyDeviceToHost, c->st));
+  } else {
     if (cell_cap) {
       if (record) LAUNCH(c, k_nbh_poly_cell<1>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap, PL);
       else LAUNCH(c, k_nbh_poly_cell<0>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap, PL);
@@ -1463,8 +1476,16 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
     c->wave[t].ensure(c->wave[t].n + 1, poly || t >= 7);
     W.w[t] = view(c->wave[t]);
   }
-  if (!poly) LAUNCH(c, k_nbh_sphere<true>, nblk(n, 128), 128, 0, A, C, W);
-  else {
+  if (!poly) {
+    // wave 0 is a copy of what the count pass recorded (unless a particle overflowed its slots); the driver / mesh waves are
+    // enumerated again — a loop over the drivers per particle
+    const bool copy0 = A.pp_tmp && c->h_nbh[1] == 0;
+    bool other = false;
+    for (int t = 4; t < NT; t++) other = other || (active[t] && c->wave[t].n);
+    A.skip_pp = copy0 ? 1 : 0;
+    if (!copy0 || other) LAUNCH(c, k_nbh_sphere<true>, nblk(n, 128), 128, 0, A, C, W);
+    if (copy0 && c->wave[0].n) LAUNCH(c, k_nbh_sphere_copy, nblk(n), BLK, 0, view(c->pa), c->pp_tmp.p, C.c[0], n, W.w[0]);
+  } else {
     if (cell_cap) {
       const uint32_t overflow = c->h_nbh[1];
       const unsigned long long need = *reinterpret_cast<unsigned long long*>(c->h_nbh + 2);

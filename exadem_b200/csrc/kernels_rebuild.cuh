@@ -246,7 +246,13 @@ struct NbhArgs {
   // with — no regular contact is enumerated between the two while the bond holds.  CSR over the real slots; nullptr without bonds.
   const uint32_t* ign_off;
   const unsigned long long* ign_ids;
+  // spheres: the count pass also RECORDS what it finds — candidate s of particle a at pp_tmp[s * nreal + a] = (partner slot, flag
+  // byte), up to PP_TMP_CAP per particle — so that the fill pass is a copy (k_nbh_sphere_copy) instead of a second walk over the
+  // 27-cell stencil; a particle with more candidates raises *pp_overflow and the fill pass enumerates again.
+  uint2* pp_tmp;
+  uint32_t* pp_overflow;
 };
+constexpr uint32_t PP_TMP_CAP = 16;
 __device__ __forceinline__ bool bond_ignored(const NbhArgs& A, uint32_t owner, unsigned long long partner_id) {
   if (!A.ign_off) return false;
   for (uint32_t q = A.ign_off[owner]; q < A.ign_off[owner + 1]; q++)
@@ -360,7 +366,7 @@ __global__ void __launch_bounds__(128) k_nbh_sphere(NbhArgs A, CntTab C, WTab W)
   }
   uint32_t n0 = 0;
   const uint32_t base0 = FILL ? C.c[0][a] : 0;
-  for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
+  if (!(FILL && A.skip_pp)) for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
     const uint64_t idb = A.P.id[b];
     uint8_t ghost = 0;
     if (A.symetric) {  // nbh_sphere.cu:245-249
@@ -369,6 +375,7 @@ __global__ void __launch_bounds__(128) k_nbh_sphere(NbhArgs A, CntTab C, WTab W)
       if (ida >= idb) return;
       if (gc) ghost = 1;
     }
+    if (!FILL && A.pp_tmp && n0 < PP_TMP_CAP) A.pp_tmp[(size_t)n0 * A.nreal + a] = make_uint2(b, (uint32_t)(ghost << 1));
     if (FILL) {
       const uint32_t k = base0 + n0;
       W.w[0].ij[k] = make_uint2(a, b);
@@ -380,12 +387,28 @@ __global__ void __launch_bounds__(128) k_nbh_sphere(NbhArgs A, CntTab C, WTab W)
   });
   if (!FILL) {
     C.c[0][a] = n0;
+    if (A.pp_tmp && n0 > PP_TMP_CAP) *A.pp_overflow = 1u;
     if (C.c[4]) C.c[4][a] = nd[0];
     if (C.c[5]) C.c[5][a] = nd[1];
     if (C.c[6]) C.c[6][a] = nd[2];
     if (C.c[7]) C.c[7][a] = nm[0];
     if (C.c[8]) C.c[8][a] = nm[1];
     if (C.c[9]) C.c[9][a] = nm[2];
+  }
+}
+
+// fill pass of wave 0 from the candidates recorded by the count pass: off = the scanned counts (CSR by owner)
+__global__ void __launch_bounds__(BLK) k_nbh_sphere_copy(PView P, const uint2* __restrict__ tmp, const uint32_t* __restrict__ off, uint32_t n, WView w) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const uint32_t k0 = off[a], cnt = off[a + 1] - k0;
+  for (uint32_t s = 0; s < cnt; s++) {
+    const uint2 e = tmp[(size_t)s * n + a];
+    const uint32_t k = k0 + s;
+    w.ij[k] = make_uint2(a, e.x);
+    w.flg[k] = (uint8_t)e.y;
+    w.ft[k] = make_double4(0, 0, 0, __longlong_as_double((long long)P.id[e.x]));
+    w.mo[k] = make_double4(0, 0, 0, 0);
   }
 }
 
