@@ -15,6 +15,8 @@
 #include "kernels_twin.cuh"
 #include "kernels_driver.cuh"
 #include "kernels_bond.cuh"
+#include "kernels_bond_rebuild.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include "comm.cuh"
 
 using namespace edb;
@@ -130,6 +132,16 @@ struct edb_context {
   DevBuf<uint2> b_ij, b_sub, b_itf;
   DevBuf<double4> b_par, b_fr, b_tds, b_fd, b_cp;
   DevBuf<uint8_t> b_mode, b_unbroken, b_itf_broken;
+  DevBuf<ulonglong2> b_ids;                       // (id_i, id_j) per bond
+  DevBuf<uint8_t> b_ghost;
+  // second set + scratch of the device-side rebuild (kernels_bond_rebuild.cuh)
+  DevBuf<uint2> b2_ij, b2_sub;
+  DevBuf<double4> b2_par, b2_fr, b2_tds, b2_fd, b2_cp;
+  DevBuf<uint8_t> b2_mode, b2_unbroken, b2_ghost, cub_tmp;
+  DevBuf<ulonglong2> b2_ids;
+  DevBuf<uint32_t> b_key, b_key2, b_idx, b_idx2, b_fl_ign, b_rk_ign, b_fl_itf, b_rk_itf, b_ikey, b_ikey2, b_ival, b_ist, b_irk, b_cnt;
+  uint32_t n_conv_dev = 0;                        // broken bonds queued on the device as vertex-vertex history (d_conv)
+  bool env_bonds_host = false;                    // EDB_BONDS_HOST: bonds go through the host at every rebuild (the round-1 path)
   DevBuf<uint32_t> b_plist, b_inc_off, b_inc;
   uint32_t n_bond_particles = 0, n_interfaces = 0;
   DevBuf<uint32_t> b_ign_off;
@@ -331,6 +343,7 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
   c->cfg = *cfg;
   if (c->cfg.nranks < 1) c->cfg.nranks = 1;
   c->env_no_fan = getenv("EDB_NO_FAN") != nullptr;
+  c->env_bonds_host = getenv("EDB_BONDS_HOST") != nullptr;
   c->env_nbh_two_pass = getenv("EDB_NBH_TWO_PASS") != nullptr;
   c->env_land_copy = getenv("EDB_LAND_COPY") != nullptr;
   c->env_gather_mail = getenv("EDB_GATHER_MAIL") != nullptr;
@@ -1239,6 +1252,7 @@ static void driver_force_sums(edb_context* c);
 static void bonds_download(edb_context* c);
 static void bonds_upload(edb_context* c);
 static void bonds_retire_broken(edb_context* c);
+static void bonds_rebuild_device(edb_context* c);
 static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   ScopedTimer tm(c, B_REBUILD);
   const GridDev& G = c->G;
@@ -1404,9 +1418,13 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   if (!c->h_bonds.empty()) {
     // persistent interactions (nbh_polyhedron.cpp:146-149): the bonds follow their particles into the new order by id, and the pairs
     // they glue are ignored by the contact enumeration while they hold
-    bonds_download(c);
-    bonds_retire_broken(c);   // broken bonds leave wave 13; those with friction are queued as vertex-vertex history (below, after k_history)
-    bonds_upload(c);
+    if (c->bonds_on_device && !multi && !c->env_bonds_host) {
+      bonds_rebuild_device(c);  // slots follow old2new, stable sort by new owner, broken bonds cut off / queued, tables rebuilt: all on the device
+    } else {
+      bonds_download(c);
+      bonds_retire_broken(c);   // broken bonds leave wave 13; those with friction are queued as vertex-vertex history (below, after k_history)
+      bonds_upload(c);
+    }
     if (c->have_ignore) { A.ign_off = c->b_ign_off.p; A.ign_ids = c->b_ign_ids.p; }
   }
   WTab W{};
@@ -1514,6 +1532,10 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
         if (!had) ow.n = 0;
         LAUNCH(c, k_history, nblk(c->wave[t].n), BLK, 0, view(c->wave[t]), ow, c->new2old.p, had ? c->n_old_real : n_before, poly || t >= 7, t, H);
       }
+  }
+  if (c->n_conv_dev) {
+    if (c->wave[0].n) LAUNCH(c, k_bond_convert, nblk(c->n_conv_dev), BLK, 0, c->d_conv.p, c->n_conv_dev, view(c->wave[0]));
+    c->n_conv_dev = 0;
   }
   if (!c->h_conv.empty()) {
     if (c->wave[0].n) {
@@ -2421,7 +2443,14 @@ static void bonds_upload(edb_context* c) {
     mode[k] = (uint8_t)b.mode; ub[k] = b.unbroken;
   }
   c->b_ij.ensure(n); c->b_sub.ensure(n); c->b_par.ensure(n); c->b_fr.ensure(n); c->b_tds.ensure(n); c->b_fd.ensure(n); c->b_cp.ensure(n);
-  c->b_mode.ensure(n); c->b_unbroken.ensure(n);
+  c->b_mode.ensure(n); c->b_unbroken.ensure(n); c->b_ids.ensure(n); c->b_ghost.ensure(n);
+  {
+    std::vector<ulonglong2> ids2(n);
+    std::vector<uint8_t> gh(n);
+    for (size_t k = 0; k < n; k++) { ids2[k] = make_ulonglong2(c->h_bonds[k].id_i, c->h_bonds[k].id_j); gh[k] = (uint8_t)c->h_bonds[k].ghost; }
+    CK(cudaMemcpy(c->b_ids.p, ids2.data(), n * sizeof(ulonglong2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->b_ghost.p, gh.data(), n, cudaMemcpyHostToDevice));
+  }
   CK(cudaMemcpy(c->b_ij.p, ij.data(), n * sizeof(uint2), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->b_sub.p, sub.data(), n * sizeof(uint2), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->b_par.p, par.data(), n * sizeof(double4), cudaMemcpyHostToDevice));
@@ -2488,6 +2517,89 @@ static void bonds_upload(edb_context* c) {
   if (!itf.empty()) {
     CK(cudaMemcpy(c->b_itf.p, itf.data(), itf.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     CK(cudaMemset(c->b_itf_broken.p, 0, itf.size()));
+  }
+  c->bonds_on_device = true;
+}
+// The device-side form of bonds_download + bonds_retire_broken + bonds_upload (kernels_bond_rebuild.cuh): called by rebuild() once the
+// re-binning permutation old2new is known.  Two host reads of a few counters; the host mirror follows through the permutation of the
+// surviving bonds (its dynamic fields stay stale until bonds_download).
+static void bonds_rebuild_device(edb_context* c) {
+  const uint32_t n = (uint32_t)c->h_bonds.size();
+  const uint32_t np = c->nreal;
+  c->n_conv_dev = 0;
+  if (n == 0) return;
+  auto arrays = [&](bool second) {
+    return second ? BondArrays{c->b2_ij.p, c->b2_sub.p, c->b2_ids.p, c->b2_par.p, c->b2_fr.p, c->b2_tds.p, c->b2_fd.p, c->b2_cp.p, c->b2_mode.p, c->b2_unbroken.p, c->b2_ghost.p}
+                  : BondArrays{c->b_ij.p, c->b_sub.p, c->b_ids.p, c->b_par.p, c->b_fr.p, c->b_tds.p, c->b_fd.p, c->b_cp.p, c->b_mode.p, c->b_unbroken.p, c->b_ghost.p};
+  };
+  c->b2_ij.ensure(n); c->b2_sub.ensure(n); c->b2_ids.ensure(n); c->b2_par.ensure(n); c->b2_fr.ensure(n); c->b2_tds.ensure(n); c->b2_fd.ensure(n);
+  c->b2_cp.ensure(n); c->b2_mode.ensure(n); c->b2_unbroken.ensure(n); c->b2_ghost.ensure(n);
+  c->b_key.ensure(n + 1); c->b_key2.ensure(n + 1); c->b_idx.ensure(n + 1); c->b_idx2.ensure(n + 1); c->b_cnt.ensure(8);
+  c->d_conv.ensure(n);
+  CK(cudaMemsetAsync(c->b_cnt.p, 0, 32, c->st));
+  LAUNCH(c, k_bond_rekey, nblk(n), BLK, 0, arrays(false), n, c->old2new.p, c->b_key.p, c->b_idx.p, c->b_cnt.p, c->d_conv.p);
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, c->b_key.p, c->b_key2.p, c->b_idx.p, c->b_idx2.p, (int)n, 0, 32, c->st);
+  size_t tb2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb2, c->b_key.p, c->b_key2.p, c->b_idx.p, c->b_idx2.p, (int)(2 * n), 0, 32, c->st);
+  c->cub_tmp.ensure(std::max(tb, tb2) + 16);
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb, c->b_key.p, c->b_key2.p, c->b_idx.p, c->b_idx2.p, (int)n, 0, 32, c->st));
+  c->ctr.kernel_launches += 4;
+  uint32_t h_cnt[8] = {};
+  CK(cudaMemcpyAsync(h_cnt, c->b_cnt.p, 32, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  const uint32_t n_keep = n - h_cnt[0];
+  c->n_conv_dev = h_cnt[1];
+  // host mirror: the surviving bonds in their new order (static fields; the dynamic ones are read back on demand)
+  {
+    std::vector<uint32_t> perm(n_keep);
+    if (n_keep) CK(cudaMemcpy(perm.data(), c->b_idx2.p, (size_t)n_keep * 4, cudaMemcpyDeviceToHost));
+    std::vector<edb_inner_bond> nh(n_keep);
+    for (uint32_t k = 0; k < n_keep; k++) { nh[k] = c->h_bonds[perm[k]]; nh[k].unbroken = 1; }
+    c->h_bonds.swap(nh);
+  }
+  c->n_bond_particles = 0; c->n_interfaces = 0; c->have_ignore = false;
+  if (n_keep == 0) { c->bonds_on_device = false; return; }
+  LAUNCH(c, k_bond_permute, nblk(n_keep), BLK, 0, arrays(true), arrays(false), n_keep, c->b_key2.p, c->b_idx2.p, c->old2new.p);
+  std::swap(c->b_ij, c->b2_ij); std::swap(c->b_sub, c->b2_sub); std::swap(c->b_ids, c->b2_ids); std::swap(c->b_par, c->b2_par);
+  std::swap(c->b_fr, c->b2_fr); std::swap(c->b_tds, c->b2_tds); std::swap(c->b_fd, c->b2_fd); std::swap(c->b_cp, c->b2_cp);
+  std::swap(c->b_mode, c->b2_mode); std::swap(c->b_unbroken, c->b2_unbroken); std::swap(c->b_ghost, c->b2_ghost);
+  // derived tables
+  const uint32_t m = n_keep;
+  c->b_fl_ign.ensure(m + 2); c->b_rk_ign.ensure(m + 2); c->b_fl_itf.ensure(m + 2); c->b_rk_itf.ensure(m + 2);
+  c->b_ikey.ensure(2 * (size_t)m + 2); c->b_ikey2.ensure(2 * (size_t)m + 2); c->b_ival.ensure(2 * (size_t)m + 2); c->b_inc.ensure(2 * (size_t)m + 2);
+  c->b_ist.ensure(2 * (size_t)m + 2); c->b_irk.ensure(2 * (size_t)m + 3);
+  c->b_ign_off.ensure((size_t)np + 2); c->b_ign_ids.ensure((size_t)m + 1);
+  c->b_itf.ensure((size_t)m + 1); c->b_itf_broken.ensure((size_t)m + 1);
+  c->b_plist.ensure(2 * (size_t)m + 2); c->b_inc_off.ensure(2 * (size_t)m + 3);
+  c->tmp.ensure((size_t)np + 2);
+  CK(cudaMemsetAsync(c->tmp.p, 0, ((size_t)np + 1) * 4, c->st));            // per-owner count of ignore entries
+  CK(cudaMemsetAsync(c->b_cnt.p, 0, 32, c->st));
+  LAUNCH(c, k_bond_flags, nblk(m), BLK, 0, arrays(false), m, c->b_fl_ign.p, c->tmp.p, c->b_fl_itf.p, c->b_ikey.p, c->b_ival.p, c->b_cnt.p);
+  scan_u32(c, c->tmp.p, c->b_ign_off.p, np);
+  scan_u32(c, c->b_fl_ign.p, c->b_rk_ign.p, m);
+  scan_u32(c, c->b_fl_itf.p, c->b_rk_itf.p, m);
+  LAUNCH(c, k_bond_scatter, nblk(m), BLK, 0, arrays(false), m, c->b_fl_ign.p, c->b_rk_ign.p, c->b_ign_ids.p, c->b_fl_itf.p, c->b_rk_itf.p, c->b_itf.p);
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tb2, c->b_ikey.p, c->b_ikey2.p, c->b_ival.p, c->b_inc.p, (int)(2 * m), 0, 32, c->st));
+  c->ctr.kernel_launches += 4;
+  CK(cudaMemcpyAsync(h_cnt, c->b_cnt.p, 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(h_cnt + 1, c->b_rk_ign.p + m, 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(h_cnt + 2, c->b_rk_itf.p + m, 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  const uint32_t n_valid = h_cnt[0], n_ign = h_cnt[1], n_itf = h_cnt[2];
+  c->have_ignore = n_ign > 0;
+  c->n_interfaces = n_itf;
+  if (n_itf) {
+    LAUNCH(c, k_itf_lengths, nblk(n_itf), BLK, 0, c->b_itf.p, n_itf, m);
+    CK(cudaMemsetAsync(c->b_itf_broken.p, 0, n_itf, c->st));
+  }
+  if (n_valid) {
+    LAUNCH(c, k_bond_inc_flags, nblk(n_valid), BLK, 0, c->b_ikey2.p, n_valid, c->b_ist.p);
+    scan_u32(c, c->b_ist.p, c->b_irk.p, n_valid);
+    LAUNCH(c, k_bond_inc_lists, nblk(n_valid + 1), BLK, 0, c->b_ikey2.p, c->b_ist.p, c->b_irk.p, n_valid, c->b_plist.p, c->b_inc_off.p);
+    CK(cudaMemcpyAsync(h_cnt, c->b_irk.p + n_valid, 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    c->n_bond_particles = h_cnt[0];
   }
   c->bonds_on_device = true;
 }
