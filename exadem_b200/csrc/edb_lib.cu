@@ -141,6 +141,7 @@ struct edb_context {
   DevBuf<ulonglong2> b2_ids;
   DevBuf<uint32_t> b_key, b_key2, b_idx, b_idx2, b_fl_ign, b_rk_ign, b_fl_itf, b_rk_itf, b_ikey, b_ikey2, b_ival, b_ist, b_irk, b_cnt;
   uint32_t n_conv_dev = 0;                        // broken bonds queued on the device as vertex-vertex history (d_conv)
+  bool env_bonds_unfused = false;                 // EDB_BONDS_UNFUSED: edb_run_verlet with bonds runs the operator-by-operator loop
   bool env_bonds_host = false;                    // EDB_BONDS_HOST: bonds go through the host at every rebuild (the round-1 path)
   DevBuf<uint32_t> b_plist, b_inc_off, b_inc;
   uint32_t n_bond_particles = 0, n_interfaces = 0;
@@ -344,6 +345,7 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
   if (c->cfg.nranks < 1) c->cfg.nranks = 1;
   c->env_no_fan = getenv("EDB_NO_FAN") != nullptr;
   c->env_bonds_host = getenv("EDB_BONDS_HOST") != nullptr;
+  c->env_bonds_unfused = getenv("EDB_BONDS_UNFUSED") != nullptr;
   c->env_nbh_two_pass = getenv("EDB_NBH_TWO_PASS") != nullptr;
   c->env_land_copy = getenv("EDB_LAND_COPY") != nullptr;
   c->env_gather_mail = getenv("EDB_GATHER_MAIL") != nullptr;
@@ -1745,7 +1747,7 @@ static void contact_waves(edb_context* c, double dt, const unsigned long long* g
 // next_flag (FUSE 2 only): where the rebuild trigger of the next step is accumulated (nullptr: not evaluated)
 template <int FUSE>
 static void gather(edb_context* c, const double* g, double dt, const unsigned long long* gate = nullptr,
-                   unsigned long long* next_flag = nullptr, double thr = 0.0) {
+                   unsigned long long* next_flag = nullptr, double thr = 0.0, bool base_from_arrays = false) {
   ScopedTimer tm(c, B_GATHER);
   const bool poly = c->poly();
   GatherArgs A{};
@@ -1766,6 +1768,7 @@ static void gather(edb_context* c, const double* g, double dt, const unsigned lo
   A.dt2 = dt * dt * 0.5;
   A.gate = gate;
   A.next_flag = next_flag;
+  A.base_from_arrays = base_from_arrays ? 1 : 0;
   A.reset_queue = (FUSE == 2 && !poly) ? c->d_need_count : nullptr;
   if (A.reset_queue) c->queue_clean = true;
   A.pr_backup = next_flag ? c->pr_backup.p : nullptr;
@@ -1842,8 +1845,9 @@ static void trigger_standalone(edb_context* c, int slot, double thr) {
 // memory, one step behind the launch front) afterwards.  When the flag says "rebuild", the gated kernels have done nothing and
 // the step is enqueued again behind the rebuild.  The GPU never idles on the host in the common no-rebuild case.
 
-static void bond_force_launch(edb_context* c, double dt);
+static void bond_force_launch(edb_context* c, double dt, const unsigned long long* gate = nullptr);
 static uint64_t interface_criterion_launch(edb_context* c);
+static void interface_criterion_async(edb_context* c, unsigned long long* flag);
 static void bond_friction_updater_launch(edb_context* c);
 // The same macro with moving drivers (edb_set_driver_motions): operator by operator in the reference's order
 // (config_numerical_schemes.msp:12-29, check_and_update_particles of config_move_particles.msp:186-189), drivers integrated on the
@@ -1998,12 +2002,17 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
   API_BEGIN(c)
   uint64_t nb = 0;
   if (!c->have_prev) { rebuild(c, rcut_inc, symetric); }
-  if (!c->h_bonds.empty()) {
+  const bool bonds = !c->h_bonds.empty();
+  if (bonds) {
     if (c->cfg.nranks > 1) throw StateError{EDB_ERR_STATE, "edb_run_verlet: inner bonds on several ranks are not supported yet"};
-    nb = c->drivers_moving ? run_verlet_moving(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every)
-                           : run_verlet_bonds(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every);
-    if (n_rebuilds) *n_rebuilds = nb;
-    return EDB_OK;
+    // moving drivers, a fixed rebuild period, or EDB_BONDS_UNFUSED: the fragmentation macro operator by operator (one host read per step);
+    // otherwise the speculative loop below carries the bond operators (the fracture criterion feeds the device-side rebuild trigger)
+    if (c->drivers_moving || rebuild_every > 0 || c->env_bonds_unfused) {
+      nb = c->drivers_moving ? run_verlet_moving(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every)
+                             : run_verlet_bonds(c, dt, g, rcut_inc, symetric, nsteps, rebuild_every);
+      if (n_rebuilds) *n_rebuilds = nb;
+      return EDB_OK;
+    }
   }
   const bool mv = c->drivers_moving;
   if (mv && c->env_drivers_unfused) {
@@ -2011,8 +2020,10 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
     if (n_rebuilds) *n_rebuilds = nb;
     return EDB_OK;
   }
-  const bool trig = rebuild_every == 0;
-  const double thr = 0.5 * rcut_inc;
+  // with bonds a break must rebuild even when the caller asked for no displacement trigger (rebuild_every < 0): the trigger slot
+  // then only counts broken interfaces (an infinite displacement threshold)
+  const bool trig = rebuild_every == 0 || bonds;
+  const double thr = rebuild_every == 0 ? 0.5 * rcut_inc : 1e300;
   const bool poly = c->poly();
   double tcur = c->physical_time;   // physical time of the step being enqueued (advanced by repeated addition like next_time_step)
   if (mv) {
@@ -2029,9 +2040,13 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
     const int slot = it & 1, nslot = slot ^ 1;
     auto step_kernels = [&](const unsigned long long* gate) {
       bool zeroed = false;
+      if (bonds) {   // reset_force_moment, gravity_force, inner_bond_polyhedron into the force arrays; the gather starts from them
+        LAUNCH(c, k_reset_gravity, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, g[0], g[1], g[2], gate);
+        bond_force_launch(c, dt, gate);
+      }
       contact_waves(c, dt, gate, (!last && trig) ? c->d_sflag + nslot : nullptr, &zeroed);
       if (last) {
-        gather<1>(c, g, dt, gate);
+        gather<1>(c, g, dt, gate, nullptr, 0.0, bonds);
         if (mv) driver_cycle(c, g, dt, tcur + dt, true, false, gate, nullptr, thr);
         return;
       }
@@ -2041,7 +2056,7 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
         return;
       }
       if (!zeroed) CK(cudaMemsetAsync(c->d_sflag + nslot, 0, 8, c->st));
-      gather<2>(c, g, dt, gate, c->d_sflag + nslot, thr);
+      gather<2>(c, g, dt, gate, c->d_sflag + nslot, thr, bonds);
       if (mv) driver_cycle(c, g, dt, tcur + dt, true, true, gate, c->d_sflag + nslot, thr);
     };
     if (!trig) {
@@ -2051,6 +2066,10 @@ extern "C" int edb_run_verlet(edb_context* c, double dt, const double g[3], doub
       step_kernels(nullptr);
     } else {
       const edb_counters snap = c->ctr;
+      if (bonds) {   // apply_interface_fracture_criterion + broken_interface_friction_updater of this step: a break is a rebuild trigger
+        interface_criterion_async(c, c->d_sflag + slot);
+        bond_friction_updater_launch(c);
+      }
       ghost_refresh(c, false, c->d_sflag + slot, true);
       trigger_publish(c, slot);
       compute_vertices(c, it > 0);
@@ -2719,14 +2738,14 @@ extern "C" int edb_update_interfaces(edb_context* c, uint64_t* n_interfaces) {
   if (n_interfaces) *n_interfaces = c->n_interfaces;
   API_END(c)
 }
-static void bond_force_launch(edb_context* c, double dt) {
+static void bond_force_launch(edb_context* c, double dt, const unsigned long long* gate) {
   const uint32_t n = (uint32_t)c->h_bonds.size();
   if (n == 0) return;
   if (!c->bonds_on_device) throw StateError{EDB_ERR_STATE, "inner_bond_polyhedron before edb_import_inner_bonds / edb_update_interfaces"};
   if (!c->ibp_groups) throw StateError{EDB_ERR_STATE, "inner_bond_polyhedron before edb_set_inner_bond_params"};
   if (c->S.nvmax <= 0 || !c->vert.p) throw StateError{EDB_ERR_STATE, "inner_bond_polyhedron needs the world vertices (edb_compute_vertices)"};
-  LAUNCH(c, k_bond_force, nblk(n), BLK, 0, bond_view(c), view(c->pa), c->vert.p, c->S, c->d_ibp.p, c->ibp_groups, dt);
-  LAUNCH(c, k_bond_gather, nblk(c->n_bond_particles), BLK, 0, bond_view(c), view(c->pa), c->b_plist.p, c->b_inc_off.p, c->b_inc.p, c->n_bond_particles);
+  LAUNCH(c, k_bond_force, nblk(n), BLK, 0, bond_view(c), view(c->pa), c->vert.p, c->S, c->d_ibp.p, c->ibp_groups, dt, gate);
+  LAUNCH(c, k_bond_gather, nblk(c->n_bond_particles), BLK, 0, bond_view(c), view(c->pa), c->b_plist.p, c->b_inc_off.p, c->b_inc.p, c->n_bond_particles, gate);
   c->ctr.interaction_updates += n;
 }
 static uint64_t interface_criterion_launch(edb_context* c) {
@@ -2736,6 +2755,11 @@ static uint64_t interface_criterion_launch(edb_context* c) {
   CK(cudaMemcpyAsync(c->h_flag, c->d_flag, 8, cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
   return c->h_flag[0];
+}
+// speculative loop: the number of interfaces that break is ADDED to the rebuild trigger of the step (device flag), no host read
+static void interface_criterion_async(edb_context* c, unsigned long long* flag) {
+  if (c->n_interfaces == 0) return;
+  LAUNCH(c, k_interface_criterion, nblk(c->n_interfaces), BLK, 0, bond_view(c), c->b_itf.p, c->n_interfaces, c->b_itf_broken.p, flag);
 }
 static void bond_friction_updater_launch(edb_context* c) {
   if (c->n_interfaces == 0 || !c->bonds_on_device) return;

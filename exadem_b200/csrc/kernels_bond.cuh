@@ -57,9 +57,9 @@ EDB_HD bool interface_breaks(int mode, double c1, double c2, double En, double E
 
 // one thread per bond: vertex-vertex detection on the world vertices (detection_vertex_vertex, shape_detection_api.hpp) + the law
 __global__ void __launch_bounds__(BLK) k_bond_force(BondView B, PView P, const double4* __restrict__ vert, ShapesView S, const BondParams* __restrict__ ibp,
-                                                    int n_groups, double dt) {
+                                                    int n_groups, double dt, const unsigned long long* gate) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= B.n) return;
+  if (k >= B.n || (gate && *gate)) return;
   const uint2 ij = B.ij[k];
   // a broken bond no longer acts (its conversion into a vertex-vertex contact at the next rebuild is not built yet, see the header)
   if (ij.x == 0xffffffffu || ij.y == 0xffffffffu || !B.unbroken[k]) {
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(BLK) k_bond_force(BondView B, PView P, const d
 // one thread per particle that carries bonds: f += sum(+-f_i), mom += sum(cross(cp - r, +-f_i)) over its incident bonds in list order
 // (inner_bond.hpp:166-178).  inc = bond index << 1 | side (0: particle is i, 1: particle is j).
 __global__ void __launch_bounds__(BLK) k_bond_gather(BondView B, PView P, const uint32_t* __restrict__ plist, const uint32_t* __restrict__ inc_off,
-                                                     const uint32_t* __restrict__ inc, uint32_t nlist) {
+                                                     const uint32_t* __restrict__ inc, uint32_t nlist, const unsigned long long* gate) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nlist) return;
+  if (t >= nlist || (gate && *gate)) return;
   const uint32_t p = plist[t];
   const v3 r = xyz(ldg4(P.pr + p));
   v3 f = mk3(P.fx[p], P.fy[p], P.fz[p]), m = mk3(P.mx[p], P.my[p], P.mz[p]);

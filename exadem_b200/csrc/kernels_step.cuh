@@ -139,6 +139,14 @@ __global__ void k_gravity(PView P, uint32_t n, double gx, double gy, double gz) 
   const double m = P.vm[p].w;
   P.fx[p] += gx * m; P.fy[p] += gy * m; P.fz[p] += gz * m;
 }
+// reset_force_moment + gravity_force in one pass (same expressions: 0 + g m), gated like the other kernels of a speculative step
+__global__ void k_reset_gravity(PView P, uint32_t n, double gx, double gy, double gz, const unsigned long long* gate) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n || (gate && *gate)) return;
+  const double m = P.vm[p].w;
+  P.fx[p] = 0.0 + gx * m; P.fy[p] = 0.0 + gy * m; P.fz[p] = 0.0 + gz * m;
+  P.mx[p] = 0; P.my[p] = 0; P.mz[p] = 0;
+}
 __global__ void k_force_to_accel(PView P, uint32_t n) {  // force_to_accel.hpp:26-33
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
@@ -678,6 +686,9 @@ struct GatherArgs {
   unsigned long long* next_flag;       // += number of particles with |r - r_backup|^2 >= thr2 after the next prolog
   const unsigned long long* gate;      // see ContactArgs::gate
   uint32_t* reset_queue;               // FUSE 2: zeroed for the next step's k_contact_sphere_pp (saves a memset per step)
+  // FUSE 1 / 2: start the sums from the force / moment ARRAYS instead of from gravity — they hold reset_force_moment + gravity_force +
+  // inner_bond_polyhedron of this step (k_reset_gravity, k_bond_gather), in the operator order of the fragmentation macro
+  int base_from_arrays;
 };
 
 // role_i: particle acts as "i" of the record: F += f, M += (cp - r) x f + mom;  as "j": F += -f, M += (cp - r) x (-f) + (-mom)
@@ -742,8 +753,13 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
   double4 vm;
   if (FUSE) {
     vm = KEEP ? ld4h(A.P.vm + p, pol.keep) : ld4(A.P.vm + p);
-    F = mk3(0.0 + A.g[0] * vm.w, 0.0 + A.g[1] * vm.w, 0.0 + A.g[2] * vm.w);
-    M = mk3(0, 0, 0);
+    if (A.base_from_arrays) {
+      F = mk3(A.P.fx[p], A.P.fy[p], A.P.fz[p]);
+      M = mk3(A.P.mx[p], A.P.my[p], A.P.mz[p]);
+    } else {
+      F = mk3(0.0 + A.g[0] * vm.w, 0.0 + A.g[1] * vm.w, 0.0 + A.g[2] * vm.w);
+      M = mk3(0, 0, 0);
+    }
   } else {
     F = mk3(A.P.fx[p], A.P.fy[p], A.P.fz[p]);
     M = mk3(A.P.mx[p], A.P.my[p], A.P.mz[p]);
