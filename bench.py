@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-poly", action="store_true", help="skip the polyhedra line reported alongside (N=1 only)")
+    ap.add_argument("--no-mixed", action="store_true", help="skip the 4 M mixed spheres + polyhedra line (configs[3]) reported alongside (N=1 only)")
     ap.add_argument("--no-secondary", action="store_true", help="N>1: skip the box-brick / single-brick lines reported alongside")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     return ap.parse_args()
@@ -388,12 +389,19 @@ def sphere_rooflines(c, counts, active, n_real, ms, steps, peak, peak_src, tr, w
     return out
 
 
-def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=60, warmup=10):
-    """BASELINE configs[2] reported alongside (north_star): ~500 k octahedra, the vertex/edge/face contact path.  The timed region is a
-    FLOWING state (the packing falls under gravity with random angular velocities) so that it contains neighbour rebuilds."""
+DRIFT = 8.0   # uniform drift velocity of the "flowing" polyhedra lines: 8e-4 per step against a trigger of rcut_inc/2 = 0.05
+
+
+def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=150, warmup=10, mixed=False):
+    """BASELINE configs[2] (and, mixed=True, configs[3]) reported alongside (north_star): ~500 k octahedra, the vertex/edge/face contact
+    path.  The timed region is a FLOWING state: the whole packing drifts through its periodic box (the walled mixed case: falls) at
+    DRIFT, so the displacement trigger fires every ~60 steps and the timed region CONTAINS neighbour rebuilds — their cost is inside
+    `value`, `rebuilds_in_timed_region` says how many."""
     from exadem_b200 import Engine, workloads
     side = int(round(n ** (1.0 / 3.0)))
-    wl = workloads.polyhedra_box((side, side, side), pitch=0.78)
+    wl = mixed_workload(n) if mixed else workloads.polyhedra_box((side, side, side), pitch=0.78)
+    if not mixed:   # (the walled mixed packing relaxes violently on its own: its trigger fires every ~10 steps without any drift)
+        wl.particles.vx += DRIFT
     eng = wl.setup(Engine(lib, wl.config(device=device)))
     eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)
     eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, warmup, 0)
@@ -418,6 +426,7 @@ def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=60, warmup=
     t = c.contact_pp_ms / steps * 1e-3            # the two launches that cover the four particle-particle waves, per step
     rec = float(counts[:4].sum())
     hot = float(active[:4].sum())
+    nv_mean = 6.0 if not mixed else 5.0
     # the two launches' own traffic: detection reads ij + sub + flg (17 B) per record and, through L1/L2, the two vertex sets of every
     # owner-partner pair (counted once per particle: 32 B x 6 vertices + type/homothety sectors); the law pass moves 128 B of history /
     # wrench + 6 particle sectors + the 4 B list entry per record in contact
@@ -425,7 +434,9 @@ def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=60, warmup=
     # 184 B/record + 8 (sub) + 24 k of vertices (k = 2 V-V, 3 V-E, 1 + 3 V-F on triangles, 4 E-E) + 92 B/particle per wave
     alg = sum(float(counts[w]) * (192.0 + 24.0 * k) for w, k in ((0, 2), (1, 3), (2, 4), (3, 4))) + 4 * 92.0 * n_real
     tp, cap = traffic_for(tr, "k_detect_poly_pp+k_law_poly_pp", "poly", steps, warmup)
-    return {"workload": f"{n_real} octahedra, periodic packing (configs[2])", "value": c.interaction_updates / (ms * 1e-3),
+    what = (f"{n_real} spheres + octahedra + cubes, cohesive law, closed mesh walls (configs[3])" if mixed
+            else f"{n_real} octahedra, periodic packing (configs[2])")
+    return {"workload": what + (f", drifting at {DRIFT} (flowing state)" if not mixed else ", relaxing from the lattice (flowing state)"), "value": c.interaction_updates / (ms * 1e-3),
             "unit": UNIT, "particle_steps_per_s": c.particle_steps / (ms * 1e-3), "steps": steps, "ms_per_step": ms / steps,
             "interactions": int(counts.sum()), "active_interactions": int(active.sum()), "rebuilds_in_timed_region": int(nreb),
             "rebuild_once_ms": reb,
@@ -655,9 +666,11 @@ def main():
                 "share_of_step": c.contact_pp_ms / ms if ms > 0 else None}
     roof["per_step_ms"] = per_step
     roof["rebuild_once_ms"] = rebuild_once_ms
-    poly = None
+    poly = mixed = None
     if world == 1 and not args.no_poly and name == "drum":
         poly = polyhedra_line(lib, peak, peak_src, local, tr)
+        if not args.no_mixed:
+            mixed = polyhedra_line(lib, peak, peak_src, local, tr, n=4_000_000, steps=40, warmup=5, mixed=True)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_baseline_leg(make(0, 1), args.cpu_seconds)
@@ -673,6 +686,8 @@ def main():
         line["roofline_" + ("gather" if roof_other["kernel"].startswith("k_gather") else "contact")] = roof_other
     if poly is not None:
         line["polyhedra"] = poly
+    if mixed is not None:
+        line["mixed_4m"] = mixed
     if box is not None:
         line["box_bricks"] = box
     if single is not None:

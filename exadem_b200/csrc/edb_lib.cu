@@ -1701,7 +1701,11 @@ static void launch_contact_waves(edb_context* c, double dt, const unsigned long 
         }
       } else {
         if (!queue_clean) CK(cudaMemsetAsync(c->d_need_count, 0, 4, c->st));
+#if EDB_PP_PIPE
+        LAUNCH(c, k_contact_sphere_pp_pipe<LAW>, (uint32_t)std::min<uint64_t>(nblk(w.n, CHUNK * (PP_BLK / 32)), (uint64_t)c->n_sm * PP_MINB), PP_BLK, 0, A, c->d_need_count);
+#else
         LAUNCH(c, k_contact_sphere_pp<LAW>, (uint32_t)std::min<uint64_t>(nblk(w.n, CHUNK * (PP_BLK / 32)), (uint64_t)c->n_sm * PP_MINB), PP_BLK, 0, A, c->d_need_count);
+#endif
       }
       c->ctr.contact_pp_launches++;
       c->ctr.contact_pp_records += w.n;

@@ -90,6 +90,13 @@ __device__ __forceinline__ double reach2(double bnd, double R, v3 c) {
   return r * r;
 }
 
+// index of the n-th (0-based) set bit of m.  __fns is a ~40-instruction library routine and was 10 % of the instructions of the
+// neighbour build (profiles/r2_ncu_polynbh_lines.txt); the masks here have a handful of bits set.
+__device__ __forceinline__ uint32_t nth_set_bit(uint32_t m, uint32_t n) {
+  for (uint32_t k = 0; k < n; k++) m &= m - 1;
+  return (uint32_t)__ffs((int)m) - 1u;
+}
+
 struct NbhPool {
   uint32_t* words;                // cap_chunks * CHW
   uint32_t* cursor;               // next free chunk
@@ -141,6 +148,7 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
   __shared__ uint32_t s_cbase[28], s_cbeg[27], s_next;
   __shared__ uint8_t s_cgc[27];
   __shared__ uint16_t s_queue[NPC_THREADS / 32][64];
+  __shared__ uint32_t s_vmask[NPC_THREADS / 32][2][32];   // vertex-vs-OBB prefilter masks (mA, mB) of the pairs of one OBB round
 
   const GridDev& G = A.G;
   const uint32_t c = blockIdx.x;
@@ -290,12 +298,55 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
         if (lane < rest) qu[lane] = keep;
         __syncwarp();
         nq = rest;
+        // Vertex-vs-OBB prefilters of ALL the pairs that passed this OBB round, batched: a pair needs nv_a (resp. nv_b) lanes, so a
+        // round serves 32 / S pairs (S = 8, 16 or 32 lanes per pair) instead of one — with octahedra 4 pairs per round.  The OBBs are
+        // enlarged in two half steps like the reference (:268-276, :305-310); same functions on the same inputs as before, only computed
+        // ahead of the pair loop.
+        {
+          const int npass = __popc(pm);
+          uint32_t* vmA = s_vmask[wid][0];
+          uint32_t* vmB = s_vmask[wid][1];
+          const int SA = sa.nv <= 8 ? 8 : (sa.nv <= 16 ? 16 : 32), SB = nvmax <= 8 ? 8 : (nvmax <= 16 ? 16 : 32);
+          for (int q0 = 0; q0 < npass; q0 += 32 / SA) {
+            const int q = q0 + lane / SA, v = lane % SA;
+            const int l = (int)nth_set_bit(pm, (uint32_t)(q < npass ? q : 0));
+            const uint32_t Lq = __shfl_sync(0xffffffffu, Lc, l);
+            bool ok = false;
+            if (q < npass && v < sa.nv) {
+              const double4 rb = s_pr[Lq], qb4 = s_q[Lq];
+              Obb oj = obb_world(A.S.sh[s_type[Lq]].obb, mk3(rb.x, rb.y, rb.z), q4{qb4.x, qb4.y, qb4.z, qb4.w}, s_h[Lq]);
+              obb_enlarge(oj, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
+              ok = obb_intersect(oj, obb_point(va[v], rma));
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (q < npass && v == 0) vmA[q] = SA == 32 ? m : ((m >> (lane & ~(SA - 1))) & ((1u << SA) - 1u));
+          }
+          for (int q0 = 0; q0 < npass; q0 += 32 / SB) {
+            const int q = q0 + lane / SB, v = lane % SB;
+            const int l = (int)nth_set_bit(pm, (uint32_t)(q < npass ? q : 0));
+            const uint32_t Lq = __shfl_sync(0xffffffffu, Lc, l);
+            bool ok = false;
+            if (q < npass) {
+              const ShapeDev* __restrict__ psq = A.S.sh + s_type[Lq];
+              if (v < psq->nv) {
+                Obb oi = obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha);
+                obb_enlarge(oi, 0.5 * rV); obb_enlarge(oi, 0.5 * rV);
+                const SV vq{s_vert + (size_t)Lq * nvmax};
+                ok = obb_intersect(oi, obb_point(vq[v], s_h[Lq] * psq->radius));
+              }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (q < npass && v == 0) vmB[q] = SB == 32 ? m : ((m >> (lane & ~(SB - 1))) & ((1u << SB) - 1u));
+          }
+          __syncwarp();
+        }
+        int qi = 0;
         while (pm) {
           const int l = __ffs(pm) - 1;
           pm &= pm - 1;
           const uint32_t Lb = __shfl_sync(0xffffffffu, Lc, l);   // warp-uniform
           const uint32_t b = s_slot[Lb];
-          const double4 rb = s_pr[Lb], qb4 = s_q[Lb];
+          const double4 rb = s_pr[Lb];
           const unsigned long long idb = s_id[Lb];
           const ShapeDev* __restrict__ psb = A.S.sh + s_type[Lb];
           const struct { int nv, ne, nf, e0, f0, fi0; double radius; } sb{psb->nv, psb->ne, psb->nf, psb->e0, psb->f0, psb->fi0, psb->radius};
@@ -303,18 +354,8 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
           const SV vb{s_vert + (size_t)Lb * nvmax};
           const double rmb = hb * sb.radius;
           const int* eb = A.S.edges + 2 * sb.e0;
-          // vertex-vs-OBB prefilters, one vertex per lane; the OBBs are enlarged in two half steps like the reference (:268-276, :305-310)
-          unsigned mA, mB;
-          {
-            Obb oj = obb_world(psb->obb, mk3(rb.x, rb.y, rb.z), q4{qb4.x, qb4.y, qb4.z, qb4.w}, hb);
-            obb_enlarge(oj, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
-            mA = __ballot_sync(0xffffffffu, lane < sa.nv && obb_intersect(oj, obb_point(va[lane < sa.nv ? lane : 0], rma)));
-          }
-          {
-            Obb oi = obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha);
-            obb_enlarge(oi, 0.5 * rV); obb_enlarge(oi, 0.5 * rV);
-            mB = __ballot_sync(0xffffffffu, lane < sb.nv && obb_intersect(oi, obb_point(vb[lane < sb.nv ? lane : 0], rmb)));
-          }
+          const unsigned mA = s_vmask[wid][0][qi], mB = s_vmask[wid][1][qi];
+          qi++;
           // edge reach masks (see seg_point_d2): lanes [0, ne_a) test a's edges against b's bounding sphere, lanes [16, 16 + ne_b)
           // b's edges against a's; shapes with more than 16 edges keep every edge
           unsigned eA = sa.ne >= 32 ? 0xffffffffu : ((1u << sa.ne) - 1u), eB = sb.ne >= 32 ? 0xffffffffu : ((1u << sb.ne) - 1u);
@@ -348,11 +389,11 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
           // The vertex-vs-OBB prefilter usually keeps 1-3 of the vertices: the test index space is built over the KEPT vertices only
           // (n-th set bit of the mask, ascending, so the emission order is unchanged) and the lanes stay busy.
           const uint32_t nA = __popc(mA), nB = __popc(mB);
-          auto vtxA = [&](uint32_t n) { return (uint32_t)__fns(mA, 0, (int)n + 1); };
-          auto vtxB = [&](uint32_t n) { return (uint32_t)__fns(mB, 0, (int)n + 1); };
+          auto vtxA = [&](uint32_t n) { return nth_set_bit(mA, n); };
+          auto vtxB = [&](uint32_t n) { return nth_set_bit(mB, n); };
           const uint32_t nEA = __popc(eA), nEB = __popc(eB);
-          auto edgA = [&](uint32_t n) { return (uint32_t)__fns(eA, 0, (int)n + 1); };
-          auto edgB = [&](uint32_t n) { return (uint32_t)__fns(eB, 0, (int)n + 1); };
+          auto edgA = [&](uint32_t n) { return nth_set_bit(eA, n); };
+          auto edgB = [&](uint32_t n) { return nth_set_bit(eB, n); };
           // A -> B (swap = 0): vertices of a against vertices / edges / faces of b
           group(0, nA * nvb,
                 [&](uint32_t x) { const uint32_t i = vtxA(x / nvb), j = x % nvb; return filter_vv(rV, va[i], rma, vb[j], rmb); },
@@ -440,14 +481,14 @@ __global__ void __launch_bounds__(256) k_nbh_poly_replay(NbhArgs A, CntTab C, WT
       W.w[t].ft[k] = make_double4(0, 0, 0, __longlong_as_double((long long)idb));
       W.w[t].mo[k] = make_double4(0, 0, 0, 0);
     };
-    auto vtxA = [&](uint32_t n) { return (uint32_t)__fns(mA, 0, (int)n + 1); };
-    auto vtxB = [&](uint32_t n) { return (uint32_t)__fns(mB, 0, (int)n + 1); };
+    auto vtxA = [&](uint32_t n) { return nth_set_bit(mA, n); };
+    auto vtxB = [&](uint32_t n) { return nth_set_bit(mB, n); };
     group(0, nA * nvb, [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
     group(1, nA * neb, [&](uint32_t x, uint32_t k) { write(1, k, a, b, vtxA(x / neb), x % neb, f0); });
     group(2, nA * nfb, [&](uint32_t x, uint32_t k) { write(2, k, a, b, vtxA(x / nfb), x % nfb, f0); });
     const uint32_t nEB = __popc(eB);
     group(3, __popc(eA) * nEB,
-          [&](uint32_t x, uint32_t k) { write(3, k, a, b, (uint32_t)__fns(eA, 0, (int)(x / nEB) + 1), (uint32_t)__fns(eB, 0, (int)(x % nEB) + 1), f0); });
+          [&](uint32_t x, uint32_t k) { write(3, k, a, b, nth_set_bit(eA, x / nEB), nth_set_bit(eB, x % nEB), f0); });
     group(1, nB * nea, [&](uint32_t x, uint32_t k) { write(1, k, b, a, vtxB(x / nea), x % nea, f1); });
     group(2, nB * nfa, [&](uint32_t x, uint32_t k) { write(2, k, b, a, vtxB(x / nfa), x % nfa, f1); });
   }

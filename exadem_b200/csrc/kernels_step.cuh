@@ -404,6 +404,112 @@ __global__ void __launch_bounds__(PP_BLK, PP_MINB) k_contact_sphere_pp(ContactAr
   }
 }
 
+// Software-pipelined form of k_contact_sphere_pp (EDB_PP_PIPE: 1 = operands prefetched into L2, 2 = into L1): a warp DETECTS chunk
+// c+1 (compaction into the other entry buffer) and issues prefetches for the operands of its entries BEFORE it evaluates the law on
+// the entries of chunk c, so that the seven scattered sectors of a law entry have a whole detect + law phase to arrive instead of
+// being waited for at full DRAM latency by the first instruction that needs them.  Same arithmetic, same record order per warp.
+#ifndef EDB_PP_PIPE
+#define EDB_PP_PIPE 0
+#endif
+template <int LAW>
+__global__ void __launch_bounds__(PP_BLK, PP_MINB) k_contact_sphere_pp_pipe(ContactArgs A, uint32_t* __restrict__ queue) {
+  if (gated(A.gate)) return;
+  if (A.zero_flag && blockIdx.x == 0 && threadIdx.x == 0) *A.zero_flag = 0;
+  __shared__ uint4 s_ent[PP_BLK / 32][2][CHUNK];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t nchunk = (A.w.n + CHUNK - 1) / CHUNK;
+  const uint32_t nwarp = gridDim.x * (PP_BLK / 32);
+  // detect one chunk into `ents`; returns the number of entries (warp-uniform); prefetches their operands
+  auto detect = [&](uint32_t chunk, uint4* ents) -> uint32_t {
+    const uint32_t k0 = chunk * CHUNK + lane * 4;
+    uint2 ij[4];
+    uint32_t f4 = 0;
+    if (k0 + 4 <= A.w.n) {
+      const uint4 a = reinterpret_cast<const uint4*>(A.w.ij + k0)[0], b = reinterpret_cast<const uint4*>(A.w.ij + k0)[1];
+      f4 = *reinterpret_cast<const uint32_t*>(A.w.flg + k0);
+      ij[0] = make_uint2(a.x, a.y); ij[1] = make_uint2(a.z, a.w); ij[2] = make_uint2(b.x, b.y); ij[3] = make_uint2(b.z, b.w);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        ij[u] = make_uint2(0, 0);
+        if (k0 + u < A.w.n) {
+          ij[u] = A.w.ij[k0 + u];
+          f4 |= (uint32_t)A.w.flg[k0 + u] << (8 * u);
+        }
+      }
+    }
+    bool need[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) need[u] = (f4 >> (8 * u)) & FLG_HOT;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (!need[u] && k0 + u < A.w.n) need[u] = detect_need<LAW>(A, ij[u], 0ull);
+    uint32_t c = 0;
+#pragma unroll
+    for (int u = 0; u < 4; u++) c += need[u] ? 1u : 0u;
+    const uint32_t inc = warp_incl_scan(c);
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t pos = inc - c;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+      if (need[u]) {
+        ents[pos++] = make_uint4(k0 + u, ij[u].x, ij[u].y, (f4 >> (8 * u)) & 0xffu);
+        const bool rem = ij[u].y >= A.rem_lo;
+        if (EDB_PP_PIPE == 2) {
+          prefetch_l1(A.P.pr + ij[u].x); prefetch_l1((rem ? A.g_pr : A.P.pr) + ij[u].y); prefetch_l1(A.P.wg + ij[u].x);
+          prefetch_l1((rem ? A.g_wg : A.P.wg) + ij[u].y); prefetch_l1(A.P.vm + ij[u].x); prefetch_l1((rem ? A.g_vm : A.P.vm) + ij[u].y);
+          prefetch_l1(A.w.ft + k0 + u);
+        } else {
+          prefetch_l2(A.P.pr + ij[u].x); prefetch_l2((rem ? A.g_pr : A.P.pr) + ij[u].y); prefetch_l2(A.P.wg + ij[u].x);
+          prefetch_l2((rem ? A.g_wg : A.P.wg) + ij[u].y); prefetch_l2(A.P.vm + ij[u].x); prefetch_l2((rem ? A.g_vm : A.P.vm) + ij[u].y);
+          prefetch_l2(A.w.ft + k0 + u);
+        }
+      }
+    __syncwarp();
+    return total;
+  };
+  auto law = [&](const uint4* ents, uint32_t total) {
+    for (uint32_t i = lane; i < total; i += 32) {
+      const uint4 e = ents[i];
+      const uint32_t k = e.x;
+      const uint8_t fl = (uint8_t)e.w;
+      const bool remj = e.z >= A.rem_lo;
+      const double4 pi = ldg4(A.P.pr + e.y), pj = ldg4((remj ? A.g_pr : A.P.pr) + e.z);
+      const double4 wi = ldg4(A.P.wg + e.y), wj = ldg4((remj ? A.g_wg : A.P.wg) + e.z);
+      const double4 vi = ldg4(A.P.vm + e.y), vj = ldg4((remj ? A.g_vm : A.P.vm) + e.z);
+      Hist H;
+      H.ft = ld4(A.w.ft + k);
+      H.mo = (fl & FLG_MOM) ? ld4(A.w.mo + k) : make_double4(0, 0, 0, 0);
+      const v3 ri = mk3(pi.x, pi.y, pi.z), rj = mk3(pj.x, pj.y, pj.z);
+      const Contact ct = detect_vv(ri, pi.w, rj, pj.w);
+      const Params& cp = cp_pp(A.prm, group_of(wi), group_of(wj));
+      bool contact = ct.hit;
+      if (LAW == LAW_COHESIVE) contact = contact || ct.dn <= cp.dncut;
+      const double meff = (vi.w * vj.w) / (vi.w + vj.w);
+      const double reff = (pi.w * pj.w) / (pi.w + pj.w);
+      finish_record<LAW>(A, k, fl, contact, ct, cp, meff, reff, ri, mk3(vi.x, vi.y, vi.z), mk3(wi.x, wi.y, wi.z), rj,
+                         mk3(vj.x, vj.y, vj.z), mk3(wj.x, wj.y, wj.z), H);
+    }
+    __syncwarp();
+  };
+  uint32_t cur = blockIdx.x * (PP_BLK / 32) + wid;
+  if (cur >= nchunk) return;
+  int buf = 0;
+  uint32_t tot_cur = detect(cur, s_ent[wid][0]);
+  for (;;) {
+    uint32_t nxt = 0;
+    if (lane == 0) nxt = atomicAdd(queue, 1u);
+    nxt = nwarp + __shfl_sync(0xffffffffu, nxt, 0);
+    uint32_t tot_nxt = 0;
+    const bool have_next = nxt < nchunk;
+    if (have_next) tot_nxt = detect(nxt, s_ent[wid][buf ^ 1]);
+    law(s_ent[wid][buf], tot_cur);
+    if (!have_next) break;
+    buf ^= 1;
+    tot_cur = tot_nxt;
+  }
+}
+
 // detection of a driver record (waves 4,5,6): sphere::ContactLawDriverFunc (contact_sphere.hpp:232-296),
 // polyhedron::ContactLawDriverFunc (polyhedron/contact.hpp:237-303)
 template <bool POLY>
