@@ -216,6 +216,25 @@ def link_bandwidth(nbytes=128 << 20, reps=3):
             b.synchronize()
             best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
         out[name] = best
+    # both directions at once (what the e2e loop does: the upload of step n+1 runs beside the download of step n)
+    h2 = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d2 = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+    best = 0.0
+    for _ in range(reps + 1):
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(s_up):
+            for _k in range(2):
+                d2.copy_(h2, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            a.record()
+            h.copy_(d, non_blocking=True)
+            b.record()
+        b.synchronize()
+        torch.cuda.synchronize()
+        best = max(best, nbytes / (a.elapsed_time(b) * 1e-3) / 1e9)
+    out["d2h_gbs_while_h2d"] = best
     return out
 
 
@@ -448,7 +467,8 @@ def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=150, warmup
                          "algorithmic_bytes_per_launch": alg, "frac_algorithmic": alg / t / 1e9 / peak if t > 0 else None,
                          "algorithmic_note": "SURVEY 8(d): 184 B/record + 8 (sub) + 24 k vertex bytes (k = 2 V-V, 3 V-E, 1+n_face V-F, 4 E-E) + 92 B/particle per wave",
                          "mean_launch_ms": t * 1e3,
-                         "note": "the detection pass is fp64-arithmetic bound (V-E / V-F / E-E closest-point tests on ~95 % records that do not touch), not HBM-bound"},
+                         "note": "ncu (profiles/r2_ncu_polystep.txt): the detection pass is bound by its scattered vertex gathers (fp64 pipe 10 %, "
+                                 "long-scoreboard 27 per issue), ~95 % of the records are candidates that do not touch"},
             "per_step_ms": {"contact_all": c.contact_ms / steps, "gather_fused": c.gather_ms / steps, "ghost": c.ghost_ms / steps,
                             "rebuild_amortised": c.rebuild_ms / steps}}
 
@@ -582,7 +602,8 @@ def main():
         link = link_bandwidth() if rank == 0 else {}
         e2e = {"value": iu_e / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ke,
                "ms_per_step": 1e3 * dt / ke, "link": link,
-               "floor_ms_per_step": (1e3 * (d2h / world) / (link["d2h_gbs"] * 1e9)) if link.get("d2h_gbs") else None,
+               "floor_ms_per_step": (1e3 * (d2h / world) / (link["d2h_gbs_while_h2d"] * 1e9)) if link.get("d2h_gbs_while_h2d") else None,
+               "floor": "d2h bytes per rank / measured device-to-host bandwidth while a host-to-device copy runs beside it (the two copies of consecutive steps overlap)",
                "what": "edb_upload_dynamic_async (r, v, vrot, orient from pinned host memory) -> edb_run_verlet(1 step) -> "
                        "edb_download_dynamic_async (r, v, vrot, orient, f, mom, arot to pinned host memory), every step, all ranks; "
                        "PCIe floor = d2h bytes / link bandwidth (the copies of consecutive steps overlap, the download is the longer leg)"}

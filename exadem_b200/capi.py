@@ -134,6 +134,14 @@ class Shape(C.Structure):
                 ("obb", C.c_double * 15), ("radius", C.c_double)]
 
 
+class Region(C.Structure):
+    _fields_ = [("lo", C.c_double * 3), ("hi", C.c_double * 3), ("quadric", C.c_double * 16), ("id_start", C.c_uint64), ("id_end", C.c_uint64),
+                ("use_bounds", C.c_int32), ("use_ids", C.c_int32), ("use_quadric", C.c_int32), ("pad", C.c_int32)]
+
+
+CSG_AND, CSG_OR, CSG_NOT = -1, -2, -3
+
+
 class Interaction(C.Structure):
     _fields_ = [("id_i", C.c_uint64), ("cell_i", C.c_uint32), ("p_i", C.c_uint16), ("pad_i", C.c_uint16),
                 ("sub_i", C.c_uint32), ("pad_i2", C.c_uint32),
@@ -531,6 +539,35 @@ class Engine:
 
     def freeze_particles(self):
         self._call("freeze_particles")
+
+    def set_particle_regions(self, regions):
+        """regions: list of dicts with optional keys bounds=(lo, hi), ids=(start, end), quadric=4x4 (row-major)"""
+        arr = (Region * max(len(regions), 1))()
+        for i, r in enumerate(regions):
+            R = arr[i]
+            if "bounds" in r:
+                R.use_bounds = 1
+                for k in range(3):
+                    R.lo[k], R.hi[k] = float(r["bounds"][0][k]), float(r["bounds"][1][k])
+            if "ids" in r:
+                R.use_ids = 1
+                R.id_start, R.id_end = int(r["ids"][0]), int(r["ids"][1])
+            if "quadric" in r:
+                R.use_quadric = 1
+                q = np.asarray(r["quadric"], dtype=np.float64).reshape(16)
+                for k in range(16):
+                    R.quadric[k] = float(q[k])
+        self._call("set_particle_regions", C.c_int32(len(regions)), arr)
+
+    def _expr(self, expr):
+        e = (C.c_int32 * max(len(expr), 1))(*expr)
+        return C.c_int32(len(expr)), e
+
+    def reset_force_moment_region(self, expr):
+        self._call("reset_force_moment_region", *self._expr(expr))
+
+    def freeze_particles_region(self, expr):
+        self._call("freeze_particles_region", *self._expr(expr))
 
     def displ_over(self, threshold) -> int:
         n = C.c_uint64()

@@ -51,6 +51,9 @@ struct edb_context {
   DevBuf<uint32_t> cidx, cidx2, ccount, cstart, cfill, tmp, new2old, old2new, cbeg, cend;
   DevBuf<uint32_t> scan_bsum, scan_total;
   DevBuf<double4> pr_backup, q_backup, vert;
+  DevBuf<RegionDev> d_regions;       // particle regions of the `region` slots (edb_set_particle_regions)
+  int n_regions = 0;
+  DevBuf<uint16_t> ptype;            // polyhedra: shape index per slot (reals + ghosts), refreshed with the world vertices
   bool have_backup = false;
   // ghost table (host-built, static for a given grid)
   uint32_t n_gent = 0;
@@ -1057,7 +1060,8 @@ static void compute_vertices(edb_context* c, bool ghosts_only = false) {
   if (c->S.nvmax <= 0) throw StateError{EDB_ERR_STATE, "polyhedron mode needs edb_set_shapes"};
   c->vert.ensure((size_t)ntot * c->S.nvmax + 1, true, c->st);
   const uint32_t first = ghosts_only ? c->nreal : 0;
-  LAUNCH(c, k_compute_vertices, nblk(ntot - first), BLK, 0, view(c->pa), first, ntot, c->S, c->vert.p);
+  c->ptype.ensure((size_t)ntot + 1, true, c->st);
+  LAUNCH(c, k_compute_vertices, nblk(ntot - first), BLK, 0, view(c->pa), first, ntot, c->S, c->vert.p, c->ptype.p);
 }
 
 // Multi-GPU: particles that left the brick move to their new owner together with their active interaction records.
@@ -1643,6 +1647,52 @@ extern "C" int edb_push_to_angular_acceleration(edb_context* c) {
   LAUNCH(c, k_epilog<0>, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, 0.0);
   API_END(c)
 }
+extern "C" int edb_set_particle_regions(edb_context* c, int32_t n, const edb_region* r) {
+  API_BEGIN(c)
+  if (n < 0 || (n > 0 && !r)) throw StateError{EDB_ERR_INVALID, "edb_set_particle_regions: bad region table"};
+  quiesce(c);
+  std::vector<RegionDev> h((size_t)n);
+  for (int i = 0; i < n; i++) {
+    RegionDev& d = h[i];
+    for (int k = 0; k < 3; k++) { d.lo[k] = r[i].lo[k]; d.hi[k] = r[i].hi[k]; }
+    for (int k = 0; k < 16; k++) d.Q[k] = r[i].quadric[k];
+    d.id0 = r[i].id_start; d.id1 = r[i].id_end;
+    d.use_bounds = r[i].use_bounds; d.use_ids = r[i].use_ids; d.use_quadric = r[i].use_quadric; d.pad = 0;
+  }
+  c->d_regions.ensure((size_t)n + 1);
+  if (n) CK(cudaMemcpy(c->d_regions.p, h.data(), (size_t)n * sizeof(RegionDev), cudaMemcpyHostToDevice));
+  c->n_regions = n;
+  API_END(c)
+}
+static RegionExpr region_expr(edb_context* c, int32_t n_expr, const int32_t* expr) {
+  if (n_expr < 0 || n_expr > EDB_CSG_MAX || (n_expr > 0 && !expr)) throw StateError{EDB_ERR_INVALID, "region expression: 0..EDB_CSG_MAX tokens"};
+  RegionExpr E{};
+  E.reg = c->d_regions.p;
+  E.n = n_expr;
+  int sp = 0;
+  for (int q = 0; q < n_expr; q++) {
+    const int t = expr[q];
+    if (t >= 0) { if (t >= c->n_regions) throw StateError{EDB_ERR_INVALID, "region expression names a region that was not set"}; sp++; }
+    else if (t == EDB_CSG_NOT) { if (sp < 1) throw StateError{EDB_ERR_INVALID, "malformed region expression"}; }
+    else if (t == EDB_CSG_AND || t == EDB_CSG_OR) { if (sp < 2) throw StateError{EDB_ERR_INVALID, "malformed region expression"}; sp--; }
+    else throw StateError{EDB_ERR_INVALID, "unknown token in region expression"};
+    E.tok[q] = t;
+  }
+  if (n_expr && sp != 1) throw StateError{EDB_ERR_INVALID, "malformed region expression"};
+  return E;
+}
+extern "C" int edb_reset_force_moment_region(edb_context* c, int32_t n_expr, const int32_t* expr) {
+  API_BEGIN(c)
+  const RegionExpr E = region_expr(c, n_expr, expr);
+  LAUNCH(c, k_region_set<false>, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, E);
+  API_END(c)
+}
+extern "C" int edb_freeze_particles_region(edb_context* c, int32_t n_expr, const int32_t* expr) {
+  API_BEGIN(c)
+  const RegionExpr E = region_expr(c, n_expr, expr);
+  LAUNCH(c, k_region_set<true>, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal, E);
+  API_END(c)
+}
 extern "C" int edb_freeze_particles(edb_context* c) {
   API_BEGIN(c)
   LAUNCH(c, k_freeze, nblk(c->nreal), BLK, 0, view(c->pa), c->nreal);
@@ -1654,7 +1704,7 @@ template <int LAW>
 static void launch_contact_waves(edb_context* c, double dt, const unsigned long long* gate, unsigned long long* zero_flag) {
   const bool poly = c->poly();
   ContactArgs A{view(c->pa), WView{}, c->prm, c->drv.p, c->vert.p, c->S, dt, 0, c->symetric, c->M, gate, zero_flag,
-                nullptr, nullptr, nullptr, 0xffffffffu};
+                nullptr, nullptr, nullptr, 0xffffffffu, c->ptype.p};
   if (c->ghost_in_landing) {   // spheres on several GPUs, inside edb_run_verlet: remote ghosts are read from the landing zone
     const uint32_t lo = c->nreal + c->comm.n_local_ghost;
     const double4* land = c->comm.landing_of(c->ghost_in_landing);

@@ -161,17 +161,79 @@ __global__ void k_freeze(PView P, uint32_t n) {  // freeze_particles.cu:33-88 (w
   v.x = v.y = v.z = 0; w.x = w.y = w.z = 0;
   P.vm[p] = v; P.wg[p] = w;
 }
+// particle regions (exanb ParticleRegion / ParticleRegionCSG; the `region` slot of reset_force_moment.cu:36-57, freeze_particles.cu:47-66)
+struct RegionDev {
+  double lo[3], hi[3], Q[16];
+  unsigned long long id0, id1;
+  int use_bounds, use_ids, use_quadric, pad;
+};
+struct RegionExpr {
+  const RegionDev* reg;
+  int n;
+  int tok[EDB_CSG_MAX];
+};
+__device__ __forceinline__ bool in_region(const RegionDev& R, double x, double y, double z, unsigned long long id) {
+  if (R.use_bounds && !(x >= R.lo[0] && x < R.hi[0] && y >= R.lo[1] && y < R.hi[1] && z >= R.lo[2] && z < R.hi[2])) return false;
+  if (R.use_ids && !(id >= R.id0 && id < R.id1)) return false;
+  if (R.use_quadric) {
+    const double v[4] = {x, y, z, 1.0};
+    double s = 0.0;
+    for (int i = 0; i < 4; i++) {
+      double t = 0.0;
+      for (int j = 0; j < 4; j++) t += R.Q[4 * i + j] * v[j];
+      s += v[i] * t;
+    }
+    if (!(s <= 0.0)) return false;
+  }
+  return true;
+}
+__device__ __forceinline__ bool csg_contains(const RegionExpr& E, double x, double y, double z, unsigned long long id) {
+  if (E.n == 0) return true;
+  unsigned int stack = 0;   // bit k = k-th entry from the bottom
+  int sp = 0;
+  for (int q = 0; q < E.n; q++) {
+    const int t = E.tok[q];
+    if (t >= 0) { stack = (stack & ~(1u << sp)) | ((in_region(E.reg[t], x, y, z, id) ? 1u : 0u) << sp); sp++; }
+    else if (t == EDB_CSG_NOT) { stack ^= 1u << (sp - 1); }
+    else {
+      const unsigned a = (stack >> (sp - 2)) & 1u, b = (stack >> (sp - 1)) & 1u;
+      const unsigned r = t == EDB_CSG_AND ? (a & b) : (a | b);
+      sp--;
+      stack = (stack & ~(1u << (sp - 1))) | (r << (sp - 1));
+    }
+  }
+  return stack & 1u;
+}
+template <bool FREEZE>
+__global__ void k_region_set(PView P, uint32_t n, RegionExpr E) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double4 r = P.pr[p];
+  if (!csg_contains(E, r.x, r.y, r.z, P.id[p])) return;
+  P.fx[p] = 0; P.fy[p] = 0; P.fz[p] = 0; P.mx[p] = 0; P.my[p] = 0; P.mz[p] = 0;
+  if (FREEZE) {
+    double4 v = P.vm[p], w = P.wg[p];
+    v.x = v.y = v.z = 0; w.x = w.y = w.z = 0;
+    P.vm[p] = v; P.wg[p] = w;
+  }
+}
 // compute_vertices.hpp:26-67: world vertex k of particle p = r + Q*(h*v_k)  (shape.hpp:259-262)
-__global__ void k_compute_vertices(PView P, uint32_t first, uint32_t n, ShapesView S, double4* __restrict__ vert) {
+// The 4th component of every world vertex carries the particle's Minkowski radius h * shape.radius, and ptype[p] the shape index: the
+// detection pass of the polyhedron contact operator then needs no particle sector at all (it fetched wg and homothety of both
+// particles of every record for these two numbers: 128 B of sectors per record, profiles/r2_ncu_polystep.txt).
+__global__ void k_compute_vertices(PView P, uint32_t first, uint32_t n, ShapesView S, double4* __restrict__ vert, uint16_t* __restrict__ ptype) {
   const uint32_t p = first + blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const double4 r = P.pr[p], Q = P.q[p];
-  const ShapeDev sh = S.sh[type_of(P.wg[p])];
+  const uint32_t ty = type_of(P.wg[p]);
+  const ShapeDev sh = S.sh[ty];
   const double h = P.h[p];
+  const double rm = h * sh.radius;
   const q4 q{Q.x, Q.y, Q.z, Q.w};
+  if (ptype) ptype[p] = (uint16_t)ty;
   for (int k = 0; k < sh.nv; k++) {
     const v3 w = mk3(r.x, r.y, r.z) + qrot(q, h * S.verts[sh.v0 + k]);
-    vert[(size_t)p * S.nvmax + k] = make_double4(w.x, w.y, w.z, 0.0);
+    vert[(size_t)p * S.nvmax + k] = make_double4(w.x, w.y, w.z, rm);
   }
 }
 // particle_displ_over / vertex_displ_over (backup_dem.hpp:66-100): count of particles (vertices) with |d|^2 >= thr^2
@@ -226,6 +288,7 @@ struct ContactArgs {
   // ghosts; g_pr / g_vm / g_wg are already offset by -rem_lo.  rem_lo = 0xffffffff: everything is read from the particle arrays.
   const double4 *g_pr, *g_vm, *g_wg;
   uint32_t rem_lo;
+  const uint16_t* ptype;   // polyhedra: shape index per slot (k_compute_vertices)
 };
 __device__ __forceinline__ bool gated(const unsigned long long* gate) { return gate && *gate; }
 
@@ -623,13 +686,17 @@ __global__ void __launch_bounds__(BLK, 4) k_detect_poly_pp(ContactArgs A, PolyWa
     const uint8_t fl = w.flg[k];
     if (fl & FLG_HOT) { need[u] = true; continue; }
     const uint2 ij = w.ij[k], sb = w.sub[k];
-    const double4 wi = ldg4(A.P.wg + ij.x), wj = ldg4(A.P.wg + ij.y);
-    const ShapeDev& si = A.S.sh[type_of(wi)];
-    const ShapeDev& sj = A.S.sh[type_of(wj)];
-    const double rmi = A.P.h[ij.x] * si.radius, rmj = A.P.h[ij.y] * sj.radius;
+    // shape index from the compact table, Minkowski radius from the 4th component of the first world vertex: no particle sector
+    const ShapeDev& si = A.S.sh[A.ptype[ij.x]];
+    const ShapeDev& sj = A.S.sh[A.ptype[ij.y]];
+    const double rmi = ldg4(A.vert + (size_t)ij.x * A.S.nvmax).w, rmj = ldg4(A.vert + (size_t)ij.y * A.S.nvmax).w;
     const Contact c = detect_poly_record(A, t, ij, sb, si, sj, rmi, rmj);
     need[u] = c.hit;
-    if (LAW == LAW_COHESIVE) need[u] = need[u] || c.dn <= cp_pp(A.prm, group_of(wi), group_of(wj)).dncut;
+    if (LAW == LAW_COHESIVE) {
+      double dncut = A.prm.pp.dncut;
+      if (A.prm.tpp) dncut = cp_pp(A.prm, group_of(ldg4(A.P.wg + ij.x)), group_of(ldg4(A.P.wg + ij.y))).dncut;
+      need[u] = need[u] || c.dn <= dncut;
+    }
   }
   uint32_t c = 0;
 #pragma unroll
@@ -1023,7 +1090,7 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
     for (int k = 0; k < nv; k++) {
       const v3 lv = h * A.S.verts[v0 + k];
       const v3 vn = mk3(rn.x, rn.y, rn.z) + qrot(qn, lv);
-      A.vert[(size_t)p * A.S.nvmax + k] = make_double4(vn.x, vn.y, vn.z, 0.0);
+      A.vert[(size_t)p * A.S.nvmax + k] = make_double4(vn.x, vn.y, vn.z, h * sh.radius);
       if (trig) {
         const v3 vo = mk3(rb.x, rb.y, rb.z) + qrot(qb, lv);
         const v3 d = vn - vo;

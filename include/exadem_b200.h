@@ -230,6 +230,25 @@ int edb_push_to_quaternion(edb_context*, double dt);         /* [push_to_quatern
 int edb_push_to_angular_velocity(edb_context*, double dt);   /* [push_to_angular_velocity] */
 int edb_push_to_angular_acceleration(edb_context*);          /* [push_to_angular_acceleration] */
 int edb_freeze_particles(edb_context*);                      /* [freeze_particles] src/numericalscheme/freeze_particles.cu:33-88 (no region) */
+/* The `region` slot of reset_force_moment / freeze_particles (reset_force_moment.cu:36-57, freeze_particles.cu:47-66): exaNBody's
+   ParticleRegions + ParticleRegionCSG.  A region is the conjunction of an axis-aligned box (lo <= r < hi), an id range
+   [id_start, id_end) and a quadric  (x y z 1) Q (x y z 1)^T <= 0  (row-major 4x4), each optional; a CSG expression over the regions is
+   given in reverse Polish notation: a token k >= 0 pushes "the particle is inside region k", EDB_CSG_AND / EDB_CSG_OR / EDB_CSG_NOT
+   combine the top of the stack (the form exaNBody's build_from_expression_string compiles `region: A and not B` into).
+   Parity unpinned: exaNBody's sources are not in the reference tree; restated from the operators' call sites and documentation. */
+typedef struct edb_region {
+  double lo[3], hi[3];
+  double quadric[16];
+  uint64_t id_start, id_end;
+  int32_t use_bounds, use_ids, use_quadric, pad;
+} edb_region;
+#define EDB_CSG_AND (-1)
+#define EDB_CSG_OR (-2)
+#define EDB_CSG_NOT (-3)
+#define EDB_CSG_MAX 32
+int edb_set_particle_regions(edb_context*, int32_t n, const edb_region* regions);
+int edb_reset_force_moment_region(edb_context*, int32_t n_expr, const int32_t* expr);   /* f = mom = 0 for the particles inside */
+int edb_freeze_particles_region(edb_context*, int32_t n_expr, const int32_t* expr);     /* f = mom = v = vrot = 0 for the particles inside */
 /* [particle_displ_over | vertex_displ_over] rebuild trigger: *over = #particles (vertices) moved >= threshold since
  * the last edb_update_particle_neighbors (which takes the backup, backup_dem.cpp:40-80); all-reduced over ranks. */
 int edb_displ_over(edb_context*, double threshold, uint64_t* over);

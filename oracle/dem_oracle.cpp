@@ -117,6 +117,7 @@ struct Sim {
   std::vector<q4> q;
   std::vector<double> mass, h, radius;
   std::vector<uint64_t> id;
+  std::vector<edb_region> regions;   // particle regions of the `region` slots
   std::vector<uint32_t> type, group;
   std::vector<uint32_t> gsrc;
   std::vector<v3> gshift;
@@ -951,6 +952,51 @@ int orc_push_to_angular_acceleration(orc_sim* h) { angular_accel(*(Sim*)h); retu
 int orc_freeze_particles(orc_sim* h) {
   Sim& s = *(Sim*)h;
   for (size_t p = 0; p < s.nreal; p++) { s.f[p] = {0, 0, 0}; s.mom[p] = {0, 0, 0}; s.v[p] = {0, 0, 0}; s.w[p] = {0, 0, 0}; }
+  return 0;
+}
+// the `region` slot of reset_force_moment / freeze_particles (reset_force_moment.cu:36-57, freeze_particles.cu:47-66): exaNBody's
+// ParticleRegion::contains (box, id range, quadric) under a ParticleRegionCSG expression, here in reverse Polish notation
+static bool orc_in_region(const edb_region& R, const v3& r, uint64_t id) {
+  if (R.use_bounds && !(r.x >= R.lo[0] && r.x < R.hi[0] && r.y >= R.lo[1] && r.y < R.hi[1] && r.z >= R.lo[2] && r.z < R.hi[2])) return false;
+  if (R.use_ids && !(id >= R.id_start && id < R.id_end)) return false;
+  if (R.use_quadric) {
+    const double v[4] = {r.x, r.y, r.z, 1.0};
+    double s = 0.0;
+    for (int i = 0; i < 4; i++) {
+      double t = 0.0;
+      for (int j = 0; j < 4; j++) t += R.quadric[4 * i + j] * v[j];
+      s += v[i] * t;
+    }
+    if (!(s <= 0.0)) return false;
+  }
+  return true;
+}
+static bool orc_csg(const Sim& s, int n, const int32_t* tok, const v3& r, uint64_t id) {
+  if (n == 0) return true;
+  std::vector<bool> st;
+  for (int q = 0; q < n; q++) {
+    const int t = tok[q];
+    if (t >= 0) st.push_back(orc_in_region(s.regions[t], r, id));
+    else if (t == EDB_CSG_NOT) st.back() = !st.back();
+    else { const bool b = st.back(); st.pop_back(); const bool a = st.back(); st.back() = t == EDB_CSG_AND ? (a && b) : (a || b); }
+  }
+  return st.back();
+}
+int orc_set_particle_regions(orc_sim* h, int32_t n, const edb_region* r) {
+  Sim& s = *(Sim*)h;
+  s.regions.assign(r, r + n);
+  return 0;
+}
+int orc_reset_force_moment_region(orc_sim* h, int32_t n, const int32_t* tok) {
+  Sim& s = *(Sim*)h;
+  for (size_t p = 0; p < s.nreal; p++)
+    if (orc_csg(s, n, tok, s.r[p], s.id[p])) { s.f[p] = {0, 0, 0}; s.mom[p] = {0, 0, 0}; }
+  return 0;
+}
+int orc_freeze_particles_region(orc_sim* h, int32_t n, const int32_t* tok) {
+  Sim& s = *(Sim*)h;
+  for (size_t p = 0; p < s.nreal; p++)
+    if (orc_csg(s, n, tok, s.r[p], s.id[p])) { s.f[p] = {0, 0, 0}; s.mom[p] = {0, 0, 0}; s.v[p] = {0, 0, 0}; s.w[p] = {0, 0, 0}; }
   return 0;
 }
 int orc_displ_over(orc_sim* h, double thr, uint64_t* over) { *over = displ_over(*(Sim*)h, thr); return 0; }
