@@ -77,9 +77,12 @@ class ClockSampler:
         self.device = device
 
     def start(self):
+        # (samples go to a file: a pipe nobody reads fills up after a few thousand lines and stalls nvidia-smi during long set-ups)
+        import tempfile
         try:
+            self.out = tempfile.NamedTemporaryFile("w+", prefix="edb_clocks_", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "10",
-                                       "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-i", str(self.device)], stdout=self.out, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
@@ -98,9 +101,16 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
         try:
-            out, _ = self.p.communicate(timeout=5)
+            self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
+        try:
+            self.out.flush()
+            self.out.seek(0)
+            out = self.out.read()
+            self.out.close()
+            os.unlink(self.out.name)
+        except Exception:
             out = ""
         sm, mx, reasons = [], [], set()
         for line in out.splitlines():

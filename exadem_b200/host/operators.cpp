@@ -253,10 +253,32 @@ class DriverDisplacementOver : public OperatorNode {
     std::string documentation() const final { return doc; }               \
     void execute() final { ck(*grid, call(grid->ctx, *dt), #Class); }     \
   }
-EDB_SIMPLE_OP(ResetForceMomentNode, edb_reset_force_moment, "reset_force_moment: f = 0, mom = 0 (src/numericalscheme/reset_force_moment.cu:33-73)");
+// reset_force_moment / freeze_particles with the reference's optional `particle_regions` + `region` slots (reset_force_moment.cu:36-57,
+// freeze_particles.cu:47-66).  ParticleRegions = the region table, ParticleRegionCSG = the expression over it, here already compiled to
+// reverse Polish notation (what exaNBody's build_from_expression_string produces from `region: A and not B`).
+using ParticleRegions = std::vector<edb_region>;
+using ParticleRegionCSG = std::vector<int32_t>;
+#define EDB_REGION_OP(Class, call, call_region, doc)                                                        \
+  class Class : public OperatorNode {                                                                       \
+    ADD_SLOT(GridB200, grid, INPUT_OUTPUT, REQUIRED);                                                       \
+    ADD_SLOT(ParticleRegions, particle_regions, INPUT, OPTIONAL);                                           \
+    ADD_SLOT(ParticleRegionCSG, region, INPUT, OPTIONAL);                                                   \
+   public:                                                                                                  \
+    std::string documentation() const final { return doc; }                                                 \
+    void execute() final {                                                                                  \
+      if (!region.has_value()) { ck(*grid, call(grid->ctx), #Class); return; }                              \
+      if (!particle_regions.has_value())                                                                    \
+        throw std::runtime_error(#Class ": Region is defined, but particle_regions has no value");          \
+      ck(*grid, edb_set_particle_regions(grid->ctx, (int32_t)particle_regions->size(), particle_regions->data()), #Class); \
+      ck(*grid, call_region(grid->ctx, (int32_t)region->size(), region->data()), #Class);                   \
+    }                                                                                                       \
+  }
+EDB_REGION_OP(ResetForceMomentNode, edb_reset_force_moment, edb_reset_force_moment_region,
+              "reset_force_moment: f = 0, mom = 0, optionally inside a region (src/numericalscheme/reset_force_moment.cu:33-73)");
 EDB_SIMPLE_OP(ForceToAccel, edb_force_to_accel, "force_to_accel: f /= m (src/numericalscheme/force_to_accel.cu:32-53)");
 EDB_SIMPLE_OP(PushToAngularAcceleration, edb_push_to_angular_acceleration, "push_to_angular_acceleration (src/numericalscheme/push_to_angular_acceleration.cu)");
-EDB_SIMPLE_OP(FreezeParticles, edb_freeze_particles, "freeze_particles / pas_libere_pas_delivre (src/numericalscheme/freeze_particles.cu:33-88)");
+EDB_REGION_OP(FreezeParticles, edb_freeze_particles, edb_freeze_particles_region,
+              "freeze_particles / pas_libere_pas_delivre, optionally inside a region (src/numericalscheme/freeze_particles.cu:33-88)");
 EDB_SIMPLE_OP(PolyhedraComputeVertices, edb_compute_vertices, "compute_vertices (src/polyhedron/compute_vertices.cu:34-109)");
 EDB_SIMPLE_OP(UpdateGhostsRQ, edb_ghost_update_rq, "ghost_update_rq (src/grid/update_ghosts.cu:46-63)");
 EDB_DT_OP(CombinedComputeProlog, edb_combined_compute_prolog, "combined_compute_prolog (src/numericalscheme/combined_compute_prolog.cu:81-117)");
