@@ -131,6 +131,7 @@ struct ShapeDev {
   int v0, e0, f0, fi0;  // offsets into the pooled arrays (vertices, edges(pairs), face table, face indices)
   Obb obb;
   double radius;
+  double vmax;   // largest vertex norm (homothety 1): bound of the vertex displacement under a rotation
 };
 struct ShapesView {
   const ShapeDev* sh;

@@ -769,6 +769,8 @@ extern "C" int edb_set_shapes(edb_context* c, int32_t n, const edb_shape* sh) {
     const double* o = sh[i].obb;
     S.obb = Obb{mk3(o[0], o[1], o[2]), mk3(o[3], o[4], o[5]), mk3(o[6], o[7], o[8]), mk3(o[9], o[10], o[11]), mk3(o[12], o[13], o[14])};
     S.radius = sh[i].radius;
+    S.vmax = 0.0;
+    for (int k = 0; k < S.nv; k++) S.vmax = std::max(S.vmax, norm(sv[S.v0 + k]));
     nvmax = std::max(nvmax, S.nv);
     c->h_sh.push_back(S);
   }

@@ -1082,9 +1082,20 @@ __global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constan
     const ShapeDev& sh = A.S.sh[type_of(w)];
     const double h = A.P.h[p];
     const q4 qn{Q.x, Q.y, Q.z, Q.w};
-    const bool trig = A.next_flag && A.q_backup;
+    bool trig = A.next_flag && A.q_backup;
     double4 rb = make_double4(0, 0, 0, 0), Qb = make_double4(1, 0, 0, 0);
-    if (trig) { rb = ldg4(A.pr_backup + p); Qb = ldg4(A.q_backup + p); }
+    if (trig) {
+      rb = ldg4(A.pr_backup + p); Qb = ldg4(A.q_backup + p);
+      // Conservative early-out of vertex_displ_over: a vertex moved by at most |r - r_b| + 2 |sin(theta/2)| |lv|, theta the rotation
+      // between the backup and the current orientation (|vec(q q_b^-1)| = |sin(theta/2)|), |lv| <= h * vmax.  When that bound (with a
+      // 1e-9 relative margin, orders above the rounding of either side) is below the threshold no vertex can count, and the six
+      // backup-vertex rotations of the exact test are skipped; in a packing that is almost every particle on almost every step.
+      const v3 dr = mk3(rn.x, rn.y, rn.z) - mk3(rb.x, rb.y, rb.z);
+      const v3 un = mk3(Q.y, Q.z, Q.w), ub = mk3(Qb.y, Qb.z, Qb.w);
+      const v3 vq = Qb.x * un - Q.x * ub - cross(un, ub);
+      const double bound = (norm(dr) + 2.0 * norm(vq) * h * sh.vmax) * 1.000000001;
+      if (bound * bound < A.thr2) trig = false;
+    }
     const q4 qb{Qb.x, Qb.y, Qb.z, Qb.w};
     const int nv = sh.nv, v0 = sh.v0;
     for (int k = 0; k < nv; k++) {
