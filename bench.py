@@ -436,11 +436,16 @@ def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=150, warmup
     eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, warmup, 0)
     eng.sync()
     eng.reset_counters()
-    eng.set_timing(True)
+    eng.set_timing(False)                       # timed region without the per-kernel events (see Job.timed)
     eng.event_record(0)
     nreb = eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, steps, 0)
     eng.event_record(1)
     ms = eng.event_elapsed_ms(0, 1)
+    cv = eng.counters()
+    eng.reset_counters()
+    eng.set_timing(True)                        # second pass of the same length: per-kernel breakdown
+    nreb2 = eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, steps, 0)
+    eng.sync()
     c = eng.counters()
     counts, active = eng.interaction_counts()
     eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)
@@ -465,8 +470,8 @@ def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=150, warmup
     tp, cap = traffic_for(tr, "k_detect_poly_pp+k_law_poly_pp", "poly", steps, warmup)
     what = (f"{n_real} spheres + octahedra + cubes, cohesive law, closed mesh walls (configs[3])" if mixed
             else f"{n_real} octahedra, periodic packing (configs[2])")
-    return {"workload": what + (f", drifting at {DRIFT} (flowing state)" if not mixed else ", relaxing from the lattice (flowing state)"), "value": c.interaction_updates / (ms * 1e-3),
-            "unit": UNIT, "particle_steps_per_s": c.particle_steps / (ms * 1e-3), "steps": steps, "ms_per_step": ms / steps,
+    return {"workload": what + (f", drifting at {DRIFT} (flowing state)" if not mixed else ", relaxing from the lattice (flowing state)"), "value": cv.interaction_updates / (ms * 1e-3),
+            "unit": UNIT, "particle_steps_per_s": cv.particle_steps / (ms * 1e-3), "steps": steps, "ms_per_step": ms / steps,
             "interactions": int(counts.sum()), "active_interactions": int(active.sum()), "rebuilds_in_timed_region": int(nreb),
             "rebuild_once_ms": reb,
             "roofline": {"kernel": "k_detect_poly_pp + k_law_poly_pp (4 waves)", "bound": "hbm", "achieved": own / t / 1e9 if t > 0 else 0.0,
@@ -480,7 +485,8 @@ def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=150, warmup
                          "note": "ncu (profiles/r2_ncu_polystep.txt): the detection pass is bound by its scattered vertex gathers (fp64 pipe 10 %, "
                                  "long-scoreboard 27 per issue), ~95 % of the records are candidates that do not touch"},
             "per_step_ms": {"contact_all": c.contact_ms / steps, "gather_fused": c.gather_ms / steps, "ghost": c.ghost_ms / steps,
-                            "rebuild_amortised": c.rebuild_ms / steps}}
+                            "rebuild_amortised": c.rebuild_ms / steps, "rebuilds_in_this_pass": int(nreb2),
+                            "note": "second pass of the same number of steps with per-kernel CUDA events on"}}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -506,13 +512,16 @@ class Job:
 
     def timed(self, steps, warmup):
         """W warm-up steps, then EXACTLY `steps` steps bracketed by barrier + synchronize; CUDA events on the library stream.
-        -> (ms on this rank, counters, rebuilds, (wall t0, t1))"""
+        The per-kernel CUDA events of the library (edb_set_timing) cost ~0.015 ms per step (measured: 0.219 -> 0.234 ms on the 1 M
+        drum, scripts/timing_ab.py), so they stay OFF in the timed region; the per-kernel breakdown comes from a second pass of the
+        same number of steps right behind it (`self.breakdown`: counters of that pass, its ms, the interaction counts after it).
+        -> (ms on this rank, counters of the timed region, rebuilds, (wall t0, t1))"""
         wl, eng = self.wl, self.eng
         eng.update_particle_neighbors(wl.rcut_inc, wl.symetric)
         eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, max(warmup, 3), 0)
         self.barrier()
         eng.reset_counters()
-        eng.set_timing(True)
+        eng.set_timing(False)
         self.barrier()
         eng.event_record(0)
         w0 = time.time()
@@ -522,8 +531,26 @@ class Job:
         self.barrier()
         w1 = time.time()
         c = eng.counters()
+        # second pass: the same number of steps with the per-kernel events on
+        eng.reset_counters()
+        eng.set_timing(True)
+        self.barrier()
+        eng.event_record(2)
+        eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, wl.symetric, steps, 0)
+        eng.event_record(3)
+        ms2 = eng.event_elapsed_ms(2, 3)
+        self.barrier()
+        c2 = eng.counters()
         eng.set_timing(False)
+        counts, active = eng.interaction_counts()
+        self.breakdown = {"c": c2, "ms": ms2, "counts": counts, "active": active, "steps": steps}
         return ms, c, nreb, (w0, w1)
+
+    def per_step_ms(self):
+        b = self.breakdown
+        c, k = b["c"], b["steps"]
+        return {"contact_all": c.contact_ms / k, "gather_fused": c.gather_ms / k, "prolog": c.prolog_ms / k, "ghost": c.ghost_ms / k,
+                "rebuild_amortised": c.rebuild_ms / k, "step_with_kernel_events": b["ms"] / k}
 
 
 def reduce_stats(world, ms, c, nreb):
@@ -571,7 +598,8 @@ def main():
 
     ms, c, nreb, win = job.timed(args.steps, args.warmup)
     windows.append(win)
-    counts, active = eng.interaction_counts()
+    counts, active = job.breakdown["counts"], job.breakdown["active"]
+    cb, msb_pass = job.breakdown["c"], job.breakdown["ms"]     # per-kernel pass (events on), the steps right behind the timed region
     ms, iu, ps, launches, nreb_max = reduce_stats(world, ms, c, nreb)
     value = iu / (ms * 1e-3)
 
@@ -641,13 +669,13 @@ def main():
         bargs.workload = "box"
         _, bmake, bdesc, _ = resolve_workload(bargs, world)
         jb = Job(lib, bmake, rank, world, local)
-        msb, cb, nrb, winb = jb.timed(args.steps, args.warmup)
+        msb, cbx, nrb, winb = jb.timed(args.steps, args.warmup)
         windows.append(winb)
-        bcounts, bactive = jb.eng.interaction_counts()
-        msb, iub, psb, _, nrbm = reduce_stats(world, msb, cb, nrb)
+        bcounts, bactive = jb.breakdown["counts"], jb.breakdown["active"]
+        msb, iub, psb, _, nrbm = reduce_stats(world, msb, cbx, nrb)
         box = {"workload": bdesc, "particles_per_gpu": int(jb.wl.particles.n), "value": iub / (msb * 1e-3), "ms_per_step": msb / args.steps,
                "rebuilds_in_timed_region": int(nrbm), "interactions_per_gpu": int(bcounts.sum()), "active_interactions_per_gpu": int(bactive.sum()),
-               "per_step_ms": {"contact_all": cb.contact_ms / args.steps, "gather_fused": cb.gather_ms / args.steps, "ghost": cb.ghost_ms / args.steps}}
+               "per_step_ms": jb.per_step_ms()}
         jb.eng.close()
         dist.barrier()
         if rank == 0:
@@ -657,7 +685,7 @@ def main():
             box["single_gpu_same_brick"] = {"workload": "one brick of the same size alone on one GPU (periodic onto itself)",
                                             "particles": int(j1.wl.particles.n), "value": c1.interaction_updates / (ms1 * 1e-3),
                                             "ms_per_step": ms1 / args.steps, "rebuilds_in_timed_region": int(nreb1),
-                                            "per_step_ms": {"contact_all": c1.contact_ms / args.steps, "gather_fused": c1.gather_ms / args.steps}}
+                                            "per_step_ms": j1.per_step_ms()}
             j1.eng.close()
         dist.barrier()
 
@@ -670,7 +698,7 @@ def main():
             windows.append(win1)
             single = {"workload": "one brick of the same size alone on one GPU (periodic onto itself)", "particles": int(j1.wl.particles.n),
                       "value": c1.interaction_updates / (ms1 * 1e-3), "ms_per_step": ms1 / args.steps, "rebuilds_in_timed_region": int(nreb1),
-                      "per_step_ms": {"contact_all": c1.contact_ms / args.steps, "gather_fused": c1.gather_ms / args.steps}}
+                      "per_step_ms": j1.per_step_ms()}
             j1.eng.close()
         dist.barrier()
     if rank != 0:
@@ -678,23 +706,23 @@ def main():
     clocks = sampler.stop(windows)
     peak, peak_src = peaks()
     tr = load_traffic()
-    per_step = {"contact_all": c.contact_ms / args.steps, "gather_fused": c.gather_ms / args.steps, "prolog": c.prolog_ms / args.steps,
-                "ghost": c.ghost_ms / args.steps, "rebuild_amortised": c.rebuild_ms / args.steps}
+    per_step = job.per_step_ms()
+    per_step["note"] = ("second pass of the same number of steps with the library's per-kernel CUDA events on (they cost ~0.015 ms per step "
+                        "and are off in the timed region)")
     roof = roof_other = None
     if wl.mode == 0:
-        rf = sphere_rooflines(c, counts, active, n_real, ms, args.steps, peak, peak_src, tr, name, max(args.warmup, 3))
+        rf = sphere_rooflines(cb, counts, active, n_real, msb_pass, args.steps, peak, peak_src, tr, name, max(args.warmup, 3) + args.steps)
         # `roofline` = the kernel with the larger share of the step; the other one rides beside it under its own key
         keys = sorted(rf, key=lambda k: -(rf[k]["share_of_step"] or 0.0))
         roof = rf[keys[0]]
         roof_other = rf[keys[1]] if len(keys) > 1 else None
     else:
-        npp = max(c.contact_pp_launches, 1)
-        t = c.contact_pp_ms / npp * 1e-3
-        alg = c.bytes_contact_algorithmic / npp
+        t = cb.contact_pp_ms / args.steps * 1e-3
+        alg = cb.bytes_contact_algorithmic / args.steps
         roof = {"kernel": "k_detect_poly_pp + k_law_poly_pp", "bound": "hbm", "achieved": alg / t / 1e9 if t > 0 else 0.0, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": alg / t / 1e9 / peak if t > 0 else 0.0, "traffic": None,
                 "bytes_model": "SURVEY 8(d) algorithmic bytes incl. vertices", "mean_launch_ms": t * 1e3,
-                "share_of_step": c.contact_pp_ms / ms if ms > 0 else None}
+                "share_of_step": cb.contact_pp_ms / msb_pass if msb_pass > 0 else None}
     roof["per_step_ms"] = per_step
     roof["rebuild_once_ms"] = rebuild_once_ms
     poly = mixed = None
