@@ -467,7 +467,7 @@ def polyhedra_line(lib, peak, peak_src, device, tr, n=500_000, steps=150, warmup
     own = 17.0 * rec + (128.0 + 192.0 + 4.0) * hot + n_real * (32.0 * 6 + 64.0)
     # 184 B/record + 8 (sub) + 24 k of vertices (k = 2 V-V, 3 V-E, 1 + 3 V-F on triangles, 4 E-E) + 92 B/particle per wave
     alg = sum(float(counts[w]) * (192.0 + 24.0 * k) for w, k in ((0, 2), (1, 3), (2, 4), (3, 4))) + 4 * 92.0 * n_real
-    tp, cap = traffic_for(tr, "k_detect_poly_pp+k_law_poly_pp", "poly", steps, warmup)
+    tp, cap = traffic_for(tr, "k_detect_poly_pp+k_law_poly_pp", "poly", steps, warmup) if not mixed else (None, None)
     what = (f"{n_real} spheres + octahedra + cubes, cohesive law, closed mesh walls (configs[3])" if mixed
             else f"{n_real} octahedra, periodic packing (configs[2])")
     return {"workload": what + (f", drifting at {DRIFT} (flowing state)" if not mixed else ", relaxing from the lattice (flowing state)"), "value": cv.interaction_updates / (ms * 1e-3),
