@@ -1842,8 +1842,8 @@ static void gather(edb_context* c, const double* g, double dt, const unsigned lo
     c->comm.fan_begin(F, c->cfg.nranks > 1 && next_flag != nullptr && c->env_gather_mail);
     c->ghost_pushed = true;
   }
-  if (poly) LAUNCH(c, (k_gather<FUSE, true>), nblk(c->nreal), BLK, 0, A, F);
-  else LAUNCH(c, (k_gather<FUSE, false>), nblk(c->nreal), BLK, 0, A, F);
+  if (poly) LAUNCH(c, (k_gather<FUSE, true>), nblk(c->nreal, G_BLK), G_BLK, 0, A, F);
+  else LAUNCH(c, (k_gather<FUSE, false>), nblk(c->nreal, G_BLK), G_BLK, 0, A, F);
   c->ctr.gather_launches++;
 }
 

@@ -886,12 +886,16 @@ __device__ __forceinline__ void add_wrench(const double4& fd, const double4& cp,
 //         already hold the particle: one pass over the particle arrays per time step instead of three.  The intermediate
 //         acceleration / moment / angular acceleration are not stored (nothing reads them before the next gather overwrites
 //         them; the last step of edb_run_verlet runs FUSE 1, so the state a caller can observe is complete).
+#ifndef EDB_G_BLK
+#define EDB_G_BLK 128      // profiles/r2_sweep_gather_block.log: 128 x 6 CTAs 0.1105 ms, 192 x 4 0.1120, 256 x 3 0.1127, 384 x 2 0.1145
+#endif
+constexpr int G_BLK = EDB_G_BLK;   // threads per block of k_gather
 #ifndef EDB_G_MINB
-#define EDB_G_MINB 3
+#define EDB_G_MINB 6
 #endif
 constexpr int GU = EDB_GU;
 template <int FUSE, bool POLY>
-__global__ void __launch_bounds__(BLK, EDB_G_MINB) k_gather(const __grid_constant__ GatherArgs A, const __grid_constant__ FanArgs FAN) {
+__global__ void __launch_bounds__(G_BLK, EDB_G_MINB) k_gather(const __grid_constant__ GatherArgs A, const __grid_constant__ FanArgs FAN) {
 #if EDB_G_REVERSE
   const uint32_t p = (gridDim.x - 1 - blockIdx.x) * blockDim.x + threadIdx.x;
 #else

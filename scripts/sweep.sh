@@ -6,6 +6,6 @@ for v in build/variants/*.so; do
   echo "== $(basename $v .so)"
   python bench.py --steps 200 --warmup 20 --no-cpu-baseline --no-e2e --no-poly "$@" 2>&1 | grep "^{" | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); r=d['roofline']; print('value %.4g  ms/step %.4f' % (d['value'], d['ms_per_step']), {k: round(v,4) for k,v in r['per_step_ms'].items()})"
+d=json.loads(sys.stdin.read()); r=d['roofline']; print('value %.4g  ms/step %.4f' % (d['value'], d['ms_per_step']), {k: round(v,4) for k,v in r['per_step_ms'].items() if isinstance(v, float)})"
 done
 cp /tmp/product.so exadem_b200/libexadem_b200.so
