@@ -372,6 +372,9 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
             eA = km & 0xffffu;
             eB = km >> 16;
           }
+          // a pair whose prefilters leave no test at all (no vertex of either inside the other's enlarged OBB, no two edges within reach)
+          // produces no record: it is neither evaluated nor written to the stream (the replay never hears of it)
+          if ((mA | mB) == 0u && (eA == 0u || eB == 0u)) continue;
           const uint8_t ghost = s_gc[Lb];
           const uint8_t f0 = (uint8_t)(ghost << 1), f1 = (uint8_t)(1 | (ghost << 1));
           if (!FILL) {   // pair header of the stream
