@@ -53,6 +53,8 @@ def main():
     ap.add_argument("--rebuild-every", type=int, default=10)
     ap.add_argument("--rtol", type=float, default=1e-10)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--then-ops", type=int, default=0, help="after run_verlet, this many more steps operator by operator")
+    ap.add_argument("--dump", default=None, help="write the ContactState view of wave 0 right after run_verlet to <dump>.rank<r>.npz")
     ap.add_argument("--moving", action="store_true", help="add a stress-controlled floor (surface, LINEAR_COMPRESSIVE_MOTION): reaction all-reduce")
     args = ap.parse_args()
 
@@ -96,6 +98,25 @@ def main():
     sym = wl.symetric
     eng.update_particle_neighbors(wl.rcut_inc, sym)
     nreb = eng.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, sym, args.steps, args.rebuild_every)
+
+    def ops_step(e):
+        # one step of numerical_scheme_verlet operator by operator, without a rebuild (config_numerical_schemes.msp:6-30)
+        e.combined_compute_prolog(wl.dt)
+        e.ghost_update_rq()
+        e.compute_vertices()
+        e.reset_force_moment()
+        e.gravity_force(wl.gravity)
+        e.contact(wl.dt)
+        e.force_to_accel()
+        e.combined_compute_epilog(wl.dt)
+
+    if args.dump:
+        # ContactState view right after run_verlet: the contact point of a record that is not in contact is recomputed from the CURRENT
+        # positions of i and j — for a j on a neighbour brick, from its ghost slot
+        st = eng.get_contact_state(0)
+        np.savez(f"{args.dump}.rank{rank}.npz", dn=st[0], cp=st[1], fn=st[2], ft=st[3])
+    for _ in range(args.then_ops):
+        ops_step(eng)
     pa = eng.download_particles()
     rec = eng.export_interactions()
     ctr = eng.counters()
@@ -114,6 +135,8 @@ def main():
             ref.set_system_mass(system_mass)
         ref.update_particle_neighbors(wl.rcut_inc, sym)
         nreb_ref = ref.run_verlet(wl.dt, wl.gravity, wl.rcut_inc, sym, args.steps, args.rebuild_every)
+        for _ in range(args.then_ops):
+            ops_step(ref)
         pr = ref.download_particles()
         rr = ref.export_interactions()
         try:

@@ -41,6 +41,23 @@ def test_two_gpu_spheres_other_ghost_paths(env):
     _run(2, "--mode", "sphere", "--steps", "60", "--rebuild-every", "0", env=env)
 
 
+def test_two_gpu_ghost_slots_current_after_run_verlet(tmp_path):
+    """Inside edb_run_verlet the remote ghosts are read in the landing zone and the ghost slots are only brought home at the end of the
+    call.  The ContactState view taken right after the call recomputes contact points from the ghost SLOTS: it must be bit-identical to
+    the one of a run that copies the landing zone into the slots at every step (EDB_LAND_COPY=1), and operator-by-operator steps that
+    follow must match the single-domain oracle."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import numpy as np
+    a, b = str(tmp_path / "inplace"), str(tmp_path / "copy")
+    _run(2, "--mode", "sphere", "--steps", "25", "--rebuild-every", "0", "--then-ops", "3", "--dump", a)
+    _run(2, "--mode", "sphere", "--steps", "25", "--rebuild-every", "0", "--then-ops", "3", "--dump", b, env={"EDB_LAND_COPY": "1"})
+    for r in range(2):
+        x, y = np.load(f"{a}.rank{r}.npz"), np.load(f"{b}.rank{r}.npz")
+        for k in ("dn", "cp", "fn", "ft"):
+            assert x[k].shape == y[k].shape and len(x[k]) > 100 and np.array_equal(x[k], y[k]), (r, k)
+
+
 def test_two_gpu_drum_slabs():
     """The N>1 bench workload (drum cut into slabs along its periodic axis, cylinder driver on every rank), parity vs the oracle."""
     if _ngpu() < 2:
