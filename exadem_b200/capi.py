@@ -480,13 +480,14 @@ class Engine:
         v = pa.view()
         self._call("download_dynamic", C.byref(v))
 
-    def upload_dynamic_async(self, pa: ParticleArrays):
-        """pinned host arrays; returns once the copies are enqueued (see include/exadem_b200.h)"""
-        v = pa.view()
+    def upload_dynamic_async(self, pa: ParticleArrays, view=None):
+        """pinned host arrays; returns once the copies are enqueued (see include/exadem_b200.h).  `view`: a pa.view() made once by a
+        caller that steps in a loop (building the 31-pointer struct costs more host time than the call)"""
+        v = view if view is not None else pa.view()
         self._call("upload_dynamic_async", C.byref(v))
 
-    def download_dynamic_async(self, pa: ParticleArrays, field_mask: int = DYN_ALL):
-        v = pa.view()
+    def download_dynamic_async(self, pa: ParticleArrays, field_mask: int = DYN_ALL, view=None):
+        v = view if view is not None else pa.view()
         self._call("download_dynamic_async", C.byref(v), C.c_uint32(field_mask))
 
     def num_particles(self):
