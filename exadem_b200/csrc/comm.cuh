@@ -174,6 +174,7 @@ struct LandArgs {
   // completed (stream order), a system-scope fence by the mailing threads then orders its peer stores before the mail.
   unsigned long long* out_mail[P2P_MAXR];
   int n_out;
+  unsigned long long* host_flag;    // mapped host copy of the summed trigger count (nullptr: the caller publishes it itself)
 };
 __global__ void __launch_bounds__(BLK) k_ghost_land(const __grid_constant__ LandArgs A) {
   __shared__ unsigned long long s_cnt[P2P_MAXR];
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(BLK) k_ghost_land(const __grid_constant__ Land
     for (int r = 0; r < A.nranks; r++)
       if (r != A.me) t += s_cnt[r];
     *A.count = t;
+    if (A.host_flag) { *A.host_flag = t; __threadfence_system(); }
   }
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < A.n; k += gridDim.x * blockDim.x) {
     st4(A.P.pr + A.base + k, ld4(A.land + k));
@@ -441,7 +443,8 @@ struct Comm {
   }
   // copy = false: only the mail is exchanged (our mail out, everybody's in, trigger counts summed); the caller reads the ghosts in
   // the landing zone.  Returns the epoch that landed.
-  uint32_t land_pending(PView P, uint32_t nreal, unsigned long long* count, cudaStream_t st, uint64_t* launches, bool copy = true) {
+  uint32_t land_pending(PView P, uint32_t nreal, unsigned long long* count, cudaStream_t st, uint64_t* launches, bool copy = true,
+                        unsigned long long* host_flag = nullptr) {
     const uint32_t e = fan_epoch_pending;
     fan_epoch_pending = 0;
     const int par = (int)(e & 1u);
@@ -453,6 +456,7 @@ struct Comm {
     L.nranks = nranks; L.me = rank; L.epoch = e; L.count = count;
     L.land = p2p_land(p2p.base, p2p.cap, par);
     L.cap = p2p.cap; L.n = copy ? nrem : 0; L.base = nreal + n_local_ghost;
+    L.host_flag = count ? host_flag : nullptr;
     if (!fan_mailed)
       for (int r = 0; r < nranks; r++)
         if (r != rank) L.out_mail[L.n_out++] = p2p_mail(p2p.peer_base[r], par) + rank;

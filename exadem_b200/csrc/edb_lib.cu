@@ -75,6 +75,7 @@ struct edb_context {
   uint64_t nbh_replays = 0;
   DevBuf<FanEnt> fan_ent;
   bool have_fan = false, ghost_pushed = false;
+  bool flag_published = false;     // the landing launch of this step already stored the trigger count into h_sflag
   uint32_t ghost_in_landing = 0;   // epoch whose remote ghosts live in the landing zone only (0: the ghost slots are current)
   // debugging switches read once at creation: EDB_NO_FAN (separate ghost kernels), EDB_NBH_POLY_PER_THREAD, EDB_NBH_NO_REPLAY
   bool env_no_fan = false, env_nbh_per_thread = false, env_nbh_no_replay = false;
@@ -1033,7 +1034,11 @@ static void ghost_refresh(edb_context* c, bool all, unsigned long long* trig = n
     if (c->cfg.nranks > 1) {
       ScopedTimer tm(c, B_GHOST);
       const bool stay = in_place && !c->poly() && !c->env_land_copy;
-      const uint32_t e = c->comm.land_pending(view(c->pa), c->nreal, trig, c->st, &c->ctr.kernel_launches, !stay);
+      // the landing launch also stores the summed trigger count into the host's mapped copy (saves the publishing launch)
+      unsigned long long* hf = nullptr;
+      if (in_place && trig && !c->st_up && trig >= c->d_sflag && trig < c->d_sflag + 2) hf = c->h_sflag_dev + (trig - c->d_sflag);
+      const uint32_t e = c->comm.land_pending(view(c->pa), c->nreal, trig, c->st, &c->ctr.kernel_launches, !stay, hf);
+      c->flag_published = hf != nullptr;
       c->ghost_in_landing = stay ? e : 0;
     }
     return;
@@ -1893,7 +1898,8 @@ static void trigger_publish(edb_context* c, int slot) {
   // round trip through the copy engine (measured: 0.219 -> 0.210 ms per step on the 1 M drum).  Not while the asynchronous host
   // copies of a host-owned grid are in flight: the SM's store then queues behind megabytes of DMA on the PCIe link and the kernel —
   // and every kernel of the step behind it — waits for it (measured: e2e 4.2 -> 6.4 ms per step), so that path keeps the copy.
-  if (c->st_up) CK(cudaMemcpyAsync(c->h_sflag + slot, c->d_sflag + slot, 8, cudaMemcpyDeviceToHost, c->st));
+  if (c->flag_published) c->flag_published = false;   // (k_ghost_land of this step stored it)
+  else if (c->st_up) CK(cudaMemcpyAsync(c->h_sflag + slot, c->d_sflag + slot, 8, cudaMemcpyDeviceToHost, c->st));
   else LAUNCH(c, k_publish_flag, 1, 1, 0, c->h_sflag_dev + slot, c->d_sflag + slot);
   CK(cudaEventRecord(c->ev_sflag[slot], c->st));
 }
