@@ -77,3 +77,30 @@ def test_reference_arm_is_immune_to_a_pinned_launcher():
     assert r.returncode == 0, r.stderr[-2000:]
     d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][0])
     assert d["run"]["threads_in_parallel_region"] == (os.cpu_count() or 1), d["run"]
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line_carries_the_whole_contract():
+    """`python bench.py` (N = 1, small workload): every key the driver reads is there and means something"""
+    d = run_bench("--steps", "6", "--warmup", "3", "--particles", "30000", "--no-poly", "--cpu-seconds", "1")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["metric"] == "interaction-updates/s" and d["n_gpus"] == 1 and d["steps"] == 6 and d["higher_is_better"] is True
+    assert d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None and d["scaling"] == "weak"
+    # value = records processed by the contact kernels in the timed region / its duration
+    assert d["value"] > 0 and abs(d["value"] * d["ms_per_step"] * 1e-3 / d["run"]["interactions_per_gpu"] - 1.0) < 0.02
+    assert "workload" in d["config"] and "l2" in d["config"]
+    r = d["roofline"]
+    for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "mean_launch_ms", "share_of_step", "per_step_ms"):
+        assert k in r, k
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0 < r["frac"] < 1.5 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    other = d.get("roofline_contact") or d.get("roofline_gather")
+    assert other and other["kernel"] != r["kernel"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c and c["unit"] == d["unit"]
+    e = d["e2e"]
+    n = d["run"]["particles_per_gpu"]
+    assert e["h2d_bytes_per_step"] == 13 * 8 * n and e["d2h_bytes_per_step"] == 22 * 8 * n and 0 < e["value"] < d["value"]
+    assert d["gpu_launches"] >= 3 * 6      # at least contact + gather + flag per step, counted inside the timed region
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
