@@ -69,6 +69,7 @@ struct edb_context {
   DevBuf<uint32_t> fan_cnt, fan_off, fan_bits;
   // polyhedron neighbour build: stream pool of the count pass (kernels_nbh_poly.cuh)
   DevBuf<uint32_t> nbh_pool, nbh_first, nbh_ctr;
+  DevBuf<unsigned long long> rmax_dev;   // bits of the largest pr.w over reals + ghosts (k_max_radius), read by for_each_neighbor
   DevBuf<uint2> pp_tmp;              // spheres: candidates recorded by the count pass of the neighbour build (kernels_rebuild.cuh)
   uint32_t nbh_pool_chunks = 0;
   uint32_t* h_nbh = nullptr;   // pinned copy of nbh_ctr
@@ -79,6 +80,7 @@ struct edb_context {
   uint32_t ghost_in_landing = 0;   // epoch whose remote ghosts live in the landing zone only (0: the ghost slots are current)
   // debugging switches read once at creation: EDB_NO_FAN (separate ghost kernels), EDB_NBH_POLY_PER_THREAD, EDB_NBH_NO_REPLAY
   bool env_no_fan = false, env_nbh_per_thread = false, env_nbh_no_replay = false;
+  bool env_nbh_no_cull = false;      // EDB_NBH_NO_CULL: visit all 27 stencil cells per particle (no cell-level reach test)
   bool env_nbh_two_pass = false;     // EDB_NBH_TWO_PASS: spheres enumerate twice (count, fill) like round 1
   bool env_gather_mail = false;       // EDB_GATHER_MAIL: the gather's last block sends the mail instead of the landing launch
   bool env_land_copy = false;         // EDB_LAND_COPY: always copy the landing zone into the ghost slots (the round-1 path)
@@ -352,6 +354,7 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
   c->env_bonds_host = getenv("EDB_BONDS_HOST") != nullptr;
   c->env_bonds_unfused = getenv("EDB_BONDS_UNFUSED") != nullptr;
   c->env_nbh_two_pass = getenv("EDB_NBH_TWO_PASS") != nullptr;
+  c->env_nbh_no_cull = getenv("EDB_NBH_NO_CULL") != nullptr;
   c->env_land_copy = getenv("EDB_LAND_COPY") != nullptr;
   c->env_gather_mail = getenv("EDB_GATHER_MAIL") != nullptr;
   c->env_nbh_per_thread = getenv("EDB_NBH_POLY_PER_THREAD") != nullptr;
@@ -442,6 +445,7 @@ extern "C" int edb_destroy(edb_context* c) {
   if (c->d_need_count) cudaFree(c->d_need_count);
   if (c->d_sflag) cudaFree(c->d_sflag);
   if (c->h_sflag) cudaFreeHost(c->h_sflag);
+  c->rmax_dev.release();
   c->pp_tmp.release();
   if (c->h_nbh) cudaFreeHost(c->h_nbh);
   for (int i = 0; i < 2; i++) if (c->ev_sflag[i]) cudaEventDestroy(c->ev_sflag[i]);
@@ -1430,6 +1434,12 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   }
   NbhArgs A{view(c->pa), c->cidx.p, c->cbeg.p, c->cend.p, G, c->drv.p, (int)c->h_drv.size(), rcut_inc, symetric, n, c->vert.p, c->S, c->M, 0,
             nullptr, nullptr};
+  if (!c->env_nbh_no_cull) {
+    c->rmax_dev.ensure(2);
+    CK(cudaMemsetAsync(c->rmax_dev.p, 0, 8, c->st));
+    LAUNCH(c, k_max_radius, nblk(n + c->nghost), BLK, 0, c->pa.pr.p, n + c->nghost, c->rmax_dev.p);
+    A.rmax_all = reinterpret_cast<const double*>(c->rmax_dev.p);
+  }
   if (!c->h_bonds.empty()) {
     // persistent interactions (nbh_polyhedron.cpp:146-149): the bonds follow their particles into the new order by id, and the pairs
     // they glue are ignored by the contact enumeration while they hold

@@ -251,7 +251,16 @@ struct NbhArgs {
   // 27-cell stencil; a particle with more candidates raises *pp_overflow and the fill pass enumerates again.
   uint2* pp_tmp;
   uint32_t* pp_overflow;
+  // largest pr.w over reals + ghosts (device scalar, k_max_radius): lets for_each_neighbor skip the stencil cells that lie wholly
+  // beyond ra.w + max radius + rcut_inc of the particle (nullptr: every cell of the stencil is visited)
+  const double* rmax_all;
 };
+__global__ void k_max_radius(const double4* __restrict__ pr, uint32_t n, unsigned long long* __restrict__ out) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  double r = p < n ? pr[p].w : 0.0;
+  for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+  if ((threadIdx.x & 31) == 0 && r > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(r));   // positive doubles order like their bits
+}
 constexpr uint32_t PP_TMP_CAP = 16;
 __device__ __forceinline__ bool bond_ignored(const NbhArgs& A, uint32_t owner, unsigned long long partner_id) {
   if (!A.ign_off) return false;
@@ -276,11 +285,26 @@ template <class F>
 __device__ __forceinline__ void for_each_neighbor(const NbhArgs& A, uint32_t a, const double4 ra, F&& f) {
   int ci, cj, ck;
   cell_ijk(A.G, A.cidx[a], ci, cj, ck);
+  // Distance from the particle to the face it shares with the neighbour cell in each direction (cell c of the shelled grid covers
+  // [lo + (c-1) cs, lo + c cs)): a stencil cell whose nearest point is farther than the largest possible filter radius holds no
+  // candidate.  The visiting order of the remaining cells is unchanged, and so is the order of the records.  With cells of 2.5 and a
+  // reach of 1.4 (the drum) a particle needs 9.5 of its 27 cells on average — but the 32 particles of a warp sit all over their cell and
+  // the warp walks the union, so the 1 M-sphere build stays at 1.8 ms (measured); it pays for sparse or strongly polydisperse sets.
+  double reach2 = 1.7976931348623157e308, gx[3], gy[3], gz[3];
+  if (A.rmax_all) {
+    const double reach = (ra.w + *A.rmax_all + A.rcut_inc) * 1.000000001;
+    reach2 = reach * reach;
+  }
+  gx[1] = gy[1] = gz[1] = 0.0;
+  gx[0] = fmax(ra.x - (A.G.lo[0] + (ci - 1) * A.G.cs[0]), 0.0); gx[2] = fmax((A.G.lo[0] + ci * A.G.cs[0]) - ra.x, 0.0);
+  gy[0] = fmax(ra.y - (A.G.lo[1] + (cj - 1) * A.G.cs[1]), 0.0); gy[2] = fmax((A.G.lo[1] + cj * A.G.cs[1]) - ra.y, 0.0);
+  gz[0] = fmax(ra.z - (A.G.lo[2] + (ck - 1) * A.G.cs[2]), 0.0); gz[2] = fmax((A.G.lo[2] + ck * A.G.cs[2]) - ra.z, 0.0);
   for (int dk = -1; dk <= 1; dk++)
     for (int dj = -1; dj <= 1; dj++)
       for (int di = -1; di <= 1; di++) {
         const int i = ci + di, j = cj + dj, k = ck + dk;
         if (i < 0 || j < 0 || k < 0 || i >= A.G.g[0] || j >= A.G.g[1] || k >= A.G.g[2]) continue;
+        if (gx[di + 1] * gx[di + 1] + gy[dj + 1] * gy[dj + 1] + gz[dk + 1] * gz[dk + 1] > reach2) continue;
         const uint32_t cb = cell_lin(A.G, i, j, k);
         const bool gc = is_ghost_cell(A.G, i, j, k);
         const uint32_t e = A.cend[cb];
