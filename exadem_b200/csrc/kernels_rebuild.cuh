@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(128) k_nbh_sphere(NbhArgs A, CntTab C, WTab W)
   }
   uint32_t n0 = 0;
   const uint32_t base0 = FILL ? C.c[0][a] : 0;
-  if (!(FILL && A.skip_pp)) for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
+  if (!A.skip_pp) for_each_neighbor(A, a, ra, [&](uint32_t b, bool gc) {
     const uint64_t idb = A.P.id[b];
     uint8_t ghost = 0;
     if (A.symetric) {  // nbh_sphere.cu:245-249
@@ -410,14 +410,78 @@ __global__ void __launch_bounds__(128) k_nbh_sphere(NbhArgs A, CntTab C, WTab W)
     n0++;
   });
   if (!FILL) {
-    C.c[0][a] = n0;
-    if (A.pp_tmp && n0 > PP_TMP_CAP) *A.pp_overflow = 1u;
+    if (!A.skip_pp) {
+      C.c[0][a] = n0;
+      if (A.pp_tmp && n0 > PP_TMP_CAP) *A.pp_overflow = 1u;
+    }
     if (C.c[4]) C.c[4][a] = nd[0];
     if (C.c[5]) C.c[5][a] = nd[1];
     if (C.c[6]) C.c[6][a] = nd[2];
     if (C.c[7]) C.c[7][a] = nm[0];
     if (C.c[8]) C.c[8][a] = nm[1];
     if (C.c[9]) C.c[9][a] = nm[2];
+  }
+}
+
+// Count pass of wave 0 with a WARP per particle (spheres): the lanes take 32 consecutive candidates of a stencil cell at a time — one
+// coalesced 1 KB load instead of 32 dependent trips through a per-thread loop —, the cell-level reach test is warp-uniform (one
+// particle), so 9.5 instead of 27 cells are visited, and a ballot keeps the accepted candidates in the serial loop's order
+// (cell order, then slot order): same records, same order, same pp_tmp contents as k_nbh_sphere<false>.
+// Measured (drum, 1.05 M spheres): 2.40 ms per rebuild against 1.78 ms for the thread-per-particle count: a cell holds ~4 spheres,
+// so 28 of 32 lanes idle per stencil cell. Kept behind EDB_NBH_WARP (parity-green) for dense cells; off by default.
+__global__ void __launch_bounds__(256) k_nbh_sphere_warp(NbhArgs A, uint32_t* __restrict__ cnt0) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (a >= A.nreal) return;
+  const double4 ra = A.P.pr[a];
+  const uint64_t ida = A.P.id[a];
+  int ci, cj, ck;
+  cell_ijk(A.G, A.cidx[a], ci, cj, ck);
+  double reach2 = 1.7976931348623157e308, gx[3], gy[3], gz[3];
+  if (A.rmax_all) {
+    const double reach = (ra.w + *A.rmax_all + A.rcut_inc) * 1.000000001;
+    reach2 = reach * reach;
+  }
+  gx[1] = gy[1] = gz[1] = 0.0;
+  gx[0] = fmax(ra.x - (A.G.lo[0] + (ci - 1) * A.G.cs[0]), 0.0); gx[2] = fmax((A.G.lo[0] + ci * A.G.cs[0]) - ra.x, 0.0);
+  gy[0] = fmax(ra.y - (A.G.lo[1] + (cj - 1) * A.G.cs[1]), 0.0); gy[2] = fmax((A.G.lo[1] + cj * A.G.cs[1]) - ra.y, 0.0);
+  gz[0] = fmax(ra.z - (A.G.lo[2] + (ck - 1) * A.G.cs[2]), 0.0); gz[2] = fmax((A.G.lo[2] + ck * A.G.cs[2]) - ra.z, 0.0);
+  uint32_t n0 = 0;
+  for (int dk = -1; dk <= 1; dk++)
+    for (int dj = -1; dj <= 1; dj++)
+      for (int di = -1; di <= 1; di++) {
+        const int i = ci + di, j = cj + dj, k = ck + dk;
+        if (i < 0 || j < 0 || k < 0 || i >= A.G.g[0] || j >= A.G.g[1] || k >= A.G.g[2]) continue;
+        if (gx[di + 1] * gx[di + 1] + gy[dj + 1] * gy[dj + 1] + gz[dk + 1] * gz[dk + 1] > reach2) continue;
+        const uint32_t cb = cell_lin(A.G, i, j, k);
+        const bool gc = is_ghost_cell(A.G, i, j, k);
+        const uint32_t e = A.cend[cb];
+        for (uint32_t b0 = A.cbeg[cb]; b0 < e; b0 += 32) {
+          const uint32_t b = b0 + lane;
+          bool ok = false;
+          uint8_t ghost = 0;
+          if (b < e && b != a) {
+            const double4 rb = ldg4(A.P.pr + b);
+            const v3 d = mk3(rb.x, rb.y, rb.z) - mk3(ra.x, ra.y, ra.z);
+            const double d2 = dot(d, d);
+            const double rmax = ra.w + rb.w + A.rcut_inc;
+            if (d2 > 0.0 && d2 < rmax * rmax) {   // ContactNeighborFilterFunc (chunk_neighbors_contact.cpp:46-57)
+              const uint64_t idb = A.P.id[b];
+              if (A.symetric) ok = !(ida >= idb && !gc);           // nbh_sphere.cu:245-249
+              else { ok = ida < idb; ghost = gc ? 1 : 0; }          // :272-279
+            }
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          if (ok) {
+            const uint32_t pos = n0 + __popc(m & ((1u << lane) - 1u));
+            if (A.pp_tmp && pos < PP_TMP_CAP) A.pp_tmp[(size_t)pos * A.nreal + a] = make_uint2(b, (uint32_t)(ghost << 1));
+          }
+          n0 += __popc(m);
+        }
+      }
+  if (lane == 0) {
+    cnt0[a] = n0;
+    if (A.pp_tmp && n0 > PP_TMP_CAP) *A.pp_overflow = 1u;
   }
 }
 
