@@ -1485,7 +1485,7 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   if (cell_cap) {
     c->nbh_ctr.ensure(8);   // [0] cursor  [1] overflow  [2,3] need (u64)
     CK(cudaMemsetAsync(c->nbh_ctr.p, 0, 32, c->st));
-    c->nbh_first.ensure(n + 1);
+    c->nbh_first.ensure((size_t)n * NPC_PARTS + 1);
     record = c->nbh_pool_chunks > 0 && !c->env_nbh_no_replay;
     PL = NbhPool{c->nbh_pool.p, c->nbh_ctr.p, record ? c->nbh_pool_chunks : 0u, c->nbh_first.p,
                  reinterpret_cast<unsigned long long*>(c->nbh_ctr.p + 2), c->nbh_ctr.p + 1};
@@ -1514,6 +1514,9 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
     if (A.pp_tmp) CK(cudaMemcpyAsync(c->h_nbh, c->nbh_ctr.p, 32, cudaMemcpyDeviceToHost, c->st));
   } else {
     if (cell_cap) {
+      if (NPC_PARTS > 1)   // the parts of an owner add their counts
+        for (int t = 0; t < 4; t++)
+          if (C.c[t]) CK(cudaMemsetAsync(C.c[t], 0, (size_t)(n + 1) * 4, c->st));
       if (record) LAUNCH(c, k_nbh_poly_cell<1>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap, PL);
       else LAUNCH(c, k_nbh_poly_cell<0>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap, PL);
       CK(cudaMemcpyAsync(c->h_nbh, c->nbh_ctr.p, 32, cudaMemcpyDeviceToHost, c->st));

@@ -29,7 +29,20 @@ namespace edb {
 #ifndef EDB_NPC_MINB
 #define EDB_NPC_MINB 1
 #endif
+#ifndef EDB_NPC_PARTS
+#define EDB_NPC_PARTS 1
+#endif
+#ifndef EDB_NPC_NI
+#define EDB_NPC_NI 0
+#endif
 constexpr int NPC_THREADS = EDB_NPC_THREADS;
+// EDB_NPC_PARTS > 1: a warp's work item in the count pass is 1/NPC_PARTS of an owner's stencil (a contiguous range of 32-candidate
+// chunks) instead of the whole owner; every part writes its own stream, the counts are added per owner, the replay walks the parts
+// in order, so the records and their order are unchanged (parity-green at 4).  The idea was load balance — a cell holds 8 / 12 / 18 /
+// 27 octahedra on 16 warps, ncu shows 11 of 16 resident warps active on average —, the measurement says no: 19.6 / 23.6 / 29.8 /
+// 36.2 / 40.7 ms per build at 1 / 2 / 4 / 8 / 14 parts (profiles/r2_sweep_poly_parts.log): every part pays its own OBB round and
+// prefilter rounds on a handful of lanes, and that costs more than the idle warps did.  Default 1.
+constexpr uint32_t NPC_PARTS = EDB_NPC_PARTS;
 constexpr int CHW = 64;                       // words per pool chunk; word 0 links to the next chunk
 constexpr uint32_t NPC_NONE = 0xffffffffu;
 
@@ -97,11 +110,34 @@ __device__ __forceinline__ uint32_t nth_set_bit(uint32_t m, uint32_t n) {
   return (uint32_t)__ffs((int)m) - 1u;
 }
 
+// EDB_NPC_NI (bit 0: OBB test, bit 1: filters): out-of-line copies of the big inlined bodies, to shrink the kernel's code (ncu: 16 % of
+// the warp samples are instruction-fetch stalls on 6700 SASS instructions)
+__device__ __noinline__ bool obb_intersect_ni(const Obb& a, const Obb& b) { return obb_intersect(a, b); }
+__device__ __noinline__ bool filter_ve_ni(double rV, v3 vi, double ri, v3 vf, v3 vs, double rj) { return filter_ve(rV, vi, ri, vf, vs, rj); }
+__device__ __noinline__ bool filter_ee_ni(double rV, v3 fi, v3 si, double ri, v3 fj, v3 sj, double rj) { return filter_ee(rV, fi, si, ri, fj, sj, rj); }
+__device__ __noinline__ bool filter_vf_ni(double rV, v3 vi, double ri, const double4* vb, double rj, const int* idx, int nf) {
+  return filter_vf(rV, vi, ri, SV{vb}, rj, idx, nf);
+}
+#if EDB_NPC_NI & 1
+#define NPC_OBB_INTERSECT obb_intersect_ni
+#else
+#define NPC_OBB_INTERSECT obb_intersect
+#endif
+#if EDB_NPC_NI & 2
+#define NPC_FILTER_VE filter_ve_ni
+#define NPC_FILTER_EE filter_ee_ni
+#define NPC_FILTER_VF(rV, vi, ri, vb, rj, idx, nf) filter_vf_ni(rV, vi, ri, (vb).p, rj, idx, nf)
+#else
+#define NPC_FILTER_VE filter_ve
+#define NPC_FILTER_EE filter_ee
+#define NPC_FILTER_VF(rV, vi, ri, vb, rj, idx, nf) filter_vf(rV, vi, ri, vb, rj, idx, nf)
+#endif
+
 struct NbhPool {
   uint32_t* words;                // cap_chunks * CHW
   uint32_t* cursor;               // next free chunk
   uint32_t cap_chunks;
-  uint32_t* first;                // per owner slot: first chunk of its stream (NPC_NONE: no pair)
+  uint32_t* first;                // per (owner slot, part): first chunk of its stream (NPC_NONE: no pair)
   unsigned long long* need;       // += chunks every owner would need (sizes the pool for the next rebuild)
   uint32_t* overflow;             // set when the pool ran out: the fill pass falls back to recomputation
 };
@@ -153,10 +189,6 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
   const GridDev& G = A.G;
   const uint32_t c = blockIdx.x;
   const int ci = c % G.nc[0] + 1, cj = (c / G.nc[0]) % G.nc[1] + 1, ck = c / (G.nc[0] * G.nc[1]) + 1;
-  {
-    const uint32_t lin = cell_lin(G, ci, cj, ck);
-    if (A.cend[lin] == A.cbeg[lin]) return;   // empty cell: nothing to own (uniform for the block)
-  }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
   // ---- stage the stencil ------------------------------------------------------------------------------------------------
@@ -175,12 +207,13 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
     const uint32_t inc = warp_incl_scan(cnt);
     if (lane < 27) s_cbase[lane] = inc - cnt;
     const uint32_t nst0 = __shfl_sync(0xffffffffu, inc, 31);
+    const bool owners = __shfl_sync(0xffffffffu, cnt, 13) != 0;   // empty centre cell: nothing to own, nothing is staged
     if (lane == 0) {
       s_cbase[27] = nst0;
-      mbar_expect_tx(&s_bar, nst0 * (uint32_t)(nvmax * 32 + 64));
+      if (owners) mbar_expect_tx(&s_bar, nst0 * (uint32_t)(nvmax * 32 + 64));
     }
     __syncwarp();
-    if (lane < 27 && cnt) {
+    if (owners && lane < 27 && cnt) {
       const uint32_t o = inc - cnt;
       tma_load_1d(s_vert + (size_t)o * nvmax, A.vert + (size_t)beg * nvmax, cnt * (uint32_t)nvmax * 32u, &s_bar);
       tma_load_1d(s_pr + o, A.P.pr + beg, cnt * 32u, &s_bar);
@@ -188,17 +221,21 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
     }
   }
   __syncthreads();
+  if (s_cbase[14] == s_cbase[13]) return;   // uniform for the block
   const uint32_t nst = s_cbase[27];
-  for (int t = 0; t < 27; t++) {
-    const uint32_t o = s_cbase[t], n = s_cbase[t + 1] - o, beg = s_cbeg[t];
-    for (uint32_t x = threadIdx.x; x < n; x += NPC_THREADS) {
-      const uint32_t slot = beg + x;
-      s_slot[o + x] = slot;
-      s_id[o + x] = A.P.id[slot];
-      s_h[o + x] = A.P.h[slot];
-      s_type[o + x] = type_of_bits(A.P.wg[slot].w);
-      s_gc[o + x] = s_cgc[t];
-    }
+  // one pass over the staged particles (a thread finds its stencil cell in the prefix table) — a loop over the 27 cells would
+  // serialise 27 global-load latencies on the ~17 threads a cell keeps busy while the other warps wait at the barrier
+  for (uint32_t x = threadIdx.x; x < nst; x += NPC_THREADS) {
+    int t = 0;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1)
+      if (t + s < 27 && s_cbase[t + s] <= x) t += s;
+    const uint32_t slot = s_cbeg[t] + (x - s_cbase[t]);
+    s_slot[x] = slot;
+    s_id[x] = A.P.id[slot];
+    s_h[x] = A.P.h[slot];
+    s_type[x] = type_of_bits(A.P.wg[slot].w);
+    s_gc[x] = s_cgc[t];
   }
   mbar_wait(&s_bar, 0);
   __syncthreads();
@@ -206,11 +243,15 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
   // ---- owners (taken from a shared counter: the work per owner varies with its number of neighbours) -----------------------
   const double rV = A.rcut_inc;
   const uint32_t own0 = s_cbase[13], nown = s_cbase[14] - own0;
+  const uint32_t nparts = FILL ? 1u : NPC_PARTS;   // the recomputing fill needs the whole owner (its offsets run through the parts)
+  const uint32_t nchunk = (nst + 31) / 32;
   for (;;) {
-    uint32_t oi_ = 0;
-    if (lane == 0) oi_ = atomicAdd(&s_next, 1u);
-    oi_ = __shfl_sync(0xffffffffu, oi_, 0);
-    if (oi_ >= nown) break;
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(&s_next, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= nown * nparts) break;
+    const uint32_t oi_ = item / nparts, part = item % nparts;
+    const uint32_t ch_lo = nchunk * part / nparts * 32, ch_hi = min(nst, nchunk * (part + 1) / nparts * 32);
     const uint32_t La = own0 + oi_;
     const uint32_t a = s_slot[La];
     const double4 ra = s_pr[La], qa4 = s_q[La];
@@ -241,7 +282,7 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
         if (wfill == CHW) {
           const uint32_t nc = atomicAdd(PL.cursor, 1u);
           if (nc >= PL.cap_chunks) { wovf = true; atomicExch(PL.overflow, 1u); return; }
-          if (wchunk == NPC_NONE) PL.first[a] = nc;
+          if (wchunk == NPC_NONE) PL.first[(size_t)a * NPC_PARTS + part] = nc;
           else PL.words[(size_t)wchunk * CHW] = nc;
           wchunk = nc;
           wfill = 1;
@@ -264,7 +305,7 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
     // full warp of queued candidates at a time instead of on the one or two lanes of a chunk that happen to be in range.
     uint16_t* qu = s_queue[wid];
     uint32_t nq = 0;
-    for (uint32_t ch = 0; ch < nst; ch += 32) {
+    for (uint32_t ch = ch_lo; ch < ch_hi; ch += 32) {
       const uint32_t L = ch + lane;
       bool near = false;
       if (L < nst && L != La) {
@@ -279,7 +320,7 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
       if (near) qu[nq + __popc(nm & ((1u << lane) - 1u))] = (uint16_t)L;
       nq += __popc(nm);
       __syncwarp();
-      const bool last_chunk = ch + 32 >= nst;
+      const bool last_chunk = ch + 32 >= ch_hi;
       while (nq >= 32 || (last_chunk && nq > 0)) {
         const uint32_t take = nq < 32 ? nq : 32;
         const uint32_t Lc = lane < take ? qu[lane] : 0;
@@ -289,7 +330,7 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
           Obb oi = obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha);
           Obb oj = obb_world(A.S.sh[s_type[Lc]].obb, mk3(rb.x, rb.y, rb.z), q4{qb4.x, qb4.y, qb4.z, qb4.w}, s_h[Lc]);
           obb_enlarge(oi, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
-          pass = obb_intersect(oi, oj);
+          pass = NPC_OBB_INTERSECT(oi, oj);
         }
         unsigned pm = __ballot_sync(0xffffffffu, pass);
         const uint32_t rest = nq - take;   // < 32: a chunk adds at most 32 and the queue is drained as soon as it holds 32
@@ -316,7 +357,7 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
               const double4 rb = s_pr[Lq], qb4 = s_q[Lq];
               Obb oj = obb_world(A.S.sh[s_type[Lq]].obb, mk3(rb.x, rb.y, rb.z), q4{qb4.x, qb4.y, qb4.z, qb4.w}, s_h[Lq]);
               obb_enlarge(oj, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
-              ok = obb_intersect(oj, obb_point(va[v], rma));
+              ok = NPC_OBB_INTERSECT(oj, obb_point(va[v], rma));
             }
             const unsigned m = __ballot_sync(0xffffffffu, ok);
             if (q < npass && v == 0) vmA[q] = SA == 32 ? m : ((m >> (lane & ~(SA - 1))) & ((1u << SA) - 1u));
@@ -332,7 +373,7 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
                 Obb oi = obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha);
                 obb_enlarge(oi, 0.5 * rV); obb_enlarge(oi, 0.5 * rV);
                 const SV vq{s_vert + (size_t)Lq * nvmax};
-                ok = obb_intersect(oi, obb_point(vq[v], s_h[Lq] * psq->radius));
+                ok = NPC_OBB_INTERSECT(oi, obb_point(vq[v], s_h[Lq] * psq->radius));
               }
             }
             const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -402,41 +443,44 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
                 [&](uint32_t x) { const uint32_t i = vtxA(x / nvb), j = x % nvb; return filter_vv(rV, va[i], rma, vb[j], rmb); },
                 [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
           group(1, nA * neb,
-                [&](uint32_t x) { const uint32_t i = vtxA(x / neb), j = x % neb; return filter_ve(rV, va[i], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb); },
+                [&](uint32_t x) { const uint32_t i = vtxA(x / neb), j = x % neb; return NPC_FILTER_VE(rV, va[i], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb); },
                 [&](uint32_t x, uint32_t k) { write(1, k, a, b, vtxA(x / neb), x % neb, f0); });
           group(2, nA * nfb,
                 [&](uint32_t x) {
                   const uint32_t i = vtxA(x / nfb), j = x % nfb;
-                  return filter_vf(rV, va[i], rma, vb, rmb, A.S.fidx + sb.fi0 + A.S.foff[sb.f0 + j], A.S.fn[sb.f0 + j]);
+                  return NPC_FILTER_VF(rV, va[i], rma, vb, rmb, A.S.fidx + sb.fi0 + A.S.foff[sb.f0 + j], A.S.fn[sb.f0 + j]);
                 },
                 [&](uint32_t x, uint32_t k) { write(2, k, a, b, vtxA(x / nfb), x % nfb, f0); });
           // edge-edge over the edges within reach only (ascending in both indices: the emission order of the full double loop)
           group(3, nEA * nEB,
                 [&](uint32_t x) {
                   const uint32_t i = edgA(x / nEB), j = edgB(x % nEB);
-                  return filter_ee(rV, va[ea[2 * i]], va[ea[2 * i + 1]], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb);
+                  return NPC_FILTER_EE(rV, va[ea[2 * i]], va[ea[2 * i + 1]], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb);
                 },
                 [&](uint32_t x, uint32_t k) { write(3, k, a, b, edgA(x / nEB), edgB(x % nEB), f0); });
           // B -> A (swap = 1): pi = b, pj = a; the owner stays a (interaction_pair.hpp:75-90)
           group(1, nB * nea,
-                [&](uint32_t x) { const uint32_t j = vtxB(x / nea), i = x % nea; return filter_ve(rV, vb[j], rmb, va[ea[2 * i]], va[ea[2 * i + 1]], rma); },
+                [&](uint32_t x) { const uint32_t j = vtxB(x / nea), i = x % nea; return NPC_FILTER_VE(rV, vb[j], rmb, va[ea[2 * i]], va[ea[2 * i + 1]], rma); },
                 [&](uint32_t x, uint32_t k) { write(1, k, b, a, vtxB(x / nea), x % nea, f1); });
           group(2, nB * nfa,
                 [&](uint32_t x) {
                   const uint32_t j = vtxB(x / nfa), i = x % nfa;
-                  return filter_vf(rV, vb[j], rmb, va, rma, A.S.fidx + sa.fi0 + A.S.foff[sa.f0 + i], A.S.fn[sa.f0 + i]);
+                  return NPC_FILTER_VF(rV, vb[j], rmb, va, rma, A.S.fidx + sa.fi0 + A.S.foff[sa.f0 + i], A.S.fn[sa.f0 + i]);
                 },
                 [&](uint32_t x, uint32_t k) { write(2, k, b, a, vtxB(x / nfa), x % nfa, f1); });
         }
       }
     }
     if (!FILL) {
-      if (nw) emit(NPC_NONE);   // end of the owner's stream
+      if (nw) emit(NPC_NONE);   // end of this part's stream
       if (lane == 0) {
 #pragma unroll
-        for (int t = 0; t < 4; t++) C.c[t][a] = run[t];
+        for (int t = 0; t < 4; t++) {
+          if (NPC_PARTS == 1) C.c[t][a] = run[t];
+          else if (run[t]) atomicAdd(&C.c[t][a], run[t]);   // the host zeroed the counts; integer sums: order-independent
+        }
         if (nw) atomicAdd(PL.need, (unsigned long long)((nw + CHW - 2) / (CHW - 1)));
-        if (MODE == 1 && wchunk == NPC_NONE) PL.first[a] = NPC_NONE;
+        if (MODE == 1 && wchunk == NPC_NONE) PL.first[(size_t)a * NPC_PARTS + part] = NPC_NONE;
       }
     }
   }
@@ -448,9 +492,7 @@ __global__ void __launch_bounds__(256) k_nbh_poly_replay(NbhArgs A, CntTab C, WT
   const int lane = threadIdx.x & 31;
   const uint32_t a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (a >= A.nreal) return;
-  uint32_t chunk = PL.first[a];
-  if (chunk == NPC_NONE) return;
-  uint32_t pos = 1;
+  uint32_t chunk = NPC_NONE, pos = 1;
   auto rd = [&]() {
     if (pos == CHW) { chunk = PL.words[(size_t)chunk * CHW]; pos = 1; }
     return PL.words[(size_t)chunk * CHW + pos++];
@@ -460,7 +502,11 @@ __global__ void __launch_bounds__(256) k_nbh_poly_replay(NbhArgs A, CntTab C, WT
   uint32_t run[4] = {0, 0, 0, 0}, base[4];
 #pragma unroll
   for (int t = 0; t < 4; t++) base[t] = C.c[t][a];
-  for (;;) {
+  for (uint32_t part = 0; part < NPC_PARTS; part++) {   // the parts of the owner's stencil in order: the order of the unsplit walk
+   chunk = PL.first[(size_t)a * NPC_PARTS + part];
+   if (chunk == NPC_NONE) continue;
+   pos = 1;
+   for (;;) {
     const uint32_t b = rd();
     if (b == NPC_NONE) break;
     const uint32_t idlo = rd(), idhi = rd(), gt = rd(), mA = rd(), mB = rd(), eA = rd(), eB = rd();
@@ -494,6 +540,7 @@ __global__ void __launch_bounds__(256) k_nbh_poly_replay(NbhArgs A, CntTab C, WT
           [&](uint32_t x, uint32_t k) { write(3, k, a, b, nth_set_bit(eA, x / nEB), nth_set_bit(eB, x % nEB), f0); });
     group(1, nB * nea, [&](uint32_t x, uint32_t k) { write(1, k, b, a, vtxB(x / nea), x % nea, f1); });
     group(2, nB * nfa, [&](uint32_t x, uint32_t k) { write(2, k, b, a, vtxB(x / nfa), x % nfa, f1); });
+   }
   }
 }
 
