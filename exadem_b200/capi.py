@@ -587,6 +587,15 @@ class Engine:
         self._call("simulation_state", C.c_int32(1 if symetric else 0), C.byref(out))
         return out
 
+    def dem_cost_model(self):
+        """[dem_cost_model] cost per real cell of this rank's grid, shape (nz, ny, nx) (x fastest like the reference's CellCosts)."""
+        dims = (C.c_int32 * 3)()
+        self._call("dem_cost_model", dims, None, C.c_uint64(0))
+        nx, ny, nz = (int(d) for d in dims)
+        out = np.zeros((nz, ny, nx))
+        self._call("dem_cost_model", dims, _as(out, _D), C.c_uint64(out.size))
+        return out
+
     def stress_tensor(self):
         """[stress_tensor] per-particle 3x3 sum of f (x) (cp - r) over the contacts of the last step, upload order."""
         nr = C.c_uint64()

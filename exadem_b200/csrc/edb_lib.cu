@@ -55,6 +55,7 @@ struct edb_context {
   int n_regions = 0;
   DevBuf<uint16_t> ptype;            // polyhedra: shape index per slot (reals + ghosts), refreshed with the world vertices
   bool have_backup = false;
+  bool have_cells = false;           // cbeg / cend / cidx describe the current particle set (set by the rebuild)
   // ghost table (host-built, static for a given grid)
   uint32_t n_gent = 0;
   DevBuf<uint32_t> g_cell, g_src_cell, g_count, g_off, g_src, g_ent;
@@ -901,6 +902,7 @@ extern "C" int edb_upload_particles(edb_context* c, const edb_particles* P) {
   if (P->radius)
     for (uint64_t i = 0; i < n; i++) c->rmax_upload = std::max(c->rmax_upload, P->radius[i]);
   c->nreal = (uint32_t)n;
+  c->have_cells = false;
   c->nghost = 0;
   clear_interactions(c);
   API_END(c)
@@ -1618,6 +1620,7 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
     c->have_inc = true;
   }
   c->ctr.rebuilds++;
+  c->have_cells = true;
 }
 
 extern "C" int edb_update_particle_neighbors(edb_context* c, double rcut_inc, int32_t symetric) {
@@ -2910,6 +2913,59 @@ extern "C" int edb_stress_tensor(edb_context* c, double* stress9) {
   LAUNCH(c, k_stress, nblk(c->nreal), BLK, 0, A, c->stage.p);
   CK(cudaMemcpyAsync(stress9, c->stage.p, (size_t)c->nreal * 9 * sizeof(double), cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
+  API_END(c)
+}
+
+// ---- dem_cost_model (src/interaction/dem_cost_model.cpp:63-92) ------------------------------------------------------------
+struct CostOff {
+  const uint32_t* off[NT];
+};
+__constant__ double c_cost_weight[NT] = {1, 3, 5, 4, 1, 1, 1, 1, 3, 5, 4, 3, 5, 1};
+// thread per real cell: the owners of a cell are contiguous slots of the cell-sorted arrays, so the records they own in a wave are
+// one difference of the wave's CSR offsets
+__global__ void k_cell_costs(GridDev G, const uint32_t* __restrict__ cbeg, const uint32_t* __restrict__ cend, CostOff O, double* __restrict__ out) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= (uint32_t)G.nc[0] * G.nc[1] * G.nc[2]) return;
+  const int ci = c % G.nc[0] + 1, cj = (c / G.nc[0]) % G.nc[1] + 1, ck = c / (G.nc[0] * G.nc[1]) + 1;
+  const uint32_t lin = cell_lin(G, ci, cj, ck), b = cbeg[lin], e = cend[lin];
+  double cost = 3.0 * (double)(e - b) + 1.0;
+  if (e > b)
+    for (int t = 0; t < NT; t++)
+      if (O.off[t]) cost += c_cost_weight[t] * (double)(O.off[t][e] - O.off[t][b]);
+  out[c] = cost;
+}
+// inner bonds (type 13) live in their own arrays: one per bond, in the owner's cell (integer-valued sums: order-independent)
+__global__ void k_cell_costs_bonds(GridDev G, const uint2* __restrict__ ij, uint32_t n, const uint32_t* __restrict__ cidx, uint32_t nreal,
+                                   double* __restrict__ out) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t a = ij[k].x;
+  if (a >= nreal) return;
+  int ci, cj, ck;
+  cell_ijk(G, cidx[a], ci, cj, ck);
+  atomicAdd(&out[(uint32_t)(ci - 1) + G.nc[0] * ((uint32_t)(cj - 1) + G.nc[1] * (uint32_t)(ck - 1))], c_cost_weight[13]);
+}
+extern "C" int edb_dem_cost_model(edb_context* c, int32_t grid_dims[3], double* costs, uint64_t cap) {
+  API_BEGIN(c)
+  const GridDev& G = c->G;
+  if (grid_dims)
+    for (int d = 0; d < 3; d++) grid_dims[d] = G.nc[d];
+  if (costs) {
+    const uint64_t ncell = (uint64_t)G.nc[0] * G.nc[1] * G.nc[2];
+    if (cap < ncell) throw StateError{EDB_ERR_CAPACITY, "dem_cost_model: cost buffer smaller than the real-cell grid"};
+    if (!c->have_cells) throw StateError{EDB_ERR_STATE, "dem_cost_model: no cell grid yet (edb_update_particle_neighbors first)"};
+    quiesce(c);
+    CostOff O{};
+    for (int t = 0; t < NT; t++) O.off[t] = c->wave[t].n ? c->wave[t].off.p : nullptr;
+    DevBuf<double> d_cost;
+    d_cost.ensure(ncell + 1);
+    LAUNCH(c, k_cell_costs, nblk(ncell), BLK, 0, G, c->cbeg.p, c->cend.p, O, d_cost.p);
+    if (!c->h_bonds.empty() && c->bonds_on_device)
+      LAUNCH(c, k_cell_costs_bonds, nblk(c->h_bonds.size()), BLK, 0, G, c->b_ij.p, (uint32_t)c->h_bonds.size(), c->cidx.p, c->nreal, d_cost.p);
+    CK(cudaMemcpyAsync(costs, d_cost.p, ncell * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    d_cost.release();
+  }
   API_END(c)
 }
 

@@ -325,6 +325,23 @@ class StressTensor : public OperatorNode {
     stress.set(std::move(out));
   }
 };
+// src/interaction/dem_cost_model.cpp:37-92 — per-cell cost estimate for the load balancer; result in slot `cell_costs` (x fastest
+// over the real cells) with the grid dimensions in `cell_costs_dims`
+class DEMCostModel : public OperatorNode {
+  ADD_SLOT(GridB200, grid, INPUT, REQUIRED);
+  ADD_SLOT(std::vector<double>, cell_costs, OUTPUT);
+  ADD_SLOT(std::vector<int>, cell_costs_dims, OUTPUT);
+ public:
+  std::string documentation() const final { return "Estimates the cost of every inner cell (3 N + 1 + weighted interaction counts) for the load balancing."; }
+  void execute() final {
+    int32_t dims[3] = {0, 0, 0};
+    ck(*grid, edb_dem_cost_model(grid->ctx, dims, nullptr, 0), "dem_cost_model");
+    std::vector<double> out((size_t)dims[0] * dims[1] * dims[2]);
+    ck(*grid, edb_dem_cost_model(grid->ctx, dims, out.data(), out.size()), "dem_cost_model");
+    cell_costs.set(std::move(out));
+    cell_costs_dims.set(std::vector<int>{dims[0], dims[1], dims[2]});
+  }
+};
 // src/io/simulation_state.cu:80-175 — the reductions of the log line (this rank's share); result in slot `simulation_state` as
 // {kinetic xyz, rotation xyz, mass, min_dn, n_particles, n_active, n_total}
 class SimulationStateNode : public OperatorNode {
@@ -370,6 +387,7 @@ ONIKA_AUTORUN_INIT(exadem_b200_hot_path) {
   f->register_factory("nbh_sphere", make_simple_operator<UpdateContactInteractionSphere>);
   f->register_factory("nbh_polyhedron", make_simple_operator<UpdateGridCellInteractionPolyhedron>);
   f->register_factory("stress_tensor", make_simple_operator<StressTensor>);
+  f->register_factory("dem_cost_model", make_simple_operator<DEMCostModel>);
   f->register_factory("simulation_state", make_simple_operator<SimulationStateNode>);
   f->register_factory("compute_driver_force_moment", make_simple_operator<ComputeDriverForceMoment>);
   // bookkeeping operators of update_particles_full (config_move_particles.msp:141-154) that the device layout makes implicit

@@ -35,9 +35,53 @@ def rank_coords(rank: int, pgrid) -> tuple[int, int, int]:
     return rank % pgrid[0], (rank // pgrid[0]) % pgrid[1], rank // (pgrid[0] * pgrid[1])
 
 
-def brick_bounds(glo, ghi, pgrid, rank):
-    """Bounds of the brick of `rank`: the global box cut into pgrid equal parts per axis."""
+def balanced_cuts(cost_zyx: np.ndarray, pgrid, min_cells: int = 1):
+    """Rectilinear load balance from the dem_cost_model field (Engine.dem_cost_model(), shape (nz, ny, nx) over the GLOBAL real-cell
+    grid): per axis, the cell indices at which the box is cut into pgrid[d] slabs so that the largest slab cost (marginal sum of the
+    axis) is as small as possible, every slab keeping at least `min_cells` cells.  Returns [cuts_x, cuts_y, cuts_z], each a list of
+    pgrid[d] + 1 increasing cell indices from 0 to n_d.
+
+    Stands in for exaNBody's load_balance_rcb on this path ("RCB by dem_cost_model weights"): tensor-product cuts keep the
+    26-neighbour brick topology the NVLink ghost path is built on, where RCB would give every brick an arbitrary set of neighbours.
+    The minimisation is exact (dynamic programme over the prefix sums, n_d <= a few hundred cells, <= 8 slabs)."""
+    cost = np.asarray(cost_zyx, dtype=np.float64)
+    out = []
+    for d in range(3):
+        axes = tuple(a for a in range(3) if a != 2 - d)          # array axis of x is 2, y 1, z 0
+        m = cost.sum(axis=axes)
+        n, parts = len(m), int(pgrid[d])
+        if parts * min_cells > n:
+            raise ValueError(f"balanced_cuts: axis {d} has {n} cells, cannot hold {parts} slabs of >= {min_cells} cells")
+        pre = np.concatenate([[0.0], np.cumsum(m)])
+        inf = float("inf")
+        best = np.full((parts + 1, n + 1), inf)
+        arg = np.zeros((parts + 1, n + 1), dtype=np.int64)
+        best[0, 0] = 0.0
+        for k in range(1, parts + 1):
+            for e in range(k * min_cells, n - (parts - k) * min_cells + 1):
+                b = np.arange((k - 1) * min_cells, e - min_cells + 1)
+                cand = np.maximum(best[k - 1, b], pre[e] - pre[b])
+                j = int(np.argmin(cand))                          # first minimum: ties go to the earliest cut (deterministic)
+                best[k, e], arg[k, e] = cand[j], b[j]
+        cuts, e = [n], n
+        for k in range(parts, 0, -1):
+            e = int(arg[k, e])
+            cuts.append(e)
+        out.append(cuts[::-1])
+    return out
+
+
+def cuts_to_positions(cuts, glo, ghi, global_cells):
+    """Cell-index cuts -> coordinates (the global cell grid is uniform: cell d has size (ghi - glo) / global_cells[d])."""
+    return [[glo[d] + (ghi[d] - glo[d]) * c / global_cells[d] for c in cuts[d]] for d in range(3)]
+
+
+def brick_bounds(glo, ghi, pgrid, rank, cuts=None):
+    """Bounds of the brick of `rank`: the global box cut into pgrid equal parts per axis, or at the coordinates `cuts`
+    (cuts[d] = pgrid[d] + 1 increasing positions from glo[d] to ghi[d], see balanced_cuts / cuts_to_positions)."""
     c = rank_coords(rank, pgrid)
+    if cuts is not None:
+        return tuple(float(cuts[d][c[d]]) for d in range(3)), tuple(float(cuts[d][c[d] + 1]) for d in range(3))
     lo, hi = [], []
     for d in range(3):
         ln = (ghi[d] - glo[d]) / pgrid[d]
@@ -46,13 +90,16 @@ def brick_bounds(glo, ghi, pgrid, rank):
     return tuple(lo), tuple(hi)
 
 
-def owner_rank(pos: np.ndarray, glo, ghi, pgrid) -> np.ndarray:
-    """Rank owning each position (N,3) — same rule as the device-side migration classifier."""
+def owner_rank(pos: np.ndarray, glo, ghi, pgrid, cuts=None) -> np.ndarray:
+    """Rank owning each position (N,3) — same rule as the device-side migration classifier (brick_of, kernels_migrate.cuh)."""
     r = np.zeros(len(pos), dtype=np.int64)
     mult = 1
     for d in range(3):
-        ln = (ghi[d] - glo[d]) / pgrid[d]
-        c = np.clip(np.floor((pos[:, d] - glo[d]) / ln).astype(np.int64), 0, pgrid[d] - 1)
+        if cuts is not None:
+            c = np.clip(np.searchsorted(np.asarray(cuts[d], dtype=np.float64), pos[:, d], side="right") - 1, 0, pgrid[d] - 1)
+        else:
+            ln = (ghi[d] - glo[d]) / pgrid[d]
+            c = np.clip(np.floor((pos[:, d] - glo[d]) / ln).astype(np.int64), 0, pgrid[d] - 1)
         r += mult * c
         mult *= pgrid[d]
     return r

@@ -288,6 +288,12 @@ int edb_stress_tensor(edb_context*, double* stress9);
  * the real particles; interaction totals over the waves (PartnerGhost records skipped, particle-particle waves counted twice when
  * `symetric`), active = dn < 0 or non-zero friction/moment history, min_dn over the active ones.  Values of THIS rank (the
  * reference's operator then MPI_Allreduce's them). */
+/* [dem_cost_model] src/interaction/dem_cost_model.cpp:63-92: per real cell of this rank's grid (x fastest, the ghost shell excluded)
+ * cost = 3 N + 1 + sum over the interaction records owned by the cell's particles of the type weight {1,3,5,4, 1,1,1, 1,3,5,4,3,5, 1}
+ * (types 0..13); with no interaction list built yet cost = 3 N + 1.  grid_dims[3] receives the real-cell grid dimensions; costs may
+ * be NULL to query them.  The values feed the load balancer (exaNBody load_balance_rcb; here exadem_b200.parallel.balanced_cuts). */
+int edb_dem_cost_model(edb_context*, int32_t grid_dims[3], double* costs, uint64_t cap);
+
 typedef struct edb_sim_state {
   double kinetic_energy[3], rotation_energy[3], mass, min_dn;
   uint64_t n_particles, n_active_interactions, n_total_interactions;

@@ -1541,6 +1541,38 @@ int orc_interaction_counts(orc_sim* h, uint64_t* counts, uint64_t* active) {
   }
   return 0;
 }
+// dem_cost_model.cpp:63-92: inner (non-ghost) cells only; cost = 3 N + 1 + sum of the type weights of the records stored with the
+// cell's particles (PartnerGhost copies live in ghost cells and are not seen); no list at all: 3 N + 1
+int orc_dem_cost_model(orc_sim* h, int32_t* grid_dims, double* costs, uint64_t cap) {
+  Sim& s = *(Sim*)h;
+  if (grid_dims) for (int d = 0; d < 3; d++) grid_dims[d] = s.nc[d];
+  if (!costs) return 0;
+  const size_t ncell = (size_t)s.nc[0] * s.nc[1] * s.nc[2];
+  if (cap < ncell) { s.err = "dem_cost_model: cost buffer smaller than the real-cell grid"; return EDB_ERR_CAPACITY; }
+  if (s.cstart.empty()) { s.err = "dem_cost_model: no cell grid yet"; return EDB_ERR_STATE; }
+  static const double weight[EDB_NTYPES] = {1, 3, 5, 4, 1, 1, 1, 1, 3, 5, 4, 3, 5, 1};
+  std::vector<double> per_particle(s.nreal, 0.0);
+  const bool skip_interaction = s.inter.empty() && s.bonds.empty();
+  if (!skip_interaction) {
+    for (const Inter& I : s.inter) {
+      if (I.ghost == 2) continue;   // stored in a ghost cell
+      const uint32_t o = I.owner();
+      if (o < s.nreal) per_particle[o] += weight[I.type];
+    }
+    for (const Sim::Bond& b : s.bonds)
+      if (b.ghost != 2 && b.i < s.nreal) per_particle[b.i] += weight[13];
+  }
+  for (int k = 1; k <= s.nc[2]; k++)
+    for (int j = 1; j <= s.nc[1]; j++)
+      for (int i = 1; i <= s.nc[0]; i++) {
+        const size_t c = s.cell_of(i, j, k);
+        const size_t n = s.cstart[c + 1] - s.cstart[c];
+        double cost = 3.0 * (double)n + 1.0;
+        for (size_t x = s.cstart[c]; x < s.cstart[c + 1]; x++) cost += per_particle[s.citems[x]];
+        costs[(size_t)(i - 1) + (size_t)s.nc[0] * ((size_t)(j - 1) + (size_t)s.nc[1] * (size_t)(k - 1))] = cost;
+      }
+  return 0;
+}
 int orc_export_interactions(orc_sim* h, edb_interaction* out, uint64_t cap, uint64_t* n) {
   Sim& s = *(Sim*)h;
   uint64_t k = 0;
