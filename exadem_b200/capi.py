@@ -587,6 +587,11 @@ class Engine:
         self._call("simulation_state", C.c_int32(1 if symetric else 0), C.byref(out))
         return out
 
+    def set_brick_cuts(self, cuts):
+        """Cost-balanced decomposition: cuts[d] = pgrid[d] + 1 increasing positions (None = uniform along d).  Before comm_init / upload."""
+        arr = [None if c is None else (C.c_double * len(c))(*[float(x) for x in c]) for c in cuts]
+        self._call("set_brick_cuts", *arr)
+
     def dem_cost_model(self):
         """[dem_cost_model] cost per real cell of this rank's grid, shape (nz, ny, nx) (x fastest like the reference's CellCosts)."""
         dims = (C.c_int32 * 3)()

@@ -1,9 +1,11 @@
 // comm.cuh — spatial decomposition over the GPUs of one box: ghost-layer plan + NCCL exchange (replaces the MPI path of
 // ghost_update_rq / UpdateGhostsNode, src/grid/update_ghosts.cu:46-63, and of migrate_cell_particles_interaction).
 //
-// Decomposition: uniform bricks on a pgrid[0] x pgrid[1] x pgrid[2] process grid, rank = x + px*(y + py*z).  Because all
-// bricks have the same cell grid, every rank can compute every other rank's ghost table locally, so the send lists need
-// no handshake: rank A sends, in B's enumeration order, exactly the cells B's table names as sources on A.
+// Decomposition: rectilinear bricks on a pgrid[0] x pgrid[1] x pgrid[2] process grid, rank = x + px*(y + py*z): uniform by default,
+// or cut at the per-axis positions of edb_set_brick_cuts (cost-balanced, exadem_b200.parallel.balanced_cuts).  The cuts are global
+// knowledge and a brick's cell grid follows from its bounds, so every rank can compute every other rank's ghost table locally and the
+// send lists need no handshake: rank A sends, in B's enumeration order, exactly the cells B's table names as sources on A.  (Tensor-
+// product cuts keep two face neighbours on the same transverse cell grid, so ghost cells still map one to one onto source cells.)
 // NCCL is resolved at run time (dlopen of the libnccl already loaded by torch, else the system one) so that the library
 // has no link-time dependency and a single NCCL instance lives in the process.
 #pragma once
@@ -311,6 +313,7 @@ struct Comm {
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
   int pg[3] = {1, 1, 1}, rc[3] = {0, 0, 0};
+  std::vector<double> cuts[3];   // per axis pg[d] + 1 cut positions (edb_set_brick_cuts); empty = uniform bricks
   uint32_t n_local_ghost = 0;
   std::map<int, Peer> peers;
   DevBuf<unsigned long long> d_red;
@@ -524,14 +527,18 @@ struct Comm {
     if (p2p.d_done) { cudaFree(p2p.d_done); p2p.d_done = nullptr; }
     if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
     comm = nullptr;
+    release_peers();
+    d_red.release();
+    d_gather.release();
+  }
+  void release_peers() {
     for (auto& kv : peers) {
       Peer& p = kv.second;
       p.d_rgcell.release(); p.d_rcnt.release(); p.d_roff.release(); p.d_scell.release(); p.d_scnt.release(); p.d_soff.release();
       p.d_smap.release(); p.d_sent.release(); p.d_sshift.release(); p.s_pr.release(); p.s_vm.release(); p.s_wg.release(); p.s_q.release();
       p.s_h.release(); p.s_id.release();
     }
-    d_red.release();
-    d_gather.release();
+    peers.clear();
   }
   static void coords(const int pg[3], int r, int out[3]) {
     out[0] = r % pg[0];
@@ -545,31 +552,41 @@ struct Comm {
     coords(pg, rank, rc);
     peers.clear();
   }
-  // source of ghost cell idx[] of the brick at coords `who` : returns false when there is none (non-periodic wall)
-  static bool source_of(const edb_config& cfg, const GridDev& G, const int pg[3], const int who[3], const int idx[3], int src[3],
-                        double shift[3], int* peer) {
+  // real cells along axis d of the bricks at coordinate `coord` of that axis (same rule as setup_grid; uniform bricks share ours)
+  int nc_axis(const edb_config& cfg, const GridDev& G, int d, int coord) const {
+    if (cuts[d].empty()) return G.nc[d];
+    const double len = cuts[d][coord + 1] - cuts[d][coord];
+    return std::max(1, (int)std::floor(len / cfg.cell_size + 1e-9));
+  }
+  // source of ghost cell idx[] of the brick at coords `who` : returns false when there is none (non-periodic wall).  src[] is a cell
+  // of the SOURCE brick's grid, src_g[] that grid's dimensions (with the ghost shell)
+  bool source_of(const edb_config& cfg, const GridDev& G, const int who[3], const int idx[3], int src[3], int src_g[3], double shift[3],
+                 int* peer) const {
     int rb[3];
     for (int d = 0; d < 3; d++) {
       rb[d] = who[d]; src[d] = idx[d]; shift[d] = 0.0;
+      const int gw = nc_axis(cfg, G, d, who[d]) + 2;
       if (idx[d] == 0) {
-        rb[d] = who[d] - 1; src[d] = G.nc[d];
+        rb[d] = who[d] - 1;
         if (rb[d] < 0) {
           if (!cfg.periodic[d]) return false;
           rb[d] = pg[d] - 1; shift[d] = -(cfg.ghi[d] - cfg.glo[d]);
         }
-      } else if (idx[d] == G.g[d] - 1) {
+        src[d] = nc_axis(cfg, G, d, rb[d]);
+      } else if (idx[d] == gw - 1) {
         rb[d] = who[d] + 1; src[d] = 1;
         if (rb[d] >= pg[d]) {
           if (!cfg.periodic[d]) return false;
           rb[d] = 0; shift[d] = cfg.ghi[d] - cfg.glo[d];
         }
       }
+      src_g[d] = nc_axis(cfg, G, d, rb[d]) + 2;
     }
     *peer = rb[0] + pg[0] * (rb[1] + pg[1] * rb[2]);
     return true;
   }
-  bool ghost_source(const edb_config& cfg, const GridDev& G, const int idx[3], int src[3], double shift[3], int* peer) const {
-    return source_of(cfg, G, pg, rc, idx, src, shift, peer);
+  bool ghost_source(const edb_config& cfg, const GridDev& G, const int idx[3], int src[3], int src_g[3], double shift[3], int* peer) const {
+    return source_of(cfg, G, rc, idx, src, src_g, shift, peer);
   }
   void plan_add_remote(int peer, uint32_t gcell, uint32_t scell, const double shift[3]) {
     Peer& p = peers[peer];
@@ -581,20 +598,23 @@ struct Comm {
     for (auto& kv : peers) kv.second.send.clear();
     for (int pr = 0; pr < nranks; pr++) {
       if (pr == rank) continue;
-      int who[3];
+      int who[3], gw[3];
       coords(pg, pr, who);
-      for (int k = 0; k < G.g[2]; k++)
-        for (int j = 0; j < G.g[1]; j++)
-          for (int i = 0; i < G.g[0]; i++) {
-            if (!(i == 0 || j == 0 || k == 0 || i == G.g[0] - 1 || j == G.g[1] - 1 || k == G.g[2] - 1)) continue;
+      for (int d = 0; d < 3; d++) gw[d] = nc_axis(cfg, G, d, who[d]) + 2;   // the RECEIVER's grid
+      for (int k = 0; k < gw[2]; k++)
+        for (int j = 0; j < gw[1]; j++)
+          for (int i = 0; i < gw[0]; i++) {
+            if (!(i == 0 || j == 0 || k == 0 || i == gw[0] - 1 || j == gw[1] - 1 || k == gw[2] - 1)) continue;
             const int idx[3] = {i, j, k};
-            int src[3], peer;
+            int src[3], src_g[3], peer;
             double shift[3];
-            if (!source_of(cfg, G, pg, who, idx, src, shift, &peer)) continue;
+            if (!source_of(cfg, G, who, idx, src, src_g, shift, &peer)) continue;
             if (peer != rank) continue;
+            if (src_g[0] != G.g[0] || src_g[1] != G.g[1] || src_g[2] != G.g[2])
+              throw StateError{EDB_ERR_INVALID, "brick cuts: this rank's bounds do not match the cuts (cell grids disagree)"};
             Peer& p = peers[pr];
             p.rank = pr;
-            const uint32_t cg = (uint32_t)i + G.g[0] * ((uint32_t)j + G.g[1] * (uint32_t)k);
+            const uint32_t cg = (uint32_t)i + gw[0] * ((uint32_t)j + gw[1] * (uint32_t)k);
             const uint32_t cs = (uint32_t)src[0] + G.g[0] * ((uint32_t)src[1] + G.g[1] * (uint32_t)src[2]);
             p.send.push_back(GhostEntry{cg, cs, {shift[0], shift[1], shift[2]}});
           }

@@ -309,12 +309,12 @@ static void setup_grid(edb_context* c) {
       for (int i = 0; i < G.g[0]; i++) {
         const int idx[3] = {i, j, k};
         if (!(i == 0 || j == 0 || k == 0 || i == G.g[0] - 1 || j == G.g[1] - 1 || k == G.g[2] - 1)) continue;
-        int src[3];
+        int src[3], src_g[3];
         double shift[3];
         int peer;
-        if (!c->comm.ghost_source(c->cfg, G, idx, src, shift, &peer)) continue;
+        if (!c->comm.ghost_source(c->cfg, G, idx, src, src_g, shift, &peer)) continue;
         const uint32_t cg = (uint32_t)i + G.g[0] * ((uint32_t)j + G.g[1] * (uint32_t)k);
-        const uint32_t csrc = (uint32_t)src[0] + G.g[0] * ((uint32_t)src[1] + G.g[1] * (uint32_t)src[2]);
+        const uint32_t csrc = (uint32_t)src[0] + src_g[0] * ((uint32_t)src[1] + src_g[1] * (uint32_t)src[2]);   // in the source brick's grid
         if (peer == c->cfg.rank) {
           gc.push_back(cg); gs.push_back(csrc);
           sh.push_back(shift[0]); sh.push_back(shift[1]); sh.push_back(shift[2]);
@@ -402,6 +402,36 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
   }
   *out = c;
   return EDB_OK;
+}
+
+// Cost-balanced decomposition: the bricks of the process grid are cut at these positions instead of uniformly (the reference's
+// load_balance_rcb fed by dem_cost_model; here tensor-product cuts, see comm.cuh).  Re-plans the ghost layer of this rank.
+extern "C" int edb_set_brick_cuts(edb_context* c, const double* cx, const double* cy, const double* cz) {
+  API_BEGIN(c)
+  if (c->nreal || c->comm.comm) throw StateError{EDB_ERR_STATE, "edb_set_brick_cuts: call before edb_comm_init and before the first upload"};
+  const double* in[3] = {cx, cy, cz};
+  int rc[3];
+  Comm::coords(c->comm.pg, c->cfg.rank, rc);
+  for (int d = 0; d < 3; d++) {
+    c->comm.cuts[d].clear();
+    if (!in[d]) continue;
+    const int pg = c->comm.pg[d];
+    if (pg + 1 > MAX_CUTS) throw StateError{EDB_ERR_INVALID, "edb_set_brick_cuts: more than 16 bricks along an axis"};
+    const double L = c->cfg.ghi[d] - c->cfg.glo[d], tol = 1e-9 * L;
+    if (std::fabs(in[d][0] - c->cfg.glo[d]) > tol || std::fabs(in[d][pg] - c->cfg.ghi[d]) > tol)
+      throw StateError{EDB_ERR_INVALID, "edb_set_brick_cuts: the first / last cut must be the global bounds"};
+    for (int k = 0; k < pg; k++)
+      if (!(in[d][k + 1] - in[d][k] >= c->cfg.cell_size * (1.0 - 1e-9)))
+        throw StateError{EDB_ERR_INVALID, "edb_set_brick_cuts: every brick must be at least one cell_size wide"};
+    if (std::fabs(in[d][rc[d]] - c->cfg.lo[d]) > tol || std::fabs(in[d][rc[d] + 1] - c->cfg.hi[d]) > tol)
+      throw StateError{EDB_ERR_INVALID, "edb_set_brick_cuts: this rank's lo / hi are not the cuts of its brick"};
+    c->comm.cuts[d].assign(in[d], in[d] + pg + 1);
+    c->comm.cuts[d][rc[d]] = c->cfg.lo[d];       // the brick's own bounds bit for bit (its cell grid is computed from them)
+    c->comm.cuts[d][rc[d] + 1] = c->cfg.hi[d];
+  }
+  c->comm.release_peers();
+  setup_grid(c);
+  API_END(c)
 }
 
 extern "C" int edb_destroy(edb_context* c) {
@@ -1091,6 +1121,8 @@ static uint32_t migrate(edb_context* c, uint32_t* n_live) {
   for (int d = 0; d < 3; d++) {
     B.glo[d] = c->cfg.glo[d]; B.ghi[d] = c->cfg.ghi[d]; B.pg[d] = c->comm.pg[d]; B.periodic[d] = c->cfg.periodic[d];
     B.len[d] = (c->cfg.ghi[d] - c->cfg.glo[d]) / c->comm.pg[d];
+    B.ncut[d] = (int)c->comm.cuts[d].size();
+    for (int k = 0; k < B.ncut[d]; k++) B.cut[d][k] = c->comm.cuts[d][k];
   }
   B.me = me;
   c->mig_dest.ensure(n + 1); c->mig_midx.ensure(n + 1);

@@ -24,17 +24,26 @@ struct MigRec {  // 72 B: one active interaction record of a migrating owner
 };
 static_assert(sizeof(MigPart) == 240 && sizeof(MigRec) == 72, "migration wire format");
 
+constexpr int MAX_CUTS = 17;   // pgrid[d] <= 16
 struct BrickMap {
-  double glo[3], ghi[3], len[3];  // global box, brick length per axis
+  double glo[3], ghi[3], len[3];  // global box, brick length per axis (uniform bricks)
+  double cut[3][MAX_CUTS];        // edb_set_brick_cuts: ncut[d] = pg[d] + 1 positions, 0 = uniform along d
+  int ncut[3];
   int pg[3], periodic[3];
   int me;
 };
 
-__device__ __forceinline__ int brick_of(const BrickMap& B, const double c[3]) {
+__host__ __device__ __forceinline__ int brick_of(const BrickMap& B, const double c[3]) {
   int r = 0, mult = 1;
 #pragma unroll
   for (int d = 0; d < 3; d++) {
-    int k = (int)floor((c[d] - B.glo[d]) / B.len[d]);
+    int k;
+    if (B.ncut[d]) {   // last cut <= c (bricks are [cut_k, cut_k+1))
+      k = 0;
+      for (int q = 1; q < B.ncut[d] - 1; q++) k += c[d] >= B.cut[d][q] ? 1 : 0;
+    } else {
+      k = (int)floor((c[d] - B.glo[d]) / B.len[d]);
+    }
     k = k < 0 ? 0 : (k > B.pg[d] - 1 ? B.pg[d] - 1 : k);
     r += mult * k;
     mult *= B.pg[d];

@@ -1,9 +1,10 @@
-"""Host-side plumbing of the multi-GPU path: uniform brick decomposition of the global box over the GPUs of one node
-and the NCCL bootstrap (one process per GPU; torch.distributed only carries the 128-byte NCCL unique id and the
+"""Host-side plumbing of the multi-GPU path: brick decomposition of the global box over the GPUs of one node (uniform, or cut
+at cost-balanced positions: balanced_cuts / Engine.set_brick_cuts) and the NCCL bootstrap (one process per GPU; torch.distributed only carries the 128-byte NCCL unique id and the
 scalar reductions of bench.py — the per-step ghost exchange itself runs inside libexadem_b200 over NCCL/NVLink).
 
 Replaces, for this path, the reference's MPI spatial decomposition (exaNBody `load_balance_rcb` + `UpdateGhostsNode`,
-SURVEY.md 2d/2e): uniform bricks instead of RCB (the benchmark boxes are uniform), same 1-cell ghost layer.
+SURVEY.md 2d/2e): rectilinear bricks instead of RCB — uniform for the benchmark boxes, cost-balanced per axis from the
+dem_cost_model field otherwise —, same 1-cell ghost layer.
 """
 from __future__ import annotations
 
@@ -198,6 +199,21 @@ def brick_config(wl, rank: int, nranks: int, device: int = 0):
     return capi.make_config(wl.lo, wl.hi, cs, wl.periodic, wl.mode, device, glo=glo, ghi=ghi, rank=rank, nranks=nranks, pgrid=pg)
 
 
+def balanced_decomposition(positions, glo, ghi, cell_size, pgrid, cost_zyx=None, min_cells=1):
+    """Cut positions of a cost-balanced decomposition.  `cost_zyx` is the dem_cost_model field over the global real-cell grid
+    (nz, ny, nx); when None the cost of a cell is 3 N + 1 from the particle positions — what dem_cost_model returns before any
+    interaction list exists (dem_cost_model.cpp:74-77).  Returns (cuts as coordinates per axis, global cell counts)."""
+    gcells, _ = grid_dims(glo, ghi, cell_size)
+    if cost_zyx is None:
+        pos = np.asarray(positions)
+        idx = [np.clip(np.floor((pos[:, d] - glo[d]) / ((ghi[d] - glo[d]) / gcells[d])).astype(np.int64), 0, gcells[d] - 1) for d in range(3)]
+        cnt = np.zeros((gcells[2], gcells[1], gcells[0]))
+        np.add.at(cnt, (idx[2], idx[1], idx[0]), 1.0)
+        cost_zyx = 3.0 * cnt + 1.0
+    cuts = balanced_cuts(cost_zyx, pgrid, min_cells=min_cells)
+    return cuts_to_positions(cuts, glo, ghi, gcells), gcells, cuts
+
+
 def init_comm(engine, lib, rank: int):
     """Broadcast rank 0's NCCL unique id through torch.distributed and create the library's communicator."""
     import torch
@@ -223,10 +239,18 @@ def grid_dims(lo, hi, cell_size):
     return nc, cs
 
 
-def ghost_plan(glo, ghi, periodic, pgrid, rank, nc):
+def cells_per_brick(cuts, cell_size, pgrid):
+    """nc_axis[d][coord] = real cells along axis d of the bricks at that coordinate (same rule as the library's setup_grid)."""
+    return [[max(1, int(np.floor((cuts[d][k + 1] - cuts[d][k]) / cell_size + 1e-9))) for k in range(pgrid[d])] for d in range(3)]
+
+
+def ghost_plan(glo, ghi, periodic, pgrid, rank, nc, nc_axis=None):
     """List of (ghost cell ijk, source rank, source cell ijk, shift) for the brick of `rank` (cells are 1-based inside
-    the ghost-shelled local grid, like the device code)."""
+    the ghost-shelled local grid, like the device code).  `nc_axis` (cells_per_brick) describes bricks cut at non-uniform
+    positions: the grid of `rank` and of the source bricks then come from it and `nc` is ignored."""
     me = rank_coords(rank, pgrid)
+    if nc_axis is not None:
+        nc = [nc_axis[d][me[d]] for d in range(3)]
     g = [n + 2 for n in nc]
     plan = []
     for k in range(g[2]):
@@ -239,13 +263,13 @@ def ghost_plan(glo, ghi, periodic, pgrid, rank, nc):
                 for d in range(3):
                     if idx[d] == 0:
                         rb[d] -= 1
-                        src[d] = nc[d]
                         if rb[d] < 0:
                             if not periodic[d]:
                                 ok = False
                                 break
                             rb[d] = pgrid[d] - 1
                             shift[d] = -(ghi[d] - glo[d])
+                        src[d] = nc[d] if nc_axis is None else nc_axis[d][rb[d]]   # last real cell of the SOURCE brick
                     elif idx[d] == g[d] - 1:
                         rb[d] += 1
                         src[d] = 1
@@ -260,25 +284,25 @@ def ghost_plan(glo, ghi, periodic, pgrid, rank, nc):
     return plan
 
 
-def send_plan(glo, ghi, periodic, pgrid, rank, nc):
+def send_plan(glo, ghi, periodic, pgrid, rank, nc, nc_axis=None):
     """What `rank` must SEND: for every other rank, the entries of THAT rank's ghost plan whose source is `rank`, in that
-    rank's enumeration order (every brick has the same cell grid, so no handshake is needed) — mirrors
+    rank's enumeration order (every rank can compute every brick's cell grid, so no handshake is needed) — mirrors
     Comm::plan_send_lists in csrc/comm.cuh."""
     nranks = pgrid[0] * pgrid[1] * pgrid[2]
     out = {}
     for other in range(nranks):
         if other == rank:
             continue
-        ent = [(g, s, sh) for (g, src_rank, s, sh) in ghost_plan(glo, ghi, periodic, pgrid, other, nc) if src_rank == rank]
+        ent = [(g, s, sh) for (g, src_rank, s, sh) in ghost_plan(glo, ghi, periodic, pgrid, other, nc, nc_axis) if src_rank == rank]
         if ent:
             out[other] = ent
     return out
 
 
-def recv_plan(glo, ghi, periodic, pgrid, rank, nc):
+def recv_plan(glo, ghi, periodic, pgrid, rank, nc, nc_axis=None):
     """What `rank` RECEIVES, per source rank, in its own enumeration order (local periodic images excluded)."""
     out = {}
-    for (g, src_rank, s, sh) in ghost_plan(glo, ghi, periodic, pgrid, rank, nc):
+    for (g, src_rank, s, sh) in ghost_plan(glo, ghi, periodic, pgrid, rank, nc, nc_axis):
         if src_rank != rank:
             out.setdefault(src_rank, []).append((g, s, sh))
     return out

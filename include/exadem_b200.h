@@ -288,6 +288,12 @@ int edb_stress_tensor(edb_context*, double* stress9);
  * the real particles; interaction totals over the waves (PartnerGhost records skipped, particle-particle waves counted twice when
  * `symetric`), active = dn < 0 or non-zero friction/moment history, min_dn over the active ones.  Values of THIS rank (the
  * reference's operator then MPI_Allreduce's them). */
+/* Cost-balanced decomposition (the reference's `load_balance_rcb` step of load_balancing_if_triggered, config_move_particles.msp:114-139,
+ * fed by dem_cost_model): the bricks of the process grid are bounded by the per-axis cut positions c{x,y,z}[0..pgrid[d]] (first = glo,
+ * last = ghi, NULL = uniform along that axis) instead of equal parts; this rank's lo/hi must be the cuts of its own brick.  Call on every
+ * rank with the same cuts, before edb_comm_init and before the first upload. */
+int edb_set_brick_cuts(edb_context*, const double* cx, const double* cy, const double* cz);
+
 /* [dem_cost_model] src/interaction/dem_cost_model.cpp:63-92: per real cell of this rank's grid (x fastest, the ghost shell excluded)
  * cost = 3 N + 1 + sum over the interaction records owned by the cell's particles of the type weight {1,3,5,4, 1,1,1, 1,3,5,4,3,5, 1}
  * (types 0..13); with no interaction list built yet cost = 3 N + 1.  grid_dims[3] receives the real-cell grid dimensions; costs may

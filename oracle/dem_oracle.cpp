@@ -140,11 +140,18 @@ struct Sim {
   // vb[0] x vb[1] x vb[2] bricks of whole cells and a neighbour cell of ANOTHER brick is treated exactly like the ghost
   // cell it would be on the owning MPI rank of the reference (pair enumerated from both sides, partner force discarded).
   int vb[3]{1, 1, 1};
+  std::vector<int> vcut[3];   // non-uniform virtual bricks: vb[d] + 1 cell indices (0 .. nc[d]) per axis, empty = equal parts
   int brick_of_cell(int i, int j, int k) const {
     const int c[3] = {i, j, k};
     int r = 0, mult = 1;
     for (int d = 0; d < 3; d++) {
-      int b = (c[d] - 1) / (nc[d] / vb[d]);
+      int b;
+      if (!vcut[d].empty()) {
+        b = 0;
+        for (int q = 1; q < vb[d]; q++) b += (c[d] - 1) >= vcut[d][q] ? 1 : 0;
+      } else {
+        b = (c[d] - 1) / (nc[d] / vb[d]);
+      }
       b = b < 0 ? 0 : (b > vb[d] - 1 ? vb[d] - 1 : b);
       r += mult * b;
       mult *= vb[d];
@@ -193,8 +200,13 @@ static void build_grid(Sim& s) {
     s.cs[d] = (s.cfg.hi[d] - s.cfg.lo[d]) / s.nc[d];
     s.g[d] = s.nc[d] + 2;
   }
-  for (int d = 0; d < 3; d++)
+  for (int d = 0; d < 3; d++) {
+    if (!s.vcut[d].empty()) {
+      if ((int)s.vcut[d].size() != s.vb[d] + 1 || s.vcut[d].front() != 0 || s.vcut[d].back() != s.nc[d]) { s.err = "virtual brick cuts do not span the grid"; s.vcut[d].clear(); s.vb[d] = 1; }
+      continue;
+    }
     if (s.nc[d] % s.vb[d]) { s.err = "virtual bricks must hold a whole number of cells"; s.vb[d] = 1; }
+  }
   s.resize_particles(s.nreal);
   wrap_positions(s);
   const size_t ncell = (size_t)s.g[0] * s.g[1] * s.g[2];
@@ -773,6 +785,16 @@ int orc_destroy(orc_sim* h) { delete (Sim*)h; return 0; }
 int orc_set_virtual_bricks(orc_sim* h, const int32_t* pg) {
   Sim& s = *(Sim*)h;
   for (int d = 0; d < 3; d++) s.vb[d] = pg[d] < 1 ? 1 : pg[d];
+  return 0;
+}
+// virtual bricks bounded by cell-index cuts (vb[d] + 1 entries per axis; NULL = equal parts): the emulation of edb_set_brick_cuts
+int orc_set_virtual_cuts(orc_sim* h, const int32_t* cx, const int32_t* cy, const int32_t* cz) {
+  Sim& s = *(Sim*)h;
+  const int32_t* in[3] = {cx, cy, cz};
+  for (int d = 0; d < 3; d++) {
+    s.vcut[d].clear();
+    if (in[d]) s.vcut[d].assign(in[d], in[d] + s.vb[d] + 1);
+  }
   return 0;
 }
 int orc_set_threads(orc_sim* h, int n) { ((Sim*)h)->omp_threads = n < 1 ? 1 : n; return 0; }

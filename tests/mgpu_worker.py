@@ -55,6 +55,8 @@ def main():
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--then-ops", type=int, default=0, help="after run_verlet, this many more steps operator by operator")
     ap.add_argument("--dump", default=None, help="write the ContactState view of wave 0 right after run_verlet to <dump>.rank<r>.npz")
+    ap.add_argument("--balanced", action="store_true", help="thin the particles out on one side of the box and cut the bricks where "
+                    "dem_cost_model's cost field balances (edb_set_brick_cuts) instead of uniformly")
     ap.add_argument("--moving", action="store_true", help="add a stress-controlled floor (surface, LINEAR_COMPRESSIVE_MOTION): reaction all-reduce")
     args = ap.parse_args()
 
@@ -77,14 +79,26 @@ def main():
         wl.drivers = list(wl.drivers) + [dict(kind=capi.DRIVER_SURFACE, offset=0.03, normal=(0, 0, 1), center=(0, 0, 0.03))]
         wl.motions = [dict(motion_type="STATIONARY")] * (len(wl.drivers) - 1) + [
             dict(motion_type="LINEAR_COMPRESSIVE_MOTION", motion_vector=(0, 0, -1), sigma=2000.0, damprate=0.0, surface=area)]
+    cuts = cell_cuts = None
+    if args.balanced:
+        # a heap on the low-x side: 35 % of the particles of the upper half of the box are kept.  The cost field is dem_cost_model's
+        # before any list exists (3 N + 1 per global cell); the cuts minimise the largest brick cost per axis, whole global cells
+        r = wl.particles.vec("r")
+        rng = np.random.default_rng(0xD3B9)
+        keep = (r[:, 0] < 0.5 * (wl.lo[0] + wl.hi[0])) | (rng.random(wl.particles.n) < 0.35)
+        wl.particles = parallel.select(wl.particles, keep)
+        cuts, gcells, cell_cuts = parallel.balanced_decomposition(wl.particles.vec("r"), wl.lo, wl.hi, wl.effective_cell_size(), pg, min_cells=2)
+        assert any(len(set(np.diff(c))) > 1 for c in cell_cuts), f"the balanced cuts came out uniform: {cell_cuts}"
     system_mass = float(wl.particles.mass.sum())
     pos = wl.particles.vec("r")
-    mine = parallel.owner_rank(pos, wl.lo, wl.hi, pg) == rank
-    lo, hi = parallel.brick_bounds(wl.lo, wl.hi, pg, rank)
+    mine = parallel.owner_rank(pos, wl.lo, wl.hi, pg, cuts) == rank
+    lo, hi = parallel.brick_bounds(wl.lo, wl.hi, pg, rank, cuts)
     cfg = capi.make_config(lo, hi, wl.effective_cell_size(), wl.periodic, wl.mode, local, glo=wl.lo, ghi=wl.hi, rank=rank,
                            nranks=world, pgrid=pg)
     lib = Library()
     eng = Engine(lib, cfg)
+    if cuts is not None:
+        eng.set_brick_cuts(cuts)
     parallel.init_comm(eng, lib, rank)
     eng.set_law(wl.law)
     eng.set_contact_params(wl.params, wl.params_driver)
@@ -131,6 +145,8 @@ def main():
         ref = wl.setup(OracleEngine(OracleLibrary(), wl.config()))
         ref.set_threads(os.cpu_count() or 1)
         ref.set_virtual_bricks(pg)   # same both-sides enumeration of brick-straddling pairs as the N ranks (quirk Q6)
+        if cell_cuts is not None:
+            ref.set_virtual_cuts(cell_cuts)
         if wl.motions:
             ref.set_system_mass(system_mass)
         ref.update_particle_neighbors(wl.rcut_inc, sym)
@@ -182,6 +198,10 @@ def main():
             cb = rr
             active = int((np.abs(cb["friction"]).sum(axis=1) > 0).sum())
             moved = sum(abs(c - counts[0]) for c in counts)
+            if cell_cuts is not None:
+                uni = np.bincount(parallel.owner_rank(pos, wl.lo, wl.hi, pg), minlength=world)
+                print(f"balanced cuts (cells) {cell_cuts}: particles per rank {counts} (uniform bricks would hold {uni.tolist()})", flush=True)
+                assert max(counts) < max(uni), "the balanced decomposition is not better than the uniform one"
             print(f"mgpu parity OK: {world} GPUs pgrid={pg} mode={args.mode} particles={pr.n} per-rank={counts} rebuilds={nreb_ref} "
                   f"interactions={n} (active {active}) max field err={max(errs.values()):.2e}", flush=True)
         except AssertionError as e:

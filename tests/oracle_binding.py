@@ -43,6 +43,11 @@ class OracleEngine(capi.Engine):
         """Multi-rank emulation: treat cells of another brick like the ghost cells they would be on the owning rank."""
         self._call("set_virtual_bricks", (C.c_int32 * 3)(*pgrid))
 
+    def set_virtual_cuts(self, cell_cuts):
+        """Virtual bricks bounded by cell-index cuts per axis (after set_virtual_bricks): emulates Engine.set_brick_cuts."""
+        arr = [None if c is None else (C.c_int32 * len(c))(*[int(x) for x in c]) for c in cell_cuts]
+        self._call("set_virtual_cuts", *arr)
+
     def set_particle_clusters(self, ids, cluster):
         """field::cluster per particle id (oracle-only input of stick_polyhedra)."""
         import numpy as np

@@ -65,6 +65,16 @@ def test_two_gpu_drum_slabs():
     _run(2, "--mode", "drum", "--steps", "60", "--rebuild-every", "0")
 
 
+@pytest.mark.parametrize("mode", ["sphere", "poly"])
+def test_two_gpu_cost_balanced_cuts(mode):
+    """Bricks cut where the dem_cost_model field balances (edb_set_brick_cuts) instead of uniformly: a box with a heap on one side, the
+    two bricks hold different cell grids (3 + 5 cells along x), particles migrate across the cut, polyhedron twins cross it — same parity
+    bar against the oracle, whose virtual bricks are cut at the same cells."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, "--mode", mode, "--steps", "60", "--rebuild-every", "10", "--balanced")
+
+
 @pytest.mark.parametrize("env", [{}, {"EDB_DRIVERS_UNFUSED": "1"}], ids=["fused-loop", "operator-loop"])
 def test_two_gpu_moving_driver(env):
     """A stress-controlled floor under a two-brick box: the reaction of the contacts is all-reduced (NCCL) before force_to_accel_driver,

@@ -24,7 +24,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, periodic, ret):
+def _worker(rank, world, port, periodic, ret, balanced=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -33,9 +33,17 @@ def _worker(rank, world, port, periodic, ret):
         side = [10.0 * pg[d] for d in range(3)]
         wl = workloads.spheres_box(tuple(int(s) for s in side), jitter=0.03, seed=7, periodic=periodic)
         glo, ghi = wl.lo, wl.hi
+        cuts = nc_axis = None
+        if balanced:   # a heap on the low side of x and y: bricks cut where the 3 N + 1 cost balances, different cell grids per brick
+            r = wl.particles.vec("r")
+            keep = ((r[:, 0] < 0.5 * side[0]) & (r[:, 1] < 0.6 * side[1])) | (np.random.default_rng(3).random(wl.particles.n) < 0.3)
+            wl.particles = parallel.select(wl.particles, keep)
+            cuts, gcells, cell_cuts = parallel.balanced_decomposition(wl.particles.vec("r"), glo, ghi, 2.5, pg, min_cells=1)
+            assert any(len(set(np.diff(c))) > 1 for c in cell_cuts), cell_cuts
+            nc_axis = parallel.cells_per_brick(cuts, 2.5, pg)
         pos = wl.particles.vec("r")
-        mine = parallel.owner_rank(pos, glo, ghi, pg) == rank
-        lo, hi = parallel.brick_bounds(glo, ghi, pg, rank)
+        mine = parallel.owner_rank(pos, glo, ghi, pg, cuts) == rank
+        lo, hi = parallel.brick_bounds(glo, ghi, pg, rank, cuts)
         assert all(lo[d] <= pos[mine][:, d].min() and pos[mine][:, d].max() < hi[d] + 1e-12 for d in range(3))
         # (i) exact partition
         t = torch.tensor([int(mine.sum()), int(wl.particles.id[mine].sum())], dtype=torch.int64)
@@ -43,8 +51,10 @@ def _worker(rank, world, port, periodic, ret):
         assert int(t[0]) == wl.particles.n and int(t[1]) == int(wl.particles.id.sum())
         # (ii) send list == the peer's recv list
         nc, cs = parallel.grid_dims(lo, hi, 2.5)
-        sp = parallel.send_plan(glo, ghi, periodic, pg, rank, nc)
-        rp = parallel.recv_plan(glo, ghi, periodic, pg, rank, nc)
+        if nc_axis is not None:
+            assert nc == [nc_axis[d][parallel.rank_coords(rank, pg)[d]] for d in range(3)]
+        sp = parallel.send_plan(glo, ghi, periodic, pg, rank, nc, nc_axis)
+        rp = parallel.recv_plan(glo, ghi, periodic, pg, rank, nc, nc_axis)
         plans = [None] * world
         dist.all_gather_object(plans, {"send": sp, "recv": rp})
         for other in range(world):
@@ -60,7 +70,7 @@ def _worker(rank, world, port, periodic, ret):
         cells_all = [None] * world
         dist.all_gather_object(cells_all, local)
         got = []
-        for (g, src_rank, s, sh) in parallel.ghost_plan(glo, ghi, periodic, pg, rank, nc):
+        for (g, src_rank, s, sh) in parallel.ghost_plan(glo, ghi, periodic, pg, rank, nc, nc_axis):
             for r in cells_all[src_rank].get(tuple(s), []):
                 got.append(r + np.array(sh))
         got = np.array(got) if got else np.zeros((0, 3))
@@ -93,12 +103,15 @@ def _worker(rank, world, port, periodic, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,periodic", [(2, (1, 1, 1)), (2, (1, 0, 1)), (4, (1, 1, 0))])
-def test_brick_plan_gloo(world, periodic):
+@pytest.mark.parametrize("world,periodic,balanced", [(2, (1, 1, 1), False), (2, (1, 0, 1), False), (4, (1, 1, 0), False),
+                                                     (2, (1, 1, 1), True), (4, (1, 1, 0), True)])
+def test_brick_plan_gloo(world, periodic, balanced):
+    """balanced: the bricks are cut at the cost-balanced positions (parallel.balanced_cuts), so neighbouring bricks hold different
+    cell grids; the ghost plan must still reproduce the single-domain periodic images."""
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, periodic, ret)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, periodic, ret, balanced)) for r in range(world)]
     for p_ in procs:
         p_.start()
     for p_ in procs:
