@@ -167,9 +167,15 @@ struct edb_context {
   // asynchronous host <-> device path of a host-owned grid (edb_upload_dynamic_async / edb_download_dynamic_async): own copy
   // streams so that the download of step n, the upload of step n+1 and the kernels of step n+1 overlap on a full-duplex link
   cudaStream_t st_up = nullptr, st_dn = nullptr;
+  cudaStream_t st_flag = nullptr;      // high-priority side stream that publishes the rebuild trigger while asynchronous host copies run
+  cudaEvent_t ev_flag_src = nullptr;
   cudaEvent_t ev_up_done = nullptr, ev_up_consumed = nullptr, ev_dn_ready[2] = {}, ev_dn_done[2] = {}, ev_field[22] = {};
   bool up_consumed_valid = false, dn_done_valid[2] = {false, false}, field_valid[22] = {};
   int dn_parity = 0;
+  // EDB_TRACE_ASYNC: timed events at the ends of every upload / step / download of the asynchronous copy pipeline, printed at destroy
+  bool env_flag_on_stream = false;   // EDB_FLAG_ON_STREAM: the round-2 first form (8-byte copy on the compute stream), for comparison
+  bool trace_async = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
   DevBuf<double> stage_up, stage_dn[2];
   // staging for host transfers
   DevBuf<double> stage;
@@ -358,6 +364,8 @@ extern "C" int edb_create(const edb_config* cfg, edb_context** out) {
   c->env_nbh_two_pass = getenv("EDB_NBH_TWO_PASS") != nullptr;
   c->env_nbh_no_cull = getenv("EDB_NBH_NO_CULL") != nullptr;
   c->env_nbh_warp = getenv("EDB_NBH_WARP") != nullptr;
+  c->trace_async = getenv("EDB_TRACE_ASYNC") != nullptr;
+  c->env_flag_on_stream = getenv("EDB_FLAG_ON_STREAM") != nullptr;
   c->env_land_copy = getenv("EDB_LAND_COPY") != nullptr;
   c->env_gather_mail = getenv("EDB_GATHER_MAIL") != nullptr;
   c->env_nbh_per_thread = getenv("EDB_NBH_POLY_PER_THREAD") != nullptr;
@@ -434,11 +442,14 @@ extern "C" int edb_set_brick_cuts(edb_context* c, const double* cx, const double
   API_END(c)
 }
 
+static void trace_dump(edb_context* c);
 extern "C" int edb_destroy(edb_context* c) {
   if (!c) return EDB_ERR_INVALID;
   cudaSetDevice(c->cfg.device);
   cudaStreamSynchronize(c->st);
   if (c->st2) { cudaStreamSynchronize(c->st2); cudaStreamDestroy(c->st2); }
+  trace_dump(c);
+  if (c->st_flag) { cudaStreamSynchronize(c->st_flag); cudaStreamDestroy(c->st_flag); cudaEventDestroy(c->ev_flag_src); }
   if (c->st_up) {
     cudaStreamSynchronize(c->st_up); cudaStreamSynchronize(c->st_dn);
     cudaStreamDestroy(c->st_up); cudaStreamDestroy(c->st_dn);
@@ -984,6 +995,25 @@ extern "C" int edb_download_dynamic(edb_context* c, edb_particles* P) {
 }
 
 // ---- asynchronous forms (pinned host buffers) ------------------------------------------------------------------------------------
+static void trace_mark(edb_context* c, const char* what, cudaStream_t s) {
+  if (!c->trace_async || c->trace_ev.size() > 4000) return;
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(e, s));
+  c->trace_ev.push_back({what, e});
+}
+static void trace_dump(edb_context* c) {
+  if (c->trace_ev.empty()) return;
+  cudaDeviceSynchronize();
+  const size_t n = c->trace_ev.size(), from = n > 160 ? n - 160 : 0;
+  for (size_t k = from; k < n; k++) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->trace_ev[from].second, c->trace_ev[k].second);
+    fprintf(stderr, "[edb trace] %10.4f ms  %s\n", ms, c->trace_ev[k].first);
+  }
+  for (auto& e : c->trace_ev) cudaEventDestroy(e.second);
+  c->trace_ev.clear();
+}
 static void async_streams(edb_context* c) {
   if (c->st_up) return;
   CK(cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking));
@@ -1007,6 +1037,8 @@ extern "C" int edb_upload_dynamic_async(edb_context* c, const edb_particles* P) 
   if (c->stage_up.cap < 13 * n + 1) { quiesce(c); c->stage_up.ensure(13 * n + 1); }
   // the staging area is free once the scatter kernel of the previous upload has read it
   if (c->up_consumed_valid) CK(cudaStreamWaitEvent(c->st_up, c->ev_up_consumed, 0));
+  if (c->field_valid[0]) CK(cudaStreamWaitEvent(c->st_up, c->ev_field[0], 0));
+  trace_mark(c, "upload begin (field 0 of the previous download landed)", c->st_up);
   for (int i = 0; i < 13; i++) {
     // the same host array may still be the target of the previous asynchronous download: field by field, so that on a full-duplex
     // link this upload runs one field behind that download instead of after it
@@ -1014,8 +1046,10 @@ extern "C" int edb_upload_dynamic_async(edb_context* c, const edb_particles* P) 
     CK(cudaMemcpyAsync(c->stage_up.p + (size_t)i * n, f[i], n * 8, cudaMemcpyHostToDevice, c->st_up));
   }
   CK(cudaEventRecord(c->ev_up_done, c->st_up));
+  trace_mark(c, "upload end", c->st_up);
   CK(cudaStreamWaitEvent(c->st, c->ev_up_done, 0));
   LAUNCH(c, k_scatter_dynamic, nblk(n), BLK, 0, view(c->pa), c->stage_up.p, (uint32_t)n);
+  trace_mark(c, "scatter end", c->st);
   CK(cudaEventRecord(c->ev_up_consumed, c->st));
   c->up_consumed_valid = true;
   API_END(c)
@@ -1029,9 +1063,11 @@ extern "C" int edb_download_dynamic_async(edb_context* c, edb_particles* P, uint
   if (c->stage_dn[par].cap < 22 * n + 1) { quiesce(c); c->stage_dn[par].ensure(22 * n + 1); }
   // two staging areas: the snapshot of step n+1 is taken while the copy of step n is still draining
   if (c->dn_done_valid[par]) CK(cudaStreamWaitEvent(c->st, c->ev_dn_done[par], 0));
+  trace_mark(c, "step end (download requested)", c->st);
   LAUNCH(c, k_gather_dynamic, nblk(n), BLK, 0, view(c->pa), c->stage_dn[par].p, (uint32_t)n);
   CK(cudaEventRecord(c->ev_dn_ready[par], c->st));
   CK(cudaStreamWaitEvent(c->st_dn, c->ev_dn_ready[par], 0));
+  trace_mark(c, "download begin", c->st_dn);
   double* f[22] = {P->rx, P->ry, P->rz, P->vx, P->vy, P->vz, P->vrotx, P->vroty, P->vrotz, P->qw, P->qx, P->qy, P->qz,
                    P->fx, P->fy, P->fz, P->momx, P->momy, P->momz, P->arotx, P->aroty, P->arotz};
   // groups: bit 0 r, 1 v, 2 vrot, 3 orient, 4 f (acceleration), 5 mom, 6 arot
@@ -1043,6 +1079,7 @@ extern "C" int edb_download_dynamic_async(edb_context* c, edb_particles* P, uint
     c->field_valid[i] = true;
   }
   CK(cudaEventRecord(c->ev_dn_done[par], c->st_dn));
+  trace_mark(c, "download end", c->st_dn);
   c->dn_done_valid[par] = true;
   API_END(c)
 }
@@ -1957,10 +1994,28 @@ __global__ void k_publish_flag(unsigned long long* __restrict__ host_mapped, con
 }
 static void trigger_publish(edb_context* c, int slot) {
   // A one-thread kernel stores the flag into mapped host memory: an 8-byte cudaMemcpyAsync between two kernels costs the stream a
-  // round trip through the copy engine (measured: 0.219 -> 0.210 ms per step on the 1 M drum).  Not while the asynchronous host
-  // copies of a host-owned grid are in flight: the SM's store then queues behind megabytes of DMA on the PCIe link and the kernel —
-  // and every kernel of the step behind it — waits for it (measured: e2e 4.2 -> 6.4 ms per step), so that path keeps the copy.
+  // round trip through the copy engine (measured: 0.219 -> 0.210 ms per step on the 1 M drum).
+  // While the asynchronous host copies of a host-owned grid are in flight neither form may sit on the compute stream: the 8-byte copy
+  // queues in the copy engine behind the 176 MB download of the previous step and the SM's store (with its system-scope fence) behind
+  // the same bytes on the link, and every kernel of the step waits behind it (EDB_TRACE_ASYNC: the step ended 0.22 ms after the
+  // previous download instead of 1 ms before it; with the store on the stream: e2e 4.2 -> 6.4 ms per step).  The store then goes to a
+  // high-priority side stream: the step's kernels run at once, only the host's wait for the flag sees the link.
   if (c->flag_published) c->flag_published = false;   // (k_ghost_land of this step stored it)
+  else if (c->st_up && !c->env_flag_on_stream) {
+    if (!c->st_flag) {
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&c->st_flag, cudaStreamNonBlocking, hi));
+      CK(cudaEventCreateWithFlags(&c->ev_flag_src, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(c->ev_flag_src, c->st));
+    CK(cudaStreamWaitEvent(c->st_flag, c->ev_flag_src, 0));
+    k_publish_flag<<<1, 1, 0, c->st_flag>>>(c->h_sflag_dev + slot, c->d_sflag + slot);
+    CK(cudaGetLastError());
+    c->ctr.kernel_launches++;
+    CK(cudaEventRecord(c->ev_sflag[slot], c->st_flag));
+    return;
+  }
   else if (c->st_up) CK(cudaMemcpyAsync(c->h_sflag + slot, c->d_sflag + slot, 8, cudaMemcpyDeviceToHost, c->st));
   else LAUNCH(c, k_publish_flag, 1, 1, 0, c->h_sflag_dev + slot, c->d_sflag + slot);
   CK(cudaEventRecord(c->ev_sflag[slot], c->st));
