@@ -35,6 +35,13 @@ namespace edb {
 #ifndef EDB_NPC_NI
 #define EDB_NPC_NI 0
 #endif
+// EDB_NPC_HOIST bit 0: the owner's world OBB is computed once per owner and kept in shared memory (every OBB round and every
+// vertex-of-b prefilter round used to rebuild it per lane: four quaternion rotations); bit 1: the candidates' world OBBs of an OBB
+// round stay in the registers of the lane that tested them and the vertex-of-a prefilter rounds fetch them by shuffle instead of
+// rebuilding them per lane.  Same values from the same functions on the same inputs: the candidate set is unchanged.
+#ifndef EDB_NPC_HOIST
+#define EDB_NPC_HOIST 1
+#endif
 constexpr int NPC_THREADS = EDB_NPC_THREADS;
 // EDB_NPC_PARTS > 1: a warp's work item in the count pass is 1/NPC_PARTS of an owner's stencil (a contiguous range of 32-candidate
 // chunks) instead of the whole owner; every part writes its own stream, the counts are added per owner, the replay walks the parts
@@ -185,6 +192,9 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
   __shared__ uint8_t s_cgc[27];
   __shared__ uint16_t s_queue[NPC_THREADS / 32][64];
   __shared__ uint32_t s_vmask[NPC_THREADS / 32][2][32];   // vertex-vs-OBB prefilter masks (mA, mB) of the pairs of one OBB round
+#if EDB_NPC_HOIST & 1
+  __shared__ double s_oa[NPC_THREADS / 32][16];           // the owner's world OBB (c, e1, e2, e3, ext), not enlarged
+#endif
 
   const GridDev& G = A.G;
   const uint32_t c = blockIdx.x;
@@ -267,6 +277,24 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
     double bnda = 0.0;
     if (lane < sa.nv) bnda = norm(va[lane] - mk3(ra.x, ra.y, ra.z));
     for (int o = 16; o > 0; o >>= 1) bnda = fmax(bnda, __shfl_xor_sync(0xffffffffu, bnda, o));
+#if EDB_NPC_HOIST & 1
+    {
+      __syncwarp();   // (the previous owner's readers are done)
+      const Obb o = obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha);
+      if (lane == 0) {
+        double* d = s_oa[wid];
+        d[0] = o.c.x; d[1] = o.c.y; d[2] = o.c.z; d[3] = o.e1.x; d[4] = o.e1.y; d[5] = o.e1.z; d[6] = o.e2.x; d[7] = o.e2.y; d[8] = o.e2.z;
+        d[9] = o.e3.x; d[10] = o.e3.y; d[11] = o.e3.z; d[12] = o.ext.x; d[13] = o.ext.y; d[14] = o.ext.z;
+      }
+      __syncwarp();
+    }
+    auto owner_obb = [&]() {
+      const double* d = s_oa[wid];
+      return Obb{mk3(d[0], d[1], d[2]), mk3(d[3], d[4], d[5]), mk3(d[6], d[7], d[8]), mk3(d[9], d[10], d[11]), mk3(d[12], d[13], d[14])};
+    };
+#else
+    auto owner_obb = [&]() { return obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha); };
+#endif
     uint32_t run[4] = {0, 0, 0, 0};
     uint32_t base[4] = {0, 0, 0, 0};
     if (FILL) {
@@ -325,12 +353,18 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
         const uint32_t take = nq < 32 ? nq : 32;
         const uint32_t Lc = lane < take ? qu[lane] : 0;
         bool pass = false;
+#if EDB_NPC_HOIST & 2
+        Obb ojk{};   // this lane's candidate, enlarged once: the prefilter rounds below read it by shuffle
+#endif
         if (lane < take) {
           const double4 rb = s_pr[Lc], qb4 = s_q[Lc];
-          Obb oi = obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha);
+          Obb oi = owner_obb();
           Obb oj = obb_world(A.S.sh[s_type[Lc]].obb, mk3(rb.x, rb.y, rb.z), q4{qb4.x, qb4.y, qb4.z, qb4.w}, s_h[Lc]);
           obb_enlarge(oi, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
           pass = NPC_OBB_INTERSECT(oi, oj);
+#if EDB_NPC_HOIST & 2
+          ojk = oj;
+#endif
         }
         unsigned pm = __ballot_sync(0xffffffffu, pass);
         const uint32_t rest = nq - take;   // < 32: a chunk adds at most 32 and the queue is drained as soon as it holds 32
@@ -353,12 +387,21 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
             const int l = (int)nth_set_bit(pm, (uint32_t)(q < npass ? q : 0));
             const uint32_t Lq = __shfl_sync(0xffffffffu, Lc, l);
             bool ok = false;
+#if EDB_NPC_HOIST & 2
+            auto sh3 = [&](v3 a) { return mk3(__shfl_sync(0xffffffffu, a.x, l), __shfl_sync(0xffffffffu, a.y, l), __shfl_sync(0xffffffffu, a.z, l)); };
+            Obb oj{sh3(ojk.c), sh3(ojk.e1), sh3(ojk.e2), sh3(ojk.e3), sh3(ojk.ext)};   // enlarged once by the lane that tested it
+            if (q < npass && v < sa.nv) {
+              obb_enlarge(oj, 0.5 * rV);
+              ok = NPC_OBB_INTERSECT(oj, obb_point(va[v], rma));
+            }
+#else
             if (q < npass && v < sa.nv) {
               const double4 rb = s_pr[Lq], qb4 = s_q[Lq];
               Obb oj = obb_world(A.S.sh[s_type[Lq]].obb, mk3(rb.x, rb.y, rb.z), q4{qb4.x, qb4.y, qb4.z, qb4.w}, s_h[Lq]);
               obb_enlarge(oj, 0.5 * rV); obb_enlarge(oj, 0.5 * rV);
               ok = NPC_OBB_INTERSECT(oj, obb_point(va[v], rma));
             }
+#endif
             const unsigned m = __ballot_sync(0xffffffffu, ok);
             if (q < npass && v == 0) vmA[q] = SA == 32 ? m : ((m >> (lane & ~(SA - 1))) & ((1u << SA) - 1u));
           }
@@ -370,7 +413,7 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
             if (q < npass) {
               const ShapeDev* __restrict__ psq = A.S.sh + s_type[Lq];
               if (v < psq->nv) {
-                Obb oi = obb_world(psa->obb, mk3(ra.x, ra.y, ra.z), qa, ha);
+                Obb oi = owner_obb();
                 obb_enlarge(oi, 0.5 * rV); obb_enlarge(oi, 0.5 * rV);
                 const SV vq{s_vert + (size_t)Lq * nvmax};
                 ok = NPC_OBB_INTERSECT(oi, obb_point(vq[v], s_h[Lq] * psq->radius));
