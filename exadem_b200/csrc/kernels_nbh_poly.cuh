@@ -39,6 +39,13 @@ namespace edb {
 // vertex-of-b prefilter round used to rebuild it per lane: four quaternion rotations); bit 1: the candidates' world OBBs of an OBB
 // round stay in the registers of the lane that tested them and the vertex-of-a prefilter rounds fetch them by shuffle instead of
 // rebuilding them per lane.  Same values from the same functions on the same inputs: the candidate set is unchanged.
+// EDB_NPC_MERGE: the two vertex-edge groups of a pair (a's vertices on b's edges, b's vertices on a's edges) share one test index
+// space, and so do the two vertex-face groups: both directions go to the same wave and are adjacent there, so the records and their
+// order do not change, but two octahedra need one vertex-face round instead of two (16 + 16 tests) and the kernel holds one inlined
+// copy of each filter instead of two.
+#ifndef EDB_NPC_MERGE
+#define EDB_NPC_MERGE 1
+#endif
 #ifndef EDB_NPC_HOIST
 #define EDB_NPC_HOIST 1
 #endif
@@ -485,6 +492,48 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
           group(0, nA * nvb,
                 [&](uint32_t x) { const uint32_t i = vtxA(x / nvb), j = x % nvb; return filter_vv(rV, va[i], rma, vb[j], rmb); },
                 [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
+#if EDB_NPC_MERGE
+          {
+            // tests [0, nAB) are A -> B, the rest B -> A (swap = 1: pi = b, pj = a; the owner stays a, interaction_pair.hpp:75-90)
+            const uint32_t nAB = nA * neb;
+            group(1, nAB + nB * nea,
+                  [&](uint32_t x) {
+                    const bool fw = x < nAB;
+                    const uint32_t y = fw ? x : x - nAB, nE = fw ? neb : nea, e = y % nE;
+                    const uint32_t v = fw ? vtxA(y / nE) : vtxB(y / nE);
+                    const SV& P = fw ? va : vb;
+                    const SV& Q = fw ? vb : va;
+                    const int* E = fw ? eb : ea;
+                    return NPC_FILTER_VE(rV, P[v], fw ? rma : rmb, Q[E[2 * e]], Q[E[2 * e + 1]], fw ? rmb : rma);
+                  },
+                  [&](uint32_t x, uint32_t k) {
+                    if (x < nAB) write(1, k, a, b, vtxA(x / neb), x % neb, f0);
+                    else write(1, k, b, a, vtxB((x - nAB) / nea), (x - nAB) % nea, f1);
+                  });
+            const uint32_t nAF = nA * nfb;
+            group(2, nAF + nB * nfa,
+                  [&](uint32_t x) {
+                    const bool fw = x < nAF;
+                    const uint32_t y = fw ? x : x - nAF, nF = fw ? nfb : nfa, f = y % nF;
+                    const uint32_t v = fw ? vtxA(y / nF) : vtxB(y / nF);
+                    const SV& P = fw ? va : vb;
+                    const SV& Q = fw ? vb : va;
+                    const int f0s = fw ? sb.f0 : sa.f0, fi0s = fw ? sb.fi0 : sa.fi0;
+                    return NPC_FILTER_VF(rV, P[v], fw ? rma : rmb, Q, fw ? rmb : rma, A.S.fidx + fi0s + A.S.foff[f0s + f], A.S.fn[f0s + f]);
+                  },
+                  [&](uint32_t x, uint32_t k) {
+                    if (x < nAF) write(2, k, a, b, vtxA(x / nfb), x % nfb, f0);
+                    else write(2, k, b, a, vtxB((x - nAF) / nfa), (x - nAF) % nfa, f1);
+                  });
+            group(3, nEA * nEB,
+                  [&](uint32_t x) {
+                    const uint32_t i = edgA(x / nEB), j = edgB(x % nEB);
+                    return NPC_FILTER_EE(rV, va[ea[2 * i]], va[ea[2 * i + 1]], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb);
+                  },
+                  [&](uint32_t x, uint32_t k) { write(3, k, a, b, edgA(x / nEB), edgB(x % nEB), f0); });
+            continue;
+          }
+#endif
           group(1, nA * neb,
                 [&](uint32_t x) { const uint32_t i = vtxA(x / neb), j = x % neb; return NPC_FILTER_VE(rV, va[i], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb); },
                 [&](uint32_t x, uint32_t k) { write(1, k, a, b, vtxA(x / neb), x % neb, f0); });
@@ -576,6 +625,22 @@ __global__ void __launch_bounds__(256) k_nbh_poly_replay(NbhArgs A, CntTab C, WT
     auto vtxA = [&](uint32_t n) { return nth_set_bit(mA, n); };
     auto vtxB = [&](uint32_t n) { return nth_set_bit(mB, n); };
     group(0, nA * nvb, [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
+#if EDB_NPC_MERGE
+    {
+      const uint32_t nAB = nA * neb, nAF = nA * nfb, nEBm = __popc(eB);
+      group(1, nAB + nB * nea, [&](uint32_t x, uint32_t k) {
+        if (x < nAB) write(1, k, a, b, vtxA(x / neb), x % neb, f0);
+        else write(1, k, b, a, vtxB((x - nAB) / nea), (x - nAB) % nea, f1);
+      });
+      group(2, nAF + nB * nfa, [&](uint32_t x, uint32_t k) {
+        if (x < nAF) write(2, k, a, b, vtxA(x / nfb), x % nfb, f0);
+        else write(2, k, b, a, vtxB((x - nAF) / nfa), (x - nAF) % nfa, f1);
+      });
+      group(3, __popc(eA) * nEBm,
+            [&](uint32_t x, uint32_t k) { write(3, k, a, b, nth_set_bit(eA, x / nEBm), nth_set_bit(eB, x % nEBm), f0); });
+      continue;
+    }
+#endif
     group(1, nA * neb, [&](uint32_t x, uint32_t k) { write(1, k, a, b, vtxA(x / neb), x % neb, f0); });
     group(2, nA * nfb, [&](uint32_t x, uint32_t k) { write(2, k, a, b, vtxA(x / nfb), x % nfb, f0); });
     const uint32_t nEB = __popc(eB);
