@@ -55,6 +55,7 @@ struct edb_context {
   int n_regions = 0;
   DevBuf<uint16_t> ptype;            // polyhedra: shape index per slot (reals + ghosts), refreshed with the world vertices
   bool have_backup = false;
+  int shape_nemax = 0;               // largest edge count over the shapes (the cell-block neighbour kernel holds edge sets in 32-bit masks)
   bool have_cells = false;           // cbeg / cend / cidx describe the current particle set (set by the rebuild)
   // ghost table (host-built, static for a given grid)
   uint32_t n_gent = 0;
@@ -823,6 +824,7 @@ extern "C" int edb_set_shapes(edb_context* c, int32_t n, const edb_shape* sh) {
     S.vmax = 0.0;
     for (int k = 0; k < S.nv; k++) S.vmax = std::max(S.vmax, norm(sv[S.v0 + k]));
     nvmax = std::max(nvmax, S.nv);
+    c->shape_nemax = i == 0 ? S.ne : std::max(c->shape_nemax, S.ne);
     c->h_sh.push_back(S);
   }
   c->d_sh.ensure(n + 1); c->d_sv.ensure(sv.size() + 1); c->d_se.ensure(se.size() + 1); c->d_sfoff.ensure(sfoff.size() + 1);
@@ -1533,7 +1535,7 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
   const uint32_t n_real_cells = (uint32_t)G.nc[0] * G.nc[1] * G.nc[2];
   bool drv_waves = false;
   for (int t = 4; t < NT; t++) drv_waves = drv_waves || active[t];
-  if (poly && c->S.nvmax <= 32 && !c->env_nbh_per_thread) {
+  if (poly && c->S.nvmax <= 32 && c->shape_nemax <= 32 && !c->env_nbh_per_thread) {
     CK(cudaMemsetAsync(c->d_flag + 1, 0, 8, c->st));
     LAUNCH(c, k_stencil_max, nblk(n_real_cells), BLK, 0, G, c->cbeg.p, c->cend.p, c->d_flag + 1);
     CK(cudaMemcpyAsync(c->h_flag + 1, c->d_flag + 1, 8, cudaMemcpyDeviceToHost, c->st));

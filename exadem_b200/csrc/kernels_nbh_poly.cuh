@@ -46,6 +46,15 @@ namespace edb {
 #ifndef EDB_NPC_MERGE
 #define EDB_NPC_MERGE 1
 #endif
+// EDB_NPC_VECULL (needs EDB_NPC_MERGE): the vertex-edge tests run over the edges within reach only, like the edge-edge tests.
+// filter_ve accepts (vertex v of a, edge e of b) only if v is within R = ri + rj + rV of the point of e's LINE at a parameter in
+// [-rV, 1 + rV], i.e. within R + rV |e| of the segment; v lies within bnd_a of a's centre, so an edge of b farther than
+// bnd_a + R + rV |e| from a's centre cannot pass against any vertex of a.  Same margin as the edge-edge cull; ascending edge order kept.
+// Parity-green but SLOWER: 17.4 ms per build against 15.8 (profiles/r2_sweep_poly_vecull.log) — the merged group already fits two
+// rounds, and the n-th-set-bit decode of the edge index in every test costs more than the tests it saves.  Off.
+#ifndef EDB_NPC_VECULL
+#define EDB_NPC_VECULL 0
+#endif
 #ifndef EDB_NPC_HOIST
 #define EDB_NPC_HOIST 1
 #endif
@@ -450,18 +459,32 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
           // edge reach masks (see seg_point_d2): lanes [0, ne_a) test a's edges against b's bounding sphere, lanes [16, 16 + ne_b)
           // b's edges against a's; shapes with more than 16 edges keep every edge
           unsigned eA = sa.ne >= 32 ? 0xffffffffu : ((1u << sa.ne) - 1u), eB = sb.ne >= 32 ? 0xffffffffu : ((1u << sb.ne) - 1u);
+          unsigned eAv = eA, eBv = eB;   // the same for the vertex-edge tests (wider reach)
           if (sa.ne <= 16 && sb.ne <= 16) {
             double bndb = 0.0;
             if (lane < sb.nv) bndb = norm(vb[lane] - mk3(rb.x, rb.y, rb.z));
             for (int o = 16; o > 0; o >>= 1) bndb = fmax(bndb, __shfl_xor_sync(0xffffffffu, bndb, o));
             const double Rr = rma + rmb + rV;
-            bool keep = false;
-            if (lane < sa.ne) keep = seg_point_d2(va[ea[2 * lane]], va[ea[2 * lane + 1]], mk3(rb.x, rb.y, rb.z)) <= reach2(bndb, Rr, mk3(rb.x, rb.y, rb.z));
-            else if (lane >= 16 && lane - 16 < sb.ne)
-              keep = seg_point_d2(vb[eb[2 * (lane - 16)]], vb[eb[2 * (lane - 16) + 1]], mk3(ra.x, ra.y, ra.z)) <= reach2(bnda, Rr, mk3(ra.x, ra.y, ra.z));
+            bool keep = false, keepv = false;
+            if (lane < sa.ne) {
+              const v3 p0 = va[ea[2 * lane]], p1 = va[ea[2 * lane + 1]], cb = mk3(rb.x, rb.y, rb.z);
+              const double d2 = seg_point_d2(p0, p1, cb);
+              keep = d2 <= reach2(bndb, Rr, cb);
+              keepv = d2 <= reach2(bndb, Rr + rV * norm(p1 - p0), cb);
+            } else if (lane >= 16 && lane - 16 < sb.ne) {
+              const v3 p0 = vb[eb[2 * (lane - 16)]], p1 = vb[eb[2 * (lane - 16) + 1]], ca = mk3(ra.x, ra.y, ra.z);
+              const double d2 = seg_point_d2(p0, p1, ca);
+              keep = d2 <= reach2(bnda, Rr, ca);
+              keepv = d2 <= reach2(bnda, Rr + rV * norm(p1 - p0), ca);
+            }
             const unsigned km = __ballot_sync(0xffffffffu, keep);
             eA = km & 0xffffu;
             eB = km >> 16;
+#if EDB_NPC_MERGE && EDB_NPC_VECULL
+            const unsigned kv = __ballot_sync(0xffffffffu, keepv);
+            eAv = kv & 0xffffu;
+            eBv = kv >> 16;
+#endif
           }
           // a pair whose prefilters leave no test at all (no vertex of either inside the other's enlarged OBB, no two edges within reach)
           // produces no record: it is neither evaluated nor written to the stream (the replay never hears of it)
@@ -471,6 +494,9 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
           if (!FILL) {   // pair header of the stream
             emit(b); emit((uint32_t)idb); emit((uint32_t)(idb >> 32)); emit((uint32_t)ghost | (s_type[Lb] << 8)); emit(mA); emit(mB);
             emit(eA); emit(eB);
+#if EDB_NPC_MERGE && EDB_NPC_VECULL
+            emit(eAv); emit(eBv);
+#endif
           }
           auto write = [&](int t, uint32_t k, uint32_t i, uint32_t j, uint32_t si, uint32_t sj, uint8_t flg) {
             W.w[t].ij[k] = make_uint2(i, j);
@@ -495,6 +521,25 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
 #if EDB_NPC_MERGE
           {
             // tests [0, nAB) are A -> B, the rest B -> A (swap = 1: pi = b, pj = a; the owner stays a, interaction_pair.hpp:75-90)
+#if EDB_NPC_VECULL
+            const uint32_t nEBv = __popc(eBv), nEAv = __popc(eAv);   // (a's vertices meet b's edges within reach, and the other way round)
+            const uint32_t nAB = nA * nEBv;
+            group(1, nAB + nB * nEAv,
+                  [&](uint32_t x) {
+                    const bool fw = x < nAB;
+                    const uint32_t y = fw ? x : x - nAB, nE = fw ? nEBv : nEAv;
+                    const uint32_t e = nth_set_bit(fw ? eBv : eAv, y % nE);
+                    const uint32_t v = fw ? vtxA(y / nE) : vtxB(y / nE);
+                    const SV& P = fw ? va : vb;
+                    const SV& Q = fw ? vb : va;
+                    const int* E = fw ? eb : ea;
+                    return NPC_FILTER_VE(rV, P[v], fw ? rma : rmb, Q[E[2 * e]], Q[E[2 * e + 1]], fw ? rmb : rma);
+                  },
+                  [&](uint32_t x, uint32_t k) {
+                    if (x < nAB) write(1, k, a, b, vtxA(x / nEBv), nth_set_bit(eBv, x % nEBv), f0);
+                    else write(1, k, b, a, vtxB((x - nAB) / nEAv), nth_set_bit(eAv, (x - nAB) % nEAv), f1);
+                  });
+#else
             const uint32_t nAB = nA * neb;
             group(1, nAB + nB * nea,
                   [&](uint32_t x) {
@@ -510,6 +555,7 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
                     if (x < nAB) write(1, k, a, b, vtxA(x / neb), x % neb, f0);
                     else write(1, k, b, a, vtxB((x - nAB) / nea), (x - nAB) % nea, f1);
                   });
+#endif
             const uint32_t nAF = nA * nfb;
             group(2, nAF + nB * nfa,
                   [&](uint32_t x) {
@@ -602,6 +648,9 @@ __global__ void __launch_bounds__(256) k_nbh_poly_replay(NbhArgs A, CntTab C, WT
     const uint32_t b = rd();
     if (b == NPC_NONE) break;
     const uint32_t idlo = rd(), idhi = rd(), gt = rd(), mA = rd(), mB = rd(), eA = rd(), eB = rd();
+#if EDB_NPC_MERGE && EDB_NPC_VECULL
+    const uint32_t eAv = rd(), eBv = rd();
+#endif
     const unsigned long long idb = ((unsigned long long)idhi << 32) | idlo;
     const uint8_t ghost = (uint8_t)(gt & 0xffu);
     const ShapeDev* __restrict__ psb = A.S.sh + (gt >> 8);
@@ -627,11 +676,20 @@ __global__ void __launch_bounds__(256) k_nbh_poly_replay(NbhArgs A, CntTab C, WT
     group(0, nA * nvb, [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
 #if EDB_NPC_MERGE
     {
-      const uint32_t nAB = nA * neb, nAF = nA * nfb, nEBm = __popc(eB);
+      const uint32_t nAF = nA * nfb, nEBm = __popc(eB);
+#if EDB_NPC_VECULL
+      const uint32_t nEBv = __popc(eBv), nEAv = __popc(eAv), nAB = nA * nEBv;
+      group(1, nAB + nB * nEAv, [&](uint32_t x, uint32_t k) {
+        if (x < nAB) write(1, k, a, b, vtxA(x / nEBv), nth_set_bit(eBv, x % nEBv), f0);
+        else write(1, k, b, a, vtxB((x - nAB) / nEAv), nth_set_bit(eAv, (x - nAB) % nEAv), f1);
+      });
+#else
+      const uint32_t nAB = nA * neb;
       group(1, nAB + nB * nea, [&](uint32_t x, uint32_t k) {
         if (x < nAB) write(1, k, a, b, vtxA(x / neb), x % neb, f0);
         else write(1, k, b, a, vtxB((x - nAB) / nea), (x - nAB) % nea, f1);
       });
+#endif
       group(2, nAF + nB * nfa, [&](uint32_t x, uint32_t k) {
         if (x < nAF) write(2, k, a, b, vtxA(x / nfb), x % nfb, f0);
         else write(2, k, b, a, vtxB((x - nAF) / nfa), (x - nAF) % nfa, f1);
