@@ -1628,6 +1628,9 @@ static void rebuild(edb_context* c, double rcut_inc, int symetric) {
       } else {
         LAUNCH(c, k_nbh_poly_cell<2>, n_real_cells, NPC_THREADS, cell_smem, A, C, W, cell_cap, PL);
       }
+      if (c->trace_async)
+        fprintf(stderr, "[edb trace] poly rebuild %llu: cell_cap %u smem %zu record %d overflow %u need %llu pool %u chunks\n",
+                (unsigned long long)c->ctr.rebuilds, cell_cap, cell_smem, (int)record, overflow, need, c->nbh_pool_chunks);
       // size the pool for the next rebuild (25 % head room)
       const unsigned long long want = need + need / 4 + 1024;
       if (need + need / 16 + 64 > c->nbh_pool_chunks && want * CHW < (1ull << 32)) {   // grow only when the head room is used up
