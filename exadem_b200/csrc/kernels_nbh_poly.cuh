@@ -55,6 +55,16 @@ namespace edb {
 #ifndef EDB_NPC_VECULL
 #define EDB_NPC_VECULL 0
 #endif
+// EDB_NPC_TAB: the kept vertices / edges of a pair (set bits of mA, mB, eA, eB and of the vertex-edge reach masks) are written once
+// per pair into small per-warp tables, ascending, so that a test decodes its vertex or edge with one shared-memory load instead of an
+// n-th-set-bit loop.  EDB_NPC_FDIV: test index -> (row, column) by a float reciprocal (exact for these sizes: indices < 2^10, divisors
+// <= 32, the quotient is at least 1/64 away from the next integer) instead of a 32-bit integer division per test.
+#ifndef EDB_NPC_TAB
+#define EDB_NPC_TAB 1
+#endif
+#ifndef EDB_NPC_FDIV
+#define EDB_NPC_FDIV 1
+#endif
 #ifndef EDB_NPC_HOIST
 #define EDB_NPC_HOIST 1
 #endif
@@ -210,6 +220,9 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
   __shared__ uint32_t s_vmask[NPC_THREADS / 32][2][32];   // vertex-vs-OBB prefilter masks (mA, mB) of the pairs of one OBB round
 #if EDB_NPC_HOIST & 1
   __shared__ double s_oa[NPC_THREADS / 32][16];           // the owner's world OBB (c, e1, e2, e3, ext), not enlarged
+#endif
+#if EDB_NPC_TAB
+  __shared__ uint8_t s_tab[NPC_THREADS / 32][6][32];      // per pair: kept vertices of a, of b, edges of a, of b, V-E edges of a, of b
 #endif
 
   const GridDev& G = A.G;
@@ -509,43 +522,81 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
           // The vertex-vs-OBB prefilter usually keeps 1-3 of the vertices: the test index space is built over the KEPT vertices only
           // (n-th set bit of the mask, ascending, so the emission order is unchanged) and the lanes stay busy.
           const uint32_t nA = __popc(mA), nB = __popc(mB);
+          const uint32_t nEA = __popc(eA), nEB = __popc(eB);
+#if EDB_NPC_TAB
+          {
+            __syncwarp();   // (the previous pair's readers are done)
+            const unsigned below = (1u << lane) - 1u;
+            const unsigned ms[6] = {mA, mB, eA, eB, eAv, eBv};
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+              if ((ms[k] >> lane) & 1u) s_tab[wid][k][__popc(ms[k] & below)] = (uint8_t)lane;
+            __syncwarp();
+          }
+          auto vtxA = [&](uint32_t n) { return (uint32_t)s_tab[wid][0][n]; };
+          auto vtxB = [&](uint32_t n) { return (uint32_t)s_tab[wid][1][n]; };
+          auto edgA = [&](uint32_t n) { return (uint32_t)s_tab[wid][2][n]; };
+          auto edgB = [&](uint32_t n) { return (uint32_t)s_tab[wid][3][n]; };
+          auto edgAv = [&](uint32_t n) { return (uint32_t)s_tab[wid][4][n]; };
+          auto edgBv = [&](uint32_t n) { return (uint32_t)s_tab[wid][5][n]; };
+#else
           auto vtxA = [&](uint32_t n) { return nth_set_bit(mA, n); };
           auto vtxB = [&](uint32_t n) { return nth_set_bit(mB, n); };
-          const uint32_t nEA = __popc(eA), nEB = __popc(eB);
           auto edgA = [&](uint32_t n) { return nth_set_bit(eA, n); };
           auto edgB = [&](uint32_t n) { return nth_set_bit(eB, n); };
+          auto edgAv = [&](uint32_t n) { return nth_set_bit(eAv, n); };
+          auto edgBv = [&](uint32_t n) { return nth_set_bit(eBv, n); };
+#endif
+          (void)edgAv; (void)edgBv;
+          // x -> (x / d, x % d)
+#if EDB_NPC_FDIV
+          auto rcpf = [](uint32_t d) { return 1.0f / (float)(d ? d : 1u); };
+          auto divm = [](uint32_t x, uint32_t d, float rc, uint32_t& q, uint32_t& r) { q = (uint32_t)(((float)x + 0.5f) * rc); r = x - q * d; };
+#else
+          auto rcpf = [](uint32_t) { return 0.0f; };
+          auto divm = [](uint32_t x, uint32_t d, float, uint32_t& q, uint32_t& r) { q = x / d; r = x % d; };
+#endif
           // A -> B (swap = 0): vertices of a against vertices / edges / faces of b
-          group(0, nA * nvb,
-                [&](uint32_t x) { const uint32_t i = vtxA(x / nvb), j = x % nvb; return filter_vv(rV, va[i], rma, vb[j], rmb); },
-                [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
+          {
+            const float rc = rcpf(nvb);
+            group(0, nA * nvb,
+                  [&](uint32_t x) { uint32_t q, j; divm(x, nvb, rc, q, j); return filter_vv(rV, va[vtxA(q)], rma, vb[j], rmb); },
+                  [&](uint32_t x, uint32_t k) { write(0, k, a, b, vtxA(x / nvb), x % nvb, f0); });
+          }
 #if EDB_NPC_MERGE
           {
             // tests [0, nAB) are A -> B, the rest B -> A (swap = 1: pi = b, pj = a; the owner stays a, interaction_pair.hpp:75-90)
 #if EDB_NPC_VECULL
             const uint32_t nEBv = __popc(eBv), nEAv = __popc(eAv);   // (a's vertices meet b's edges within reach, and the other way round)
             const uint32_t nAB = nA * nEBv;
+            const float rcB = rcpf(nEBv), rcA = rcpf(nEAv);
             group(1, nAB + nB * nEAv,
                   [&](uint32_t x) {
                     const bool fw = x < nAB;
                     const uint32_t y = fw ? x : x - nAB, nE = fw ? nEBv : nEAv;
-                    const uint32_t e = nth_set_bit(fw ? eBv : eAv, y % nE);
-                    const uint32_t v = fw ? vtxA(y / nE) : vtxB(y / nE);
+                    uint32_t q, r;
+                    divm(y, nE, fw ? rcB : rcA, q, r);
+                    const uint32_t e = fw ? edgBv(r) : edgAv(r);
+                    const uint32_t v = fw ? vtxA(q) : vtxB(q);
                     const SV& P = fw ? va : vb;
                     const SV& Q = fw ? vb : va;
                     const int* E = fw ? eb : ea;
                     return NPC_FILTER_VE(rV, P[v], fw ? rma : rmb, Q[E[2 * e]], Q[E[2 * e + 1]], fw ? rmb : rma);
                   },
                   [&](uint32_t x, uint32_t k) {
-                    if (x < nAB) write(1, k, a, b, vtxA(x / nEBv), nth_set_bit(eBv, x % nEBv), f0);
-                    else write(1, k, b, a, vtxB((x - nAB) / nEAv), nth_set_bit(eAv, (x - nAB) % nEAv), f1);
+                    if (x < nAB) write(1, k, a, b, vtxA(x / nEBv), edgBv(x % nEBv), f0);
+                    else write(1, k, b, a, vtxB((x - nAB) / nEAv), edgAv((x - nAB) % nEAv), f1);
                   });
 #else
             const uint32_t nAB = nA * neb;
+            const float rcB = rcpf(neb), rcA = rcpf(nea);
             group(1, nAB + nB * nea,
                   [&](uint32_t x) {
                     const bool fw = x < nAB;
-                    const uint32_t y = fw ? x : x - nAB, nE = fw ? neb : nea, e = y % nE;
-                    const uint32_t v = fw ? vtxA(y / nE) : vtxB(y / nE);
+                    const uint32_t y = fw ? x : x - nAB, nE = fw ? neb : nea;
+                    uint32_t q, e;
+                    divm(y, nE, fw ? rcB : rcA, q, e);
+                    const uint32_t v = fw ? vtxA(q) : vtxB(q);
                     const SV& P = fw ? va : vb;
                     const SV& Q = fw ? vb : va;
                     const int* E = fw ? eb : ea;
@@ -557,11 +608,14 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
                   });
 #endif
             const uint32_t nAF = nA * nfb;
+            const float rfB = rcpf(nfb), rfA = rcpf(nfa);
             group(2, nAF + nB * nfa,
                   [&](uint32_t x) {
                     const bool fw = x < nAF;
-                    const uint32_t y = fw ? x : x - nAF, nF = fw ? nfb : nfa, f = y % nF;
-                    const uint32_t v = fw ? vtxA(y / nF) : vtxB(y / nF);
+                    const uint32_t y = fw ? x : x - nAF, nF = fw ? nfb : nfa;
+                    uint32_t q, f;
+                    divm(y, nF, fw ? rfB : rfA, q, f);
+                    const uint32_t v = fw ? vtxA(q) : vtxB(q);
                     const SV& P = fw ? va : vb;
                     const SV& Q = fw ? vb : va;
                     const int f0s = fw ? sb.f0 : sa.f0, fi0s = fw ? sb.fi0 : sa.fi0;
@@ -571,9 +625,12 @@ __global__ void __launch_bounds__(NPC_THREADS, EDB_NPC_MINB) k_nbh_poly_cell(Nbh
                     if (x < nAF) write(2, k, a, b, vtxA(x / nfb), x % nfb, f0);
                     else write(2, k, b, a, vtxB((x - nAF) / nfa), (x - nAF) % nfa, f1);
                   });
+            const float rce = rcpf(nEB);
             group(3, nEA * nEB,
                   [&](uint32_t x) {
-                    const uint32_t i = edgA(x / nEB), j = edgB(x % nEB);
+                    uint32_t q, r;
+                    divm(x, nEB, rce, q, r);
+                    const uint32_t i = edgA(q), j = edgB(r);
                     return NPC_FILTER_EE(rV, va[ea[2 * i]], va[ea[2 * i + 1]], rma, vb[eb[2 * j]], vb[eb[2 * j + 1]], rmb);
                   },
                   [&](uint32_t x, uint32_t k) { write(3, k, a, b, edgA(x / nEB), edgB(x % nEB), f0); });
